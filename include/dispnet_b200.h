@@ -1,0 +1,227 @@
+/*
+ * dispnet_b200.h -- C ABI of libdispnet_b200.so (sm_100a).
+ *
+ * Drop-in boundary for the data-parallel training hot path of zenithfang/supervised_dispnet:
+ * the library kernels that the reference reaches through PyTorch (ATen/cuDNN) from
+ *   models/Disp_vgg_BN.py:136-191, models/DispNetS.py:93-140, models/PoseExpNet.py:58-95,
+ *   models/Disp_res_50.py:139-198            (conv / convT / BN / pool / act / cat / upsample)
+ *   loss_functions.py:104-129, :317-386, :401-448 and inverse_warp.py:160-193  (per-pixel losses)
+ * are replaced one-for-one by the entry points below.  Plain pointers and sizes only; no torch types.
+ *
+ * Conventions
+ *   - every function is stream-ordered on `stream` (a cudaStream_t passed as void*), allocates
+ *     nothing, keeps no global state (except cached function attributes) and is re-entrant;
+ *   - return value: 0 = ok, >0 = cudaError_t of the launch, <0 = DN_E_* argument error;
+ *   - activations live in HBM as NHWC "views": channel stride 1, arbitrary element strides for
+ *     N/H/W so that concat slices, 2x2 phase sub-lattices and crops are views, not copies;
+ *   - dtype codes: DN_F32 = 0, DN_F16 = 1, DN_BF16 = 2.
+ */
+#ifndef DISPNET_B200_H
+#define DISPNET_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DN_F32 0
+#define DN_F16 1
+#define DN_BF16 2
+
+#define DN_ACT_NONE 0
+#define DN_ACT_RELU 1
+#define DN_ACT_LRELU 2 /* LeakyReLU(0.1): models/Disp_vgg_BN.py:40-45 */
+
+#define DN_E_ARG (-1)
+#define DN_E_UNSUPPORTED (-2)
+
+#define DN_MAX_TAPS 49
+#define DN_MAX_SRC 4
+
+/* NHWC view of an activation tensor (strides in ELEMENTS of `dtype`; channel stride is 1). */
+typedef struct dn_view {
+  void* ptr;
+  int32_t dtype;
+  int32_t N, H, W, C;
+  int64_t sN, sH, sW;
+} dn_view;
+
+/* One filter tap of a gather-convolution: reads source view `src` at (ho*stride+dh, wo*stride+dw)
+ * and multiplies by packed weight matrix number `wt`. */
+typedef struct dn_tap {
+  int32_t src, dh, dw, wt;
+} dn_tap;
+
+/*
+ * Gather-convolution ("implicit GEMM") problem:
+ *   out[n,ho,wo,co] = act( bias[co] + sum_t sum_ci in[t.src][n, ho*stride+t.dh, wo*stride+t.dw, ci]
+ *                                                * w[t.wt][co][ci] )  (+ out if accumulate)
+ * with zero contribution outside a source view.  nn.Conv2d forward, each 2x2 output phase of
+ * nn.ConvTranspose2d forward, and the data-gradients of both are instances.
+ * `w` is packed [ntaps_w][Cout_pad][Cin_pad] (Cin contiguous) in dtype `w_dtype` by dn_pack_weight.
+ */
+typedef struct dn_igemm {
+  dn_view in[DN_MAX_SRC];
+  int32_t nsrc;
+  dn_view out;
+  const void* w;
+  int32_t w_dtype;
+  int32_t cin_pad, cout_pad; /* packed weight matrix dims (multiples of 8) */
+  const float* bias;         /* [Cout] fp32 or NULL */
+  int32_t act;               /* DN_ACT_* applied after bias */
+  int32_t accumulate;        /* 1: out += result (act must be NONE) */
+  int32_t stride;            /* input stride of the gather (1 or 2) */
+  int32_t ntaps;
+  dn_tap taps[DN_MAX_TAPS];
+  float out_scale;           /* result multiplied by this before bias/act (1.0 normally) */
+} dn_igemm;
+
+/*
+ * Weight-gradient problem:
+ *   dw[t.wt][cp][cq] (+)= scale * sum_{n,h,w} p[t.src][n,h,w,cp] * q[n, h*stride+t.dh, w*stride+t.dw, cq]
+ * p = output-gradient view(s) (one per phase), q = saved input activation.  dw is fp32
+ * [ntaps_w][cp_pad][cq_pad] and must be zeroed by the caller (split-K partial sums are added atomically).
+ */
+typedef struct dn_wgrad {
+  dn_view p[DN_MAX_SRC];
+  int32_t nsrc;
+  dn_view q;
+  float* dw;
+  int32_t cp_pad, cq_pad;
+  int32_t stride;
+  int32_t ntaps;
+  dn_tap taps[DN_MAX_TAPS];
+  float scale;
+} dn_wgrad;
+
+/* ---- library ------------------------------------------------------------------------------ */
+int dn_version(void);
+const char* dn_error_string(int code);
+/* 1 when the running device is sm_100 and the tcgen05 path can be used. */
+int dn_tc_available(void);
+
+/* ---- layout / packing (replaces ATen copies: torch.cat, .contiguous(), weight re-layout) ---- */
+/* NCHW fp32 [N,C,H,W] -> channels [c0, c0+C) of NHWC view `dst` (channels >= c0+C left untouched). */
+int dn_pack_input(const float* src, int N, int C, int H, int W, const dn_view* dst, int c0, void* stream);
+/* dst[t][r][c] = src[r*s_r + c*s_c + kh[t]*s_kh + kw[t]*s_kw] for r<R, c<Cc, else 0.
+ * dst is [T][R_pad][C_pad] of dtype `dst_dtype`; src is the fp32 torch parameter. */
+int dn_pack_weight(const float* src, void* dst, int dst_dtype, int T, int R, int Cc, int R_pad, int C_pad,
+                   const int32_t* kh, const int32_t* kw, int64_t s_r, int64_t s_c, int64_t s_kh, int64_t s_kw,
+                   void* stream);
+/* inverse of dn_pack_weight for fp32 gradients: dst[r*s_r + c*s_c + kh[t]*s_kh + kw[t]*s_kw] = scale*src[t][r][c] */
+int dn_unpack_wgrad(const float* src, float* dst, int T, int R, int Cc, int R_pad, int C_pad,
+                    const int32_t* kh, const int32_t* kw, int64_t s_r, int64_t s_c, int64_t s_kh, int64_t s_kw,
+                    float scale, void* stream);
+
+/* ---- convolutions (nn.Conv2d / nn.ConvTranspose2d fwd, dgrad, wgrad) ------------------------- */
+/* backend: 0 = CUDA-core tiled kernel (any shape/dtype), 1 = tcgen05/TMA kernel (fp16/bf16, stride 1). */
+int dn_igemm_run(const dn_igemm* p, int backend, void* stream);
+int dn_wgrad_run(const dn_wgrad* p, int backend, void* stream);
+/* returns 1 if the tcgen05 backend accepts this problem */
+int dn_igemm_tc_supported(const dn_igemm* p);
+int dn_wgrad_tc_supported(const dn_wgrad* p);
+
+/* ---- BatchNorm2d (training) + ReLU + MaxPool2d(2,2)  (models/Disp_vgg_BN.py:137-141) ---------- */
+/* sums[2*C] (double) += per-channel sum and sum of squares of y; caller zeroes sums. */
+int dn_bn_stats(const dn_view* y, double* sums, void* stream);
+/* mean/invstd from sums; running stats update (momentum, unbiased var); scale_shift[2C] = (g*invstd, b-mean*g*invstd).
+ * count = N*H*W.  If training == 0 uses running stats instead. */
+int dn_bn_finalize(const double* sums, double count, const float* gamma, const float* beta, float* running_mean,
+                   float* running_var, float momentum, float eps, int training, int update_running,
+                   float* mean_invstd, float* scale_shift, int C, void* stream);
+/* out = pool?( act( y*scale+shift (+ residual) ) );  pool in {0,1}: 1 = 2x2/2 max pool (out is H/2 x W/2). */
+int dn_bn_apply(const dn_view* y, const float* scale_shift, const dn_view* residual, int act, int pool,
+                const dn_view* out, void* stream);
+/* backward: pass 1 accumulates red[2C] (double): sum(dyhat), sum(dyhat*xhat), where dyhat is the gradient
+ * routed back through pool/act; pass 2 writes dy (and dres if residual). */
+int dn_bn_bwd_reduce(const dn_view* dout, const dn_view* y, const dn_view* residual, const float* mean_invstd,
+                     const float* gamma, const float* beta, int act, int pool, double* red, void* stream);
+int dn_bn_bwd_apply(const dn_view* dout, const dn_view* y, const dn_view* residual, const float* mean_invstd,
+                    const float* gamma, const float* beta, int act, int pool, const double* red, double count,
+                    float gscale, float* dgamma, float* dbeta, const dn_view* dy, const dn_view* dres,
+                    int dres_accumulate, void* stream);
+
+/* ---- pointwise / pooling ------------------------------------------------------------------ */
+/* dy = dout * act'(out) in place on `dout`; dbias[c] = gscale * sum(dy) (fp32, overwritten) if dbias != NULL */
+int dn_act_bwd(const dn_view* dout, const dn_view* out, int act, float* dbias, float gscale, void* stream);
+int dn_maxpool_fwd(const dn_view* x, const dn_view* out, int k, int stride, int pad, void* stream);
+int dn_maxpool_bwd(const dn_view* dout, const dn_view* x, const dn_view* dx, int k, int stride, int pad,
+                   int accumulate, void* stream);
+/* out = act(a + b); bwd: d = dout*act'(out) added (accumulate flags) to da and db */
+int dn_add_act_fwd(const dn_view* a, const dn_view* b, int act, const dn_view* out, void* stream);
+int dn_add_act_bwd(const dn_view* dout, const dn_view* out, int act, const dn_view* da, int da_acc,
+                   const dn_view* db, int db_acc, void* stream);
+/* out (same shape) = act(x)  and its backward (not in place) */
+int dn_act_fwd(const dn_view* x, int act, const dn_view* out, void* stream);
+int dn_copy_view(const dn_view* src, const dn_view* dst, int accumulate, void* stream);
+
+/* ---- disparity heads (alpha*sigmoid(conv)+beta, models/Disp_vgg_BN.py:168) -------------------- */
+/* z: 1-channel conv output view; disp: fp32 [N,1,H,W]; optional `up` = 1-channel view of size (upH,upW) that
+ * receives the x2-upsampled disparity (mode 0 nearest, 1 bilinear align_corners=False), cropped to the view. */
+int dn_head_fwd(const dn_view* z, float alpha, float beta, float* disp, const dn_view* up, int up_mode,
+                void* stream);
+/* dz = (gscale*gdisp + upsample^T(dup)) * alpha*s*(1-s), s = sigmoid(z) recomputed from the saved conv output.
+ * gdisp (fp32, from autograd, may be NULL) is unscaled; dup already carries the gradient scale. */
+int dn_head_bwd(const float* gdisp, const dn_view* dup, int up_mode, const dn_view* z, float alpha, float gscale,
+                const dn_view* dz, void* stream);
+/* sigmoid mask heads of PoseExpNet (models/PoseExpNet.py:82-85): mask fp32 NCHW [N,C,H,W] = sigmoid(z) */
+int dn_sigmoid_nchw_fwd(const dn_view* z, float* out, void* stream);
+int dn_sigmoid_nchw_bwd(const float* gout, const float* out, float gscale, const dn_view* dz, void* stream);
+/* pose = scale * mean_{h,w} z  -> fp32 [N,C]  (models/PoseExpNet.py:71-73) */
+int dn_spatial_mean_fwd(const dn_view* z, float scale, float* out, void* stream);
+int dn_spatial_mean_bwd(const float* gout, float scale, const dn_view* dz, void* stream);
+
+/* ---- per-pixel losses ------------------------------------------------------------------------ */
+/* l1_loss (loss_functions.py:104-129): pred/gt fp32 [B,H,W] (pred row-stride = W).  ws: [2B] floats
+ * (per-sample sum, count).  loss[0] = sum_b (sum_b/count_b) / B  (NaN when a sample has no valid pixel). */
+int dn_l1_fwd(const float* gt, const float* pred, int B, int HW, float max_depth, float* ws, float* loss,
+              void* stream);
+int dn_l1_bwd(const float* gt, const float* pred, int B, int HW, float max_depth, const float* ws,
+              const float* gout, float* gpred, void* stream);
+/* smooth_loss (loss_functions.py:367-386) for one scale: loss[0] += weight * (4 abs-means).  p fp32 [B,H,W]. */
+int dn_smooth_fwd(const float* p, int B, int H, int W, float weight, float* loss, void* stream);
+int dn_smooth_bwd(const float* p, int B, int H, int W, float weight, const float* gout, float* gp, void* stream);
+/* compute_errors (loss_functions.py:401-448): counters[B][4] int32 = n_valid, n<1.25, n<1.25^2, n<1.25^3;
+ * sums[B][5] double = sum|d|, sum|d|/gt, sum d^2/gt, sum d^2, sum (ln gt - ln p)^2.  Caller zeroes both.
+ * crop window [y1,y2)x[x1,x2) (whole image when crop==0).  scale[b] (optional) multiplies pred (median scaling). */
+int dn_depth_errors(const float* gt, const float* pred, int B, int H, int W, float max_depth, int crop, int y1,
+                    int y2, int x1, int x2, const float* scale, int32_t* counters, double* sums, void* stream);
+/* F.interpolate(mode='area') by integer factor f (loss_functions.py:326-327): NCHW fp32 */
+int dn_area_down(const float* src, int NC, int H, int W, int f, float* dst, void* stream);
+/*
+ * Fused inverse warp + photometric term for one (scale, ref) pair (inverse_warp.py:160-193,
+ * loss_functions.py:331-342):  tgt/ref fp32 [B,3,h,w]; depth fp32 [B,h,w]; pose [B,6] with batch stride
+ * pose_stride; K, Kinv [B,3,3] already scaled for this pyramid level; mask [B,h,w] with batch stride or NULL.
+ * rot_mode 0 euler / 1 quat; pad_mode 0 zeros / 1 border; align_corners 0/1.
+ * fwd: loss[0] += sum|diff| / (B*3*h*w); nanflag[0] |= 1 if any diff is NaN; optionally writes `warped`.
+ * bwd: gdepth [B,h,w] (overwritten), gpose [B,6] (+=, batch stride pose_stride), gmask [B,h,w] (overwritten).
+ */
+int dn_warp_photo_fwd(const float* tgt, const float* ref, const float* depth, const float* pose, int pose_stride,
+                      const float* K, const float* Kinv, const float* mask, int64_t mask_bstride, int B, int h,
+                      int w, int rot_mode, int pad_mode, int align_corners, float* warped, float* loss,
+                      int32_t* nanflag, void* stream);
+int dn_warp_photo_bwd(const float* tgt, const float* ref, const float* depth, const float* pose, int pose_stride,
+                      const float* K, const float* Kinv, const float* mask, int64_t mask_bstride, int B, int h,
+                      int w, int rot_mode, int pad_mode, int align_corners, const float* gout, float* gdepth,
+                      float* gpose, float* gmask, int64_t gmask_bstride, float* ws /* [12*B] scratch */, void* stream);
+/* plain inverse_warp forward/backward on its own (inverse_warp.py:160-193): out [B,C,h,w]. */
+int dn_inverse_warp_fwd(const float* img, const float* depth, const float* pose, const float* K, const float* Kinv,
+                        int B, int C, int h, int w, int rot_mode, int pad_mode, int align_corners, float* out,
+                        void* stream);
+int dn_inverse_warp_bwd(const float* img, const float* depth, const float* pose, const float* K, const float* Kinv,
+                        int B, int C, int h, int w, int rot_mode, int pad_mode, int align_corners, const float* gout,
+                        float* gimg /* += or NULL */, float* gdepth, float* gpose /* += or NULL */,
+                        float* ws /* [12*B] scratch */, void* stream);
+/* explainability_loss (loss_functions.py:357-364): loss[0] += -mean(max(log m, -100)) */
+int dn_explain_fwd(const float* mask, int64_t n, float* loss, void* stream);
+int dn_explain_bwd(const float* mask, int64_t n, const float* gout, float* gmask, void* stream);
+
+/* ---- misc ---------------------------------------------------------------------------------- */
+int dn_fill_f32(float* p, int64_t n, float v, void* stream);
+int dn_axpy_f32(const float* x, float a, float* y, int64_t n, void* stream); /* y += a*x */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DISPNET_B200_H */

@@ -1,0 +1,1203 @@
+// Layer kernels of the DispNet-family encoder/decoder stacks: packing, the CUDA-core gather-convolution
+// (backend 0 of dn_igemm_run / dn_wgrad_run: any shape, stride, dtype), BatchNorm(+ReLU+MaxPool2) training
+// forward/backward, pooling, pointwise and the disparity heads.  All HBM-bound kernels walk NHWC views with
+// 16-byte channel vectors when the view allows it and size their grids in multiples of the SM count.
+//
+// Reference semantics restated: nn.Conv2d / nn.ConvTranspose2d (cross-correlation,
+// zero padding), nn.BatchNorm2d training statistics (biased var to normalise, unbiased to running_var,
+// momentum .1, eps 1e-5), MaxPool2d first-max tie rule, LeakyReLU(0.1), alpha*sigmoid+beta heads.
+#include "dn_common.cuh"
+
+// =================================================================================================
+// packing
+// =================================================================================================
+__global__ void pack_input_kernel(const float* __restrict__ src, int N, int C, int H, int W, dn_view dst, int c0) {
+  long long total = (long long)N * H * W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int w = (int)(i % W);
+    long long r = i / W;
+    int h = (int)(r % H);
+    int n = (int)(r / H);
+    long long o = dn_off(dst, n, h, w) + c0;
+    for (int c = 0; c < C; ++c) dn_st(dst.ptr, dst.dtype, o + c, src[(((long long)n * C + c) * H + h) * W + w]);
+  }
+}
+
+DN_EXPORT int dn_pack_input(const float* src, int N, int C, int H, int W, const dn_view* dst, int c0, void* stream) {
+  if (!src || !dst || dst->N != N || dst->H != H || dst->W != W || c0 + C > dst->C) return DN_E_ARG;
+  long long total = (long long)N * H * W;
+  int blocks = (int)((total + 255) / 256);
+  int cap = dn_num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  pack_input_kernel<<<blocks, 256, 0, dn_stream(stream)>>>(src, N, C, H, W, *dst, c0);
+  DN_CHECK_LAUNCH();
+  return 0;
+}
+
+struct TapList {
+  int32_t kh[DN_MAX_TAPS];
+  int32_t kw[DN_MAX_TAPS];
+};
+
+__global__ void pack_weight_kernel(const float* __restrict__ src, void* dst, int dt, int T, int R, int Cc, int R_pad,
+                                   int C_pad, TapList taps, long long s_r, long long s_c, long long s_kh, long long s_kw) {
+  long long total = (long long)T * R_pad * C_pad;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % C_pad);
+    long long q = i / C_pad;
+    int r = (int)(q % R_pad);
+    int t = (int)(q / R_pad);
+    float v = 0.f;
+    if (r < R && c < Cc) v = src[r * s_r + c * s_c + taps.kh[t] * s_kh + taps.kw[t] * s_kw];
+    dn_st(dst, dt, i, v);
+  }
+}
+
+DN_EXPORT int dn_pack_weight(const float* src, void* dst, int dst_dtype, int T, int R, int Cc, int R_pad, int C_pad,
+                             const int32_t* kh, const int32_t* kw, int64_t s_r, int64_t s_c, int64_t s_kh, int64_t s_kw,
+                             void* stream) {
+  if (T < 1 || T > DN_MAX_TAPS || R_pad < R || C_pad < Cc) return DN_E_ARG;
+  TapList tl;
+  for (int i = 0; i < T; ++i) { tl.kh[i] = kh[i]; tl.kw[i] = kw[i]; }
+  long long total = (long long)T * R_pad * C_pad;
+  int blocks = (int)((total + 255) / 256);
+  int cap = dn_num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  pack_weight_kernel<<<blocks, 256, 0, dn_stream(stream)>>>(src, dst, dst_dtype, T, R, Cc, R_pad, C_pad, tl, s_r, s_c, s_kh, s_kw);
+  DN_CHECK_LAUNCH();
+  return 0;
+}
+
+__global__ void unpack_wgrad_kernel(const float* __restrict__ src, float* __restrict__ dst, int T, int R, int Cc, int R_pad,
+                                    int C_pad, TapList taps, long long s_r, long long s_c, long long s_kh, long long s_kw,
+                                    float scale) {
+  long long total = (long long)T * R * Cc;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % Cc);
+    long long q = i / Cc;
+    int r = (int)(q % R);
+    int t = (int)(q / R);
+    dst[r * s_r + c * s_c + taps.kh[t] * s_kh + taps.kw[t] * s_kw] = scale * src[((long long)t * R_pad + r) * C_pad + c];
+  }
+}
+
+DN_EXPORT int dn_unpack_wgrad(const float* src, float* dst, int T, int R, int Cc, int R_pad, int C_pad, const int32_t* kh,
+                              const int32_t* kw, int64_t s_r, int64_t s_c, int64_t s_kh, int64_t s_kw, float scale,
+                              void* stream) {
+  if (T < 1 || T > DN_MAX_TAPS) return DN_E_ARG;
+  TapList tl;
+  for (int i = 0; i < T; ++i) { tl.kh[i] = kh[i]; tl.kw[i] = kw[i]; }
+  long long total = (long long)T * R * Cc;
+  int blocks = (int)((total + 255) / 256);
+  int cap = dn_num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  unpack_wgrad_kernel<<<blocks, 256, 0, dn_stream(stream)>>>(src, dst, T, R, Cc, R_pad, C_pad, tl, s_r, s_c, s_kh, s_kw, scale);
+  DN_CHECK_LAUNCH();
+  return 0;
+}
+
+// =================================================================================================
+// CUDA-core gather-convolution (backend 0): 256 threads, BMxBN output tile, 4x4 per thread, K chunks of 16
+// =================================================================================================
+template <int BM, int BN>
+__global__ void __launch_bounds__(256) igemm_generic_kernel(const __grid_constant__ dn_igemm p) {
+  constexpr int BK = 16;
+  constexpr int TXN = BN / 4;
+  static_assert((BM / 4) * (BN / 4) == 256, "tile/threads mismatch");
+  __shared__ float As[BK][BM + 4];
+  __shared__ float Bs[BK][BN + 4];
+  __shared__ int rn[BM], rh[BM], rw[BM];
+  const int tid = threadIdx.x;
+  const long long M = (long long)p.out.N * p.out.H * p.out.W;
+  const long long m0 = (long long)blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+  for (int r = tid; r < BM; r += 256) {
+    long long m = m0 + r;
+    if (m < M) {
+      int wo = (int)(m % p.out.W);
+      long long q = m / p.out.W;
+      rw[r] = wo; rh[r] = (int)(q % p.out.H); rn[r] = (int)(q / p.out.H);
+    } else { rn[r] = -1; rh[r] = 0; rw[r] = 0; }
+  }
+  __syncthreads();
+  const int ty = tid / TXN, tx = tid % TXN;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int t = 0; t < p.ntaps; ++t) {
+    const dn_tap tap = p.taps[t];
+    const dn_view& src = p.in[tap.src];
+    const int Cin = src.C;
+    const long long wbase = (long long)tap.wt * p.cout_pad * p.cin_pad;
+    for (int c0 = 0; c0 < Cin; c0 += BK) {
+      for (int i = tid; i < BM * BK; i += 256) {
+        int r = i / BK, k = i % BK;
+        float v = 0.f;
+        int n = rn[r];
+        int ci = c0 + k;
+        if (n >= 0 && ci < Cin) {
+          int hi = rh[r] * p.stride + tap.dh, wi = rw[r] * p.stride + tap.dw;
+          if (hi >= 0 && hi < src.H && wi >= 0 && wi < src.W) v = dn_ld(src.ptr, src.dtype, dn_off(src, n, hi, wi) + ci);
+        }
+        As[k][r] = v;
+      }
+      for (int i = tid; i < BN * BK; i += 256) {
+        int c = i / BK, k = i % BK;
+        int co = n0 + c, ci = c0 + k;
+        float v = 0.f;
+        if (co < p.cout_pad && ci < p.cin_pad) v = dn_ld(p.w, p.w_dtype, wbase + (long long)co * p.cin_pad + ci);
+        Bs[k][c] = v;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < BK; ++k) {
+        float a[4], b[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[i] = As[k][ty * 4 + i];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) b[j] = Bs[k][tx * 4 + j];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+      }
+      __syncthreads();
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int r = ty * 4 + i;
+    int n = rn[r];
+    if (n < 0) continue;
+    long long o = dn_off(p.out, n, rh[r], rw[r]);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int co = n0 + tx * 4 + j;
+      if (co >= p.out.C) continue;
+      float v = acc[i][j] * p.out_scale;
+      if (p.bias) v += p.bias[co];
+      v = dn_act(v, p.act);
+      if (p.accumulate) v += dn_ld(p.out.ptr, p.out.dtype, o + co);
+      dn_st(p.out.ptr, p.out.dtype, o + co, v);
+    }
+  }
+}
+
+static int igemm_check(const dn_igemm* p) {
+  if (!p || p->nsrc < 1 || p->nsrc > DN_MAX_SRC || p->ntaps < 1 || p->ntaps > DN_MAX_TAPS) return DN_E_ARG;
+  if (p->stride < 1 || !p->w || !p->out.ptr) return DN_E_ARG;
+  if (p->accumulate && p->act != DN_ACT_NONE) return DN_E_ARG;
+  for (int t = 0; t < p->ntaps; ++t)
+    if (p->taps[t].src < 0 || p->taps[t].src >= p->nsrc) return DN_E_ARG;
+  for (int s = 0; s < p->nsrc; ++s)
+    if (!p->in[s].ptr || p->in[s].C > p->cin_pad || p->in[s].N != p->out.N) return DN_E_ARG;
+  if (p->out.C > p->cout_pad) return DN_E_ARG;
+  return 0;
+}
+
+int dn_igemm_generic(const dn_igemm* p, cudaStream_t st) {
+  long long M = (long long)p->out.N * p->out.H * p->out.W;
+  if (M == 0) return 0;
+  if (p->out.C <= 16) {
+    dim3 grid((unsigned)((M + 255) / 256), (unsigned)((p->out.C + 15) / 16));
+    igemm_generic_kernel<256, 16><<<grid, 256, 0, st>>>(*p);
+  } else {
+    dim3 grid((unsigned)((M + 63) / 64), (unsigned)((p->out.C + 63) / 64));
+    igemm_generic_kernel<64, 64><<<grid, 256, 0, st>>>(*p);
+  }
+  DN_CHECK_LAUNCH();
+  return 0;
+}
+
+// weight gradient on CUDA cores: one 64x64 (cp x cq) tile per block per tap per pixel split
+__global__ void __launch_bounds__(256) wgrad_generic_kernel(const __grid_constant__ dn_wgrad p, int splits, long long chunk) {
+  constexpr int BK = 16;
+  __shared__ float As[BK][64 + 4];
+  __shared__ float Bs[BK][64 + 4];
+  __shared__ long long offP[BK], offQ[BK];
+  const int tid = threadIdx.x;
+  const int t = blockIdx.z / splits, split = blockIdx.z % splits;
+  const dn_tap tap = p.taps[t];
+  const dn_view& P = p.p[tap.src];
+  const dn_view& Q = p.q;
+  const long long M = (long long)P.N * P.H * P.W;
+  const long long mbeg = split * chunk;
+  long long mend = mbeg + chunk;
+  if (mend > M) mend = M;
+  const int cp0 = blockIdx.x * 64, cq0 = blockIdx.y * 64;
+  const int ty = tid / 16, tx = tid % 16;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (long long m0 = mbeg; m0 < mend; m0 += BK) {
+    if (tid < BK) {
+      long long m = m0 + tid;
+      long long op = -1, oq = -1;
+      if (m < mend) {
+        int w = (int)(m % P.W);
+        long long q = m / P.W;
+        int h = (int)(q % P.H), n = (int)(q / P.H);
+        op = dn_off(P, n, h, w);
+        int hi = h * p.stride + tap.dh, wi = w * p.stride + tap.dw;
+        if (hi >= 0 && hi < Q.H && wi >= 0 && wi < Q.W) oq = dn_off(Q, n, hi, wi);
+      }
+      offP[tid] = op; offQ[tid] = oq;
+    }
+    __syncthreads();
+    for (int i = tid; i < BK * 64; i += 256) {
+      int k = i / 64, c = i % 64;
+      float a = 0.f, b = 0.f;
+      if (offP[k] >= 0 && offQ[k] >= 0) {
+        if (cp0 + c < P.C) a = dn_ld(P.ptr, P.dtype, offP[k] + cp0 + c);
+        if (cq0 + c < Q.C) b = dn_ld(Q.ptr, Q.dtype, offQ[k] + cq0 + c);
+      }
+      As[k][c] = a; Bs[k][c] = b;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[k][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[k][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  float* dw = p.dw + (long long)tap.wt * p.cp_pad * p.cq_pad;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int cp = cp0 + ty * 4 + i;
+    if (cp >= P.C) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int cq = cq0 + tx * 4 + j;
+      if (cq >= Q.C) continue;
+      atomicAdd(dw + (long long)cp * p.cq_pad + cq, acc[i][j] * p.scale);
+    }
+  }
+}
+
+int dn_wgrad_generic(const dn_wgrad* p, cudaStream_t st) {
+  const dn_view& P = p->p[0];
+  long long M = (long long)P.N * P.H * P.W;
+  if (M == 0) return 0;
+  int tiles = ((P.C + 63) / 64) * ((p->q.C + 63) / 64) * p->ntaps;
+  int target = dn_num_sms() * 4;
+  int splits = (target + tiles - 1) / tiles;
+  long long maxsplits = (M + 255) / 256;
+  if (splits > maxsplits) splits = (int)maxsplits;
+  if (splits < 1) splits = 1;
+  while ((long long)splits * p->ntaps > 65535) splits = (splits + 1) / 2;
+  long long chunk = (M + splits - 1) / splits;
+  chunk = (chunk + 15) / 16 * 16;
+  dim3 grid((P.C + 63) / 64, (p->q.C + 63) / 64, p->ntaps * splits);
+  wgrad_generic_kernel<<<grid, 256, 0, st>>>(*p, splits, chunk);
+  DN_CHECK_LAUNCH();
+  return 0;
+}
+
+static int wgrad_check(const dn_wgrad* p) {
+  if (!p || p->nsrc < 1 || p->nsrc > DN_MAX_SRC || p->ntaps < 1 || p->ntaps > DN_MAX_TAPS || !p->dw || !p->q.ptr) return DN_E_ARG;
+  for (int s = 0; s < p->nsrc; ++s) {
+    if (!p->p[s].ptr || p->p[s].C > p->cp_pad) return DN_E_ARG;
+    if (p->p[s].N != p->p[0].N || p->p[s].H != p->p[0].H || p->p[s].W != p->p[0].W || p->p[s].C != p->p[0].C) return DN_E_ARG;
+  }
+  if (p->q.C > p->cq_pad || p->q.N != p->p[0].N) return DN_E_ARG;
+  for (int t = 0; t < p->ntaps; ++t)
+    if (p->taps[t].src < 0 || p->taps[t].src >= p->nsrc) return DN_E_ARG;
+  return 0;
+}
+
+int dn_igemm_tc(const dn_igemm* p, cudaStream_t st);   // dn_tc.cu
+int dn_wgrad_tc(const dn_wgrad* p, cudaStream_t st);   // dn_tc.cu
+
+DN_EXPORT int dn_igemm_run(const dn_igemm* p, int backend, void* stream) {
+  int e = igemm_check(p);
+  if (e) return e;
+  if (backend == 1) {
+    if (!dn_igemm_tc_supported(p)) return DN_E_UNSUPPORTED;
+    return dn_igemm_tc(p, dn_stream(stream));
+  }
+  return dn_igemm_generic(p, dn_stream(stream));
+}
+
+DN_EXPORT int dn_wgrad_run(const dn_wgrad* p, int backend, void* stream) {
+  int e = wgrad_check(p);
+  if (e) return e;
+  if (backend == 1) {
+    if (!dn_wgrad_tc_supported(p)) return DN_E_UNSUPPORTED;
+    return dn_wgrad_tc(p, dn_stream(stream));
+  }
+  return dn_wgrad_generic(p, dn_stream(stream));
+}
+
+// =================================================================================================
+// channel-group walkers: a thread owns CH consecutive channels (8 via 16-byte vectors, or 1 scalar)
+// =================================================================================================
+template <int CH>
+__device__ __forceinline__ void ldc(const dn_view& v, long long off, float* f) {
+  if (CH == 8) {
+    if (v.dtype == DN_F16) Vec8<__half>::load((const __half*)v.ptr + off, f);
+    else Vec8<__nv_bfloat16>::load((const __nv_bfloat16*)v.ptr + off, f);
+  } else {
+    f[0] = dn_ld(v.ptr, v.dtype, off);
+  }
+}
+template <int CH>
+__device__ __forceinline__ void stc(const dn_view& v, long long off, const float* f) {
+  if (CH == 8) {
+    if (v.dtype == DN_F16) Vec8<__half>::store((__half*)v.ptr + off, f);
+    else Vec8<__nv_bfloat16>::store((__nv_bfloat16*)v.ptr + off, f);
+  } else {
+    dn_st(v.ptr, v.dtype, off, f[0]);
+  }
+}
+
+struct CgGeom {
+  int CG;    // channel groups in the tensor
+  int CGb;   // channel groups per block (power of two <= 256)
+  int PL;    // pixel lanes per block = 256 / CGb
+  dim3 grid;
+};
+
+static CgGeom cg_geom(int C, int ch, long long pixels) {
+  CgGeom g;
+  g.CG = (C + ch - 1) / ch;
+  int b = 1;
+  while (b < g.CG && b < 256) b <<= 1;
+  g.CGb = b;
+  g.PL = 256 / b;
+  int gy = (g.CG + b - 1) / b;
+  long long bx = (pixels + g.PL - 1) / g.PL;
+  long long cap = (long long)dn_num_sms() * 8 / gy;
+  if (cap < 1) cap = 1;
+  if (bx > cap) bx = cap;
+  if (bx < 1) bx = 1;
+  g.grid = dim3((unsigned)bx, (unsigned)gy);
+  return g;
+}
+
+#define CG_PROLOGUE(view_for_dims)                                            \
+  const int cgl = threadIdx.x % CGb;                                          \
+  const int pl = threadIdx.x / CGb;                                           \
+  const int cg = blockIdx.y * CGb + cgl;                                      \
+  const int c0 = cg * CH;                                                     \
+  const bool cvalid = c0 < (view_for_dims).C;                                 \
+  const int PLn = 256 / CGb;                                                  \
+  const long long npix = (long long)(view_for_dims).N * (view_for_dims).H * (view_for_dims).W;
+
+// block-level reduction of NV per-thread float values over the pixel lanes; lane 0 threads get the result
+template <int NV>
+__device__ __forceinline__ void cg_block_reduce(float* vals, int CGb) {
+  __shared__ float red[256 * NV];
+  const int tid = threadIdx.x;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) red[i * 256 + tid] = vals[i];
+  __syncthreads();
+  const int PLn = 256 / CGb;
+  if (tid < CGb) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      float s = 0.f;
+      for (int l = 0; l < PLn; ++l) s += red[i * 256 + l * CGb + tid];
+      vals[i] = s;
+    }
+  }
+  __syncthreads();
+}
+
+// ---- BN statistics --------------------------------------------------------------------------------
+template <int CH>
+__global__ void __launch_bounds__(256) bn_stats_kernel(dn_view y, double* __restrict__ sums, int CGb) {
+  CG_PROLOGUE(y)
+  float acc[2 * CH];
+#pragma unroll
+  for (int i = 0; i < 2 * CH; ++i) acc[i] = 0.f;
+  if (cvalid) {
+    for (long long px = (long long)blockIdx.x * PLn + pl; px < npix; px += (long long)gridDim.x * PLn) {
+      int w = (int)(px % y.W);
+      long long q = px / y.W;
+      int h = (int)(q % y.H), n = (int)(q / y.H);
+      float f[CH];
+      ldc<CH>(y, dn_off(y, n, h, w) + c0, f);
+#pragma unroll
+      for (int i = 0; i < CH; ++i) { acc[i] += f[i]; acc[CH + i] = fmaf(f[i], f[i], acc[CH + i]); }
+    }
+  }
+  cg_block_reduce<2 * CH>(acc, CGb);
+  if (threadIdx.x < CGb && cvalid) {
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+      if (c0 + i < y.C) {
+        atomicAdd(sums + c0 + i, (double)acc[i]);
+        atomicAdd(sums + y.C + c0 + i, (double)acc[CH + i]);
+      }
+    }
+  }
+}
+
+DN_EXPORT int dn_bn_stats(const dn_view* y, double* sums, void* stream) {
+  if (!y || !sums) return DN_E_ARG;
+  long long npix = (long long)y->N * y->H * y->W;
+  if (dn_vec8_ok(y)) {
+    CgGeom g = cg_geom(y->C, 8, npix);
+    bn_stats_kernel<8><<<g.grid, 256, 0, dn_stream(stream)>>>(*y, sums, g.CGb);
+  } else {
+    CgGeom g = cg_geom(y->C, 1, npix);
+    bn_stats_kernel<1><<<g.grid, 256, 0, dn_stream(stream)>>>(*y, sums, g.CGb);
+  }
+  DN_CHECK_LAUNCH();
+  return 0;
+}
+
+__device__ __forceinline__ void bn_scale_shift(float gamma, float beta, float mean, float invstd, float& sc, float& sh) {
+  sc = gamma * invstd;
+  sh = beta - mean * sc;
+}
+
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, double count, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* running_mean, float* running_var, float momentum,
+                                   float eps, int training, int update_running, float* mean_invstd, float* scale_shift, int C) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float mean, invstd;
+  if (training) {
+    double m = sums[c] / count;
+    double var = sums[C + c] / count - m * m;
+    if (var < 0) var = 0;
+    mean = (float)m;
+    invstd = (float)(1.0 / sqrt(var + (double)eps));
+    if (update_running) {
+      double unb = count > 1 ? var * count / (count - 1) : var;
+      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+      running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unb;
+    }
+  } else {
+    mean = running_mean[c];
+    invstd = 1.f / sqrtf(running_var[c] + eps);
+  }
+  mean_invstd[c] = mean;
+  mean_invstd[C + c] = invstd;
+  float sc, sh;
+  bn_scale_shift(gamma ? gamma[c] : 1.f, beta ? beta[c] : 0.f, mean, invstd, sc, sh);
+  scale_shift[c] = sc;
+  scale_shift[C + c] = sh;
+}
+
+DN_EXPORT int dn_bn_finalize(const double* sums, double count, const float* gamma, const float* beta, float* running_mean,
+                             float* running_var, float momentum, float eps, int training, int update_running,
+                             float* mean_invstd, float* scale_shift, int C, void* stream) {
+  if (!mean_invstd || !scale_shift || C < 1) return DN_E_ARG;
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, dn_stream(stream)>>>(sums, count, gamma, beta, running_mean, running_var,
+                                                                      momentum, eps, training, update_running, mean_invstd,
+                                                                      scale_shift, C);
+  DN_CHECK_LAUNCH();
+  return 0;
+}
+
+// ---- BN apply (+residual) + act (+2x2 max pool) ------------------------------------------------------
+template <int CH>
+__global__ void __launch_bounds__(256) bn_apply_kernel(dn_view y, const float* __restrict__ scale_shift, dn_view res, int has_res,
+                                                       int act, int pool, dn_view out, int CGb) {
+  CG_PROLOGUE(out)
+  if (!cvalid) return;
+  float sc[CH], sh[CH];
+#pragma unroll
+  for (int i = 0; i < CH; ++i) {
+    int c = c0 + i < out.C ? c0 + i : out.C - 1;
+    sc[i] = scale_shift[c];
+    sh[i] = scale_shift[out.C + c];
+  }
+  for (long long px = (long long)blockIdx.x * PLn + pl; px < npix; px += (long long)gridDim.x * PLn) {
+    int w = (int)(px % out.W);
+    long long q = px / out.W;
+    int h = (int)(q % out.H), n = (int)(q / out.H);
+    float o[CH];
+    if (pool) {
+#pragma unroll
+      for (int i = 0; i < CH; ++i) o[i] = -INFINITY;
+#pragma unroll
+      for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+          float f[CH];
+          ldc<CH>(y, dn_off(y, n, 2 * h + a, 2 * w + b) + c0, f);
+#pragma unroll
+          for (int i = 0; i < CH; ++i) {
+            float v = dn_act(fmaf(f[i], sc[i], sh[i]), act);
+            o[i] = v > o[i] ? v : o[i];
+          }
+        }
+    } else {
+      float f[CH], r[CH];
+      ldc<CH>(y, dn_off(y, n, h, w) + c0, f);
+      if (has_res) ldc<CH>(res, dn_off(res, n, h, w) + c0, r);
+#pragma unroll
+      for (int i = 0; i < CH; ++i) {
+        float v = fmaf(f[i], sc[i], sh[i]);
+        if (has_res) v += r[i];
+        o[i] = dn_act(v, act);
+      }
+    }
+    stc<CH>(out, dn_off(out, n, h, w) + c0, o);
+  }
+}
+
+DN_EXPORT int dn_bn_apply(const dn_view* y, const float* scale_shift, const dn_view* residual, int act, int pool,
+                          const dn_view* out, void* stream) {
+  if (!y || !out || !scale_shift) return DN_E_ARG;
+  if (pool && (residual || out->H * 2 > y->H || out->W * 2 > y->W)) return DN_E_ARG;
+  if (!pool && (out->H != y->H || out->W != y->W)) return DN_E_ARG;
+  if (out->C != y->C || out->N != y->N) return DN_E_ARG;
+  long long npix = (long long)out->N * out->H * out->W;
+  dn_view r = residual ? *residual : *y;
+  bool vec = dn_vec8_ok(y) && dn_vec8_ok(out) && (!residual || dn_vec8_ok(residual));
+  if (vec) {
+    CgGeom g = cg_geom(out->C, 8, npix);
+    bn_apply_kernel<8><<<g.grid, 256, 0, dn_stream(stream)>>>(*y, scale_shift, r, residual != nullptr, act, pool, *out, g.CGb);
+  } else {
+    CgGeom g = cg_geom(out->C, 1, npix);
+    bn_apply_kernel<1><<<g.grid, 256, 0, dn_stream(stream)>>>(*y, scale_shift, r, residual != nullptr, act, pool, *out, g.CGb);
+  }
+  DN_CHECK_LAUNCH();
+  return 0;
+}
+
+// routes dout of one output pixel back to the (up to 4) y positions: dyhat[k] for k = a*2+b
+template <int CH>
+__device__ __forceinline__ void bn_route(const dn_view& y, const dn_view& res, int has_res, const dn_view& dout, int n, int h,
+                                         int w, int c0, const float* sc, const float* sh, int act, int pool,
+                                         float (*yv)[CH], float (*dyh)[CH]) {
+  float g[CH];
+  ldc<CH>(dout, dn_off(dout, n, h, w) + c0, g);
+  if (pool) {
+    float best[CH];
+    int bi[CH];
+#pragma unroll
+    for (int i = 0; i < CH; ++i) { best[i] = -INFINITY; bi[i] = 0; }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      ldc<CH>(y, dn_off(y, n, 2 * h + (k >> 1), 2 * w + (k & 1)) + c0, yv[k]);
+#pragma unroll
+      for (int i = 0; i < CH; ++i) {
+        float v = dn_act(fmaf(yv[k][i], sc[i], sh[i]), act);
+        if (v > best[i]) { best[i] = v; bi[i] = k; }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int i = 0; i < CH; ++i) dyh[k][i] = (bi[i] == k) ? g[i] * dn_act_grad(best[i], act) : 0.f;
+  } else {
+    ldc<CH>(y, dn_off(y, n, h, w) + c0, yv[0]);
+    float r[CH];
+    if (has_res) ldc<CH>(res, dn_off(res, n, h, w) + c0, r);
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+      float v = fmaf(yv[0][i], sc[i], sh[i]);
+      if (has_res) v += r[i];
+      dyh[0][i] = g[i] * dn_act_grad(dn_act(v, act), act);
+    }
+  }
+}
+
+template <int CH>
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(dn_view dout, dn_view y, dn_view res, int has_res,
+                                                            const float* __restrict__ mean_invstd, const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, int act, int pool, double* red, int CGb) {
+  CG_PROLOGUE(dout)
+  const int C = dout.C;
+  float acc[2 * CH];
+#pragma unroll
+  for (int i = 0; i < 2 * CH; ++i) acc[i] = 0.f;
+  if (cvalid) {
+    float sc[CH], sh[CH], mean[CH], istd[CH];
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+      int c = c0 + i < C ? c0 + i : C - 1;
+      mean[i] = mean_invstd[c]; istd[i] = mean_invstd[C + c];
+      bn_scale_shift(gamma ? gamma[c] : 1.f, beta ? beta[c] : 0.f, mean[i], istd[i], sc[i], sh[i]);
+    }
+    const int np = pool ? 4 : 1;
+    for (long long px = (long long)blockIdx.x * PLn + pl; px < npix; px += (long long)gridDim.x * PLn) {
+      int w = (int)(px % dout.W);
+      long long q = px / dout.W;
+      int h = (int)(q % dout.H), n = (int)(q / dout.H);
+      float yv[4][CH], dyh[4][CH];
+      bn_route<CH>(y, res, has_res, dout, n, h, w, c0, sc, sh, act, pool, yv, dyh);
+      for (int k = 0; k < np; ++k)
+#pragma unroll
+        for (int i = 0; i < CH; ++i) {
+          acc[i] += dyh[k][i];
+          acc[CH + i] = fmaf(dyh[k][i], (yv[k][i] - mean[i]) * istd[i], acc[CH + i]);
+        }
+    }
+  }
+  cg_block_reduce<2 * CH>(acc, CGb);
+  if (threadIdx.x < CGb && cvalid) {
+#pragma unroll
+    for (int i = 0; i < CH; ++i)
+      if (c0 + i < C) {
+        atomicAdd(red + c0 + i, (double)acc[i]);
+        atomicAdd(red + C + c0 + i, (double)acc[CH + i]);
+      }
+  }
+}
+
+DN_EXPORT int dn_bn_bwd_reduce(const dn_view* dout, const dn_view* y, const dn_view* residual, const float* mean_invstd,
+                               const float* gamma, const float* beta, int act, int pool, double* red, void* stream) {
+  if (!dout || !y || !mean_invstd || !red) return DN_E_ARG;
+  long long npix = (long long)dout->N * dout->H * dout->W;
+  dn_view r = residual ? *residual : *y;
+  bool vec = dn_vec8_ok(y) && dn_vec8_ok(dout) && (!residual || dn_vec8_ok(residual));
+  if (vec) {
+    CgGeom g = cg_geom(dout->C, 8, npix);
+    bn_bwd_reduce_kernel<8><<<g.grid, 256, 0, dn_stream(stream)>>>(*dout, *y, r, residual != nullptr, mean_invstd, gamma, beta, act, pool, red, g.CGb);
+  } else {
+    CgGeom g = cg_geom(dout->C, 1, npix);
+    bn_bwd_reduce_kernel<1><<<g.grid, 256, 0, dn_stream(stream)>>>(*dout, *y, r, residual != nullptr, mean_invstd, gamma, beta, act, pool, red, g.CGb);
+  }
+  DN_CHECK_LAUNCH();
+  return 0;
+}
+
+template <int CH>
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(dn_view dout, dn_view y, dn_view res, int has_res,
+                                                           const float* __restrict__ mean_invstd, const float* __restrict__ gamma,
+                                                           const float* __restrict__ beta, int act, int pool,
+                                                           const double* __restrict__ red, double count, float gscale,
+                                                           float* dgamma, float* dbeta, dn_view dy, dn_view dres, int has_dres,
+                                                           int dres_acc, int CGb) {
+  CG_PROLOGUE(dout)
+  const int C = dout.C;
+  if (!cvalid) return;
+  float sc[CH], sh[CH], mean[CH], istd[CH], m1[CH], m2[CH];
+#pragma unroll
+  for (int i = 0; i < CH; ++i) {
+    int c = c0 + i < C ? c0 + i : C - 1;
+    mean[i] = mean_invstd[c]; istd[i] = mean_invstd[C + c];
+    bn_scale_shift(gamma ? gamma[c] : 1.f, beta ? beta[c] : 0.f, mean[i], istd[i], sc[i], sh[i]);
+    m1[i] = (float)(red[c] / count);
+    m2[i] = (float)(red[C + c] / count);
+    if (blockIdx.x == 0 && pl == 0 && c0 + i < C) {
+      if (dgamma) dgamma[c] = (float)(red[C + c] * (double)gscale);
+      if (dbeta) dbeta[c] = (float)(red[c] * (double)gscale);
+    }
+  }
+  const int np = pool ? 4 : 1;
+  for (long long px = (long long)blockIdx.x * PLn + pl; px < npix; px += (long long)gridDim.x * PLn) {
+    int w = (int)(px % dout.W);
+    long long q = px / dout.W;
+    int h = (int)(q % dout.H), n = (int)(q / dout.H);
+    float yv[4][CH], dyh[4][CH];
+    bn_route<CH>(y, res, has_res, dout, n, h, w, c0, sc, sh, act, pool, yv, dyh);
+    for (int k = 0; k < np; ++k) {
+      float o[CH];
+#pragma unroll
+      for (int i = 0; i < CH; ++i) {
+        float xh = (yv[k][i] - mean[i]) * istd[i];
+        o[i] = sc[i] * (dyh[k][i] - m1[i] - xh * m2[i]);
+      }
+      int hh = pool ? 2 * h + (k >> 1) : h, ww = pool ? 2 * w + (k & 1) : w;
+      stc<CH>(dy, dn_off(dy, n, hh, ww) + c0, o);
+    }
+    if (has_dres) {
+      float o[CH];
+      long long off = dn_off(dres, n, h, w) + c0;
+      if (dres_acc) ldc<CH>(dres, off, o);
+#pragma unroll
+      for (int i = 0; i < CH; ++i) o[i] = dres_acc ? o[i] + dyh[0][i] : dyh[0][i];
+      stc<CH>(dres, off, o);
+    }
+  }
+}
+
+DN_EXPORT int dn_bn_bwd_apply(const dn_view* dout, const dn_view* y, const dn_view* residual, const float* mean_invstd,
+                              const float* gamma, const float* beta, int act, int pool, const double* red, double count,
+                              float gscale, float* dgamma, float* dbeta, const dn_view* dy, const dn_view* dres,
+                              int dres_accumulate, void* stream) {
+  if (!dout || !y || !mean_invstd || !red || !dy) return DN_E_ARG;
+  long long npix = (long long)dout->N * dout->H * dout->W;
+  dn_view r = residual ? *residual : *y;
+  dn_view dr = dres ? *dres : *dy;
+  bool vec = dn_vec8_ok(y) && dn_vec8_ok(dout) && dn_vec8_ok(dy) && (!residual || dn_vec8_ok(residual)) && (!dres || dn_vec8_ok(dres));
+  if (vec) {
+    CgGeom g = cg_geom(dout->C, 8, npix);
+    bn_bwd_apply_kernel<8><<<g.grid, 256, 0, dn_stream(stream)>>>(*dout, *y, r, residual != nullptr, mean_invstd, gamma, beta, act, pool, red, count, gscale, dgamma, dbeta, *dy, dr, dres != nullptr, dres_accumulate, g.CGb);
+  } else {
+    CgGeom g = cg_geom(dout->C, 1, npix);
+    bn_bwd_apply_kernel<1><<<g.grid, 256, 0, dn_stream(stream)>>>(*dout, *y, r, residual != nullptr, mean_invstd, gamma, beta, act, pool, red, count, gscale, dgamma, dbeta, *dy, dr, dres != nullptr, dres_accumulate, g.CGb);
+  }
+  DN_CHECK_LAUNCH();
+  return 0;
+}
+
+// ---- activation backward (in place) + bias gradient ---------------------------------------------------
+template <int CH>
+__global__ void __launch_bounds__(256) act_bwd_kernel(dn_view dout, dn_view out, int act, float* dbias, float gscale, int CGb) {
+  CG_PROLOGUE(dout)
+  float acc[CH];
+#pragma unroll
+  for (int i = 0; i < CH; ++i) acc[i] = 0.f;
+  if (cvalid) {
+    for (long long px = (long long)blockIdx.x * PLn + pl; px < npix; px += (long long)gridDim.x * PLn) {
+      int w = (int)(px % dout.W);
+      long long q = px / dout.W;
+      int h = (int)(q % dout.H), n = (int)(q / dout.H);
+      float g[CH], o[CH];
+      long long off = dn_off(dout, n, h, w) + c0;
+      ldc<CH>(dout, off, g);
+      if (act != DN_ACT_NONE) {
+        ldc<CH>(out, dn_off(out, n, h, w) + c0, o);
+#pragma unroll
+        for (int i = 0; i < CH; ++i) g[i] *= dn_act_grad(o[i], act);
+        stc<CH>(dout, off, g);
+      }
+#pragma unroll
+      for (int i = 0; i < CH; ++i) acc[i] += g[i];
+    }
+  }
+  if (dbias) {
+    cg_block_reduce<CH>(acc, CGb);
+    if (threadIdx.x < CGb && cvalid) {
+#pragma unroll
+      for (int i = 0; i < CH; ++i)
+        if (c0 + i < dout.C) atomicAdd(dbias + c0 + i, acc[i] * gscale);
+    }
+  }
+}
+
+DN_EXPORT int dn_act_bwd(const dn_view* dout, const dn_view* out, int act, float* dbias, float gscale, void* stream) {
+  if (!dout || (!out && act != DN_ACT_NONE)) return DN_E_ARG;
+  if (act == DN_ACT_NONE && !dbias) return 0;
+  long long npix = (long long)dout->N * dout->H * dout->W;
+  if (dbias) {
+    cudaError_t e = cudaMemsetAsync(dbias, 0, sizeof(float) * dout->C, dn_stream(stream));
+    if (e != cudaSuccess) return (int)e;
+  }
+  dn_view o = out ? *out : *dout;
+  bool vec = dn_vec8_ok(dout) && (!out || dn_vec8_ok(out));
+  if (vec) {
+    CgGeom g = cg_geom(dout->C, 8, npix);
+    act_bwd_kernel<8><<<g.grid, 256, 0, dn_stream(stream)>>>(*dout, o, act, dbias, gscale, g.CGb);
+  } else {
+    CgGeom g = cg_geom(dout->C, 1, npix);
+    act_bwd_kernel<1><<<g.grid, 256, 0, dn_stream(stream)>>>(*dout, o, act, dbias, gscale, g.CGb);
+  }
+  DN_CHECK_LAUNCH();
+  return 0;
+}
+
+// ---- generic max pool (ResNet stem 3/2/1) -----------------------------------------------------------------
+__global__ void maxpool_fwd_kernel(dn_view x, dn_view out, int k, int s, int p) {
+  long long total = (long long)out.N * out.H * out.W * out.C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % out.C);
+    long long q = i / out.C;
+    int w = (int)(q % out.W); q /= out.W;
+    int h = (int)(q % out.H);
+    int n = (int)(q / out.H);
+    float best = -INFINITY;
+    for (int a = 0; a < k; ++a) {
+      int hi = h * s - p + a;
+      if (hi < 0 || hi >= x.H) continue;
+      for (int b = 0; b < k; ++b) {
+        int wi = w * s - p + b;
+        if (wi < 0 || wi >= x.W) continue;
+        float v = dn_ld(x.ptr, x.dtype, dn_off(x, n, hi, wi) + c);
+        if (v > best) best = v;
+      }
+    }
+    dn_st(out.ptr, out.dtype, dn_off(out, n, h, w) + c, best);
+  }
+}
+
+__global__ void maxpool_bwd_kernel(dn_view dout, dn_view x, dn_view dx, int k, int s, int p, int accumulate) {
+  long long total = (long long)x.N * x.H * x.W * x.C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % x.C);
+    long long q = i / x.C;
+    int w = (int)(q % x.W); q /= x.W;
+    int h = (int)(q % x.H);
+    int n = (int)(q / x.H);
+    float g = 0.f;
+    // windows (oh, ow) that contain (h, w)
+    int oh_lo = (h + p - k + 1 + s - 1) / s; if (h + p - k + 1 < 0) oh_lo = 0;
+    int oh_hi = (h + p) / s; if (oh_hi > dout.H - 1) oh_hi = dout.H - 1;
+    int ow_lo = (w + p - k + 1 + s - 1) / s; if (w + p - k + 1 < 0) ow_lo = 0;
+    int ow_hi = (w + p) / s; if (ow_hi > dout.W - 1) ow_hi = dout.W - 1;
+    for (int oh = oh_lo; oh <= oh_hi; ++oh)
+      for (int ow = ow_lo; ow <= ow_hi; ++ow) {
+        float best = -INFINITY;
+        int bh = -1, bw = -1;
+        for (int a = 0; a < k; ++a) {
+          int hi = oh * s - p + a;
+          if (hi < 0 || hi >= x.H) continue;
+          for (int b = 0; b < k; ++b) {
+            int wi = ow * s - p + b;
+            if (wi < 0 || wi >= x.W) continue;
+            float v = dn_ld(x.ptr, x.dtype, dn_off(x, n, hi, wi) + c);
+            if (v > best) { best = v; bh = hi; bw = wi; }
+          }
+        }
+        if (bh == h && bw == w) g += dn_ld(dout.ptr, dout.dtype, dn_off(dout, n, oh, ow) + c);
+      }
+    long long o = dn_off(dx, n, h, w) + c;
+    if (accumulate) g += dn_ld(dx.ptr, dx.dtype, o);
+    dn_st(dx.ptr, dx.dtype, o, g);
+  }
+}
+
+static int ew_blocks(long long total) {
+  long long b = (total + 255) / 256;
+  long long cap = (long long)dn_num_sms() * 16;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+DN_EXPORT int dn_maxpool_fwd(const dn_view* x, const dn_view* out, int k, int stride, int pad, void* stream) {
+  if (!x || !out || x->C != out->C) return DN_E_ARG;
+  long long total = (long long)out->N * out->H * out->W * out->C;
+  maxpool_fwd_kernel<<<ew_blocks(total), 256, 0, dn_stream(stream)>>>(*x, *out, k, stride, pad);
+  DN_CHECK_LAUNCH();
+  return 0;
+}
+
+DN_EXPORT int dn_maxpool_bwd(const dn_view* dout, const dn_view* x, const dn_view* dx, int k, int stride, int pad,
+                             int accumulate, void* stream) {
+  if (!x || !dout || !dx) return DN_E_ARG;
+  long long total = (long long)x->N * x->H * x->W * x->C;
+  maxpool_bwd_kernel<<<ew_blocks(total), 256, 0, dn_stream(stream)>>>(*dout, *x, *dx, k, stride, pad, accumulate);
+  DN_CHECK_LAUNCH();
+  return 0;
+}
+
+// ---- pointwise over views ------------------------------------------------------------------------------------
+// mode 0: out = act(a + b?)   mode 1: copy/accumulate   mode 2: add_act backward
+template <int CH>
+__global__ void __launch_bounds__(256) ew_fwd_kernel(dn_view a, dn_view b, int has_b, int act, dn_view out, int accumulate) {
+  const int CG = (out.C + CH - 1) / CH;
+  long long total = (long long)out.N * out.H * out.W * CG;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c0 = (int)(i % CG) * CH;
+    long long q = i / CG;
+    int w = (int)(q % out.W); q /= out.W;
+    int h = (int)(q % out.H);
+    int n = (int)(q / out.H);
+    float fa[CH], fb[CH], fo[CH];
+    ldc<CH>(a, dn_off(a, n, h, w) + c0, fa);
+    if (has_b) ldc<CH>(b, dn_off(b, n, h, w) + c0, fb);
+    long long oo = dn_off(out, n, h, w) + c0;
+    if (accumulate) ldc<CH>(out, oo, fo);
+#pragma unroll
+    for (int k = 0; k < CH; ++k) {
+      float v = dn_act(has_b ? fa[k] + fb[k] : fa[k], act);
+      fo[k] = accumulate ? fo[k] + v : v;
+    }
+    stc<CH>(out, oo, fo);
+  }
+}
+
+static int ew_launch(const dn_view* a, const dn_view* b, int act, const dn_view* out, int accumulate, void* stream) {
+  if (!a || !out || a->C != out->C || a->N != out->N || a->H != out->H || a->W != out->W) return DN_E_ARG;
+  bool vec = dn_vec8_ok(a) && dn_vec8_ok(out) && (!b || dn_vec8_ok(b));
+  dn_view bb = b ? *b : *a;
+  if (vec) {
+    long long total = (long long)out->N * out->H * out->W * (out->C / 8);
+    ew_fwd_kernel<8><<<ew_blocks(total), 256, 0, dn_stream(stream)>>>(*a, bb, b != nullptr, act, *out, accumulate);
+  } else {
+    long long total = (long long)out->N * out->H * out->W * out->C;
+    ew_fwd_kernel<1><<<ew_blocks(total), 256, 0, dn_stream(stream)>>>(*a, bb, b != nullptr, act, *out, accumulate);
+  }
+  DN_CHECK_LAUNCH();
+  return 0;
+}
+
+DN_EXPORT int dn_add_act_fwd(const dn_view* a, const dn_view* b, int act, const dn_view* out, void* stream) {
+  return ew_launch(a, b, act, out, 0, stream);
+}
+DN_EXPORT int dn_act_fwd(const dn_view* x, int act, const dn_view* out, void* stream) {
+  return ew_launch(x, nullptr, act, out, 0, stream);
+}
+DN_EXPORT int dn_copy_view(const dn_view* src, const dn_view* dst, int accumulate, void* stream) {
+  return ew_launch(src, nullptr, DN_ACT_NONE, dst, accumulate, stream);
+}
+
+template <int CH>
+__global__ void __launch_bounds__(256) add_act_bwd_kernel(dn_view dout, dn_view out, int act, dn_view da, int da_acc, int has_da,
+                                                          dn_view db, int db_acc, int has_db) {
+  const int CG = (dout.C + CH - 1) / CH;
+  long long total = (long long)dout.N * dout.H * dout.W * CG;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c0 = (int)(i % CG) * CH;
+    long long q = i / CG;
+    int w = (int)(q % dout.W); q /= dout.W;
+    int h = (int)(q % dout.H);
+    int n = (int)(q / dout.H);
+    float g[CH], o[CH], t[CH];
+    ldc<CH>(dout, dn_off(dout, n, h, w) + c0, g);
+    if (act != DN_ACT_NONE) {
+      ldc<CH>(out, dn_off(out, n, h, w) + c0, o);
+#pragma unroll
+      for (int k = 0; k < CH; ++k) g[k] *= dn_act_grad(o[k], act);
+    }
+    if (has_da) {
+      long long off = dn_off(da, n, h, w) + c0;
+      if (da_acc) {
+        ldc<CH>(da, off, t);
+#pragma unroll
+        for (int k = 0; k < CH; ++k) t[k] += g[k];
+        stc<CH>(da, off, t);
+      } else stc<CH>(da, off, g);
+    }
+    if (has_db) {
+      long long off = dn_off(db, n, h, w) + c0;
+      if (db_acc) {
+        ldc<CH>(db, off, t);
+#pragma unroll
+        for (int k = 0; k < CH; ++k) t[k] += g[k];
+        stc<CH>(db, off, t);
+      } else stc<CH>(db, off, g);
+    }
+  }
+}
+
+DN_EXPORT int dn_add_act_bwd(const dn_view* dout, const dn_view* out, int act, const dn_view* da, int da_acc,
+                             const dn_view* db, int db_acc, void* stream) {
+  if (!dout || (!out && act != DN_ACT_NONE)) return DN_E_ARG;
+  dn_view o = out ? *out : *dout;
+  dn_view a = da ? *da : *dout, b = db ? *db : *dout;
+  bool vec = dn_vec8_ok(dout) && (!out || dn_vec8_ok(out)) && (!da || dn_vec8_ok(da)) && (!db || dn_vec8_ok(db));
+  if (vec) {
+    long long total = (long long)dout->N * dout->H * dout->W * (dout->C / 8);
+    add_act_bwd_kernel<8><<<ew_blocks(total), 256, 0, dn_stream(stream)>>>(*dout, o, act, a, da_acc, da != nullptr, b, db_acc, db != nullptr);
+  } else {
+    long long total = (long long)dout->N * dout->H * dout->W * dout->C;
+    add_act_bwd_kernel<1><<<ew_blocks(total), 256, 0, dn_stream(stream)>>>(*dout, o, act, a, da_acc, da != nullptr, b, db_acc, db != nullptr);
+  }
+  DN_CHECK_LAUNCH();
+  return 0;
+}
+
+// ---- disparity heads ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float dn_sigmoid(float x) { return 1.f / (1.f + expf(-x)); }
+
+__global__ void head_fwd_kernel(dn_view z, float alpha, float beta, float* __restrict__ disp) {
+  long long total = (long long)z.N * z.H * z.W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int w = (int)(i % z.W);
+    long long q = i / z.W;
+    int h = (int)(q % z.H), n = (int)(q / z.H);
+    disp[i] = alpha * dn_sigmoid(dn_ld(z.ptr, z.dtype, dn_off(z, n, h, w))) + beta;
+  }
+}
+
+// bilinear x2, align_corners=False source index (ATen area_pixel_compute_source_index)
+__device__ __forceinline__ void bil_src(int o, int insz, int& i0, int& i1, float& l0, float& l1) {
+  float s = 0.5f * ((float)o + 0.5f) - 0.5f;
+  if (s < 0.f) s = 0.f;
+  i0 = (int)s;
+  if (i0 > insz - 1) i0 = insz - 1;
+  i1 = i0 + ((i0 < insz - 1) ? 1 : 0);
+  l1 = s - (float)i0;
+  l0 = 1.f - l1;
+}
+
+__global__ void head_up_kernel(const float* __restrict__ disp, int N, int H, int W, dn_view up, int mode) {
+  long long total = (long long)up.N * up.H * up.W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int x = (int)(i % up.W);
+    long long q = i / up.W;
+    int y = (int)(q % up.H), n = (int)(q / up.H);
+    const float* d = disp + (long long)n * H * W;
+    float v;
+    if (mode == 0) {
+      v = d[(y >> 1) * W + (x >> 1)];
+    } else {
+      int y0, y1, x0, x1; float ly0, ly1, lx0, lx1;
+      bil_src(y, H, y0, y1, ly0, ly1);
+      bil_src(x, W, x0, x1, lx0, lx1);
+      v = ly0 * (lx0 * d[y0 * W + x0] + lx1 * d[y0 * W + x1]) + ly1 * (lx0 * d[y1 * W + x0] + lx1 * d[y1 * W + x1]);
+    }
+    dn_st(up.ptr, up.dtype, dn_off(up, n, y, x), v);
+  }
+}
+
+DN_EXPORT int dn_head_fwd(const dn_view* z, float alpha, float beta, float* disp, const dn_view* up, int up_mode, void* stream) {
+  if (!z || !disp) return DN_E_ARG;
+  long long total = (long long)z->N * z->H * z->W;
+  head_fwd_kernel<<<ew_blocks(total), 256, 0, dn_stream(stream)>>>(*z, alpha, beta, disp);
+  DN_CHECK_LAUNCH();
+  if (up) {
+    if (up->H > 2 * z->H || up->W > 2 * z->W || up->N != z->N) return DN_E_ARG;
+    long long t2 = (long long)up->N * up->H * up->W;
+    head_up_kernel<<<ew_blocks(t2), 256, 0, dn_stream(stream)>>>(disp, z->N, z->H, z->W, *up, up_mode);
+    DN_CHECK_LAUNCH();
+  }
+  return 0;
+}
+
+__global__ void head_bwd_kernel(const float* __restrict__ gdisp, dn_view dup, int has_up, int mode, dn_view z, float alpha,
+                                float gscale, dn_view dz) {
+  long long total = (long long)z.N * z.H * z.W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int w = (int)(i % z.W);
+    long long q = i / z.W;
+    int h = (int)(q % z.H), n = (int)(q / z.H);
+    float g = gdisp ? gdisp[i] * gscale : 0.f;   // gdisp is unscaled fp32 from autograd; dup is already scaled
+    if (has_up) {
+      if (mode == 0) {
+        for (int a = 0; a < 2; ++a)
+          for (int b = 0; b < 2; ++b) {
+            int y = 2 * h + a, x = 2 * w + b;
+            if (y < dup.H && x < dup.W) g += dn_ld(dup.ptr, dup.dtype, dn_off(dup, n, y, x));
+          }
+      } else {
+        for (int y = 2 * h - 2; y <= 2 * h + 2; ++y) {
+          if (y < 0 || y >= dup.H) continue;
+          int y0, y1; float ly0, ly1;
+          bil_src(y, z.H, y0, y1, ly0, ly1);
+          float wy = (y0 == h ? ly0 : 0.f) + (y1 == h ? ly1 : 0.f);
+          if (wy == 0.f) continue;
+          for (int x = 2 * w - 2; x <= 2 * w + 2; ++x) {
+            if (x < 0 || x >= dup.W) continue;
+            int x0, x1; float lx0, lx1;
+            bil_src(x, z.W, x0, x1, lx0, lx1);
+            float wx = (x0 == w ? lx0 : 0.f) + (x1 == w ? lx1 : 0.f);
+            if (wx == 0.f) continue;
+            g += wy * wx * dn_ld(dup.ptr, dup.dtype, dn_off(dup, n, y, x));
+          }
+        }
+      }
+    }
+    float s = dn_sigmoid(dn_ld(z.ptr, z.dtype, dn_off(z, n, h, w)));
+    dn_st(dz.ptr, dz.dtype, dn_off(dz, n, h, w), g * alpha * s * (1.f - s));
+  }
+}
+
+DN_EXPORT int dn_head_bwd(const float* gdisp, const dn_view* dup, int up_mode, const dn_view* z, float alpha, float gscale,
+                          const dn_view* dz, void* stream) {
+  if (!z || !dz) return DN_E_ARG;
+  long long total = (long long)z->N * z->H * z->W;
+  dn_view d = dup ? *dup : *z;
+  head_bwd_kernel<<<ew_blocks(total), 256, 0, dn_stream(stream)>>>(gdisp, d, dup != nullptr, up_mode, *z, alpha, gscale, *dz);
+  DN_CHECK_LAUNCH();
+  return 0;
+}
+
+__global__ void sigmoid_nchw_fwd_kernel(dn_view z, float* __restrict__ out) {
+  long long total = (long long)z.N * z.C * z.H * z.W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int w = (int)(i % z.W);
+    long long q = i / z.W;
+    int h = (int)(q % z.H); q /= z.H;
+    int c = (int)(q % z.C), n = (int)(q / z.C);
+    out[i] = dn_sigmoid(dn_ld(z.ptr, z.dtype, dn_off(z, n, h, w) + c));
+  }
+}
+__global__ void sigmoid_nchw_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ out, float gscale, dn_view dz) {
+  long long total = (long long)dz.N * dz.C * dz.H * dz.W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int w = (int)(i % dz.W);
+    long long q = i / dz.W;
+    int h = (int)(q % dz.H); q /= dz.H;
+    int c = (int)(q % dz.C), n = (int)(q / dz.C);
+    float s = out[i];
+    dn_st(dz.ptr, dz.dtype, dn_off(dz, n, h, w) + c, (gout ? gout[i] : 0.f) * gscale * s * (1.f - s));
+  }
+}
+DN_EXPORT int dn_sigmoid_nchw_fwd(const dn_view* z, float* out, void* stream) {
+  if (!z || !out) return DN_E_ARG;
+  long long total = (long long)z->N * z->C * z->H * z->W;
+  sigmoid_nchw_fwd_kernel<<<ew_blocks(total), 256, 0, dn_stream(stream)>>>(*z, out);
+  DN_CHECK_LAUNCH();
+  return 0;
+}
+DN_EXPORT int dn_sigmoid_nchw_bwd(const float* gout, const float* out, float gscale, const dn_view* dz, void* stream) {
+  if (!dz || !out) return DN_E_ARG;
+  long long total = (long long)dz->N * dz->C * dz->H * dz->W;
+  sigmoid_nchw_bwd_kernel<<<ew_blocks(total), 256, 0, dn_stream(stream)>>>(gout, out, gscale, *dz);
+  DN_CHECK_LAUNCH();
+  return 0;
+}
+
+__global__ void spatial_mean_fwd_kernel(dn_view z, float scale, float* __restrict__ out) {
+  int n = blockIdx.x / z.C, c = blockIdx.x % z.C;
+  float s = 0.f;
+  int HW = z.H * z.W;
+  for (int i = threadIdx.x; i < HW; i += blockDim.x) s += dn_ld(z.ptr, z.dtype, dn_off(z, n, i / z.W, i % z.W) + c);
+  __shared__ float red[32];
+  s = dn_warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+    out[blockIdx.x] = scale * (t / (float)HW);
+  }
+}
+__global__ void spatial_mean_bwd_kernel(const float* __restrict__ gout, float scale, dn_view dz) {
+  long long total = (long long)dz.N * dz.H * dz.W * dz.C;
+  float inv = scale / (float)(dz.H * dz.W);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % dz.C);
+    long long q = i / dz.C;
+    int w = (int)(q % dz.W); q /= dz.W;
+    int h = (int)(q % dz.H);
+    int n = (int)(q / dz.H);
+    dn_st(dz.ptr, dz.dtype, dn_off(dz, n, h, w) + c, gout[n * dz.C + c] * inv);
+  }
+}
+DN_EXPORT int dn_spatial_mean_fwd(const dn_view* z, float scale, float* out, void* stream) {
+  if (!z || !out) return DN_E_ARG;
+  spatial_mean_fwd_kernel<<<z->N * z->C, 128, 0, dn_stream(stream)>>>(*z, scale, out);
+  DN_CHECK_LAUNCH();
+  return 0;
+}
+DN_EXPORT int dn_spatial_mean_bwd(const float* gout, float scale, const dn_view* dz, void* stream) {
+  if (!dz || !gout) return DN_E_ARG;
+  long long total = (long long)dz->N * dz->H * dz->W * dz->C;
+  spatial_mean_bwd_kernel<<<ew_blocks(total), 256, 0, dn_stream(stream)>>>(gout, scale, *dz);
+  DN_CHECK_LAUNCH();
+  return 0;
+}
+
+// ---- misc -------------------------------------------------------------------------------------------------------------
+__global__ void fill_kernel(float* p, long long n, float v) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
+}
+__global__ void axpy_kernel(const float* __restrict__ x, float a, float* y, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) y[i] += a * x[i];
+}
+DN_EXPORT int dn_fill_f32(float* p, int64_t n, float v, void* stream) {
+  if (n <= 0) return 0;
+  fill_kernel<<<ew_blocks(n), 256, 0, dn_stream(stream)>>>(p, n, v);
+  DN_CHECK_LAUNCH();
+  return 0;
+}
+DN_EXPORT int dn_axpy_f32(const float* x, float a, float* y, int64_t n, void* stream) {
+  if (n <= 0) return 0;
+  axpy_kernel<<<ew_blocks(n), 256, 0, dn_stream(stream)>>>(x, a, y, n);
+  DN_CHECK_LAUNCH();
+  return 0;
+}
+
+DN_EXPORT int dn_version(void) { return 100; }
+DN_EXPORT const char* dn_error_string(int code) {
+  if (code == 0) return "ok";
+  if (code == DN_E_ARG) return "dispnet_b200: invalid argument";
+  if (code == DN_E_UNSUPPORTED) return "dispnet_b200: problem not supported by the requested backend";
+  if (code > 0) return cudaGetErrorString((cudaError_t)code);
+  return "dispnet_b200: unknown error";
+}

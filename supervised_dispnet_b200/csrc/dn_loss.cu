@@ -1,0 +1,731 @@
+// Per-pixel loss / geometry kernels (HBM-bound, fp32): masked L1 depth loss, second-order smoothness,
+// depth-error counters, area pyramid, explainability BCE, and the fused inverse-warp + photometric term.
+// Each replaces a chain of ATen launches in loss_functions.py / inverse_warp.py with one pass; reductions are
+// warp-shuffle -> shared -> one atomic per block.  Arithmetic follows SURVEY.md appendix A.1-A.5.
+#include "dn_common.cuh"
+
+namespace {
+
+__device__ __forceinline__ float block_sum(float v) {
+  __shared__ float red[32];
+  v = dn_warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+  if (threadIdx.x < 32) {
+    t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    t = dn_warp_sum(t);
+  }
+  return t;  // valid in warp 0
+}
+__device__ __forceinline__ double block_sum_d(double v) {
+  __shared__ double redd[32];
+  v = dn_warp_sum_d(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) redd[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = 0.0;
+  if (threadIdx.x < 32) {
+    t = threadIdx.x < (blockDim.x >> 5) ? redd[threadIdx.x] : 0.0;
+    t = dn_warp_sum_d(t);
+  }
+  return t;
+}
+
+inline int blocks_for(long long n, int per_block, int cap_mult = 8) {
+  long long b = (n + per_block - 1) / per_block;
+  long long cap = (long long)dn_num_sms() * cap_mult;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// l1_loss (loss_functions.py:104-129)
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) l1_fwd_kernel(const float* __restrict__ gt, const float* __restrict__ pred, int HW,
+                                                     float maxd, float* ws) {
+  const int b = blockIdx.y;
+  const float* g = gt + (long long)b * HW;
+  const float* p = pred + (long long)b * HW;
+  float s = 0.f, c = 0.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
+    float gv = g[i];
+    if (gv > 0.f && gv < maxd) {
+      float pv = fminf(fmaxf(p[i], 1e-3f), maxd);
+      s += fabsf(gv - pv);
+      c += 1.f;
+    }
+  }
+  s = block_sum(s);
+  c = block_sum(c);
+  if (threadIdx.x == 0) {
+    atomicAdd(ws + 2 * b, s);
+    atomicAdd(ws + 2 * b + 1, c);
+  }
+}
+__global__ void l1_finalize_kernel(const float* ws, int B, float* loss) {
+  float t = 0.f;
+  for (int b = 0; b < B; ++b) t += ws[2 * b] / ws[2 * b + 1];   // 0/0 -> NaN like mean() of an empty selection
+  loss[0] = t / (float)B;
+}
+__global__ void __launch_bounds__(256) l1_bwd_kernel(const float* __restrict__ gt, const float* __restrict__ pred, int HW,
+                                                     float maxd, const float* __restrict__ ws, int B,
+                                                     const float* __restrict__ gout, float* __restrict__ gpred) {
+  const int b = blockIdx.y;
+  const float* g = gt + (long long)b * HW;
+  const float* p = pred + (long long)b * HW;
+  float* o = gpred + (long long)b * HW;
+  const float k = gout[0] / (ws[2 * b + 1] * (float)B);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
+    float gv = g[i], pv = p[i], r = 0.f;
+    if (gv > 0.f && gv < maxd && pv >= 1e-3f && pv <= maxd) {
+      float d = pv - gv;
+      r = d > 0.f ? k : (d < 0.f ? -k : 0.f);
+    }
+    o[i] = r;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// smooth_loss (loss_functions.py:367-386), one scale
+// ---------------------------------------------------------------------------------------------------
+struct SmoothCoef { float c1, c2, c3, c4; };
+
+__device__ __forceinline__ float sgn(float x) { return x > 0.f ? 1.f : (x < 0.f ? -1.f : 0.f); }
+
+__device__ __forceinline__ float sm_dx2(const float* p, int W, int v, int u) {
+  const float* r = p + v * W + u;
+  return (r[2] - r[1]) - (r[1] - r[0]);
+}
+__device__ __forceinline__ float sm_dy2(const float* p, int W, int v, int u) {
+  const float* r = p + v * W + u;
+  return (r[2 * W] - r[W]) - (r[W] - r[0]);
+}
+__device__ __forceinline__ float sm_dxdy(const float* p, int W, int v, int u) {   // dx[v+1,u] - dx[v,u]
+  const float* r = p + v * W + u;
+  return (r[W + 1] - r[W]) - (r[1] - r[0]);
+}
+__device__ __forceinline__ float sm_dydx(const float* p, int W, int v, int u) {   // dy[v,u+1] - dy[v,u]
+  const float* r = p + v * W + u;
+  return (r[W + 1] - r[1]) - (r[W] - r[0]);
+}
+
+__global__ void __launch_bounds__(256) smooth_fwd_kernel(const float* __restrict__ p, int H, int W, SmoothCoef k, float* loss) {
+  const float* pb = p + (long long)blockIdx.y * H * W;
+  float s = 0.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < H * W; i += gridDim.x * blockDim.x) {
+    int v = i / W, u = i % W;
+    if (u < W - 2) s += k.c1 * fabsf(sm_dx2(pb, W, v, u));
+    if (v < H - 2) s += k.c4 * fabsf(sm_dy2(pb, W, v, u));
+    if (u < W - 1 && v < H - 1) s += k.c2 * fabsf(sm_dxdy(pb, W, v, u)) + k.c3 * fabsf(sm_dydx(pb, W, v, u));
+  }
+  s = block_sum(s);
+  if (threadIdx.x == 0) atomicAdd(loss, s);
+}
+
+__global__ void __launch_bounds__(256) smooth_bwd_kernel(const float* __restrict__ p, int H, int W, SmoothCoef k,
+                                                         const float* __restrict__ gout, float* __restrict__ gp) {
+  const float* pb = p + (long long)blockIdx.y * H * W;
+  float* gb = gp + (long long)blockIdx.y * H * W;
+  const float go = gout[0];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < H * W; i += gridDim.x * blockDim.x) {
+    int v = i / W, u = i % W;
+    float g = 0.f;
+    // dx2[v,uu] = p[uu+2] - 2 p[uu+1] + p[uu]
+    if (u <= W - 3) g += k.c1 * sgn(sm_dx2(pb, W, v, u));
+    if (u >= 1 && u - 1 <= W - 3) g -= 2.f * k.c1 * sgn(sm_dx2(pb, W, v, u - 1));
+    if (u >= 2) g += k.c1 * sgn(sm_dx2(pb, W, v, u - 2));
+    if (v <= H - 3) g += k.c4 * sgn(sm_dy2(pb, W, v, u));
+    if (v >= 1 && v - 1 <= H - 3) g -= 2.f * k.c4 * sgn(sm_dy2(pb, W, v - 1, u));
+    if (v >= 2) g += k.c4 * sgn(sm_dy2(pb, W, v - 2, u));
+    // mixed terms: +p[v,u] - p[v,u+1] - p[v+1,u] + p[v+1,u+1], defined for v<=H-2, u<=W-2
+    if (v <= H - 2 && u <= W - 2) g += k.c2 * sgn(sm_dxdy(pb, W, v, u)) + k.c3 * sgn(sm_dydx(pb, W, v, u));
+    if (v <= H - 2 && u >= 1) g -= k.c2 * sgn(sm_dxdy(pb, W, v, u - 1)) + k.c3 * sgn(sm_dydx(pb, W, v, u - 1));
+    if (v >= 1 && u <= W - 2) g -= k.c2 * sgn(sm_dxdy(pb, W, v - 1, u)) + k.c3 * sgn(sm_dydx(pb, W, v - 1, u));
+    if (v >= 1 && u >= 1) g += k.c2 * sgn(sm_dxdy(pb, W, v - 1, u - 1)) + k.c3 * sgn(sm_dydx(pb, W, v - 1, u - 1));
+    gb[i] = g * go;
+  }
+}
+
+SmoothCoef smooth_coef(int B, int H, int W, float weight) {
+  SmoothCoef k;
+  k.c1 = weight / ((float)B * H * (W - 2));
+  k.c2 = weight / ((float)B * (H - 1) * (W - 1));
+  k.c3 = k.c2;
+  k.c4 = weight / ((float)B * (H - 2) * W);
+  return k;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// compute_errors (loss_functions.py:401-448)
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) depth_errors_kernel(const float* __restrict__ gt, const float* __restrict__ pred, int H, int W,
+                                                           float maxd, int y1, int y2, int x1, int x2,
+                                                           const float* __restrict__ scale, int32_t* counters, double* sums) {
+  const int b = blockIdx.y;
+  const float* g = gt + (long long)b * H * W;
+  const float* p = pred + (long long)b * H * W;
+  const float sc = scale ? scale[b] : 1.f;
+  int n = 0, a1 = 0, a2 = 0, a3 = 0;
+  double s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0;
+  const float t1 = 1.25f, t2 = (float)(1.25 * 1.25), t3 = (float)(1.25 * 1.25 * 1.25);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < H * W; i += gridDim.x * blockDim.x) {
+    int y = i / W, x = i % W;
+    float gv = g[i];
+    if (!(gv > 0.f && gv < maxd) || y < y1 || y >= y2 || x < x1 || x >= x2) continue;
+    float pv = fminf(fmaxf(p[i], 1e-3f), maxd);
+    if (scale) pv = pv * sc;
+    float th = fmaxf(gv / pv, pv / gv);
+    n += 1;
+    a1 += th < t1; a2 += th < t2; a3 += th < t3;
+    float d = gv - pv;
+    float lg = logf(gv) - logf(pv);
+    s0 += (double)fabsf(d);
+    s1 += (double)(fabsf(d) / gv);
+    s2 += (double)(d * d / gv);
+    s3 += (double)(d * d);
+    s4 += (double)(lg * lg);
+  }
+  // integer counters: warp reduce then one atomic per warp
+  for (int o = 16; o > 0; o >>= 1) {
+    n += __shfl_xor_sync(0xffffffffu, n, o);
+    a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+    a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+    a3 += __shfl_xor_sync(0xffffffffu, a3, o);
+  }
+  if ((threadIdx.x & 31) == 0 && n) {
+    atomicAdd(counters + 4 * b, n); atomicAdd(counters + 4 * b + 1, a1);
+    atomicAdd(counters + 4 * b + 2, a2); atomicAdd(counters + 4 * b + 3, a3);
+  }
+  s0 = block_sum_d(s0); s1 = block_sum_d(s1); s2 = block_sum_d(s2); s3 = block_sum_d(s3); s4 = block_sum_d(s4);
+  if (threadIdx.x == 0) {
+    atomicAdd(sums + 5 * b, s0); atomicAdd(sums + 5 * b + 1, s1); atomicAdd(sums + 5 * b + 2, s2);
+    atomicAdd(sums + 5 * b + 3, s3); atomicAdd(sums + 5 * b + 4, s4);
+  }
+}
+
+__global__ void area_down_kernel(const float* __restrict__ src, int NC, int H, int W, int f, float* __restrict__ dst) {
+  const int h = H / f, w = W / f;
+  long long total = (long long)NC * h * w;
+  const float inv = 1.f / (float)(f * f);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int x = (int)(i % w);
+    long long q = i / w;
+    int y = (int)(q % h);
+    long long nc = q / h;
+    const float* s = src + (nc * H + (long long)y * f) * W + (long long)x * f;
+    float a = 0.f;
+    for (int dy = 0; dy < f; ++dy)
+      for (int dx = 0; dx < f; ++dx) a += s[dy * W + dx];
+    dst[i] = a * inv;
+  }
+}
+
+__global__ void explain_fwd_kernel(const float* __restrict__ m, long long n, float inv, float* loss) {
+  float s = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    s -= fmaxf(logf(m[i]), -100.f);
+  s = block_sum(s);
+  if (threadIdx.x == 0) atomicAdd(loss, s * inv);
+}
+__global__ void explain_bwd_kernel(const float* __restrict__ m, long long n, float inv, const float* __restrict__ gout, float* __restrict__ gm) {
+  const float go = gout[0] * inv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float v = m[i];
+    gm[i] = (v - 1.f) / fmaxf((1.f - v) * v, 1e-12f) * go;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// inverse warp geometry (inverse_warp.py:26-193; grid_sample semantics of ATen GridSampler)
+// ---------------------------------------------------------------------------------------------------
+struct PoseMats {   // per batch element, built once per block in shared memory
+  float Kinv[9];
+  float K[9];
+  float R[9];
+  float t[3];
+  float Prot[9];    // K @ R
+  float Ptr[3];     // K @ t
+};
+
+__device__ void mat3_mul(const float* a, const float* b, float* c) {
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) c[i * 3 + j] = a[i * 3] * b[j] + a[i * 3 + 1] * b[3 + j] + a[i * 3 + 2] * b[6 + j];
+}
+
+__device__ void euler_mats(const float* ang, float* X, float* Y, float* Z) {
+  float cx = cosf(ang[0]), sx = sinf(ang[0]), cy = cosf(ang[1]), sy = sinf(ang[1]), cz = cosf(ang[2]), sz = sinf(ang[2]);
+  float z[9] = {cz, -sz, 0, sz, cz, 0, 0, 0, 1};
+  float y[9] = {cy, 0, sy, 0, 1, 0, -sy, 0, cy};
+  float x[9] = {1, 0, 0, 0, cx, -sx, 0, sx, cx};
+  for (int i = 0; i < 9; ++i) { X[i] = x[i]; Y[i] = y[i]; Z[i] = z[i]; }
+}
+
+__device__ void quat_rot(const float* q4, float* R) {   // q4 normalised (w,x,y,z)  (inverse_warp.py:128-137)
+  float w = q4[0], x = q4[1], y = q4[2], z = q4[3];
+  float w2 = w * w, x2 = x * x, y2 = y * y, z2 = z * z;
+  float wx = w * x, wy = w * y, wz = w * z, xy = x * y, xz = x * z, yz = y * z;
+  R[0] = w2 + x2 - y2 - z2; R[1] = 2 * xy - 2 * wz; R[2] = 2 * wy + 2 * xz;
+  R[3] = 2 * wz + 2 * xy; R[4] = w2 - x2 + y2 - z2; R[5] = 2 * yz - 2 * wx;
+  R[6] = 2 * xz - 2 * wy; R[7] = 2 * wx + 2 * yz; R[8] = w2 - x2 - y2 + z2;
+}
+
+__device__ void build_pose(const float* pose, const float* K, const float* Kinv, int rot_mode, PoseMats& m) {
+  for (int i = 0; i < 9; ++i) { m.K[i] = K[i]; m.Kinv[i] = Kinv[i]; }
+  for (int i = 0; i < 3; ++i) m.t[i] = pose[i];
+  if (rot_mode == 0) {
+    float X[9], Y[9], Z[9], XY[9];
+    euler_mats(pose + 3, X, Y, Z);
+    mat3_mul(X, Y, XY);
+    mat3_mul(XY, Z, m.R);
+  } else {
+    float q[4] = {1.f, pose[3], pose[4], pose[5]};
+    float nrm = sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    for (int i = 0; i < 4; ++i) q[i] /= nrm;
+    quat_rot(q, m.R);
+  }
+  mat3_mul(m.K, m.R, m.Prot);
+  for (int i = 0; i < 3; ++i) m.Ptr[i] = m.K[i * 3] * m.t[0] + m.K[i * 3 + 1] * m.t[1] + m.K[i * 3 + 2] * m.t[2];
+}
+
+struct WarpPix {
+  float cam[3];     // camera-frame point
+  float ray[3];     // Kinv @ (u,v,1)
+  float px, py, pz, Z;
+  float ix, iy;     // unnormalised sampling position
+  float dix_dxn, diy_dyn;   // multipliers incl. zeros-mode replacement and border clipping (0 when no gradient)
+  bool zclamped;
+  int x0, y0;
+  float wx0, wx1, wy0, wy1;
+  bool finite;
+};
+
+__device__ __forceinline__ void warp_pixel(const PoseMats& m, int u, int v, float d, int h, int w, int pad_mode, int align,
+                                           WarpPix& o) {
+  const float fu = (float)u, fv = (float)v;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    o.ray[k] = m.Kinv[k * 3] * fu + m.Kinv[k * 3 + 1] * fv + m.Kinv[k * 3 + 2];
+    o.cam[k] = o.ray[k] * d;
+  }
+  o.px = m.Prot[0] * o.cam[0] + m.Prot[1] * o.cam[1] + m.Prot[2] * o.cam[2] + m.Ptr[0];
+  o.py = m.Prot[3] * o.cam[0] + m.Prot[4] * o.cam[1] + m.Prot[5] * o.cam[2] + m.Ptr[1];
+  o.pz = m.Prot[6] * o.cam[0] + m.Prot[7] * o.cam[1] + m.Prot[8] * o.cam[2] + m.Ptr[2];
+  o.zclamped = !(o.pz >= 1e-3f);
+  o.Z = fmaxf(o.pz, 1e-3f);
+  float xn = 2.f * (o.px / o.Z) / (float)(w - 1) - 1.f;
+  float yn = 2.f * (o.py / o.Z) / (float)(h - 1) - 1.f;
+  float gx = 1.f, gy = 1.f;
+  if (pad_mode == 0) {
+    if (xn > 1.f || xn < -1.f) { xn = 2.f; gx = 0.f; }
+    if (yn > 1.f || yn < -1.f) { yn = 2.f; gy = 0.f; }
+  }
+  float ix, iy;
+  if (align) {
+    ix = ((xn + 1.f) / 2.f) * (float)(w - 1); gx *= 0.5f * (float)(w - 1);
+    iy = ((yn + 1.f) / 2.f) * (float)(h - 1); gy *= 0.5f * (float)(h - 1);
+  } else {
+    ix = ((xn + 1.f) * (float)w - 1.f) / 2.f; gx *= 0.5f * (float)w;
+    iy = ((yn + 1.f) * (float)h - 1.f) / 2.f; gy *= 0.5f * (float)h;
+  }
+  if (pad_mode == 1) {   // border: clip_coordinates(_set_grad)
+    if (!(ix > 0.f)) { ix = 0.f; gx = 0.f; } else if (ix >= (float)(w - 1)) { ix = (float)(w - 1); gx = 0.f; }
+    if (!(iy > 0.f)) { iy = 0.f; gy = 0.f; } else if (iy >= (float)(h - 1)) { iy = (float)(h - 1); gy = 0.f; }
+  }
+  o.ix = ix; o.iy = iy; o.dix_dxn = gx; o.diy_dyn = gy;
+  o.finite = isfinite(ix) && isfinite(iy) && fabsf(ix) < 1e9f && fabsf(iy) < 1e9f;
+  float fx = floorf(ix), fy = floorf(iy);
+  o.x0 = o.finite ? (int)fx : -10; o.y0 = o.finite ? (int)fy : -10;
+  o.wx1 = ix - fx; o.wx0 = (fx + 1.f) - ix;
+  o.wy1 = iy - fy; o.wy0 = (fy + 1.f) - iy;
+}
+
+// bilinear fetch of C channels (channel stride cs); returns values and, optionally, d/dix, d/diy
+template <int C, bool GRAD>
+__device__ __forceinline__ void bil_fetch(const float* __restrict__ img, long long cs, int h, int w, const WarpPix& p, float* val,
+                                          float* dvx, float* dvy) {
+  const int x0 = p.x0, y0 = p.y0, x1 = x0 + 1, y1 = y0 + 1;
+  const bool bx0 = x0 >= 0 && x0 < w, bx1 = x1 >= 0 && x1 < w, by0 = y0 >= 0 && y0 < h, by1 = y1 >= 0 && y1 < h;
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    const float* ic = img + c * cs;
+    float nw = (bx0 && by0) ? ic[y0 * w + x0] : 0.f;
+    float ne = (bx1 && by0) ? ic[y0 * w + x1] : 0.f;
+    float sw = (bx0 && by1) ? ic[y1 * w + x0] : 0.f;
+    float se = (bx1 && by1) ? ic[y1 * w + x1] : 0.f;
+    val[c] = nw * (p.wx0 * p.wy0) + ne * (p.wx1 * p.wy0) + sw * (p.wx0 * p.wy1) + se * (p.wx1 * p.wy1);
+    if (GRAD) {
+      dvx[c] = -nw * p.wy0 + ne * p.wy0 - sw * p.wy1 + se * p.wy1;
+      dvy[c] = -nw * p.wx0 - ne * p.wx1 + sw * p.wx0 + se * p.wx1;
+    }
+  }
+}
+
+// chain d(loss)/d(ix,iy) -> depth gradient and the 12 per-batch pose accumulators (q = K^T gp ; G = q cam^T)
+__device__ __forceinline__ void warp_chain(const PoseMats& m, const WarpPix& p, int h, int w, float gix, float giy, float& gdepth,
+                                           float* acc12) {
+  float gxn = gix * p.dix_dxn, gyn = giy * p.diy_dyn;
+  float ax = 2.f / (float)(w - 1), ay = 2.f / (float)(h - 1);
+  float gpx = gxn * ax / p.Z;
+  float gpy = gyn * ay / p.Z;
+  float gZ = -(gxn * ax * p.px + gyn * ay * p.py) / (p.Z * p.Z);
+  float gpz = p.zclamped ? 0.f : gZ;
+  // p = Prot cam + Ptr ; cam = ray * d
+  float gc0 = m.Prot[0] * gpx + m.Prot[3] * gpy + m.Prot[6] * gpz;
+  float gc1 = m.Prot[1] * gpx + m.Prot[4] * gpy + m.Prot[7] * gpz;
+  float gc2 = m.Prot[2] * gpx + m.Prot[5] * gpy + m.Prot[8] * gpz;
+  gdepth = gc0 * p.ray[0] + gc1 * p.ray[1] + gc2 * p.ray[2];
+  float q0 = m.K[0] * gpx + m.K[3] * gpy + m.K[6] * gpz;
+  float q1 = m.K[1] * gpx + m.K[4] * gpy + m.K[7] * gpz;
+  float q2 = m.K[2] * gpx + m.K[5] * gpy + m.K[8] * gpz;
+  acc12[0] += q0; acc12[1] += q1; acc12[2] += q2;
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    acc12[3 + j] += q0 * p.cam[j];
+    acc12[6 + j] += q1 * p.cam[j];
+    acc12[9 + j] += q2 * p.cam[j];
+  }
+}
+
+__device__ void block_reduce12(float* acc12, float* dst) {
+  __shared__ float red12[12][33];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < 12; ++i) {
+    float v = dn_warp_sum(acc12[i]);
+    if (lane == 0) red12[i][wid] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 12) {
+    float t = 0.f;
+    for (int k = 0; k < (int)(blockDim.x >> 5); ++k) t += red12[threadIdx.x][k];
+    atomicAdd(dst + threadIdx.x, t);
+  }
+}
+
+// (q, G) -> pose gradient for one batch element
+__global__ void pose_grad_finalize_kernel(const float* __restrict__ ws, const float* __restrict__ pose, int pose_stride, int B,
+                                          int rot_mode, float* gpose) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const float* a = ws + 12 * b;
+  const float* ps = pose + (long long)b * pose_stride;
+  float* g = gpose + (long long)b * pose_stride;
+  g[0] += a[0]; g[1] += a[1]; g[2] += a[2];
+  const float* G = a + 3;
+  if (rot_mode == 0) {
+    float X[9], Y[9], Z[9];
+    euler_mats(ps + 3, X, Y, Z);
+    float cx = X[4], sx = X[7], cy = Y[0], sy = Y[2], cz = Z[0], sz = Z[3];
+    float dX[9] = {0, 0, 0, 0, -sx, -cx, 0, cx, -sx};
+    float dY[9] = {-sy, 0, cy, 0, 0, 0, -cy, 0, -sy};
+    float dZ[9] = {-sz, -cz, 0, cz, -sz, 0, 0, 0, 0};
+    float T1[9], T2[9];
+    float r;
+    mat3_mul(dX, Y, T1); mat3_mul(T1, Z, T2);
+    r = 0.f; for (int i = 0; i < 9; ++i) r += G[i] * T2[i];
+    g[3] += r;
+    mat3_mul(X, dY, T1); mat3_mul(T1, Z, T2);
+    r = 0.f; for (int i = 0; i < 9; ++i) r += G[i] * T2[i];
+    g[4] += r;
+    mat3_mul(X, Y, T1); mat3_mul(T1, dZ, T2);
+    r = 0.f; for (int i = 0; i < 9; ++i) r += G[i] * T2[i];
+    g[5] += r;
+  } else {
+    float q[4] = {1.f, ps[3], ps[4], ps[5]};
+    float nrm = sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    float w = q[0] / nrm, x = q[1] / nrm, y = q[2] / nrm, z = q[3] / nrm;
+    // dR/d(w,x,y,z) contracted with G
+    float gw = G[0] * 2 * w + G[1] * (-2 * z) + G[2] * (2 * y) + G[3] * (2 * z) + G[4] * 2 * w + G[5] * (-2 * x) + G[6] * (-2 * y) + G[7] * (2 * x) + G[8] * 2 * w;
+    float gx = G[0] * 2 * x + G[1] * (2 * y) + G[2] * (2 * z) + G[3] * (2 * y) + G[4] * (-2 * x) + G[5] * (-2 * w) + G[6] * (2 * z) + G[7] * (2 * w) + G[8] * (-2 * x);
+    float gy = G[0] * (-2 * y) + G[1] * (2 * x) + G[2] * (2 * w) + G[3] * (2 * x) + G[4] * (2 * y) + G[5] * (2 * z) + G[6] * (-2 * w) + G[7] * (2 * z) + G[8] * (-2 * y);
+    float gz = G[0] * (-2 * z) + G[1] * (-2 * w) + G[2] * (2 * x) + G[3] * (2 * w) + G[4] * (-2 * z) + G[5] * (2 * y) + G[6] * (2 * x) + G[7] * (2 * y) + G[8] * (2 * z);
+    float dot = gw * w + gx * x + gy * y + gz * z;
+    g[3] += (gx - x * dot) / nrm;
+    g[4] += (gy - y * dot) / nrm;
+    g[5] += (gz - z * dot) / nrm;
+  }
+}
+
+__global__ void __launch_bounds__(256) warp_photo_fwd_kernel(const float* __restrict__ tgt, const float* __restrict__ ref,
+                                                             const float* __restrict__ depth, const float* __restrict__ pose,
+                                                             int pose_stride, const float* __restrict__ K,
+                                                             const float* __restrict__ Kinv, const float* __restrict__ mask,
+                                                             long long mask_bs, int h, int w, int rot_mode, int pad_mode, int align,
+                                                             float* warped, float inv_count, float* loss, int32_t* nanflag) {
+  __shared__ PoseMats m;
+  const int b = blockIdx.y;
+  if (threadIdx.x == 0) build_pose(pose + (long long)b * pose_stride, K + 9 * b, Kinv + 9 * b, rot_mode, m);
+  __syncthreads();
+  const long long hw = (long long)h * w;
+  const float* tb = tgt + 3 * hw * b;
+  const float* rb = ref + 3 * hw * b;
+  float s = 0.f;
+  bool bad = false;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < hw; i += gridDim.x * blockDim.x) {
+    int v = i / w, u = i % w;
+    WarpPix p;
+    warp_pixel(m, u, v, depth[hw * b + i], h, w, pad_mode, align, p);
+    float val[3];
+    bil_fetch<3, false>(rb, hw, h, w, p, val, nullptr, nullptr);
+    if (warped) { warped[3 * hw * b + i] = val[0]; warped[3 * hw * b + hw + i] = val[1]; warped[3 * hw * b + 2 * hw + i] = val[2]; }
+    float oob = (val[0] == 0.f && val[1] == 0.f && val[2] == 0.f) ? 0.f : 1.f;
+    float mk = mask ? mask[mask_bs * b + i] : 1.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float e = (tb[c * hw + i] - val[c]) * oob;
+      if (mask) e *= mk;
+      s += fabsf(e);
+      bad |= (e != e);
+    }
+  }
+  s = block_sum(s);
+  if (threadIdx.x == 0) atomicAdd(loss, s * inv_count);
+  if (bad && nanflag) atomicOr(nanflag, 1);
+}
+
+__global__ void __launch_bounds__(256) warp_photo_bwd_kernel(const float* __restrict__ tgt, const float* __restrict__ ref,
+                                                             const float* __restrict__ depth, const float* __restrict__ pose,
+                                                             int pose_stride, const float* __restrict__ K,
+                                                             const float* __restrict__ Kinv, const float* __restrict__ mask,
+                                                             long long mask_bs, int h, int w, int rot_mode, int pad_mode, int align,
+                                                             float inv_count, const float* __restrict__ gout, float* __restrict__ gdepth,
+                                                             float* ws, float* gmask, long long gmask_bs) {
+  __shared__ PoseMats m;
+  const int b = blockIdx.y;
+  if (threadIdx.x == 0) build_pose(pose + (long long)b * pose_stride, K + 9 * b, Kinv + 9 * b, rot_mode, m);
+  __syncthreads();
+  const long long hw = (long long)h * w;
+  const float* tb = tgt + 3 * hw * b;
+  const float* rb = ref + 3 * hw * b;
+  const float go = gout[0] * inv_count;
+  float acc12[12];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) acc12[i] = 0.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < hw; i += gridDim.x * blockDim.x) {
+    int v = i / w, u = i % w;
+    WarpPix p;
+    warp_pixel(m, u, v, depth[hw * b + i], h, w, pad_mode, align, p);
+    float val[3], dvx[3], dvy[3];
+    bil_fetch<3, true>(rb, hw, h, w, p, val, dvx, dvy);
+    float oob = (val[0] == 0.f && val[1] == 0.f && val[2] == 0.f) ? 0.f : 1.f;
+    float mk = mask ? mask[mask_bs * b + i] : 1.f;
+    float gix = 0.f, giy = 0.f, gm = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float e0 = (tb[c * hw + i] - val[c]) * oob;
+      float e = mask ? e0 * mk : e0;
+      float sg = sgn(e) * go;          // dL/de
+      gm += sg * e0;
+      float gW = -sg * oob * (mask ? mk : 1.f);
+      gix += gW * dvx[c];
+      giy += gW * dvy[c];
+    }
+    float gd;
+    warp_chain(m, p, h, w, gix, giy, gd, acc12);
+    gdepth[hw * b + i] = gd;
+    if (gmask) gmask[gmask_bs * b + i] = gm;
+  }
+  block_reduce12(acc12, ws + 12 * b);
+}
+
+template <int CMAX>
+__global__ void __launch_bounds__(256) inverse_warp_fwd_kernel(const float* __restrict__ img, const float* __restrict__ depth,
+                                                               const float* __restrict__ pose, const float* __restrict__ K,
+                                                               const float* __restrict__ Kinv, int C, int h, int w, int rot_mode,
+                                                               int pad_mode, int align, float* __restrict__ out) {
+  __shared__ PoseMats m;
+  const int b = blockIdx.y;
+  if (threadIdx.x == 0) build_pose(pose + 6 * b, K + 9 * b, Kinv + 9 * b, rot_mode, m);
+  __syncthreads();
+  const long long hw = (long long)h * w;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < hw; i += gridDim.x * blockDim.x) {
+    WarpPix p;
+    warp_pixel(m, i % w, i / w, depth[hw * b + i], h, w, pad_mode, align, p);
+    for (int c = 0; c < C; ++c) {
+      float val[1];
+      bil_fetch<1, false>(img + ((long long)b * C + c) * hw, hw, h, w, p, val, nullptr, nullptr);
+      out[((long long)b * C + c) * hw + i] = val[0];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) inverse_warp_bwd_kernel(const float* __restrict__ img, const float* __restrict__ depth,
+                                                               const float* __restrict__ pose, const float* __restrict__ K,
+                                                               const float* __restrict__ Kinv, int C, int h, int w, int rot_mode,
+                                                               int pad_mode, int align, const float* __restrict__ gout, float* gimg,
+                                                               float* __restrict__ gdepth, float* ws) {
+  __shared__ PoseMats m;
+  const int b = blockIdx.y;
+  if (threadIdx.x == 0) build_pose(pose + 6 * b, K + 9 * b, Kinv + 9 * b, rot_mode, m);
+  __syncthreads();
+  const long long hw = (long long)h * w;
+  float acc12[12];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) acc12[i] = 0.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < hw; i += gridDim.x * blockDim.x) {
+    WarpPix p;
+    warp_pixel(m, i % w, i / w, depth[hw * b + i], h, w, pad_mode, align, p);
+    float gix = 0.f, giy = 0.f;
+    const int x0 = p.x0, y0 = p.y0, x1 = x0 + 1, y1 = y0 + 1;
+    const bool bx0 = x0 >= 0 && x0 < w, bx1 = x1 >= 0 && x1 < w, by0 = y0 >= 0 && y0 < h, by1 = y1 >= 0 && y1 < h;
+    for (int c = 0; c < C; ++c) {
+      float val[1], dvx[1], dvy[1];
+      const long long base = ((long long)b * C + c) * hw;
+      bil_fetch<1, true>(img + base, hw, h, w, p, val, dvx, dvy);
+      float g = gout[base + i];
+      gix += g * dvx[0];
+      giy += g * dvy[0];
+      if (gimg) {
+        if (bx0 && by0) atomicAdd(gimg + base + y0 * w + x0, g * p.wx0 * p.wy0);
+        if (bx1 && by0) atomicAdd(gimg + base + y0 * w + x1, g * p.wx1 * p.wy0);
+        if (bx0 && by1) atomicAdd(gimg + base + y1 * w + x0, g * p.wx0 * p.wy1);
+        if (bx1 && by1) atomicAdd(gimg + base + y1 * w + x1, g * p.wx1 * p.wy1);
+      }
+    }
+    float gd;
+    warp_chain(m, p, h, w, gix, giy, gd, acc12);
+    if (gdepth) gdepth[hw * b + i] = gd;
+  }
+  block_reduce12(acc12, ws + 12 * b);
+}
+
+}  // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+DN_EXPORT int dn_l1_fwd(const float* gt, const float* pred, int B, int HW, float max_depth, float* ws, float* loss, void* stream) {
+  if (!gt || !pred || !ws || !loss || B < 1 || HW < 1) return DN_E_ARG;
+  cudaStream_t st = dn_stream(stream);
+  cudaError_t e = cudaMemsetAsync(ws, 0, sizeof(float) * 2 * B, st);
+  if (e != cudaSuccess) return (int)e;
+  int bx = blocks_for(HW, 256 * 4);
+  int cap = dn_num_sms() * 4 / B; if (cap < 1) cap = 1;
+  if (bx > cap) bx = cap;
+  l1_fwd_kernel<<<dim3(bx, B), 256, 0, st>>>(gt, pred, HW, max_depth, ws);
+  DN_CHECK_LAUNCH();
+  l1_finalize_kernel<<<1, 1, 0, st>>>(ws, B, loss);
+  DN_CHECK_LAUNCH();
+  return 0;
+}
+
+DN_EXPORT int dn_l1_bwd(const float* gt, const float* pred, int B, int HW, float max_depth, const float* ws, const float* gout,
+                        float* gpred, void* stream) {
+  if (!gt || !pred || !ws || !gout || !gpred) return DN_E_ARG;
+  int bx = blocks_for(HW, 256 * 4);
+  int cap = dn_num_sms() * 4 / B; if (cap < 1) cap = 1;
+  if (bx > cap) bx = cap;
+  l1_bwd_kernel<<<dim3(bx, B), 256, 0, dn_stream(stream)>>>(gt, pred, HW, max_depth, ws, B, gout, gpred);
+  DN_CHECK_LAUNCH();
+  return 0;
+}
+
+static int grid_bx(int hw, int B) {
+  int bx = blocks_for(hw, 256);
+  int cap = dn_num_sms() * 8 / B; if (cap < 1) cap = 1;
+  if (bx > cap) bx = cap;
+  return bx;
+}
+
+DN_EXPORT int dn_smooth_fwd(const float* p, int B, int H, int W, float weight, float* loss, void* stream) {
+  if (!p || !loss || H < 3 || W < 3) return DN_E_ARG;
+  smooth_fwd_kernel<<<dim3(grid_bx(H * W, B), B), 256, 0, dn_stream(stream)>>>(p, H, W, smooth_coef(B, H, W, weight), loss);
+  DN_CHECK_LAUNCH();
+  return 0;
+}
+DN_EXPORT int dn_smooth_bwd(const float* p, int B, int H, int W, float weight, const float* gout, float* gp, void* stream) {
+  if (!p || !gout || !gp || H < 3 || W < 3) return DN_E_ARG;
+  smooth_bwd_kernel<<<dim3(grid_bx(H * W, B), B), 256, 0, dn_stream(stream)>>>(p, H, W, smooth_coef(B, H, W, weight), gout, gp);
+  DN_CHECK_LAUNCH();
+  return 0;
+}
+
+DN_EXPORT int dn_depth_errors(const float* gt, const float* pred, int B, int H, int W, float max_depth, int crop, int y1, int y2,
+                              int x1, int x2, const float* scale, int32_t* counters, double* sums, void* stream) {
+  if (!gt || !pred || !counters || !sums) return DN_E_ARG;
+  if (!crop) { y1 = 0; y2 = H; x1 = 0; x2 = W; }
+  depth_errors_kernel<<<dim3(grid_bx(H * W, B), B), 256, 0, dn_stream(stream)>>>(gt, pred, H, W, max_depth, y1, y2, x1, x2, scale, counters, sums);
+  DN_CHECK_LAUNCH();
+  return 0;
+}
+
+DN_EXPORT int dn_area_down(const float* src, int NC, int H, int W, int f, float* dst, void* stream) {
+  if (!src || !dst || f < 1 || H % f || W % f) return DN_E_ARG;
+  long long total = (long long)NC * (H / f) * (W / f);
+  area_down_kernel<<<blocks_for(total, 256, 16), 256, 0, dn_stream(stream)>>>(src, NC, H, W, f, dst);
+  DN_CHECK_LAUNCH();
+  return 0;
+}
+
+DN_EXPORT int dn_explain_fwd(const float* mask, int64_t n, float* loss, void* stream) {
+  if (!mask || !loss || n < 1) return DN_E_ARG;
+  explain_fwd_kernel<<<blocks_for(n, 1024), 256, 0, dn_stream(stream)>>>(mask, n, 1.f / (float)n, loss);
+  DN_CHECK_LAUNCH();
+  return 0;
+}
+DN_EXPORT int dn_explain_bwd(const float* mask, int64_t n, const float* gout, float* gmask, void* stream) {
+  if (!mask || !gout || !gmask || n < 1) return DN_E_ARG;
+  explain_bwd_kernel<<<blocks_for(n, 1024), 256, 0, dn_stream(stream)>>>(mask, n, 1.f / (float)n, gout, gmask);
+  DN_CHECK_LAUNCH();
+  return 0;
+}
+
+DN_EXPORT int dn_warp_photo_fwd(const float* tgt, const float* ref, const float* depth, const float* pose, int pose_stride,
+                                const float* K, const float* Kinv, const float* mask, int64_t mask_bstride, int B, int h, int w,
+                                int rot_mode, int pad_mode, int align_corners, float* warped, float* loss, int32_t* nanflag,
+                                void* stream) {
+  if (!tgt || !ref || !depth || !pose || !K || !Kinv || !loss || B < 1 || h < 2 || w < 2) return DN_E_ARG;
+  float inv = 1.f / ((float)B * 3.f * (float)h * (float)w);
+  warp_photo_fwd_kernel<<<dim3(grid_bx(h * w, B), B), 256, 0, dn_stream(stream)>>>(tgt, ref, depth, pose, pose_stride, K, Kinv, mask,
+                                                                                   mask_bstride, h, w, rot_mode, pad_mode,
+                                                                                   align_corners, warped, inv, loss, nanflag);
+  DN_CHECK_LAUNCH();
+  return 0;
+}
+
+DN_EXPORT int dn_warp_photo_bwd(const float* tgt, const float* ref, const float* depth, const float* pose, int pose_stride,
+                                const float* K, const float* Kinv, const float* mask, int64_t mask_bstride, int B, int h, int w,
+                                int rot_mode, int pad_mode, int align_corners, const float* gout, float* gdepth, float* gpose,
+                                float* gmask, int64_t gmask_bstride, float* ws, void* stream) {
+  if (!tgt || !ref || !depth || !pose || !K || !Kinv || !gout || !gdepth || !gpose || !ws) return DN_E_ARG;
+  cudaStream_t st = dn_stream(stream);
+  cudaError_t e = cudaMemsetAsync(ws, 0, sizeof(float) * 12 * B, st);
+  if (e != cudaSuccess) return (int)e;
+  float inv = 1.f / ((float)B * 3.f * (float)h * (float)w);
+  warp_photo_bwd_kernel<<<dim3(grid_bx(h * w, B), B), 256, 0, st>>>(tgt, ref, depth, pose, pose_stride, K, Kinv, mask, mask_bstride, h, w,
+                                                                    rot_mode, pad_mode, align_corners, inv, gout, gdepth, ws, gmask,
+                                                                    gmask_bstride);
+  DN_CHECK_LAUNCH();
+  pose_grad_finalize_kernel<<<(B + 63) / 64, 64, 0, st>>>(ws, pose, pose_stride, B, rot_mode, gpose);
+  DN_CHECK_LAUNCH();
+  return 0;
+}
+
+DN_EXPORT int dn_inverse_warp_fwd(const float* img, const float* depth, const float* pose, const float* K, const float* Kinv, int B,
+                                  int C, int h, int w, int rot_mode, int pad_mode, int align_corners, float* out, void* stream) {
+  if (!img || !depth || !pose || !K || !Kinv || !out || B < 1 || h < 2 || w < 2) return DN_E_ARG;
+  inverse_warp_fwd_kernel<1><<<dim3(grid_bx(h * w, B), B), 256, 0, dn_stream(stream)>>>(img, depth, pose, K, Kinv, C, h, w, rot_mode,
+                                                                                        pad_mode, align_corners, out);
+  DN_CHECK_LAUNCH();
+  return 0;
+}
+
+DN_EXPORT int dn_inverse_warp_bwd(const float* img, const float* depth, const float* pose, const float* K, const float* Kinv, int B,
+                                  int C, int h, int w, int rot_mode, int pad_mode, int align_corners, const float* gout, float* gimg,
+                                  float* gdepth, float* gpose, float* ws, void* stream) {
+  if (!img || !depth || !pose || !K || !Kinv || !gout || !ws) return DN_E_ARG;
+  cudaStream_t st = dn_stream(stream);
+  cudaError_t e = cudaMemsetAsync(ws, 0, sizeof(float) * 12 * B, st);
+  if (e != cudaSuccess) return (int)e;
+  inverse_warp_bwd_kernel<<<dim3(grid_bx(h * w, B), B), 256, 0, st>>>(img, depth, pose, K, Kinv, C, h, w, rot_mode, pad_mode,
+                                                                      align_corners, gout, gimg, gdepth, ws);
+  DN_CHECK_LAUNCH();
+  if (gpose) {
+    pose_grad_finalize_kernel<<<(B + 63) / 64, 64, 0, st>>>(ws, pose, 6, B, rot_mode, gpose);
+    DN_CHECK_LAUNCH();
+  }
+  return 0;
+}

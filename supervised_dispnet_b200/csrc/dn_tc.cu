@@ -1,0 +1,706 @@
+// tcgen05 / TMA / TMEM implicit-GEMM convolution kernels for sm_100a (backend 1 of dn_igemm_run / dn_wgrad_run).
+//
+//   igemm_tc_kernel : out[pixel][co] = sum_tap sum_ci in[pixel + tap][ci] * w[tap][co][ci]
+//       A (activations) is fetched by 4-D TMA boxes {64 ch, wb, hb, nb} straight from the NHWC view -- the tap shift is a
+//       coordinate offset and zero padding is TMA out-of-bounds fill, so there is no im2col buffer; B (packed weights) by 3-D
+//       TMA; both land in 128B-swizzled shared memory and feed tcgen05.mma (M=128, N<=256, K=16) with fp32 accumulators in
+//       TMEM.  Persistent CTAs (one per SM), 3 warp roles (TMA producer / MMA issuer / 4 epilogue warps), a multi-stage
+//       smem ring and two TMEM accumulator stages so the epilogue of tile i overlaps the main loop of tile i+1.
+//   wgrad_tc_kernel : dw[tap][cp][cq] += sum_pixel dy[pixel][cp] * x[pixel + tap][cq]
+//       both operands are "MN-major" (the reduction index = pixel is the row index of the TMA box), split-K over pixel
+//       tiles across CTAs, fp32 partial sums reduced with vector red.global.add.
+//
+// Forward nn.Conv2d (stride 1), the four output phases of nn.ConvTranspose2d, and the data gradients of both run on
+// igemm_tc_kernel with different tap tables / views; weight gradients of both on wgrad_tc_kernel.
+#include "dn_common.cuh"
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <string.h>
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)m) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* smem, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+          smem_u32(smem)),
+      "l"((uint64_t)m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* smem, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          smem_u32(smem)),
+      "l"((uint64_t)m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() { asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// shared-memory matrix descriptor, 128B swizzle (cute::UMMA::SmemDescriptor): start>>4 | LBO>>4 <<16 | SBO>>4 <<32 | version 1
+// <<46 | layout SWIZZLE_128B (2) << 61
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+constexpr int kMaxTcTaps = 16;
+constexpr int kRows = 128;          // pixels per tile = UMMA M
+constexpr int kChunk = 64;          // channels per K chunk = one 128-byte swizzled row
+
+struct TcTap { int16_t src, dh, dw, wt; };
+
+struct IgemmTcParams {
+  CUtensorMap tmA[DN_MAX_SRC];
+  CUtensorMap tmB;
+  TcTap taps[kMaxTcTaps];
+  int ntaps, nsrc;
+  int kchunks;        // ceil(Cin / 64)
+  int last_ksteps;    // UMMA_K steps in the last chunk (1..4)
+  int wb, hb, nb;     // pixel box (wb*hb*nb == 128)
+  int tilesW, tilesH, tilesN, ntile_n, num_tiles;
+  int stages;
+  uint32_t idesc;
+  dn_view out;
+  const float* bias;
+  int act, accumulate;
+  float out_scale;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(192, 1) igemm_tc_kernel(const __grid_constant__ IgemmTcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  constexpr uint32_t A_BYTES = kRows * 128;
+  constexpr uint32_t B_BYTES = BN * 128;
+  constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+  // carve: [stages x (A|B)] | barriers | tmem ptr | bias tile
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int stages = p.stages;
+  uint64_t* full_bar = (uint64_t*)(smem + (size_t)stages * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + stages;
+  uint64_t* tfull_bar = empty_bar + stages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_ptr = (uint32_t*)(tempty_bar + 2);
+  float* bias_s = (float*)(tmem_ptr + 2);   // [2][BN]
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.nsrc; ++s) tma_prefetch_desc(&p.tmA[s]);
+    tma_prefetch_desc(&p.tmB);
+    for (int s = 0; s < stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 128); }
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int k_iters = p.ntaps * p.kchunks;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int nt = tile % p.ntile_n;
+        int m = tile / p.ntile_n;
+        const int tw = m % p.tilesW; m /= p.tilesW;
+        const int th = m % p.tilesH;
+        const int tn = m / p.tilesH;
+        const int w0 = tw * p.wb, h0 = th * p.hb, n0 = tn * p.nb;
+        for (int t = 0; t < p.ntaps; ++t) {
+          const TcTap tap = p.taps[t];
+          for (int kc = 0; kc < p.kchunks; ++kc) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = smem + (size_t)stage * STAGE_BYTES;
+            uint8_t* sb = sa + A_BYTES;
+            mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+            tma_load_4d(sa, &p.tmA[tap.src], &full_bar[stage], kc * kChunk, w0 + tap.dw, h0 + tap.dh, n0);
+            tma_load_3d(sb, &p.tmB, &full_bar[stage], kc * kChunk, nt * BN, tap.wt);
+            if (++stage == stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int it = 0; it < k_iters; ++it) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + (size_t)stage * STAGE_BYTES);
+          const uint32_t sb = sa + A_BYTES;
+          const int ks = ((it % p.kchunks) == p.kchunks - 1) ? p.last_ksteps : 4;
+          for (int k = 0; k < ks; ++k) {
+            const uint64_t ad = make_desc(sa + k * 32, 16, 1024);
+            const uint64_t bd = make_desc(sb + k * 32, 16, 1024);
+            umma_f16(d_tmem, ad, bd, p.idesc, (it > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (it == k_iters - 1) umma_commit(&tfull_bar[acc]);
+          if (++stage == stages) { stage = 0; phase ^= 1; }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ================= epilogue warps (2..5): TMEM -> registers -> bias/act -> HBM =================
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;          // tile row = TMEM lane = pixel within the box
+    const int et = threadIdx.x - 64;        // 0..127
+    int acc = 0; uint32_t acc_phase = 0;
+    const int wi = row % p.wb;
+    const int hi = (row / p.wb) % p.hb;
+    const int ni = row / (p.wb * p.hb);
+    const int esz = p.out.dtype == DN_F32 ? 4 : 2;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int nt = tile % p.ntile_n;
+      int m = tile / p.ntile_n;
+      const int tw = m % p.tilesW; m /= p.tilesW;
+      const int th = m % p.tilesH;
+      const int tn = m / p.tilesH;
+      const int w = tw * p.wb + wi, h = th * p.hb + hi, n = tn * p.nb + ni;
+      const bool valid = (w < p.out.W) && (h < p.out.H) && (n < p.out.N);
+      const int co0 = nt * BN;
+      float* bs = bias_s + acc * BN;
+      for (int c = et; c < BN; c += 128) bs[c] = (p.bias && co0 + c < p.out.C) ? p.bias[co0 + c] : 0.f;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+      uint8_t* optr = (uint8_t*)p.out.ptr + (size_t)(dn_off(p.out, n, h, w) + co0) * esz;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld16(taddr + c0, r);
+        tmem_ld_wait();
+        if (valid && co0 + c0 < p.out.C) {
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = dn_act(__uint_as_float(r[j]) * p.out_scale + bs[c0 + j], p.act);
+          if (p.out.dtype == DN_F16) {
+            __half* o = (__half*)optr + c0;
+            if (p.accumulate) {
+              float a[8];
+              Vec8<__half>::load(o, a);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] += a[j];
+              Vec8<__half>::load(o + 8, a);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[8 + j] += a[j];
+            }
+            Vec8<__half>::store(o, v);
+            Vec8<__half>::store(o + 8, v + 8);
+          } else {
+            __nv_bfloat16* o = (__nv_bfloat16*)optr + c0;
+            if (p.accumulate) {
+              float a[8];
+              Vec8<__nv_bfloat16>::load(o, a);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] += a[j];
+              Vec8<__nv_bfloat16>::load(o + 8, a);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[8 + j] += a[j];
+            }
+            Vec8<__nv_bfloat16>::store(o, v);
+            Vec8<__nv_bfloat16>::store(o + 8, v + 8);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight gradient
+// ------------------------------------------------------------------------------------------------
+struct WgradTcParams {
+  CUtensorMap tmP[DN_MAX_SRC];
+  CUtensorMap tmQ;
+  TcTap taps[kMaxTcTaps];
+  int ntaps;
+  int wb, hb, nb;          // pixel box, wb*hb*nb == KPX
+  int tilesW, tilesH, tilesN, num_ptiles;
+  int cp_tiles, cq_tiles;  // output tiles: 128 x BNQ
+  int cp_blocks;           // 64-channel blocks of P actually present in a cp tile (1 or 2)
+  int splits, ptiles_per_split;
+  int stages;
+  uint32_t idesc;
+  float* dw;
+  int cp, cq, cp_pad, cq_pad;
+  float scale;
+};
+
+constexpr int KPX = 64;   // pixels (= GEMM K) per pipeline stage
+
+template <int BNQ>
+__global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant__ WgradTcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  constexpr uint32_t BLK_BYTES = KPX * 128;              // one [KPX px][64 ch] swizzled block
+  constexpr uint32_t A_BYTES = 2 * BLK_BYTES;            // M = 128 channels of P
+  constexpr uint32_t B_BYTES = (BNQ / 64) * BLK_BYTES;
+  constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr uint32_t TMEM_COLS = BNQ <= 32 ? 32 : BNQ <= 64 ? 64 : BNQ <= 128 ? 128 : 256;
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int stages = p.stages;
+  uint64_t* full_bar = (uint64_t*)(smem + (size_t)stages * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + stages;
+  uint64_t* done_bar = empty_bar + stages;
+  uint32_t* tmem_ptr = (uint32_t*)(done_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // work item: (tap, cp tile, cq tile, split)
+  int item = blockIdx.x;
+  const int split = item % p.splits; item /= p.splits;
+  const int cqt = item % p.cq_tiles; item /= p.cq_tiles;
+  const int cpt = item % p.cp_tiles; item /= p.cp_tiles;
+  const TcTap tap = p.taps[item];
+  const int pt_beg = split * p.ptiles_per_split;
+  int pt_end = pt_beg + p.ptiles_per_split;
+  if (pt_end > p.num_ptiles) pt_end = p.num_ptiles;
+  const int n_iters = pt_end - pt_beg;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmP[tap.src]);
+    tma_prefetch_desc(&p.tmQ);
+    for (int s = 0; s < stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(done_bar, 1);
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  // bytes that really arrive per stage: only the P blocks that exist are loaded
+  const uint32_t tx_bytes = (uint32_t)p.cp_blocks * BLK_BYTES + B_BYTES;
+
+  if (n_iters > 0) {
+    if (warp == 0) {
+      if (lane == 0) {
+        int stage = 0; uint32_t phase = 0;
+        for (int pt = pt_beg; pt < pt_end; ++pt) {
+          int m = pt;
+          const int tw = m % p.tilesW; m /= p.tilesW;
+          const int th = m % p.tilesH;
+          const int tn = m / p.tilesH;
+          const int w0 = tw * p.wb, h0 = th * p.hb, n0 = tn * p.nb;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + (size_t)stage * STAGE_BYTES;
+          uint8_t* sb = sa + A_BYTES;
+          mbar_expect_tx(&full_bar[stage], tx_bytes);
+          for (int j = 0; j < p.cp_blocks; ++j)
+            tma_load_4d(sa + j * BLK_BYTES, &p.tmP[tap.src], &full_bar[stage], cpt * 128 + j * 64, w0, h0, n0);
+#pragma unroll
+          for (int j = 0; j < BNQ / 64; ++j)
+            tma_load_4d(sb + j * BLK_BYTES, &p.tmQ, &full_bar[stage], cqt * BNQ + j * 64, w0 + tap.dw, h0 + tap.dh, n0);
+          if (++stage == stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        int stage = 0; uint32_t phase = 0;
+        for (int it = 0; it < n_iters; ++it) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + (size_t)stage * STAGE_BYTES);
+          const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+          for (int k = 0; k < KPX / 16; ++k) {
+            // MN-major, 128B swizzle: LBO = distance between 64-channel blocks, SBO = 8 pixel rows = 1024 B
+            const uint64_t ad = make_desc(sa + k * 2048, BLK_BYTES, 1024);
+            const uint64_t bd = make_desc(sb + k * 2048, BLK_BYTES, 1024);
+            umma_f16(tmem_base, ad, bd, p.idesc, (it > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (it == n_iters - 1) umma_commit(done_bar);
+          if (++stage == stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    } else {
+      const int q = warp & 3;
+      const int row = q * 32 + lane;        // cp within the tile
+      const int cp = cpt * 128 + row;
+      mbar_wait(done_bar, 0);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+      float* drow = p.dw + ((size_t)tap.wt * p.cp_pad + cp) * p.cq_pad + cqt * BNQ;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BNQ; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld16(taddr + c0, r);
+        tmem_ld_wait();
+        if (cp < p.cp && cqt * BNQ + c0 < p.cq_pad) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4)
+            red_add_v4(drow + c0 + j, __uint_as_float(r[j]) * p.scale, __uint_as_float(r[j + 1]) * p.scale,
+                       __uint_as_float(r[j + 2]) * p.scale, __uint_as_float(r[j + 3]) * p.scale);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (!fn) {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (PFN_cuTensorMapEncodeTiled_v12000)f;
+  }
+  return fn;
+}
+
+bool view_tma_ok(const dn_view& v) {
+  if (v.dtype != DN_F16 && v.dtype != DN_BF16) return false;
+  if (((uintptr_t)v.ptr % 16) != 0) return false;
+  if ((v.sW % 8) || (v.sH % 8) || (v.sN % 8)) return false;
+  if (v.sW <= 0 || v.sH <= 0 || v.sN <= 0) return false;
+  return true;
+}
+
+// 4-D map (C, W, H, N) of an NHWC view, box {64, wb, hb, nb}, 128B swizzle, zero OOB fill
+int make_view_map(CUtensorMap* tm, const dn_view& v, int wb, int hb, int nb) {
+  auto enc = get_encode();
+  if (!enc) return DN_E_UNSUPPORTED;
+  cuuint64_t dims[4] = {(cuuint64_t)v.C, (cuuint64_t)v.W, (cuuint64_t)v.H, (cuuint64_t)v.N};
+  cuuint64_t strides[3] = {(cuuint64_t)v.sW * 2, (cuuint64_t)v.sH * 2, (cuuint64_t)v.sN * 2};
+  cuuint32_t box[4] = {(cuuint32_t)kChunk, (cuuint32_t)wb, (cuuint32_t)hb, (cuuint32_t)nb};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUtensorMapDataType dt = v.dtype == DN_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  CUresult r = enc(tm, dt, 4, v.ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : DN_E_ARG;
+}
+
+// choose a pixel box with wb*hb*nb == rows that minimises the number of tiles
+void choose_box(int N, int H, int W, int rows, int& wb, int& hb, int& nb) {
+  long long best = -1;
+  wb = rows; hb = 1; nb = 1;
+  for (int a = 1; a <= rows; a <<= 1)
+    for (int b = 1; a * b <= rows; b <<= 1) {
+      int c = rows / (a * b);
+      long long tiles = (long long)((W + a - 1) / a) * ((H + b - 1) / b) * ((N + c - 1) / c);
+      if (best < 0 || tiles < best || (tiles == best && a > wb)) { best = tiles; wb = a; hb = b; nb = c; }
+    }
+}
+
+uint32_t make_idesc(int a_dtype, int b_dtype, int a_mn_major, int b_mn_major, int M, int N) {
+  uint32_t d = 0;
+  d |= 1u << 4;                                         // D format f32
+  d |= (uint32_t)(a_dtype == DN_BF16 ? 1 : 0) << 7;     // A format
+  d |= (uint32_t)(b_dtype == DN_BF16 ? 1 : 0) << 10;    // B format
+  d |= (uint32_t)(a_mn_major ? 1 : 0) << 15;
+  d |= (uint32_t)(b_mn_major ? 1 : 0) << 16;
+  d |= (uint32_t)(N >> 3) << 17;
+  d |= (uint32_t)(M >> 4) << 24;
+  return d;
+}
+
+int pick_bn(int cout_pad) {
+  if (cout_pad >= 256) return 256;
+  if (cout_pad > 64) return 128;
+  if (cout_pad > 32) return 64;
+  if (cout_pad > 16) return 32;
+  return 16;
+}
+
+template <int BN>
+int launch_igemm(const IgemmTcParams& P, cudaStream_t st) {
+  constexpr uint32_t STAGE_BYTES = kRows * 128 + BN * 128;
+  int stages = P.stages;
+  size_t smem = (size_t)stages * STAGE_BYTES + 1024 + (2 * stages + 4) * 8 + 16 + 2 * BN * 4;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(igemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  int grid = P.num_tiles < dn_num_sms() ? P.num_tiles : dn_num_sms();
+  igemm_tc_kernel<BN><<<grid, 192, smem, st>>>(P);
+  DN_CHECK_LAUNCH();
+  return 0;
+}
+
+template <int BNQ>
+int launch_wgrad(const WgradTcParams& P, int items, cudaStream_t st) {
+  constexpr uint32_t STAGE_BYTES = 2 * KPX * 128 + (BNQ / 64) * KPX * 128;
+  size_t smem = (size_t)P.stages * STAGE_BYTES + 1024 + (2 * P.stages + 1) * 8 + 16;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<BNQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  wgrad_tc_kernel<BNQ><<<items, 192, smem, st>>>(P);
+  DN_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // namespace
+
+DN_EXPORT int dn_tc_available(void) {
+  static int cached = -1;
+  if (cached < 0) {
+    int dev = 0, major = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    cached = (major == 10 && get_encode() != nullptr) ? 1 : 0;
+  }
+  return cached;
+}
+
+DN_EXPORT int dn_igemm_tc_supported(const dn_igemm* p) {
+  if (!p || p->stride != 1 || p->ntaps > kMaxTcTaps || p->ntaps < 1) return 0;
+  if (p->w_dtype != DN_F16 && p->w_dtype != DN_BF16) return 0;
+  if (p->out.dtype != DN_F16 && p->out.dtype != DN_BF16) return 0;
+  if (!view_tma_ok(p->out) || (p->out.C % 16) != 0) return 0;
+  if ((p->cin_pad % 64) != 0 || (p->cout_pad % 16) != 0 || ((uintptr_t)p->w % 16) != 0) return 0;
+  for (int s = 0; s < p->nsrc; ++s) {
+    if (!view_tma_ok(p->in[s]) || p->in[s].dtype != p->w_dtype) return 0;
+    if (p->in[s].C != p->in[0].C) return 0;
+  }
+  int bn = pick_bn(p->cout_pad);
+  if (p->cout_pad % bn != 0 && p->cout_pad > bn) return 0;
+  return 1;
+}
+
+int dn_igemm_tc(const dn_igemm* p, cudaStream_t st) {
+  IgemmTcParams P;
+  memset(&P, 0, sizeof(P));
+  const int BN = pick_bn(p->cout_pad);
+  choose_box(p->out.N, p->out.H, p->out.W, kRows, P.wb, P.hb, P.nb);
+  for (int s = 0; s < p->nsrc; ++s) {
+    int e = make_view_map(&P.tmA[s], p->in[s], P.wb, P.hb, P.nb);
+    if (e) return e;
+  }
+  {
+    auto enc = get_encode();
+    if (!enc) return DN_E_UNSUPPORTED;
+    int nw = 0;
+    for (int t = 0; t < p->ntaps; ++t) nw = p->taps[t].wt + 1 > nw ? p->taps[t].wt + 1 : nw;
+    cuuint64_t dims[3] = {(cuuint64_t)p->cin_pad, (cuuint64_t)p->cout_pad, (cuuint64_t)nw};
+    cuuint64_t strides[2] = {(cuuint64_t)p->cin_pad * 2, (cuuint64_t)p->cin_pad * p->cout_pad * 2};
+    cuuint32_t box[3] = {(cuuint32_t)kChunk, (cuuint32_t)BN, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUtensorMapDataType dt = p->w_dtype == DN_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    CUresult r = enc(&P.tmB, dt, 3, (void*)p->w, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return DN_E_ARG;
+  }
+  for (int t = 0; t < p->ntaps; ++t) {
+    P.taps[t].src = (int16_t)p->taps[t].src; P.taps[t].dh = (int16_t)p->taps[t].dh;
+    P.taps[t].dw = (int16_t)p->taps[t].dw; P.taps[t].wt = (int16_t)p->taps[t].wt;
+  }
+  P.ntaps = p->ntaps;
+  P.nsrc = p->nsrc;
+  const int Cin = p->in[0].C;
+  P.kchunks = (Cin + kChunk - 1) / kChunk;
+  int rem = Cin - (P.kchunks - 1) * kChunk;
+  P.last_ksteps = (rem + 15) / 16;
+  P.tilesW = (p->out.W + P.wb - 1) / P.wb;
+  P.tilesH = (p->out.H + P.hb - 1) / P.hb;
+  P.tilesN = (p->out.N + P.nb - 1) / P.nb;
+  P.ntile_n = (p->cout_pad + BN - 1) / BN;
+  P.num_tiles = P.tilesW * P.tilesH * P.tilesN * P.ntile_n;
+  const uint32_t stage_bytes = kRows * 128 + BN * 128;
+  P.stages = (int)((200 * 1024) / stage_bytes);
+  if (P.stages > 8) P.stages = 8;
+  P.idesc = make_idesc(p->in[0].dtype, p->w_dtype, 0, 0, 128, BN);
+  P.out = p->out;
+  P.bias = p->bias;
+  P.act = p->act;
+  P.accumulate = p->accumulate;
+  P.out_scale = p->out_scale;
+  switch (BN) {
+    case 256: return launch_igemm<256>(P, st);
+    case 128: return launch_igemm<128>(P, st);
+    case 64: return launch_igemm<64>(P, st);
+    case 32: return launch_igemm<32>(P, st);
+    default: return launch_igemm<16>(P, st);
+  }
+}
+
+DN_EXPORT int dn_wgrad_tc_supported(const dn_wgrad* p) {
+  if (!p || p->stride != 1 || p->ntaps > kMaxTcTaps || p->ntaps < 1) return 0;
+  if (!view_tma_ok(p->q)) return 0;
+  for (int s = 0; s < p->nsrc; ++s)
+    if (!view_tma_ok(p->p[s])) return 0;
+  if ((p->cq_pad % 64) != 0 || (p->cp_pad % 8) != 0 || ((uintptr_t)p->dw % 16) != 0) return 0;
+  if ((p->p[0].C % 8) != 0 || (p->q.C % 8) != 0) return 0;
+  return 1;
+}
+
+int dn_wgrad_tc(const dn_wgrad* p, cudaStream_t st) {
+  WgradTcParams P;
+  memset(&P, 0, sizeof(P));
+  const dn_view& P0 = p->p[0];
+  choose_box(P0.N, P0.H, P0.W, KPX, P.wb, P.hb, P.nb);
+  for (int s = 0; s < p->nsrc; ++s) {
+    int e = make_view_map(&P.tmP[s], p->p[s], P.wb, P.hb, P.nb);
+    if (e) return e;
+  }
+  {
+    int e = make_view_map(&P.tmQ, p->q, P.wb, P.hb, P.nb);
+    if (e) return e;
+  }
+  for (int t = 0; t < p->ntaps; ++t) {
+    P.taps[t].src = (int16_t)p->taps[t].src; P.taps[t].dh = (int16_t)p->taps[t].dh;
+    P.taps[t].dw = (int16_t)p->taps[t].dw; P.taps[t].wt = (int16_t)p->taps[t].wt;
+  }
+  P.ntaps = p->ntaps;
+  P.tilesW = (P0.W + P.wb - 1) / P.wb;
+  P.tilesH = (P0.H + P.hb - 1) / P.hb;
+  P.tilesN = (P0.N + P.nb - 1) / P.nb;
+  P.num_ptiles = P.tilesW * P.tilesH * P.tilesN;
+  const int BNQ = p->cq_pad >= 256 ? 256 : (p->cq_pad >= 128 ? 128 : 64);
+  P.cp_tiles = (P0.C + 127) / 128;
+  P.cq_tiles = (p->cq_pad + BNQ - 1) / BNQ;
+  P.cp_blocks = P0.C > 64 ? 2 : 1;
+  const int out_tiles = P.ntaps * P.cp_tiles * P.cq_tiles;
+  int splits = (2 * dn_num_sms() + out_tiles - 1) / out_tiles;
+  if (splits > P.num_ptiles) splits = P.num_ptiles;
+  if (splits < 1) splits = 1;
+  P.ptiles_per_split = (P.num_ptiles + splits - 1) / splits;
+  P.splits = (P.num_ptiles + P.ptiles_per_split - 1) / P.ptiles_per_split;
+  const uint32_t stage_bytes = 2 * KPX * 128 + (BNQ / 64) * KPX * 128;
+  P.stages = (int)((200 * 1024) / stage_bytes);
+  if (P.stages > 8) P.stages = 8;
+  P.idesc = make_idesc(P0.dtype, p->q.dtype, 1, 1, 128, BNQ);
+  P.dw = p->dw;
+  P.cp = P0.C; P.cq = p->q.C; P.cp_pad = p->cp_pad; P.cq_pad = p->cq_pad;
+  P.scale = p->scale;
+  const int items = out_tiles * P.splits;
+  switch (BNQ) {
+    case 256: return launch_wgrad<256>(P, items, st);
+    case 128: return launch_wgrad<128>(P, items, st);
+    default: return launch_wgrad<64>(P, items, st);
+  }
+}
