@@ -195,7 +195,8 @@ int dn_area_down(const float* src, int NC, int H, int W, int f, float* dst, void
  * pose_stride; K, Kinv [B,3,3] already scaled for this pyramid level; mask [B,h,w] with batch stride or NULL.
  * rot_mode 0 euler / 1 quat; pad_mode 0 zeros / 1 border; align_corners 0/1.
  * fwd: loss[0] += sum|diff| / (B*3*h*w); nanflag[0] |= 1 if any diff is NaN; optionally writes `warped`.
- * bwd: gdepth [B,h,w] (overwritten), gpose [B,6] (+=, batch stride pose_stride), gmask [B,h,w] (overwritten).
+ * bwd: gdepth [B,h,w] (+=, caller zeroes; summed over reference frames), gpose [B,6] (+=, batch stride pose_stride),
+ *      gmask [B,h,w] (overwritten).
  */
 int dn_warp_photo_fwd(const float* tgt, const float* ref, const float* depth, const float* pose, int pose_stride,
                       const float* K, const float* Kinv, const float* mask, int64_t mask_bstride, int B, int h,

@@ -1,0 +1,140 @@
+"""ctypes binding of libdispnet_b200.so (the C ABI declared in include/dispnet_b200.h).
+
+The product path has no CPU or PyTorch fallback: if the shared library is missing or a call fails, this
+module raises.  PyTorch is used by the callers only for device memory, streams and autograd glue.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libdispnet_b200.so')
+
+DN_F32, DN_F16, DN_BF16 = 0, 1, 2
+ACT_NONE, ACT_RELU, ACT_LRELU = 0, 1, 2
+MAX_TAPS, MAX_SRC = 49, 4
+
+
+class DnView(C.Structure):
+    _fields_ = [('ptr', C.c_void_p), ('dtype', C.c_int32), ('N', C.c_int32), ('H', C.c_int32), ('W', C.c_int32),
+                ('C', C.c_int32), ('sN', C.c_int64), ('sH', C.c_int64), ('sW', C.c_int64)]
+
+
+class DnTap(C.Structure):
+    _fields_ = [('src', C.c_int32), ('dh', C.c_int32), ('dw', C.c_int32), ('wt', C.c_int32)]
+
+
+class DnIgemm(C.Structure):
+    _fields_ = [('inp', DnView * MAX_SRC), ('nsrc', C.c_int32), ('out', DnView), ('w', C.c_void_p),
+                ('w_dtype', C.c_int32), ('cin_pad', C.c_int32), ('cout_pad', C.c_int32), ('bias', C.c_void_p),
+                ('act', C.c_int32), ('accumulate', C.c_int32), ('stride', C.c_int32), ('ntaps', C.c_int32),
+                ('taps', DnTap * MAX_TAPS), ('out_scale', C.c_float)]
+
+
+class DnWgrad(C.Structure):
+    _fields_ = [('p', DnView * MAX_SRC), ('nsrc', C.c_int32), ('q', DnView), ('dw', C.c_void_p),
+                ('cp_pad', C.c_int32), ('cq_pad', C.c_int32), ('stride', C.c_int32), ('ntaps', C.c_int32),
+                ('taps', DnTap * MAX_TAPS), ('scale', C.c_float)]
+
+
+_P = C.c_void_p
+_I = C.c_int
+_I64 = C.c_int64
+_F = C.c_float
+_D = C.c_double
+_V = C.POINTER(DnView)
+_IP = C.POINTER(C.c_int32)
+
+_SIGS = {
+    'dn_version': ([], _I),
+    'dn_tc_available': ([], _I),
+    'dn_pack_input': ([_P, _I, _I, _I, _I, _V, _I, _P], _I),
+    'dn_pack_weight': ([_P, _P, _I, _I, _I, _I, _I, _I, _IP, _IP, _I64, _I64, _I64, _I64, _P], _I),
+    'dn_unpack_wgrad': ([_P, _P, _I, _I, _I, _I, _I, _IP, _IP, _I64, _I64, _I64, _I64, _F, _P], _I),
+    'dn_igemm_run': ([C.POINTER(DnIgemm), _I, _P], _I),
+    'dn_wgrad_run': ([C.POINTER(DnWgrad), _I, _P], _I),
+    'dn_igemm_tc_supported': ([C.POINTER(DnIgemm)], _I),
+    'dn_wgrad_tc_supported': ([C.POINTER(DnWgrad)], _I),
+    'dn_bn_stats': ([_V, _P, _P], _I),
+    'dn_bn_finalize': ([_P, _D, _P, _P, _P, _P, _F, _F, _I, _I, _P, _P, _I, _P], _I),
+    'dn_bn_apply': ([_V, _P, _V, _I, _I, _V, _P], _I),
+    'dn_bn_bwd_reduce': ([_V, _V, _V, _P, _P, _P, _I, _I, _P, _P], _I),
+    'dn_bn_bwd_apply': ([_V, _V, _V, _P, _P, _P, _I, _I, _P, _D, _F, _P, _P, _V, _V, _I, _P], _I),
+    'dn_act_bwd': ([_V, _V, _I, _P, _F, _P], _I),
+    'dn_maxpool_fwd': ([_V, _V, _I, _I, _I, _P], _I),
+    'dn_maxpool_bwd': ([_V, _V, _V, _I, _I, _I, _I, _P], _I),
+    'dn_add_act_fwd': ([_V, _V, _I, _V, _P], _I),
+    'dn_add_act_bwd': ([_V, _V, _I, _V, _I, _V, _I, _P], _I),
+    'dn_act_fwd': ([_V, _I, _V, _P], _I),
+    'dn_copy_view': ([_V, _V, _I, _P], _I),
+    'dn_head_fwd': ([_V, _F, _F, _P, _V, _I, _P], _I),
+    'dn_head_bwd': ([_P, _V, _I, _V, _F, _F, _V, _P], _I),
+    'dn_sigmoid_nchw_fwd': ([_V, _P, _P], _I),
+    'dn_sigmoid_nchw_bwd': ([_P, _P, _F, _V, _P], _I),
+    'dn_spatial_mean_fwd': ([_V, _F, _P, _P], _I),
+    'dn_spatial_mean_bwd': ([_P, _F, _V, _P], _I),
+    'dn_l1_fwd': ([_P, _P, _I, _I, _F, _P, _P, _P], _I),
+    'dn_l1_bwd': ([_P, _P, _I, _I, _F, _P, _P, _P, _P], _I),
+    'dn_smooth_fwd': ([_P, _I, _I, _I, _F, _P, _P], _I),
+    'dn_smooth_bwd': ([_P, _I, _I, _I, _F, _P, _P, _P], _I),
+    'dn_depth_errors': ([_P, _P, _I, _I, _I, _F, _I, _I, _I, _I, _I, _P, _P, _P, _P], _I),
+    'dn_area_down': ([_P, _I, _I, _I, _I, _P, _P], _I),
+    'dn_warp_photo_fwd': ([_P, _P, _P, _P, _I, _P, _P, _P, _I64, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P], _I),
+    'dn_warp_photo_bwd': ([_P, _P, _P, _P, _I, _P, _P, _P, _I64, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _I64, _P,
+                           _P], _I),
+    'dn_inverse_warp_fwd': ([_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P], _I),
+    'dn_inverse_warp_bwd': ([_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P], _I),
+    'dn_explain_fwd': ([_P, _I64, _P, _P], _I),
+    'dn_explain_bwd': ([_P, _I64, _P, _P, _P], _I),
+    'dn_fill_f32': ([_P, _I64, _F, _P], _I),
+    'dn_axpy_f32': ([_P, _F, _P, _I64, _P], _I),
+}
+
+EXPORTS = tuple(sorted(list(_SIGS) + ['dn_error_string']))
+
+_lib = None
+
+
+def lib():
+    """Load (once) and return the shared library; raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                'libdispnet_b200.so is missing (%s): build it with `python -c "import __graft_entry__ as g; '
+                'g.build()"` or `make -C supervised_dispnet_b200/csrc`. There is no CPU / PyTorch fallback.' % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        for name, (args, res) in _SIGS.items():
+            f = getattr(L, name)
+            f.argtypes = args
+            f.restype = res
+        L.dn_error_string.argtypes = [_I]
+        L.dn_error_string.restype = C.c_char_p
+        _lib = L
+    return _lib
+
+
+def check(code, what=''):
+    if code != 0:
+        msg = lib().dn_error_string(code).decode()
+        raise RuntimeError('dispnet_b200 %s failed: %s (code %d)' % (what, msg, code))
+
+
+def call(name, *args):
+    check(getattr(lib(), name)(*args), name)
+
+
+def stream_ptr():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (or None)."""
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError('dispnet_b200: tensors must live on a CUDA device (got %s); the CUDA extension is the '
+                               'only implementation of this path' % t.device)

@@ -525,7 +525,7 @@ __global__ void __launch_bounds__(256) warp_photo_bwd_kernel(const float* __rest
     }
     float gd;
     warp_chain(m, p, h, w, gix, giy, gd, acc12);
-    gdepth[hw * b + i] = gd;
+    gdepth[hw * b + i] += gd;   // accumulated over reference frames; caller zeroes
     if (gmask) gmask[gmask_bs * b + i] = gm;
   }
   block_reduce12(acc12, ws + 12 * b);

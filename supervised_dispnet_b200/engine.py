@@ -1,0 +1,646 @@
+"""Host-side layer engine: static per-shape execution plans over NHWC views, driving the C-ABI kernels.
+
+This is tensor plumbing only -- every arithmetic step is a call into libdispnet_b200.so.  A `Plan` is built
+once per (network, input shape, mode); it owns the activation / gradient arenas in HBM (sized for the
+180 GB part: nothing is re-materialised), the packed-weight workspaces and the ordered op list.  Concatenation
+(`torch.cat` in the reference decoders) never happens: producers write straight into channel slices of the
+consumer's buffer, transposed convolutions write 2x2 phase sub-lattices, crops are views.
+
+Gradient flow mirrors the reference's autograd graph: ops run in reverse order; the first writer of a gradient
+region overwrites, later writers accumulate (decided statically at plan-build time).
+"""
+import ctypes as C
+import os
+
+import torch
+
+from . import _lib as L
+
+_DT = {torch.float32: L.DN_F32, torch.float16: L.DN_F16, torch.bfloat16: L.DN_BF16}
+
+
+def _ru(x, m):
+    return (x + m - 1) // m * m
+
+
+class Precision:
+    """Storage / compute types of a plan.  'fp32': CUDA-core kernels, fp32 everywhere (exact-parity mode).
+    'fp16': fp16 activations and weights, gradient activations in `grad` dtype (scaled by `gscale` when
+    fp16), fp32 accumulation everywhere, tcgen05 kernels where the problem shape allows."""
+
+    def __init__(self, name):
+        self.name = name
+        if name == 'fp32':
+            self.act, self.grad, self.gscale = torch.float32, torch.float32, 1.0
+        elif name == 'fp16':
+            self.act, self.grad, self.gscale = torch.float16, torch.float16, 4096.0
+        elif name == 'fp16_bf16grad':
+            self.act, self.grad, self.gscale = torch.float16, torch.bfloat16, 1.0
+        elif name == 'bf16':
+            self.act, self.grad, self.gscale = torch.bfloat16, torch.bfloat16, 1.0
+        else:
+            raise ValueError('unknown precision %r' % name)
+
+
+def default_precision():
+    return os.environ.get('DISPNET_B200_PRECISION', 'fp16')
+
+
+def tc_enabled():
+    return os.environ.get('DISPNET_B200_BACKEND', 'auto') != 'generic' and L.lib().dn_tc_available() == 1
+
+
+class Buf:
+    """NHWC storage with channel pitch rounded to 8 elements (16-byte pixel alignment for TMA / vector access)."""
+
+    def __init__(self, N, H, W, Cc, dtype, device, zero=True):
+        self.N, self.H, self.W, self.C = N, H, W, Cc
+        self.Cp = _ru(Cc, 8)
+        self.dtype = dtype
+        f = torch.zeros if zero else torch.empty
+        self.t = f((N, H, W, self.Cp), dtype=dtype, device=device)
+        self.grad = None
+        self.written = []      # channel intervals of .grad already written during the backward walk (plan time)
+
+    def view(self):
+        return View(self, 0, self.C, self.H, self.W, 0, self.W * self.Cp, self.Cp)
+
+    def grad_buf(self, gdtype):
+        if self.grad is None:
+            self.grad = Buf(self.N, self.H, self.W, self.C, gdtype, self.t.device)
+        return self.grad
+
+
+class View:
+    """Channel slice / phase sub-lattice / crop of a Buf (element strides; channel stride 1)."""
+
+    def __init__(self, buf, c0, Cc, H, W, off, sH, sW):
+        self.buf, self.c0, self.C, self.H, self.W = buf, c0, Cc, H, W
+        self.off, self.sH, self.sW = off, sH, sW
+        self.N = buf.N
+        self.sN = buf.H * buf.W * buf.Cp
+        self._dn = None
+
+    def channels(self, c0, Cc):
+        assert c0 + Cc <= self.C
+        return View(self.buf, self.c0 + c0, Cc, self.H, self.W, self.off, self.sH, self.sW)
+
+    def crop(self, H, W):
+        assert H <= self.H and W <= self.W
+        return View(self.buf, self.c0, self.C, H, W, self.off, self.sH, self.sW)
+
+    def phase(self, a, b):
+        H = (self.H - a + 1) // 2
+        W = (self.W - b + 1) // 2
+        return View(self.buf, self.c0, self.C, H, W, self.off + a * self.sH + b * self.sW, 2 * self.sH, 2 * self.sW)
+
+    def dn(self):
+        if self._dn is None:
+            es = self.buf.t.element_size()
+            self._dn = L.DnView(self.buf.t.data_ptr() + (self.off + self.c0) * es, _DT[self.buf.dtype], self.N, self.H,
+                                self.W, self.C, self.sN, self.sH, self.sW)
+        return self._dn
+
+    def ref(self):
+        return C.byref(self.dn())
+
+    def grad_view(self, gdtype):
+        g = self.buf.grad_buf(gdtype)
+        return View(g, self.c0, self.C, self.H, self.W, self.off, self.sH, self.sW)
+
+    # ---- plan-time gradient bookkeeping: returns True if a write to this region must accumulate
+    def claim_grad_write(self):
+        lo, hi = self.c0, self.c0 + self.C
+        w = self.buf.written
+        covered = any(a <= lo and hi <= b for a, b in w)
+        partial = any(a < hi and lo < b for a, b in w)
+        if not covered:
+            if partial:
+                raise RuntimeError('partially overlapping gradient writes are not supported')
+            w.append((lo, hi))
+        return covered
+
+    def to_nchw(self):
+        """Debug helper: NCHW fp32 copy of the view."""
+        t = self.buf.t.view(-1)
+        idx_n = torch.arange(self.N, device=t.device).view(-1, 1, 1, 1) * self.sN
+        idx_h = torch.arange(self.H, device=t.device).view(1, -1, 1, 1) * self.sH
+        idx_w = torch.arange(self.W, device=t.device).view(1, 1, -1, 1) * self.sW
+        idx_c = torch.arange(self.C, device=t.device).view(1, 1, 1, -1)
+        return t[idx_n + idx_h + idx_w + idx_c + self.off + self.c0].permute(0, 3, 1, 2).float().contiguous()
+
+
+def _i32arr(vals):
+    return (C.c_int32 * len(vals))(*vals)
+
+
+def _backend(kind, prob):
+    if not tc_enabled():
+        return 0
+    fn = L.lib().dn_igemm_tc_supported if kind == 'igemm' else L.lib().dn_wgrad_tc_supported
+    return 1 if fn(C.byref(prob)) == 1 else 0
+
+
+def _mk_igemm(ins, out, w, w_dtype, cin_pad, cout_pad, bias, act, accumulate, stride, taps, out_scale=1.0):
+    p = L.DnIgemm()
+    for i, v in enumerate(ins):
+        p.inp[i] = v.dn()
+    p.nsrc = len(ins)
+    p.out = out.dn()
+    p.w = w.data_ptr()
+    p.w_dtype = _DT[w_dtype]
+    p.cin_pad, p.cout_pad = cin_pad, cout_pad
+    p.bias = bias
+    p.act, p.accumulate, p.stride = act, int(accumulate), stride
+    p.ntaps = len(taps)
+    for i, (s, dh, dw, wt) in enumerate(taps):
+        p.taps[i] = L.DnTap(s, dh, dw, wt)
+    p.out_scale = out_scale
+    return p
+
+
+def _mk_wgrad(ps, q, dw, cp_pad, cq_pad, stride, taps, scale):
+    p = L.DnWgrad()
+    for i, v in enumerate(ps):
+        p.p[i] = v.dn()
+    p.nsrc = len(ps)
+    p.q = q.dn()
+    p.dw = dw.data_ptr()
+    p.cp_pad, p.cq_pad, p.stride = cp_pad, cq_pad, stride
+    p.ntaps = len(taps)
+    for i, (s, dh, dw_, wt) in enumerate(taps):
+        p.taps[i] = L.DnTap(s, dh, dw_, wt)
+    p.scale = scale
+    return p
+
+
+class Op:
+    def fwd(self, plan):
+        raise NotImplementedError
+
+    def plan_bwd(self, plan):
+        pass
+
+    def bwd(self, plan):
+        pass
+
+
+class InputOp(Op):
+    """NCHW fp32 input tensor(s) -> channel slices of one NHWC buffer (replaces torch.cat of PoseExpNet inputs)."""
+
+    def __init__(self, plan, shapes):
+        N, _, H, W = shapes[0]
+        self.chans = [s[1] for s in shapes]
+        self.buf = Buf(N, H, W, sum(self.chans), plan.prec.act, plan.device)
+        self.out = self.buf.view()
+
+    def fwd(self, plan):
+        c0 = 0
+        for x, c in zip(plan.inputs, self.chans):
+            L.call('dn_pack_input', L.ptr(x), x.shape[0], c, x.shape[2], x.shape[3], self.out.ref(), c0, plan.stream)
+            c0 += c
+
+
+class ConvOp(Op):
+    """nn.Conv2d (any k / stride / pad) or nn.ConvTranspose2d (stride 2), with fused bias + activation."""
+
+    def __init__(self, plan, name, x, out, k, stride=1, pad=None, transposed=False, bias=True, act=L.ACT_NONE,
+                 needs_dx=True):
+        self.name, self.x, self.out = name, x, out
+        self.k, self.stride, self.transposed, self.act = k, stride, transposed, act
+        self.pad = (k - 1) // 2 if pad is None else pad
+        self.needs_dx = needs_dx
+        self.Cin, self.Cout = x.C, out.C
+        self.has_bias = bias
+        self.cin_pad, self.cout_pad = _ru(self.Cin, 64), _ru(self.Cout, 16)
+        self.cinT_pad, self.coutT_pad = _ru(self.Cin, 16), _ru(self.Cout, 64)   # dgrad roles swapped
+        T = k * k
+        dev = plan.device
+        self.wp = torch.zeros((T, self.cout_pad, self.cin_pad), dtype=plan.prec.act, device=dev)
+        self.kh = _i32arr([t // k for t in range(T)])
+        self.kw = _i32arr([t % k for t in range(T)])
+        # source strides of the torch parameter seen as [co][ci][kh][kw]
+        if transposed:      # nn.ConvTranspose2d weight is [Cin, Cout, k, k]
+            self.s_co, self.s_ci = T, self.Cout * T
+        else:
+            self.s_co, self.s_ci = self.Cin * T, T
+        # ---- forward problems
+        self.fwd_probs = []
+        if not transposed:
+            taps = [(0, kh - self.pad, kw - self.pad, kh * k + kw) for kh in range(k) for kw in range(k)]
+            self.fwd_probs.append(dict(ins=[x], out=out, taps=taps, stride=stride))
+        else:
+            assert stride == 2
+            for a in range(2):
+                for b in range(2):
+                    ov = out.phase(a, b)
+                    if ov.H == 0 or ov.W == 0:
+                        continue
+                    taps = [(0, (a + self.pad - kh) // 2, (b + self.pad - kw) // 2, kh * k + kw)
+                            for kh in range(k) if (a + self.pad - kh) % 2 == 0
+                            for kw in range(k) if (b + self.pad - kw) % 2 == 0]
+                    self.fwd_probs.append(dict(ins=[x], out=ov, taps=taps, stride=1, phase=(a, b)))
+        self._fwd_built = None
+        plan.register_param(name + '.weight')
+        if bias:
+            plan.register_param(name + '.bias')
+
+    def _build_fwd(self, plan):
+        built = []
+        for pr in self.fwd_probs:
+            p = _mk_igemm(pr['ins'], pr['out'], self.wp, plan.prec.act, self.cin_pad, self.cout_pad, None, self.act, False,
+                          pr['stride'], pr['taps'])
+            built.append((p, _backend('igemm', p)))
+        return built
+
+    def fwd(self, plan):
+        W = plan.param(self.name + '.weight')
+        T = self.k * self.k
+        L.call('dn_pack_weight', L.ptr(W), L.ptr(self.wp), _DT[plan.prec.act], T, self.Cout, self.Cin, self.cout_pad,
+               self.cin_pad, self.kh, self.kw, self.s_co, self.s_ci, self.k, 1, plan.stream)
+        if self._fwd_built is None:
+            self._fwd_built = self._build_fwd(plan)
+        b = plan.param(self.name + '.bias') if self.has_bias else None
+        for p, be in self._fwd_built:
+            p.bias = b.data_ptr() if b is not None else None
+            L.call('dn_igemm_run', C.byref(p), be, plan.stream)
+
+    def plan_bwd(self, plan):
+        g = plan.prec.grad
+        T = self.k * self.k
+        dev = plan.device
+        self.gout = self.out.grad_view(g)
+        self.dwp = torch.zeros((T, self.cout_pad, self.cin_pad), dtype=torch.float32, device=dev)
+        k, pad = self.k, self.pad
+        # ---- weight-gradient problems
+        self.wg = []
+        if not self.transposed:
+            taps = [(0, kh - pad, kw - pad, kh * k + kw) for kh in range(k) for kw in range(k)]
+            self.wg.append(_mk_wgrad([self.gout], self.x, self.dwp, self.cout_pad, self.cin_pad, self.stride, taps, 1.0))
+        else:
+            for pr in self.fwd_probs:
+                a, b = pr['phase']
+                self.wg.append(_mk_wgrad([self.gout.phase(a, b)], self.x, self.dwp, self.cout_pad, self.cin_pad, 1,
+                                         pr['taps'], 1.0))
+        self.wg = [(p, _backend('wgrad', p)) for p in self.wg]
+        # ---- data-gradient problems
+        self.dg = []
+        if self.needs_dx:
+            self.wpT = torch.zeros((T, self.cinT_pad, self.coutT_pad), dtype=g, device=dev)
+            gx = self.x.grad_view(g)
+            acc = gx.claim_grad_write()
+            self.dx_zero_first = None
+            if not self.transposed and self.stride == 1:
+                taps = [(0, pad - kh, pad - kw, kh * k + kw) for kh in range(k) for kw in range(k)]
+                probs = [dict(ins=[self.gout], out=gx, taps=taps)]
+            elif not self.transposed:
+                assert self.stride == 2
+                probs = []
+                for a in range(2):
+                    for b in range(2):
+                        gv = gx.phase(a, b)
+                        if gv.H == 0 or gv.W == 0:
+                            continue
+                        taps = [(0, (a + pad - kh) // 2, (b + pad - kw) // 2, kh * k + kw)
+                                for kh in range(k) if (a + pad - kh) % 2 == 0
+                                for kw in range(k) if (b + pad - kw) % 2 == 0]
+                        if taps:
+                            probs.append(dict(ins=[self.gout], out=gv, taps=taps))
+                        elif not acc:
+                            self.dx_zero_first = gx
+            else:
+                ins, taps = [], []
+                for pr in self.fwd_probs:
+                    a, b = pr['phase']
+                    ins.append(self.gout.phase(a, b))
+                    taps += [(len(ins) - 1, -dh, -dw, wt) for (_, dh, dw, wt) in pr['taps']]
+                probs = [dict(ins=ins, out=gx, taps=taps)]
+            for pr in probs:
+                p = _mk_igemm(pr['ins'], pr['out'], self.wpT, g, self.coutT_pad, self.cinT_pad, None, L.ACT_NONE, acc, 1,
+                              pr['taps'])
+                self.dg.append((p, _backend('igemm', p)))
+
+    def bwd(self, plan):
+        W = plan.param(self.name + '.weight')
+        T = self.k * self.k
+        inv = 1.0 / plan.prec.gscale
+        gb = plan.grad_of(self.name + '.bias') if self.has_bias else None
+        if self.act != L.ACT_NONE or gb is not None:
+            L.call('dn_act_bwd', self.gout.ref(), self.out.ref(), self.act, L.ptr(gb), inv, plan.stream)
+        self.dwp.zero_()
+        for p, be in self.wg:
+            L.call('dn_wgrad_run', C.byref(p), be, plan.stream)
+        gw = plan.grad_of(self.name + '.weight')
+        L.call('dn_unpack_wgrad', L.ptr(self.dwp), L.ptr(gw), T, self.Cout, self.Cin, self.cout_pad, self.cin_pad, self.kh,
+               self.kw, self.s_co, self.s_ci, self.k, 1, inv, plan.stream)
+        if self.needs_dx:
+            if self.dx_zero_first is not None:
+                self.dx_zero_first.buf.t.zero_()
+            # transposed role: rows = ci, cols = co
+            L.call('dn_pack_weight', L.ptr(W), L.ptr(self.wpT), _DT[plan.prec.grad], T, self.Cin, self.Cout, self.cinT_pad,
+                   self.coutT_pad, self.kh, self.kw, self.s_ci, self.s_co, self.k, 1, plan.stream)
+            for p, be in self.dg:
+                L.call('dn_igemm_run', C.byref(p), be, plan.stream)
+
+
+class BNOp(Op):
+    """nn.BatchNorm2d (+ residual add) + activation (+ MaxPool2d(2,2)).  `out=None`: statistics only (the dead bn1
+    of Disp_res_50, models/Disp_res_50.py:143-145, whose running buffers still update)."""
+
+    def __init__(self, plan, name, y, out, act=L.ACT_RELU, pool=False, residual=None):
+        self.name, self.y, self.out, self.act, self.pool, self.res = name, y, out, act, int(pool), residual
+        Cc = y.C
+        dev = plan.device
+        self.sums = torch.zeros(2 * Cc, dtype=torch.float64, device=dev)
+        self.red = torch.zeros(2 * Cc, dtype=torch.float64, device=dev)
+        self.mean_invstd = torch.zeros(2 * Cc, dtype=torch.float32, device=dev)
+        self.scale_shift = torch.zeros(2 * Cc, dtype=torch.float32, device=dev)
+        self.count = float(y.N * y.H * y.W)
+        if out is not None:
+            plan.register_param(name + '.weight')
+            plan.register_param(name + '.bias')
+
+    def fwd(self, plan):
+        st = plan.stream
+        g, b = plan.param(self.name + '.weight'), plan.param(self.name + '.bias')
+        rm, rv = plan.buffer(self.name + '.running_mean'), plan.buffer(self.name + '.running_var')
+        if plan.training:
+            self.sums.zero_()
+            L.call('dn_bn_stats', self.y.ref(), L.ptr(self.sums), st)
+            plan.buffer(self.name + '.num_batches_tracked').add_(1)
+        L.call('dn_bn_finalize', L.ptr(self.sums), self.count, L.ptr(g), L.ptr(b), L.ptr(rm), L.ptr(rv), 0.1, 1e-5,
+               int(plan.training), 1, L.ptr(self.mean_invstd), L.ptr(self.scale_shift), self.y.C, st)
+        if self.out is not None:
+            L.call('dn_bn_apply', self.y.ref(), L.ptr(self.scale_shift), self.res.ref() if self.res else None, self.act,
+                   self.pool, self.out.ref(), st)
+
+    def plan_bwd(self, plan):
+        if self.out is None:
+            return
+        g = plan.prec.grad
+        self.gout = self.out.grad_view(g)
+        self.gy = self.y.grad_view(g)
+        assert not self.gy.claim_grad_write(), 'conv output feeding BN must have a single consumer'
+        self.gres, self.gres_acc = None, 0
+        if self.res is not None:
+            self.gres = self.res.grad_view(g)
+            self.gres_acc = int(self.gres.claim_grad_write())
+
+    def bwd(self, plan):
+        if self.out is None:
+            return
+        st = plan.stream
+        gm, bt = plan.param(self.name + '.weight'), plan.param(self.name + '.bias')
+        self.red.zero_()
+        res = self.res.ref() if self.res else None
+        L.call('dn_bn_bwd_reduce', self.gout.ref(), self.y.ref(), res, L.ptr(self.mean_invstd), L.ptr(gm), L.ptr(bt),
+               self.act, self.pool, L.ptr(self.red), st)
+        L.call('dn_bn_bwd_apply', self.gout.ref(), self.y.ref(), res, L.ptr(self.mean_invstd), L.ptr(gm), L.ptr(bt),
+               self.act, self.pool, L.ptr(self.red), self.count, 1.0 / plan.prec.gscale,
+               L.ptr(plan.grad_of(self.name + '.weight')), L.ptr(plan.grad_of(self.name + '.bias')), self.gy.ref(),
+               self.gres.ref() if self.gres else None, self.gres_acc, st)
+
+
+class MaxPoolOp(Op):
+    def __init__(self, plan, x, out, k, stride, pad):
+        self.x, self.out, self.k, self.s, self.p = x, out, k, stride, pad
+
+    def fwd(self, plan):
+        L.call('dn_maxpool_fwd', self.x.ref(), self.out.ref(), self.k, self.s, self.p, plan.stream)
+
+    def plan_bwd(self, plan):
+        g = plan.prec.grad
+        self.gout = self.out.grad_view(g)
+        self.gx = self.x.grad_view(g)
+        self.acc = int(self.gx.claim_grad_write())
+
+    def bwd(self, plan):
+        L.call('dn_maxpool_bwd', self.gout.ref(), self.x.ref(), self.gx.ref(), self.k, self.s, self.p, self.acc, plan.stream)
+
+
+class ActOp(Op):
+    """out = act(x) as its own pass (Disp_res_50 relu1 = relu(conv1), models/Disp_res_50.py:145)."""
+
+    def __init__(self, plan, x, out, act, needs_dx=True):
+        self.x, self.out, self.act, self.needs_dx = x, out, act, needs_dx
+
+    def fwd(self, plan):
+        L.call('dn_act_fwd', self.x.ref(), self.act, self.out.ref(), plan.stream)
+
+    def plan_bwd(self, plan):
+        g = plan.prec.grad
+        self.gout = self.out.grad_view(g)
+        self.gx = self.x.grad_view(g)
+        self.acc = int(self.gx.claim_grad_write())
+
+    def bwd(self, plan):
+        L.call('dn_add_act_bwd', self.gout.ref(), self.out.ref(), self.act, self.gx.ref(), self.acc, None, 0, plan.stream)
+
+
+class HeadOp(Op):
+    """alpha * sigmoid(z) + beta -> fp32 NCHW output, plus the x2 up-sampled copy written into the next iconv's
+    input slot (models/Disp_vgg_BN.py:168-171 nearest; models/DispNetS.py:119-120 bilinear + crop_like)."""
+
+    def __init__(self, plan, z, alpha, beta, up=None, up_mode=0):
+        self.z, self.alpha, self.beta, self.up, self.up_mode = z, float(alpha), float(beta), up, up_mode
+        self.idx = plan.add_output((z.N, 1, z.H, z.W))
+
+    def fwd(self, plan):
+        out = plan.outputs[self.idx]
+        L.call('dn_head_fwd', self.z.ref(), self.alpha, self.beta, L.ptr(out), self.up.ref() if self.up else None,
+               self.up_mode, plan.stream)
+
+    def plan_bwd(self, plan):
+        g = plan.prec.grad
+        self.gz = self.z.grad_view(g)
+        assert not self.gz.claim_grad_write()
+        self.gup = self.up.grad_view(g) if self.up is not None else None
+
+    def bwd(self, plan):
+        go = plan.gouts[self.idx]
+        L.call('dn_head_bwd', L.ptr(go), self.gup.ref() if self.gup else None, self.up_mode, self.z.ref(), self.alpha,
+               plan.prec.gscale, self.gz.ref(), plan.stream)
+
+
+class SigmoidOutOp(Op):
+    """PoseExpNet explainability masks: sigmoid(conv) -> fp32 NCHW (models/PoseExpNet.py:82-85)."""
+
+    def __init__(self, plan, z):
+        self.z = z
+        self.idx = plan.add_output((z.N, z.C, z.H, z.W))
+
+    def fwd(self, plan):
+        L.call('dn_sigmoid_nchw_fwd', self.z.ref(), L.ptr(plan.outputs[self.idx]), plan.stream)
+
+    def plan_bwd(self, plan):
+        self.gz = self.z.grad_view(plan.prec.grad)
+        assert not self.gz.claim_grad_write()
+
+    def bwd(self, plan):
+        go = plan.gouts[self.idx]
+        L.call('dn_sigmoid_nchw_bwd', L.ptr(go), L.ptr(plan.saved_outputs[self.idx]), plan.prec.gscale, self.gz.ref(),
+               plan.stream)
+
+
+class MeanOutOp(Op):
+    """pose = scale * spatial mean of the 1x1 pose_pred conv (models/PoseExpNet.py:71-73) -> fp32 [N, C]."""
+
+    def __init__(self, plan, z, scale):
+        self.z, self.scale = z, float(scale)
+        self.idx = plan.add_output((z.N, z.C))
+
+    def fwd(self, plan):
+        L.call('dn_spatial_mean_fwd', self.z.ref(), self.scale, L.ptr(plan.outputs[self.idx]), plan.stream)
+
+    def plan_bwd(self, plan):
+        self.gz = self.z.grad_view(plan.prec.grad)
+        assert not self.gz.claim_grad_write()
+
+    def bwd(self, plan):
+        go = plan.gouts[self.idx]
+        if go is None:
+            self.gz.buf.t.zero_()
+            return
+        L.call('dn_spatial_mean_bwd', L.ptr(go), self.scale * plan.prec.gscale, self.gz.ref(), plan.stream)
+
+
+class Plan:
+    def __init__(self, module, device, precision, training):
+        self.module = module
+        self.device = device
+        self.prec = Precision(precision)
+        self.training = training
+        self.ops = []
+        self.param_names = []
+        self.out_shapes = []
+        self.outputs = []
+        self.saved_outputs = []
+        self.gouts = []
+        self.inputs = []
+        self._params = {}
+        self._grads = {}
+        self.stream = None
+        self._bwd_planned = False
+        self.generation = 0
+
+    # ---- construction
+    def add(self, op):
+        self.ops.append(op)
+        return op
+
+    def register_param(self, name):
+        if name not in self.param_names:
+            self.param_names.append(name)
+
+    def add_output(self, shape):
+        self.out_shapes.append(tuple(shape))
+        return len(self.out_shapes) - 1
+
+    def new_buf(self, N, H, W, Cc, dtype=None):
+        return Buf(N, H, W, Cc, dtype or self.prec.act, self.device)
+
+    # ---- run-time lookups
+    def param(self, name):
+        return self._params[name]
+
+    def buffer(self, name):
+        return self._params[name]
+
+    def grad_of(self, name):
+        return self._grads[name]
+
+    def bind(self, tensors):
+        self._params = tensors
+
+    def run_forward(self, inputs):
+        for x in inputs:
+            L.require_cuda(x)
+        self.inputs = [x.contiguous().float() for x in inputs]
+        self.stream = L.stream_ptr()
+        self.outputs = [torch.empty(s, dtype=torch.float32, device=self.device) for s in self.out_shapes]
+        for op in self.ops:
+            op.fwd(self)
+        self.saved_outputs = self.outputs
+        self.generation += 1
+        return tuple(self.outputs)
+
+    def plan_backward(self):
+        if self._bwd_planned:
+            return
+        for op in reversed(self.ops):
+            op.plan_bwd(self)
+        self._bwd_planned = True
+
+    def run_backward(self, gouts):
+        self.plan_backward()
+        self.stream = L.stream_ptr()
+        self.gouts = [None if g is None else g.contiguous().float() for g in gouts]
+        total = sum(self._params[n].numel() for n in self.param_names)
+        flat = torch.zeros(total, dtype=torch.float32, device=self.device)
+        self._grads, o = {}, 0
+        for n in self.param_names:
+            p = self._params[n]
+            self._grads[n] = flat[o:o + p.numel()].view(p.shape)
+            o += p.numel()
+        for op in reversed(self.ops):
+            op.bwd(self)
+        return self._grads
+
+
+class _NetFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, plan, n_inputs, *tensors):
+        inputs = tensors[:n_inputs]
+        outs = plan.run_forward(inputs)
+        ctx.plan = plan
+        ctx.generation = plan.generation
+        ctx.n_inputs = n_inputs
+        ctx.param_order = plan._fn_param_order
+        return outs
+
+    @staticmethod
+    def backward(ctx, *gouts):
+        plan = ctx.plan
+        if plan.generation != ctx.generation:
+            raise RuntimeError('dispnet_b200: backward() after a newer forward() of the same module/shape: the activation '
+                               'arena has been overwritten (run forward -> backward in lockstep, as train.py does)')
+        grads = plan.run_backward(gouts)
+        res = [None, None] + [None] * ctx.n_inputs
+        for name in ctx.param_order:
+            res.append(grads.get(name))
+        return tuple(res)
+
+
+class PlannedModule(torch.nn.Module):
+    """Base of the drop-in model classes: owns parameters/buffers with the reference's state_dict keys and runs
+    the forward through a cached Plan inside one autograd node."""
+
+    precision = None
+
+    def _build_plan(self, plan, shapes):
+        raise NotImplementedError
+
+    def _plan_for(self, inputs):
+        dev = inputs[0].device
+        prec = self.precision or default_precision()
+        key = (tuple(tuple(x.shape) for x in inputs), self.training, prec, str(dev))
+        plans = self.__dict__.setdefault('_plans', {})
+        if key not in plans:
+            plan = Plan(self, dev, prec, self.training)
+            with torch.no_grad():
+                self._build_plan(plan, [tuple(x.shape) for x in inputs])
+            plans[key] = plan
+        return plans[key]
+
+    def _run(self, inputs):
+        if not inputs[0].is_cuda:
+            raise RuntimeError('dispnet_b200 models run on CUDA only (no CPU fallback): move the module and inputs to a '
+                               'B200 device')
+        plan = self._plan_for(inputs)
+        named = dict(self.named_parameters())
+        tensors = dict(named)
+        tensors.update(dict(self.named_buffers()))
+        plan.bind(tensors)
+        order = [n for n in plan.param_names]
+        plan._fn_param_order = order
+        return _NetFn.apply(plan, len(inputs), *inputs, *[named[n] for n in order])

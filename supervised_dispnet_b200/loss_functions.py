@@ -1,0 +1,282 @@
+"""Drop-in `loss_functions` module (reference: loss_functions.py): same names, argument meaning and return
+types for the functions on the training hot path, each executed by fused CUDA kernels of libdispnet_b200.so.
+
+  l1_loss                           reference :104-129   one masked-reduce kernel (+ finalize), no host sync
+  photometric_reconstruction_loss   reference :317-354   area pyramid + one fused warp/photometric kernel per
+                                                          (scale, ref) pair, fused analytic backward
+  explainability_loss               reference :357-364
+  smooth_loss                       reference :367-386   one stencil+reduce kernel per scale
+  compute_errors                    reference :401-448   one kernel; integer counters bit-exact
+
+Losses are 0-dim CUDA tensors supporting .item(), arithmetic and .backward() exactly as train.py:488-521 uses
+them.  There is no CPU implementation: CPU tensors raise.
+"""
+import numpy as np
+import torch
+
+from . import _lib as L
+from .inverse_warp import _PAD, _ROT
+
+# the reference asserts `loss == loss` after every (scale, ref) pair (:342), a host sync each; here the NaN flag
+# is accumulated on the device and only read back when this is switched on.
+STRICT_NAN_CHECK = False
+ALIGN_CORNERS = False     # see inverse_warp.py docstring
+
+
+def _max_depth(datasets):
+    if datasets == 'kitti':
+        return 80.0
+    if datasets == 'nyu':
+        return 10.0
+    raise TypeError('undefined datasets')
+
+
+# ---------------------------------------------------------------------------------------------------------
+class _L1Fn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, gt, pred, maxd):
+        L.require_cuda(gt, pred)
+        gt, pred = gt.contiguous().float(), pred.contiguous().float()
+        B = pred.shape[0]
+        HW = pred[0].numel()
+        ws = torch.empty(2 * B, dtype=torch.float32, device=pred.device)
+        loss = torch.empty((), dtype=torch.float32, device=pred.device)
+        L.call('dn_l1_fwd', L.ptr(gt), L.ptr(pred), B, HW, maxd, L.ptr(ws), L.ptr(loss), L.stream_ptr())
+        ctx.save_for_backward(gt, pred, ws)
+        ctx.maxd = maxd
+        return loss
+
+    @staticmethod
+    def backward(ctx, gout):
+        gt, pred, ws = ctx.saved_tensors
+        B = pred.shape[0]
+        g = torch.empty_like(pred)
+        gout = gout.contiguous().float()
+        L.call('dn_l1_bwd', L.ptr(gt), L.ptr(pred), B, pred[0].numel(), ctx.maxd, L.ptr(ws), L.ptr(gout), L.ptr(g),
+               L.stream_ptr())
+        return None, g, None
+
+
+def l1_loss(gt_depth, depth, datasets):
+    """sum_b mean_{valid_b} |gt - clamp(pred, 1e-3, max)| / B, using depth[0][:, 0] only (reference :104-129)."""
+    maxd = _max_depth(datasets)
+    pred = depth[0][:, 0]
+    return _L1Fn.apply(gt_depth, pred, maxd)
+
+
+# ---------------------------------------------------------------------------------------------------------
+class _SmoothFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, *maps):
+        L.require_cuda(*maps)
+        maps = [m.contiguous().float() for m in maps]
+        loss = torch.zeros((), dtype=torch.float32, device=maps[0].device)
+        st = L.stream_ptr()
+        weight = 1.0
+        ctx.weights = []
+        for m in maps:
+            b, _, h, w = m.shape
+            L.call('dn_smooth_fwd', L.ptr(m), b * m.shape[1], h, w, weight, L.ptr(loss), st)
+            ctx.weights.append(weight)
+            weight /= 2.3
+        ctx.save_for_backward(*maps)
+        return loss
+
+    @staticmethod
+    def backward(ctx, gout):
+        gout = gout.contiguous().float()
+        st = L.stream_ptr()
+        grads = []
+        for m, wgt in zip(ctx.saved_tensors, ctx.weights):
+            g = torch.empty_like(m)
+            b, _, h, w = m.shape
+            L.call('dn_smooth_bwd', L.ptr(m), b * m.shape[1], h, w, wgt, L.ptr(gout), L.ptr(g), st)
+            grads.append(g)
+        return tuple(grads)
+
+
+def smooth_loss(pred_map):
+    """Second-order smoothness over the scale list, weights 1, 1/2.3, ... (reference :367-386)."""
+    if type(pred_map) not in [tuple, list]:
+        pred_map = [pred_map]
+    return _SmoothFn.apply(*pred_map)
+
+
+# ---------------------------------------------------------------------------------------------------------
+class _ExplainFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, *masks):
+        L.require_cuda(*masks)
+        masks = [m.contiguous().float() for m in masks]
+        loss = torch.zeros((), dtype=torch.float32, device=masks[0].device)
+        st = L.stream_ptr()
+        for m in masks:
+            L.call('dn_explain_fwd', L.ptr(m), m.numel(), L.ptr(loss), st)
+        ctx.save_for_backward(*masks)
+        return loss
+
+    @staticmethod
+    def backward(ctx, gout):
+        gout = gout.contiguous().float()
+        st = L.stream_ptr()
+        grads = []
+        for m in ctx.saved_tensors:
+            g = torch.empty_like(m)
+            L.call('dn_explain_bwd', L.ptr(m), m.numel(), L.ptr(gout), L.ptr(g), st)
+            grads.append(g)
+        return tuple(grads)
+
+
+def explainability_loss(mask):
+    """sum over scales of BCE(mask, 1) (reference :357-364)."""
+    if type(mask) not in [tuple, list]:
+        mask = [mask]
+    return _ExplainFn.apply(*mask)
+
+
+# ---------------------------------------------------------------------------------------------------------
+def _area_down(x, h, w):
+    B, Cc, H, W = x.shape
+    if (H, W) == (h, w):
+        return x
+    f = H // h
+    if f * h != H or W // w != f or f * w != W:
+        raise RuntimeError('photometric pyramid needs integer area ratios (got %dx%d -> %dx%d)' % (H, W, h, w))
+    out = torch.empty((B, Cc, h, w), dtype=torch.float32, device=x.device)
+    L.call('dn_area_down', L.ptr(x), B * Cc, H, W, f, L.ptr(out), L.stream_ptr())
+    return out
+
+
+class _PhotoFn(torch.autograd.Function):
+    """inputs: pose [B,R,6], then S depth maps [B,1,h,w], then S masks [B,R,h,w] (or absent)."""
+
+    @staticmethod
+    def forward(ctx, cfg, tgt, refs, K, Kinv, pose, *maps):
+        rot, pad, align, S, has_mask = cfg
+        depths = [d.contiguous().float() for d in maps[:S]]
+        masks = [m.contiguous().float() for m in maps[S:]] if has_mask else [None] * S
+        L.require_cuda(tgt, pose, K, Kinv, *depths)
+        tgt = tgt.contiguous().float()
+        refs = [r.contiguous().float() for r in refs]
+        pose = pose.contiguous().float()
+        K, Kinv = K.contiguous().float(), Kinv.contiguous().float()
+        B, _, H, W = tgt.shape
+        R = len(refs)
+        dev = tgt.device
+        st = L.stream_ptr()
+        loss = torch.zeros((), dtype=torch.float32, device=dev)
+        nanflag = torch.zeros(1, dtype=torch.int32, device=dev)
+        saved = []
+        for d, m in zip(depths, masks):
+            b, _, h, w = d.shape
+            downscale = H / h
+            tgt_s = _area_down(tgt, h, w)
+            refs_s = [_area_down(r, h, w) for r in refs]
+            Ks = torch.cat((K[:, 0:2] / downscale, K[:, 2:]), dim=1).contiguous()
+            Kis = torch.cat((Kinv[:, :, 0:2] * downscale, Kinv[:, :, 2:]), dim=2).contiguous()
+            for i, r in enumerate(refs_s):
+                mp = None if m is None else L.C.c_void_p(m.data_ptr() + 4 * i * h * w)
+                L.call('dn_warp_photo_fwd', L.ptr(tgt_s), L.ptr(r), L.ptr(d), L.C.c_void_p(pose.data_ptr() + 4 * 6 * i),
+                       6 * R, L.ptr(Ks), L.ptr(Kis), mp, R * h * w, B, h, w, rot, pad, align, None, L.ptr(loss),
+                       L.ptr(nanflag), st)
+            saved.append((tgt_s, refs_s, Ks, Kis))
+        if STRICT_NAN_CHECK:
+            assert int(nanflag.item()) == 0, 'photometric loss is NaN'
+        ctx.cfg = cfg
+        ctx.saved = (saved, depths, masks, pose)
+        ctx.nanflag = nanflag
+        return loss
+
+    @staticmethod
+    def backward(ctx, gout):
+        rot, pad, align, S, has_mask = ctx.cfg
+        saved, depths, masks, pose = ctx.saved
+        gout = gout.contiguous().float()
+        B, R = pose.shape[0], pose.shape[1]
+        dev = pose.device
+        st = L.stream_ptr()
+        gpose = torch.zeros_like(pose)
+        ws = torch.empty(12 * B, dtype=torch.float32, device=dev)
+        gdepths, gmasks = [], []
+        for (tgt_s, refs_s, Ks, Kis), d, m in zip(saved, depths, masks):
+            b, _, h, w = d.shape
+            gd = torch.zeros_like(d)
+            gm = torch.empty_like(m) if m is not None else None
+            for i, r in enumerate(refs_s):
+                mp = None if m is None else L.C.c_void_p(m.data_ptr() + 4 * i * h * w)
+                gmp = None if m is None else L.C.c_void_p(gm.data_ptr() + 4 * i * h * w)
+                L.call('dn_warp_photo_bwd', L.ptr(tgt_s), L.ptr(r), L.ptr(d), L.C.c_void_p(pose.data_ptr() + 4 * 6 * i),
+                       6 * R, L.ptr(Ks), L.ptr(Kis), mp, R * h * w, B, h, w, rot, pad, align, L.ptr(gout), L.ptr(gd),
+                       L.C.c_void_p(gpose.data_ptr() + 4 * 6 * i), gmp, R * h * w, L.ptr(ws), st)
+            gdepths.append(gd)
+            gmasks.append(gm)
+        res = [None, None, None, None, None, gpose] + gdepths
+        if has_mask:
+            res += gmasks
+        return tuple(res)
+
+
+def photometric_reconstruction_loss(tgt_img, ref_imgs, intrinsics, intrinsics_inv, depth, explainability_mask, pose,
+                                    rotation_mode='euler', padding_mode='zeros'):
+    """sum over scales and reference frames of mean |(tgt_s - warp(ref_s)) * in_view * mask| (reference :317-354)."""
+    if type(explainability_mask) not in [tuple, list]:
+        explainability_mask = [explainability_mask]
+    if type(depth) not in [list, tuple]:
+        depth = [depth]
+    assert (explainability_mask[0] is None) or (len(explainability_mask) == len(depth))
+    has_mask = explainability_mask[0] is not None
+    S = len(depth)
+    if not has_mask:
+        S = min(S, len(explainability_mask))       # zip() semantics of the reference loop (:352)
+    cfg = (_ROT[rotation_mode], _PAD[padding_mode], int(ALIGN_CORNERS), S, has_mask)
+    maps = list(depth[:S]) + (list(explainability_mask[:S]) if has_mask else [])
+    return _PhotoFn.apply(cfg, tgt_img, list(ref_imgs), intrinsics, intrinsics_inv, pose, *maps)
+
+
+# ---------------------------------------------------------------------------------------------------------
+def error_counters(gt, pred, dataset='kitti', crop=True, unsupervised=False):
+    """Raw per-sample results of the metric kernel: (counters int64 [B,4], sums float64 [B,5]) on the host.
+    counters = n_valid, n(thresh<1.25), n(<1.25^2), n(<1.25^3); these are the bit-exact integers of SURVEY 8(a9)."""
+    L.require_cuda(gt, pred)
+    gt, pred = gt.contiguous().float(), pred.contiguous().float()
+    B, H, W = gt.shape
+    if dataset == 'kitti':
+        if not crop:
+            raise UnboundLocalError("max_depth / crop_mask are unbound in the reference for dataset='kitti', crop=False "
+                                    "(loss_functions.py:411-420)")
+        maxd = 80.0
+        y1, y2 = int(0.40810811 * H), int(0.99189189 * H)
+        x1, x2 = int(0.03594771 * W), int(0.96405229 * W)
+        use_crop = 1
+    else:
+        maxd = 10.0
+        y1, y2, x1, x2 = 0, H, 0, W
+        use_crop = 0
+    scale = None
+    if unsupervised:
+        sc = []
+        for g, p in zip(gt, pred):
+            valid = (g > 0) & (g < maxd)
+            if use_crop:
+                cm = torch.zeros_like(valid)
+                cm[y1:y2, x1:x2] = True
+                valid = valid & cm
+            sc.append(torch.median(g[valid]) / torch.median(p[valid].clamp(1e-3, maxd)))
+        scale = torch.stack(sc).float().contiguous()
+    counters = torch.zeros((B, 4), dtype=torch.int32, device=gt.device)
+    sums = torch.zeros((B, 5), dtype=torch.float64, device=gt.device)
+    L.call('dn_depth_errors', L.ptr(gt), L.ptr(pred), B, H, W, maxd, use_crop, y1, y2, x1, x2, L.ptr(scale), L.ptr(counters),
+           L.ptr(sums), L.stream_ptr())
+    return counters.cpu().numpy().astype(np.int64), sums.cpu().numpy()
+
+
+@torch.no_grad()
+def compute_errors(gt, pred, dataset='kitti', crop=True, unsupervised=False):
+    """[abs_diff, abs_rel, sq_rel, rmse, rmse_log, a1, a2, a3], each summed over samples / B (reference :401-448)."""
+    cnt, s = error_counters(gt, pred, dataset, crop, unsupervised)
+    B = gt.size(0)
+    n = cnt[:, 0].astype(np.float64)
+    with np.errstate(divide='ignore', invalid='ignore'):
+        per = np.stack([s[:, 0] / n, s[:, 1] / n, s[:, 2] / n, np.sqrt(s[:, 3] / n), np.sqrt(s[:, 4] / n),
+                        cnt[:, 1] / n, cnt[:, 2] / n, cnt[:, 3] / n], 1)
+    return [float(v) / B for v in per.sum(0)]
