@@ -1,0 +1,304 @@
+#!/usr/bin/env python
+"""bench.py -- images/sec of the DispNet hot path (BASELINE.json configs[1]: Disp_vgg_BN + L1 depth loss, synthetic
+KITTI-shaped 128x416 batches, b=32 per GPU), one process per GPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is one pass of the hot path over one batch: disp_net forward -> 1/disp -> l1_loss + smooth_loss ->
+backward -> Adam (what train.train() does per batch, reference train.py:420-522).
+  value : steps timed with inputs already resident in HBM (CUDA events, max over ranks)
+  e2e   : the same metric through the public API `supervised_dispnet_b200.train.train()` with pinned HOST batches:
+          H2D copy of every batch and the D2H `loss.item()` of every step are inside the timed region
+  roofline : the tcgen05 gather-convolution kernel (forward + data-gradient launches), algorithmic FLOPs / device time
+          measured with CUDA events around every launch in a separate pass of the same step
+  cpu_baseline : the oracle port (oracle/nets.py + oracle/losses.py, torch CPU fp32) on this box's host cores
+--impl reference times that CPU implementation alone (bounded sample per step).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+
+import torch  # noqa: E402
+
+H, W, BATCH = 128, 416, 32
+TRAIN_GFLOP_PER_IMG = 110.7        # BASELINE.md section 3 (3 x forward MACs x 2), Disp_vgg_BN @ 128x416
+METRIC = 'images/sec (128x416, b=32/GPU)'
+
+
+def load_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d['hbm_gbs'], tf_burst=d['bf16_tflops'], tf_sust=d['bf16_tflops_sustained'], src='measured')
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src='fallback')
+
+
+def synth_batch(b, seed, pinned=False):
+    """images U(0,1) normalised to [-1,1]; KITTI-like sparse depth, ~5% valid, >=1 valid px in the crop."""
+    import _inputs as I
+    x = I.images(b, H, W, seed)
+    gt = I.sparse_gt(b, H, W, seed + 1, 'kitti', density=0.05)
+    if pinned:
+        x, gt = x.pin_memory(), gt.pin_memory()
+    return x, gt
+
+
+class ClockSampler(threading.Thread):
+    Q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                      '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
+                f = [s.strip() for s in out.strip().split(',')]
+                if len(f) >= 7:
+                    self.samples.append(f)
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.samples:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['unsampled'])
+        sm = sorted(float(s[0]) for s in self.samples)
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [n for i, n in enumerate(names) if any(s[3 + i].lower().startswith('active') for s in self.samples)]
+        return dict(sm_mhz=sm[len(sm) // 2], sm_max_mhz=float(self.samples[0][1]), reasons=reasons, samples=len(sm))
+
+
+# ------------------------------------------------------------------------------------------------------------
+# CPU arm: oracle port of the same step
+# ------------------------------------------------------------------------------------------------------------
+def cpu_step_fn():
+    from oracle import nets as ON, losses as OL
+    sd = ON.init_state_dict('Disp_vgg_BN', 0, skip_dead=True)
+    params = [v.requires_grad_(True) for k, v in sd.items() if v.dtype.is_floating_point and 'running' not in k]
+    opt = torch.optim.Adam(params, lr=2e-4, betas=(0.9, 0.999))
+
+    def step(x, gt):
+        disp = ON.disp_vgg_bn(sd, x, True)
+        depth = [1 / d for d in disp]
+        loss = 1.0 * OL.l1_loss(gt, depth, 'kitti') + 0.0 * OL.smooth_loss(depth)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        return float(loss)
+    return step
+
+
+def cpu_baseline(budget_s=20.0):
+    torch.set_num_threads(os.cpu_count() or 1)
+    step = cpu_step_fn()
+    x, gt = synth_batch(1, 100)
+    t0 = time.time()
+    step(x, gt)
+    t1 = time.time() - t0                      # one image incl. first-touch costs
+    b = int(max(1, min(BATCH, budget_s / max(t1, 1e-3) * 1.3)))
+    x, gt = synth_batch(b, 101)
+    t0 = time.time()
+    step(x, gt)
+    dt = time.time() - t0
+    return dict(value=b / dt, unit='images/sec', cores=torch.get_num_threads(), kind='port',
+                sample='1 step of the oracle port (torch CPU fp32: Disp_vgg_BN fwd + L1 + smooth + bwd + Adam) at b=%d, %dx%d, '
+                       'after a b=1 warm-up step' % (b, H, W))
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    torch.set_num_threads(os.cpu_count() or 1)
+    step = cpu_step_fn()
+    x, gt = synth_batch(1, 100)
+    t0 = time.time()
+    step(x, gt)
+    t1 = time.time() - t0
+    total = args.steps + args.warmup
+    b = int(max(1, min(BATCH, 150.0 / total / max(t1, 1e-3) * 1.3)))
+    x, gt = synth_batch(b, 101)
+    for _ in range(args.warmup):
+        step(x, gt)
+    t0 = time.time()
+    for _ in range(args.steps):
+        step(x, gt)
+    dt = time.time() - t0
+    v = args.steps * b / dt
+    line = dict(metric=METRIC, value=v, unit='images/sec', n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=1000 * dt / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32',
+                data='synthetic', impl='reference',
+                config=dict(workload='Disp_vgg_BN + L1 depth loss, synthetic KITTI 128x416', per_step_batch=b,
+                            note='reference CPU path (oracle port: the reference is pure PyTorch, no native code to compile); '
+                                 'each step is a bounded sample of b=%d images of the b=32 workload' % b),
+                cpu_baseline=dict(value=v, unit='images/sec', cores=torch.get_num_threads(), kind='port',
+                                  sample='%d steps at b=%d' % (args.steps, b)),
+                e2e=dict(value=v, unit='images/sec', h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    import supervised_dispnet_b200 as S
+    from supervised_dispnet_b200 import _lib as L, loss_functions as LF, train as T
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    if L.lib().dn_tc_available() != 1:
+        raise RuntimeError('tcgen05 path unavailable on this device; bench.py measures the sm_100a kernels only')
+
+    torch.manual_seed(0)
+    net = S.models.Disp_vgg_BN('kitti')
+    net.init_weights()
+    net = net.to(dev).train()
+    model = net
+    if world > 1:
+        model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local], broadcast_buffers=True,
+                                                          gradient_as_bucket_view=True)
+    params = [p for p in net.parameters() if p.requires_grad]
+    opt = torch.optim.Adam(params, lr=2e-4, betas=(0.9, 0.999), fused=True)
+
+    x_h, gt_h = synth_batch(BATCH, 10 + rank, pinned=True)
+    x_d, gt_d = x_h.to(dev), gt_h.to(dev)
+
+    def step(x, gt, m=None):
+        disp = (m or model)(x)
+        depth = [1 / d for d in disp]
+        loss = 1.0 * LF.l1_loss(gt, depth, 'kitti') + 0.0 * LF.smooth_loss(depth)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step(x_d, gt_d)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    calls0 = L.CALLS
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss = step(x_d, gt_d)
+    e1.record()
+    barrier()
+    calls = L.CALLS - calls0
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms)
+    last_loss = float(loss)
+
+    # ---- e2e: public API with host batches
+    targs = T.default_args(batch_size=BATCH, smooth_loss_weight=0.0)
+
+    class Loader:
+        def __iter__(self):
+            for _ in range(args.steps):
+                yield x_h, gt_h
+    T.train(targs, [(x_h, gt_h)] * 2, model, None, opt, 2)
+    barrier()
+    e0.record()
+    T.train(targs, Loader(), model, None, opt, args.steps)
+    e1.record()
+    barrier()
+    sampler.stop_flag = True
+    ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    ms2 = float(ms2)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline pass (rank 0): CUDA events around every kernel launch of the same step
+    peaks = load_peaks()
+    L.PROFILE = []
+    nprof = 3
+    for _ in range(nprof):
+        step(x_d, gt_d, net)          # the bare module: the other ranks have left, no DDP collective here
+    torch.cuda.synchronize()
+    agg = {}
+    for name, tag, a, b in L.PROFILE:
+        key = name if tag is None else '%s[%s,%s]' % (name, tag[0], 'tc' if tag[1] else 'cuda-core')
+        t, n, f = agg.get(key, (0.0, 0, 0.0))
+        agg[key] = (t + a.elapsed_time(b), n + 1, f + (tag[2] if tag else 0.0))
+    L.PROFILE = None
+    tc_t = sum(t for k, (t, n, f) in agg.items() if k.startswith('dn_igemm_run') and 'tc' in k) / nprof
+    tc_f = sum(f for k, (t, n, f) in agg.items() if k.startswith('dn_igemm_run') and 'tc' in k) / nprof
+    tc_n = sum(n for k, (t, n, f) in agg.items() if k.startswith('dn_igemm_run') and 'tc' in k) / nprof
+    kern_ms = sum(t for (t, n, f) in agg.values()) / nprof
+    achieved = tc_f / (tc_t * 1e-3) / 1e12 if tc_t > 0 else 0.0
+    breakdown = {k: round(t / nprof, 3) for k, (t, n, f) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:14]}
+
+    total_imgs = BATCH * world * args.steps
+    value = total_imgs / (ms * 1e-3)
+    e2e = total_imgs / (ms2 * 1e-3)
+    line = dict(metric=METRIC, value=value, unit='images/sec', n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
+                ms_per_step=ms / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
+                dtype=os.environ.get('DISPNET_B200_PRECISION', 'fp16') + ' (fp32 accumulate)', data='synthetic',
+                config=dict(workload='configs[1]: Disp_vgg_BN + L1 depth loss (+0*smooth as train.py does), synthetic KITTI '
+                                     '128x416, b=32/GPU, fwd+loss+bwd+Adam', global_batch=BATCH * world,
+                            parallelism='dp%d' % world,
+                            l2='per-step working set (activations+gradients ~4 GB) >> 126 MB L2; no explicit flush needed',
+                            last_loss=last_loss),
+                clocks=sampler.summary(),
+                e2e=dict(value=e2e, unit='images/sec', h2d_bytes_per_step=x_h.numel() * 4 + gt_h.numel() * 4,
+                         d2h_bytes_per_step=4, ms_per_step=ms2 / args.steps),
+                gpu_launches=calls,
+                roofline=dict(bound='tensor', kernel='igemm_tc_kernel (forward + data-gradient gather-convolutions)',
+                              achieved=achieved, peak=peaks['tf_sust'], unit='TFLOP/s', frac=achieved / peaks['tf_sust'],
+                              traffic=None, peak_source=peaks['src'] + ' sustained bf16 (kernel timed inside a long step)',
+                              launches_per_step=tc_n, kernel_ms_per_step=tc_t, flops_per_step=tc_f,
+                              step_fraction_of_tensor_roofline=(value / world * TRAIN_GFLOP_PER_IMG) / (peaks['tf_sust'] * 1e3)),
+                kernel_breakdown_ms_per_step=breakdown, all_kernels_ms_per_step=kern_ms)
+    if world == 1 and not args.no_cpu:
+        line['cpu_baseline'] = cpu_baseline()
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours')
+    ap.add_argument('--no-cpu', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

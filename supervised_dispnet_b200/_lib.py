@@ -119,8 +119,23 @@ def check(code, what=''):
         raise RuntimeError('dispnet_b200 %s failed: %s (code %d)' % (what, msg, code))
 
 
-def call(name, *args):
+# ---- optional per-call device timing (bench.py roofline pass): PROFILE = [] switches it on
+PROFILE = None
+CALLS = 0
+
+
+def call(name, *args, tag=None):
+    global CALLS
+    CALLS += 1
+    if PROFILE is None:
+        check(getattr(lib(), name)(*args), name)
+        return
+    import torch
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
     check(getattr(lib(), name)(*args), name)
+    e1.record()
+    PROFILE.append((name, tag, e0, e1))
 
 
 def stream_ptr():

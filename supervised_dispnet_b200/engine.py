@@ -174,6 +174,15 @@ def _mk_wgrad(ps, q, dw, cp_pad, cq_pad, stride, taps, scale):
     return p
 
 
+def _igemm_flops(p):
+    """Algorithmic FLOPs of a gather-convolution: 2 * output pixels * Cout * (taps * Cin), true (unpadded) sizes."""
+    return 2.0 * p.out.N * p.out.H * p.out.W * p.out.C * p.ntaps * p.inp[0].C
+
+
+def _wgrad_flops(p):
+    return 2.0 * p.p[0].N * p.p[0].H * p.p[0].W * p.p[0].C * p.q.C * p.ntaps
+
+
 class Op:
     def fwd(self, plan):
         raise NotImplementedError
@@ -250,7 +259,7 @@ class ConvOp(Op):
         for pr in self.fwd_probs:
             p = _mk_igemm(pr['ins'], pr['out'], self.wp, plan.prec.act, self.cin_pad, self.cout_pad, None, self.act, False,
                           pr['stride'], pr['taps'])
-            built.append((p, _backend('igemm', p)))
+            built.append((p, _backend('igemm', p), _igemm_flops(p)))
         return built
 
     def fwd(self, plan):
@@ -261,9 +270,9 @@ class ConvOp(Op):
         if self._fwd_built is None:
             self._fwd_built = self._build_fwd(plan)
         b = plan.param(self.name + '.bias') if self.has_bias else None
-        for p, be in self._fwd_built:
+        for p, be, fl in self._fwd_built:
             p.bias = b.data_ptr() if b is not None else None
-            L.call('dn_igemm_run', C.byref(p), be, plan.stream)
+            L.call('dn_igemm_run', C.byref(p), be, plan.stream, tag=('fwd', be, fl))
 
     def plan_bwd(self, plan):
         g = plan.prec.grad
@@ -282,7 +291,7 @@ class ConvOp(Op):
                 a, b = pr['phase']
                 self.wg.append(_mk_wgrad([self.gout.phase(a, b)], self.x, self.dwp, self.cout_pad, self.cin_pad, 1,
                                          pr['taps'], 1.0))
-        self.wg = [(p, _backend('wgrad', p)) for p in self.wg]
+        self.wg = [(p, _backend('wgrad', p), _wgrad_flops(p)) for p in self.wg]
         # ---- data-gradient problems
         self.dg = []
         if self.needs_dx:
@@ -318,7 +327,7 @@ class ConvOp(Op):
             for pr in probs:
                 p = _mk_igemm(pr['ins'], pr['out'], self.wpT, g, self.coutT_pad, self.cinT_pad, None, L.ACT_NONE, acc, 1,
                               pr['taps'])
-                self.dg.append((p, _backend('igemm', p)))
+                self.dg.append((p, _backend('igemm', p), _igemm_flops(p)))
 
     def bwd(self, plan):
         W = plan.param(self.name + '.weight')
@@ -328,8 +337,8 @@ class ConvOp(Op):
         if self.act != L.ACT_NONE or gb is not None:
             L.call('dn_act_bwd', self.gout.ref(), self.out.ref(), self.act, L.ptr(gb), inv, plan.stream)
         self.dwp.zero_()
-        for p, be in self.wg:
-            L.call('dn_wgrad_run', C.byref(p), be, plan.stream)
+        for p, be, fl in self.wg:
+            L.call('dn_wgrad_run', C.byref(p), be, plan.stream, tag=('wgrad', be, fl))
         gw = plan.grad_of(self.name + '.weight')
         L.call('dn_unpack_wgrad', L.ptr(self.dwp), L.ptr(gw), T, self.Cout, self.Cin, self.cout_pad, self.cin_pad, self.kh,
                self.kw, self.s_co, self.s_ci, self.k, 1, inv, plan.stream)
@@ -339,8 +348,8 @@ class ConvOp(Op):
             # transposed role: rows = ci, cols = co
             L.call('dn_pack_weight', L.ptr(W), L.ptr(self.wpT), _DT[plan.prec.grad], T, self.Cin, self.Cout, self.cinT_pad,
                    self.coutT_pad, self.kh, self.kw, self.s_ci, self.s_co, self.k, 1, plan.stream)
-            for p, be in self.dg:
-                L.call('dn_igemm_run', C.byref(p), be, plan.stream)
+            for p, be, fl in self.dg:
+                L.call('dn_igemm_run', C.byref(p), be, plan.stream, tag=('dgrad', be, fl))
 
 
 class BNOp(Op):

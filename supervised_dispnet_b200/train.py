@@ -1,0 +1,140 @@
+"""Host-side mirror of the reference's training loop `train.train(args, train_loader, disp_net, pose_exp_net,
+optimizer, epoch_size, logger, train_writer)` (reference train.py:394-539) for the hot-path configurations.
+
+Same signature, argument meaning and per-step call order as the reference (H2D copy -> disp_net -> 1/disp ->
+loss_functions.* -> zero_grad / backward / step -> loss.item()), so that a reference checkout can also simply do
+`import supervised_dispnet_b200.models as models; import supervised_dispnet_b200.loss_functions as loss_functions`
+and keep its own train.py.  Differences, all forced by breakages documented in SURVEY.md 3.3:
+  * a batch may be the reference's 2-tuple `(tgt_img, gt_depth)` (supervised) or the 5-tuple
+    `(tgt_img, ref_imgs, intrinsics, intrinsics_inv, gt_depth)` the reference's commented-out line :418 used
+    (the checked-in unsupervised branch reads unbound names);
+  * only `--loss L1` is wired for the supervised branch (the other nine losses are out of scope);
+  * tensorboard / csv side effects happen only when `train_writer` / `args.save_path` are given.
+"""
+import csv
+import os
+import time
+from types import SimpleNamespace
+
+import torch
+
+from . import loss_functions
+
+n_iter = 0
+
+
+class AverageMeter(object):
+    """Running average of one or several values (reference logger.py:62-89)."""
+
+    def __init__(self, i=1, precision=3):
+        self.meters, self.precision = i, precision
+        self.reset(i)
+
+    def reset(self, i):
+        self.val, self.avg, self.sum, self.count = [0] * i, [0] * i, [0] * i, 0
+
+    def update(self, val, n=1):
+        if not isinstance(val, list):
+            val = [val]
+        assert len(val) == self.meters
+        self.count += n
+        for i, v in enumerate(val):
+            self.val[i] = v
+            self.sum[i] += v * n
+            self.avg[i] = self.sum[i] / self.count
+
+    def __repr__(self):
+        val = ' '.join(['{:.{}f}'.format(v, self.precision) for v in self.val])
+        avg = ' '.join(['{:.{}f}'.format(a, self.precision) for a in self.avg])
+        return '{} ({})'.format(val, avg)
+
+
+def default_args(**kw):
+    """argparse defaults of the reference that the loop reads (train.py:28-91)."""
+    a = dict(photo_loss_weight=1.0, mask_loss_weight=0.0, smooth_loss_weight=0.0, unsupervised=False, dataset='kitti',
+             loss='L1', monodepth2=False, diff_lr=False, rotation_mode='euler', padding_mode='zeros', print_freq=10,
+             training_output_freq=0, batch_size=4, network='disp_vgg_BN', save_path=None, log_full='progress_log_full.csv')
+    a.update(kw)
+    return SimpleNamespace(**a)
+
+
+def train(args, train_loader, disp_net, pose_exp_net, optimizer, epoch_size, logger=None, train_writer=None,
+          device=None):
+    global n_iter
+    device = device or next(disp_net.parameters()).device
+    batch_time, data_time, losses = AverageMeter(), AverageMeter(), AverageMeter(precision=4)
+    w1, w2, w3 = args.photo_loss_weight, args.mask_loss_weight, args.smooth_loss_weight
+    disp_net.train()
+    if pose_exp_net is not None:
+        pose_exp_net.train()
+    if getattr(args, 'diff_lr', False):
+        for m in disp_net.modules():
+            if m.__class__.__name__.find('BatchNorm') != -1:
+                m.eval()
+    end = time.time()
+    if logger is not None:
+        logger.train_bar.update(0)
+
+    for i, batch in enumerate(train_loader):
+        data_time.update(time.time() - end)
+        if len(batch) == 2:
+            tgt_img, gt_depth = batch
+            ref_imgs = intrinsics = intrinsics_inv = None
+        else:
+            tgt_img, ref_imgs, intrinsics, intrinsics_inv, gt_depth = batch
+        tgt_img = tgt_img.to(device, non_blocking=True)
+
+        if args.unsupervised:
+            ref_imgs = [img.to(device, non_blocking=True) for img in ref_imgs]
+            intrinsics = intrinsics.to(device, non_blocking=True)
+            intrinsics_inv = intrinsics_inv.to(device, non_blocking=True)
+            explainability_mask, pose = pose_exp_net(tgt_img, ref_imgs)
+
+        if gt_depth is not None:
+            gt_depth = gt_depth.to(device, non_blocking=True)
+            if args.dataset == 'nyu' and gt_depth.dim() == 4:
+                gt_depth = torch.squeeze(gt_depth[:, 0, :, :])
+
+        disparities = disp_net(tgt_img)
+        scale = 5.4 if getattr(args, 'monodepth2', False) else 1
+        depth = [scale / disp for disp in disparities]
+
+        if not args.unsupervised:
+            if args.loss != 'L1':
+                raise TypeError('undefined loss')      # the reference does `raise "undefined loss"` (a TypeError in py3)
+            loss_1 = loss_functions.l1_loss(gt_depth, depth, args.dataset)
+        else:
+            loss_1 = loss_functions.photometric_reconstruction_loss(tgt_img, ref_imgs, intrinsics, intrinsics_inv, depth,
+                                                                    explainability_mask, pose, args.rotation_mode,
+                                                                    args.padding_mode)
+        loss_2 = loss_functions.explainability_loss(explainability_mask) if w2 > 0 else 0
+        loss_3 = loss_functions.smooth_loss(depth)
+        loss = w1 * loss_1 + w2 * loss_2 + w3 * loss_3
+
+        if train_writer is not None and i > 0 and n_iter % args.print_freq == 0:
+            train_writer.add_scalar('photometric_error', loss_1.item(), n_iter)
+            if w2 > 0:
+                train_writer.add_scalar('explanability_loss', loss_2.item(), n_iter)
+            train_writer.add_scalar('disparity_smoothness_loss', loss_3.item(), n_iter)
+            train_writer.add_scalar('total_loss', loss.item(), n_iter)
+
+        losses.update(loss.item(), args.batch_size)      # the per-step D2H read of the reference (:517)
+
+        optimizer.zero_grad()
+        loss.backward()
+        optimizer.step()
+
+        batch_time.update(time.time() - end)
+        end = time.time()
+        if getattr(args, 'save_path', None):
+            with open(os.path.join(str(args.save_path), args.log_full), 'a') as csvfile:
+                csv.writer(csvfile, delimiter='\t').writerow([loss.item(), loss_1.item(), loss_2.item() if w2 > 0 else 0,
+                                                              loss_3.item()])
+        if logger is not None:
+            logger.train_bar.update(i + 1)
+            if i % args.print_freq == 0:
+                logger.train_writer.write('Train: Time {} Data {} Loss {}'.format(batch_time, data_time, losses))
+        if i >= epoch_size - 1:
+            break
+        n_iter += 1
+    return losses.avg[0]

@@ -66,7 +66,7 @@ class OneConv(E.PlannedModule):
 
     def backends(self, x):
         plan = self._plan_for([x])
-        return dict(fwd=[b for _, b in self.op._fwd_built], wgrad=[b for _, b in self.op.wg], dgrad=[b for _, b in self.op.dg])
+        return dict(fwd=[b[1] for b in self.op._fwd_built], wgrad=[b[1] for b in self.op.wg], dgrad=[b[1] for b in self.op.dg])
 
 
 class DumpOp(E.Op):

@@ -168,23 +168,25 @@ def _model_compare(prod, oracle_fwd, sd, inputs, precision, n_out):
     loss_p = sum((p * I.probe_like(o, i).to(DEV)).sum() for i, (p, o) in enumerate(zip(flat_p, flat_o)))
     loss_o.backward()
     loss_p.backward()
-    worst, worst_name, named = 0.0, '', dict(prod.named_parameters())
+    named = dict(prod.named_parameters())
     gnorm = math.sqrt(sum(float(v.grad.double().norm() ** 2) for k, v in sd_o.items() if v.requires_grad and v.grad is not None))
+    errs, num2 = [], 0.0
     for k, v in sd_o.items():
         if not (v.requires_grad and v.grad is not None):
             continue
         g = named[k].grad
         if g is None:
-            worst, worst_name = float('inf'), k + ' (missing)'
+            errs.append((float('inf'), k + ' (missing)'))
             continue
-        # relative to the parameter's own gradient norm, floored at 1e-4 of the global gradient norm so that
+        d = float((g.detach().double().cpu() - v.grad.double()).norm())
+        num2 += d * d
+        # relative to the parameter's own gradient norm, floored at 1e-3 of the global gradient norm so that
         # analytically-zero gradients (conv biases in front of BatchNorm) are judged on an absolute scale
-        denom = max(float(v.grad.double().norm()), 1e-4 * gnorm)
-        e = float((g.detach().double().cpu() - v.grad.double()).norm()) / denom
-        if e > worst:
-            worst, worst_name = e, k
-    res['grad'] = worst
-    res['worst'] = worst_name
+        errs.append((d / max(float(v.grad.double().norm()), 1e-3 * gnorm), k))
+    errs.sort(reverse=True)
+    res['grad'] = errs[0][0]
+    res['gglobal'] = math.sqrt(num2) / gnorm
+    res['worst'] = ','.join('%s:%.1e' % (k, e) for e, k in errs[:3])
     bufs = dict(prod.named_buffers())
     rs = [rel(bufs[k], sd_o[k]) for k in sd_o if 'running' in k]
     if rs:

@@ -7,7 +7,7 @@ run() {  # name, env, args...
   local name=$1; shift
   local envs=$1; shift
   echo "######## $name"
-  env $envs timeout 300 python tools/gpu_check.py "$@" --out gpurun_out/check_$name.json > gpurun_out/check_$name.log 2>&1
+  env $envs timeout 150 python tools/gpu_check.py "$@" --out gpurun_out/check_$name.json > gpurun_out/check_$name.log 2>&1
   echo "exit=$?" >> gpurun_out/check_$name.log
   grep -E "^(conv|loss|model)/|^exit=|tc_available" gpurun_out/check_$name.log | cut -c1-220
 }
