@@ -213,6 +213,11 @@ def run_ours(args):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms)
     last_loss = float(loss)
+    if args.minimal:
+        if rank == 0:
+            print(json.dumps(dict(metric=METRIC, value=BATCH * world * args.steps / (ms * 1e-3), ms_per_step=ms / args.steps,
+                                  minimal=True)), flush=True)
+        return
 
     # ---- e2e: public API with host batches
     targs = T.default_args(batch_size=BATCH, smooth_loss_weight=0.0)
@@ -293,6 +298,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours')
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--minimal', action='store_true', help='warm-up + timed steps only (for runs under ncu)')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

@@ -75,6 +75,8 @@ typedef struct dn_igemm {
   int32_t ntaps;
   dn_tap taps[DN_MAX_TAPS];
   float out_scale;           /* result multiplied by this before bias/act (1.0 normally) */
+  int32_t out_pad_ok;        /* 1: channels [out.C, roundup(out.C, 8)) of every output pixel are padding that the
+                                kernel may overwrite (lets the 16-byte vector epilogue serve odd channel counts) */
 } dn_igemm;
 
 /*
@@ -123,8 +125,11 @@ int dn_igemm_tc_supported(const dn_igemm* p);
 int dn_wgrad_tc_supported(const dn_wgrad* p);
 
 /* ---- BatchNorm2d (training) + ReLU + MaxPool2d(2,2)  (models/Disp_vgg_BN.py:137-141) ---------- */
-/* sums[2*C] (double) += per-channel sum and sum of squares of y; caller zeroes sums. */
-int dn_bn_stats(const dn_view* y, double* sums, void* stream);
+/* Per-channel reductions are two-stage (per-block partials in `ws`, then a tiny second kernel) so that no atomics
+ * contend on C addresses.  `ws` must hold dn_reduce_ws_floats(C) floats. */
+int64_t dn_reduce_ws_floats(int C);
+/* sums[2*C] (double) = per-channel sum and sum of squares of y (overwritten). */
+int dn_bn_stats(const dn_view* y, double* sums, float* ws, void* stream);
 /* mean/invstd from sums; running stats update (momentum, unbiased var); scale_shift[2C] = (g*invstd, b-mean*g*invstd).
  * count = N*H*W.  If training == 0 uses running stats instead. */
 int dn_bn_finalize(const double* sums, double count, const float* gamma, const float* beta, float* running_mean,
@@ -136,7 +141,8 @@ int dn_bn_apply(const dn_view* y, const float* scale_shift, const dn_view* resid
 /* backward: pass 1 accumulates red[2C] (double): sum(dyhat), sum(dyhat*xhat), where dyhat is the gradient
  * routed back through pool/act; pass 2 writes dy (and dres if residual). */
 int dn_bn_bwd_reduce(const dn_view* dout, const dn_view* y, const dn_view* residual, const float* mean_invstd,
-                     const float* gamma, const float* beta, int act, int pool, double* red, void* stream);
+                     const float* gamma, const float* beta, int act, int pool, double* red /* overwritten */, float* ws,
+                     void* stream);
 int dn_bn_bwd_apply(const dn_view* dout, const dn_view* y, const dn_view* residual, const float* mean_invstd,
                     const float* gamma, const float* beta, int act, int pool, const double* red, double count,
                     float gscale, float* dgamma, float* dbeta, const dn_view* dy, const dn_view* dres,
@@ -144,7 +150,7 @@ int dn_bn_bwd_apply(const dn_view* dout, const dn_view* y, const dn_view* residu
 
 /* ---- pointwise / pooling ------------------------------------------------------------------ */
 /* dy = dout * act'(out) in place on `dout`; dbias[c] = gscale * sum(dy) (fp32, overwritten) if dbias != NULL */
-int dn_act_bwd(const dn_view* dout, const dn_view* out, int act, float* dbias, float gscale, void* stream);
+int dn_act_bwd(const dn_view* dout, const dn_view* out, int act, float* dbias, float gscale, float* ws, void* stream);
 int dn_maxpool_fwd(const dn_view* x, const dn_view* out, int k, int stride, int pad, void* stream);
 int dn_maxpool_bwd(const dn_view* dout, const dn_view* x, const dn_view* dx, int k, int stride, int pad,
                    int accumulate, void* stream);

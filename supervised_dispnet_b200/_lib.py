@@ -27,7 +27,7 @@ class DnIgemm(C.Structure):
     _fields_ = [('inp', DnView * MAX_SRC), ('nsrc', C.c_int32), ('out', DnView), ('w', C.c_void_p),
                 ('w_dtype', C.c_int32), ('cin_pad', C.c_int32), ('cout_pad', C.c_int32), ('bias', C.c_void_p),
                 ('act', C.c_int32), ('accumulate', C.c_int32), ('stride', C.c_int32), ('ntaps', C.c_int32),
-                ('taps', DnTap * MAX_TAPS), ('out_scale', C.c_float)]
+                ('taps', DnTap * MAX_TAPS), ('out_scale', C.c_float), ('out_pad_ok', C.c_int32)]
 
 
 class DnWgrad(C.Structure):
@@ -54,12 +54,13 @@ _SIGS = {
     'dn_wgrad_run': ([C.POINTER(DnWgrad), _I, _P], _I),
     'dn_igemm_tc_supported': ([C.POINTER(DnIgemm)], _I),
     'dn_wgrad_tc_supported': ([C.POINTER(DnWgrad)], _I),
-    'dn_bn_stats': ([_V, _P, _P], _I),
+    'dn_reduce_ws_floats': ([_I], _I64),
+    'dn_bn_stats': ([_V, _P, _P, _P], _I),
     'dn_bn_finalize': ([_P, _D, _P, _P, _P, _P, _F, _F, _I, _I, _P, _P, _I, _P], _I),
     'dn_bn_apply': ([_V, _P, _V, _I, _I, _V, _P], _I),
-    'dn_bn_bwd_reduce': ([_V, _V, _V, _P, _P, _P, _I, _I, _P, _P], _I),
+    'dn_bn_bwd_reduce': ([_V, _V, _V, _P, _P, _P, _I, _I, _P, _P, _P], _I),
     'dn_bn_bwd_apply': ([_V, _V, _V, _P, _P, _P, _I, _I, _P, _D, _F, _P, _P, _V, _V, _I, _P], _I),
-    'dn_act_bwd': ([_V, _V, _I, _P, _F, _P], _I),
+    'dn_act_bwd': ([_V, _V, _I, _P, _F, _P, _P], _I),
     'dn_maxpool_fwd': ([_V, _V, _I, _I, _I, _P], _I),
     'dn_maxpool_bwd': ([_V, _V, _V, _I, _I, _I, _I, _P], _I),
     'dn_add_act_fwd': ([_V, _V, _I, _V, _P], _I),

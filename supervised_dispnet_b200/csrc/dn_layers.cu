@@ -382,6 +382,7 @@ static CgGeom cg_geom(int C, int ch, long long pixels) {
   long long cap = (long long)dn_num_sms() * 8 / gy;
   if (cap < 1) cap = 1;
   if (bx > cap) bx = cap;
+  if (bx > 2048) bx = 2048;
   if (bx < 1) bx = 1;
   g.grid = dim3((unsigned)bx, (unsigned)gy);
   return g;
@@ -416,9 +417,21 @@ __device__ __forceinline__ void cg_block_reduce(float* vals, int CGb) {
   __syncthreads();
 }
 
+// second stage of the per-channel reductions: out[j] = scale * sum_blk ws[blk][j]  (double accumulation)
+constexpr int kMaxReduceBlocks = 2048;
+template <typename TO>
+__global__ void reduce_partials_kernel(const float* __restrict__ ws, int nblk, int n, TO* __restrict__ out, double scale) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  double s = 0.0;
+  for (int b = 0; b < nblk; ++b) s += (double)ws[(long long)b * n + j];
+  out[j] = (TO)(s * scale);
+}
+DN_EXPORT int64_t dn_reduce_ws_floats(int C) { return (int64_t)kMaxReduceBlocks * 2 * (C + 8); }
+
 // ---- BN statistics --------------------------------------------------------------------------------
 template <int CH>
-__global__ void __launch_bounds__(256) bn_stats_kernel(dn_view y, double* __restrict__ sums, int CGb) {
+__global__ void __launch_bounds__(256) bn_stats_kernel(dn_view y, float* __restrict__ ws, int CGb) {
   CG_PROLOGUE(y)
   float acc[2 * CH];
 #pragma unroll
@@ -436,26 +449,30 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(dn_view y, double* __rest
   }
   cg_block_reduce<2 * CH>(acc, CGb);
   if (threadIdx.x < CGb && cvalid) {
+    float* w = ws + (long long)blockIdx.x * 2 * y.C;
 #pragma unroll
     for (int i = 0; i < CH; ++i) {
       if (c0 + i < y.C) {
-        atomicAdd(sums + c0 + i, (double)acc[i]);
-        atomicAdd(sums + y.C + c0 + i, (double)acc[CH + i]);
+        w[c0 + i] = acc[i];
+        w[y.C + c0 + i] = acc[CH + i];
       }
     }
   }
 }
 
-DN_EXPORT int dn_bn_stats(const dn_view* y, double* sums, void* stream) {
-  if (!y || !sums) return DN_E_ARG;
+DN_EXPORT int dn_bn_stats(const dn_view* y, double* sums, float* ws, void* stream) {
+  if (!y || !sums || !ws) return DN_E_ARG;
   long long npix = (long long)y->N * y->H * y->W;
+  CgGeom g;
   if (dn_vec8_ok(y)) {
-    CgGeom g = cg_geom(y->C, 8, npix);
-    bn_stats_kernel<8><<<g.grid, 256, 0, dn_stream(stream)>>>(*y, sums, g.CGb);
+    g = cg_geom(y->C, 8, npix);
+    bn_stats_kernel<8><<<g.grid, 256, 0, dn_stream(stream)>>>(*y, ws, g.CGb);
   } else {
-    CgGeom g = cg_geom(y->C, 1, npix);
-    bn_stats_kernel<1><<<g.grid, 256, 0, dn_stream(stream)>>>(*y, sums, g.CGb);
+    g = cg_geom(y->C, 1, npix);
+    bn_stats_kernel<1><<<g.grid, 256, 0, dn_stream(stream)>>>(*y, ws, g.CGb);
   }
+  DN_CHECK_LAUNCH();
+  reduce_partials_kernel<double><<<(2 * y->C + 127) / 128, 128, 0, dn_stream(stream)>>>(ws, g.grid.x, 2 * y->C, sums, 1.0);
   DN_CHECK_LAUNCH();
   return 0;
 }
@@ -614,7 +631,7 @@ __device__ __forceinline__ void bn_route(const dn_view& y, const dn_view& res, i
 template <int CH>
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(dn_view dout, dn_view y, dn_view res, int has_res,
                                                             const float* __restrict__ mean_invstd, const float* __restrict__ gamma,
-                                                            const float* __restrict__ beta, int act, int pool, double* red, int CGb) {
+                                                            const float* __restrict__ beta, int act, int pool, float* __restrict__ ws, int CGb) {
   CG_PROLOGUE(dout)
   const int C = dout.C;
   float acc[2 * CH];
@@ -645,28 +662,32 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(dn_view dout, dn_vie
   }
   cg_block_reduce<2 * CH>(acc, CGb);
   if (threadIdx.x < CGb && cvalid) {
+    float* w = ws + (long long)blockIdx.x * 2 * C;
 #pragma unroll
     for (int i = 0; i < CH; ++i)
       if (c0 + i < C) {
-        atomicAdd(red + c0 + i, (double)acc[i]);
-        atomicAdd(red + C + c0 + i, (double)acc[CH + i]);
+        w[c0 + i] = acc[i];
+        w[C + c0 + i] = acc[CH + i];
       }
   }
 }
 
 DN_EXPORT int dn_bn_bwd_reduce(const dn_view* dout, const dn_view* y, const dn_view* residual, const float* mean_invstd,
-                               const float* gamma, const float* beta, int act, int pool, double* red, void* stream) {
-  if (!dout || !y || !mean_invstd || !red) return DN_E_ARG;
+                               const float* gamma, const float* beta, int act, int pool, double* red, float* ws, void* stream) {
+  if (!dout || !y || !mean_invstd || !red || !ws) return DN_E_ARG;
   long long npix = (long long)dout->N * dout->H * dout->W;
   dn_view r = residual ? *residual : *y;
   bool vec = dn_vec8_ok(y) && dn_vec8_ok(dout) && (!residual || dn_vec8_ok(residual));
+  CgGeom g;
   if (vec) {
-    CgGeom g = cg_geom(dout->C, 8, npix);
-    bn_bwd_reduce_kernel<8><<<g.grid, 256, 0, dn_stream(stream)>>>(*dout, *y, r, residual != nullptr, mean_invstd, gamma, beta, act, pool, red, g.CGb);
+    g = cg_geom(dout->C, 8, npix);
+    bn_bwd_reduce_kernel<8><<<g.grid, 256, 0, dn_stream(stream)>>>(*dout, *y, r, residual != nullptr, mean_invstd, gamma, beta, act, pool, ws, g.CGb);
   } else {
-    CgGeom g = cg_geom(dout->C, 1, npix);
-    bn_bwd_reduce_kernel<1><<<g.grid, 256, 0, dn_stream(stream)>>>(*dout, *y, r, residual != nullptr, mean_invstd, gamma, beta, act, pool, red, g.CGb);
+    g = cg_geom(dout->C, 1, npix);
+    bn_bwd_reduce_kernel<1><<<g.grid, 256, 0, dn_stream(stream)>>>(*dout, *y, r, residual != nullptr, mean_invstd, gamma, beta, act, pool, ws, g.CGb);
   }
+  DN_CHECK_LAUNCH();
+  reduce_partials_kernel<double><<<(2 * dout->C + 127) / 128, 128, 0, dn_stream(stream)>>>(ws, g.grid.x, 2 * dout->C, red, 1.0);
   DN_CHECK_LAUNCH();
   return 0;
 }
@@ -744,7 +765,7 @@ DN_EXPORT int dn_bn_bwd_apply(const dn_view* dout, const dn_view* y, const dn_vi
 
 // ---- activation backward (in place) + bias gradient ---------------------------------------------------
 template <int CH>
-__global__ void __launch_bounds__(256) act_bwd_kernel(dn_view dout, dn_view out, int act, float* dbias, float gscale, int CGb) {
+__global__ void __launch_bounds__(256) act_bwd_kernel(dn_view dout, dn_view out, int act, float* ws, int CGb) {
   CG_PROLOGUE(dout)
   float acc[CH];
 #pragma unroll
@@ -767,34 +788,36 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(dn_view dout, dn_view out,
       for (int i = 0; i < CH; ++i) acc[i] += g[i];
     }
   }
-  if (dbias) {
+  if (ws) {
     cg_block_reduce<CH>(acc, CGb);
     if (threadIdx.x < CGb && cvalid) {
+      float* w = ws + (long long)blockIdx.x * dout.C;
 #pragma unroll
       for (int i = 0; i < CH; ++i)
-        if (c0 + i < dout.C) atomicAdd(dbias + c0 + i, acc[i] * gscale);
+        if (c0 + i < dout.C) w[c0 + i] = acc[i];
     }
   }
 }
 
-DN_EXPORT int dn_act_bwd(const dn_view* dout, const dn_view* out, int act, float* dbias, float gscale, void* stream) {
-  if (!dout || (!out && act != DN_ACT_NONE)) return DN_E_ARG;
+DN_EXPORT int dn_act_bwd(const dn_view* dout, const dn_view* out, int act, float* dbias, float gscale, float* ws, void* stream) {
+  if (!dout || (!out && act != DN_ACT_NONE) || (dbias && !ws)) return DN_E_ARG;
   if (act == DN_ACT_NONE && !dbias) return 0;
   long long npix = (long long)dout->N * dout->H * dout->W;
-  if (dbias) {
-    cudaError_t e = cudaMemsetAsync(dbias, 0, sizeof(float) * dout->C, dn_stream(stream));
-    if (e != cudaSuccess) return (int)e;
-  }
   dn_view o = out ? *out : *dout;
   bool vec = dn_vec8_ok(dout) && (!out || dn_vec8_ok(out));
+  CgGeom g;
   if (vec) {
-    CgGeom g = cg_geom(dout->C, 8, npix);
-    act_bwd_kernel<8><<<g.grid, 256, 0, dn_stream(stream)>>>(*dout, o, act, dbias, gscale, g.CGb);
+    g = cg_geom(dout->C, 8, npix);
+    act_bwd_kernel<8><<<g.grid, 256, 0, dn_stream(stream)>>>(*dout, o, act, dbias ? ws : nullptr, g.CGb);
   } else {
-    CgGeom g = cg_geom(dout->C, 1, npix);
-    act_bwd_kernel<1><<<g.grid, 256, 0, dn_stream(stream)>>>(*dout, o, act, dbias, gscale, g.CGb);
+    g = cg_geom(dout->C, 1, npix);
+    act_bwd_kernel<1><<<g.grid, 256, 0, dn_stream(stream)>>>(*dout, o, act, dbias ? ws : nullptr, g.CGb);
   }
   DN_CHECK_LAUNCH();
+  if (dbias) {
+    reduce_partials_kernel<float><<<(dout->C + 127) / 128, 128, 0, dn_stream(stream)>>>(ws, g.grid.x, dout->C, dbias, (double)gscale);
+    DN_CHECK_LAUNCH();
+  }
   return 0;
 }
 

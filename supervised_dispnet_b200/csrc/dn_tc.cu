@@ -145,6 +145,8 @@ struct IgemmTcParams {
   int wb, hb, nb;     // pixel box (wb*hb*nb == 128)
   int tilesW, tilesH, tilesN, ntile_n, num_tiles;
   int stages;
+  int n_mma;          // MMA N actually issued (multiple of 16, <= BN)
+  int c_eff;          // output channels the epilogue may write (out.C, or rounded up to 8 when padding may be overwritten)
   uint32_t idesc;
   dn_view out;
   const float* bias;
@@ -270,40 +272,47 @@ __global__ void __launch_bounds__(192, 1) igemm_tc_kernel(const __grid_constant_
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
       uint8_t* optr = (uint8_t*)p.out.ptr + (size_t)(dn_off(p.out, n, h, w) + co0) * esz;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 16) {
+      for (int c0 = 0; c0 < p.n_mma; c0 += 16) {
         uint32_t r[16];
         tmem_ld16(taddr + c0, r);
         tmem_ld_wait();
-        if (valid && co0 + c0 < p.out.C) {
+        if (valid && co0 + c0 < p.c_eff) {
           float v[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = dn_act(__uint_as_float(r[j]) * p.out_scale + bs[c0 + j], p.act);
-          if (p.out.dtype == DN_F16) {
+          if (p.out.dtype == DN_F32) {
+            float* o = (float*)optr + c0;
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (co0 + c0 + j < p.out.C) o[j] = p.accumulate ? o[j] + v[j] : v[j];
+          } else if (p.out.dtype == DN_F16) {
             __half* o = (__half*)optr + c0;
-            if (p.accumulate) {
-              float a[8];
-              Vec8<__half>::load(o, a);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] += a[j];
-              Vec8<__half>::load(o + 8, a);
+            for (int hh = 0; hh < 2; ++hh) {
+              if (co0 + c0 + 8 * hh < p.c_eff) {
+                if (p.accumulate) {
+                  float a[8];
+                  Vec8<__half>::load(o + 8 * hh, a);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) v[8 + j] += a[j];
+                  for (int j = 0; j < 8; ++j) v[8 * hh + j] += a[j];
+                }
+                Vec8<__half>::store(o + 8 * hh, v + 8 * hh);
+              }
             }
-            Vec8<__half>::store(o, v);
-            Vec8<__half>::store(o + 8, v + 8);
           } else {
             __nv_bfloat16* o = (__nv_bfloat16*)optr + c0;
-            if (p.accumulate) {
-              float a[8];
-              Vec8<__nv_bfloat16>::load(o, a);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] += a[j];
-              Vec8<__nv_bfloat16>::load(o + 8, a);
+            for (int hh = 0; hh < 2; ++hh) {
+              if (co0 + c0 + 8 * hh < p.c_eff) {
+                if (p.accumulate) {
+                  float a[8];
+                  Vec8<__nv_bfloat16>::load(o + 8 * hh, a);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) v[8 + j] += a[j];
+                  for (int j = 0; j < 8; ++j) v[8 * hh + j] += a[j];
+                }
+                Vec8<__nv_bfloat16>::store(o + 8 * hh, v + 8 * hh);
+              }
             }
-            Vec8<__nv_bfloat16>::store(o, v);
-            Vec8<__nv_bfloat16>::store(o + 8, v + 8);
           }
         }
       }
@@ -525,7 +534,7 @@ uint32_t make_idesc(int a_dtype, int b_dtype, int a_mn_major, int b_mn_major, in
 }
 
 int pick_bn(int cout_pad) {
-  if (cout_pad >= 256) return 256;
+  if (cout_pad > 128) return 256;
   if (cout_pad > 64) return 128;
   if (cout_pad > 32) return 64;
   if (cout_pad > 16) return 32;
@@ -580,15 +589,16 @@ DN_EXPORT int dn_tc_available(void) {
 DN_EXPORT int dn_igemm_tc_supported(const dn_igemm* p) {
   if (!p || p->stride != 1 || p->ntaps > kMaxTcTaps || p->ntaps < 1) return 0;
   if (p->w_dtype != DN_F16 && p->w_dtype != DN_BF16) return 0;
-  if (p->out.dtype != DN_F16 && p->out.dtype != DN_BF16) return 0;
-  if (!view_tma_ok(p->out) || (p->out.C % 16) != 0) return 0;
+  if (p->out.dtype != DN_F32) {   // 16-byte vector epilogue
+    if (!view_tma_ok(p->out)) return 0;
+    if ((p->out.C % 8) != 0 && !p->out_pad_ok) return 0;
+  }
   if ((p->cin_pad % 64) != 0 || (p->cout_pad % 16) != 0 || ((uintptr_t)p->w % 16) != 0) return 0;
   for (int s = 0; s < p->nsrc; ++s) {
     if (!view_tma_ok(p->in[s]) || p->in[s].dtype != p->w_dtype) return 0;
     if (p->in[s].C != p->in[0].C) return 0;
   }
-  int bn = pick_bn(p->cout_pad);
-  if (p->cout_pad % bn != 0 && p->cout_pad > bn) return 0;
+  if (p->cout_pad > 256 && (p->cout_pad % 256) != 0) return 0;
   return 1;
 }
 
@@ -633,7 +643,9 @@ int dn_igemm_tc(const dn_igemm* p, cudaStream_t st) {
   const uint32_t stage_bytes = kRows * 128 + BN * 128;
   P.stages = (int)((200 * 1024) / stage_bytes);
   if (P.stages > 8) P.stages = 8;
-  P.idesc = make_idesc(p->in[0].dtype, p->w_dtype, 0, 0, 128, BN);
+  P.n_mma = p->cout_pad < BN ? p->cout_pad : BN;
+  P.c_eff = (p->out.dtype != DN_F32 && p->out_pad_ok) ? (p->out.C + 7) / 8 * 8 : p->out.C;
+  P.idesc = make_idesc(p->in[0].dtype, p->w_dtype, 0, 0, 128, P.n_mma);
   P.out = p->out;
   P.bias = p->bias;
   P.act = p->act;
@@ -654,7 +666,6 @@ DN_EXPORT int dn_wgrad_tc_supported(const dn_wgrad* p) {
   for (int s = 0; s < p->nsrc; ++s)
     if (!view_tma_ok(p->p[s])) return 0;
   if ((p->cq_pad % 64) != 0 || (p->cp_pad % 8) != 0 || ((uintptr_t)p->dw % 16) != 0) return 0;
-  if ((p->p[0].C % 8) != 0 || (p->q.C % 8) != 0) return 0;
   return 1;
 }
 

@@ -34,7 +34,10 @@ class Precision:
             self.act, self.grad, self.gscale = torch.float32, torch.float32, 1.0
         elif name == 'fp16':
             self.act, self.grad, self.gscale = torch.float16, torch.float16, 4096.0
-        elif name == 'fp16_bf16grad':
+        elif name in ('mixed', 'fp16_bf16grad'):
+            # fp16 forward (11-bit significand keeps disparities within ~1e-3 of fp32), bf16 gradient activations
+            # (fp32 exponent range: no loss scaling).  tcgen05 kind::f16 cannot mix the two operand formats, so the
+            # weight-gradient GEMM reads a bf16 copy of the saved activation made just in time (ConvOp.bwd).
             self.act, self.grad, self.gscale = torch.float16, torch.bfloat16, 1.0
         elif name == 'bf16':
             self.act, self.grad, self.gscale = torch.bfloat16, torch.bfloat16, 1.0
@@ -43,7 +46,7 @@ class Precision:
 
 
 def default_precision():
-    return os.environ.get('DISPNET_B200_PRECISION', 'fp16')
+    return os.environ.get('DISPNET_B200_PRECISION', 'mixed')
 
 
 def tc_enabled():
@@ -53,12 +56,15 @@ def tc_enabled():
 class Buf:
     """NHWC storage with channel pitch rounded to 8 elements (16-byte pixel alignment for TMA / vector access)."""
 
-    def __init__(self, N, H, W, Cc, dtype, device, zero=True):
+    def __init__(self, N, H, W, Cc, dtype, device, zero=True, storage=None):
         self.N, self.H, self.W, self.C = N, H, W, Cc
         self.Cp = _ru(Cc, 8)
         self.dtype = dtype
-        f = torch.zeros if zero else torch.empty
-        self.t = f((N, H, W, self.Cp), dtype=dtype, device=device)
+        if storage is not None:     # carve from a shared scratch tensor
+            self.t = storage[:N * H * W * self.Cp * torch.empty((), dtype=dtype).element_size()].view(dtype).view(N, H, W, self.Cp)
+        else:
+            f = torch.zeros if zero else torch.empty
+            self.t = f((N, H, W, self.Cp), dtype=dtype, device=device)
         self.grad = None
         self.written = []      # channel intervals of .grad already written during the backward walk (plan time)
 
@@ -141,6 +147,11 @@ def _backend(kind, prob):
     return 1 if fn(C.byref(prob)) == 1 else 0
 
 
+def _pad_ok(v):
+    """True when the channels between v.C and the next multiple of 8 are padding of v's buffer."""
+    return int(v.C % 8 != 0 and v.c0 % 8 == 0 and v.c0 + v.C == v.buf.C)
+
+
 def _mk_igemm(ins, out, w, w_dtype, cin_pad, cout_pad, bias, act, accumulate, stride, taps, out_scale=1.0):
     p = L.DnIgemm()
     for i, v in enumerate(ins):
@@ -156,6 +167,7 @@ def _mk_igemm(ins, out, w, w_dtype, cin_pad, cout_pad, bias, act, accumulate, st
     for i, (s, dh, dw, wt) in enumerate(taps):
         p.taps[i] = L.DnTap(s, dh, dw, wt)
     p.out_scale = out_scale
+    p.out_pad_ok = _pad_ok(out)
     return p
 
 
@@ -282,16 +294,26 @@ class ConvOp(Op):
         self.dwp = torch.zeros((T, self.cout_pad, self.cin_pad), dtype=torch.float32, device=dev)
         k, pad = self.k, self.pad
         # ---- weight-gradient problems
-        self.wg = []
-        if not self.transposed:
-            taps = [(0, kh - pad, kw - pad, kh * k + kw) for kh in range(k) for kw in range(k)]
-            self.wg.append(_mk_wgrad([self.gout], self.x, self.dwp, self.cout_pad, self.cin_pad, self.stride, taps, 1.0))
-        else:
-            for pr in self.fwd_probs:
-                a, b = pr['phase']
-                self.wg.append(_mk_wgrad([self.gout.phase(a, b)], self.x, self.dwp, self.cout_pad, self.cin_pad, 1,
-                                         pr['taps'], 1.0))
-        self.wg = [(p, _backend('wgrad', p), _wgrad_flops(p)) for p in self.wg]
+        def wg_probs(q):
+            probs = []
+            if not self.transposed:
+                taps = [(0, kh - pad, kw - pad, kh * k + kw) for kh in range(k) for kw in range(k)]
+                probs.append(_mk_wgrad([self.gout], q, self.dwp, self.cout_pad, self.cin_pad, self.stride, taps, 1.0))
+            else:
+                for pr in self.fwd_probs:
+                    a, b = pr['phase']
+                    probs.append(_mk_wgrad([self.gout.phase(a, b)], q, self.dwp, self.cout_pad, self.cin_pad, 1, pr['taps'],
+                                           1.0))
+            return [(p, _backend('wgrad', p), _wgrad_flops(p)) for p in probs]
+
+        self.xq = None
+        self.wg = wg_probs(self.x)
+        if plan.prec.act != g and plan.prec.act != torch.float32 and tc_enabled():
+            # kind::f16 MMAs need both operands in one format: use a just-in-time copy of x in the gradient dtype
+            xq = plan.scratch_buf(self.x.N, self.x.H, self.x.W, self.x.C, g).view()
+            alt = wg_probs(xq)
+            if all(be == 1 for _, be, _ in alt):
+                self.xq, self.wg = xq, alt
         # ---- data-gradient problems
         self.dg = []
         if self.needs_dx:
@@ -335,8 +357,11 @@ class ConvOp(Op):
         inv = 1.0 / plan.prec.gscale
         gb = plan.grad_of(self.name + '.bias') if self.has_bias else None
         if self.act != L.ACT_NONE or gb is not None:
-            L.call('dn_act_bwd', self.gout.ref(), self.out.ref(), self.act, L.ptr(gb), inv, plan.stream)
+            L.call('dn_act_bwd', self.gout.ref(), self.out.ref(), self.act, L.ptr(gb), inv, L.ptr(plan.reduce_ws(self.Cout)),
+                   plan.stream)
         self.dwp.zero_()
+        if self.xq is not None:
+            L.call('dn_copy_view', self.x.ref(), self.xq.ref(), 0, plan.stream)
         for p, be, fl in self.wg:
             L.call('dn_wgrad_run', C.byref(p), be, plan.stream, tag=('wgrad', be, fl))
         gw = plan.grad_of(self.name + '.weight')
@@ -374,8 +399,7 @@ class BNOp(Op):
         g, b = plan.param(self.name + '.weight'), plan.param(self.name + '.bias')
         rm, rv = plan.buffer(self.name + '.running_mean'), plan.buffer(self.name + '.running_var')
         if plan.training:
-            self.sums.zero_()
-            L.call('dn_bn_stats', self.y.ref(), L.ptr(self.sums), st)
+            L.call('dn_bn_stats', self.y.ref(), L.ptr(self.sums), L.ptr(plan.reduce_ws(self.y.C)), st)
             plan.buffer(self.name + '.num_batches_tracked').add_(1)
         L.call('dn_bn_finalize', L.ptr(self.sums), self.count, L.ptr(g), L.ptr(b), L.ptr(rm), L.ptr(rv), 0.1, 1e-5,
                int(plan.training), 1, L.ptr(self.mean_invstd), L.ptr(self.scale_shift), self.y.C, st)
@@ -400,10 +424,9 @@ class BNOp(Op):
             return
         st = plan.stream
         gm, bt = plan.param(self.name + '.weight'), plan.param(self.name + '.bias')
-        self.red.zero_()
         res = self.res.ref() if self.res else None
         L.call('dn_bn_bwd_reduce', self.gout.ref(), self.y.ref(), res, L.ptr(self.mean_invstd), L.ptr(gm), L.ptr(bt),
-               self.act, self.pool, L.ptr(self.red), st)
+               self.act, self.pool, L.ptr(self.red), L.ptr(plan.reduce_ws(self.y.C)), st)
         L.call('dn_bn_bwd_apply', self.gout.ref(), self.y.ref(), res, L.ptr(self.mean_invstd), L.ptr(gm), L.ptr(bt),
                self.act, self.pool, L.ptr(self.red), self.count, 1.0 / plan.prec.gscale,
                L.ptr(plan.grad_of(self.name + '.weight')), L.ptr(plan.grad_of(self.name + '.bias')), self.gy.ref(),
@@ -530,6 +553,8 @@ class Plan:
         self._grads = {}
         self.stream = None
         self._bwd_planned = False
+        self._scratch = None
+        self._ws = None
         self.generation = 0
 
     # ---- construction
@@ -547,6 +572,19 @@ class Plan:
 
     def new_buf(self, N, H, W, Cc, dtype=None):
         return Buf(N, H, W, Cc, dtype or self.prec.act, self.device)
+
+    def scratch_buf(self, N, H, W, Cc, dtype):
+        """Buf carved from the plan's shared scratch storage (valid only between consecutive launches)."""
+        need = N * H * W * _ru(Cc, 8) * 4
+        if self._scratch is None or self._scratch.numel() < need:
+            raise RuntimeError('scratch storage too small')
+        return Buf(N, H, W, Cc, dtype, self.device, storage=self._scratch)
+
+    def reduce_ws(self, Cc):
+        need = int(L.lib().dn_reduce_ws_floats(Cc))
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.float32, device=self.device)
+        return self._ws
 
     # ---- run-time lookups
     def param(self, name):
@@ -576,6 +614,8 @@ class Plan:
     def plan_backward(self):
         if self._bwd_planned:
             return
+        big = max([op.x.buf.t.numel() for op in self.ops if isinstance(op, ConvOp)] + [1])
+        self._scratch = torch.empty(big * 4, dtype=torch.uint8, device=self.device)
         for op in reversed(self.ops):
             op.plan_bwd(self)
         self._bwd_planned = True

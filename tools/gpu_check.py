@@ -80,6 +80,13 @@ def section_models(precision):
         guarded('model/%s/%s' % (precision, name), lambda fn=fn: fn(precision))
 
 
+def section_full(precision):
+    import _parity as P
+    guarded('full/%s/Disp_vgg_BN_b4_128x416' % precision, lambda: P.vgg_case(precision, B=4, H=128, W=416))
+    guarded('full/%s/Disp_res_50_b2_128x160' % precision, lambda: P.res50_case(precision, B=2, H=128, W=160))
+    guarded('full/%s/DispNetS_b4_128x416' % precision, lambda: P.dispnets_case(precision, B=4, H=128, W=416))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('section')
@@ -90,7 +97,7 @@ def main():
                                                            torch.cuda.get_device_name(0)), flush=True)
     from supervised_dispnet_b200 import _lib as L
     print('tc_available', L.lib().dn_tc_available(), 'backend env', os.environ.get('DISPNET_B200_BACKEND', 'auto'), flush=True)
-    {'conv': section_conv, 'losses': section_losses, 'models': section_models}[a.section](a.precision)
+    {'conv': section_conv, 'losses': section_losses, 'models': section_models, 'full': section_full}[a.section](a.precision)
     if a.out:
         os.makedirs(os.path.dirname(a.out), exist_ok=True)
         with open(a.out, 'w') as f:
