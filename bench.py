@@ -255,6 +255,17 @@ def run_ours(args):
         key = name if tag is None else '%s[%s,%s]' % (name, tag[0], 'tc' if tag[1] else 'cuda-core')
         t, n, f = agg.get(key, (0.0, 0, 0.0))
         agg[key] = (t + a.elapsed_time(b), n + 1, f + (tag[2] if tag else 0.0))
+    if args.dump:
+        per = {}
+        for name, tag, a, b in L.PROFILE:
+            if tag is None:
+                continue
+            k = '%s %s %s' % (tag[3], tag[0], 'tc' if tag[1] else 'cc')
+            t, f = per.get(k, (0.0, 0.0))
+            per[k] = (t + a.elapsed_time(b) / nprof, f + tag[2] / nprof)
+        with open(args.dump, 'w') as fh:
+            for k, (t, f) in sorted(per.items(), key=lambda kv: -kv[1][0]):
+                fh.write('%-44s %8.3f ms %9.2f GFLOP %8.1f TFLOP/s\n' % (k, t, f / 1e9, f / (t * 1e-3) / 1e12 if t > 0 else 0))
     L.PROFILE = None
     tc_t = sum(t for k, (t, n, f) in agg.items() if k.startswith('dn_igemm_run') and 'tc' in k) / nprof
     tc_f = sum(f for k, (t, n, f) in agg.items() if k.startswith('dn_igemm_run') and 'tc' in k) / nprof
@@ -298,6 +309,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours')
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--dump', default=None, help='write per-layer conv kernel timings of the roofline pass here')
     ap.add_argument('--minimal', action='store_true', help='warm-up + timed steps only (for runs under ncu)')
     args = ap.parse_args()
     if args.impl == 'reference':

@@ -437,14 +437,28 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(dn_view y, float* __restr
 #pragma unroll
   for (int i = 0; i < 2 * CH; ++i) acc[i] = 0.f;
   if (cvalid) {
-    for (long long px = (long long)blockIdx.x * PLn + pl; px < npix; px += (long long)gridDim.x * PLn) {
-      int w = (int)(px % y.W);
-      long long q = px / y.W;
-      int h = (int)(q % y.H), n = (int)(q / y.H);
-      float f[CH];
-      ldc<CH>(y, dn_off(y, n, h, w) + c0, f);
+    // 4 independent 16-byte loads in flight per thread (HBM latency hiding), tail handled by the validity flags
+    const unsigned stride = gridDim.x * PLn;
+    for (unsigned px0 = blockIdx.x * PLn + pl; px0 < (unsigned)npix; px0 += 4 * stride) {
+      float f[4][CH];
+      bool ok[4];
 #pragma unroll
-      for (int i = 0; i < CH; ++i) { acc[i] += f[i]; acc[CH + i] = fmaf(f[i], f[i], acc[CH + i]); }
+      for (int u = 0; u < 4; ++u) {
+        const unsigned px = px0 + u * stride;
+        ok[u] = px < (unsigned)npix;
+        const unsigned pc = ok[u] ? px : px0;
+        const unsigned q = pc / (unsigned)y.W;
+        const int w = (int)(pc - q * (unsigned)y.W);
+        const int n = (int)(q / (unsigned)y.H);
+        const int h = (int)(q - (unsigned)n * (unsigned)y.H);
+        ldc<CH>(y, dn_off(y, n, h, w) + c0, f[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (ok[u]) {
+#pragma unroll
+          for (int i = 0; i < CH; ++i) { acc[i] += f[u][i]; acc[CH + i] = fmaf(f[u][i], f[u][i], acc[CH + i]); }
+        }
     }
   }
   cg_block_reduce<2 * CH>(acc, CGb);
@@ -535,10 +549,11 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(dn_view y, const float* _
     sc[i] = scale_shift[c];
     sh[i] = scale_shift[out.C + c];
   }
-  for (long long px = (long long)blockIdx.x * PLn + pl; px < npix; px += (long long)gridDim.x * PLn) {
-    int w = (int)(px % out.W);
-    long long q = px / out.W;
-    int h = (int)(q % out.H), n = (int)(q / out.H);
+  for (unsigned px = blockIdx.x * PLn + pl; px < (unsigned)npix; px += gridDim.x * PLn) {
+    const unsigned q = px / (unsigned)out.W;
+    const int w = (int)(px - q * (unsigned)out.W);
+    const int n = (int)(q / (unsigned)out.H);
+    const int h = (int)(q - (unsigned)n * (unsigned)out.H);
     float o[CH];
     if (pool) {
 #pragma unroll
@@ -590,84 +605,107 @@ DN_EXPORT int dn_bn_apply(const dn_view* y, const float* scale_shift, const dn_v
   return 0;
 }
 
-// routes dout of one output pixel back to the (up to 4) y positions: dyhat[k] for k = a*2+b
-template <int CH>
-__device__ __forceinline__ void bn_route(const dn_view& y, const dn_view& res, int has_res, const dn_view& dout, int n, int h,
-                                         int w, int c0, const float* sc, const float* sh, int act, int pool,
-                                         float (*yv)[CH], float (*dyh)[CH]) {
-  float g[CH];
-  ldc<CH>(dout, dn_off(dout, n, h, w) + c0, g);
-  if (pool) {
-    float best[CH];
-    int bi[CH];
+// Backward of BatchNorm(+residual)+act(+2x2 max pool).  POOL is a compile-time switch so that the un-pooled path keeps
+// a small register footprint (occupancy is what hides HBM latency here); the pooled path keeps the four window values
+// in registers, finds the arg-max (first maximum wins, as ATen's max_pool2d) and routes the gradient to it.
+// Per-channel constants live in shared memory ([6][C+CH]: scale, shift, mean, invstd, m1, m2) to keep registers for loads.
+template <int CH, bool POOL>
+struct BnBwdPix {
+  float yv[POOL ? 4 : 1][CH];
+  float g[CH];          // dout * act'(.) of the selected position (pooled) / of the pixel
+  unsigned sel;         // pooled: 2 bits per channel, which of the 4 window positions receives g
+
+  __device__ __forceinline__ void load(const dn_view& y, const dn_view& res, int has_res, const dn_view& dout, int n, int h,
+                                       int w, int c0, const float* __restrict__ sc, const float* __restrict__ sh, int act) {
+    ldc<CH>(dout, dn_off(dout, n, h, w) + c0, g);
+    sel = 0;
+    if (POOL) {
 #pragma unroll
-    for (int i = 0; i < CH; ++i) { best[i] = -INFINITY; bi[i] = 0; }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      ldc<CH>(y, dn_off(y, n, 2 * h + (k >> 1), 2 * w + (k & 1)) + c0, yv[k]);
+      for (int k = 0; k < 4; ++k) ldc<CH>(y, dn_off(y, n, 2 * h + (k >> 1), 2 * w + (k & 1)) + c0, yv[POOL ? k : 0]);
 #pragma unroll
       for (int i = 0; i < CH; ++i) {
-        float v = dn_act(fmaf(yv[k][i], sc[i], sh[i]), act);
-        if (v > best[i]) { best[i] = v; bi[i] = k; }
+        float best = -INFINITY;
+        unsigned bk = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float v = dn_act(fmaf(yv[POOL ? k : 0][i], sc[i], sh[i]), act);
+          if (v > best) { best = v; bk = k; }
+        }
+        g[i] *= dn_act_grad(best, act);
+        sel |= bk << (2 * i);
+      }
+    } else {
+      ldc<CH>(y, dn_off(y, n, h, w) + c0, yv[0]);
+      float r[CH];
+      if (has_res) ldc<CH>(res, dn_off(res, n, h, w) + c0, r);
+#pragma unroll
+      for (int i = 0; i < CH; ++i) {
+        float v = fmaf(yv[0][i], sc[i], sh[i]);
+        if (has_res) v += r[i];
+        g[i] *= dn_act_grad(dn_act(v, act), act);
       }
     }
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-#pragma unroll
-      for (int i = 0; i < CH; ++i) dyh[k][i] = (bi[i] == k) ? g[i] * dn_act_grad(best[i], act) : 0.f;
-  } else {
-    ldc<CH>(y, dn_off(y, n, h, w) + c0, yv[0]);
-    float r[CH];
-    if (has_res) ldc<CH>(res, dn_off(res, n, h, w) + c0, r);
-#pragma unroll
-    for (int i = 0; i < CH; ++i) {
-      float v = fmaf(yv[0][i], sc[i], sh[i]);
-      if (has_res) v += r[i];
-      dyh[0][i] = g[i] * dn_act_grad(dn_act(v, act), act);
-    }
   }
-}
+  __device__ __forceinline__ int which(int i) const { return POOL ? (int)((sel >> (2 * i)) & 3u) : 0; }
+  __device__ __forceinline__ float dyhat(int k, int i) const { return (!POOL || which(i) == k) ? g[i] : 0.f; }
+  __device__ __forceinline__ float ysel(int i) const {
+    float v = yv[0][i];
+    if (POOL) {
+      const int k = which(i);
+      v = k == 1 ? yv[POOL ? 1 : 0][i] : v;
+      v = k == 2 ? yv[POOL ? 2 : 0][i] : v;
+      v = k == 3 ? yv[POOL ? 3 : 0][i] : v;
+    }
+    return v;
+  }
+};
 
-template <int CH>
-__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(dn_view dout, dn_view y, dn_view res, int has_res,
-                                                            const float* __restrict__ mean_invstd, const float* __restrict__ gamma,
-                                                            const float* __restrict__ beta, int act, int pool, float* __restrict__ ws, int CGb) {
+template <int CH, bool POOL>
+__global__ void __launch_bounds__(256, 2) bn_bwd_reduce_kernel(dn_view dout, dn_view y, dn_view res, int has_res,
+                                                               const float* __restrict__ mean_invstd, const float* __restrict__ gamma,
+                                                               const float* __restrict__ beta, int act, float* __restrict__ ws, int CGb) {
+  extern __shared__ float cst[];
   CG_PROLOGUE(dout)
   const int C = dout.C;
+  const int Cs = C + CH;    // padded stride so that a tail channel group can read past C
+  for (int c = threadIdx.x; c < 4 * Cs; c += blockDim.x) cst[c] = 0.f;
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float mean = mean_invstd[c], istd = mean_invstd[C + c], sc, sh;
+    bn_scale_shift(gamma ? gamma[c] : 1.f, beta ? beta[c] : 0.f, mean, istd, sc, sh);
+    cst[c] = sc; cst[Cs + c] = sh; cst[2 * Cs + c] = mean; cst[3 * Cs + c] = istd;
+  }
+  __syncthreads();
   float acc[2 * CH];
 #pragma unroll
   for (int i = 0; i < 2 * CH; ++i) acc[i] = 0.f;
   if (cvalid) {
-    float sc[CH], sh[CH], mean[CH], istd[CH];
+    const float* sc = cst + c0;
+    const float* sh = cst + Cs + c0;
+    const float* mean = cst + 2 * Cs + c0;
+    const float* istd = cst + 3 * Cs + c0;
+    for (unsigned px = blockIdx.x * PLn + pl; px < (unsigned)npix; px += gridDim.x * PLn) {
+      const unsigned q = px / (unsigned)dout.W;
+      const int w = (int)(px - q * (unsigned)dout.W);
+      const int n = (int)(q / (unsigned)dout.H);
+      const int h = (int)(q - (unsigned)n * (unsigned)dout.H);
+      BnBwdPix<CH, POOL> P;
+      P.load(y, res, has_res, dout, n, h, w, c0, sc, sh, act);
 #pragma unroll
-    for (int i = 0; i < CH; ++i) {
-      int c = c0 + i < C ? c0 + i : C - 1;
-      mean[i] = mean_invstd[c]; istd[i] = mean_invstd[C + c];
-      bn_scale_shift(gamma ? gamma[c] : 1.f, beta ? beta[c] : 0.f, mean[i], istd[i], sc[i], sh[i]);
-    }
-    const int np = pool ? 4 : 1;
-    for (long long px = (long long)blockIdx.x * PLn + pl; px < npix; px += (long long)gridDim.x * PLn) {
-      int w = (int)(px % dout.W);
-      long long q = px / dout.W;
-      int h = (int)(q % dout.H), n = (int)(q / dout.H);
-      float yv[4][CH], dyh[4][CH];
-      bn_route<CH>(y, res, has_res, dout, n, h, w, c0, sc, sh, act, pool, yv, dyh);
-      for (int k = 0; k < np; ++k)
-#pragma unroll
-        for (int i = 0; i < CH; ++i) {
-          acc[i] += dyh[k][i];
-          acc[CH + i] = fmaf(dyh[k][i], (yv[k][i] - mean[i]) * istd[i], acc[CH + i]);
-        }
+      for (int i = 0; i < CH; ++i) {
+        acc[i] += P.g[i];
+        acc[CH + i] = fmaf(P.g[i], (P.ysel(i) - mean[i]) * istd[i], acc[CH + i]);
+      }
     }
   }
   cg_block_reduce<2 * CH>(acc, CGb);
   if (threadIdx.x < CGb && cvalid) {
-    float* w = ws + (long long)blockIdx.x * 2 * C;
+    float* wsp = ws + (long long)blockIdx.x * 2 * C;
 #pragma unroll
     for (int i = 0; i < CH; ++i)
       if (c0 + i < C) {
-        w[c0 + i] = acc[i];
-        w[C + c0 + i] = acc[CH + i];
+        wsp[c0 + i] = acc[i];
+        wsp[C + c0 + i] = acc[CH + i];
       }
   }
 }
@@ -678,58 +716,69 @@ DN_EXPORT int dn_bn_bwd_reduce(const dn_view* dout, const dn_view* y, const dn_v
   long long npix = (long long)dout->N * dout->H * dout->W;
   dn_view r = residual ? *residual : *y;
   bool vec = dn_vec8_ok(y) && dn_vec8_ok(dout) && (!residual || dn_vec8_ok(residual));
-  CgGeom g;
-  if (vec) {
-    g = cg_geom(dout->C, 8, npix);
-    bn_bwd_reduce_kernel<8><<<g.grid, 256, 0, dn_stream(stream)>>>(*dout, *y, r, residual != nullptr, mean_invstd, gamma, beta, act, pool, ws, g.CGb);
-  } else {
-    g = cg_geom(dout->C, 1, npix);
-    bn_bwd_reduce_kernel<1><<<g.grid, 256, 0, dn_stream(stream)>>>(*dout, *y, r, residual != nullptr, mean_invstd, gamma, beta, act, pool, ws, g.CGb);
-  }
+  cudaStream_t st = dn_stream(stream);
+  const int ch = vec ? 8 : 1;
+  CgGeom g = cg_geom(dout->C, ch, npix);
+  const int hr = residual != nullptr;
+  const size_t sm = sizeof(float) * 4 * (dout->C + ch);
+  if (vec && pool) bn_bwd_reduce_kernel<8, true><<<g.grid, 256, sm, st>>>(*dout, *y, r, hr, mean_invstd, gamma, beta, act, ws, g.CGb);
+  else if (vec) bn_bwd_reduce_kernel<8, false><<<g.grid, 256, sm, st>>>(*dout, *y, r, hr, mean_invstd, gamma, beta, act, ws, g.CGb);
+  else if (pool) bn_bwd_reduce_kernel<1, true><<<g.grid, 256, sm, st>>>(*dout, *y, r, hr, mean_invstd, gamma, beta, act, ws, g.CGb);
+  else bn_bwd_reduce_kernel<1, false><<<g.grid, 256, sm, st>>>(*dout, *y, r, hr, mean_invstd, gamma, beta, act, ws, g.CGb);
   DN_CHECK_LAUNCH();
-  reduce_partials_kernel<double><<<(2 * dout->C + 127) / 128, 128, 0, dn_stream(stream)>>>(ws, g.grid.x, 2 * dout->C, red, 1.0);
+  reduce_partials_kernel<double><<<(2 * dout->C + 127) / 128, 128, 0, st>>>(ws, g.grid.x, 2 * dout->C, red, 1.0);
   DN_CHECK_LAUNCH();
   return 0;
 }
 
-template <int CH>
-__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(dn_view dout, dn_view y, dn_view res, int has_res,
-                                                           const float* __restrict__ mean_invstd, const float* __restrict__ gamma,
-                                                           const float* __restrict__ beta, int act, int pool,
-                                                           const double* __restrict__ red, double count, float gscale,
-                                                           float* dgamma, float* dbeta, dn_view dy, dn_view dres, int has_dres,
-                                                           int dres_acc, int CGb) {
+template <int CH, bool POOL>
+__global__ void __launch_bounds__(256, 2) bn_bwd_apply_kernel(dn_view dout, dn_view y, dn_view res, int has_res,
+                                                              const float* __restrict__ mean_invstd, const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta, int act,
+                                                              const double* __restrict__ red, double count, float gscale,
+                                                              float* dgamma, float* dbeta, dn_view dy, dn_view dres, int has_dres,
+                                                              int dres_acc, int CGb) {
+  extern __shared__ float cst[];
   CG_PROLOGUE(dout)
   const int C = dout.C;
-  if (!cvalid) return;
-  float sc[CH], sh[CH], mean[CH], istd[CH], m1[CH], m2[CH];
-#pragma unroll
-  for (int i = 0; i < CH; ++i) {
-    int c = c0 + i < C ? c0 + i : C - 1;
-    mean[i] = mean_invstd[c]; istd[i] = mean_invstd[C + c];
-    bn_scale_shift(gamma ? gamma[c] : 1.f, beta ? beta[c] : 0.f, mean[i], istd[i], sc[i], sh[i]);
-    m1[i] = (float)(red[c] / count);
-    m2[i] = (float)(red[C + c] / count);
-    if (blockIdx.x == 0 && pl == 0 && c0 + i < C) {
+  const int Cs = C + CH;
+  for (int c = threadIdx.x; c < 6 * Cs; c += blockDim.x) cst[c] = 0.f;
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float mean = mean_invstd[c], istd = mean_invstd[C + c], sc, sh;
+    bn_scale_shift(gamma ? gamma[c] : 1.f, beta ? beta[c] : 0.f, mean, istd, sc, sh);
+    cst[c] = sc; cst[Cs + c] = sh; cst[2 * Cs + c] = mean; cst[3 * Cs + c] = istd;
+    cst[4 * Cs + c] = (float)(red[c] / count);
+    cst[5 * Cs + c] = (float)(red[C + c] / count);
+    if (blockIdx.x == 0 && blockIdx.y == 0) {
       if (dgamma) dgamma[c] = (float)(red[C + c] * (double)gscale);
       if (dbeta) dbeta[c] = (float)(red[c] * (double)gscale);
     }
   }
-  const int np = pool ? 4 : 1;
-  for (long long px = (long long)blockIdx.x * PLn + pl; px < npix; px += (long long)gridDim.x * PLn) {
-    int w = (int)(px % dout.W);
-    long long q = px / dout.W;
-    int h = (int)(q % dout.H), n = (int)(q / dout.H);
-    float yv[4][CH], dyh[4][CH];
-    bn_route<CH>(y, res, has_res, dout, n, h, w, c0, sc, sh, act, pool, yv, dyh);
-    for (int k = 0; k < np; ++k) {
+  __syncthreads();
+  if (!cvalid) return;
+  const float* sc = cst + c0;
+  const float* sh = cst + Cs + c0;
+  const float* mean = cst + 2 * Cs + c0;
+  const float* istd = cst + 3 * Cs + c0;
+  const float* m1 = cst + 4 * Cs + c0;
+  const float* m2 = cst + 5 * Cs + c0;
+  for (unsigned px = blockIdx.x * PLn + pl; px < (unsigned)npix; px += gridDim.x * PLn) {
+    const unsigned q = px / (unsigned)dout.W;
+    const int w = (int)(px - q * (unsigned)dout.W);
+    const int n = (int)(q / (unsigned)dout.H);
+    const int h = (int)(q - (unsigned)n * (unsigned)dout.H);
+    BnBwdPix<CH, POOL> P;
+    P.load(y, res, has_res, dout, n, h, w, c0, sc, sh, act);
+#pragma unroll
+    for (int k = 0; k < (POOL ? 4 : 1); ++k) {
       float o[CH];
 #pragma unroll
       for (int i = 0; i < CH; ++i) {
-        float xh = (yv[k][i] - mean[i]) * istd[i];
-        o[i] = sc[i] * (dyh[k][i] - m1[i] - xh * m2[i]);
+        float xh = (P.yv[POOL ? k : 0][i] - mean[i]) * istd[i];
+        o[i] = sc[i] * (P.dyhat(k, i) - m1[i] - xh * m2[i]);
       }
-      int hh = pool ? 2 * h + (k >> 1) : h, ww = pool ? 2 * w + (k & 1) : w;
+      int hh = POOL ? 2 * h + (k >> 1) : h, ww = POOL ? 2 * w + (k & 1) : w;
       stc<CH>(dy, dn_off(dy, n, hh, ww) + c0, o);
     }
     if (has_dres) {
@@ -737,7 +786,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(dn_view dout, dn_view
       long long off = dn_off(dres, n, h, w) + c0;
       if (dres_acc) ldc<CH>(dres, off, o);
 #pragma unroll
-      for (int i = 0; i < CH; ++i) o[i] = dres_acc ? o[i] + dyh[0][i] : dyh[0][i];
+      for (int i = 0; i < CH; ++i) o[i] = dres_acc ? o[i] + P.g[i] : P.g[i];
       stc<CH>(dres, off, o);
     }
   }
@@ -752,13 +801,19 @@ DN_EXPORT int dn_bn_bwd_apply(const dn_view* dout, const dn_view* y, const dn_vi
   dn_view r = residual ? *residual : *y;
   dn_view dr = dres ? *dres : *dy;
   bool vec = dn_vec8_ok(y) && dn_vec8_ok(dout) && dn_vec8_ok(dy) && (!residual || dn_vec8_ok(residual)) && (!dres || dn_vec8_ok(dres));
-  if (vec) {
-    CgGeom g = cg_geom(dout->C, 8, npix);
-    bn_bwd_apply_kernel<8><<<g.grid, 256, 0, dn_stream(stream)>>>(*dout, *y, r, residual != nullptr, mean_invstd, gamma, beta, act, pool, red, count, gscale, dgamma, dbeta, *dy, dr, dres != nullptr, dres_accumulate, g.CGb);
-  } else {
-    CgGeom g = cg_geom(dout->C, 1, npix);
-    bn_bwd_apply_kernel<1><<<g.grid, 256, 0, dn_stream(stream)>>>(*dout, *y, r, residual != nullptr, mean_invstd, gamma, beta, act, pool, red, count, gscale, dgamma, dbeta, *dy, dr, dres != nullptr, dres_accumulate, g.CGb);
-  }
+  cudaStream_t st = dn_stream(stream);
+  const int ch = vec ? 8 : 1;
+  CgGeom g = cg_geom(dout->C, ch, npix);
+  const int hr = residual != nullptr, hd = dres != nullptr;
+  const size_t sm = sizeof(float) * 6 * (dout->C + ch);
+#define BN_BWD_APPLY(CHV, PV)                                                                                               \
+  bn_bwd_apply_kernel<CHV, PV><<<g.grid, 256, sm, st>>>(*dout, *y, r, hr, mean_invstd, gamma, beta, act, red, count, gscale, \
+                                                        dgamma, dbeta, *dy, dr, hd, dres_accumulate, g.CGb)
+  if (vec && pool) BN_BWD_APPLY(8, true);
+  else if (vec) BN_BWD_APPLY(8, false);
+  else if (pool) BN_BWD_APPLY(1, true);
+  else BN_BWD_APPLY(1, false);
+#undef BN_BWD_APPLY
   DN_CHECK_LAUNCH();
   return 0;
 }
@@ -771,10 +826,11 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(dn_view dout, dn_view out,
 #pragma unroll
   for (int i = 0; i < CH; ++i) acc[i] = 0.f;
   if (cvalid) {
-    for (long long px = (long long)blockIdx.x * PLn + pl; px < npix; px += (long long)gridDim.x * PLn) {
-      int w = (int)(px % dout.W);
-      long long q = px / dout.W;
-      int h = (int)(q % dout.H), n = (int)(q / dout.H);
+    for (unsigned px = blockIdx.x * PLn + pl; px < (unsigned)npix; px += gridDim.x * PLn) {
+      const unsigned q = px / (unsigned)dout.W;
+      const int w = (int)(px - q * (unsigned)dout.W);
+      const int n = (int)(q / (unsigned)dout.H);
+      const int h = (int)(q - (unsigned)n * (unsigned)dout.H);
       float g[CH], o[CH];
       long long off = dn_off(dout, n, h, w) + c0;
       ldc<CH>(dout, off, g);
@@ -910,14 +966,15 @@ DN_EXPORT int dn_maxpool_bwd(const dn_view* dout, const dn_view* x, const dn_vie
 // mode 0: out = act(a + b?)   mode 1: copy/accumulate   mode 2: add_act backward
 template <int CH>
 __global__ void __launch_bounds__(256) ew_fwd_kernel(dn_view a, dn_view b, int has_b, int act, dn_view out, int accumulate) {
-  const int CG = (out.C + CH - 1) / CH;
-  long long total = (long long)out.N * out.H * out.W * CG;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    int c0 = (int)(i % CG) * CH;
-    long long q = i / CG;
-    int w = (int)(q % out.W); q /= out.W;
-    int h = (int)(q % out.H);
-    int n = (int)(q / out.H);
+  const unsigned CG = (out.C + CH - 1) / CH;
+  const unsigned total = (unsigned)out.N * out.H * out.W * CG;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    unsigned q = i / CG;
+    const int c0 = (int)(i - q * CG) * CH;
+    unsigned q2 = q / (unsigned)out.W;
+    const int w = (int)(q - q2 * (unsigned)out.W);
+    const int n = (int)(q2 / (unsigned)out.H);
+    const int h = (int)(q2 - (unsigned)n * (unsigned)out.H);
     float fa[CH], fb[CH], fo[CH];
     ldc<CH>(a, dn_off(a, n, h, w) + c0, fa);
     if (has_b) ldc<CH>(b, dn_off(b, n, h, w) + c0, fb);
@@ -960,14 +1017,15 @@ DN_EXPORT int dn_copy_view(const dn_view* src, const dn_view* dst, int accumulat
 template <int CH>
 __global__ void __launch_bounds__(256) add_act_bwd_kernel(dn_view dout, dn_view out, int act, dn_view da, int da_acc, int has_da,
                                                           dn_view db, int db_acc, int has_db) {
-  const int CG = (dout.C + CH - 1) / CH;
-  long long total = (long long)dout.N * dout.H * dout.W * CG;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    int c0 = (int)(i % CG) * CH;
-    long long q = i / CG;
-    int w = (int)(q % dout.W); q /= dout.W;
-    int h = (int)(q % dout.H);
-    int n = (int)(q / dout.H);
+  const unsigned CG = (dout.C + CH - 1) / CH;
+  const unsigned total = (unsigned)dout.N * dout.H * dout.W * CG;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    unsigned q = i / CG;
+    const int c0 = (int)(i - q * CG) * CH;
+    unsigned q2 = q / (unsigned)dout.W;
+    const int w = (int)(q - q2 * (unsigned)dout.W);
+    const int n = (int)(q2 / (unsigned)dout.H);
+    const int h = (int)(q2 - (unsigned)n * (unsigned)dout.H);
     float g[CH], o[CH], t[CH];
     ldc<CH>(dout, dn_off(dout, n, h, w) + c0, g);
     if (act != DN_ACT_NONE) {

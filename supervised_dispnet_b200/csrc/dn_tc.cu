@@ -337,12 +337,15 @@ struct WgradTcParams {
   CUtensorMap tmQ;
   TcTap taps[kMaxTcTaps];
   int ntaps;
+  int tpc, ngroups;        // taps per CTA (they share the dy tile), number of tap groups
   int wb, hb, nb;          // pixel box, wb*hb*nb == KPX
   int tilesW, tilesH, tilesN, num_ptiles;
   int cp_tiles, cq_tiles;  // output tiles: 128 x BNQ
   int cp_blocks;           // 64-channel blocks of P actually present in a cp tile (1 or 2)
   int splits, ptiles_per_split;
   int stages;
+  int n_mma;               // MMA N per tap (multiple of 16, <= BNQ)
+  int tmem_cols;
   uint32_t idesc;
   float* dw;
   int cp, cq, cp_pad, cq_pad;
@@ -356,9 +359,8 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr uint32_t BLK_BYTES = KPX * 128;              // one [KPX px][64 ch] swizzled block
   constexpr uint32_t A_BYTES = 2 * BLK_BYTES;            // M = 128 channels of P
-  constexpr uint32_t B_BYTES = (BNQ / 64) * BLK_BYTES;
-  constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
-  constexpr uint32_t TMEM_COLS = BNQ <= 32 ? 32 : BNQ <= 64 ? 64 : BNQ <= 128 ? 128 : 256;
+  constexpr uint32_t B_BYTES = (BNQ / 64) * BLK_BYTES;   // per tap
+  const uint32_t STAGE_BYTES = A_BYTES + (uint32_t)p.tpc * B_BYTES;
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int stages = p.stages;
   uint64_t* full_bar = (uint64_t*)(smem + (size_t)stages * STAGE_BYTES);
@@ -369,19 +371,22 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  // work item: (tap, cp tile, cq tile, split)
+  // work item: tap group fastest so that CTAs running together share the same pixel range in L2
   int item = blockIdx.x;
-  const int split = item % p.splits; item /= p.splits;
+  const int grp = item % p.ngroups; item /= p.ngroups;
   const int cqt = item % p.cq_tiles; item /= p.cq_tiles;
   const int cpt = item % p.cp_tiles; item /= p.cp_tiles;
-  const TcTap tap = p.taps[item];
+  const int split = item;
+  const int t0 = grp * p.tpc;
+  const int nt = (p.ntaps - t0) < p.tpc ? (p.ntaps - t0) : p.tpc;
+  const int src = p.taps[t0].src;     // all taps of one launch share the dy view
   const int pt_beg = split * p.ptiles_per_split;
   int pt_end = pt_beg + p.ptiles_per_split;
   if (pt_end > p.num_ptiles) pt_end = p.num_ptiles;
   const int n_iters = pt_end - pt_beg;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&p.tmP[tap.src]);
+    tma_prefetch_desc(&p.tmP[src]);
     tma_prefetch_desc(&p.tmQ);
     for (int s = 0; s < stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     mbar_init(done_bar, 1);
@@ -389,7 +394,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
     fence_proxy_async();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_ptr, TMEM_COLS);
+    tmem_alloc(tmem_ptr, (uint32_t)p.tmem_cols);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -397,8 +402,8 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  // bytes that really arrive per stage: only the P blocks that exist are loaded
-  const uint32_t tx_bytes = (uint32_t)p.cp_blocks * BLK_BYTES + B_BYTES;
+  // bytes that really arrive per stage: only the P blocks that exist and the taps of this group are loaded
+  const uint32_t tx_bytes = (uint32_t)p.cp_blocks * BLK_BYTES + (uint32_t)nt * B_BYTES;
 
   if (n_iters > 0) {
     if (warp == 0) {
@@ -412,13 +417,16 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
           const int w0 = tw * p.wb, h0 = th * p.hb, n0 = tn * p.nb;
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + (size_t)stage * STAGE_BYTES;
-          uint8_t* sb = sa + A_BYTES;
           mbar_expect_tx(&full_bar[stage], tx_bytes);
           for (int j = 0; j < p.cp_blocks; ++j)
-            tma_load_4d(sa + j * BLK_BYTES, &p.tmP[tap.src], &full_bar[stage], cpt * 128 + j * 64, w0, h0, n0);
+            tma_load_4d(sa + j * BLK_BYTES, &p.tmP[src], &full_bar[stage], cpt * 128 + j * 64, w0, h0, n0);
+          for (int t = 0; t < nt; ++t) {
+            const TcTap tap = p.taps[t0 + t];
+            uint8_t* sb = sa + A_BYTES + (size_t)t * B_BYTES;
 #pragma unroll
-          for (int j = 0; j < BNQ / 64; ++j)
-            tma_load_4d(sb + j * BLK_BYTES, &p.tmQ, &full_bar[stage], cqt * BNQ + j * 64, w0 + tap.dw, h0 + tap.dh, n0);
+            for (int j = 0; j < BNQ / 64; ++j)
+              tma_load_4d(sb + j * BLK_BYTES, &p.tmQ, &full_bar[stage], cqt * BNQ + j * 64, w0 + tap.dw, h0 + tap.dh, n0);
+          }
           if (++stage == stages) { stage = 0; phase ^= 1; }
         }
       }
@@ -429,13 +437,15 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + (size_t)stage * STAGE_BYTES);
-          const uint32_t sb = sa + A_BYTES;
+          for (int t = 0; t < nt; ++t) {
+            const uint32_t sb = sa + A_BYTES + (uint32_t)t * B_BYTES;
 #pragma unroll
-          for (int k = 0; k < KPX / 16; ++k) {
-            // MN-major, 128B swizzle: LBO = distance between 64-channel blocks, SBO = 8 pixel rows = 1024 B
-            const uint64_t ad = make_desc(sa + k * 2048, BLK_BYTES, 1024);
-            const uint64_t bd = make_desc(sb + k * 2048, BLK_BYTES, 1024);
-            umma_f16(tmem_base, ad, bd, p.idesc, (it > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < KPX / 16; ++k) {
+              // MN-major, 128B swizzle: LBO = distance between 64-channel blocks, SBO = 8 pixel rows = 1024 B
+              const uint64_t ad = make_desc(sa + k * 2048, BLK_BYTES, 1024);
+              const uint64_t bd = make_desc(sb + k * 2048, BLK_BYTES, 1024);
+              umma_f16(tmem_base + (uint32_t)(t * p.n_mma), ad, bd, p.idesc, (it > 0 || k > 0) ? 1u : 0u);
+            }
           }
           umma_commit(&empty_bar[stage]);
           if (it == n_iters - 1) umma_commit(done_bar);
@@ -448,18 +458,20 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
       const int cp = cpt * 128 + row;
       mbar_wait(done_bar, 0);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-      float* drow = p.dw + ((size_t)tap.wt * p.cp_pad + cp) * p.cq_pad + cqt * BNQ;
+      for (int t = 0; t < nt; ++t) {
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * p.n_mma);
+        float* drow = p.dw + ((size_t)p.taps[t0 + t].wt * p.cp_pad + cp) * p.cq_pad + cqt * BNQ;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BNQ; c0 += 16) {
-        uint32_t r[16];
-        tmem_ld16(taddr + c0, r);
-        tmem_ld_wait();
-        if (cp < p.cp && cqt * BNQ + c0 < p.cq_pad) {
+        for (int c0 = 0; c0 < p.n_mma; c0 += 16) {
+          uint32_t r[16];
+          tmem_ld16(taddr + c0, r);
+          tmem_ld_wait();
+          if (cp < p.cp && cqt * BNQ + c0 < p.cq_pad) {
 #pragma unroll
-          for (int j = 0; j < 16; j += 4)
-            red_add_v4(drow + c0 + j, __uint_as_float(r[j]) * p.scale, __uint_as_float(r[j + 1]) * p.scale,
-                       __uint_as_float(r[j + 2]) * p.scale, __uint_as_float(r[j + 3]) * p.scale);
+            for (int j = 0; j < 16; j += 4)
+              red_add_v4(drow + c0 + j, __uint_as_float(r[j]) * p.scale, __uint_as_float(r[j + 1]) * p.scale,
+                         __uint_as_float(r[j + 2]) * p.scale, __uint_as_float(r[j + 3]) * p.scale);
+          }
         }
       }
     }
@@ -468,7 +480,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
   }
 }
 
@@ -534,6 +546,10 @@ uint32_t make_idesc(int a_dtype, int b_dtype, int a_mn_major, int b_mn_major, in
 }
 
 int pick_bn(int cout_pad) {
+  if (cout_pad > 256) {   // several N tiles: the largest tile width that divides the (16-aligned) channel count
+    for (int bn = 256; bn >= 16; bn >>= 1)
+      if (cout_pad % bn == 0) return bn;
+  }
   if (cout_pad > 128) return 256;
   if (cout_pad > 64) return 128;
   if (cout_pad > 32) return 64;
@@ -560,8 +576,8 @@ int launch_igemm(const IgemmTcParams& P, cudaStream_t st) {
 
 template <int BNQ>
 int launch_wgrad(const WgradTcParams& P, int items, cudaStream_t st) {
-  constexpr uint32_t STAGE_BYTES = 2 * KPX * 128 + (BNQ / 64) * KPX * 128;
-  size_t smem = (size_t)P.stages * STAGE_BYTES + 1024 + (2 * P.stages + 1) * 8 + 16;
+  const uint32_t stage_bytes = 2 * KPX * 128 + (uint32_t)P.tpc * (BNQ / 64) * KPX * 128;
+  size_t smem = (size_t)P.stages * stage_bytes + 1024 + (2 * P.stages + 1) * 8 + 16;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<BNQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -598,7 +614,6 @@ DN_EXPORT int dn_igemm_tc_supported(const dn_igemm* p) {
     if (!view_tma_ok(p->in[s]) || p->in[s].dtype != p->w_dtype) return 0;
     if (p->in[s].C != p->in[0].C) return 0;
   }
-  if (p->cout_pad > 256 && (p->cout_pad % 256) != 0) return 0;
   return 1;
 }
 
@@ -695,16 +710,36 @@ int dn_wgrad_tc(const dn_wgrad* p, cudaStream_t st) {
   P.cp_tiles = (P0.C + 127) / 128;
   P.cq_tiles = (p->cq_pad + BNQ - 1) / BNQ;
   P.cp_blocks = P0.C > 64 ? 2 : 1;
-  const int out_tiles = P.ntaps * P.cp_tiles * P.cq_tiles;
+  P.n_mma = BNQ;
+  if (P.cq_tiles == 1) {
+    int n16 = (p->q.C + 15) / 16 * 16;
+    if (n16 < BNQ) P.n_mma = n16;
+  }
+  // taps that share one dy tile in a CTA: bounded by TMEM columns (512) and by keeping >= 3 pipeline stages
+  const uint32_t a_bytes = 2 * KPX * 128, b_bytes = (BNQ / 64) * KPX * 128;
+  int tpc = 512 / P.n_mma;
+  int by_smem = (int)((64 * 1024 - a_bytes) / b_bytes);
+  if (by_smem < 1) by_smem = 1;
+  if (tpc > by_smem) tpc = by_smem;
+  if (tpc > P.ntaps) tpc = P.ntaps;
+  // all taps of a group must read the same dy view
+  for (int t = 1; t < P.ntaps; ++t)
+    if (p->taps[t].src != p->taps[0].src) { tpc = 1; break; }
+  P.ngroups = (P.ntaps + tpc - 1) / tpc;
+  P.tpc = (P.ntaps + P.ngroups - 1) / P.ngroups;
+  P.ngroups = (P.ntaps + P.tpc - 1) / P.tpc;
+  int cols = P.tpc * P.n_mma;
+  P.tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512;
+  const int out_tiles = P.ngroups * P.cp_tiles * P.cq_tiles;
   int splits = (2 * dn_num_sms() + out_tiles - 1) / out_tiles;
   if (splits > P.num_ptiles) splits = P.num_ptiles;
   if (splits < 1) splits = 1;
   P.ptiles_per_split = (P.num_ptiles + splits - 1) / splits;
   P.splits = (P.num_ptiles + P.ptiles_per_split - 1) / P.ptiles_per_split;
-  const uint32_t stage_bytes = 2 * KPX * 128 + (BNQ / 64) * KPX * 128;
+  const uint32_t stage_bytes = a_bytes + (uint32_t)P.tpc * b_bytes;
   P.stages = (int)((200 * 1024) / stage_bytes);
   if (P.stages > 8) P.stages = 8;
-  P.idesc = make_idesc(P0.dtype, p->q.dtype, 1, 1, 128, BNQ);
+  P.idesc = make_idesc(P0.dtype, p->q.dtype, 1, 1, 128, P.n_mma);
   P.dw = p->dw;
   P.cp = P0.C; P.cq = p->q.C; P.cp_pad = p->cp_pad; P.cq_pad = p->cq_pad;
   P.scale = p->scale;

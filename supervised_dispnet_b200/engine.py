@@ -226,8 +226,11 @@ class ConvOp(Op):
     """nn.Conv2d (any k / stride / pad) or nn.ConvTranspose2d (stride 2), with fused bias + activation."""
 
     def __init__(self, plan, name, x, out, k, stride=1, pad=None, transposed=False, bias=True, act=L.ACT_NONE,
-                 needs_dx=True):
+                 needs_dx=True, bn_follows=False):
         self.name, self.x, self.out = name, x, out
+        # a bias in front of BatchNorm has an analytically zero gradient (BN subtracts the batch mean); the reference
+        # computes rounding noise around 0 there.  We write exact zeros and skip the extra pass over dy.
+        self.bias_grad_zero = bn_follows
         self.k, self.stride, self.transposed, self.act = k, stride, transposed, act
         self.pad = (k - 1) // 2 if pad is None else pad
         self.needs_dx = needs_dx
@@ -284,7 +287,7 @@ class ConvOp(Op):
         b = plan.param(self.name + '.bias') if self.has_bias else None
         for p, be, fl in self._fwd_built:
             p.bias = b.data_ptr() if b is not None else None
-            L.call('dn_igemm_run', C.byref(p), be, plan.stream, tag=('fwd', be, fl))
+            L.call('dn_igemm_run', C.byref(p), be, plan.stream, tag=('fwd', be, fl, self.name))
 
     def plan_bwd(self, plan):
         g = plan.prec.grad
@@ -355,7 +358,7 @@ class ConvOp(Op):
         W = plan.param(self.name + '.weight')
         T = self.k * self.k
         inv = 1.0 / plan.prec.gscale
-        gb = plan.grad_of(self.name + '.bias') if self.has_bias else None
+        gb = plan.grad_of(self.name + '.bias') if (self.has_bias and not self.bias_grad_zero) else None
         if self.act != L.ACT_NONE or gb is not None:
             L.call('dn_act_bwd', self.gout.ref(), self.out.ref(), self.act, L.ptr(gb), inv, L.ptr(plan.reduce_ws(self.Cout)),
                    plan.stream)
@@ -363,7 +366,7 @@ class ConvOp(Op):
         if self.xq is not None:
             L.call('dn_copy_view', self.x.ref(), self.xq.ref(), 0, plan.stream)
         for p, be, fl in self.wg:
-            L.call('dn_wgrad_run', C.byref(p), be, plan.stream, tag=('wgrad', be, fl))
+            L.call('dn_wgrad_run', C.byref(p), be, plan.stream, tag=('wgrad', be, fl, self.name))
         gw = plan.grad_of(self.name + '.weight')
         L.call('dn_unpack_wgrad', L.ptr(self.dwp), L.ptr(gw), T, self.Cout, self.Cin, self.cout_pad, self.cin_pad, self.kh,
                self.kw, self.s_co, self.s_ci, self.k, 1, inv, plan.stream)
@@ -374,7 +377,7 @@ class ConvOp(Op):
             L.call('dn_pack_weight', L.ptr(W), L.ptr(self.wpT), _DT[plan.prec.grad], T, self.Cin, self.Cout, self.cinT_pad,
                    self.coutT_pad, self.kh, self.kw, self.s_ci, self.s_co, self.k, 1, plan.stream)
             for p, be, fl in self.dg:
-                L.call('dn_igemm_run', C.byref(p), be, plan.stream, tag=('dgrad', be, fl))
+                L.call('dn_igemm_run', C.byref(p), be, plan.stream, tag=('dgrad', be, fl, self.name))
 
 
 class BNOp(Op):

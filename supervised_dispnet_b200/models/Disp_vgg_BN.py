@@ -99,7 +99,7 @@ class Disp_vgg_BN(E.PlannedModule):
             for j in range(nconv):
                 ci = conv_idx[k]
                 y = nb(N, h, w, planes[b]).view()
-                plan.add(E.ConvOp(plan, 'features.features.%d' % ci, x, y, 3, needs_dx=(k > 0)))
+                plan.add(E.ConvOp(plan, 'features.features.%d' % ci, x, y, 3, needs_dx=(k > 0), bn_follows=True))
                 last = j == nconv - 1
                 if last:
                     h, w = h // 2, w // 2

@@ -1,0 +1,34 @@
+"""Runs a few full-size single-layer cases (forward + backward) for ncu captures / event timing.
+    python tools/prof_conv.py [case ...]"""
+import os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
+import torch
+import _harness as Hn
+CASES = {
+    'iconv0': (dict(cin=17, cout=16, k=3, act=2), (32, 17, 128, 416)),
+    'feat3': (dict(cin=64, cout=64, k=3), (32, 64, 128, 416)),
+    'feat0': (dict(cin=3, cout=64, k=3), (32, 3, 128, 416)),
+    'feat10': (dict(cin=128, cout=128, k=3), (32, 128, 64, 208)),
+    'feat17': (dict(cin=256, cout=256, k=3), (32, 256, 32, 104)),
+    'feat27': (dict(cin=512, cout=512, k=3), (32, 512, 16, 52)),
+    'upconv0': (dict(cin=32, cout=16, k=4, stride=2, pad=1, transposed=True, act=2), (32, 32, 64, 208)),
+}
+names = sys.argv[1:] or list(CASES)
+prec = os.environ.get('DISPNET_B200_PRECISION', 'mixed')
+for n in names:
+    cfg, shape = CASES[n]
+    torch.manual_seed(0)
+    m = Hn.OneConv(precision=prec, **cfg).cuda().train()
+    x = torch.randn(shape, device='cuda')
+    for it in range(3):
+        out = m(x)
+        out.sum().backward()
+    torch.cuda.synchronize()
+    from supervised_dispnet_b200 import _lib as L
+    L.PROFILE = []
+    out = m(x); out.sum().backward(); torch.cuda.synchronize()
+    for name, tag, a, b in L.PROFILE:
+        if tag:
+            print('%-8s %-6s %s %8.3f ms %8.1f TFLOP/s' % (n, tag[0], 'tc' if tag[1] else 'cc', a.elapsed_time(b), tag[2] / a.elapsed_time(b) / 1e9))
+    L.PROFILE = None
