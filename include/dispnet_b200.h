@@ -102,6 +102,8 @@ int dn_version(void);
 const char* dn_error_string(int code);
 /* 1 when the running device is sm_100 and the tcgen05 path can be used. */
 int dn_tc_available(void);
+/* Profiling aid: 8 x uint64 device counters that igemm launches add per-role cycle counts to (NULL switches it off). */
+int dn_tc_set_debug(void* device_counters);
 
 /* ---- layout / packing (replaces ATen copies: torch.cat, .contiguous(), weight re-layout) ---- */
 /* NCHW fp32 [N,C,H,W] -> channels [c0, c0+C) of NHWC view `dst` (channels >= c0+C left untouched). */

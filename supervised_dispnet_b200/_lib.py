@@ -47,6 +47,7 @@ _IP = C.POINTER(C.c_int32)
 _SIGS = {
     'dn_version': ([], _I),
     'dn_tc_available': ([], _I),
+    'dn_tc_set_debug': ([_P], _I),
     'dn_pack_input': ([_P, _I, _I, _I, _I, _V, _I, _P], _I),
     'dn_pack_weight': ([_P, _P, _I, _I, _I, _I, _I, _I, _IP, _IP, _I64, _I64, _I64, _I64, _P], _I),
     'dn_unpack_wgrad': ([_P, _P, _I, _I, _I, _I, _I, _IP, _IP, _I64, _I64, _I64, _I64, _F, _P], _I),

@@ -419,14 +419,25 @@ __device__ __forceinline__ void cg_block_reduce(float* vals, int CGb) {
 
 // second stage of the per-channel reductions: out[j] = scale * sum_blk ws[blk][j]  (double accumulation)
 constexpr int kMaxReduceBlocks = 2048;
+// 256 threads = 32 columns x 8 row groups; each group strides over the partial rows, then a shared-memory combine
 template <typename TO>
-__global__ void reduce_partials_kernel(const float* __restrict__ ws, int nblk, int n, TO* __restrict__ out, double scale) {
-  int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n) return;
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ ws, int nblk, int n, TO* __restrict__ out, double scale) {
+  __shared__ double part[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + tx;
   double s = 0.0;
-  for (int b = 0; b < nblk; ++b) s += (double)ws[(long long)b * n + j];
-  out[j] = (TO)(s * scale);
+  if (j < n)
+    for (int b = ty; b < nblk; b += 8) s += (double)ws[(long long)b * n + j];
+  part[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && j < n) {
+    double t = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += part[k][tx];
+    out[j] = (TO)(t * scale);
+  }
 }
+static inline int reduce_blocks(int n) { return (n + 31) / 32; }
 DN_EXPORT int64_t dn_reduce_ws_floats(int C) { return (int64_t)kMaxReduceBlocks * 2 * (C + 8); }
 
 // ---- BN statistics --------------------------------------------------------------------------------
@@ -486,7 +497,7 @@ DN_EXPORT int dn_bn_stats(const dn_view* y, double* sums, float* ws, void* strea
     bn_stats_kernel<1><<<g.grid, 256, 0, dn_stream(stream)>>>(*y, ws, g.CGb);
   }
   DN_CHECK_LAUNCH();
-  reduce_partials_kernel<double><<<(2 * y->C + 127) / 128, 128, 0, dn_stream(stream)>>>(ws, g.grid.x, 2 * y->C, sums, 1.0);
+  reduce_partials_kernel<double><<<reduce_blocks(2 * y->C), 256, 0, dn_stream(stream)>>>(ws, g.grid.x, 2 * y->C, sums, 1.0);
   DN_CHECK_LAUNCH();
   return 0;
 }
@@ -721,12 +732,21 @@ DN_EXPORT int dn_bn_bwd_reduce(const dn_view* dout, const dn_view* y, const dn_v
   CgGeom g = cg_geom(dout->C, ch, npix);
   const int hr = residual != nullptr;
   const size_t sm = sizeof(float) * 4 * (dout->C + ch);
+  if (sm > 200 * 1024) return DN_E_UNSUPPORTED;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(bn_bwd_reduce_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(bn_bwd_reduce_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(bn_bwd_reduce_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(bn_bwd_reduce_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr_done = true;
+  }
   if (vec && pool) bn_bwd_reduce_kernel<8, true><<<g.grid, 256, sm, st>>>(*dout, *y, r, hr, mean_invstd, gamma, beta, act, ws, g.CGb);
   else if (vec) bn_bwd_reduce_kernel<8, false><<<g.grid, 256, sm, st>>>(*dout, *y, r, hr, mean_invstd, gamma, beta, act, ws, g.CGb);
   else if (pool) bn_bwd_reduce_kernel<1, true><<<g.grid, 256, sm, st>>>(*dout, *y, r, hr, mean_invstd, gamma, beta, act, ws, g.CGb);
   else bn_bwd_reduce_kernel<1, false><<<g.grid, 256, sm, st>>>(*dout, *y, r, hr, mean_invstd, gamma, beta, act, ws, g.CGb);
   DN_CHECK_LAUNCH();
-  reduce_partials_kernel<double><<<(2 * dout->C + 127) / 128, 128, 0, st>>>(ws, g.grid.x, 2 * dout->C, red, 1.0);
+  reduce_partials_kernel<double><<<reduce_blocks(2 * dout->C), 256, 0, st>>>(ws, g.grid.x, 2 * dout->C, red, 1.0);
   DN_CHECK_LAUNCH();
   return 0;
 }
@@ -806,6 +826,15 @@ DN_EXPORT int dn_bn_bwd_apply(const dn_view* dout, const dn_view* y, const dn_vi
   CgGeom g = cg_geom(dout->C, ch, npix);
   const int hr = residual != nullptr, hd = dres != nullptr;
   const size_t sm = sizeof(float) * 6 * (dout->C + ch);
+  if (sm > 200 * 1024) return DN_E_UNSUPPORTED;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(bn_bwd_apply_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(bn_bwd_apply_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(bn_bwd_apply_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(bn_bwd_apply_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr_done = true;
+  }
 #define BN_BWD_APPLY(CHV, PV)                                                                                               \
   bn_bwd_apply_kernel<CHV, PV><<<g.grid, 256, sm, st>>>(*dout, *y, r, hr, mean_invstd, gamma, beta, act, red, count, gscale, \
                                                         dgamma, dbeta, *dy, dr, hd, dres_accumulate, g.CGb)
@@ -871,7 +900,7 @@ DN_EXPORT int dn_act_bwd(const dn_view* dout, const dn_view* out, int act, float
   }
   DN_CHECK_LAUNCH();
   if (dbias) {
-    reduce_partials_kernel<float><<<(dout->C + 127) / 128, 128, 0, dn_stream(stream)>>>(ws, g.grid.x, dout->C, dbias, (double)gscale);
+    reduce_partials_kernel<float><<<reduce_blocks(dout->C), 256, 0, dn_stream(stream)>>>(ws, g.grid.x, dout->C, dbias, (double)gscale);
     DN_CHECK_LAUNCH();
   }
   return 0;

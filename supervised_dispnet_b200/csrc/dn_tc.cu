@@ -46,6 +46,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
+// one lane of a fully converged warp; keeps the surrounding control flow warp-uniform so that descriptors and barrier
+// addresses stay in uniform registers (issuing tcgen05 / TMA from inside `if (lane == 0)` makes the compiler wrap every
+// instruction in an elect/broadcast loop)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n"
+      ".reg .b32 %%rx;\n"
+      ".reg .pred %%px;\n"
+      "elect.sync %%rx|%%px, %1;\n"
+      "@%%px mov.s32 %0, 1;\n"
+      "}\n"
+      : "+r"(pred)
+      : "r"(0xffffffffu));
+  return pred != 0;
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -152,6 +168,7 @@ struct IgemmTcParams {
   const float* bias;
   int act, accumulate;
   float out_scale;
+  unsigned long long* dbg;   // optional per-role cycle counters (dn_tc_set_debug)
 };
 
 template <int BN>
@@ -194,56 +211,83 @@ __global__ void __launch_bounds__(192, 1) igemm_tc_kernel(const __grid_constant_
   const int k_iters = p.ntaps * p.kchunks;
 
   if (warp == 0) {
-    // ================= TMA producer =================
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const int nt = tile % p.ntile_n;
-        int m = tile / p.ntile_n;
-        const int tw = m % p.tilesW; m /= p.tilesW;
-        const int th = m % p.tilesH;
-        const int tn = m / p.tilesH;
-        const int w0 = tw * p.wb, h0 = th * p.hb, n0 = tn * p.nb;
-        for (int t = 0; t < p.ntaps; ++t) {
-          const TcTap tap = p.taps[t];
-          for (int kc = 0; kc < p.kchunks; ++kc) {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
+    // ================= TMA producer (whole warp runs the loop, one elected lane issues) =================
+    int stage = 0; uint32_t phase = 0;
+    long long dbg_acc0 = 0;
+    const long long tstart = p.dbg ? clock64() : 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int nt = tile % p.ntile_n;
+      int m = tile / p.ntile_n;
+      const int tw = m % p.tilesW; m /= p.tilesW;
+      const int th = m % p.tilesH;
+      const int tn = m / p.tilesH;
+      const int w0 = tw * p.wb, h0 = th * p.hb, n0 = tn * p.nb;
+      for (int t = 0; t < p.ntaps; ++t) {
+        const TcTap tap = p.taps[t];
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          const long long t0 = p.dbg ? clock64() : 0;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (p.dbg) dbg_acc0 += clock64() - t0;
+          if (elect_one()) {
             uint8_t* sa = smem + (size_t)stage * STAGE_BYTES;
             uint8_t* sb = sa + A_BYTES;
             mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
             tma_load_4d(sa, &p.tmA[tap.src], &full_bar[stage], kc * kChunk, w0 + tap.dw, h0 + tap.dh, n0);
             tma_load_3d(sb, &p.tmB, &full_bar[stage], kc * kChunk, nt * BN, tap.wt);
-            if (++stage == stages) { stage = 0; phase ^= 1; }
           }
+          __syncwarp();
+          if (++stage == stages) { stage = 0; phase ^= 1; }
         }
       }
     }
+    if (p.dbg && lane == 0) {
+      atomicAdd(p.dbg + 0, (unsigned long long)dbg_acc0);
+      atomicAdd(p.dbg + 1, (unsigned long long)(clock64() - tstart));
+    }
   } else if (warp == 1) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      int acc = 0; uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-        for (int it = 0; it < k_iters; ++it) {
+    // ================= MMA issuer (whole warp waits on the barriers, one elected lane issues) =================
+    int stage = 0; uint32_t phase = 0;
+    int acc = 0; uint32_t acc_phase = 0;
+    long long dbg_full = 0, dbg_te = 0;
+    const long long tstart = p.dbg ? clock64() : 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      long long t0 = p.dbg ? clock64() : 0;
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      if (p.dbg) dbg_te += clock64() - t0;
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+      uint32_t first = 1;
+      for (int t = 0; t < p.ntaps; ++t) {
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          t0 = p.dbg ? clock64() : 0;
           mbar_wait(&full_bar[stage], phase);
+          if (p.dbg) dbg_full += clock64() - t0;
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + (size_t)stage * STAGE_BYTES);
-          const uint32_t sb = sa + A_BYTES;
-          const int ks = ((it % p.kchunks) == p.kchunks - 1) ? p.last_ksteps : 4;
-          for (int k = 0; k < ks; ++k) {
-            const uint64_t ad = make_desc(sa + k * 32, 16, 1024);
-            const uint64_t bd = make_desc(sb + k * 32, 16, 1024);
-            umma_f16(d_tmem, ad, bd, p.idesc, (it > 0 || k > 0) ? 1u : 0u);
+          const uint64_t ad0 = make_desc(sa, 16, 1024);
+          const uint64_t bd0 = make_desc(sa + A_BYTES, 16, 1024);
+          const int ks = (kc == p.kchunks - 1) ? p.last_ksteps : 4;
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              if (k < ks) {
+                // advance 16 K-elements = 32 bytes inside the 128-byte swizzled row: +2 in the (addr >> 4) field
+                umma_f16(d_tmem, ad0 + (uint64_t)(2 * k), bd0 + (uint64_t)(2 * k), p.idesc, (first && k == 0) ? 0u : 1u);
+              }
+            }
+            umma_commit(&empty_bar[stage]);
+            if (t == p.ntaps - 1 && kc == p.kchunks - 1) umma_commit(&tfull_bar[acc]);
           }
-          umma_commit(&empty_bar[stage]);
-          if (it == k_iters - 1) umma_commit(&tfull_bar[acc]);
+          __syncwarp();
+          first = 0;
           if (++stage == stages) { stage = 0; phase ^= 1; }
         }
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (p.dbg && lane == 0) {
+      atomicAdd(p.dbg + 2, (unsigned long long)dbg_full); atomicAdd(p.dbg + 3, (unsigned long long)dbg_te);
+      atomicAdd(p.dbg + 4, (unsigned long long)(clock64() - tstart));
     }
   } else {
     // ================= epilogue warps (2..5): TMEM -> registers -> bias/act -> HBM =================
@@ -267,7 +311,9 @@ __global__ void __launch_bounds__(192, 1) igemm_tc_kernel(const __grid_constant_
       float* bs = bias_s + acc * BN;
       for (int c = et; c < BN; c += 128) bs[c] = (p.bias && co0 + c < p.out.C) ? p.bias[co0 + c] : 0.f;
       asm volatile("bar.sync 1, 128;" ::: "memory");
+      const long long te0 = p.dbg ? clock64() : 0;
       mbar_wait(&tfull_bar[acc], acc_phase);
+      const long long te1 = p.dbg ? clock64() : 0;
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
       uint8_t* optr = (uint8_t*)p.out.ptr + (size_t)(dn_off(p.out, n, h, w) + co0) * esz;
@@ -318,6 +364,10 @@ __global__ void __launch_bounds__(192, 1) igemm_tc_kernel(const __grid_constant_
       }
       tc_fence_before();
       mbar_arrive(&tempty_bar[acc]);
+      if (p.dbg && et == 0) {
+        atomicAdd(p.dbg + 5, (unsigned long long)(te1 - te0));
+        atomicAdd(p.dbg + 6, (unsigned long long)(clock64() - te1));
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
@@ -407,15 +457,15 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
 
   if (n_iters > 0) {
     if (warp == 0) {
-      if (lane == 0) {
-        int stage = 0; uint32_t phase = 0;
-        for (int pt = pt_beg; pt < pt_end; ++pt) {
-          int m = pt;
-          const int tw = m % p.tilesW; m /= p.tilesW;
-          const int th = m % p.tilesH;
-          const int tn = m / p.tilesH;
-          const int w0 = tw * p.wb, h0 = th * p.hb, n0 = tn * p.nb;
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+      int stage = 0; uint32_t phase = 0;
+      for (int pt = pt_beg; pt < pt_end; ++pt) {
+        int m = pt;
+        const int tw = m % p.tilesW; m /= p.tilesW;
+        const int th = m % p.tilesH;
+        const int tn = m / p.tilesH;
+        const int w0 = tw * p.wb, h0 = th * p.hb, n0 = tn * p.nb;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (elect_one()) {
           uint8_t* sa = smem + (size_t)stage * STAGE_BYTES;
           mbar_expect_tx(&full_bar[stage], tx_bytes);
           for (int j = 0; j < p.cp_blocks; ++j)
@@ -427,30 +477,32 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
             for (int j = 0; j < BNQ / 64; ++j)
               tma_load_4d(sb + j * BLK_BYTES, &p.tmQ, &full_bar[stage], cqt * BNQ + j * 64, w0 + tap.dw, h0 + tap.dh, n0);
           }
-          if (++stage == stages) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == stages) { stage = 0; phase ^= 1; }
       }
     } else if (warp == 1) {
-      if (lane == 0) {
-        int stage = 0; uint32_t phase = 0;
-        for (int it = 0; it < n_iters; ++it) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + (size_t)stage * STAGE_BYTES);
+      int stage = 0; uint32_t phase = 0;
+      for (int it = 0; it < n_iters; ++it) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + (size_t)stage * STAGE_BYTES);
+        // MN-major, 128B swizzle: LBO = distance between 64-channel blocks, SBO = 8 pixel rows = 1024 B;
+        // 16 pixels (one UMMA_K step) further down = +2048 bytes = +128 in the (addr >> 4) field
+        const uint64_t ad0 = make_desc(sa, BLK_BYTES, 1024);
+        if (elect_one()) {
           for (int t = 0; t < nt; ++t) {
-            const uint32_t sb = sa + A_BYTES + (uint32_t)t * B_BYTES;
+            const uint64_t bd0 = make_desc(sa + A_BYTES + (uint32_t)t * B_BYTES, BLK_BYTES, 1024);
 #pragma unroll
-            for (int k = 0; k < KPX / 16; ++k) {
-              // MN-major, 128B swizzle: LBO = distance between 64-channel blocks, SBO = 8 pixel rows = 1024 B
-              const uint64_t ad = make_desc(sa + k * 2048, BLK_BYTES, 1024);
-              const uint64_t bd = make_desc(sb + k * 2048, BLK_BYTES, 1024);
-              umma_f16(tmem_base + (uint32_t)(t * p.n_mma), ad, bd, p.idesc, (it > 0 || k > 0) ? 1u : 0u);
-            }
+            for (int k = 0; k < KPX / 16; ++k)
+              umma_f16(tmem_base + (uint32_t)(t * p.n_mma), ad0 + (uint64_t)(128 * k), bd0 + (uint64_t)(128 * k), p.idesc,
+                       (it > 0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);
           if (it == n_iters - 1) umma_commit(done_bar);
-          if (++stage == stages) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == stages) { stage = 0; phase ^= 1; }
       }
     } else {
       const int q = warp & 3;
@@ -589,7 +641,16 @@ int launch_wgrad(const WgradTcParams& P, int items, cudaStream_t st) {
   return 0;
 }
 
+unsigned long long* g_tc_dbg = nullptr;
+
 }  // namespace
+
+// debug: device buffer of 8 counters (cycles summed over CTAs): [0] producer wait-empty, [1] producer total,
+// [2] MMA wait-full, [3] MMA wait-tmem-empty, [4] MMA total, [5] epilogue wait-tmem-full, [6] epilogue drain+store
+DN_EXPORT int dn_tc_set_debug(void* device_counters) {
+  g_tc_dbg = (unsigned long long*)device_counters;
+  return 0;
+}
 
 DN_EXPORT int dn_tc_available(void) {
   static int cached = -1;
@@ -666,6 +727,7 @@ int dn_igemm_tc(const dn_igemm* p, cudaStream_t st) {
   P.act = p->act;
   P.accumulate = p->accumulate;
   P.out_scale = p->out_scale;
+  P.dbg = g_tc_dbg;
   switch (BN) {
     case 256: return launch_igemm<256>(P, st);
     case 128: return launch_igemm<128>(P, st);

@@ -32,3 +32,24 @@ for n in names:
         if tag:
             print('%-8s %-6s %s %8.3f ms %8.1f TFLOP/s' % (n, tag[0], 'tc' if tag[1] else 'cc', a.elapsed_time(b), tag[2] / a.elapsed_time(b) / 1e9))
     L.PROFILE = None
+
+# optional per-role cycle counters of the tcgen05 forward kernel: DN_TC_DEBUG=1
+if os.environ.get('DN_TC_DEBUG'):
+    import ctypes
+    for n in names:
+        cfg, shape = CASES[n]
+        torch.manual_seed(0)
+        m = Hn.OneConv(precision=prec, **cfg).cuda().train()
+        x = torch.randn(shape, device='cuda')
+        with torch.no_grad():
+            m(x); m(x)
+        cnt = torch.zeros(8, dtype=torch.int64, device='cuda')
+        L.lib().dn_tc_set_debug(ctypes.c_void_p(cnt.data_ptr()))
+        with torch.no_grad():
+            m(x)
+        torch.cuda.synchronize()
+        L.lib().dn_tc_set_debug(None)
+        c = cnt.cpu().tolist()
+        nct = 148.0
+        print('%-8s fwd cycles/CTA: producer wait_empty %.0f of %.0f | mma wait_full %.0f wait_tmem_empty %.0f of %.0f | epi wait_full %.0f work %.0f'
+              % (n, c[0] / nct, c[1] / nct, c[2] / nct, c[3] / nct, c[4] / nct, c[5] / nct, c[6] / nct))
