@@ -104,6 +104,8 @@ const char* dn_error_string(int code);
 int dn_tc_available(void);
 /* Profiling aid: 8 x uint64 device counters that igemm launches add per-role cycle counts to (NULL switches it off). */
 int dn_tc_set_debug(void* device_counters);
+/* 1 (default): 3x3 stride-1 problems with many pixels use the shared-memory halo variant of the tcgen05 kernel. */
+int dn_tc_set_halo(int enabled);
 
 /* ---- layout / packing (replaces ATen copies: torch.cat, .contiguous(), weight re-layout) ---- */
 /* NCHW fp32 [N,C,H,W] -> channels [c0, c0+C) of NHWC view `dst` (channels >= c0+C left untouched). */
@@ -137,9 +139,11 @@ int dn_bn_stats(const dn_view* y, double* sums, float* ws, void* stream);
 int dn_bn_finalize(const double* sums, double count, const float* gamma, const float* beta, float* running_mean,
                    float* running_var, float momentum, float eps, int training, int update_running,
                    float* mean_invstd, float* scale_shift, int C, void* stream);
-/* out = pool?( act( y*scale+shift (+ residual) ) );  pool in {0,1}: 1 = 2x2/2 max pool (out is H/2 x W/2). */
+/* out = pool?( act( y*scale+shift (+ residual) ) );  pool in {0,1}: 1 = 2x2/2 max pool (out is H/2 x W/2).
+ * out2 (optional, same shape, may have another 16-bit dtype) receives a second copy of the result: the bf16 image of the
+ * activation that the weight-gradient GEMM consumes (tcgen05 kind::f16 cannot mix fp16 and bf16 operands). */
 int dn_bn_apply(const dn_view* y, const float* scale_shift, const dn_view* residual, int act, int pool,
-                const dn_view* out, void* stream);
+                const dn_view* out, const dn_view* out2, void* stream);
 /* backward: pass 1 accumulates red[2C] (double): sum(dyhat), sum(dyhat*xhat), where dyhat is the gradient
  * routed back through pool/act; pass 2 writes dy (and dres if residual). */
 int dn_bn_bwd_reduce(const dn_view* dout, const dn_view* y, const dn_view* residual, const float* mean_invstd,

@@ -48,6 +48,7 @@ _SIGS = {
     'dn_version': ([], _I),
     'dn_tc_available': ([], _I),
     'dn_tc_set_debug': ([_P], _I),
+    'dn_tc_set_halo': ([_I], _I),
     'dn_pack_input': ([_P, _I, _I, _I, _I, _V, _I, _P], _I),
     'dn_pack_weight': ([_P, _P, _I, _I, _I, _I, _I, _I, _IP, _IP, _I64, _I64, _I64, _I64, _P], _I),
     'dn_unpack_wgrad': ([_P, _P, _I, _I, _I, _I, _I, _IP, _IP, _I64, _I64, _I64, _I64, _F, _P], _I),
@@ -58,7 +59,7 @@ _SIGS = {
     'dn_reduce_ws_floats': ([_I], _I64),
     'dn_bn_stats': ([_V, _P, _P, _P], _I),
     'dn_bn_finalize': ([_P, _D, _P, _P, _P, _P, _F, _F, _I, _I, _P, _P, _I, _P], _I),
-    'dn_bn_apply': ([_V, _P, _V, _I, _I, _V, _P], _I),
+    'dn_bn_apply': ([_V, _P, _V, _I, _I, _V, _V, _P], _I),
     'dn_bn_bwd_reduce': ([_V, _V, _V, _P, _P, _P, _I, _I, _P, _P, _P], _I),
     'dn_bn_bwd_apply': ([_V, _V, _V, _P, _P, _P, _I, _I, _P, _D, _F, _P, _P, _V, _V, _I, _P], _I),
     'dn_act_bwd': ([_V, _V, _I, _P, _F, _P, _P], _I),

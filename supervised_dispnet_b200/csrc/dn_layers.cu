@@ -550,7 +550,7 @@ DN_EXPORT int dn_bn_finalize(const double* sums, double count, const float* gamm
 // ---- BN apply (+residual) + act (+2x2 max pool) ------------------------------------------------------
 template <int CH>
 __global__ void __launch_bounds__(256) bn_apply_kernel(dn_view y, const float* __restrict__ scale_shift, dn_view res, int has_res,
-                                                       int act, int pool, dn_view out, int CGb) {
+                                                       int act, int pool, dn_view out, dn_view out2, int has_out2, int CGb) {
   CG_PROLOGUE(out)
   if (!cvalid) return;
   float sc[CH], sh[CH];
@@ -593,24 +593,27 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(dn_view y, const float* _
       }
     }
     stc<CH>(out, dn_off(out, n, h, w) + c0, o);
+    if (has_out2) stc<CH>(out2, dn_off(out2, n, h, w) + c0, o);
   }
 }
 
 DN_EXPORT int dn_bn_apply(const dn_view* y, const float* scale_shift, const dn_view* residual, int act, int pool,
-                          const dn_view* out, void* stream) {
+                          const dn_view* out, const dn_view* out2, void* stream) {
   if (!y || !out || !scale_shift) return DN_E_ARG;
   if (pool && (residual || out->H * 2 > y->H || out->W * 2 > y->W)) return DN_E_ARG;
   if (!pool && (out->H != y->H || out->W != y->W)) return DN_E_ARG;
   if (out->C != y->C || out->N != y->N) return DN_E_ARG;
   long long npix = (long long)out->N * out->H * out->W;
   dn_view r = residual ? *residual : *y;
-  bool vec = dn_vec8_ok(y) && dn_vec8_ok(out) && (!residual || dn_vec8_ok(residual));
+  dn_view o2 = out2 ? *out2 : *out;
+  if (out2 && (out2->C != out->C || out2->H != out->H || out2->W != out->W || out2->N != out->N)) return DN_E_ARG;
+  bool vec = dn_vec8_ok(y) && dn_vec8_ok(out) && (!residual || dn_vec8_ok(residual)) && (!out2 || dn_vec8_ok(out2));
   if (vec) {
     CgGeom g = cg_geom(out->C, 8, npix);
-    bn_apply_kernel<8><<<g.grid, 256, 0, dn_stream(stream)>>>(*y, scale_shift, r, residual != nullptr, act, pool, *out, g.CGb);
+    bn_apply_kernel<8><<<g.grid, 256, 0, dn_stream(stream)>>>(*y, scale_shift, r, residual != nullptr, act, pool, *out, o2, out2 != nullptr, g.CGb);
   } else {
     CgGeom g = cg_geom(out->C, 1, npix);
-    bn_apply_kernel<1><<<g.grid, 256, 0, dn_stream(stream)>>>(*y, scale_shift, r, residual != nullptr, act, pool, *out, g.CGb);
+    bn_apply_kernel<1><<<g.grid, 256, 0, dn_stream(stream)>>>(*y, scale_shift, r, residual != nullptr, act, pool, *out, o2, out2 != nullptr, g.CGb);
   }
   DN_CHECK_LAUNCH();
   return 0;

@@ -379,6 +379,216 @@ __global__ void __launch_bounds__(192, 1) igemm_tc_kernel(const __grid_constant_
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// 3x3 stride-1 gather-convolution with shared-memory halo reuse ("halo" variant of igemm_tc_kernel)
+//
+// For layers with many pixels and few channels the plain kernel is bound by the TMA row rate / L2 bandwidth: every output
+// tile fetches its 128x64 activation box nine times (once per tap).  Here one (16+2) x 16-pixel halo box is fetched per
+// 64-channel chunk (the tile is 16 rows x 8 columns of pixels, the box is padded to 16 columns so that an image row is
+// 2048 bytes = two swizzle atoms) and the nine taps are nine *views* of it: the A descriptor starts (kh*16 + kw) pixels
+// further, keeps SBO = 2048 B between the 8-pixel row groups and carries base_offset = kw so that the 128-byte swizzle
+// phase of the shifted start is honoured.  The packed weights of all taps stay resident in shared memory for the
+// lifetime of the persistent CTA.
+// ------------------------------------------------------------------------------------------------
+constexpr int kHaloW = 16, kHaloH = 18;
+constexpr uint32_t kHaloBytes = kHaloW * kHaloH * 128;     // 36864
+
+__device__ __forceinline__ uint64_t make_desc_bo(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t base_offset) {
+  return make_desc(smem_addr, lbo_bytes, sbo_bytes) | ((uint64_t)(base_offset & 7u) << 49);
+}
+
+struct HaloParams {
+  CUtensorMap tmA;
+  CUtensorMap tmB;
+  int kchunks, last_ksteps;
+  int wt[9];            // packed-weight matrix index of tap (kh, kw), kh = dh + 1, kw = dw + 1
+  int tilesW, tilesH, num_tiles;
+  int stages;
+  int n_mma, c_eff;
+  uint32_t idesc;
+  dn_view out;
+  const float* bias;
+  int act, accumulate;
+  float out_scale;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(192, 1) igemm_halo_kernel(const __grid_constant__ HaloParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  constexpr uint32_t B_BYTES = BN * 128;
+  constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int stages = p.stages;
+  const int nb_tiles = 9 * p.kchunks;                       // resident weight tiles
+  uint8_t* smem_b = smem;
+  uint8_t* smem_a = smem + (size_t)nb_tiles * B_BYTES;
+  uint64_t* full_bar = (uint64_t*)(smem_a + (size_t)stages * kHaloBytes);
+  uint64_t* empty_bar = full_bar + stages;
+  uint64_t* tfull_bar = empty_bar + stages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint64_t* bfull_bar = tempty_bar + 2;
+  uint32_t* tmem_ptr = (uint32_t*)(bfull_bar + 1);
+  float* bias_s = (float*)(tmem_ptr + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmA);
+    tma_prefetch_desc(&p.tmB);
+    for (int s = 0; s < stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 128); }
+    mbar_init(bfull_bar, 1);
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ---- producer: weights once, then one halo box per (tile, chunk)
+    if (elect_one()) {
+      mbar_expect_tx(bfull_bar, (uint32_t)nb_tiles * B_BYTES);
+      for (int t = 0; t < 9; ++t)
+        for (int kc = 0; kc < p.kchunks; ++kc)
+          tma_load_3d(smem_b + (size_t)(t * p.kchunks + kc) * B_BYTES, &p.tmB, bfull_bar, kc * kChunk, 0, p.wt[t]);
+    }
+    __syncwarp();
+    int stage = 0; uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      int m = tile;
+      const int tw = m % p.tilesW; m /= p.tilesW;
+      const int th = m % p.tilesH;
+      const int n0 = m / p.tilesH;
+      for (int kc = 0; kc < p.kchunks; ++kc) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (elect_one()) {
+          mbar_expect_tx(&full_bar[stage], kHaloBytes);
+          tma_load_4d(smem_a + (size_t)stage * kHaloBytes, &p.tmA, &full_bar[stage], kc * kChunk, tw * 8 - 1, th * 16 - 1, n0);
+        }
+        __syncwarp();
+        if (++stage == stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ---- MMA issuer
+    mbar_wait(bfull_bar, 0);
+    tc_fence_after();
+    int stage = 0; uint32_t phase = 0;
+    int acc = 0; uint32_t acc_phase = 0;
+    const uint32_t sb0 = smem_u32(smem_b);
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+      for (int kc = 0; kc < p.kchunks; ++kc) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem_a + (size_t)stage * kHaloBytes);
+        const int ks = (kc == p.kchunks - 1) ? p.last_ksteps : 4;
+        if (elect_one()) {
+#pragma unroll
+          for (int t = 0; t < 9; ++t) {
+            const int kh = t / 3, kw = t % 3;
+            const uint64_t ad0 = make_desc_bo(sa + (uint32_t)(kh * kHaloW + kw) * 128, 16, 2048, (uint32_t)kw);
+            const uint64_t bd0 = make_desc(sb0 + (uint32_t)(t * p.kchunks + kc) * B_BYTES, 16, 1024);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if (k < ks) umma_f16(d_tmem, ad0 + (uint64_t)(2 * k), bd0 + (uint64_t)(2 * k), p.idesc, (kc == 0 && t == 0 && k == 0) ? 0u : 1u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (kc == p.kchunks - 1) umma_commit(&tfull_bar[acc]);
+        }
+        __syncwarp();
+        if (++stage == stages) { stage = 0; phase ^= 1; }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else {
+    // ---- epilogue: tile row r = 8 * h_local + w_local
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int et = threadIdx.x - 64;
+    int acc = 0; uint32_t acc_phase = 0;
+    const int wi = row & 7, hi = row >> 3;
+    const int esz = p.out.dtype == DN_F32 ? 4 : 2;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      int m = tile;
+      const int tw = m % p.tilesW; m /= p.tilesW;
+      const int th = m % p.tilesH;
+      const int n = m / p.tilesH;
+      const int w = tw * 8 + wi, h = th * 16 + hi;
+      const bool valid = (w < p.out.W) && (h < p.out.H);
+      float* bs = bias_s + acc * BN;
+      for (int c = et; c < BN; c += 128) bs[c] = (p.bias && c < p.out.C) ? p.bias[c] : 0.f;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+      uint8_t* optr = (uint8_t*)p.out.ptr + (size_t)dn_off(p.out, n, h, w) * esz;
+#pragma unroll 1
+      for (int c0 = 0; c0 < p.n_mma; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld16(taddr + c0, r);
+        tmem_ld_wait();
+        if (valid && c0 < p.c_eff) {
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = dn_act(__uint_as_float(r[j]) * p.out_scale + bs[c0 + j], p.act);
+          if (p.out.dtype == DN_F32) {
+            float* o = (float*)optr + c0;
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (c0 + j < p.out.C) o[j] = p.accumulate ? o[j] + v[j] : v[j];
+          } else if (p.out.dtype == DN_F16) {
+            __half* o = (__half*)optr + c0;
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh)
+              if (c0 + 8 * hh < p.c_eff) {
+                if (p.accumulate) {
+                  float a[8];
+                  Vec8<__half>::load(o + 8 * hh, a);
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) v[8 * hh + j] += a[j];
+                }
+                Vec8<__half>::store(o + 8 * hh, v + 8 * hh);
+              }
+          } else {
+            __nv_bfloat16* o = (__nv_bfloat16*)optr + c0;
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh)
+              if (c0 + 8 * hh < p.c_eff) {
+                if (p.accumulate) {
+                  float a[8];
+                  Vec8<__nv_bfloat16>::load(o + 8 * hh, a);
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) v[8 * hh + j] += a[j];
+                }
+                Vec8<__nv_bfloat16>::store(o + 8 * hh, v + 8 * hh);
+              }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // weight gradient
 // ------------------------------------------------------------------------------------------------
@@ -641,6 +851,111 @@ int launch_wgrad(const WgradTcParams& P, int items, cudaStream_t st) {
   return 0;
 }
 
+
+// ---- halo variant: eligibility + launch -------------------------------------------------------------------------
+bool g_halo_enabled = true;
+
+// fills wt[kh*3+kw]; true when the taps are exactly the 3x3 neighbourhood of one source
+bool halo_taps(const dn_igemm* p, int* wt) {
+  if (p->ntaps != 9 || p->nsrc != 1 || p->stride != 1) return false;
+  bool seen[9] = {false};
+  for (int t = 0; t < 9; ++t) {
+    int dh = p->taps[t].dh, dw = p->taps[t].dw;
+    if (dh < -1 || dh > 1 || dw < -1 || dw > 1 || p->taps[t].src != 0) return false;
+    int i = (dh + 1) * 3 + (dw + 1);
+    if (seen[i]) return false;
+    seen[i] = true;
+    wt[i] = p->taps[t].wt;
+  }
+  return true;
+}
+
+bool halo_eligible(const dn_igemm* p, int* wt) {
+  if (!g_halo_enabled || !halo_taps(p, wt)) return false;
+  if (p->cout_pad > 256) return false;
+  const int BN = pick_bn(p->cout_pad);
+  const int kchunks = (p->in[0].C + kChunk - 1) / kChunk;
+  const size_t b_bytes = (size_t)9 * kchunks * BN * 128;
+  if (b_bytes + 2 * kHaloBytes > 200 * 1024) return false;          // weights must stay resident next to >= 2 halo stages
+  const int H = p->out.H, W = p->out.W;
+  if (H != p->in[0].H || W != p->in[0].W) return false;
+  // tile = 16 rows x 8 columns: only worth it when little of the tile grid is padding
+  const double eff = (double)H * W / ((double)((H + 15) / 16 * 16) * ((W + 7) / 8 * 8));
+  return eff >= 0.85;
+}
+
+template <int BN>
+int launch_halo(const HaloParams& P, cudaStream_t st) {
+  const size_t b_bytes = (size_t)9 * P.kchunks * BN * 128;
+  size_t smem = b_bytes + (size_t)P.stages * kHaloBytes + 1024 + (2 * P.stages + 5) * 8 + 16 + 2 * BN * 4;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(igemm_halo_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  int grid = P.num_tiles < dn_num_sms() ? P.num_tiles : dn_num_sms();
+  igemm_halo_kernel<BN><<<grid, 192, smem, st>>>(P);
+  DN_CHECK_LAUNCH();
+  return 0;
+}
+
+int dn_igemm_halo(const dn_igemm* p, const int* wt, cudaStream_t st) {
+  HaloParams P;
+  memset(&P, 0, sizeof(P));
+  const int BN = pick_bn(p->cout_pad);
+  auto enc = get_encode();
+  if (!enc) return DN_E_UNSUPPORTED;
+  {
+    const dn_view& v = p->in[0];
+    cuuint64_t dims[4] = {(cuuint64_t)v.C, (cuuint64_t)v.W, (cuuint64_t)v.H, (cuuint64_t)v.N};
+    cuuint64_t strides[3] = {(cuuint64_t)v.sW * 2, (cuuint64_t)v.sH * 2, (cuuint64_t)v.sN * 2};
+    cuuint32_t box[4] = {(cuuint32_t)kChunk, (cuuint32_t)kHaloW, (cuuint32_t)kHaloH, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUtensorMapDataType dt = v.dtype == DN_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    if (enc(&P.tmA, dt, 4, v.ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return DN_E_ARG;
+  }
+  {
+    int nw = 0;
+    for (int t = 0; t < 9; ++t) nw = wt[t] + 1 > nw ? wt[t] + 1 : nw;
+    cuuint64_t dims[3] = {(cuuint64_t)p->cin_pad, (cuuint64_t)p->cout_pad, (cuuint64_t)nw};
+    cuuint64_t strides[2] = {(cuuint64_t)p->cin_pad * 2, (cuuint64_t)p->cin_pad * p->cout_pad * 2};
+    cuuint32_t box[3] = {(cuuint32_t)kChunk, (cuuint32_t)BN, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUtensorMapDataType dt = p->w_dtype == DN_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    if (enc(&P.tmB, dt, 3, (void*)p->w, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return DN_E_ARG;
+  }
+  for (int t = 0; t < 9; ++t) P.wt[t] = wt[t];
+  const int Cin = p->in[0].C;
+  P.kchunks = (Cin + kChunk - 1) / kChunk;
+  P.last_ksteps = (Cin - (P.kchunks - 1) * kChunk + 15) / 16;
+  P.tilesW = (p->out.W + 7) / 8;
+  P.tilesH = (p->out.H + 15) / 16;
+  P.num_tiles = P.tilesW * P.tilesH * p->out.N;
+  const size_t b_bytes = (size_t)9 * P.kchunks * BN * 128;
+  P.stages = (int)((200 * 1024 - b_bytes) / kHaloBytes);
+  if (P.stages > 4) P.stages = 4;
+  P.n_mma = p->cout_pad < BN ? p->cout_pad : BN;
+  P.c_eff = (p->out.dtype != DN_F32 && p->out_pad_ok) ? (p->out.C + 7) / 8 * 8 : p->out.C;
+  P.idesc = make_idesc(p->in[0].dtype, p->w_dtype, 0, 0, 128, P.n_mma);
+  P.out = p->out;
+  P.bias = p->bias;
+  P.act = p->act;
+  P.accumulate = p->accumulate;
+  P.out_scale = p->out_scale;
+  switch (BN) {
+    case 256: return launch_halo<256>(P, st);
+    case 128: return launch_halo<128>(P, st);
+    case 64: return launch_halo<64>(P, st);
+    case 32: return launch_halo<32>(P, st);
+    default: return launch_halo<16>(P, st);
+  }
+}
+
 unsigned long long* g_tc_dbg = nullptr;
 
 }  // namespace
@@ -649,6 +964,12 @@ unsigned long long* g_tc_dbg = nullptr;
 // [2] MMA wait-full, [3] MMA wait-tmem-empty, [4] MMA total, [5] epilogue wait-tmem-full, [6] epilogue drain+store
 DN_EXPORT int dn_tc_set_debug(void* device_counters) {
   g_tc_dbg = (unsigned long long*)device_counters;
+  return 0;
+}
+
+// 0 switches the shared-memory halo variant off (A/B comparisons, debugging)
+DN_EXPORT int dn_tc_set_halo(int enabled) {
+  g_halo_enabled = enabled != 0;
   return 0;
 }
 
@@ -679,6 +1000,10 @@ DN_EXPORT int dn_igemm_tc_supported(const dn_igemm* p) {
 }
 
 int dn_igemm_tc(const dn_igemm* p, cudaStream_t st) {
+  {
+    int wt[9];
+    if (halo_eligible(p, wt)) return dn_igemm_halo(p, wt, st);
+  }
   IgemmTcParams P;
   memset(&P, 0, sizeof(P));
   const int BN = pick_bn(p->cout_pad);

@@ -313,10 +313,12 @@ class ConvOp(Op):
         self.wg = wg_probs(self.x)
         if plan.prec.act != g and plan.prec.act != torch.float32 and tc_enabled():
             # kind::f16 MMAs need both operands in one format: use a just-in-time copy of x in the gradient dtype
-            xq = plan.scratch_buf(self.x.N, self.x.H, self.x.W, self.x.C, g).view()
+            sh = plan.shadow_lookup(self.x)
+            xq = sh if sh is not None else plan.scratch_buf(self.x.N, self.x.H, self.x.W, self.x.C, g).view()
             alt = wg_probs(xq)
             if all(be == 1 for _, be, _ in alt):
-                self.xq, self.wg = xq, alt
+                self.wg = alt
+                self.xq = None if sh is not None else xq     # a shadow is already filled by its producer
         # ---- data-gradient problems
         self.dg = []
         if self.needs_dx:
@@ -386,6 +388,7 @@ class BNOp(Op):
 
     def __init__(self, plan, name, y, out, act=L.ACT_RELU, pool=False, residual=None):
         self.name, self.y, self.out, self.act, self.pool, self.res = name, y, out, act, int(pool), residual
+        self.out2 = plan.shadow_of(out) if (out is not None and plan.training) else None
         Cc = y.C
         dev = plan.device
         self.sums = torch.zeros(2 * Cc, dtype=torch.float64, device=dev)
@@ -408,7 +411,7 @@ class BNOp(Op):
                int(plan.training), 1, L.ptr(self.mean_invstd), L.ptr(self.scale_shift), self.y.C, st)
         if self.out is not None:
             L.call('dn_bn_apply', self.y.ref(), L.ptr(self.scale_shift), self.res.ref() if self.res else None, self.act,
-                   self.pool, self.out.ref(), st)
+                   self.pool, self.out.ref(), self.out2.ref() if self.out2 is not None else None, st)
 
     def plan_bwd(self, plan):
         if self.out is None:
@@ -575,6 +578,27 @@ class Plan:
 
     def new_buf(self, N, H, W, Cc, dtype=None):
         return Buf(N, H, W, Cc, dtype or self.prec.act, self.device)
+
+    def shadow_of(self, v):
+        """View (same geometry) into a gradient-dtype shadow of v's buffer, created on first use; None when activations
+        and gradients share a dtype or the tensor cores are off.  Producers that can write two outputs in one pass
+        (BatchNorm apply) fill it; ConvOp.bwd then skips the just-in-time conversion of its input."""
+        if self.prec.act == self.prec.grad or self.prec.act == torch.float32 or not tc_enabled():
+            return None
+        b = v.buf
+        if getattr(b, 'shadow', None) is None:
+            b.shadow = Buf(b.N, b.H, b.W, b.C, self.prec.grad, self.device)
+            b.shadow_valid = []
+        b.shadow_valid.append((v.c0, v.c0 + v.C))
+        return View(b.shadow, v.c0, v.C, v.H, v.W, v.off, v.sH, v.sW)
+
+    def shadow_lookup(self, v):
+        b = v.buf
+        if getattr(b, 'shadow', None) is None:
+            return None
+        if any(lo <= v.c0 and v.c0 + v.C <= hi for lo, hi in b.shadow_valid):
+            return View(b.shadow, v.c0, v.C, v.H, v.W, v.off, v.sH, v.sW)
+        return None
 
     def scratch_buf(self, N, H, W, Cc, dtype):
         """Buf carved from the plan's shared scratch storage (valid only between consecutive launches)."""
