@@ -387,16 +387,13 @@ __global__ void __launch_bounds__(192, 1) igemm_tc_kernel(const __grid_constant_
 // tile fetches its 128x64 activation box nine times (once per tap).  Here one (16+2) x 16-pixel halo box is fetched per
 // 64-channel chunk (the tile is 16 rows x 8 columns of pixels, the box is padded to 16 columns so that an image row is
 // 2048 bytes = two swizzle atoms) and the nine taps are nine *views* of it: the A descriptor starts (kh*16 + kw) pixels
-// further, keeps SBO = 2048 B between the 8-pixel row groups and carries base_offset = kw so that the 128-byte swizzle
-// phase of the shifted start is honoured.  The packed weights of all taps stay resident in shared memory for the
+// further and keeps SBO = 2048 B between the 8-pixel row groups (the swizzle is address-based, so the shifted start needs
+// no base_offset).  The packed weights of all taps stay resident in shared memory for the
 // lifetime of the persistent CTA.
 // ------------------------------------------------------------------------------------------------
 constexpr int kHaloW = 16, kHaloH = 18;
 constexpr uint32_t kHaloBytes = kHaloW * kHaloH * 128;     // 36864
 
-__device__ __forceinline__ uint64_t make_desc_bo(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t base_offset) {
-  return make_desc(smem_addr, lbo_bytes, sbo_bytes) | ((uint64_t)(base_offset & 7u) << 49);
-}
 
 struct HaloParams {
   CUtensorMap tmA;
@@ -497,7 +494,9 @@ __global__ void __launch_bounds__(192, 1) igemm_halo_kernel(const __grid_constan
 #pragma unroll
           for (int t = 0; t < 9; ++t) {
             const int kh = t / 3, kw = t % 3;
-            const uint64_t ad0 = make_desc_bo(sa + (uint32_t)(kh * kHaloW + kw) * 128, 16, 2048, (uint32_t)kw);
+            // base_offset stays 0: the 128B swizzle is a function of the absolute shared-memory address bits (measured on B200:
+            // only base_offset = 0 reproduces the unshifted kernel), so a start that is not 1024-byte aligned needs no correction
+            const uint64_t ad0 = make_desc(sa + (uint32_t)(kh * kHaloW + kw) * 128, 16, 2048);
             const uint64_t bd0 = make_desc(sb0 + (uint32_t)(t * p.kchunks + kc) * B_BYTES, 16, 1024);
 #pragma unroll
             for (int k = 0; k < 4; ++k)

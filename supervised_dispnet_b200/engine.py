@@ -49,6 +49,10 @@ def default_precision():
     return os.environ.get('DISPNET_B200_PRECISION', 'mixed')
 
 
+def graphs_enabled():
+    return os.environ.get('DISPNET_B200_GRAPHS', '1') != '0' and L.PROFILE is None
+
+
 def tc_enabled():
     return os.environ.get('DISPNET_B200_BACKEND', 'auto') != 'generic' and L.lib().dn_tc_available() == 1
 
@@ -561,6 +565,8 @@ class Plan:
         self._bwd_planned = False
         self._scratch = None
         self._ws = None
+        self._fwd_graph, self._bwd_graphs, self._graph_key = None, {}, None
+        self._fwd_warm = self._bwd_warm = 0
         self.generation = 0
 
     # ---- construction
@@ -626,17 +632,65 @@ class Plan:
     def bind(self, tensors):
         self._params = tensors
 
-    def run_forward(self, inputs):
-        for x in inputs:
-            L.require_cuda(x)
-        self.inputs = [x.contiguous().float() for x in inputs]
+    # ---- eager execution -----------------------------------------------------------------------------------------
+    def _forward_impl(self, inputs):
+        self.inputs = inputs
         self.stream = L.stream_ptr()
         self.outputs = [torch.empty(s, dtype=torch.float32, device=self.device) for s in self.out_shapes]
         for op in self.ops:
             op.fwd(self)
         self.saved_outputs = self.outputs
-        self.generation += 1
         return tuple(self.outputs)
+
+    def _backward_impl(self, gouts):
+        self.stream = L.stream_ptr()
+        self.gouts = gouts
+        total = sum(self._params[n].numel() for n in self.param_names)
+        flat = torch.zeros(total, dtype=torch.float32, device=self.device)
+        self._grads, o = {}, 0
+        for n in self.param_names:
+            p = self._params[n]
+            self._grads[n] = flat[o:o + p.numel()].view(p.shape)
+            o += p.numel()
+        for op in reversed(self.ops):
+            op.bwd(self)
+        return flat
+
+    # ---- CUDA-graph execution: the whole forward (and backward) op list is captured once per plan and replayed, so a
+    # step costs two graph launches instead of ~300 host-side launches (the reference's loop is launch-bound)
+    def _ptr_key(self):
+        return tuple(self._params[n].data_ptr() for n in self.param_names) + tuple(
+            v.data_ptr() for k, v in self._params.items() if k.endswith(('running_mean', 'running_var', 'num_batches_tracked')))
+
+    def run_forward(self, inputs):
+        for x in inputs:
+            L.require_cuda(x)
+        inputs = [x.contiguous().float() for x in inputs]
+        self.generation += 1
+        if not graphs_enabled():
+            return self._forward_impl(inputs)
+        key = self._ptr_key()
+        if self._fwd_graph is not None and key != self._graph_key:
+            self._fwd_graph, self._bwd_graphs, self._fwd_warm, self._bwd_warm = None, {}, 0, 0     # storage moved: re-capture
+        self._graph_key = key
+        if self._fwd_graph is None:
+            if self._fwd_warm < 2:          # lazy one-time initialisation must happen outside a capture
+                self._fwd_warm += 1
+                return self._forward_impl(inputs)
+            self._static_in = [x.clone() for x in inputs]
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            calls0 = L.CALLS
+            with torch.cuda.graph(g, capture_error_mode='thread_local'):
+                self._static_out = self._forward_impl(self._static_in)
+            self._fwd_graph, self._fwd_calls = g, L.CALLS - calls0
+        for s_, x in zip(self._static_in, inputs):
+            s_.copy_(x)
+        self.inputs = self._static_in
+        self.outputs = self.saved_outputs = list(self._static_out)
+        self._fwd_graph.replay()
+        L.CALLS += self._fwd_calls
+        return tuple(o.clone() for o in self._static_out)
 
     def plan_backward(self):
         if self._bwd_planned:
@@ -649,18 +703,38 @@ class Plan:
 
     def run_backward(self, gouts):
         self.plan_backward()
-        self.stream = L.stream_ptr()
-        self.gouts = [None if g is None else g.contiguous().float() for g in gouts]
-        total = sum(self._params[n].numel() for n in self.param_names)
-        flat = torch.zeros(total, dtype=torch.float32, device=self.device)
-        self._grads, o = {}, 0
+        gouts = [None if g is None else g.contiguous().float() for g in gouts]
+        if not graphs_enabled() or self._fwd_graph is None:
+            self._backward_impl(gouts)
+            return self._grads
+        pattern = tuple(g is not None for g in gouts)
+        ent = self._bwd_graphs.get(pattern)
+        if ent is None:
+            if self._bwd_warm < 1:
+                self._bwd_warm += 1
+                self._backward_impl(gouts)
+                return self._grads
+            static_g = [None if g is None else g.clone() for g in gouts]
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            calls0 = L.CALLS
+            with torch.cuda.graph(g, capture_error_mode='thread_local'):
+                flat = self._backward_impl(static_g)
+            ent = (g, static_g, flat, dict(self._grads), L.CALLS - calls0)
+            self._bwd_graphs[pattern] = ent
+        g, static_g, flat, views, ncalls = ent
+        for s_, x in zip(static_g, gouts):
+            if s_ is not None:
+                s_.copy_(x)
+        g.replay()
+        L.CALLS += ncalls
+        out = flat.clone()          # autograd may keep / accumulate into what we return: hand out a private copy
+        res, o = {}, 0
         for n in self.param_names:
             p = self._params[n]
-            self._grads[n] = flat[o:o + p.numel()].view(p.shape)
+            res[n] = out[o:o + p.numel()].view(p.shape)
             o += p.numel()
-        for op in reversed(self.ops):
-            op.bwd(self)
-        return self._grads
+        return res
 
 
 class _NetFn(torch.autograd.Function):
