@@ -41,12 +41,12 @@ struct TapList {
 
 __global__ void pack_weight_kernel(const float* __restrict__ src, void* dst, int dt, int T, int R, int Cc, int R_pad,
                                    int C_pad, TapList taps, long long s_r, long long s_c, long long s_kh, long long s_kw) {
-  long long total = (long long)T * R_pad * C_pad;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    int c = (int)(i % C_pad);
-    long long q = i / C_pad;
-    int r = (int)(q % R_pad);
-    int t = (int)(q / R_pad);
+  const unsigned total = (unsigned)T * R_pad * C_pad;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned q = i / (unsigned)C_pad;
+    const int c = (int)(i - q * (unsigned)C_pad);
+    const int t = (int)(q / (unsigned)R_pad);
+    const int r = (int)(q - (unsigned)t * (unsigned)R_pad);
     float v = 0.f;
     if (r < R && c < Cc) v = src[r * s_r + c * s_c + taps.kh[t] * s_kh + taps.kw[t] * s_kw];
     dn_st(dst, dt, i, v);
@@ -71,12 +71,12 @@ DN_EXPORT int dn_pack_weight(const float* src, void* dst, int dst_dtype, int T, 
 __global__ void unpack_wgrad_kernel(const float* __restrict__ src, float* __restrict__ dst, int T, int R, int Cc, int R_pad,
                                     int C_pad, TapList taps, long long s_r, long long s_c, long long s_kh, long long s_kw,
                                     float scale) {
-  long long total = (long long)T * R * Cc;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    int c = (int)(i % Cc);
-    long long q = i / Cc;
-    int r = (int)(q % R);
-    int t = (int)(q / R);
+  const unsigned total = (unsigned)T * R * Cc;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned q = i / (unsigned)Cc;
+    const int c = (int)(i - q * (unsigned)Cc);
+    const int t = (int)(q / (unsigned)R);
+    const int r = (int)(q - (unsigned)t * (unsigned)R);
     dst[r * s_r + c * s_c + taps.kh[t] * s_kh + taps.kw[t] * s_kw] = scale * src[((long long)t * R_pad + r) * C_pad + c];
   }
 }
@@ -419,21 +419,28 @@ __device__ __forceinline__ void cg_block_reduce(float* vals, int CGb) {
 
 // second stage of the per-channel reductions: out[j] = scale * sum_blk ws[blk][j]  (double accumulation)
 constexpr int kMaxReduceBlocks = 2048;
-// 256 threads = 32 columns x 8 row groups; each group strides over the partial rows, then a shared-memory combine
+// 1024 threads = 32 columns x 32 row groups; each group strides over the partial rows, then a shared-memory combine
 template <typename TO>
-__global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ ws, int nblk, int n, TO* __restrict__ out, double scale) {
-  __shared__ double part[8][33];
+__global__ void __launch_bounds__(1024) reduce_partials_kernel(const float* __restrict__ ws, int nblk, int n, TO* __restrict__ out, double scale) {
+  __shared__ double part[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int j = blockIdx.x * 32 + tx;
   double s = 0.0;
-  if (j < n)
-    for (int b = ty; b < nblk; b += 8) s += (double)ws[(long long)b * n + j];
+  if (j < n) {
+    int b = ty;
+    for (; b + 96 < nblk; b += 128) {      // 4 independent loads in flight
+      float v0 = ws[(long long)b * n + j], v1 = ws[(long long)(b + 32) * n + j];
+      float v2 = ws[(long long)(b + 64) * n + j], v3 = ws[(long long)(b + 96) * n + j];
+      s += ((double)v0 + (double)v1) + ((double)v2 + (double)v3);
+    }
+    for (; b < nblk; b += 32) s += (double)ws[(long long)b * n + j];
+  }
   part[ty][tx] = s;
   __syncthreads();
   if (ty == 0 && j < n) {
     double t = 0.0;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) t += part[k][tx];
+    for (int k = 0; k < 32; ++k) t += part[k][tx];
     out[j] = (TO)(t * scale);
   }
 }
@@ -497,7 +504,7 @@ DN_EXPORT int dn_bn_stats(const dn_view* y, double* sums, float* ws, void* strea
     bn_stats_kernel<1><<<g.grid, 256, 0, dn_stream(stream)>>>(*y, ws, g.CGb);
   }
   DN_CHECK_LAUNCH();
-  reduce_partials_kernel<double><<<reduce_blocks(2 * y->C), 256, 0, dn_stream(stream)>>>(ws, g.grid.x, 2 * y->C, sums, 1.0);
+  reduce_partials_kernel<double><<<reduce_blocks(2 * y->C), 1024, 0, dn_stream(stream)>>>(ws, g.grid.x, 2 * y->C, sums, 1.0);
   DN_CHECK_LAUNCH();
   return 0;
 }
@@ -749,7 +756,7 @@ DN_EXPORT int dn_bn_bwd_reduce(const dn_view* dout, const dn_view* y, const dn_v
   else if (pool) bn_bwd_reduce_kernel<1, true><<<g.grid, 256, sm, st>>>(*dout, *y, r, hr, mean_invstd, gamma, beta, act, ws, g.CGb);
   else bn_bwd_reduce_kernel<1, false><<<g.grid, 256, sm, st>>>(*dout, *y, r, hr, mean_invstd, gamma, beta, act, ws, g.CGb);
   DN_CHECK_LAUNCH();
-  reduce_partials_kernel<double><<<reduce_blocks(2 * dout->C), 256, 0, st>>>(ws, g.grid.x, 2 * dout->C, red, 1.0);
+  reduce_partials_kernel<double><<<reduce_blocks(2 * dout->C), 1024, 0, st>>>(ws, g.grid.x, 2 * dout->C, red, 1.0);
   DN_CHECK_LAUNCH();
   return 0;
 }
@@ -903,7 +910,7 @@ DN_EXPORT int dn_act_bwd(const dn_view* dout, const dn_view* out, int act, float
   }
   DN_CHECK_LAUNCH();
   if (dbias) {
-    reduce_partials_kernel<float><<<reduce_blocks(dout->C), 256, 0, dn_stream(stream)>>>(ws, g.grid.x, dout->C, dbias, (double)gscale);
+    reduce_partials_kernel<float><<<reduce_blocks(dout->C), 1024, 0, dn_stream(stream)>>>(ws, g.grid.x, dout->C, dbias, (double)gscale);
     DN_CHECK_LAUNCH();
   }
   return 0;

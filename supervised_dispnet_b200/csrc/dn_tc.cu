@@ -605,6 +605,7 @@ struct WgradTcParams {
   int stages;
   int n_mma;               // MMA N per tap (multiple of 16, <= BNQ)
   int tmem_cols;
+  int halo;                // 1: x is fetched once per pixel tile as a (8+2) x 16-pixel halo box, taps are shifted views
   uint32_t idesc;
   float* dw;
   int cp, cq, cp_pad, cq_pad;
@@ -618,8 +619,9 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr uint32_t BLK_BYTES = KPX * 128;              // one [KPX px][64 ch] swizzled block
   constexpr uint32_t A_BYTES = 2 * BLK_BYTES;            // M = 128 channels of P
-  constexpr uint32_t B_BYTES = (BNQ / 64) * BLK_BYTES;   // per tap
-  const uint32_t STAGE_BYTES = A_BYTES + (uint32_t)p.tpc * B_BYTES;
+  constexpr uint32_t B_BYTES = (BNQ / 64) * BLK_BYTES;   // per tap (plain mode)
+  constexpr uint32_t HALO_BLK = 16 * 10 * 128;           // one [10 rows][16 px][64 ch] halo block (halo mode)
+  const uint32_t STAGE_BYTES = A_BYTES + (p.halo ? (uint32_t)(BNQ / 64) * HALO_BLK : (uint32_t)p.tpc * B_BYTES);
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int stages = p.stages;
   uint64_t* full_bar = (uint64_t*)(smem + (size_t)stages * STAGE_BYTES);
@@ -662,7 +664,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
   const uint32_t tmem_base = *tmem_ptr;
 
   // bytes that really arrive per stage: only the P blocks that exist and the taps of this group are loaded
-  const uint32_t tx_bytes = (uint32_t)p.cp_blocks * BLK_BYTES + (uint32_t)nt * B_BYTES;
+  const uint32_t tx_bytes = (uint32_t)p.cp_blocks * BLK_BYTES + (p.halo ? (uint32_t)(BNQ / 64) * HALO_BLK : (uint32_t)nt * B_BYTES);
 
   if (n_iters > 0) {
     if (warp == 0) {
@@ -679,12 +681,18 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
           mbar_expect_tx(&full_bar[stage], tx_bytes);
           for (int j = 0; j < p.cp_blocks; ++j)
             tma_load_4d(sa + j * BLK_BYTES, &p.tmP[src], &full_bar[stage], cpt * 128 + j * 64, w0, h0, n0);
-          for (int t = 0; t < nt; ++t) {
-            const TcTap tap = p.taps[t0 + t];
-            uint8_t* sb = sa + A_BYTES + (size_t)t * B_BYTES;
+          if (p.halo) {
 #pragma unroll
             for (int j = 0; j < BNQ / 64; ++j)
-              tma_load_4d(sb + j * BLK_BYTES, &p.tmQ, &full_bar[stage], cqt * BNQ + j * 64, w0 + tap.dw, h0 + tap.dh, n0);
+              tma_load_4d(sa + A_BYTES + j * HALO_BLK, &p.tmQ, &full_bar[stage], cqt * BNQ + j * 64, w0 - 1, h0 - 1, n0);
+          } else {
+            for (int t = 0; t < nt; ++t) {
+              const TcTap tap = p.taps[t0 + t];
+              uint8_t* sb = sa + A_BYTES + (size_t)t * B_BYTES;
+#pragma unroll
+              for (int j = 0; j < BNQ / 64; ++j)
+                tma_load_4d(sb + j * BLK_BYTES, &p.tmQ, &full_bar[stage], cqt * BNQ + j * 64, w0 + tap.dw, h0 + tap.dh, n0);
+            }
           }
         }
         __syncwarp();
@@ -701,11 +709,23 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
         const uint64_t ad0 = make_desc(sa, BLK_BYTES, 1024);
         if (elect_one()) {
           for (int t = 0; t < nt; ++t) {
-            const uint64_t bd0 = make_desc(sa + A_BYTES + (uint32_t)t * B_BYTES, BLK_BYTES, 1024);
+            if (p.halo) {
+              // pixel tile = 8 rows x 8 columns; tap (dh, dw) reads halo pixel (row + dh + 1, col + dw + 1): a view that starts
+              // ((dh+1)*16 + (dw+1)) pixels into the 16-pixel-pitch halo block.  One UMMA_K step = 16 pixels = 2 image rows.
+              const TcTap tap = p.taps[t0 + t];
+              const uint32_t sb = sa + A_BYTES + (uint32_t)((tap.dh + 1) * 16 + (tap.dw + 1)) * 128;
+              const uint64_t bd0 = make_desc(sb, HALO_BLK, 2048);
 #pragma unroll
-            for (int k = 0; k < KPX / 16; ++k)
-              umma_f16(tmem_base + (uint32_t)(t * p.n_mma), ad0 + (uint64_t)(128 * k), bd0 + (uint64_t)(128 * k), p.idesc,
-                       (it > 0 || k > 0) ? 1u : 0u);
+              for (int k = 0; k < KPX / 16; ++k)
+                umma_f16(tmem_base + (uint32_t)(t * p.n_mma), ad0 + (uint64_t)(128 * k), bd0 + (uint64_t)(256 * k), p.idesc,
+                         (it > 0 || k > 0) ? 1u : 0u);
+            } else {
+              const uint64_t bd0 = make_desc(sa + A_BYTES + (uint32_t)t * B_BYTES, BLK_BYTES, 1024);
+#pragma unroll
+              for (int k = 0; k < KPX / 16; ++k)
+                umma_f16(tmem_base + (uint32_t)(t * p.n_mma), ad0 + (uint64_t)(128 * k), bd0 + (uint64_t)(128 * k), p.idesc,
+                         (it > 0 || k > 0) ? 1u : 0u);
+            }
           }
           umma_commit(&empty_bar[stage]);
           if (it == n_iters - 1) umma_commit(done_bar);
@@ -837,7 +857,7 @@ int launch_igemm(const IgemmTcParams& P, cudaStream_t st) {
 
 template <int BNQ>
 int launch_wgrad(const WgradTcParams& P, int items, cudaStream_t st) {
-  const uint32_t stage_bytes = 2 * KPX * 128 + (uint32_t)P.tpc * (BNQ / 64) * KPX * 128;
+  const uint32_t stage_bytes = 2 * KPX * 128 + (P.halo ? (uint32_t)(BNQ / 64) * 16 * 10 * 128 : (uint32_t)P.tpc * (BNQ / 64) * KPX * 128);
   size_t smem = (size_t)P.stages * stage_bytes + 1024 + (2 * P.stages + 1) * 8 + 16;
   static bool attr_set = false;
   if (!attr_set) {
@@ -1074,13 +1094,27 @@ int dn_wgrad_tc(const dn_wgrad* p, cudaStream_t st) {
   WgradTcParams P;
   memset(&P, 0, sizeof(P));
   const dn_view& P0 = p->p[0];
-  choose_box(P0.N, P0.H, P0.W, KPX, P.wb, P.hb, P.nb);
+  // halo mode: the nine taps of a 3x3 stride-1 convolution read one shared x halo box
+  bool halo = g_halo_enabled && p->ntaps == 9 && p->nsrc == 1 && P0.H == p->q.H && P0.W == p->q.W;
+  if (halo) {
+    bool seen[9] = {false};
+    for (int t = 0; t < 9 && halo; ++t) {
+      int dh = p->taps[t].dh, dw = p->taps[t].dw;
+      if (dh < -1 || dh > 1 || dw < -1 || dw > 1 || seen[(dh + 1) * 3 + dw + 1]) halo = false;
+      else seen[(dh + 1) * 3 + dw + 1] = true;
+    }
+    const double eff = (double)P0.H * P0.W / ((double)((P0.H + 7) / 8 * 8) * ((P0.W + 7) / 8 * 8));
+    if (eff < 0.85) halo = false;
+  }
+  P.halo = halo ? 1 : 0;
+  if (halo) { P.wb = 8; P.hb = 8; P.nb = 1; }
+  else choose_box(P0.N, P0.H, P0.W, KPX, P.wb, P.hb, P.nb);
   for (int s = 0; s < p->nsrc; ++s) {
     int e = make_view_map(&P.tmP[s], p->p[s], P.wb, P.hb, P.nb);
     if (e) return e;
   }
   {
-    int e = make_view_map(&P.tmQ, p->q, P.wb, P.hb, P.nb);
+    int e = halo ? make_view_map(&P.tmQ, p->q, 16, 10, 1) : make_view_map(&P.tmQ, p->q, P.wb, P.hb, P.nb);
     if (e) return e;
   }
   for (int t = 0; t < p->ntaps; ++t) {
@@ -1106,7 +1140,7 @@ int dn_wgrad_tc(const dn_wgrad* p, cudaStream_t st) {
   int tpc = 512 / P.n_mma;
   int by_smem = (int)((64 * 1024 - a_bytes) / b_bytes);
   if (by_smem < 1) by_smem = 1;
-  if (tpc > by_smem) tpc = by_smem;
+  if (!halo && tpc > by_smem) tpc = by_smem;
   if (tpc > P.ntaps) tpc = P.ntaps;
   // all taps of a group must read the same dy view
   for (int t = 1; t < P.ntaps; ++t)
@@ -1122,7 +1156,7 @@ int dn_wgrad_tc(const dn_wgrad* p, cudaStream_t st) {
   if (splits < 1) splits = 1;
   P.ptiles_per_split = (P.num_ptiles + splits - 1) / splits;
   P.splits = (P.num_ptiles + P.ptiles_per_split - 1) / P.ptiles_per_split;
-  const uint32_t stage_bytes = a_bytes + (uint32_t)P.tpc * b_bytes;
+  const uint32_t stage_bytes = a_bytes + (halo ? (uint32_t)(BNQ / 64) * 16 * 10 * 128 : (uint32_t)P.tpc * b_bytes);
   P.stages = (int)((200 * 1024) / stage_bytes);
   if (P.stages > 8) P.stages = 8;
   P.idesc = make_idesc(P0.dtype, p->q.dtype, 1, 1, 128, P.n_mma);

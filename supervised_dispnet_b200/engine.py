@@ -323,6 +323,11 @@ class ConvOp(Op):
             if all(be == 1 for _, be, _ in alt):
                 self.wg = alt
                 self.xq = None if sh is not None else xq     # a shadow is already filled by its producer
+                if self.xq is not None:
+                    # copy whole 16-byte channel groups (vector path) when the tail channels are buffer padding
+                    cpad = _ru(self.x.C, 8) if _pad_ok(self.x) else self.x.C
+                    self.x_cp = View(self.x.buf, self.x.c0, cpad, self.x.H, self.x.W, self.x.off, self.x.sH, self.x.sW)
+                    self.xq_cp = View(xq.buf, xq.c0, cpad, xq.H, xq.W, xq.off, xq.sH, xq.sW)
         # ---- data-gradient problems
         self.dg = []
         if self.needs_dx:
@@ -370,7 +375,7 @@ class ConvOp(Op):
                    plan.stream)
         self.dwp.zero_()
         if self.xq is not None:
-            L.call('dn_copy_view', self.x.ref(), self.xq.ref(), 0, plan.stream)
+            L.call('dn_copy_view', self.x_cp.ref(), self.xq_cp.ref(), 0, plan.stream)
         for p, be, fl in self.wg:
             L.call('dn_wgrad_run', C.byref(p), be, plan.stream, tag=('wgrad', be, fl, self.name))
         gw = plan.grad_of(self.name + '.weight')
