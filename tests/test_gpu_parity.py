@@ -102,7 +102,7 @@ def test_golden_g4_photometric(golden):
                 assert rel_robust(d.grad, r) < 1e-3
                 assert ((d.grad.cpu() - r).abs() > 1e-3 * r.abs().max()).sum() <= 2
             # a sample that flips in / out of view on a 1-ulp coordinate difference moves one pose component by ~1e-3
-            assert rel(pose.grad, g['gpose']) < 3e-3
+            assert rel(pose.grad, g['gpose']) < (1e-2 if pad == 'border' else 1e-3)   # border: the 1-2 flipped pixels above
             if use_mask:
                 for m, r in zip(masks, g['gmask']):
                     assert rel(m.grad, r) < 1e-3
