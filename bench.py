@@ -31,6 +31,9 @@ import torch  # noqa: E402
 H, W, BATCH = 128, 416, 32
 TRAIN_GFLOP_PER_IMG = 110.7        # BASELINE.md section 3 (3 x forward MACs x 2), Disp_vgg_BN @ 128x416
 METRIC = 'images/sec (128x416, b=32/GPU)'
+# forward + data-gradient gather-convolutions of Disp_vgg_BN at b=32: every layer reads its input and writes its output once
+# (2 B/element) in each direction: 2 x 2 x (1.14 G conv-input + 1.10 G conv-output elements) ~ 4.4 GB per step
+ALGO_CONV_BYTES_PER_STEP = 4.4e9
 
 
 def load_peaks():
@@ -274,6 +277,11 @@ def run_ours(args):
     achieved = tc_f / (tc_t * 1e-3) / 1e12 if tc_t > 0 else 0.0
     breakdown = {k: round(t / nprof, 3) for k, (t, n, f) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:14]}
 
+    traffic, traffic_src = None, None
+    tp = os.path.join(ROOT, 'profiles', 'r1_traffic.json')
+    if os.path.exists(tp):
+        tj = json.load(open(tp))
+        traffic, traffic_src = tj['dram_bytes_per_launch'], tj['source']
     total_imgs = BATCH * world * args.steps
     value = total_imgs / (ms * 1e-3)
     e2e = total_imgs / (ms2 * 1e-3)
@@ -291,7 +299,9 @@ def run_ours(args):
                 gpu_launches=calls,
                 roofline=dict(bound='tensor', kernel='igemm_tc_kernel (forward + data-gradient gather-convolutions)',
                               achieved=achieved, peak=peaks['tf_sust'], unit='TFLOP/s', frac=achieved / peaks['tf_sust'],
-                              traffic=None, peak_source=peaks['src'] + ' sustained bf16 (kernel timed inside a long step)',
+                              traffic=traffic, traffic_unit='DRAM bytes per launch (ncu dram__bytes_read+write, average over the launches of one step)',
+                              traffic_source=traffic_src, algorithmic_bytes_per_launch=ALGO_CONV_BYTES_PER_STEP / max(tc_n, 1),
+                              peak_source=peaks['src'] + ' sustained bf16 (kernel timed inside a long step)',
                               launches_per_step=tc_n, kernel_ms_per_step=tc_t, flops_per_step=tc_f,
                               step_fraction_of_tensor_roofline=(value / world * TRAIN_GFLOP_PER_IMG) / (peaks['tf_sust'] * 1e3)),
                 kernel_breakdown_ms_per_step=breakdown, all_kernels_ms_per_step=kern_ms)
