@@ -120,6 +120,20 @@ int dn_unpack_wgrad(const float* src, float* dst, int T, int R, int Cc, int R_pa
                     const int32_t* kh, const int32_t* kw, int64_t s_r, int64_t s_c, int64_t s_kh, int64_t s_kw,
                     float scale, void* stream);
 
+/* Batched form of the two calls above: one launch serves every layer of a network (the per-layer calls are a few
+ * microseconds of fixed cost each, 80+ of them per step).  `jobs` is a DEVICE array. */
+typedef struct dn_pack_job {
+  const void* src;      /* pack: fp32 torch parameter;        unpack: packed fp32 gradient [T][R_pad][C_pad] */
+  void* dst;            /* pack: packed [T][R_pad][C_pad];    unpack: fp32 torch-layout gradient */
+  int32_t dst_dtype;    /* pack only */
+  int32_t unpack;       /* 0 = pack, 1 = unpack */
+  int32_t T, R, Cc, R_pad, C_pad, k;   /* tap t = (kh, kw) = (t / k, t % k) */
+  int64_t s_r, s_c, s_kh, s_kw;
+  float scale;          /* unpack only */
+  int32_t pad_;
+} dn_pack_job;
+int dn_pack_jobs(const dn_pack_job* jobs, int njobs, void* stream);
+
 /* ---- convolutions (nn.Conv2d / nn.ConvTranspose2d fwd, dgrad, wgrad) ------------------------- */
 /* backend: 0 = CUDA-core tiled kernel (any shape/dtype), 1 = tcgen05/TMA kernel (fp16/bf16, stride 1). */
 int dn_igemm_run(const dn_igemm* p, int backend, void* stream);

@@ -36,6 +36,13 @@ class DnWgrad(C.Structure):
                 ('taps', DnTap * MAX_TAPS), ('scale', C.c_float)]
 
 
+class DnPackJob(C.Structure):
+    _fields_ = [('src', C.c_void_p), ('dst', C.c_void_p), ('dst_dtype', C.c_int32), ('unpack', C.c_int32), ('T', C.c_int32),
+                ('R', C.c_int32), ('Cc', C.c_int32), ('R_pad', C.c_int32), ('C_pad', C.c_int32), ('k', C.c_int32),
+                ('s_r', C.c_int64), ('s_c', C.c_int64), ('s_kh', C.c_int64), ('s_kw', C.c_int64), ('scale', C.c_float),
+                ('pad_', C.c_int32)]
+
+
 _P = C.c_void_p
 _I = C.c_int
 _I64 = C.c_int64
@@ -52,6 +59,7 @@ _SIGS = {
     'dn_pack_input': ([_P, _I, _I, _I, _I, _V, _I, _P], _I),
     'dn_pack_weight': ([_P, _P, _I, _I, _I, _I, _I, _I, _IP, _IP, _I64, _I64, _I64, _I64, _P], _I),
     'dn_unpack_wgrad': ([_P, _P, _I, _I, _I, _I, _I, _IP, _IP, _I64, _I64, _I64, _I64, _F, _P], _I),
+    'dn_pack_jobs': ([_P, _I, _P], _I),
     'dn_igemm_run': ([C.POINTER(DnIgemm), _I, _P], _I),
     'dn_wgrad_run': ([C.POINTER(DnWgrad), _I, _P], _I),
     'dn_igemm_tc_supported': ([C.POINTER(DnIgemm)], _I),

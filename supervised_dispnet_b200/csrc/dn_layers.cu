@@ -96,6 +96,43 @@ DN_EXPORT int dn_unpack_wgrad(const float* src, float* dst, int T, int R, int Cc
   return 0;
 }
 
+__global__ void __launch_bounds__(256) pack_jobs_kernel(const dn_pack_job* __restrict__ jobs) {
+  const dn_pack_job j = jobs[blockIdx.y];
+  const unsigned k = (unsigned)j.k;
+  if (!j.unpack) {
+    const float* src = (const float*)j.src;
+    const unsigned total = (unsigned)j.T * j.R_pad * j.C_pad;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+      const unsigned q = i / (unsigned)j.C_pad;
+      const int c = (int)(i - q * (unsigned)j.C_pad);
+      const unsigned t = q / (unsigned)j.R_pad;
+      const int r = (int)(q - t * (unsigned)j.R_pad);
+      float v = 0.f;
+      if (r < j.R && c < j.Cc) v = src[r * j.s_r + c * j.s_c + (long long)(t / k) * j.s_kh + (long long)(t % k) * j.s_kw];
+      dn_st(j.dst, j.dst_dtype, i, v);
+    }
+  } else {
+    const float* src = (const float*)j.src;
+    float* dst = (float*)j.dst;
+    const unsigned total = (unsigned)j.T * j.R * j.Cc;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+      const unsigned q = i / (unsigned)j.Cc;
+      const int c = (int)(i - q * (unsigned)j.Cc);
+      const unsigned t = q / (unsigned)j.R;
+      const int r = (int)(q - t * (unsigned)j.R);
+      dst[r * j.s_r + c * j.s_c + (long long)(t / k) * j.s_kh + (long long)(t % k) * j.s_kw] =
+          j.scale * src[((long long)t * j.R_pad + r) * j.C_pad + c];
+    }
+  }
+}
+
+DN_EXPORT int dn_pack_jobs(const dn_pack_job* jobs, int njobs, void* stream) {
+  if (!jobs || njobs < 1) return DN_E_ARG;
+  pack_jobs_kernel<<<dim3(48, njobs), 256, 0, dn_stream(stream)>>>(jobs);
+  DN_CHECK_LAUNCH();
+  return 0;
+}
+
 // =================================================================================================
 // CUDA-core gather-convolution (backend 0): 256 threads, BMxBN output tile, 4x4 per thread, K chunks of 16
 // =================================================================================================
@@ -378,7 +415,12 @@ static CgGeom cg_geom(int C, int ch, long long pixels) {
   g.CGb = b;
   g.PL = 256 / b;
   int gy = (g.CG + b - 1) / b;
-  long long bx = (pixels + g.PL - 1) / g.PL;
+  // aim at >= 8 pixels per thread (the per-block prologue / partial-sum epilogue is a fixed cost), but never fewer blocks
+  // than SMs while there is at least one pixel per thread
+  long long bx_max = (pixels + g.PL - 1) / g.PL;
+  long long bx = (pixels + (long long)g.PL * 8 - 1) / ((long long)g.PL * 8);
+  long long floor_blocks = bx_max < dn_num_sms() ? bx_max : dn_num_sms();
+  if (bx < floor_blocks) bx = floor_blocks;
   long long cap = (long long)dn_num_sms() * 8 / gy;
   if (cap < 1) cap = 1;
   if (bx > cap) bx = cap;
@@ -705,17 +747,48 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_reduce_kernel(dn_view dout, dn_
     const float* sh = cst + Cs + c0;
     const float* mean = cst + 2 * Cs + c0;
     const float* istd = cst + 3 * Cs + c0;
-    for (unsigned px = blockIdx.x * PLn + pl; px < (unsigned)npix; px += gridDim.x * PLn) {
-      const unsigned q = px / (unsigned)dout.W;
-      const int w = (int)(px - q * (unsigned)dout.W);
-      const int n = (int)(q / (unsigned)dout.H);
-      const int h = (int)(q - (unsigned)n * (unsigned)dout.H);
-      BnBwdPix<CH, POOL> P;
-      P.load(y, res, has_res, dout, n, h, w, c0, sc, sh, act);
+    if (!POOL && !has_res) {
+      // un-pooled, no residual: 4 pixels per iteration with all 8 loads issued up front (HBM latency hiding)
+      const unsigned stride = gridDim.x * PLn;
+      for (unsigned px0 = blockIdx.x * PLn + pl; px0 < (unsigned)npix; px0 += 4 * stride) {
+        float gg[4][CH], yy[4][CH];
+        bool ok[4];
 #pragma unroll
-      for (int i = 0; i < CH; ++i) {
-        acc[i] += P.g[i];
-        acc[CH + i] = fmaf(P.g[i], (P.ysel(i) - mean[i]) * istd[i], acc[CH + i]);
+        for (int u = 0; u < 4; ++u) {
+          const unsigned px = px0 + u * stride;
+          ok[u] = px < (unsigned)npix;
+          const unsigned pc = ok[u] ? px : px0;
+          const unsigned q = pc / (unsigned)dout.W;
+          const int w = (int)(pc - q * (unsigned)dout.W);
+          const int n = (int)(q / (unsigned)dout.H);
+          const int h = (int)(q - (unsigned)n * (unsigned)dout.H);
+          ldc<CH>(dout, dn_off(dout, n, h, w) + c0, gg[u]);
+          ldc<CH>(y, dn_off(y, n, h, w) + c0, yy[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (ok[u]) {
+#pragma unroll
+            for (int i = 0; i < CH; ++i) {
+              const float g = gg[u][i] * dn_act_grad(dn_act(fmaf(yy[u][i], sc[i], sh[i]), act), act);
+              acc[i] += g;
+              acc[CH + i] = fmaf(g, (yy[u][i] - mean[i]) * istd[i], acc[CH + i]);
+            }
+          }
+      }
+    } else {
+      for (unsigned px = blockIdx.x * PLn + pl; px < (unsigned)npix; px += gridDim.x * PLn) {
+        const unsigned q = px / (unsigned)dout.W;
+        const int w = (int)(px - q * (unsigned)dout.W);
+        const int n = (int)(q / (unsigned)dout.H);
+        const int h = (int)(q - (unsigned)n * (unsigned)dout.H);
+        BnBwdPix<CH, POOL> P;
+        P.load(y, res, has_res, dout, n, h, w, c0, sc, sh, act);
+#pragma unroll
+        for (int i = 0; i < CH; ++i) {
+          acc[i] += P.g[i];
+          acc[CH + i] = fmaf(P.g[i], (P.ysel(i) - mean[i]) * istd[i], acc[CH + i]);
+        }
       }
     }
   }
@@ -793,6 +866,40 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_apply_kernel(dn_view dout, dn_v
   const float* istd = cst + 3 * Cs + c0;
   const float* m1 = cst + 4 * Cs + c0;
   const float* m2 = cst + 5 * Cs + c0;
+  if (!POOL && !has_res && !has_dres) {
+    const unsigned stride = gridDim.x * PLn;
+    for (unsigned px0 = blockIdx.x * PLn + pl; px0 < (unsigned)npix; px0 += 4 * stride) {
+      float gg[4][CH], yy[4][CH];
+      long long offo[4];
+      bool ok[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const unsigned px = px0 + u * stride;
+        ok[u] = px < (unsigned)npix;
+        const unsigned pc = ok[u] ? px : px0;
+        const unsigned q = pc / (unsigned)dout.W;
+        const int w = (int)(pc - q * (unsigned)dout.W);
+        const int n = (int)(q / (unsigned)dout.H);
+        const int h = (int)(q - (unsigned)n * (unsigned)dout.H);
+        ldc<CH>(dout, dn_off(dout, n, h, w) + c0, gg[u]);
+        ldc<CH>(y, dn_off(y, n, h, w) + c0, yy[u]);
+        offo[u] = dn_off(dy, n, h, w) + c0;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (ok[u]) {
+          float o[CH];
+#pragma unroll
+          for (int i = 0; i < CH; ++i) {
+            const float g = gg[u][i] * dn_act_grad(dn_act(fmaf(yy[u][i], sc[i], sh[i]), act), act);
+            const float xh = (yy[u][i] - mean[i]) * istd[i];
+            o[i] = sc[i] * (g - m1[i] - xh * m2[i]);
+          }
+          stc<CH>(dy, offo[u], o);
+        }
+    }
+    return;
+  }
   for (unsigned px = blockIdx.x * PLn + pl; px < (unsigned)npix; px += gridDim.x * PLn) {
     const unsigned q = px / (unsigned)dout.W;
     const int w = (int)(px - q * (unsigned)dout.W);

@@ -281,11 +281,27 @@ class ConvOp(Op):
             built.append((p, _backend('igemm', p), _igemm_flops(p)))
         return built
 
-    def fwd(self, plan):
-        W = plan.param(self.name + '.weight')
+    # ---- weight (un)packing is batched over all layers of the plan: one dn_pack_jobs launch each (Plan._run_jobs)
+    def job(self, plan, which):
         T = self.k * self.k
-        L.call('dn_pack_weight', L.ptr(W), L.ptr(self.wp), _DT[plan.prec.act], T, self.Cout, self.Cin, self.cout_pad,
-               self.cin_pad, self.kh, self.kw, self.s_co, self.s_ci, self.k, 1, plan.stream)
+        j = L.DnPackJob()
+        j.T, j.k, j.s_kh, j.s_kw = T, self.k, self.k, 1
+        W = plan.param(self.name + '.weight')
+        if which == 'fwd':
+            j.src, j.dst, j.dst_dtype, j.unpack = W.data_ptr(), self.wp.data_ptr(), _DT[plan.prec.act], 0
+            j.R, j.Cc, j.R_pad, j.C_pad, j.s_r, j.s_c = self.Cout, self.Cin, self.cout_pad, self.cin_pad, self.s_co, self.s_ci
+        elif which == 'dgrad':
+            if not self.needs_dx:
+                return None
+            j.src, j.dst, j.dst_dtype, j.unpack = W.data_ptr(), self.wpT.data_ptr(), _DT[plan.prec.grad], 0
+            j.R, j.Cc, j.R_pad, j.C_pad, j.s_r, j.s_c = self.Cin, self.Cout, self.cinT_pad, self.coutT_pad, self.s_ci, self.s_co
+        else:
+            j.src, j.dst, j.unpack = self.dwp.data_ptr(), plan.grad_of(self.name + '.weight').data_ptr(), 1
+            j.R, j.Cc, j.R_pad, j.C_pad, j.s_r, j.s_c = self.Cout, self.Cin, self.cout_pad, self.cin_pad, self.s_co, self.s_ci
+            j.scale = 1.0 / plan.prec.gscale
+        return j
+
+    def fwd(self, plan):
         if self._fwd_built is None:
             self._fwd_built = self._build_fwd(plan)
         b = plan.param(self.name + '.bias') if self.has_bias else None
@@ -298,7 +314,7 @@ class ConvOp(Op):
         T = self.k * self.k
         dev = plan.device
         self.gout = self.out.grad_view(g)
-        self.dwp = torch.zeros((T, self.cout_pad, self.cin_pad), dtype=torch.float32, device=dev)
+        self.dwp = plan.dwp_alloc(T * self.cout_pad * self.cin_pad).view(T, self.cout_pad, self.cin_pad)
         k, pad = self.k, self.pad
         # ---- weight-gradient problems
         def wg_probs(q):
@@ -366,27 +382,18 @@ class ConvOp(Op):
                 self.dg.append((p, _backend('igemm', p), _igemm_flops(p)))
 
     def bwd(self, plan):
-        W = plan.param(self.name + '.weight')
-        T = self.k * self.k
         inv = 1.0 / plan.prec.gscale
         gb = plan.grad_of(self.name + '.bias') if (self.has_bias and not self.bias_grad_zero) else None
         if self.act != L.ACT_NONE or gb is not None:
             L.call('dn_act_bwd', self.gout.ref(), self.out.ref(), self.act, L.ptr(gb), inv, L.ptr(plan.reduce_ws(self.Cout)),
                    plan.stream)
-        self.dwp.zero_()
         if self.xq is not None:
             L.call('dn_copy_view', self.x_cp.ref(), self.xq_cp.ref(), 0, plan.stream)
         for p, be, fl in self.wg:
             L.call('dn_wgrad_run', C.byref(p), be, plan.stream, tag=('wgrad', be, fl, self.name))
-        gw = plan.grad_of(self.name + '.weight')
-        L.call('dn_unpack_wgrad', L.ptr(self.dwp), L.ptr(gw), T, self.Cout, self.Cin, self.cout_pad, self.cin_pad, self.kh,
-               self.kw, self.s_co, self.s_ci, self.k, 1, inv, plan.stream)
         if self.needs_dx:
             if self.dx_zero_first is not None:
                 self.dx_zero_first.buf.t.zero_()
-            # transposed role: rows = ci, cols = co
-            L.call('dn_pack_weight', L.ptr(W), L.ptr(self.wpT), _DT[plan.prec.grad], T, self.Cin, self.Cout, self.cinT_pad,
-                   self.coutT_pad, self.kh, self.kw, self.s_ci, self.s_co, self.k, 1, plan.stream)
             for p, be, fl in self.dg:
                 L.call('dn_igemm_run', C.byref(p), be, plan.stream, tag=('dgrad', be, fl, self.name))
 
@@ -570,6 +577,9 @@ class Plan:
         self._bwd_planned = False
         self._scratch = None
         self._ws = None
+        self._gflat = None
+        self._dwp_arena, self._dwp_used = None, 0
+        self._job_tables = {}
         self._fwd_graph, self._bwd_graphs, self._graph_key = None, {}, None
         self._fwd_warm = self._bwd_warm = 0
         self.generation = 0
@@ -638,10 +648,30 @@ class Plan:
         self._params = tensors
 
     # ---- eager execution -----------------------------------------------------------------------------------------
+    def dwp_alloc(self, numel):
+        numel = _ru(numel, 64)
+        out = self._dwp_arena[self._dwp_used:self._dwp_used + numel]
+        self._dwp_used += numel
+        assert out.numel() == numel, 'packed weight-gradient arena exhausted'
+        return out
+
+    def _run_jobs(self, which):
+        key = (which, self._ptr_key())
+        ent = self._job_tables.get(which)
+        if ent is None or ent[0] != key:
+            jobs = [j for j in (op.job(self, which) for op in self.ops if isinstance(op, ConvOp)) if j is not None]
+            arr = (L.DnPackJob * len(jobs))(*jobs)
+            dev = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(self.device)
+            ent = (key, dev, len(jobs))
+            self._job_tables[which] = ent
+        if ent[2]:
+            L.call('dn_pack_jobs', L.ptr(ent[1]), ent[2], self.stream)
+
     def _forward_impl(self, inputs):
         self.inputs = inputs
         self.stream = L.stream_ptr()
         self.outputs = [torch.empty(s, dtype=torch.float32, device=self.device) for s in self.out_shapes]
+        self._run_jobs('fwd')
         for op in self.ops:
             op.fwd(self)
         self.saved_outputs = self.outputs
@@ -650,16 +680,21 @@ class Plan:
     def _backward_impl(self, gouts):
         self.stream = L.stream_ptr()
         self.gouts = gouts
-        total = sum(self._params[n].numel() for n in self.param_names)
-        flat = torch.zeros(total, dtype=torch.float32, device=self.device)
-        self._grads, o = {}, 0
-        for n in self.param_names:
-            p = self._params[n]
-            self._grads[n] = flat[o:o + p.numel()].view(p.shape)
-            o += p.numel()
+        if self._gflat is None:      # persistent fp32 gradient arena, one slice per parameter
+            total = sum(self._params[n].numel() for n in self.param_names)
+            self._gflat = torch.zeros(total, dtype=torch.float32, device=self.device)
+            self._grads, o = {}, 0
+            for n in self.param_names:
+                p = self._params[n]
+                self._grads[n] = self._gflat[o:o + p.numel()].view(p.shape)
+                o += p.numel()
+        self._gflat.zero_()
+        self._dwp_arena.zero_()
+        self._run_jobs('dgrad')
         for op in reversed(self.ops):
             op.bwd(self)
-        return flat
+        self._run_jobs('unpack')
+        return self._gflat
 
     # ---- CUDA-graph execution: the whole forward (and backward) op list is captured once per plan and replayed, so a
     # step costs two graph launches instead of ~300 host-side launches (the reference's loop is launch-bound)
@@ -700,8 +735,12 @@ class Plan:
     def plan_backward(self):
         if self._bwd_planned:
             return
-        big = max([op.x.buf.t.numel() for op in self.ops if isinstance(op, ConvOp)] + [1])
+        convs = [op for op in self.ops if isinstance(op, ConvOp)]
+        big = max([op.x.buf.t.numel() for op in convs] + [1])
         self._scratch = torch.empty(big * 4, dtype=torch.uint8, device=self.device)
+        self._dwp_arena = torch.zeros(sum(_ru(op.k * op.k * op.cout_pad * op.cin_pad, 64) for op in convs) + 64,
+                                      dtype=torch.float32, device=self.device)
+        self._dwp_used = 0
         for op in reversed(self.ops):
             op.plan_bwd(self)
         self._bwd_planned = True
@@ -710,15 +749,13 @@ class Plan:
         self.plan_backward()
         gouts = [None if g is None else g.contiguous().float() for g in gouts]
         if not graphs_enabled() or self._fwd_graph is None:
-            self._backward_impl(gouts)
-            return self._grads
+            return self._clone_grads(self._backward_impl(gouts))
         pattern = tuple(g is not None for g in gouts)
         ent = self._bwd_graphs.get(pattern)
         if ent is None:
             if self._bwd_warm < 1:
                 self._bwd_warm += 1
-                self._backward_impl(gouts)
-                return self._grads
+                return self._clone_grads(self._backward_impl(gouts))
             static_g = [None if g is None else g.clone() for g in gouts]
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
@@ -733,6 +770,9 @@ class Plan:
                 s_.copy_(x)
         g.replay()
         L.CALLS += ncalls
+        return self._clone_grads(flat)
+
+    def _clone_grads(self, flat):
         out = flat.clone()          # autograd may keep / accumulate into what we return: hand out a private copy
         res, o = {}, 0
         for n in self.param_names:

@@ -116,6 +116,7 @@ def test_conv_problem_tables_match_torch(c):
     # ---- backward problems
     gy = torch.randn_like(y)
     (y * gy).sum().backward()
+    plan._dwp_arena = torch.zeros(1 << 16)      # normally sized by Plan.plan_backward()
     op.plan_bwd(plan)
     fill_view(op.gout, gy)
     w_tT = w_t.transpose(1, 2).contiguous()                                  # [t][ci][co]
