@@ -158,8 +158,8 @@ int dn_bn_finalize(const double* sums, double count, const float* gamma, const f
  * activation that the weight-gradient GEMM consumes (tcgen05 kind::f16 cannot mix fp16 and bf16 operands). */
 int dn_bn_apply(const dn_view* y, const float* scale_shift, const dn_view* residual, int act, int pool,
                 const dn_view* out, const dn_view* out2, void* stream);
-/* backward: pass 1 accumulates red[2C] (double): sum(dyhat), sum(dyhat*xhat), where dyhat is the gradient
- * routed back through pool/act; pass 2 writes dy (and dres if residual). */
+/* backward: pass 1 writes red[2C] (double): sum(g), sum(g*y), where g is the gradient routed back through pool/act
+ * (raw sums: pass 2 derives sum(g*xhat) = invstd*(sum(g*y) - mean*sum(g)) from them); pass 2 writes dy (and dres). */
 int dn_bn_bwd_reduce(const dn_view* dout, const dn_view* y, const dn_view* residual, const float* mean_invstd,
                      const float* gamma, const float* beta, int act, int pool, double* red /* overwritten */, float* ws,
                      void* stream);

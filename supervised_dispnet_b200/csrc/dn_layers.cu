@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(256) pack_jobs_kernel(const dn_pack_job* __res
 
 DN_EXPORT int dn_pack_jobs(const dn_pack_job* jobs, int njobs, void* stream) {
   if (!jobs || njobs < 1) return DN_E_ARG;
-  pack_jobs_kernel<<<dim3(48, njobs), 256, 0, dn_stream(stream)>>>(jobs);
+  pack_jobs_kernel<<<dim3(296, njobs), 256, 0, dn_stream(stream)>>>(jobs);
   DN_CHECK_LAUNCH();
   return 0;
 }
@@ -668,10 +668,14 @@ DN_EXPORT int dn_bn_apply(const dn_view* y, const float* scale_shift, const dn_v
   return 0;
 }
 
-// Backward of BatchNorm(+residual)+act(+2x2 max pool).  POOL is a compile-time switch so that the un-pooled path keeps
-// a small register footprint (occupancy is what hides HBM latency here); the pooled path keeps the four window values
-// in registers, finds the arg-max (first maximum wins, as ATen's max_pool2d) and routes the gradient to it.
-// Per-channel constants live in shared memory ([6][C+CH]: scale, shift, mean, invstd, m1, m2) to keep registers for loads.
+// Backward of BatchNorm(+residual)+act(+2x2 max pool).
+//
+// With g = dout * act'(.) routed to the selected position, the two per-channel reductions BN backward needs are
+//   S1 = sum g      and      sum g * xhat = invstd * (S2 - mean * S1),  S2 = sum g * y,
+// so the reduce pass accumulates the *raw* S1, S2 and needs only the forward scale/shift per channel (to redo the
+// activation / arg-max decision with exactly the forward arithmetic).  The apply pass folds everything else into three
+// per-channel constants:  dy = A*g - B - Cc*y,  A = gamma*invstd, Cc = A*invstd*m2, B = A*m1 - Cc*mean, m1 = S1/M,
+// m2 = invstd*(S2 - mean*S1)/M.  Few per-thread constants = few registers = enough resident warps to hide HBM latency.
 template <int CH, bool POOL>
 struct BnBwdPix {
   float yv[POOL ? 4 : 1][CH];
@@ -679,7 +683,7 @@ struct BnBwdPix {
   unsigned sel;         // pooled: 2 bits per channel, which of the 4 window positions receives g
 
   __device__ __forceinline__ void load(const dn_view& y, const dn_view& res, int has_res, const dn_view& dout, int n, int h,
-                                       int w, int c0, const float* __restrict__ sc, const float* __restrict__ sh, int act) {
+                                       int w, int c0, const float* sc, const float* sh, int act) {
     ldc<CH>(dout, dn_off(dout, n, h, w) + c0, g);
     sel = 0;
     if (POOL) {
@@ -724,37 +728,29 @@ struct BnBwdPix {
 };
 
 template <int CH, bool POOL>
-__global__ void __launch_bounds__(256, 2) bn_bwd_reduce_kernel(dn_view dout, dn_view y, dn_view res, int has_res,
-                                                               const float* __restrict__ mean_invstd, const float* __restrict__ gamma,
-                                                               const float* __restrict__ beta, int act, float* __restrict__ ws, int CGb) {
-  extern __shared__ float cst[];
+__global__ void __launch_bounds__(256, POOL ? 2 : 3) bn_bwd_reduce_kernel(dn_view dout, dn_view y, dn_view res, int has_res,
+                                                            const float* __restrict__ mean_invstd, const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, int act, float* __restrict__ ws, int CGb) {
   CG_PROLOGUE(dout)
   const int C = dout.C;
-  const int Cs = C + CH;    // padded stride so that a tail channel group can read past C
-  for (int c = threadIdx.x; c < 4 * Cs; c += blockDim.x) cst[c] = 0.f;
-  __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float mean = mean_invstd[c], istd = mean_invstd[C + c], sc, sh;
-    bn_scale_shift(gamma ? gamma[c] : 1.f, beta ? beta[c] : 0.f, mean, istd, sc, sh);
-    cst[c] = sc; cst[Cs + c] = sh; cst[2 * Cs + c] = mean; cst[3 * Cs + c] = istd;
-  }
-  __syncthreads();
   float acc[2 * CH];
 #pragma unroll
   for (int i = 0; i < 2 * CH; ++i) acc[i] = 0.f;
   if (cvalid) {
-    const float* sc = cst + c0;
-    const float* sh = cst + Cs + c0;
-    const float* mean = cst + 2 * Cs + c0;
-    const float* istd = cst + 3 * Cs + c0;
-    if (!POOL && !has_res) {
-      // un-pooled, no residual: 4 pixels per iteration with all 8 loads issued up front (HBM latency hiding)
-      const unsigned stride = gridDim.x * PLn;
-      for (unsigned px0 = blockIdx.x * PLn + pl; px0 < (unsigned)npix; px0 += 4 * stride) {
-        float gg[4][CH], yy[4][CH];
-        bool ok[4];
+    float sc[CH], sh[CH];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+    for (int i = 0; i < CH; ++i) {
+      int c = c0 + i < C ? c0 + i : C - 1;
+      bn_scale_shift(gamma ? gamma[c] : 1.f, beta ? beta[c] : 0.f, mean_invstd[c], mean_invstd[C + c], sc[i], sh[i]);
+    }
+    if (!POOL && !has_res) {
+      // 2 pixels per iteration, loads issued up front
+      const unsigned stride = gridDim.x * PLn;
+      for (unsigned px0 = blockIdx.x * PLn + pl; px0 < (unsigned)npix; px0 += 2 * stride) {
+        float gg[2][CH], yy[2][CH];
+        bool ok[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
           const unsigned px = px0 + u * stride;
           ok[u] = px < (unsigned)npix;
           const unsigned pc = ok[u] ? px : px0;
@@ -766,13 +762,13 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_reduce_kernel(dn_view dout, dn_
           ldc<CH>(y, dn_off(y, n, h, w) + c0, yy[u]);
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
+        for (int u = 0; u < 2; ++u)
           if (ok[u]) {
 #pragma unroll
             for (int i = 0; i < CH; ++i) {
               const float g = gg[u][i] * dn_act_grad(dn_act(fmaf(yy[u][i], sc[i], sh[i]), act), act);
               acc[i] += g;
-              acc[CH + i] = fmaf(g, (yy[u][i] - mean[i]) * istd[i], acc[CH + i]);
+              acc[CH + i] = fmaf(g, yy[u][i], acc[CH + i]);
             }
           }
       }
@@ -787,7 +783,7 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_reduce_kernel(dn_view dout, dn_
 #pragma unroll
         for (int i = 0; i < CH; ++i) {
           acc[i] += P.g[i];
-          acc[CH + i] = fmaf(P.g[i], (P.ysel(i) - mean[i]) * istd[i], acc[CH + i]);
+          acc[CH + i] = fmaf(P.g[i], P.ysel(i), acc[CH + i]);
         }
       }
     }
@@ -814,20 +810,10 @@ DN_EXPORT int dn_bn_bwd_reduce(const dn_view* dout, const dn_view* y, const dn_v
   const int ch = vec ? 8 : 1;
   CgGeom g = cg_geom(dout->C, ch, npix);
   const int hr = residual != nullptr;
-  const size_t sm = sizeof(float) * 4 * (dout->C + ch);
-  if (sm > 200 * 1024) return DN_E_UNSUPPORTED;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaFuncSetAttribute(bn_bwd_reduce_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(bn_bwd_reduce_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(bn_bwd_reduce_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(bn_bwd_reduce_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr_done = true;
-  }
-  if (vec && pool) bn_bwd_reduce_kernel<8, true><<<g.grid, 256, sm, st>>>(*dout, *y, r, hr, mean_invstd, gamma, beta, act, ws, g.CGb);
-  else if (vec) bn_bwd_reduce_kernel<8, false><<<g.grid, 256, sm, st>>>(*dout, *y, r, hr, mean_invstd, gamma, beta, act, ws, g.CGb);
-  else if (pool) bn_bwd_reduce_kernel<1, true><<<g.grid, 256, sm, st>>>(*dout, *y, r, hr, mean_invstd, gamma, beta, act, ws, g.CGb);
-  else bn_bwd_reduce_kernel<1, false><<<g.grid, 256, sm, st>>>(*dout, *y, r, hr, mean_invstd, gamma, beta, act, ws, g.CGb);
+  if (vec && pool) bn_bwd_reduce_kernel<8, true><<<g.grid, 256, 0, st>>>(*dout, *y, r, hr, mean_invstd, gamma, beta, act, ws, g.CGb);
+  else if (vec) bn_bwd_reduce_kernel<8, false><<<g.grid, 256, 0, st>>>(*dout, *y, r, hr, mean_invstd, gamma, beta, act, ws, g.CGb);
+  else if (pool) bn_bwd_reduce_kernel<1, true><<<g.grid, 256, 0, st>>>(*dout, *y, r, hr, mean_invstd, gamma, beta, act, ws, g.CGb);
+  else bn_bwd_reduce_kernel<1, false><<<g.grid, 256, 0, st>>>(*dout, *y, r, hr, mean_invstd, gamma, beta, act, ws, g.CGb);
   DN_CHECK_LAUNCH();
   reduce_partials_kernel<double><<<reduce_blocks(2 * dout->C), 1024, 0, st>>>(ws, g.grid.x, 2 * dout->C, red, 1.0);
   DN_CHECK_LAUNCH();
@@ -835,45 +821,39 @@ DN_EXPORT int dn_bn_bwd_reduce(const dn_view* dout, const dn_view* y, const dn_v
 }
 
 template <int CH, bool POOL>
-__global__ void __launch_bounds__(256, 2) bn_bwd_apply_kernel(dn_view dout, dn_view y, dn_view res, int has_res,
-                                                              const float* __restrict__ mean_invstd, const float* __restrict__ gamma,
-                                                              const float* __restrict__ beta, int act,
-                                                              const double* __restrict__ red, double count, float gscale,
-                                                              float* dgamma, float* dbeta, dn_view dy, dn_view dres, int has_dres,
-                                                              int dres_acc, int CGb) {
-  extern __shared__ float cst[];
+__global__ void __launch_bounds__(256, POOL ? 2 : 3) bn_bwd_apply_kernel(dn_view dout, dn_view y, dn_view res, int has_res,
+                                                           const float* __restrict__ mean_invstd, const float* __restrict__ gamma,
+                                                           const float* __restrict__ beta, int act,
+                                                           const double* __restrict__ red, double count, float gscale,
+                                                           float* dgamma, float* dbeta, dn_view dy, dn_view dres, int has_dres,
+                                                           int dres_acc, int CGb) {
   CG_PROLOGUE(dout)
   const int C = dout.C;
-  const int Cs = C + CH;
-  for (int c = threadIdx.x; c < 6 * Cs; c += blockDim.x) cst[c] = 0.f;
-  __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float mean = mean_invstd[c], istd = mean_invstd[C + c], sc, sh;
-    bn_scale_shift(gamma ? gamma[c] : 1.f, beta ? beta[c] : 0.f, mean, istd, sc, sh);
-    cst[c] = sc; cst[Cs + c] = sh; cst[2 * Cs + c] = mean; cst[3 * Cs + c] = istd;
-    cst[4 * Cs + c] = (float)(red[c] / count);
-    cst[5 * Cs + c] = (float)(red[C + c] / count);
-    if (blockIdx.x == 0 && blockIdx.y == 0) {
-      if (dgamma) dgamma[c] = (float)(red[C + c] * (double)gscale);
-      if (dbeta) dbeta[c] = (float)(red[c] * (double)gscale);
+  if (!cvalid) return;
+  float sc[CH], sh[CH], cB[CH], cC[CH];      // A == sc
+#pragma unroll
+  for (int i = 0; i < CH; ++i) {
+    int c = c0 + i < C ? c0 + i : C - 1;
+    const float mean = mean_invstd[c], istd = mean_invstd[C + c];
+    bn_scale_shift(gamma ? gamma[c] : 1.f, beta ? beta[c] : 0.f, mean, istd, sc[i], sh[i]);
+    const double s1 = red[c], s2 = red[C + c];
+    const double sgx = (double)istd * (s2 - (double)mean * s1);      // sum g * xhat
+    const float m1 = (float)(s1 / count), m2 = (float)(sgx / count);
+    cC[i] = sc[i] * istd * m2;
+    cB[i] = sc[i] * m1 - cC[i] * mean;
+    if (blockIdx.x == 0 && pl == 0 && c0 + i < C) {
+      if (dgamma) dgamma[c] = (float)(sgx * (double)gscale);
+      if (dbeta) dbeta[c] = (float)(s1 * (double)gscale);
     }
   }
-  __syncthreads();
-  if (!cvalid) return;
-  const float* sc = cst + c0;
-  const float* sh = cst + Cs + c0;
-  const float* mean = cst + 2 * Cs + c0;
-  const float* istd = cst + 3 * Cs + c0;
-  const float* m1 = cst + 4 * Cs + c0;
-  const float* m2 = cst + 5 * Cs + c0;
   if (!POOL && !has_res && !has_dres) {
     const unsigned stride = gridDim.x * PLn;
-    for (unsigned px0 = blockIdx.x * PLn + pl; px0 < (unsigned)npix; px0 += 4 * stride) {
-      float gg[4][CH], yy[4][CH];
-      long long offo[4];
-      bool ok[4];
+    for (unsigned px0 = blockIdx.x * PLn + pl; px0 < (unsigned)npix; px0 += 2 * stride) {
+      float gg[2][CH], yy[2][CH];
+      long long offo[2];
+      bool ok[2];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < 2; ++u) {
         const unsigned px = px0 + u * stride;
         ok[u] = px < (unsigned)npix;
         const unsigned pc = ok[u] ? px : px0;
@@ -886,14 +866,13 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_apply_kernel(dn_view dout, dn_v
         offo[u] = dn_off(dy, n, h, w) + c0;
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
+      for (int u = 0; u < 2; ++u)
         if (ok[u]) {
           float o[CH];
 #pragma unroll
           for (int i = 0; i < CH; ++i) {
             const float g = gg[u][i] * dn_act_grad(dn_act(fmaf(yy[u][i], sc[i], sh[i]), act), act);
-            const float xh = (yy[u][i] - mean[i]) * istd[i];
-            o[i] = sc[i] * (g - m1[i] - xh * m2[i]);
+            o[i] = fmaf(sc[i], g, -fmaf(cC[i], yy[u][i], cB[i]));
           }
           stc<CH>(dy, offo[u], o);
         }
@@ -911,10 +890,7 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_apply_kernel(dn_view dout, dn_v
     for (int k = 0; k < (POOL ? 4 : 1); ++k) {
       float o[CH];
 #pragma unroll
-      for (int i = 0; i < CH; ++i) {
-        float xh = (P.yv[POOL ? k : 0][i] - mean[i]) * istd[i];
-        o[i] = sc[i] * (P.dyhat(k, i) - m1[i] - xh * m2[i]);
-      }
+      for (int i = 0; i < CH; ++i) o[i] = fmaf(sc[i], P.dyhat(k, i), -fmaf(cC[i], P.yv[POOL ? k : 0][i], cB[i]));
       int hh = POOL ? 2 * h + (k >> 1) : h, ww = POOL ? 2 * w + (k & 1) : w;
       stc<CH>(dy, dn_off(dy, n, hh, ww) + c0, o);
     }
@@ -942,19 +918,9 @@ DN_EXPORT int dn_bn_bwd_apply(const dn_view* dout, const dn_view* y, const dn_vi
   const int ch = vec ? 8 : 1;
   CgGeom g = cg_geom(dout->C, ch, npix);
   const int hr = residual != nullptr, hd = dres != nullptr;
-  const size_t sm = sizeof(float) * 6 * (dout->C + ch);
-  if (sm > 200 * 1024) return DN_E_UNSUPPORTED;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaFuncSetAttribute(bn_bwd_apply_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(bn_bwd_apply_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(bn_bwd_apply_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(bn_bwd_apply_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr_done = true;
-  }
-#define BN_BWD_APPLY(CHV, PV)                                                                                               \
-  bn_bwd_apply_kernel<CHV, PV><<<g.grid, 256, sm, st>>>(*dout, *y, r, hr, mean_invstd, gamma, beta, act, red, count, gscale, \
-                                                        dgamma, dbeta, *dy, dr, hd, dres_accumulate, g.CGb)
+#define BN_BWD_APPLY(CHV, PV)                                                                                              \
+  bn_bwd_apply_kernel<CHV, PV><<<g.grid, 256, 0, st>>>(*dout, *y, r, hr, mean_invstd, gamma, beta, act, red, count, gscale, \
+                                                       dgamma, dbeta, *dy, dr, hd, dres_accumulate, g.CGb)
   if (vec && pool) BN_BWD_APPLY(8, true);
   else if (vec) BN_BWD_APPLY(8, false);
   else if (pool) BN_BWD_APPLY(1, true);
