@@ -244,6 +244,19 @@ int dn_inverse_warp_bwd(const float* img, const float* depth, const float* pose,
 int dn_explain_fwd(const float* mask, int64_t n, float* loss, void* stream);
 int dn_explain_bwd(const float* mask, int64_t n, const float* gout, float* gmask, void* stream);
 
+/* ---- monodepth2-style optional terms (reference layers.py:199-266; named by the north star, uncalled in the reference) */
+/* layers.SSIM.forward(x, y) (:231-245): reflection pad 1, 3x3 average pools, clamp((1-SSIM)/2, 0, 1); x, y, out fp32 [NC,h,w] */
+int dn_ssim_fwd(const float* x, const float* y, int NC, int h, int w, float* out, void* stream);
+int dn_ssim_bwd(const float* x, const float* y, const float* gout, int NC, int h, int w, float* gx /* or NULL */,
+                float* gy /* or NULL */, void* stream);
+/* layers.get_smooth_loss(disp, img) (:199-212): loss[0] += mean|dx disp| e^{-mean_c|dx img|} + same in y; disp [B,1,h,w] */
+int dn_edge_smooth_fwd(const float* disp, const float* img, int B, int C, int h, int w, float* loss, void* stream);
+int dn_edge_smooth_bwd(const float* disp, const float* img, int B, int C, int h, int w, const float* gout, float* gdisp,
+                       void* stream);
+/* layers.compute_depth_errors(gt, pred) (:248-266) on pre-masked 1-D tensors: counters[3] (n<1.25^k), sums[4] double =
+ * sum|d|/gt, sum d^2/gt, sum d^2, sum (ln gt - ln p)^2; caller zeroes both. */
+int dn_depth_errors_raw(const float* gt, const float* pred, int64_t n, int32_t* counters, double* sums, void* stream);
+
 /* ---- misc ---------------------------------------------------------------------------------- */
 int dn_fill_f32(float* p, int64_t n, float v, void* stream);
 int dn_axpy_f32(const float* x, float a, float* y, int64_t n, void* stream); /* y += a*x */

@@ -12,5 +12,6 @@ from . import engine  # noqa: F401
 from . import models  # noqa: F401
 from . import loss_functions  # noqa: F401
 from . import inverse_warp  # noqa: F401
+from . import layers  # noqa: F401
 
 __version__ = '0.1.0'

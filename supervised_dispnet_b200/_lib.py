@@ -96,6 +96,11 @@ _SIGS = {
     'dn_inverse_warp_bwd': ([_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P], _I),
     'dn_explain_fwd': ([_P, _I64, _P, _P], _I),
     'dn_explain_bwd': ([_P, _I64, _P, _P, _P], _I),
+    'dn_ssim_fwd': ([_P, _P, _I, _I, _I, _P, _P], _I),
+    'dn_ssim_bwd': ([_P, _P, _P, _I, _I, _I, _P, _P, _P], _I),
+    'dn_edge_smooth_fwd': ([_P, _P, _I, _I, _I, _I, _P, _P], _I),
+    'dn_edge_smooth_bwd': ([_P, _P, _I, _I, _I, _I, _P, _P, _P], _I),
+    'dn_depth_errors_raw': ([_P, _P, _I64, _P, _P, _P], _I),
     'dn_fill_f32': ([_P, _I64, _F, _P], _I),
     'dn_axpy_f32': ([_P, _F, _P, _I64, _P], _I),
 }

@@ -729,3 +729,198 @@ DN_EXPORT int dn_inverse_warp_bwd(const float* img, const float* depth, const fl
   }
   return 0;
 }
+
+// =================================================================================================
+// monodepth2-style optional terms named by the north star (reference layers.py:199-266, uncalled there)
+// =================================================================================================
+namespace {
+
+__device__ __forceinline__ int refl_idx(int k, int n) { return k < 0 ? -k : (k >= n ? 2 * (n - 1) - k : k); }
+
+struct SsimStats { float mx, my, ex2, ey2, exy; };
+
+__device__ __forceinline__ SsimStats ssim_stats(const float* __restrict__ x, const float* __restrict__ y, int h, int w, int i, int j) {
+  SsimStats s = {0, 0, 0, 0, 0};
+#pragma unroll
+  for (int a = -1; a <= 1; ++a) {
+    const int ii = refl_idx(i + a, h);
+#pragma unroll
+    for (int b = -1; b <= 1; ++b) {
+      const int jj = refl_idx(j + b, w);
+      const float xv = x[ii * w + jj], yv = y[ii * w + jj];
+      s.mx += xv; s.my += yv; s.ex2 += xv * xv; s.ey2 += yv * yv; s.exy += xv * yv;
+    }
+  }
+  const float k = 1.f / 9.f;
+  s.mx *= k; s.my *= k; s.ex2 *= k; s.ey2 *= k; s.exy *= k;
+  return s;
+}
+
+constexpr float kC1 = 0.01f * 0.01f, kC2 = 0.03f * 0.03f;
+
+__device__ __forceinline__ float ssim_value(const SsimStats& s, float& n, float& d) {
+  const float sx = s.ex2 - s.mx * s.mx, sy = s.ey2 - s.my * s.my, sxy = s.exy - s.mx * s.my;
+  n = (2.f * s.mx * s.my + kC1) * (2.f * sxy + kC2);
+  d = (s.mx * s.mx + s.my * s.my + kC1) * (sx + sy + kC2);
+  return (1.f - n / d) * 0.5f;
+}
+
+__global__ void ssim_fwd_kernel(const float* __restrict__ x, const float* __restrict__ y, int h, int w, float* __restrict__ out) {
+  const long long plane = (long long)blockIdx.y * h * w;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < h * w; i += gridDim.x * blockDim.x) {
+    float n, d;
+    const float v = ssim_value(ssim_stats(x + plane, y + plane, h, w, i / w, i % w), n, d);
+    out[plane + i] = fminf(fmaxf(v, 0.f), 1.f);
+  }
+}
+
+// gradient of sum(gout * ssim) w.r.t. x and y: gather over the (up to 5x5) outputs whose reflected window holds the pixel
+__global__ void ssim_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ gout, int h, int w,
+                                float* __restrict__ gx, float* __restrict__ gy) {
+  const long long plane = (long long)blockIdx.y * h * w;
+  const float* xp = x + plane;
+  const float* yp = y + plane;
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < h * w; p += gridDim.x * blockDim.x) {
+    const int i = p / w, j = p % w;
+    const float xv = xp[p], yv = yp[p];
+    float ax = 0.f, ay = 0.f;
+    for (int oi = i - 2; oi <= i + 2; ++oi) {
+      if (oi < 0 || oi >= h) continue;
+      int mi = 0;
+      for (int a = -1; a <= 1; ++a) mi += refl_idx(oi + a, h) == i;
+      if (!mi) continue;
+      for (int oj = j - 2; oj <= j + 2; ++oj) {
+        if (oj < 0 || oj >= w) continue;
+        int mj = 0;
+        for (int b = -1; b <= 1; ++b) mj += refl_idx(oj + b, w) == j;
+        if (!mj) continue;
+        const SsimStats s = ssim_stats(xp, yp, h, w, oi, oj);
+        float n, d;
+        const float v = ssim_value(s, n, d);
+        if (v < 0.f || v > 1.f) continue;                       // clamp: no gradient outside [0, 1]
+        const float go = gout[plane + oi * w + oj] * (-0.5f) * (float)(mi * mj) * (1.f / 9.f);
+        // n = N1*N2, d = D1*D2 with N1 = 2 mx my + C1, N2 = 2 sxy + C2, D1 = mx^2 + my^2 + C1, D2 = sx + sy + C2
+        const float sx = s.ex2 - s.mx * s.mx, sy = s.ey2 - s.my * s.my, sxy = s.exy - s.mx * s.my;
+        const float N1 = 2.f * s.mx * s.my + kC1, N2 = 2.f * sxy + kC2, D1 = s.mx * s.mx + s.my * s.my + kC1, D2 = sx + sy + kC2;
+        const float inv_d = 1.f / d, q = n * inv_d * inv_d;
+        // d(n/d)/d(window element x_p) = [dn - (n/d) dd] / d, chain through mx, E[x^2], E[xy] (each has weight 1/9 per occurrence)
+        // dmx = 1, dsx = 2 x_p - 2 mx, dsxy = y_p - my
+        const float dn_x = 2.f * s.my * N2 + N1 * 2.f * (yv - s.my);
+        const float dd_x = 2.f * s.mx * D2 + D1 * (2.f * xv - 2.f * s.mx);
+        const float dn_y = 2.f * s.mx * N2 + N1 * 2.f * (xv - s.mx);
+        const float dd_y = 2.f * s.my * D2 + D1 * (2.f * yv - 2.f * s.my);
+        ax += go * (dn_x * inv_d - q * dd_x);
+        ay += go * (dn_y * inv_d - q * dd_y);
+      }
+    }
+    if (gx) gx[plane + p] = ax;
+    if (gy) gy[plane + p] = ay;
+  }
+}
+
+__global__ void __launch_bounds__(256) edge_smooth_fwd_kernel(const float* __restrict__ disp, const float* __restrict__ img, int C, int h,
+                                                              int w, float cx, float cy, float* loss) {
+  const int b = blockIdx.y;
+  const float* d = disp + (long long)b * h * w;
+  const float* im = img + (long long)b * C * h * w;
+  float s = 0.f;
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < h * w; p += gridDim.x * blockDim.x) {
+    const int i = p / w, j = p % w;
+    if (j < w - 1) {
+      float gi = 0.f;
+      for (int c = 0; c < C; ++c) gi += fabsf(im[(long long)c * h * w + p] - im[(long long)c * h * w + p + 1]);
+      s += cx * fabsf(d[p] - d[p + 1]) * expf(-gi / (float)C);
+    }
+    if (i < h - 1) {
+      float gi = 0.f;
+      for (int c = 0; c < C; ++c) gi += fabsf(im[(long long)c * h * w + p] - im[(long long)c * h * w + p + w]);
+      s += cy * fabsf(d[p] - d[p + w]) * expf(-gi / (float)C);
+    }
+  }
+  s = block_sum(s);
+  if (threadIdx.x == 0) atomicAdd(loss, s);
+}
+
+__global__ void __launch_bounds__(256) edge_smooth_bwd_kernel(const float* __restrict__ disp, const float* __restrict__ img, int C, int h,
+                                                              int w, float cx, float cy, const float* __restrict__ gout,
+                                                              float* __restrict__ gdisp) {
+  const int b = blockIdx.y;
+  const float* d = disp + (long long)b * h * w;
+  const float* im = img + (long long)b * C * h * w;
+  const float go = gout[0];
+  auto wx = [&](int p) {   // weight of the pair (p, p+1)
+    float gi = 0.f;
+    for (int c = 0; c < C; ++c) gi += fabsf(im[(long long)c * h * w + p] - im[(long long)c * h * w + p + 1]);
+    return cx * expf(-gi / (float)C) * sgn(d[p] - d[p + 1]);
+  };
+  auto wy = [&](int p) {   // weight of the pair (p, p+w)
+    float gi = 0.f;
+    for (int c = 0; c < C; ++c) gi += fabsf(im[(long long)c * h * w + p] - im[(long long)c * h * w + p + w]);
+    return cy * expf(-gi / (float)C) * sgn(d[p] - d[p + w]);
+  };
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < h * w; p += gridDim.x * blockDim.x) {
+    const int i = p / w, j = p % w;
+    float g = 0.f;
+    if (j < w - 1) g += wx(p);
+    if (j > 0) g -= wx(p - 1);
+    if (i < h - 1) g += wy(p);
+    if (i > 0) g -= wy(p - w);
+    gdisp[(long long)b * h * w + p] = g * go;
+  }
+}
+
+__global__ void __launch_bounds__(256) depth_errors_raw_kernel(const float* __restrict__ gt, const float* __restrict__ pred, long long n,
+                                                               int32_t* counters, double* sums) {
+  int a1 = 0, a2 = 0, a3 = 0;
+  double s1 = 0, s2 = 0, s3 = 0, s4 = 0;
+  const float t1 = 1.25f, t2 = (float)(1.25 * 1.25), t3 = (float)(1.25 * 1.25 * 1.25);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float g = gt[i], p = pred[i];
+    const float th = fmaxf(g / p, p / g);
+    a1 += th < t1; a2 += th < t2; a3 += th < t3;
+    const float d = g - p, lg = logf(g) - logf(p);
+    s1 += (double)(fabsf(d) / g); s2 += (double)(d * d / g); s3 += (double)(d * d); s4 += (double)(lg * lg);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    a1 += __shfl_xor_sync(0xffffffffu, a1, o); a2 += __shfl_xor_sync(0xffffffffu, a2, o); a3 += __shfl_xor_sync(0xffffffffu, a3, o);
+  }
+  if ((threadIdx.x & 31) == 0) { atomicAdd(counters, a1); atomicAdd(counters + 1, a2); atomicAdd(counters + 2, a3); }
+  s1 = block_sum_d(s1); s2 = block_sum_d(s2); s3 = block_sum_d(s3); s4 = block_sum_d(s4);
+  if (threadIdx.x == 0) { atomicAdd(sums, s1); atomicAdd(sums + 1, s2); atomicAdd(sums + 2, s3); atomicAdd(sums + 3, s4); }
+}
+
+}  // namespace
+
+DN_EXPORT int dn_ssim_fwd(const float* x, const float* y, int NC, int h, int w, float* out, void* stream) {
+  if (!x || !y || !out || h < 2 || w < 2) return DN_E_ARG;
+  ssim_fwd_kernel<<<dim3(grid_bx(h * w, NC), NC), 256, 0, dn_stream(stream)>>>(x, y, h, w, out);
+  DN_CHECK_LAUNCH();
+  return 0;
+}
+DN_EXPORT int dn_ssim_bwd(const float* x, const float* y, const float* gout, int NC, int h, int w, float* gx, float* gy, void* stream) {
+  if (!x || !y || !gout || h < 2 || w < 2) return DN_E_ARG;
+  ssim_bwd_kernel<<<dim3(grid_bx(h * w, NC), NC), 256, 0, dn_stream(stream)>>>(x, y, gout, h, w, gx, gy);
+  DN_CHECK_LAUNCH();
+  return 0;
+}
+DN_EXPORT int dn_edge_smooth_fwd(const float* disp, const float* img, int B, int C, int h, int w, float* loss, void* stream) {
+  if (!disp || !img || !loss || h < 2 || w < 2) return DN_E_ARG;
+  const float cx = 1.f / ((float)B * h * (w - 1)), cy = 1.f / ((float)B * (h - 1) * w);
+  edge_smooth_fwd_kernel<<<dim3(grid_bx(h * w, B), B), 256, 0, dn_stream(stream)>>>(disp, img, C, h, w, cx, cy, loss);
+  DN_CHECK_LAUNCH();
+  return 0;
+}
+DN_EXPORT int dn_edge_smooth_bwd(const float* disp, const float* img, int B, int C, int h, int w, const float* gout, float* gdisp,
+                                 void* stream) {
+  if (!disp || !img || !gout || !gdisp) return DN_E_ARG;
+  const float cx = 1.f / ((float)B * h * (w - 1)), cy = 1.f / ((float)B * (h - 1) * w);
+  edge_smooth_bwd_kernel<<<dim3(grid_bx(h * w, B), B), 256, 0, dn_stream(stream)>>>(disp, img, C, h, w, cx, cy, gout, gdisp);
+  DN_CHECK_LAUNCH();
+  return 0;
+}
+DN_EXPORT int dn_depth_errors_raw(const float* gt, const float* pred, int64_t n, int32_t* counters, double* sums, void* stream) {
+  if (!gt || !pred || !counters || !sums || n < 1) return DN_E_ARG;
+  depth_errors_raw_kernel<<<blocks_for(n, 1024), 256, 0, dn_stream(stream)>>>(gt, pred, n, counters, sums);
+  DN_CHECK_LAUNCH();
+  return 0;
+}

@@ -145,7 +145,7 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_b
   return d;
 }
 
-constexpr int kMaxTcTaps = 16;
+constexpr int kMaxTcTaps = DN_MAX_TAPS;
 constexpr int kRows = 128;          // pixels per tile = UMMA M
 constexpr int kChunk = 64;          // channels per K chunk = one 128-byte swizzled row
 

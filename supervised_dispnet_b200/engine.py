@@ -254,7 +254,14 @@ class ConvOp(Op):
             self.s_co, self.s_ci = self.Cin * T, T
         # ---- forward problems
         self.fwd_probs = []
-        if not transposed:
+        if not transposed and stride == 2 and x.H % 2 == 0 and x.W % 2 == 0:
+            # input pixel (2*ho + dh, 2*wo + dw) lives in phase (dh & 1, dw & 1) of x at (ho + (dh >> 1), wo + (dw >> 1)):
+            # a strided convolution is a stride-1 gather over the four 2x2 phase views (which the tcgen05 kernel serves)
+            ins = [x.phase(a, b) for a in range(2) for b in range(2)]
+            taps = [(((kh - self.pad) & 1) * 2 + ((kw - self.pad) & 1), (kh - self.pad) >> 1, (kw - self.pad) >> 1, kh * k + kw)
+                    for kh in range(k) for kw in range(k)]
+            self.fwd_probs.append(dict(ins=ins, out=out, taps=taps, stride=1))
+        elif not transposed:
             taps = [(0, kh - self.pad, kw - self.pad, kh * k + kw) for kh in range(k) for kw in range(k)]
             self.fwd_probs.append(dict(ins=[x], out=out, taps=taps, stride=stride))
         else:
@@ -319,7 +326,15 @@ class ConvOp(Op):
         # ---- weight-gradient problems
         def wg_probs(q):
             probs = []
-            if not self.transposed:
+            if not self.transposed and self.stride == 2 and q.H % 2 == 0 and q.W % 2 == 0:
+                for a in range(2):          # one problem per input phase (see the forward tables)
+                    for b in range(2):
+                        taps = [(0, (kh - pad) >> 1, (kw - pad) >> 1, kh * k + kw) for kh in range(k) for kw in range(k)
+                                if ((kh - pad) & 1) == a and ((kw - pad) & 1) == b]
+                        if taps:
+                            probs.append(_mk_wgrad([self.gout], q.phase(a, b), self.dwp, self.cout_pad, self.cin_pad, 1, taps,
+                                                   1.0))
+            elif not self.transposed:
                 taps = [(0, kh - pad, kw - pad, kh * k + kw) for kh in range(k) for kw in range(k)]
                 probs.append(_mk_wgrad([self.gout], q, self.dwp, self.cout_pad, self.cin_pad, self.stride, taps, 1.0))
             else:

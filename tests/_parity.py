@@ -125,7 +125,42 @@ def explain_case(B=2, R=2, H=32, W=48, seed=0):
     return dict(loss=abs(float(lp) - float(lo)) / abs(float(lo)), grad=max(rel(a.grad, b.grad) for a, b in zip(mp, mo)))
 
 
+def ssim_case(B=2, H=32, W=48, seed=0):
+    from supervised_dispnet_b200 import layers as LY
+    x = I.images(B, H, W, seed) * 0.5 + 0.5
+    y = I.images(B, H, W, seed + 1) * 0.5 + 0.5
+    xo, yo, xp, yp = _leaf(x), _leaf(y), _leaf(x.to(DEV)), _leaf(y.to(DEV))
+    so, sp = OL.ssim(xo, yo), LY.SSIM()(xp, yp)
+    probe = I.probe_like(so, seed)
+    (so * probe).sum().backward()
+    (sp * probe.to(DEV)).sum().backward()
+    return dict(fwd=rel(sp, so), gx=rel(xp.grad, xo.grad), gy=rel(yp.grad, yo.grad))
+
+
+def edge_smooth_case(B=2, H=32, W=48, seed=0):
+    from supervised_dispnet_b200 import layers as LY
+    img = I.images(B, H, W, seed) * 0.5 + 0.5
+    disp = I.depth_map(B, H, W, seed + 1).unsqueeze(1)
+    do, dp = _leaf(disp), _leaf(disp.to(DEV))
+    lo, lp = OL.get_smooth_loss(do, img), LY.get_smooth_loss(dp, img.to(DEV))
+    lo.backward()
+    lp.backward()
+    return dict(loss=abs(float(lp) - float(lo)) / abs(float(lo)), grad=rel(dp.grad, do.grad))
+
+
+def depth_errors_raw_case(seed=0):
+    from supervised_dispnet_b200 import layers as LY
+    a = I.depth_map(1, 8, 200, seed).flatten()
+    b = I.depth_map(1, 8, 200, seed + 1).flatten()
+    eo = OL.compute_depth_errors(a, b)
+    ep = LY.compute_depth_errors(a.to(DEV), b.to(DEV))
+    return dict(floats=max(abs(float(u) - float(v)) / max(abs(float(v)), 1e-12) for u, v in zip(ep, eo)))
+
+
 LOSS_CASES = [
+    ('layers_ssim', ssim_case),
+    ('layers_edge_smooth', edge_smooth_case),
+    ('layers_depth_errors', depth_errors_raw_case),
     ('l1_kitti', lambda: l1_case('kitti')),
     ('l1_nyu', lambda: l1_case('nyu', H=64, W=80)),
     ('l1_all_invalid_nan', lambda: l1_case('kitti', all_invalid=True)),

@@ -162,6 +162,21 @@ def test_golden_g7_compute_errors_counters_bit_exact(golden):
         LF.compute_errors(gt, pred, 'kitti', False)
 
 
+def test_golden_g9_layers_terms(golden):
+    """SSIM / edge-aware smoothness / compute_depth_errors (reference layers.py) against reference-generated values."""
+    from supervised_dispnet_b200 import layers as LY
+    g9 = golden('g9_layers')
+    x = (I.images(2, 32, 48, seed=130) * 0.5 + 0.5).to(DEV)
+    y = (I.images(2, 32, 48, seed=131) * 0.5 + 0.5).to(DEV)
+    assert rel(LY.SSIM()(x, y), g9['ssim']) < 1e-5
+    disp = I.depth_map(2, 32, 48, seed=132).unsqueeze(1).to(DEV)
+    assert float(LY.get_smooth_loss(disp, x)) == pytest.approx(float(g9['edge_smooth']), rel=1e-5)
+    a = I.depth_map(1, 8, 200, seed=133).flatten().to(DEV)
+    b = I.depth_map(1, 8, 200, seed=134).flatten().to(DEV)
+    for u, v in zip(LY.compute_depth_errors(a, b), g9['depth_errors']):
+        assert float(u) == pytest.approx(v, rel=1e-5)
+
+
 def test_golden_g1_dispnets_eval_config1(golden):
     """BASELINE configs[0]: DispNetS forward on 1x3x128x416 (eval), disparity vs the reference's own output."""
     import supervised_dispnet_b200 as S
@@ -226,7 +241,7 @@ def test_golden_g2_vgg_train_fp32(golden):
 # ------------------------------------------------------------------------------------------------------------
 # (b) oracle on the same seeded inputs
 # ------------------------------------------------------------------------------------------------------------
-LOSS_TOL = dict(loss=1e-5, grad=1e-4, gdepth=1e-3, gpose=1e-3, gmask=1e-3, gimg=1e-3, fwd=1e-4, floats=1e-5, ramp=1e-6, quad=1e-5,
+LOSS_TOL = dict(gx=1e-3, gy=1e-3, loss=1e-5, grad=1e-4, gdepth=1e-3, gpose=1e-3, gmask=1e-3, gimg=1e-3, fwd=1e-4, floats=1e-5, ramp=1e-6, quad=1e-5,
                 frac_bad=2e-3)
 
 

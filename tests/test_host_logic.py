@@ -71,6 +71,7 @@ def taps_of(p):
 CASES = [
     dict(cin=5, cout=4, k=3, stride=1, pad=1, transposed=False, hw=(6, 7)),
     dict(cin=3, cout=4, k=7, stride=2, pad=3, transposed=False, hw=(9, 10)),
+    dict(cin=3, cout=4, k=7, stride=2, pad=3, transposed=False, hw=(10, 12)),
     dict(cin=4, cout=3, k=5, stride=2, pad=2, transposed=False, hw=(8, 8)),
     dict(cin=4, cout=6, k=1, stride=2, pad=0, transposed=False, hw=(6, 6)),
     dict(cin=4, cout=3, k=4, stride=2, pad=1, transposed=True, out_pad=0, hw=(3, 5)),
@@ -134,7 +135,8 @@ def test_conv_problem_tables_match_torch(c):
     for p, be, fl in op.wg:
         ps = [E.View(op.gout.buf, op.gout.c0, op.gout.C, p.p[i].H, p.p[i].W, (p.p[i].ptr - op.gout.buf.t.data_ptr()) // 4 - op.gout.c0,
                      p.p[i].sH, p.p[i].sW) for i in range(p.nsrc)]
-        R += interp_wgrad(ps, xin, taps_of(p), p.stride, k * k, c['cout'], c['cin'])
+        qv = E.View(xin.buf, xin.c0, xin.C, p.q.H, p.q.W, (p.q.ptr - xin.buf.t.data_ptr()) // 4 - xin.c0, p.q.sH, p.q.sW)
+        R += interp_wgrad(ps, qv, taps_of(p), p.stride, k * k, c['cout'], c['cin'])
     if c['transposed']:
         gw = R.view(k, k, c['cout'], c['cin']).permute(3, 2, 0, 1)
     else:
