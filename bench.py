@@ -72,7 +72,7 @@ class ClockSampler(threading.Thread):
                     self.samples.append(f)
             except Exception:  # noqa: BLE001
                 pass
-            time.sleep(0.2)
+            time.sleep(0.05)
 
     def summary(self):
         if not self.samples:
@@ -287,7 +287,7 @@ def run_ours(args):
     e2e = total_imgs / (ms2 * 1e-3)
     line = dict(metric=METRIC, value=value, unit='images/sec', n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
                 ms_per_step=ms / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
-                dtype=os.environ.get('DISPNET_B200_PRECISION', 'fp16') + ' (fp32 accumulate)', data='synthetic',
+                dtype='fp16 operands, fp32 accumulate, bf16 gradient activations (DISPNET_B200_PRECISION=%s)' % os.environ.get('DISPNET_B200_PRECISION', 'mixed'), data='synthetic',
                 config=dict(workload='configs[1]: Disp_vgg_BN + L1 depth loss (+0*smooth as train.py does), synthetic KITTI '
                                      '128x416, b=32/GPU, fwd+loss+bwd+Adam', global_batch=BATCH * world,
                             parallelism='dp%d' % world,
