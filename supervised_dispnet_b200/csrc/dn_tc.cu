@@ -1151,9 +1151,22 @@ int dn_wgrad_tc(const dn_wgrad* p, cudaStream_t st) {
   int cols = P.tpc * P.n_mma;
   P.tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512;
   const int out_tiles = P.ngroups * P.cp_tiles * P.cq_tiles;
-  int splits = (2 * dn_num_sms() + out_tiles - 1) / out_tiles;
-  if (splits > P.num_ptiles) splits = P.num_ptiles;
-  if (splits < 1) splits = 1;
+  // split-K factor: about two waves of CTAs, chosen so that the last wave is as full as possible
+  int splits = 1;
+  {
+    const int sms = dn_num_sms();
+    int lo = (sms + out_tiles - 1) / out_tiles, hi = (3 * sms + out_tiles - 1) / out_tiles;
+    if (hi > P.num_ptiles) hi = P.num_ptiles;
+    if (lo > hi) lo = hi;
+    if (lo < 1) lo = 1;
+    double best = -1.0;
+    for (int sp = lo; sp <= hi; ++sp) {
+      const int items = out_tiles * sp;
+      const double eff = (double)items / ((double)((items + sms - 1) / sms) * sms);
+      const double score = eff - 0.02 * (double)sp / (double)(hi > 0 ? hi : 1);   // mild preference for fewer atomics
+      if (score > best) { best = score; splits = sp; }
+    }
+  }
   P.ptiles_per_split = (P.num_ptiles + splits - 1) / splits;
   P.splits = (P.num_ptiles + P.ptiles_per_split - 1) / P.ptiles_per_split;
   const uint32_t stage_bytes = a_bytes + (halo ? (uint32_t)(BNQ / 64) * 16 * 10 * 128 : (uint32_t)P.tpc * b_bytes);

@@ -402,10 +402,24 @@ class ConvOp(Op):
         if self.act != L.ACT_NONE or gb is not None:
             L.call('dn_act_bwd', self.gout.ref(), self.out.ref(), self.act, L.ptr(gb), inv, L.ptr(plan.reduce_ws(self.Cout)),
                    plan.stream)
-        if self.xq is not None:
-            L.call('dn_copy_view', self.x_cp.ref(), self.xq_cp.ref(), 0, plan.stream)
-        for p, be, fl in self.wg:
-            L.call('dn_wgrad_run', C.byref(p), be, plan.stream, tag=('wgrad', be, fl, self.name))
+        # the weight gradient only feeds the final unpack: it runs on the plan's side stream, concurrently with the data
+        # gradient and the (HBM-bound) BatchNorm / activation backward passes of the layers below on the main stream
+        side = plan.side_stream()
+        if side is not None:
+            ev = torch.cuda.Event()
+            ev.record()
+            side.wait_event(ev)
+            with torch.cuda.stream(side):
+                st = L.stream_ptr()
+                if self.xq is not None:
+                    L.call('dn_copy_view', self.x_cp.ref(), self.xq_cp.ref(), 0, st)
+                for p, be, fl in self.wg:
+                    L.call('dn_wgrad_run', C.byref(p), be, st, tag=('wgrad', be, fl, self.name))
+        else:
+            if self.xq is not None:
+                L.call('dn_copy_view', self.x_cp.ref(), self.xq_cp.ref(), 0, plan.stream)
+            for p, be, fl in self.wg:
+                L.call('dn_wgrad_run', C.byref(p), be, plan.stream, tag=('wgrad', be, fl, self.name))
         if self.needs_dx:
             if self.dx_zero_first is not None:
                 self.dx_zero_first.buf.t.zero_()
@@ -593,6 +607,7 @@ class Plan:
         self._scratch = None
         self._ws = None
         self._gflat = None
+        self._side = None
         self._dwp_arena, self._dwp_used = None, 0
         self._job_tables = {}
         self._fwd_graph, self._bwd_graphs, self._graph_key = None, {}, None
@@ -663,6 +678,13 @@ class Plan:
         self._params = tensors
 
     # ---- eager execution -----------------------------------------------------------------------------------------
+    def side_stream(self):
+        if os.environ.get('DISPNET_B200_SIDE_STREAM', '1') == '0' or L.PROFILE is not None:
+            return None
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        return self._side
+
     def dwp_alloc(self, numel):
         numel = _ru(numel, 64)
         out = self._dwp_arena[self._dwp_used:self._dwp_used + numel]
@@ -706,8 +728,12 @@ class Plan:
         self._gflat.zero_()
         self._dwp_arena.zero_()
         self._run_jobs('dgrad')
+        if self.side_stream() is not None:          # the side stream must see the zeroed arenas / packed weights
+            self._side.wait_stream(torch.cuda.current_stream())
         for op in reversed(self.ops):
             op.bwd(self)
+        if self._side is not None:
+            torch.cuda.current_stream().wait_stream(self._side)
         self._run_jobs('unpack')
         return self._gflat
 
