@@ -77,6 +77,9 @@ typedef struct dn_igemm {
   float out_scale;           /* result multiplied by this before bias/act (1.0 normally) */
   int32_t out_pad_ok;        /* 1: channels [out.C, roundup(out.C, 8)) of every output pixel are padding that the
                                 kernel may overwrite (lets the 16-byte vector epilogue serve odd channel counts) */
+  void* out2;                /* optional second copy of the result (same N/H/W/C and strides as `out`) ... */
+  int32_t out2_dtype;        /* ... in this 16-bit dtype: the bf16 image a later weight-gradient GEMM consumes */
+  int32_t pad_;
 } dn_igemm;
 
 /*

@@ -27,7 +27,8 @@ class DnIgemm(C.Structure):
     _fields_ = [('inp', DnView * MAX_SRC), ('nsrc', C.c_int32), ('out', DnView), ('w', C.c_void_p),
                 ('w_dtype', C.c_int32), ('cin_pad', C.c_int32), ('cout_pad', C.c_int32), ('bias', C.c_void_p),
                 ('act', C.c_int32), ('accumulate', C.c_int32), ('stride', C.c_int32), ('ntaps', C.c_int32),
-                ('taps', DnTap * MAX_TAPS), ('out_scale', C.c_float), ('out_pad_ok', C.c_int32)]
+                ('taps', DnTap * MAX_TAPS), ('out_scale', C.c_float), ('out_pad_ok', C.c_int32), ('out2', C.c_void_p),
+                ('out2_dtype', C.c_int32), ('pad_', C.c_int32)]
 
 
 class DnWgrad(C.Structure):

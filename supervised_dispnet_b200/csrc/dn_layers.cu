@@ -96,39 +96,43 @@ DN_EXPORT int dn_unpack_wgrad(const float* src, float* dst, int T, int R, int Cc
   return 0;
 }
 
+// one thread per (row, column) of the packed matrices; it walks all taps, so the fp32 side is touched in contiguous
+// k*k-float runs ([..][kh][kw] is innermost in both nn.Conv2d and nn.ConvTranspose2d weights) and every packed plane is
+// written (read) with unit stride across the warp
 __global__ void __launch_bounds__(256) pack_jobs_kernel(const dn_pack_job* __restrict__ jobs) {
   const dn_pack_job j = jobs[blockIdx.y];
   const unsigned k = (unsigned)j.k;
   if (!j.unpack) {
     const float* src = (const float*)j.src;
-    const unsigned total = (unsigned)j.T * j.R_pad * j.C_pad;
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-      const unsigned q = i / (unsigned)j.C_pad;
-      const int c = (int)(i - q * (unsigned)j.C_pad);
-      const unsigned t = q / (unsigned)j.R_pad;
-      const int r = (int)(q - t * (unsigned)j.R_pad);
-      float v = 0.f;
-      if (r < j.R && c < j.Cc) v = src[r * j.s_r + c * j.s_c + (long long)(t / k) * j.s_kh + (long long)(t % k) * j.s_kw];
-      dn_st(j.dst, j.dst_dtype, i, v);
+    const unsigned plane = (unsigned)j.R_pad * j.C_pad;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < plane; i += gridDim.x * blockDim.x) {
+      const unsigned r = i / (unsigned)j.C_pad;
+      const unsigned c = i - r * (unsigned)j.C_pad;
+      const bool in = (int)r < j.R && (int)c < j.Cc;
+      const float* sp = src + r * j.s_r + c * j.s_c;
+      for (unsigned t = 0; t < (unsigned)j.T; ++t) {
+        const float v = in ? sp[(long long)(t / k) * j.s_kh + (long long)(t % k) * j.s_kw] : 0.f;
+        dn_st(j.dst, j.dst_dtype, (long long)t * plane + i, v);
+      }
     }
   } else {
     const float* src = (const float*)j.src;
     float* dst = (float*)j.dst;
-    const unsigned total = (unsigned)j.T * j.R * j.Cc;
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-      const unsigned q = i / (unsigned)j.Cc;
-      const int c = (int)(i - q * (unsigned)j.Cc);
-      const unsigned t = q / (unsigned)j.R;
-      const int r = (int)(q - t * (unsigned)j.R);
-      dst[r * j.s_r + c * j.s_c + (long long)(t / k) * j.s_kh + (long long)(t % k) * j.s_kw] =
-          j.scale * src[((long long)t * j.R_pad + r) * j.C_pad + c];
+    const unsigned plane = (unsigned)j.R * j.Cc;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < plane; i += gridDim.x * blockDim.x) {
+      const unsigned r = i / (unsigned)j.Cc;
+      const unsigned c = i - r * (unsigned)j.Cc;
+      float* dp = dst + r * j.s_r + c * j.s_c;
+      const float* sp = src + (long long)r * j.C_pad + c;
+      for (unsigned t = 0; t < (unsigned)j.T; ++t)
+        dp[(long long)(t / k) * j.s_kh + (long long)(t % k) * j.s_kw] = j.scale * sp[(long long)t * j.R_pad * j.C_pad];
     }
   }
 }
 
 DN_EXPORT int dn_pack_jobs(const dn_pack_job* jobs, int njobs, void* stream) {
   if (!jobs || njobs < 1) return DN_E_ARG;
-  pack_jobs_kernel<<<dim3(296, njobs), 256, 0, dn_stream(stream)>>>(jobs);
+  pack_jobs_kernel<<<dim3(64, njobs), 256, 0, dn_stream(stream)>>>(jobs);
   DN_CHECK_LAUNCH();
   return 0;
 }
@@ -219,6 +223,7 @@ __global__ void __launch_bounds__(256) igemm_generic_kernel(const __grid_constan
       v = dn_act(v, p.act);
       if (p.accumulate) v += dn_ld(p.out.ptr, p.out.dtype, o + co);
       dn_st(p.out.ptr, p.out.dtype, o + co, v);
+      if (p.out2) dn_st(p.out2, p.out2_dtype, o + co, v);
     }
   }
 }

@@ -145,6 +145,19 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_b
   return d;
 }
 
+// second copy of an epilogue chunk (16 fp32 values) in another 16-bit dtype
+__device__ __forceinline__ void store_out2(void* base, int dtype, size_t elem_off, const float* v, int c_lo, int c_eff) {
+  if (dtype == DN_F16) {
+    __half* o = (__half*)base + elem_off;
+    if (c_lo < c_eff) Vec8<__half>::store(o, v);
+    if (c_lo + 8 < c_eff) Vec8<__half>::store(o + 8, v + 8);
+  } else {
+    __nv_bfloat16* o = (__nv_bfloat16*)base + elem_off;
+    if (c_lo < c_eff) Vec8<__nv_bfloat16>::store(o, v);
+    if (c_lo + 8 < c_eff) Vec8<__nv_bfloat16>::store(o + 8, v + 8);
+  }
+}
+
 constexpr int kMaxTcTaps = DN_MAX_TAPS;
 constexpr int kRows = 128;          // pixels per tile = UMMA M
 constexpr int kChunk = 64;          // channels per K chunk = one 128-byte swizzled row
@@ -165,6 +178,8 @@ struct IgemmTcParams {
   int c_eff;          // output channels the epilogue may write (out.C, or rounded up to 8 when padding may be overwritten)
   uint32_t idesc;
   dn_view out;
+  void* out2;
+  int out2_dtype;
   const float* bias;
   int act, accumulate;
   float out_scale;
@@ -326,6 +341,7 @@ __global__ void __launch_bounds__(192, 1) igemm_tc_kernel(const __grid_constant_
           float v[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = dn_act(__uint_as_float(r[j]) * p.out_scale + bs[c0 + j], p.act);
+          if (p.out2) store_out2(p.out2, p.out2_dtype, (size_t)(dn_off(p.out, n, h, w) + co0 + c0), v, co0 + c0, p.c_eff);
           if (p.out.dtype == DN_F32) {
             float* o = (float*)optr + c0;
 #pragma unroll
@@ -405,6 +421,8 @@ struct HaloParams {
   int n_mma, c_eff;
   uint32_t idesc;
   dn_view out;
+  void* out2;
+  int out2_dtype;
   const float* bias;
   int act, accumulate;
   float out_scale;
@@ -541,6 +559,7 @@ __global__ void __launch_bounds__(192, 1) igemm_halo_kernel(const __grid_constan
           float v[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = dn_act(__uint_as_float(r[j]) * p.out_scale + bs[c0 + j], p.act);
+          if (p.out2) store_out2(p.out2, p.out2_dtype, (size_t)(dn_off(p.out, n, h, w) + c0), v, c0, p.c_eff);
           if (p.out.dtype == DN_F32) {
             float* o = (float*)optr + c0;
 #pragma unroll
@@ -962,6 +981,8 @@ int dn_igemm_halo(const dn_igemm* p, const int* wt, cudaStream_t st) {
   P.c_eff = (p->out.dtype != DN_F32 && p->out_pad_ok) ? (p->out.C + 7) / 8 * 8 : p->out.C;
   P.idesc = make_idesc(p->in[0].dtype, p->w_dtype, 0, 0, 128, P.n_mma);
   P.out = p->out;
+  P.out2 = p->out2;
+  P.out2_dtype = p->out2_dtype;
   P.bias = p->bias;
   P.act = p->act;
   P.accumulate = p->accumulate;
@@ -1010,6 +1031,7 @@ DN_EXPORT int dn_igemm_tc_supported(const dn_igemm* p) {
     if (!view_tma_ok(p->out)) return 0;
     if ((p->out.C % 8) != 0 && !p->out_pad_ok) return 0;
   }
+  if (p->out2 && (p->out.dtype == DN_F32 || p->out2_dtype == DN_F32 || ((uintptr_t)p->out2 % 16) != 0 || p->accumulate)) return 0;
   if ((p->cin_pad % 64) != 0 || (p->cout_pad % 16) != 0 || ((uintptr_t)p->w % 16) != 0) return 0;
   for (int s = 0; s < p->nsrc; ++s) {
     if (!view_tma_ok(p->in[s]) || p->in[s].dtype != p->w_dtype) return 0;
@@ -1067,6 +1089,8 @@ int dn_igemm_tc(const dn_igemm* p, cudaStream_t st) {
   P.c_eff = (p->out.dtype != DN_F32 && p->out_pad_ok) ? (p->out.C + 7) / 8 * 8 : p->out.C;
   P.idesc = make_idesc(p->in[0].dtype, p->w_dtype, 0, 0, 128, P.n_mma);
   P.out = p->out;
+  P.out2 = p->out2;
+  P.out2_dtype = p->out2_dtype;
   P.bias = p->bias;
   P.act = p->act;
   P.accumulate = p->accumulate;

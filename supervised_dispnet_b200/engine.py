@@ -156,7 +156,7 @@ def _pad_ok(v):
     return int(v.C % 8 != 0 and v.c0 % 8 == 0 and v.c0 + v.C == v.buf.C)
 
 
-def _mk_igemm(ins, out, w, w_dtype, cin_pad, cout_pad, bias, act, accumulate, stride, taps, out_scale=1.0):
+def _mk_igemm(ins, out, w, w_dtype, cin_pad, cout_pad, bias, act, accumulate, stride, taps, out_scale=1.0, out2=None):
     p = L.DnIgemm()
     for i, v in enumerate(ins):
         p.inp[i] = v.dn()
@@ -172,6 +172,9 @@ def _mk_igemm(ins, out, w, w_dtype, cin_pad, cout_pad, bias, act, accumulate, st
         p.taps[i] = L.DnTap(s, dh, dw, wt)
     p.out_scale = out_scale
     p.out_pad_ok = _pad_ok(out)
+    if out2 is not None:
+        d2 = out2.dn()
+        p.out2, p.out2_dtype = d2.ptr, d2.dtype
     return p
 
 
@@ -218,11 +221,14 @@ class InputOp(Op):
         self.chans = [s[1] for s in shapes]
         self.buf = Buf(N, H, W, sum(self.chans), plan.prec.act, plan.device)
         self.out = self.buf.view()
+        self.shadow = plan.shadow_of(self.out) if plan.training else None
 
     def fwd(self, plan):
         c0 = 0
         for x, c in zip(plan.inputs, self.chans):
             L.call('dn_pack_input', L.ptr(x), x.shape[0], c, x.shape[2], x.shape[3], self.out.ref(), c0, plan.stream)
+            if self.shadow is not None:
+                L.call('dn_pack_input', L.ptr(x), x.shape[0], c, x.shape[2], x.shape[3], self.shadow.ref(), c0, plan.stream)
             c0 += c
 
 
@@ -276,6 +282,8 @@ class ConvOp(Op):
                             for kw in range(k) if (b + self.pad - kw) % 2 == 0]
                     self.fwd_probs.append(dict(ins=[x], out=ov, taps=taps, stride=1, phase=(a, b)))
         self._fwd_built = None
+        # activations that a later convolution consumes get a gradient-dtype shadow written by the same epilogue
+        self.out_shadow = plan.shadow_of(out) if (plan.training and act != L.ACT_NONE and out.buf.dtype != torch.float32) else None
         plan.register_param(name + '.weight')
         if bias:
             plan.register_param(name + '.bias')
@@ -283,8 +291,11 @@ class ConvOp(Op):
     def _build_fwd(self, plan):
         built = []
         for pr in self.fwd_probs:
+            o2 = None
+            if self.out_shadow is not None:
+                o2 = self.out_shadow.phase(*pr['phase']) if 'phase' in pr else self.out_shadow
             p = _mk_igemm(pr['ins'], pr['out'], self.wp, plan.prec.act, self.cin_pad, self.cout_pad, None, self.act, False,
-                          pr['stride'], pr['taps'])
+                          pr['stride'], pr['taps'], out2=o2)
             built.append((p, _backend('igemm', p), _igemm_flops(p)))
         return built
 
@@ -526,12 +537,15 @@ class HeadOp(Op):
 
     def __init__(self, plan, z, alpha, beta, up=None, up_mode=0):
         self.z, self.alpha, self.beta, self.up, self.up_mode = z, float(alpha), float(beta), up, up_mode
+        self.up_shadow = plan.shadow_of(up) if (up is not None and plan.training) else None
         self.idx = plan.add_output((z.N, 1, z.H, z.W))
 
     def fwd(self, plan):
         out = plan.outputs[self.idx]
         L.call('dn_head_fwd', self.z.ref(), self.alpha, self.beta, L.ptr(out), self.up.ref() if self.up else None,
                self.up_mode, plan.stream)
+        if self.up_shadow is not None:
+            L.call('dn_copy_view', self.up.ref(), self.up_shadow.ref(), 0, plan.stream)
 
     def plan_bwd(self, plan):
         g = plan.prec.grad
@@ -647,7 +661,14 @@ class Plan:
         b = v.buf
         if getattr(b, 'shadow', None) is None:
             return None
-        if any(lo <= v.c0 and v.c0 + v.C <= hi for lo, hi in b.shadow_valid):
+        need, covered = v.c0, False
+        for lo, hi in sorted(b.shadow_valid):       # union of the slices that producers fill
+            if lo <= need < hi:
+                need = hi
+            if need >= v.c0 + v.C:
+                covered = True
+                break
+        if covered:
             return View(b.shadow, v.c0, v.C, v.H, v.W, v.off, v.sH, v.sW)
         return None
 
