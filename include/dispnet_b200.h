@@ -186,6 +186,12 @@ int dn_act_fwd(const dn_view* x, int act, const dn_view* out, void* stream);
 int dn_copy_view(const dn_view* src, const dn_view* dst, int accumulate, void* stream);
 
 /* ---- disparity heads (alpha*sigmoid(conv)+beta, models/Disp_vgg_BN.py:168) -------------------- */
+/* predict_disp's nn.Conv2d(C, 1, 3, padding=1) (models/Disp_vgg_BN.py:66-70): w is the fp32 torch parameter [1,C,3,3],
+ * z a 1-channel view.  bwd: gx (+)= dz * w; gw[C*9] and gb[1] (fp32, torch layout, overwritten) = gscale * sums;
+ * ws needs dn_reduce_ws_floats(C) floats. */
+int dn_head_conv_fwd(const dn_view* x, const float* w, const float* bias, const dn_view* z, void* stream);
+int dn_head_conv_bwd(const dn_view* x, const float* w, const dn_view* dz, const dn_view* gx, int gx_accumulate, float* gw,
+                     float* gb, float gscale, float* ws, void* stream);
 /* z: 1-channel conv output view; disp: fp32 [N,1,H,W]; optional `up` = 1-channel view of size (upH,upW) that
  * receives the x2-upsampled disparity (mode 0 nearest, 1 bilinear align_corners=False), cropped to the view. */
 int dn_head_fwd(const dn_view* z, float alpha, float beta, float* disp, const dn_view* up, int up_mode,

@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(256) pack_jobs_kernel(const dn_pack_job* __res
 
 DN_EXPORT int dn_pack_jobs(const dn_pack_job* jobs, int njobs, void* stream) {
   if (!jobs || njobs < 1) return DN_E_ARG;
-  pack_jobs_kernel<<<dim3(64, njobs), 256, 0, dn_stream(stream)>>>(jobs);
+  pack_jobs_kernel<<<dim3(512, njobs), 256, 0, dn_stream(stream)>>>(jobs);
   DN_CHECK_LAUNCH();
   return 0;
 }
@@ -468,12 +468,14 @@ __device__ __forceinline__ void cg_block_reduce(float* vals, int CGb) {
 constexpr int kMaxReduceBlocks = 2048;
 // 1024 threads = 32 columns x 32 row groups; each group strides over the partial rows, then a shared-memory combine
 template <typename TO>
-__global__ void __launch_bounds__(1024) reduce_partials_kernel(const float* __restrict__ ws, int nblk, int n, TO* __restrict__ out, double scale) {
+__global__ void __launch_bounds__(1024) reduce_partials_kernel(const float* __restrict__ ws, int nblk, int n, TO* __restrict__ out, double scale,
+                                                               int nout = -1) {
   __shared__ double part[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int j = blockIdx.x * 32 + tx;
+  if (nout < 0) nout = n;            // row stride n, first nout columns reduced
   double s = 0.0;
-  if (j < n) {
+  if (j < nout) {
     int b = ty;
     for (; b + 96 < nblk; b += 128) {      // 4 independent loads in flight
       float v0 = ws[(long long)b * n + j], v1 = ws[(long long)(b + 32) * n + j];
@@ -484,7 +486,7 @@ __global__ void __launch_bounds__(1024) reduce_partials_kernel(const float* __re
   }
   part[ty][tx] = s;
   __syncthreads();
-  if (ty == 0 && j < n) {
+  if (ty == 0 && j < nout) {
     double t = 0.0;
 #pragma unroll
     for (int k = 0; k < 32; ++k) t += part[k][tx];
@@ -1398,4 +1400,155 @@ DN_EXPORT const char* dn_error_string(int code) {
   if (code == DN_E_UNSUPPORTED) return "dispnet_b200: problem not supported by the requested backend";
   if (code > 0) return cudaGetErrorString((cudaError_t)code);
   return "dispnet_b200: unknown error";
+}
+
+// =================================================================================================
+// disparity-head convolution: nn.Conv2d(C, 1, 3, padding=1) (models/Disp_vgg_BN.py:66-70) on CUDA cores
+//
+// One output channel makes this a 9*C-term dot product per pixel: HBM-bound (read x once), a poor fit for a 128-wide MMA
+// tile.  Forward: thread per pixel.  Backward: thread per (pixel, 8-channel group); one pass produces the data gradient
+// (accumulated into the gradient arena of x), the weight gradient (per-block partial sums, reduced by a second stage) and
+// the bias gradient.
+// =================================================================================================
+template <int CH>
+__global__ void __launch_bounds__(256) head_conv_fwd_kernel(dn_view x, const float* __restrict__ w, const float* __restrict__ bias,
+                                                            dn_view z) {
+  extern __shared__ float ws[];          // [9][C]
+  const int C = x.C;
+  for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) {
+    const int t = i / C, c = i - t * C;
+    ws[i] = w[c * 9 + t];                 // torch layout [1][C][3][3]
+  }
+  __syncthreads();
+  const unsigned npix = (unsigned)x.N * x.H * x.W;
+  const float b0 = bias ? bias[0] : 0.f;
+  for (unsigned px = blockIdx.x * blockDim.x + threadIdx.x; px < npix; px += gridDim.x * blockDim.x) {
+    const unsigned q = px / (unsigned)x.W;
+    const int wv = (int)(px - q * (unsigned)x.W);
+    const int n = (int)(q / (unsigned)x.H);
+    const int h = (int)(q - (unsigned)n * (unsigned)x.H);
+    float acc = b0;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const int hh = h + t / 3 - 1, ww = wv + t % 3 - 1;
+      if (hh < 0 || hh >= x.H || ww < 0 || ww >= x.W) continue;
+      const long long off = dn_off(x, n, hh, ww);
+      for (int c0 = 0; c0 < C; c0 += CH) {
+        float f[CH];
+        ldc<CH>(x, off + c0, f);
+#pragma unroll
+        for (int i = 0; i < CH; ++i) acc = fmaf(f[i], ws[t * C + c0 + i], acc);
+      }
+    }
+    dn_st(z.ptr, z.dtype, dn_off(z, n, h, wv), acc);
+  }
+}
+
+template <int CH>
+__global__ void __launch_bounds__(256, 2) head_conv_bwd_kernel(dn_view x, const float* __restrict__ w, dn_view dz, dn_view gx,
+                                                            int gx_acc, float* __restrict__ wsp, int CGb) {
+  extern __shared__ float ws[];          // [9][C] weights, then per-block accumulators [9*C + 1]
+  const int C = x.C;
+  float* accs = ws + 9 * C;
+  for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) {
+    const int t = i / C, c = i - t * C;
+    ws[i] = w[c * 9 + t];
+  }
+  for (int i = threadIdx.x; i < 9 * C + 1; i += blockDim.x) accs[i] = 0.f;
+  __syncthreads();
+  CG_PROLOGUE(x)
+  float acc[9][CH];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int i = 0; i < CH; ++i) acc[t][i] = 0.f;
+  float accb = 0.f;
+  if (cvalid) {
+    for (unsigned px = blockIdx.x * PLn + pl; px < (unsigned)npix; px += gridDim.x * PLn) {
+      const unsigned q = px / (unsigned)x.W;
+      const int wv = (int)(px - q * (unsigned)x.W);
+      const int n = (int)(q / (unsigned)x.H);
+      const int h = (int)(q - (unsigned)n * (unsigned)x.H);
+      float xv[CH], g[CH];
+      ldc<CH>(x, dn_off(x, n, h, wv) + c0, xv);
+#pragma unroll
+      for (int i = 0; i < CH; ++i) g[i] = 0.f;
+      // forward: z[o] = sum_t x[o + d_t] w[t]  =>  this pixel p = o + d_t feeds output o = p - d_t through tap t
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const int hh = h - (t / 3 - 1), ww = wv - (t % 3 - 1);
+        float d = 0.f;
+        if (hh >= 0 && hh < x.H && ww >= 0 && ww < x.W) d = dn_ld(dz.ptr, dz.dtype, dn_off(dz, n, hh, ww));
+#pragma unroll
+        for (int i = 0; i < CH; ++i) {
+          acc[t][i] = fmaf(d, xv[i], acc[t][i]);
+          g[i] = fmaf(d, ws[t * C + (c0 + i < C ? c0 + i : C - 1)], g[i]);
+        }
+        if (t == 4 && cg == 0) accb += d;
+      }
+      const long long go = dn_off(gx, n, h, wv) + c0;
+      if (gx_acc) {
+        float o[CH];
+        ldc<CH>(gx, go, o);
+#pragma unroll
+        for (int i = 0; i < CH; ++i) g[i] += o[i];
+      }
+      stc<CH>(gx, go, g);
+    }
+  }
+  // reduce over the lanes of a warp that own the same channel group (lane bits >= log2(CGb)), then shared atomics
+  for (int o = 16; o >= CGb && o >= 1; o >>= 1) {
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+      for (int i = 0; i < CH; ++i) acc[t][i] += __shfl_xor_sync(0xffffffffu, acc[t][i], o);
+    accb += __shfl_xor_sync(0xffffffffu, accb, o);
+  }
+  const int lane = threadIdx.x & 31;
+  if (cvalid && (CGb >= 32 || lane < CGb)) {
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+      for (int i = 0; i < CH; ++i)
+        if (c0 + i < C) atomicAdd(&accs[(c0 + i) * 9 + t], acc[t][i]);     // torch layout [C][9]
+    if (cg == 0) atomicAdd(&accs[9 * C], accb);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 9 * C + 1; i += blockDim.x) wsp[(long long)blockIdx.x * (9 * C + 1) + i] = accs[i];
+}
+
+DN_EXPORT int dn_head_conv_fwd(const dn_view* x, const float* w, const float* bias, const dn_view* z, void* stream) {
+  if (!x || !w || !z || z->C != 1 || z->N != x->N || z->H != x->H || z->W != x->W) return DN_E_ARG;
+  const long long npix = (long long)x->N * x->H * x->W;
+  const size_t sm = sizeof(float) * 9 * x->C;
+  int blocks = ew_blocks(npix);
+  if (dn_vec8_ok(x)) head_conv_fwd_kernel<8><<<blocks, 256, sm, dn_stream(stream)>>>(*x, w, bias, *z);
+  else head_conv_fwd_kernel<1><<<blocks, 256, sm, dn_stream(stream)>>>(*x, w, bias, *z);
+  DN_CHECK_LAUNCH();
+  return 0;
+}
+
+DN_EXPORT int dn_head_conv_bwd(const dn_view* x, const float* w, const dn_view* dz, const dn_view* gx, int gx_accumulate,
+                               float* gw, float* gb, float gscale, float* ws, void* stream) {
+  if (!x || !w || !dz || !gx || !gw || !ws || gx->C != x->C) return DN_E_ARG;
+  const long long npix = (long long)x->N * x->H * x->W;
+  const bool vec = dn_vec8_ok(x) && dn_vec8_ok(gx);
+  const int ch = vec ? 8 : 1;
+  CgGeom g = cg_geom(x->C, ch, npix);
+  if (g.grid.y != 1) return DN_E_UNSUPPORTED;
+  const int n = 9 * x->C + 1;
+  if ((long long)g.grid.x * n > dn_reduce_ws_floats(x->C)) g.grid.x = (unsigned)(dn_reduce_ws_floats(x->C) / n);
+  const size_t sm = sizeof(float) * (18 * x->C + 1);
+  cudaStream_t st = dn_stream(stream);
+  if (vec) head_conv_bwd_kernel<8><<<g.grid, 256, sm, st>>>(*x, w, *dz, *gx, gx_accumulate, ws, g.CGb);
+  else head_conv_bwd_kernel<1><<<g.grid, 256, sm, st>>>(*x, w, *dz, *gx, gx_accumulate, ws, g.CGb);
+  DN_CHECK_LAUNCH();
+  // second stage: [blocks][9C+1] -> gw (torch layout [1][C][3][3]) and gb; both scaled by gscale
+  reduce_partials_kernel<float><<<reduce_blocks(n - 1), 1024, 0, st>>>(ws, g.grid.x, n, gw, (double)gscale, n - 1);
+  DN_CHECK_LAUNCH();
+  if (gb) {
+    reduce_partials_kernel<float><<<1, 1024, 0, st>>>(ws + (n - 1), g.grid.x, n, gb, (double)gscale, 1);
+    DN_CHECK_LAUNCH();
+  }
+  return 0;
 }

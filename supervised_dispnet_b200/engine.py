@@ -438,6 +438,31 @@ class ConvOp(Op):
                 L.call('dn_igemm_run', C.byref(p), be, plan.stream, tag=('dgrad', be, fl, self.name))
 
 
+class HeadConvOp(Op):
+    """predict_disp's nn.Conv2d(C, 1, 3, padding=1): a 9*C-term dot product per pixel on CUDA cores (HBM-bound), with a
+    fused backward (data gradient + weight gradient + bias gradient in one pass)."""
+
+    def __init__(self, plan, name, x, z):
+        self.name, self.x, self.z = name, x, z
+        plan.register_param(name + '.weight')
+        plan.register_param(name + '.bias')
+
+    def fwd(self, plan):
+        L.call('dn_head_conv_fwd', self.x.ref(), L.ptr(plan.param(self.name + '.weight')), L.ptr(plan.param(self.name + '.bias')),
+               self.z.ref(), plan.stream)
+
+    def plan_bwd(self, plan):
+        g = plan.prec.grad
+        self.gz = self.z.grad_view(g)
+        self.gx = self.x.grad_view(g)
+        self.acc = int(self.gx.claim_grad_write())
+
+    def bwd(self, plan):
+        L.call('dn_head_conv_bwd', self.x.ref(), L.ptr(plan.param(self.name + '.weight')), self.gz.ref(), self.gx.ref(), self.acc,
+               L.ptr(plan.grad_of(self.name + '.weight')), L.ptr(plan.grad_of(self.name + '.bias')), 1.0 / plan.prec.gscale,
+               L.ptr(plan.reduce_ws(self.x.C * 5)), plan.stream)
+
+
 class BNOp(Op):
     """nn.BatchNorm2d (+ residual add) + activation (+ MaxPool2d(2,2)).  `out=None`: statistics only (the dead bn1
     of Disp_res_50, models/Disp_res_50.py:143-145, whose running buffers still update)."""

@@ -84,7 +84,7 @@ class DispNetS(E.PlannedModule):
             x = o
             if lvl <= 4:
                 z = nb(N, o.H, o.W, 1, torch.float32).view()
-                plan.add(E.ConvOp(plan, 'predict_disp%d.0' % lvl, o, z, 3, act=ACT_NONE))
+                plan.add(E.HeadConvOp(plan, 'predict_disp%d.0' % lvl, o, z))
                 heads[lvl] = plan.add(E.HeadOp(plan, z, self.alpha, self.beta, slot.get(lvl), 1))
         plan.out_order = [heads[1].idx, heads[2].idx, heads[3].idx, heads[4].idx]
 

@@ -151,7 +151,7 @@ class Disp_res_50(E.PlannedModule):
 
         def head(name, src, up_view):
             z = nb(N, src.H, src.W, 1, torch.float32).view()
-            plan.add(E.ConvOp(plan, name + '.0', src, z, 3, act=ACT_NONE))
+            plan.add(E.HeadConvOp(plan, name + '.0', src, z))
             return plan.add(E.HeadOp(plan, z, self.alpha, self.beta, up_view, 0))
 
         upc('upconv5', c5, cat5.view().channels(0, up[1]))

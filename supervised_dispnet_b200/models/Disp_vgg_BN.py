@@ -121,7 +121,7 @@ class Disp_vgg_BN(E.PlannedModule):
 
         def head(name, src, up_view):
             z = nb(N, src.H, src.W, 1, torch.float32).view()
-            plan.add(E.ConvOp(plan, name + '.0', src, z, 3, act=ACT_NONE))
+            plan.add(E.HeadConvOp(plan, name + '.0', src, z))
             return plan.add(E.HeadOp(plan, z, self.alpha, self.beta, up_view, 0))
 
         up('upconv4', c5, cat4.view().channels(0, 256))
