@@ -175,9 +175,13 @@ def run_ours(args):
     net.init_weights()
     net = net.to(dev).train()
     model = net
+    dp_mode = os.environ.get('DISPNET_B200_DP', 'flat')
     if world > 1:
-        model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local], broadcast_buffers=True,
-                                                          gradient_as_bucket_view=True)
+        from supervised_dispnet_b200 import dist as D
+        if dp_mode == 'ddp':       # torch DistributedDataParallel wrapper (bucketed all-reduce)
+            model = D.wrap_ddp(net, dev)
+        else:                      # one NCCL all-reduce of the module's flat gradient arena per step
+            D.attach(net)
     params = [p for p in net.parameters() if p.requires_grad]
     opt = torch.optim.Adam(params, lr=2e-4, betas=(0.9, 0.999), fused=True)
 
@@ -290,7 +294,7 @@ def run_ours(args):
                 dtype='fp16 operands, fp32 accumulate, bf16 gradient activations (DISPNET_B200_PRECISION=%s)' % os.environ.get('DISPNET_B200_PRECISION', 'mixed'), data='synthetic',
                 config=dict(workload='configs[1]: Disp_vgg_BN + L1 depth loss (+0*smooth as train.py does), synthetic KITTI '
                                      '128x416, b=32/GPU, fwd+loss+bwd+Adam', global_batch=BATCH * world,
-                            parallelism='dp%d' % world,
+                            parallelism='dp%d' % world, dp_mode=(dp_mode if world > 1 else None),
                             l2='per-step working set (activations+gradients ~4 GB) >> 126 MB L2; no explicit flush needed',
                             last_loss=last_loss),
                 clocks=sampler.summary(),

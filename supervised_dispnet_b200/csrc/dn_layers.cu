@@ -1420,13 +1420,16 @@ __global__ void __launch_bounds__(256) head_conv_fwd_kernel(dn_view x, const flo
     ws[i] = w[c * 9 + t];                 // torch layout [1][C][3][3]
   }
   __syncthreads();
-  const unsigned npix = (unsigned)x.N * x.H * x.W;
+  // 16x16-pixel tiles: the 3x3 neighbourhoods of a block's pixels overlap inside its own L1
+  const unsigned tilesW = (x.W + 15) / 16, tilesH = (x.H + 15) / 16;
+  const unsigned ntiles = tilesW * tilesH * (unsigned)x.N;
   const float b0 = bias ? bias[0] : 0.f;
-  for (unsigned px = blockIdx.x * blockDim.x + threadIdx.x; px < npix; px += gridDim.x * blockDim.x) {
-    const unsigned q = px / (unsigned)x.W;
-    const int wv = (int)(px - q * (unsigned)x.W);
-    const int n = (int)(q / (unsigned)x.H);
-    const int h = (int)(q - (unsigned)n * (unsigned)x.H);
+  for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const unsigned tq = tile / tilesW;
+    const int wv = (int)(tile - tq * tilesW) * 16 + (int)(threadIdx.x & 15);
+    const int n = (int)(tq / tilesH);
+    const int h = (int)(tq - (unsigned)n * tilesH) * 16 + (int)(threadIdx.x >> 4);
+    if (wv >= x.W || h >= x.H) continue;
     float acc = b0;
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
@@ -1464,11 +1467,15 @@ __global__ void __launch_bounds__(256, 2) head_conv_bwd_kernel(dn_view x, const 
     for (int i = 0; i < CH; ++i) acc[t][i] = 0.f;
   float accb = 0.f;
   if (cvalid) {
-    for (unsigned px = blockIdx.x * PLn + pl; px < (unsigned)npix; px += gridDim.x * PLn) {
-      const unsigned q = px / (unsigned)x.W;
-      const int wv = (int)(px - q * (unsigned)x.W);
-      const int n = (int)(q / (unsigned)x.H);
-      const int h = (int)(q - (unsigned)n * (unsigned)x.H);
+    const unsigned tw = PLn >= 16 ? 16 : PLn, th = PLn >= 16 ? PLn / 16 : 1;      // tile of pixel lanes (PLn is a power of two)
+    const unsigned tilesW = (x.W + tw - 1) / tw, tilesH = (x.H + th - 1) / th;
+    const unsigned ntiles = tilesW * tilesH * (unsigned)x.N;
+    for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const unsigned tq = tile / tilesW;
+      const int wv = (int)((tile - tq * tilesW) * tw + ((unsigned)pl % tw));
+      const int n = (int)(tq / tilesH);
+      const int h = (int)((tq - (unsigned)n * tilesH) * th + ((unsigned)pl / tw));
+      if (wv >= x.W || h >= x.H) continue;
       float xv[CH], g[CH];
       ldc<CH>(x, dn_off(x, n, h, wv) + c0, xv);
 #pragma unroll
@@ -1519,7 +1526,7 @@ __global__ void __launch_bounds__(256, 2) head_conv_bwd_kernel(dn_view x, const 
 
 DN_EXPORT int dn_head_conv_fwd(const dn_view* x, const float* w, const float* bias, const dn_view* z, void* stream) {
   if (!x || !w || !z || z->C != 1 || z->N != x->N || z->H != x->H || z->W != x->W) return DN_E_ARG;
-  const long long npix = (long long)x->N * x->H * x->W;
+  const long long npix = (long long)x->N * ((x->H + 15) / 16) * ((x->W + 15) / 16) * 256;
   const size_t sm = sizeof(float) * 9 * x->C;
   int blocks = ew_blocks(npix);
   if (dn_vec8_ok(x)) head_conv_fwd_kernel<8><<<blocks, 256, sm, dn_stream(stream)>>>(*x, w, bias, *z);

@@ -34,3 +34,18 @@ def allreduce_error_counters(counters, sums, group=None):
         dist.all_reduce(t, group=group)
         dist.all_reduce(c, group=group)
     return [float(v) / float(t[8]) for v in t[:8]], c.tolist()
+
+
+def attach(net, group=None):
+    """Data parallelism without the DDP wrapper: broadcast rank 0's parameters and buffers once, then let the module's own
+    backward all-reduce (average) its flat fp32 gradient arena with ONE NCCL call per step (engine.Plan._clone_grads).
+    The gradients already live in one contiguous buffer, so DDP's bucket copies, hooks and per-step buffer broadcasts buy
+    nothing here; BatchNorm running statistics stay per rank and rank 0's are the ones checkpointed, which is what the
+    reference's nn.DataParallel keeps (replica 0; train.py:316-317, 378)."""
+    if not (dist.is_available() and dist.is_initialized()):
+        raise RuntimeError('torch.distributed is not initialised')
+    with torch.no_grad():
+        for t in list(net.parameters()) + list(net.buffers()):
+            dist.broadcast(t, src=0, group=group)
+    net._dp_group = group if group is not None else dist.group.WORLD
+    return net

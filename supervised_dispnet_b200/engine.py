@@ -861,6 +861,10 @@ class Plan:
 
     def _clone_grads(self, flat):
         out = flat.clone()          # autograd may keep / accumulate into what we return: hand out a private copy
+        group = getattr(self.module, '_dp_group', None)
+        if group is not None:       # data parallel: one NCCL all-reduce (mean) of the whole gradient arena
+            import torch.distributed as dist
+            dist.all_reduce(out, op=dist.ReduceOp.AVG, group=group)
         res, o = {}, 0
         for n in self.param_names:
             p = self._params[n]
