@@ -252,6 +252,7 @@ def run_ours(args):
 
     # ---- roofline pass (rank 0): CUDA events around every kernel launch of the same step
     peaks = load_peaks()
+    net._dp_group = None            # rank 0 is alone from here on: no collective in the profiling pass
     L.PROFILE = []
     nprof = 3
     for _ in range(nprof):
