@@ -53,6 +53,15 @@ def _worker(rank, world, port, q):
         n_ddp = sum(p.numel() for p in ddp.parameters() if p.requires_grad)
         vgg = S.models.Disp_vgg_BN()
         n_train = sum(p.numel() for p in vgg.parameters() if p.requires_grad)
+        # flat data-parallel mode: attach() makes every rank start from rank 0's parameters and buffers
+        net2 = S.models.DispNetS()
+        torch.manual_seed(100 + rank)
+        net2.init_weights()
+        D.attach(net2)
+        probe = float(net2.conv1[0].weight.double().sum())
+        gathered = [torch.zeros(1, dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(gathered, torch.tensor([probe], dtype=torch.float64))
+        assert all(float(g) == float(gathered[0]) for g in gathered) and net2._dp_group is not None
         # gradient averaging semantics: mean of per-rank means == global mean for equal shards
         w = torch.nn.Parameter(torch.zeros(3))
         lin = torch.nn.parallel.DistributedDataParallel(torch.nn.Linear(3, 1, bias=False))
