@@ -615,14 +615,16 @@ struct WgradTcParams {
   CUtensorMap tmQ;
   TcTap taps[kMaxTcTaps];
   int ntaps;
-  int tpc, ngroups;        // taps per CTA (they share the dy tile), number of tap groups
+  int tpc, ngroups;        // taps per work item (they share the dy tile), number of tap groups
   int wb, hb, nb;          // pixel box, wb*hb*nb == KPX
   int tilesW, tilesH, tilesN, num_ptiles;
   int cp_tiles, cq_tiles;  // output tiles: 128 x BNQ
   int cp_blocks;           // 64-channel blocks of P actually present in a cp tile (1 or 2)
   int splits, ptiles_per_split;
+  int num_items;           // ngroups * cp_tiles * cq_tiles * splits
   int stages;
   int n_mma;               // MMA N per tap (multiple of 16, <= BNQ)
+  int nacc;                // TMEM accumulator stages (2: the atomics of item i overlap the main loop of item i+1)
   int tmem_cols;
   int halo;                // 1: x is fetched once per pixel tile as a (8+2) x 16-pixel halo box, taps are shifted views
   uint32_t idesc;
@@ -632,6 +634,25 @@ struct WgradTcParams {
 };
 
 constexpr int KPX = 64;   // pixels (= GEMM K) per pipeline stage
+
+struct WgItem { int grp, cqt, cpt, split, t0, nt, src, pt_beg, n_iters; };
+
+__device__ __forceinline__ WgItem wg_decode(const WgradTcParams& p, int item) {
+  WgItem w;
+  // tap group fastest so that CTAs running together share the same pixel range in L2
+  w.grp = item % p.ngroups; item /= p.ngroups;
+  w.cqt = item % p.cq_tiles; item /= p.cq_tiles;
+  w.cpt = item % p.cp_tiles; item /= p.cp_tiles;
+  w.split = item;
+  w.t0 = w.grp * p.tpc;
+  w.nt = (p.ntaps - w.t0) < p.tpc ? (p.ntaps - w.t0) : p.tpc;
+  w.src = p.taps[w.t0].src;     // all taps of one launch share the dy view
+  w.pt_beg = w.split * p.ptiles_per_split;
+  int pt_end = w.pt_beg + p.ptiles_per_split;
+  if (pt_end > p.num_ptiles) pt_end = p.num_ptiles;
+  w.n_iters = pt_end - w.pt_beg;
+  return w;
+}
 
 template <int BNQ>
 __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant__ WgradTcParams p) {
@@ -645,31 +666,18 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
   const int stages = p.stages;
   uint64_t* full_bar = (uint64_t*)(smem + (size_t)stages * STAGE_BYTES);
   uint64_t* empty_bar = full_bar + stages;
-  uint64_t* done_bar = empty_bar + stages;
-  uint32_t* tmem_ptr = (uint32_t*)(done_bar + 1);
+  uint64_t* tfull_bar = empty_bar + stages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_ptr = (uint32_t*)(tempty_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  // work item: tap group fastest so that CTAs running together share the same pixel range in L2
-  int item = blockIdx.x;
-  const int grp = item % p.ngroups; item /= p.ngroups;
-  const int cqt = item % p.cq_tiles; item /= p.cq_tiles;
-  const int cpt = item % p.cp_tiles; item /= p.cp_tiles;
-  const int split = item;
-  const int t0 = grp * p.tpc;
-  const int nt = (p.ntaps - t0) < p.tpc ? (p.ntaps - t0) : p.tpc;
-  const int src = p.taps[t0].src;     // all taps of one launch share the dy view
-  const int pt_beg = split * p.ptiles_per_split;
-  int pt_end = pt_beg + p.ptiles_per_split;
-  if (pt_end > p.num_ptiles) pt_end = p.num_ptiles;
-  const int n_iters = pt_end - pt_beg;
-
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&p.tmP[src]);
+    tma_prefetch_desc(&p.tmP[0]);
     tma_prefetch_desc(&p.tmQ);
     for (int s = 0; s < stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    mbar_init(done_bar, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 128); }
     fence_barrier_init();
     fence_proxy_async();
   }
@@ -681,15 +689,17 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t acc_cols = (uint32_t)(p.tpc * p.n_mma);
 
-  // bytes that really arrive per stage: only the P blocks that exist and the taps of this group are loaded
-  const uint32_t tx_bytes = (uint32_t)p.cp_blocks * BLK_BYTES + (p.halo ? (uint32_t)(BNQ / 64) * HALO_BLK : (uint32_t)nt * B_BYTES);
-
-  if (n_iters > 0) {
-    if (warp == 0) {
-      int stage = 0; uint32_t phase = 0;
-      for (int pt = pt_beg; pt < pt_end; ++pt) {
-        int m = pt;
+  if (warp == 0) {
+    // ================= TMA producer =================
+    int stage = 0; uint32_t phase = 0;
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+      const WgItem w = wg_decode(p, item);
+      // bytes that really arrive per stage: only the P blocks that exist and the taps of this group are loaded
+      const uint32_t tx_bytes = (uint32_t)p.cp_blocks * BLK_BYTES + (p.halo ? (uint32_t)(BNQ / 64) * HALO_BLK : (uint32_t)w.nt * B_BYTES);
+      for (int it = 0; it < w.n_iters; ++it) {
+        int m = w.pt_beg + it;
         const int tw = m % p.tilesW; m /= p.tilesW;
         const int th = m % p.tilesH;
         const int tn = m / p.tilesH;
@@ -699,27 +709,35 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
           uint8_t* sa = smem + (size_t)stage * STAGE_BYTES;
           mbar_expect_tx(&full_bar[stage], tx_bytes);
           for (int j = 0; j < p.cp_blocks; ++j)
-            tma_load_4d(sa + j * BLK_BYTES, &p.tmP[src], &full_bar[stage], cpt * 128 + j * 64, w0, h0, n0);
+            tma_load_4d(sa + j * BLK_BYTES, &p.tmP[w.src], &full_bar[stage], w.cpt * 128 + j * 64, w0, h0, n0);
           if (p.halo) {
 #pragma unroll
             for (int j = 0; j < BNQ / 64; ++j)
-              tma_load_4d(sa + A_BYTES + j * HALO_BLK, &p.tmQ, &full_bar[stage], cqt * BNQ + j * 64, w0 - 1, h0 - 1, n0);
+              tma_load_4d(sa + A_BYTES + j * HALO_BLK, &p.tmQ, &full_bar[stage], w.cqt * BNQ + j * 64, w0 - 1, h0 - 1, n0);
           } else {
-            for (int t = 0; t < nt; ++t) {
-              const TcTap tap = p.taps[t0 + t];
+            for (int t = 0; t < w.nt; ++t) {
+              const TcTap tap = p.taps[w.t0 + t];
               uint8_t* sb = sa + A_BYTES + (size_t)t * B_BYTES;
 #pragma unroll
               for (int j = 0; j < BNQ / 64; ++j)
-                tma_load_4d(sb + j * BLK_BYTES, &p.tmQ, &full_bar[stage], cqt * BNQ + j * 64, w0 + tap.dw, h0 + tap.dh, n0);
+                tma_load_4d(sb + j * BLK_BYTES, &p.tmQ, &full_bar[stage], w.cqt * BNQ + j * 64, w0 + tap.dw, h0 + tap.dh, n0);
             }
           }
         }
         __syncwarp();
         if (++stage == stages) { stage = 0; phase ^= 1; }
       }
-    } else if (warp == 1) {
-      int stage = 0; uint32_t phase = 0;
-      for (int it = 0; it < n_iters; ++it) {
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    int stage = 0; uint32_t phase = 0;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+      const WgItem w = wg_decode(p, item);
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_base = tmem_base + (uint32_t)acc * acc_cols;
+      for (int it = 0; it < w.n_iters; ++it) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + (size_t)stage * STAGE_BYTES);
@@ -727,46 +745,53 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
         // 16 pixels (one UMMA_K step) further down = +2048 bytes = +128 in the (addr >> 4) field
         const uint64_t ad0 = make_desc(sa, BLK_BYTES, 1024);
         if (elect_one()) {
-          for (int t = 0; t < nt; ++t) {
+          for (int t = 0; t < w.nt; ++t) {
             if (p.halo) {
               // pixel tile = 8 rows x 8 columns; tap (dh, dw) reads halo pixel (row + dh + 1, col + dw + 1): a view that starts
               // ((dh+1)*16 + (dw+1)) pixels into the 16-pixel-pitch halo block.  One UMMA_K step = 16 pixels = 2 image rows.
-              const TcTap tap = p.taps[t0 + t];
+              const TcTap tap = p.taps[w.t0 + t];
               const uint32_t sb = sa + A_BYTES + (uint32_t)((tap.dh + 1) * 16 + (tap.dw + 1)) * 128;
               const uint64_t bd0 = make_desc(sb, HALO_BLK, 2048);
 #pragma unroll
               for (int k = 0; k < KPX / 16; ++k)
-                umma_f16(tmem_base + (uint32_t)(t * p.n_mma), ad0 + (uint64_t)(128 * k), bd0 + (uint64_t)(256 * k), p.idesc,
+                umma_f16(d_base + (uint32_t)(t * p.n_mma), ad0 + (uint64_t)(128 * k), bd0 + (uint64_t)(256 * k), p.idesc,
                          (it > 0 || k > 0) ? 1u : 0u);
             } else {
               const uint64_t bd0 = make_desc(sa + A_BYTES + (uint32_t)t * B_BYTES, BLK_BYTES, 1024);
 #pragma unroll
               for (int k = 0; k < KPX / 16; ++k)
-                umma_f16(tmem_base + (uint32_t)(t * p.n_mma), ad0 + (uint64_t)(128 * k), bd0 + (uint64_t)(128 * k), p.idesc,
+                umma_f16(d_base + (uint32_t)(t * p.n_mma), ad0 + (uint64_t)(128 * k), bd0 + (uint64_t)(128 * k), p.idesc,
                          (it > 0 || k > 0) ? 1u : 0u);
             }
           }
           umma_commit(&empty_bar[stage]);
-          if (it == n_iters - 1) umma_commit(done_bar);
+          if (it == w.n_iters - 1) umma_commit(&tfull_bar[acc]);
         }
         __syncwarp();
         if (++stage == stages) { stage = 0; phase ^= 1; }
       }
-    } else {
-      const int q = warp & 3;
-      const int row = q * 32 + lane;        // cp within the tile
-      const int cp = cpt * 128 + row;
-      mbar_wait(done_bar, 0);
+      if (p.nacc == 2) { if (++acc == 2) { acc = 0; acc_phase ^= 1; } }
+      else acc_phase ^= 1;
+    }
+  } else {
+    // ================= epilogue: TMEM -> scaled fp32 partial sums -> red.global.add =================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;        // cp within the tile
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+      const WgItem w = wg_decode(p, item);
+      const int cp = w.cpt * 128 + row;
+      mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      for (int t = 0; t < nt; ++t) {
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * p.n_mma);
-        float* drow = p.dw + ((size_t)p.taps[t0 + t].wt * p.cp_pad + cp) * p.cq_pad + cqt * BNQ;
+      for (int t = 0; t < w.nt; ++t) {
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * acc_cols + (uint32_t)(t * p.n_mma);
+        float* drow = p.dw + ((size_t)p.taps[w.t0 + t].wt * p.cp_pad + cp) * p.cq_pad + w.cqt * BNQ;
 #pragma unroll 1
         for (int c0 = 0; c0 < p.n_mma; c0 += 16) {
           uint32_t r[16];
           tmem_ld16(taddr + c0, r);
           tmem_ld_wait();
-          if (cp < p.cp && cqt * BNQ + c0 < p.cq_pad) {
+          if (cp < p.cp && w.cqt * BNQ + c0 < p.cq_pad) {
 #pragma unroll
             for (int j = 0; j < 16; j += 4)
               red_add_v4(drow + c0 + j, __uint_as_float(r[j]) * p.scale, __uint_as_float(r[j + 1]) * p.scale,
@@ -774,6 +799,10 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
           }
         }
       }
+      tc_fence_before();
+      mbar_arrive(&tempty_bar[acc]);
+      if (p.nacc == 2) { if (++acc == 2) { acc = 0; acc_phase ^= 1; } }
+      else acc_phase ^= 1;
     }
   }
   tc_fence_before();
@@ -877,14 +906,15 @@ int launch_igemm(const IgemmTcParams& P, cudaStream_t st) {
 template <int BNQ>
 int launch_wgrad(const WgradTcParams& P, int items, cudaStream_t st) {
   const uint32_t stage_bytes = 2 * KPX * 128 + (P.halo ? (uint32_t)(BNQ / 64) * 16 * 10 * 128 : (uint32_t)P.tpc * (BNQ / 64) * KPX * 128);
-  size_t smem = (size_t)P.stages * stage_bytes + 1024 + (2 * P.stages + 1) * 8 + 16;
+  size_t smem = (size_t)P.stages * stage_bytes + 1024 + (2 * P.stages + 4) * 8 + 16;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<BNQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  wgrad_tc_kernel<BNQ><<<items, 192, smem, st>>>(P);
+  const int grid = items < dn_num_sms() ? items : dn_num_sms();
+  wgrad_tc_kernel<BNQ><<<grid, 192, smem, st>>>(P);
   DN_CHECK_LAUNCH();
   return 0;
 }
@@ -1169,17 +1199,21 @@ int dn_wgrad_tc(const dn_wgrad* p, cudaStream_t st) {
   // all taps of a group must read the same dy view
   for (int t = 1; t < P.ntaps; ++t)
     if (p->taps[t].src != p->taps[0].src) { tpc = 1; break; }
+  // wide tiles: prefer two accumulator stages (<= 256 columns per stage) over sharing the dy tile between more taps
+  if (P.n_mma >= 128 && tpc * P.n_mma > 256) tpc = 256 / P.n_mma;
   P.ngroups = (P.ntaps + tpc - 1) / tpc;
   P.tpc = (P.ntaps + P.ngroups - 1) / P.ngroups;
   P.ngroups = (P.ntaps + P.tpc - 1) / P.tpc;
   int cols = P.tpc * P.n_mma;
+  P.nacc = cols <= 256 ? 2 : 1;
+  cols *= P.nacc;
   P.tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512;
   const int out_tiles = P.ngroups * P.cp_tiles * P.cq_tiles;
   // split-K factor: about two waves of CTAs, chosen so that the last wave is as full as possible
   int splits = 1;
   {
     const int sms = dn_num_sms();
-    int lo = (sms + out_tiles - 1) / out_tiles, hi = (3 * sms + out_tiles - 1) / out_tiles;
+    int lo = (2 * sms + out_tiles - 1) / out_tiles, hi = (4 * sms + out_tiles - 1) / out_tiles;
     if (hi > P.num_ptiles) hi = P.num_ptiles;
     if (lo > hi) lo = hi;
     if (lo < 1) lo = 1;
@@ -1201,6 +1235,7 @@ int dn_wgrad_tc(const dn_wgrad* p, cudaStream_t st) {
   P.cp = P0.C; P.cq = p->q.C; P.cp_pad = p->cp_pad; P.cq_pad = p->cq_pad;
   P.scale = p->scale;
   const int items = out_tiles * P.splits;
+  P.num_items = items;
   switch (BNQ) {
     case 256: return launch_wgrad<256>(P, items, st);
     case 128: return launch_wgrad<128>(P, items, st);
