@@ -16,6 +16,7 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <string.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -913,7 +914,8 @@ int launch_wgrad(const WgradTcParams& P, int items, cudaStream_t st) {
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  const int grid = items < dn_num_sms() ? items : dn_num_sms();
+  int grid = items < dn_num_sms() ? items : dn_num_sms();
+  if (const char* e = getenv("DN_WGRAD_NONPERSISTENT")) { if (atoi(e) == 1) grid = items; }
   wgrad_tc_kernel<BNQ><<<grid, 192, smem, st>>>(P);
   DN_CHECK_LAUNCH();
   return 0;
@@ -1159,6 +1161,11 @@ int dn_wgrad_tc(const dn_wgrad* p, cudaStream_t st) {
     }
     const double eff = (double)P0.H * P0.W / ((double)((P0.H + 7) / 8 * 8) * ((P0.W + 7) / 8 * 8));
     if (eff < 0.85) halo = false;
+    // the halo box (20 KB per 64 channels) only pays off when several taps of one work item share it: a wide output
+    // tile leaves TMEM room for one or two taps per item, and then nine plain 8 KB boxes are cheaper than nine halo boxes
+    const int n16 = (p->q.C + 15) / 16 * 16;
+    const int n_mma_est = p->cq_pad >= 256 ? 256 : (n16 < 64 ? n16 : (p->cq_pad >= 128 ? 128 : 64));
+    if (512 / n_mma_est < 3 || (n_mma_est >= 128)) halo = false;
   }
   P.halo = halo ? 1 : 0;
   if (halo) { P.wb = 8; P.hb = 8; P.nb = 1; }
@@ -1206,6 +1213,7 @@ int dn_wgrad_tc(const dn_wgrad* p, cudaStream_t st) {
   P.ngroups = (P.ntaps + P.tpc - 1) / P.tpc;
   int cols = P.tpc * P.n_mma;
   P.nacc = cols <= 256 ? 2 : 1;
+  if (const char* e = getenv("DN_WGRAD_NACC")) { if (atoi(e) == 1) P.nacc = 1; }
   cols *= P.nacc;
   P.tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512;
   const int out_tiles = P.ngroups * P.cp_tiles * P.cq_tiles;
@@ -1213,7 +1221,7 @@ int dn_wgrad_tc(const dn_wgrad* p, cudaStream_t st) {
   int splits = 1;
   {
     const int sms = dn_num_sms();
-    int lo = (2 * sms + out_tiles - 1) / out_tiles, hi = (4 * sms + out_tiles - 1) / out_tiles;
+    int lo = (sms + out_tiles - 1) / out_tiles, hi = (2 * sms + out_tiles - 1) / out_tiles;
     if (hi > P.num_ptiles) hi = P.num_ptiles;
     if (lo > hi) lo = hi;
     if (lo < 1) lo = 1;
