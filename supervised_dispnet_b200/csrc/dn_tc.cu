@@ -419,6 +419,7 @@ struct HaloParams {
   int wt[9];            // packed-weight matrix index of tap (kh, kw), kh = dh + 1, kw = dw + 1
   int tilesW, tilesH, num_tiles;
   int stages;
+  int ring, bstages;    // ring = 1: weight tiles stream through a bstages-deep ring instead of staying resident
   int n_mma, c_eff;
   uint32_t idesc;
   dn_view out;
@@ -436,15 +437,16 @@ __global__ void __launch_bounds__(192, 1) igemm_halo_kernel(const __grid_constan
   constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int stages = p.stages;
-  const int nb_tiles = 9 * p.kchunks;                       // resident weight tiles
+  const int nb_tiles = p.ring ? p.bstages : 9 * p.kchunks;   // weight tiles in shared memory (ring slots or all of them)
   uint8_t* smem_b = smem;
   uint8_t* smem_a = smem + (size_t)nb_tiles * B_BYTES;
   uint64_t* full_bar = (uint64_t*)(smem_a + (size_t)stages * kHaloBytes);
   uint64_t* empty_bar = full_bar + stages;
   uint64_t* tfull_bar = empty_bar + stages;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint64_t* bfull_bar = tempty_bar + 2;
-  uint32_t* tmem_ptr = (uint32_t*)(bfull_bar + 1);
+  uint64_t* bfull_bar = tempty_bar + 2;                      // resident: [0]; ring: full[0..7], empty[8..15]
+  uint64_t* bempty_bar = bfull_bar + 8;
+  uint32_t* tmem_ptr = (uint32_t*)(bfull_bar + 16);
   float* bias_s = (float*)(tmem_ptr + 2);
 
   const int warp = threadIdx.x >> 5;
@@ -455,7 +457,7 @@ __global__ void __launch_bounds__(192, 1) igemm_halo_kernel(const __grid_constan
     tma_prefetch_desc(&p.tmB);
     for (int s = 0; s < stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 128); }
-    mbar_init(bfull_bar, 1);
+    for (int s = 0; s < 8; ++s) { mbar_init(&bfull_bar[s], 1); mbar_init(&bempty_bar[s], 1); }
     fence_barrier_init();
     fence_proxy_async();
   }
@@ -468,7 +470,81 @@ __global__ void __launch_bounds__(192, 1) igemm_halo_kernel(const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  if (warp == 0) {
+  if (warp == 0 && p.ring) {
+    // ---- producer, streamed weights: the halo box of item i+1 is requested before the nine weight tiles of item i
+    int stage = 0; uint32_t phase = 0;
+    int bs = 0; uint32_t bphase = 0;
+    int a_tile = blockIdx.x, a_kc = 0;
+    auto load_a = [&]() {
+      if (a_tile >= p.num_tiles) return;
+      int m = a_tile;
+      const int tw = m % p.tilesW; m /= p.tilesW;
+      const int th = m % p.tilesH;
+      const int n0 = m / p.tilesH;
+      mbar_wait(&empty_bar[stage], phase ^ 1);
+      if (elect_one()) {
+        mbar_expect_tx(&full_bar[stage], kHaloBytes);
+        tma_load_4d(smem_a + (size_t)stage * kHaloBytes, &p.tmA, &full_bar[stage], a_kc * kChunk, tw * 8 - 1, th * 16 - 1, n0);
+      }
+      __syncwarp();
+      if (++stage == stages) { stage = 0; phase ^= 1; }
+      if (++a_kc == p.kchunks) { a_kc = 0; a_tile += gridDim.x; }
+    };
+    load_a();
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      for (int kc = 0; kc < p.kchunks; ++kc) {
+        load_a();
+        for (int t = 0; t < 9; ++t) {
+          mbar_wait(&bempty_bar[bs], bphase ^ 1);
+          if (elect_one()) {
+            mbar_expect_tx(&bfull_bar[bs], B_BYTES);
+            tma_load_3d(smem_b + (size_t)bs * B_BYTES, &p.tmB, &bfull_bar[bs], kc * kChunk, 0, p.wt[t]);
+          }
+          __syncwarp();
+          if (++bs == p.bstages) { bs = 0; bphase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1 && p.ring) {
+    // ---- MMA issuer, streamed weights
+    int stage = 0; uint32_t phase = 0;
+    int bs = 0; uint32_t bphase = 0;
+    int acc = 0; uint32_t acc_phase = 0;
+    const uint32_t sb0 = smem_u32(smem_b);
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+      for (int kc = 0; kc < p.kchunks; ++kc) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem_a + (size_t)stage * kHaloBytes);
+        const int ks = (kc == p.kchunks - 1) ? p.last_ksteps : 4;
+#pragma unroll 1
+        for (int t = 0; t < 9; ++t) {
+          mbar_wait(&bfull_bar[bs], bphase);
+          tc_fence_after();
+          if (elect_one()) {
+            const int kh = t / 3, kw = t - 3 * kh;
+            const uint64_t ad0 = make_desc(sa + (uint32_t)(kh * kHaloW + kw) * 128, 16, 2048);
+            const uint64_t bd0 = make_desc(sb0 + (uint32_t)bs * B_BYTES, 16, 1024);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if (k < ks) umma_f16(d_tmem, ad0 + (uint64_t)(2 * k), bd0 + (uint64_t)(2 * k), p.idesc, (kc == 0 && t == 0 && k == 0) ? 0u : 1u);
+            umma_commit(&bempty_bar[bs]);
+            if (t == 8) {
+              umma_commit(&empty_bar[stage]);
+              if (kc == p.kchunks - 1) umma_commit(&tfull_bar[acc]);
+            }
+          }
+          __syncwarp();
+          if (++bs == p.bstages) { bs = 0; bphase ^= 1; }
+        }
+        if (++stage == stages) { stage = 0; phase ^= 1; }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else if (warp == 0) {
     // ---- producer: weights once, then one halo box per (tile, chunk)
     if (elect_one()) {
       mbar_expect_tx(bfull_bar, (uint32_t)nb_tiles * B_BYTES);
@@ -924,6 +1000,7 @@ int launch_wgrad(const WgradTcParams& P, int items, cudaStream_t st) {
 
 // ---- halo variant: eligibility + launch -------------------------------------------------------------------------
 bool g_halo_enabled = true;
+const bool g_halo_ring = []() { const char* e = getenv("DN_HALO_RING"); return !(e && e[0] == '0'); }();   // A/B knob
 
 // fills wt[kh*3+kw]; true when the taps are exactly the 3x3 neighbourhood of one source
 bool halo_taps(const dn_igemm* p, int* wt) {
@@ -946,7 +1023,10 @@ bool halo_eligible(const dn_igemm* p, int* wt) {
   const int BN = pick_bn(p->cout_pad);
   const int kchunks = (p->in[0].C + kChunk - 1) / kChunk;
   const size_t b_bytes = (size_t)9 * kchunks * BN * 128;
-  if (b_bytes + 2 * kHaloBytes > 200 * 1024) return false;          // weights must stay resident next to >= 2 halo stages
+  // weights stay resident next to >= 2 halo stages when they fit; else they stream through a ring, which measured a gain only
+  // for one-chunk problems (features.7 forward 0.099 -> 0.093 ms): N <= 128 tiles with more K are bound by the 128 B/clk
+  // shared-memory operand reads of cta_group::1 either way (A 4 KB + B 4 KB per 64-cycle 128x128x16 MMA)
+  if (b_bytes + 2 * kHaloBytes > 200 * 1024 && (BN > 128 || kchunks > 1 || !g_halo_ring)) return false;
   const int H = p->out.H, W = p->out.W;
   if (H != p->in[0].H || W != p->in[0].W) return false;
   // tile = 16 rows x 8 columns: only worth it when little of the tile grid is padding
@@ -956,8 +1036,8 @@ bool halo_eligible(const dn_igemm* p, int* wt) {
 
 template <int BN>
 int launch_halo(const HaloParams& P, cudaStream_t st) {
-  const size_t b_bytes = (size_t)9 * P.kchunks * BN * 128;
-  size_t smem = b_bytes + (size_t)P.stages * kHaloBytes + 1024 + (2 * P.stages + 5) * 8 + 16 + 2 * BN * 4;
+  const size_t b_bytes = (size_t)(P.ring ? P.bstages : 9 * P.kchunks) * BN * 128;
+  size_t smem = b_bytes + (size_t)P.stages * kHaloBytes + 1024 + (2 * P.stages + 20) * 8 + 16 + 2 * BN * 4;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(igemm_halo_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -1007,8 +1087,15 @@ int dn_igemm_halo(const dn_igemm* p, const int* wt, cudaStream_t st) {
   P.tilesH = (p->out.H + 15) / 16;
   P.num_tiles = P.tilesW * P.tilesH * p->out.N;
   const size_t b_bytes = (size_t)9 * P.kchunks * BN * 128;
-  P.stages = (int)((200 * 1024 - b_bytes) / kHaloBytes);
-  if (P.stages > 4) P.stages = 4;
+  if (b_bytes + 2 * kHaloBytes > 200 * 1024) {
+    P.ring = 1;
+    P.stages = 2;
+    P.bstages = (int)((200 * 1024 - 2 * kHaloBytes) / ((size_t)BN * 128));
+    if (P.bstages > 8) P.bstages = 8;
+  } else {
+    P.stages = (int)((200 * 1024 - b_bytes) / kHaloBytes);
+    if (P.stages > 4) P.stages = 4;
+  }
   P.n_mma = p->cout_pad < BN ? p->cout_pad : BN;
   P.c_eff = (p->out.dtype != DN_F32 && p->out_pad_ok) ? (p->out.C + 7) / 8 * 8 : p->out.C;
   P.idesc = make_idesc(p->in[0].dtype, p->w_dtype, 0, 0, 128, P.n_mma);

@@ -9,6 +9,9 @@ CASES = {
     'iconv0': (dict(cin=17, cout=16, k=3, act=2), (32, 17, 128, 416)),
     'feat3': (dict(cin=64, cout=64, k=3), (32, 64, 128, 416)),
     'feat0': (dict(cin=3, cout=64, k=3), (32, 3, 128, 416)),
+    'feat7': (dict(cin=64, cout=128, k=3), (32, 64, 64, 208)),
+    'iconv2': (dict(cin=193, cout=64, k=3, act=2), (32, 193, 32, 104)),
+    'iconv3': (dict(cin=385, cout=128, k=3, act=2), (32, 385, 16, 52)),
     'feat10': (dict(cin=128, cout=128, k=3), (32, 128, 64, 208)),
     'feat17': (dict(cin=256, cout=256, k=3), (32, 256, 32, 104)),
     'feat27': (dict(cin=512, cout=512, k=3), (32, 512, 16, 52)),
