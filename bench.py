@@ -55,32 +55,59 @@ def synth_batch(b, seed, pinned=False):
 
 
 class ClockSampler(threading.Thread):
-    Q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+    """SM clock + throttle reasons sampled during the timed region: NVML every 5 ms (in-process, ~50 us per sample), falling
+    back to `nvidia-smi --query-gpu` (the profiling recipe's clocks line, ~60 ms per sample) when NVML cannot be loaded."""
+    Q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+    NAMES = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+    BITS = [0x8, 0x40, 0x20, 0x4]      # nvmlClocksEventReason{HwSlowdown, HwThermalSlowdown, SwThermalSlowdown, SwPowerCap}
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.samples, self.stop_flag = index, [], False
+        self.index, self.samples, self.stop_flag, self.source = index, [], False, 'nvidia-smi'
+        self.nv = self.h = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            try:
+                uuid = str(torch.cuda.get_device_properties(index).uuid)
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(('GPU-' + uuid) if not uuid.startswith('GPU-') else uuid)
+            except Exception:  # noqa: BLE001
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nv, self.source = pynvml, 'nvml'
+        except Exception:  # noqa: BLE001
+            self.nv = None
+
+    def sample(self):
+        try:
+            if self.nv is not None:
+                mhz = float(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                try:
+                    mask = int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:  # noqa: BLE001
+                    mask = int(self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.samples.append((mhz, self.max_mhz, [bool(mask & b) for b in self.BITS]))
+            else:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                      '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
+                f = [t.strip() for t in out.strip().split(',')]
+                if len(f) >= 6:
+                    self.samples.append((float(f[0]), float(f[1]), [t.lower().startswith('active') for t in f[2:6]]))
+        except Exception:  # noqa: BLE001
+            pass
 
     def run(self):
         while not self.stop_flag:
-            try:
-                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
-                                      '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
-                f = [s.strip() for s in out.strip().split(',')]
-                if len(f) >= 7:
-                    self.samples.append(f)
-            except Exception:  # noqa: BLE001
-                pass
-            time.sleep(0.05)
+            self.sample()
+            time.sleep(0.005 if self.nv is not None else 0.05)
 
     def summary(self):
         if not self.samples:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=['unsampled'])
-        sm = sorted(float(s[0]) for s in self.samples)
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        reasons = [n for i, n in enumerate(names) if any(s[3 + i].lower().startswith('active') for s in self.samples)]
-        return dict(sm_mhz=sm[len(sm) // 2], sm_max_mhz=float(self.samples[0][1]), reasons=reasons, samples=len(sm))
+        sm = sorted(t[0] for t in self.samples)
+        reasons = [n for i, n in enumerate(self.NAMES) if any(t[2][i] for t in self.samples)]
+        return dict(sm_mhz=sm[len(sm) // 2], sm_max_mhz=self.samples[0][1], reasons=reasons, samples=len(sm), source=self.source)
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -213,6 +240,7 @@ def run_ours(args):
     for _ in range(args.steps):
         loss = step(x_d, gt_d)
     e1.record()
+    sampler.sample()          # the device is still working through the enqueued steps here: at least one sample under load
     barrier()
     calls = L.CALLS - calls0
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
