@@ -146,8 +146,10 @@ int dn_igemm_tc_supported(const dn_igemm* p);
 int dn_wgrad_tc_supported(const dn_wgrad* p);
 
 /* ---- BatchNorm2d (training) + ReLU + MaxPool2d(2,2)  (models/Disp_vgg_BN.py:137-141) ---------- */
-/* Per-channel reductions are two-stage (per-block partials in `ws`, then a tiny second kernel) so that no atomics
- * contend on C addresses.  `ws` must hold dn_reduce_ws_floats(C) floats. */
+/* Per-channel reductions write per-block partial rows into `ws`; the last block of each channel slab to arrive folds the
+ * rows in a fixed order (deterministic, double accumulation) inside the same launch - no contended atomics, no second
+ * kernel.  `ws` must hold dn_reduce_ws_floats(C) floats and be ZERO before its first use (it starts with arrival
+ * counters that every launch leaves at zero again); one workspace serves any number of launches on one stream. */
 int64_t dn_reduce_ws_floats(int C);
 /* sums[2*C] (double) = per-channel sum and sum of squares of y (overwritten). */
 int dn_bn_stats(const dn_view* y, double* sums, float* ws, void* stream);
@@ -156,6 +158,12 @@ int dn_bn_stats(const dn_view* y, double* sums, float* ws, void* stream);
 int dn_bn_finalize(const double* sums, double count, const float* gamma, const float* beta, float* running_mean,
                    float* running_var, float momentum, float eps, int training, int update_running,
                    float* mean_invstd, float* scale_shift, int C, void* stream);
+/* Training-mode statistics in ONE launch: dn_bn_stats + dn_bn_finalize(training = 1) + `num_batches_tracked += 1`
+ * (nn.BatchNorm2d.forward, torch/nn/modules/batchnorm.py; reference call sites models/Disp_vgg_BN.py:137-141).
+ * sums (double[2C]) and num_batches_tracked (int64[1]) may be NULL. */
+int dn_bn_train_stats(const dn_view* y, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                      int64_t* num_batches_tracked, float momentum, float eps, int update_running, double* sums,
+                      float* mean_invstd, float* scale_shift, float* ws, void* stream);
 /* out = pool?( act( y*scale+shift (+ residual) ) );  pool in {0,1}: 1 = 2x2/2 max pool (out is H/2 x W/2).
  * out2 (optional, same shape, may have another 16-bit dtype) receives a second copy of the result: the bf16 image of the
  * activation that the weight-gradient GEMM consumes (tcgen05 kind::f16 cannot mix fp16 and bf16 operands). */

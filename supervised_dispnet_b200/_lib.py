@@ -68,6 +68,7 @@ _SIGS = {
     'dn_reduce_ws_floats': ([_I], _I64),
     'dn_bn_stats': ([_V, _P, _P, _P], _I),
     'dn_bn_finalize': ([_P, _D, _P, _P, _P, _P, _F, _F, _I, _I, _P, _P, _I, _P], _I),
+    'dn_bn_train_stats': ([_V, _P, _P, _P, _P, _P, _F, _F, _I, _P, _P, _P, _P, _P], _I),
     'dn_bn_apply': ([_V, _P, _V, _I, _I, _V, _V, _P], _I),
     'dn_bn_bwd_reduce': ([_V, _V, _V, _P, _P, _P, _I, _I, _P, _P, _P], _I),
     'dn_bn_bwd_apply': ([_V, _V, _V, _P, _P, _P, _I, _I, _P, _D, _F, _P, _P, _V, _V, _I, _P], _I),

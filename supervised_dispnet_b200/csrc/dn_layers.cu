@@ -412,11 +412,12 @@ struct CgGeom {
   dim3 grid;
 };
 
-static CgGeom cg_geom(int C, int ch, long long pixels) {
+// max_cgb: channel groups per block (slab width); blocks_per_sm: cap of the grid in resident-block units
+static CgGeom cg_geom(int C, int ch, long long pixels, int max_cgb = 256, int blocks_per_sm = 8) {
   CgGeom g;
   g.CG = (C + ch - 1) / ch;
   int b = 1;
-  while (b < g.CG && b < 256) b <<= 1;
+  while (b < g.CG && b < max_cgb) b <<= 1;
   g.CGb = b;
   g.PL = 256 / b;
   int gy = (g.CG + b - 1) / b;
@@ -426,7 +427,7 @@ static CgGeom cg_geom(int C, int ch, long long pixels) {
   long long bx = (pixels + (long long)g.PL * 8 - 1) / ((long long)g.PL * 8);
   long long floor_blocks = bx_max < dn_num_sms() ? bx_max : dn_num_sms();
   if (bx < floor_blocks) bx = floor_blocks;
-  long long cap = (long long)dn_num_sms() * 8 / gy;
+  long long cap = (long long)dn_num_sms() * blocks_per_sm / gy;
   if (cap < 1) cap = 1;
   if (bx > cap) bx = cap;
   if (bx > 2048) bx = 2048;
@@ -494,11 +495,124 @@ __global__ void __launch_bounds__(1024) reduce_partials_kernel(const float* __re
   }
 }
 static inline int reduce_blocks(int n) { return (n + 31) / 32; }
-DN_EXPORT int64_t dn_reduce_ws_floats(int C) { return (int64_t)kMaxReduceBlocks * 2 * (C + 8); }
+
+// ---- single-launch reductions -------------------------------------------------------------------------------
+// A reduction workspace starts with kWsCounters uint32 arrival counters (zero before first use; the last block resets its
+// counter, so the buffer can be reused launch after launch on one stream), followed by the partial rows
+// [gridDim.x][ncols].  The grid's y index selects a channel slab; the last block of a slab to arrive folds the slab's
+// columns over all rows in a fixed order (deterministic, double accumulation) - no second launch.
+constexpr int kWsCounters = 256;
+DN_EXPORT int64_t dn_reduce_ws_floats(int C) { return (int64_t)kMaxReduceBlocks * 2 * (C + 8) + kWsCounters; }
+
+__device__ __forceinline__ bool dn_slab_last_block(float* ws) {
+  __shared__ int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned* ctr = reinterpret_cast<unsigned*>(ws) + blockIdx.y;
+    const unsigned t = atomicAdd(ctr, 1u);
+    s_last = (t == gridDim.x - 1) ? 1 : 0;
+    if (s_last) *ctr = 0u;
+  }
+  __syncthreads();
+  if (s_last) __threadfence();
+  return s_last != 0;
+}
+
+// fin[seg * cw + i] = sum over rows of rows[r][seg * seglen + cbeg + i], seg < nseg, i < cw.  All 256 threads of the block.
+__device__ __noinline__ void dn_slab_fold(const float* rows, int nrows, int ncols, int nseg, int seglen, int cbeg, int cw, double* fin) {
+  __shared__ double sm4[256 * 4];
+  const int tid = threadIdx.x;
+  if (((cw | cbeg | seglen | ncols) & 3) == 0) {
+    const int n4 = nseg * cw / 4;
+    const int rs4 = ncols / 4;
+    for (int base = 0; base < n4; base += 256) {
+      const int cnt = n4 - base < 256 ? n4 - base : 256;
+      const int lanes = 256 / cnt;
+      const int i4 = tid % cnt, lane = tid / cnt;
+      const int idx = (base + i4) * 4;
+      const int seg = idx / cw;
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+      if (lane < lanes) {
+        const float4* p = reinterpret_cast<const float4*>(rows + seg * seglen + cbeg + (idx - seg * cw));
+        int r = lane;
+        for (; r + 7 * lanes < nrows; r += 8 * lanes) {
+          float4 v[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) v[u] = __ldcg(p + (long long)(r + u * lanes) * rs4);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) { a0 += (double)v[u].x; a1 += (double)v[u].y; a2 += (double)v[u].z; a3 += (double)v[u].w; }
+        }
+        for (; r < nrows; r += lanes) {
+          const float4 v = __ldcg(p + (long long)r * rs4);
+          a0 += (double)v.x; a1 += (double)v.y; a2 += (double)v.z; a3 += (double)v.w;
+        }
+      }
+      sm4[tid * 4 + 0] = a0; sm4[tid * 4 + 1] = a1; sm4[tid * 4 + 2] = a2; sm4[tid * 4 + 3] = a3;
+      __syncthreads();
+      if (tid < cnt) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          double t = 0.0;
+          for (int l = 0; l < lanes; ++l) t += sm4[(l * cnt + tid) * 4 + k];
+          fin[idx + k] = t;
+        }
+      }
+      __syncthreads();
+    }
+  } else {
+    const int n = nseg * cw;
+    for (int base = 0; base < n; base += 256) {
+      const int cnt = n - base < 256 ? n - base : 256;
+      const int lanes = 256 / cnt;
+      const int i = tid % cnt, lane = tid / cnt;
+      const int idx = base + i;
+      const int seg = idx / cw;
+      double a = 0.0;
+      if (lane < lanes) {
+        const float* p = rows + seg * seglen + cbeg + (idx - seg * cw);
+        int r = lane;
+        for (; r + 3 * lanes < nrows; r += 4 * lanes) {
+          const float v0 = __ldcg(p + (long long)r * ncols), v1 = __ldcg(p + (long long)(r + lanes) * ncols);
+          const float v2 = __ldcg(p + (long long)(r + 2 * lanes) * ncols), v3 = __ldcg(p + (long long)(r + 3 * lanes) * ncols);
+          a += ((double)v0 + (double)v1) + ((double)v2 + (double)v3);
+        }
+        for (; r < nrows; r += lanes) a += (double)__ldcg(p + (long long)r * ncols);
+      }
+      sm4[tid] = a;
+      __syncthreads();
+      if (tid < cnt) {
+        double t = 0.0;
+        for (int l = 0; l < lanes; ++l) t += sm4[l * cnt + tid];
+        fin[idx] = t;
+      }
+      __syncthreads();
+    }
+  }
+}
+
+__device__ __forceinline__ void bn_scale_shift(float gamma, float beta, float mean, float invstd, float& sc, float& sh) {
+  sc = gamma * invstd;
+  sh = beta - mean * sc;
+}
+
+struct BnFinalize {        // optional tail of the statistics kernel: what bn_finalize_kernel does, per channel
+  int enabled;
+  int update_running;
+  float momentum, eps;
+  const float* gamma;
+  const float* beta;
+  float* running_mean;
+  float* running_var;
+  long long* num_batches_tracked;
+  float* mean_invstd;
+  float* scale_shift;
+};
 
 // ---- BN statistics --------------------------------------------------------------------------------
 template <int CH>
-__global__ void __launch_bounds__(256) bn_stats_kernel(dn_view y, float* __restrict__ ws, int CGb) {
+__global__ void __launch_bounds__(256) bn_stats_kernel(dn_view y, float* __restrict__ ws, int CGb, double* __restrict__ sums,
+                                                       BnFinalize fz) {
   CG_PROLOGUE(y)
   float acc[2 * CH];
 #pragma unroll
@@ -529,38 +643,83 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(dn_view y, float* __restr
     }
   }
   cg_block_reduce<2 * CH>(acc, CGb);
+  float* rows = ws + kWsCounters;
+  const int C = y.C;
   if (threadIdx.x < CGb && cvalid) {
-    float* w = ws + (long long)blockIdx.x * 2 * y.C;
+    float* w = rows + (long long)blockIdx.x * 2 * C;
 #pragma unroll
     for (int i = 0; i < CH; ++i) {
-      if (c0 + i < y.C) {
+      if (c0 + i < C) {
         w[c0 + i] = acc[i];
-        w[y.C + c0 + i] = acc[CH + i];
+        w[C + c0 + i] = acc[CH + i];
       }
     }
   }
+  if (!dn_slab_last_block(ws)) return;
+  __shared__ double fin[512];
+  const int cbeg = blockIdx.y * CGb * CH;
+  const int cw = C - cbeg < CGb * CH ? C - cbeg : CGb * CH;
+  dn_slab_fold(rows, gridDim.x, 2 * C, 2, C, cbeg, cw, fin);
+  const double count = (double)npix;
+  for (int i = threadIdx.x; i < cw; i += blockDim.x) {
+    const int c = cbeg + i;
+    const double s = fin[i], ss = fin[cw + i];
+    if (sums) { sums[c] = s; sums[C + c] = ss; }
+    if (fz.enabled) {
+      const double m = s / count;
+      double var = ss / count - m * m;
+      if (var < 0) var = 0;
+      const float mean = (float)m;
+      const float invstd = (float)(1.0 / sqrt(var + (double)fz.eps));
+      if (fz.update_running) {
+        const double unb = count > 1 ? var * count / (count - 1) : var;
+        fz.running_mean[c] = (1.f - fz.momentum) * fz.running_mean[c] + fz.momentum * mean;
+        fz.running_var[c] = (1.f - fz.momentum) * fz.running_var[c] + fz.momentum * (float)unb;
+      }
+      fz.mean_invstd[c] = mean;
+      fz.mean_invstd[C + c] = invstd;
+      float sc, sh;
+      bn_scale_shift(fz.gamma ? fz.gamma[c] : 1.f, fz.beta ? fz.beta[c] : 0.f, mean, invstd, sc, sh);
+      fz.scale_shift[c] = sc;
+      fz.scale_shift[C + c] = sh;
+    }
+  }
+  if (fz.enabled && fz.num_batches_tracked && blockIdx.y == 0 && threadIdx.x == 0) *fz.num_batches_tracked += 1;
 }
 
-DN_EXPORT int dn_bn_stats(const dn_view* y, double* sums, float* ws, void* stream) {
-  if (!y || !sums || !ws) return DN_E_ARG;
+static int bn_stats_launch(const dn_view* y, double* sums, const BnFinalize& fz, float* ws, void* stream) {
   long long npix = (long long)y->N * y->H * y->W;
-  CgGeom g;
   if (dn_vec8_ok(y)) {
-    g = cg_geom(y->C, 8, npix);
-    bn_stats_kernel<8><<<g.grid, 256, 0, dn_stream(stream)>>>(*y, ws, g.CGb);
+    CgGeom g = cg_geom(y->C, 8, npix, 8, 4);
+    if (g.grid.y > kWsCounters) return DN_E_UNSUPPORTED;
+    bn_stats_kernel<8><<<g.grid, 256, 0, dn_stream(stream)>>>(*y, ws, g.CGb, sums, fz);
   } else {
-    g = cg_geom(y->C, 1, npix);
-    bn_stats_kernel<1><<<g.grid, 256, 0, dn_stream(stream)>>>(*y, ws, g.CGb);
+    CgGeom g = cg_geom(y->C, 1, npix, 256, 3);
+    if (g.grid.y > kWsCounters) return DN_E_UNSUPPORTED;
+    bn_stats_kernel<1><<<g.grid, 256, 0, dn_stream(stream)>>>(*y, ws, g.CGb, sums, fz);
   }
-  DN_CHECK_LAUNCH();
-  reduce_partials_kernel<double><<<reduce_blocks(2 * y->C), 1024, 0, dn_stream(stream)>>>(ws, g.grid.x, 2 * y->C, sums, 1.0);
   DN_CHECK_LAUNCH();
   return 0;
 }
 
-__device__ __forceinline__ void bn_scale_shift(float gamma, float beta, float mean, float invstd, float& sc, float& sh) {
-  sc = gamma * invstd;
-  sh = beta - mean * sc;
+DN_EXPORT int dn_bn_stats(const dn_view* y, double* sums, float* ws, void* stream) {
+  if (!y || !sums || !ws) return DN_E_ARG;
+  BnFinalize fz;
+  memset(&fz, 0, sizeof(fz));
+  return bn_stats_launch(y, sums, fz, ws, stream);
+}
+
+// statistics + finalize (+ num_batches_tracked += 1) of a training-mode BatchNorm in ONE launch
+DN_EXPORT int dn_bn_train_stats(const dn_view* y, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                                int64_t* num_batches_tracked, float momentum, float eps, int update_running, double* sums,
+                                float* mean_invstd, float* scale_shift, float* ws, void* stream) {
+  if (!y || !ws || !mean_invstd || !scale_shift) return DN_E_ARG;
+  if (update_running && (!running_mean || !running_var)) return DN_E_ARG;
+  BnFinalize fz;
+  fz.enabled = 1; fz.update_running = update_running; fz.momentum = momentum; fz.eps = eps;
+  fz.gamma = gamma; fz.beta = beta; fz.running_mean = running_mean; fz.running_var = running_var;
+  fz.num_batches_tracked = (long long*)num_batches_tracked; fz.mean_invstd = mean_invstd; fz.scale_shift = scale_shift;
+  return bn_stats_launch(y, sums, fz, ws, stream);
 }
 
 __global__ void bn_finalize_kernel(const double* __restrict__ sums, double count, const float* __restrict__ gamma,
@@ -737,7 +896,8 @@ struct BnBwdPix {
 template <int CH, bool POOL>
 __global__ void __launch_bounds__(256, POOL ? 2 : 3) bn_bwd_reduce_kernel(dn_view dout, dn_view y, dn_view res, int has_res,
                                                             const float* __restrict__ mean_invstd, const float* __restrict__ gamma,
-                                                            const float* __restrict__ beta, int act, float* __restrict__ ws, int CGb) {
+                                                            const float* __restrict__ beta, int act, float* __restrict__ ws, int CGb,
+                                                            double* __restrict__ red) {
   CG_PROLOGUE(dout)
   const int C = dout.C;
   float acc[2 * CH];
@@ -796,14 +956,24 @@ __global__ void __launch_bounds__(256, POOL ? 2 : 3) bn_bwd_reduce_kernel(dn_vie
     }
   }
   cg_block_reduce<2 * CH>(acc, CGb);
+  float* rows = ws + kWsCounters;
   if (threadIdx.x < CGb && cvalid) {
-    float* wsp = ws + (long long)blockIdx.x * 2 * C;
+    float* wsp = rows + (long long)blockIdx.x * 2 * C;
 #pragma unroll
     for (int i = 0; i < CH; ++i)
       if (c0 + i < C) {
         wsp[c0 + i] = acc[i];
         wsp[C + c0 + i] = acc[CH + i];
       }
+  }
+  if (!dn_slab_last_block(ws)) return;
+  __shared__ double fin[512];
+  const int cbeg = blockIdx.y * CGb * CH;
+  const int cw = C - cbeg < CGb * CH ? C - cbeg : CGb * CH;
+  dn_slab_fold(rows, gridDim.x, 2 * C, 2, C, cbeg, cw, fin);
+  for (int i = threadIdx.x; i < cw; i += blockDim.x) {
+    red[cbeg + i] = fin[i];
+    red[C + cbeg + i] = fin[cw + i];
   }
 }
 
@@ -815,14 +985,13 @@ DN_EXPORT int dn_bn_bwd_reduce(const dn_view* dout, const dn_view* y, const dn_v
   bool vec = dn_vec8_ok(y) && dn_vec8_ok(dout) && (!residual || dn_vec8_ok(residual));
   cudaStream_t st = dn_stream(stream);
   const int ch = vec ? 8 : 1;
-  CgGeom g = cg_geom(dout->C, ch, npix);
+  CgGeom g = cg_geom(dout->C, ch, npix, vec ? 8 : 256, pool ? 2 : 3);
+  if (g.grid.y > kWsCounters) return DN_E_UNSUPPORTED;
   const int hr = residual != nullptr;
-  if (vec && pool) bn_bwd_reduce_kernel<8, true><<<g.grid, 256, 0, st>>>(*dout, *y, r, hr, mean_invstd, gamma, beta, act, ws, g.CGb);
-  else if (vec) bn_bwd_reduce_kernel<8, false><<<g.grid, 256, 0, st>>>(*dout, *y, r, hr, mean_invstd, gamma, beta, act, ws, g.CGb);
-  else if (pool) bn_bwd_reduce_kernel<1, true><<<g.grid, 256, 0, st>>>(*dout, *y, r, hr, mean_invstd, gamma, beta, act, ws, g.CGb);
-  else bn_bwd_reduce_kernel<1, false><<<g.grid, 256, 0, st>>>(*dout, *y, r, hr, mean_invstd, gamma, beta, act, ws, g.CGb);
-  DN_CHECK_LAUNCH();
-  reduce_partials_kernel<double><<<reduce_blocks(2 * dout->C), 1024, 0, st>>>(ws, g.grid.x, 2 * dout->C, red, 1.0);
+  if (vec && pool) bn_bwd_reduce_kernel<8, true><<<g.grid, 256, 0, st>>>(*dout, *y, r, hr, mean_invstd, gamma, beta, act, ws, g.CGb, red);
+  else if (vec) bn_bwd_reduce_kernel<8, false><<<g.grid, 256, 0, st>>>(*dout, *y, r, hr, mean_invstd, gamma, beta, act, ws, g.CGb, red);
+  else if (pool) bn_bwd_reduce_kernel<1, true><<<g.grid, 256, 0, st>>>(*dout, *y, r, hr, mean_invstd, gamma, beta, act, ws, g.CGb, red);
+  else bn_bwd_reduce_kernel<1, false><<<g.grid, 256, 0, st>>>(*dout, *y, r, hr, mean_invstd, gamma, beta, act, ws, g.CGb, red);
   DN_CHECK_LAUNCH();
   return 0;
 }
@@ -939,7 +1108,7 @@ DN_EXPORT int dn_bn_bwd_apply(const dn_view* dout, const dn_view* y, const dn_vi
 
 // ---- activation backward (in place) + bias gradient ---------------------------------------------------
 template <int CH>
-__global__ void __launch_bounds__(256) act_bwd_kernel(dn_view dout, dn_view out, int act, float* ws, int CGb) {
+__global__ void __launch_bounds__(256) act_bwd_kernel(dn_view dout, dn_view out, int act, float* ws, int CGb, float* dbias, float gscale) {
   CG_PROLOGUE(dout)
   float acc[CH];
 #pragma unroll
@@ -963,15 +1132,23 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(dn_view dout, dn_view out,
       for (int i = 0; i < CH; ++i) acc[i] += g[i];
     }
   }
-  if (ws) {
-    cg_block_reduce<CH>(acc, CGb);
-    if (threadIdx.x < CGb && cvalid) {
-      float* w = ws + (long long)blockIdx.x * dout.C;
+  if (!ws) return;
+  cg_block_reduce<CH>(acc, CGb);
+  float* rows = ws + kWsCounters;
+  const int C = dout.C;
+  const int ncols = (C + 3) & ~3;          // padded row pitch keeps the vector fold aligned
+  if (threadIdx.x < CGb && cvalid) {
+    float* w = rows + (long long)blockIdx.x * ncols;
 #pragma unroll
-      for (int i = 0; i < CH; ++i)
-        if (c0 + i < dout.C) w[c0 + i] = acc[i];
-    }
+    for (int i = 0; i < CH; ++i)
+      if (c0 + i < C) w[c0 + i] = acc[i];
   }
+  if (!dn_slab_last_block(ws)) return;
+  __shared__ double fin[512];
+  const int cbeg = blockIdx.y * CGb * CH;
+  const int cw = C - cbeg < CGb * CH ? C - cbeg : CGb * CH;
+  dn_slab_fold(rows, gridDim.x, ncols, 1, ncols, cbeg, cw, fin);
+  for (int i = threadIdx.x; i < cw; i += blockDim.x) dbias[cbeg + i] = (float)(fin[i] * (double)gscale);
 }
 
 DN_EXPORT int dn_act_bwd(const dn_view* dout, const dn_view* out, int act, float* dbias, float gscale, float* ws, void* stream) {
@@ -982,17 +1159,15 @@ DN_EXPORT int dn_act_bwd(const dn_view* dout, const dn_view* out, int act, float
   bool vec = dn_vec8_ok(dout) && (!out || dn_vec8_ok(out));
   CgGeom g;
   if (vec) {
-    g = cg_geom(dout->C, 8, npix);
-    act_bwd_kernel<8><<<g.grid, 256, 0, dn_stream(stream)>>>(*dout, o, act, dbias ? ws : nullptr, g.CGb);
+    g = cg_geom(dout->C, 8, npix, 8, 4);
+    if (g.grid.y > kWsCounters) return DN_E_UNSUPPORTED;
+    act_bwd_kernel<8><<<g.grid, 256, 0, dn_stream(stream)>>>(*dout, o, act, dbias ? ws : nullptr, g.CGb, dbias, gscale);
   } else {
-    g = cg_geom(dout->C, 1, npix);
-    act_bwd_kernel<1><<<g.grid, 256, 0, dn_stream(stream)>>>(*dout, o, act, dbias ? ws : nullptr, g.CGb);
+    g = cg_geom(dout->C, 1, npix, 256, 4);
+    if (g.grid.y > kWsCounters) return DN_E_UNSUPPORTED;
+    act_bwd_kernel<1><<<g.grid, 256, 0, dn_stream(stream)>>>(*dout, o, act, dbias ? ws : nullptr, g.CGb, dbias, gscale);
   }
   DN_CHECK_LAUNCH();
-  if (dbias) {
-    reduce_partials_kernel<float><<<reduce_blocks(dout->C), 1024, 0, dn_stream(stream)>>>(ws, g.grid.x, dout->C, dbias, (double)gscale);
-    DN_CHECK_LAUNCH();
-  }
   return 0;
 }
 
@@ -1544,17 +1719,19 @@ DN_EXPORT int dn_head_conv_bwd(const dn_view* x, const float* w, const dn_view* 
   CgGeom g = cg_geom(x->C, ch, npix);
   if (g.grid.y != 1) return DN_E_UNSUPPORTED;
   const int n = 9 * x->C + 1;
-  if ((long long)g.grid.x * n > dn_reduce_ws_floats(x->C)) g.grid.x = (unsigned)(dn_reduce_ws_floats(x->C) / n);
+  float* rows = ws + kWsCounters;        // the head of the workspace holds the arrival counters of the single-launch reductions
+  const long long cap = dn_reduce_ws_floats(x->C) - kWsCounters;
+  if ((long long)g.grid.x * n > cap) g.grid.x = (unsigned)(cap / n);
   const size_t sm = sizeof(float) * (18 * x->C + 1);
   cudaStream_t st = dn_stream(stream);
-  if (vec) head_conv_bwd_kernel<8><<<g.grid, 256, sm, st>>>(*x, w, *dz, *gx, gx_accumulate, ws, g.CGb);
-  else head_conv_bwd_kernel<1><<<g.grid, 256, sm, st>>>(*x, w, *dz, *gx, gx_accumulate, ws, g.CGb);
+  if (vec) head_conv_bwd_kernel<8><<<g.grid, 256, sm, st>>>(*x, w, *dz, *gx, gx_accumulate, rows, g.CGb);
+  else head_conv_bwd_kernel<1><<<g.grid, 256, sm, st>>>(*x, w, *dz, *gx, gx_accumulate, rows, g.CGb);
   DN_CHECK_LAUNCH();
   // second stage: [blocks][9C+1] -> gw (torch layout [1][C][3][3]) and gb; both scaled by gscale
-  reduce_partials_kernel<float><<<reduce_blocks(n - 1), 1024, 0, st>>>(ws, g.grid.x, n, gw, (double)gscale, n - 1);
+  reduce_partials_kernel<float><<<reduce_blocks(n - 1), 1024, 0, st>>>(rows, g.grid.x, n, gw, (double)gscale, n - 1);
   DN_CHECK_LAUNCH();
   if (gb) {
-    reduce_partials_kernel<float><<<1, 1024, 0, st>>>(ws + (n - 1), g.grid.x, n, gb, (double)gscale, 1);
+    reduce_partials_kernel<float><<<1, 1024, 0, st>>>(rows + (n - 1), g.grid.x, n, gb, (double)gscale, 1);
     DN_CHECK_LAUNCH();
   }
   return 0;

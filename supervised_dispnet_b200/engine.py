@@ -485,11 +485,13 @@ class BNOp(Op):
         st = plan.stream
         g, b = plan.param(self.name + '.weight'), plan.param(self.name + '.bias')
         rm, rv = plan.buffer(self.name + '.running_mean'), plan.buffer(self.name + '.running_var')
-        if plan.training:
-            L.call('dn_bn_stats', self.y.ref(), L.ptr(self.sums), L.ptr(plan.reduce_ws(self.y.C)), st)
-            plan.buffer(self.name + '.num_batches_tracked').add_(1)
-        L.call('dn_bn_finalize', L.ptr(self.sums), self.count, L.ptr(g), L.ptr(b), L.ptr(rm), L.ptr(rv), 0.1, 1e-5,
-               int(plan.training), 1, L.ptr(self.mean_invstd), L.ptr(self.scale_shift), self.y.C, st)
+        if plan.training:      # statistics, finalize and num_batches_tracked += 1 in one launch
+            L.call('dn_bn_train_stats', self.y.ref(), L.ptr(g), L.ptr(b), L.ptr(rm), L.ptr(rv),
+                   L.ptr(plan.buffer(self.name + '.num_batches_tracked')), 0.1, 1e-5, 1, None, L.ptr(self.mean_invstd),
+                   L.ptr(self.scale_shift), L.ptr(plan.reduce_ws(self.y.C)), st)
+        else:
+            L.call('dn_bn_finalize', L.ptr(self.sums), self.count, L.ptr(g), L.ptr(b), L.ptr(rm), L.ptr(rv), 0.1, 1e-5,
+                   0, 0, L.ptr(self.mean_invstd), L.ptr(self.scale_shift), self.y.C, st)
         if self.out is not None:
             L.call('dn_bn_apply', self.y.ref(), L.ptr(self.scale_shift), self.res.ref() if self.res else None, self.act,
                    self.pool, self.out.ref(), self.out2.ref() if self.out2 is not None else None, st)
@@ -707,7 +709,7 @@ class Plan:
     def reduce_ws(self, Cc):
         need = int(L.lib().dn_reduce_ws_floats(Cc))
         if self._ws is None or self._ws.numel() < need:
-            self._ws = torch.empty(need, dtype=torch.float32, device=self.device)
+            self._ws = torch.zeros(need, dtype=torch.float32, device=self.device)     # arrival counters start at zero
         return self._ws
 
     # ---- run-time lookups
