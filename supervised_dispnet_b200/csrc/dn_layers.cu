@@ -453,14 +453,18 @@ __device__ __forceinline__ void cg_block_reduce(float* vals, int CGb) {
 #pragma unroll
   for (int i = 0; i < NV; ++i) red[i * 256 + tid] = vals[i];
   __syncthreads();
+  // CGb * NV column sums spread over all threads (a column is read and overwritten by its owner only); fixed summation order
   const int PLn = 256 / CGb;
+  for (int o = tid; o < CGb * NV; o += 256) {
+    const int i = o / CGb, c = o - i * CGb;
+    float s = 0.f;
+    for (int l = 0; l < PLn; ++l) s += red[i * 256 + l * CGb + c];
+    red[i * 256 + c] = s;
+  }
+  __syncthreads();
   if (tid < CGb) {
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      float s = 0.f;
-      for (int l = 0; l < PLn; ++l) s += red[i * 256 + l * CGb + tid];
-      vals[i] = s;
-    }
+    for (int i = 0; i < NV; ++i) vals[i] = red[i * 256 + tid];
   }
   __syncthreads();
 }
@@ -596,6 +600,9 @@ __device__ __forceinline__ void bn_scale_shift(float gamma, float beta, float me
   sh = beta - mean * sc;
 }
 
+// DN_BN_FAST=0 routes everything through the generic CG walkers (A/B comparisons)
+static const bool g_bn_fast = []() { const char* e = getenv("DN_BN_FAST"); return !(e && e[0] == '0'); }();
+
 struct BnFinalize {        // optional tail of the statistics kernel: what bn_finalize_kernel does, per channel
   int enabled;
   int update_running;
@@ -608,6 +615,53 @@ struct BnFinalize {        // optional tail of the statistics kernel: what bn_fi
   float* mean_invstd;
   float* scale_shift;
 };
+
+// everything after the per-thread accumulation of the statistics kernels: block reduce, partial row, slab fold, finalize
+template <int CH>
+__device__ __forceinline__ void bn_stats_tail(float* acc, int C, double count, float* __restrict__ ws, int CGb, double* __restrict__ sums,
+                                              const BnFinalize& fz, bool cvalid, int c0) {
+  cg_block_reduce<2 * CH>(acc, CGb);
+  float* rows = ws + kWsCounters;
+  if (threadIdx.x < CGb && cvalid) {
+    float* w = rows + (long long)blockIdx.x * 2 * C;
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+      if (c0 + i < C) {
+        w[c0 + i] = acc[i];
+        w[C + c0 + i] = acc[CH + i];
+      }
+    }
+  }
+  if (!dn_slab_last_block(ws)) return;
+  __shared__ double fin[512];
+  const int cbeg = blockIdx.y * CGb * CH;
+  const int cw = C - cbeg < CGb * CH ? C - cbeg : CGb * CH;
+  dn_slab_fold(rows, gridDim.x, 2 * C, 2, C, cbeg, cw, fin);
+  for (int i = threadIdx.x; i < cw; i += blockDim.x) {
+    const int c = cbeg + i;
+    const double s = fin[i], ss = fin[cw + i];
+    if (sums) { sums[c] = s; sums[C + c] = ss; }
+    if (fz.enabled) {
+      const double m = s / count;
+      double var = ss / count - m * m;
+      if (var < 0) var = 0;
+      const float mean = (float)m;
+      const float invstd = (float)(1.0 / sqrt(var + (double)fz.eps));
+      if (fz.update_running) {
+        const double unb = count > 1 ? var * count / (count - 1) : var;
+        fz.running_mean[c] = (1.f - fz.momentum) * fz.running_mean[c] + fz.momentum * mean;
+        fz.running_var[c] = (1.f - fz.momentum) * fz.running_var[c] + fz.momentum * (float)unb;
+      }
+      fz.mean_invstd[c] = mean;
+      fz.mean_invstd[C + c] = invstd;
+      float sc, sh;
+      bn_scale_shift(fz.gamma ? fz.gamma[c] : 1.f, fz.beta ? fz.beta[c] : 0.f, mean, invstd, sc, sh);
+      fz.scale_shift[c] = sc;
+      fz.scale_shift[C + c] = sh;
+    }
+  }
+  if (fz.enabled && fz.num_batches_tracked && blockIdx.y == 0 && threadIdx.x == 0) *fz.num_batches_tracked += 1;
+}
 
 // ---- BN statistics --------------------------------------------------------------------------------
 template <int CH>
@@ -642,57 +696,25 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(dn_view y, float* __restr
         }
     }
   }
-  cg_block_reduce<2 * CH>(acc, CGb);
-  float* rows = ws + kWsCounters;
-  const int C = y.C;
-  if (threadIdx.x < CGb && cvalid) {
-    float* w = rows + (long long)blockIdx.x * 2 * C;
-#pragma unroll
-    for (int i = 0; i < CH; ++i) {
-      if (c0 + i < C) {
-        w[c0 + i] = acc[i];
-        w[C + c0 + i] = acc[CH + i];
-      }
-    }
-  }
-  if (!dn_slab_last_block(ws)) return;
-  __shared__ double fin[512];
-  const int cbeg = blockIdx.y * CGb * CH;
-  const int cw = C - cbeg < CGb * CH ? C - cbeg : CGb * CH;
-  dn_slab_fold(rows, gridDim.x, 2 * C, 2, C, cbeg, cw, fin);
-  const double count = (double)npix;
-  for (int i = threadIdx.x; i < cw; i += blockDim.x) {
-    const int c = cbeg + i;
-    const double s = fin[i], ss = fin[cw + i];
-    if (sums) { sums[c] = s; sums[C + c] = ss; }
-    if (fz.enabled) {
-      const double m = s / count;
-      double var = ss / count - m * m;
-      if (var < 0) var = 0;
-      const float mean = (float)m;
-      const float invstd = (float)(1.0 / sqrt(var + (double)fz.eps));
-      if (fz.update_running) {
-        const double unb = count > 1 ? var * count / (count - 1) : var;
-        fz.running_mean[c] = (1.f - fz.momentum) * fz.running_mean[c] + fz.momentum * mean;
-        fz.running_var[c] = (1.f - fz.momentum) * fz.running_var[c] + fz.momentum * (float)unb;
-      }
-      fz.mean_invstd[c] = mean;
-      fz.mean_invstd[C + c] = invstd;
-      float sc, sh;
-      bn_scale_shift(fz.gamma ? fz.gamma[c] : 1.f, fz.beta ? fz.beta[c] : 0.f, mean, invstd, sc, sh);
-      fz.scale_shift[c] = sc;
-      fz.scale_shift[C + c] = sh;
-    }
-  }
-  if (fz.enabled && fz.num_batches_tracked && blockIdx.y == 0 && threadIdx.x == 0) *fz.num_batches_tracked += 1;
+  bn_stats_tail<CH>(acc, y.C, (double)npix, ws, CGb, sums, fz, cvalid, c0);
 }
+
+// forward declaration of the tail used by the fast backward-reduce kernel (defined with the generic kernel below)
+template <int CH>
+__device__ __forceinline__ void bn_bwd_reduce_tail(float* acc, int C, float* __restrict__ ws, int CGb, double* __restrict__ red,
+                                                   bool cvalid, int c0);
+template <int CH>
+__device__ __forceinline__ void act_bwd_tail(float* acc, int C, float* __restrict__ ws, int CGb, float* __restrict__ dbias, float gscale,
+                                             bool cvalid, int c0);
+#include "dn_bn_fast.cuh"
 
 static int bn_stats_launch(const dn_view* y, double* sums, const BnFinalize& fz, float* ws, void* stream) {
   long long npix = (long long)y->N * y->H * y->W;
   if (dn_vec8_ok(y)) {
     CgGeom g = cg_geom(y->C, 8, npix, 8, 4);
     if (g.grid.y > kWsCounters) return DN_E_UNSUPPORTED;
-    bn_stats_kernel<8><<<g.grid, 256, 0, dn_stream(stream)>>>(*y, ws, g.CGb, sums, fz);
+    if (dn_lin(y) && npix < (1ll << 31) && g_bn_fast) bnf_stats_kernel<<<g.grid, 256, 0, dn_stream(stream)>>>(*y, ws, g.CGb, sums, fz);
+    else bn_stats_kernel<8><<<g.grid, 256, 0, dn_stream(stream)>>>(*y, ws, g.CGb, sums, fz);
   } else {
     CgGeom g = cg_geom(y->C, 1, npix, 256, 3);
     if (g.grid.y > kWsCounters) return DN_E_UNSUPPORTED;
@@ -823,7 +845,13 @@ DN_EXPORT int dn_bn_apply(const dn_view* y, const float* scale_shift, const dn_v
   dn_view o2 = out2 ? *out2 : *out;
   if (out2 && (out2->C != out->C || out2->H != out->H || out2->W != out->W || out2->N != out->N)) return DN_E_ARG;
   bool vec = dn_vec8_ok(y) && dn_vec8_ok(out) && (!residual || dn_vec8_ok(residual)) && (!out2 || dn_vec8_ok(out2));
-  if (vec) {
+  const bool fast = vec && g_bn_fast && !residual && dn_lin(y) && dn_lin(out) && (!out2 || dn_lin(out2)) && npix < (1ll << 31) &&
+                    (!pool || (y->H == 2 * out->H && y->W >= 2 * out->W));
+  if (fast) {
+    CgGeom g = cg_geom(out->C, 8, npix, 256, 4);
+    if (pool) bnf_apply_kernel<true><<<g.grid, 256, 0, dn_stream(stream)>>>(*y, scale_shift, act, *out, o2, out2 != nullptr, g.CGb);
+    else bnf_apply_kernel<false><<<g.grid, 256, 0, dn_stream(stream)>>>(*y, scale_shift, act, *out, o2, out2 != nullptr, g.CGb);
+  } else if (vec) {
     CgGeom g = cg_geom(out->C, 8, npix);
     bn_apply_kernel<8><<<g.grid, 256, 0, dn_stream(stream)>>>(*y, scale_shift, r, residual != nullptr, act, pool, *out, o2, out2 != nullptr, g.CGb);
   } else {
@@ -893,6 +921,31 @@ struct BnBwdPix {
   }
 };
 
+template <int CH>
+__device__ __forceinline__ void bn_bwd_reduce_tail(float* acc, int C, float* __restrict__ ws, int CGb, double* __restrict__ red,
+                                                   bool cvalid, int c0) {
+  cg_block_reduce<2 * CH>(acc, CGb);
+  float* rows = ws + kWsCounters;
+  if (threadIdx.x < CGb && cvalid) {
+    float* wsp = rows + (long long)blockIdx.x * 2 * C;
+#pragma unroll
+    for (int i = 0; i < CH; ++i)
+      if (c0 + i < C) {
+        wsp[c0 + i] = acc[i];
+        wsp[C + c0 + i] = acc[CH + i];
+      }
+  }
+  if (!dn_slab_last_block(ws)) return;
+  __shared__ double fin[512];
+  const int cbeg = blockIdx.y * CGb * CH;
+  const int cw = C - cbeg < CGb * CH ? C - cbeg : CGb * CH;
+  dn_slab_fold(rows, gridDim.x, 2 * C, 2, C, cbeg, cw, fin);
+  for (int i = threadIdx.x; i < cw; i += blockDim.x) {
+    red[cbeg + i] = fin[i];
+    red[C + cbeg + i] = fin[cw + i];
+  }
+}
+
 template <int CH, bool POOL>
 __global__ void __launch_bounds__(256, POOL ? 2 : 3) bn_bwd_reduce_kernel(dn_view dout, dn_view y, dn_view res, int has_res,
                                                             const float* __restrict__ mean_invstd, const float* __restrict__ gamma,
@@ -955,26 +1008,7 @@ __global__ void __launch_bounds__(256, POOL ? 2 : 3) bn_bwd_reduce_kernel(dn_vie
       }
     }
   }
-  cg_block_reduce<2 * CH>(acc, CGb);
-  float* rows = ws + kWsCounters;
-  if (threadIdx.x < CGb && cvalid) {
-    float* wsp = rows + (long long)blockIdx.x * 2 * C;
-#pragma unroll
-    for (int i = 0; i < CH; ++i)
-      if (c0 + i < C) {
-        wsp[c0 + i] = acc[i];
-        wsp[C + c0 + i] = acc[CH + i];
-      }
-  }
-  if (!dn_slab_last_block(ws)) return;
-  __shared__ double fin[512];
-  const int cbeg = blockIdx.y * CGb * CH;
-  const int cw = C - cbeg < CGb * CH ? C - cbeg : CGb * CH;
-  dn_slab_fold(rows, gridDim.x, 2 * C, 2, C, cbeg, cw, fin);
-  for (int i = threadIdx.x; i < cw; i += blockDim.x) {
-    red[cbeg + i] = fin[i];
-    red[C + cbeg + i] = fin[cw + i];
-  }
+  bn_bwd_reduce_tail<CH>(acc, C, ws, CGb, red, cvalid, c0);
 }
 
 DN_EXPORT int dn_bn_bwd_reduce(const dn_view* dout, const dn_view* y, const dn_view* residual, const float* mean_invstd,
@@ -985,10 +1019,14 @@ DN_EXPORT int dn_bn_bwd_reduce(const dn_view* dout, const dn_view* y, const dn_v
   bool vec = dn_vec8_ok(y) && dn_vec8_ok(dout) && (!residual || dn_vec8_ok(residual));
   cudaStream_t st = dn_stream(stream);
   const int ch = vec ? 8 : 1;
-  CgGeom g = cg_geom(dout->C, ch, npix, vec ? 8 : 256, pool ? 2 : 3);
+  CgGeom g = cg_geom(dout->C, ch, npix, vec ? 8 : 256, 3);
   if (g.grid.y > kWsCounters) return DN_E_UNSUPPORTED;
   const int hr = residual != nullptr;
-  if (vec && pool) bn_bwd_reduce_kernel<8, true><<<g.grid, 256, 0, st>>>(*dout, *y, r, hr, mean_invstd, gamma, beta, act, ws, g.CGb, red);
+  const bool fast = vec && g_bn_fast && !residual && dn_lin(dout) && dn_lin(y) && npix < (1ll << 31) &&
+                    (!pool || (y->H == 2 * dout->H && y->W >= 2 * dout->W));
+  if (fast && pool) bnf_bwd_reduce_kernel<true><<<g.grid, 256, 0, st>>>(*dout, *y, mean_invstd, gamma, beta, act, ws, g.CGb, red);
+  else if (fast) bnf_bwd_reduce_kernel<false><<<g.grid, 256, 0, st>>>(*dout, *y, mean_invstd, gamma, beta, act, ws, g.CGb, red);
+  else if (vec && pool) bn_bwd_reduce_kernel<8, true><<<g.grid, 256, 0, st>>>(*dout, *y, r, hr, mean_invstd, gamma, beta, act, ws, g.CGb, red);
   else if (vec) bn_bwd_reduce_kernel<8, false><<<g.grid, 256, 0, st>>>(*dout, *y, r, hr, mean_invstd, gamma, beta, act, ws, g.CGb, red);
   else if (pool) bn_bwd_reduce_kernel<1, true><<<g.grid, 256, 0, st>>>(*dout, *y, r, hr, mean_invstd, gamma, beta, act, ws, g.CGb, red);
   else bn_bwd_reduce_kernel<1, false><<<g.grid, 256, 0, st>>>(*dout, *y, r, hr, mean_invstd, gamma, beta, act, ws, g.CGb, red);
@@ -1097,13 +1135,39 @@ DN_EXPORT int dn_bn_bwd_apply(const dn_view* dout, const dn_view* y, const dn_vi
 #define BN_BWD_APPLY(CHV, PV)                                                                                              \
   bn_bwd_apply_kernel<CHV, PV><<<g.grid, 256, 0, st>>>(*dout, *y, r, hr, mean_invstd, gamma, beta, act, red, count, gscale, \
                                                        dgamma, dbeta, *dy, dr, hd, dres_accumulate, g.CGb)
-  if (vec && pool) BN_BWD_APPLY(8, true);
+  const bool fast = vec && g_bn_fast && !residual && !dres && dn_lin(dout) && dn_lin(y) && dn_lin(dy) && npix < (1ll << 31) &&
+                    (!pool || (y->H == 2 * dout->H && y->W >= 2 * dout->W));
+  if (fast) {
+    CgGeom gf = cg_geom(dout->C, 8, npix, 256, 3);
+    if (pool) bnf_bwd_apply_kernel<true><<<gf.grid, 256, 0, st>>>(*dout, *y, mean_invstd, gamma, beta, act, red, count, gscale, dgamma, dbeta, *dy, gf.CGb);
+    else bnf_bwd_apply_kernel<false><<<gf.grid, 256, 0, st>>>(*dout, *y, mean_invstd, gamma, beta, act, red, count, gscale, dgamma, dbeta, *dy, gf.CGb);
+  } else if (vec && pool) BN_BWD_APPLY(8, true);
   else if (vec) BN_BWD_APPLY(8, false);
   else if (pool) BN_BWD_APPLY(1, true);
   else BN_BWD_APPLY(1, false);
 #undef BN_BWD_APPLY
   DN_CHECK_LAUNCH();
   return 0;
+}
+
+template <int CH>
+__device__ __forceinline__ void act_bwd_tail(float* acc, int C, float* __restrict__ ws, int CGb, float* __restrict__ dbias, float gscale,
+                                             bool cvalid, int c0) {
+  cg_block_reduce<CH>(acc, CGb);
+  float* rows = ws + kWsCounters;
+  const int ncols = (C + 3) & ~3;          // padded row pitch keeps the vector fold aligned
+  if (threadIdx.x < CGb && cvalid) {
+    float* w = rows + (long long)blockIdx.x * ncols;
+#pragma unroll
+    for (int i = 0; i < CH; ++i)
+      if (c0 + i < C) w[c0 + i] = acc[i];
+  }
+  if (!dn_slab_last_block(ws)) return;
+  __shared__ double fin[512];
+  const int cbeg = blockIdx.y * CGb * CH;
+  const int cw = C - cbeg < CGb * CH ? C - cbeg : CGb * CH;
+  dn_slab_fold(rows, gridDim.x, ncols, 1, ncols, cbeg, cw, fin);
+  for (int i = threadIdx.x; i < cw; i += blockDim.x) dbias[cbeg + i] = (float)(fin[i] * (double)gscale);
 }
 
 // ---- activation backward (in place) + bias gradient ---------------------------------------------------
@@ -1133,22 +1197,7 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(dn_view dout, dn_view out,
     }
   }
   if (!ws) return;
-  cg_block_reduce<CH>(acc, CGb);
-  float* rows = ws + kWsCounters;
-  const int C = dout.C;
-  const int ncols = (C + 3) & ~3;          // padded row pitch keeps the vector fold aligned
-  if (threadIdx.x < CGb && cvalid) {
-    float* w = rows + (long long)blockIdx.x * ncols;
-#pragma unroll
-    for (int i = 0; i < CH; ++i)
-      if (c0 + i < C) w[c0 + i] = acc[i];
-  }
-  if (!dn_slab_last_block(ws)) return;
-  __shared__ double fin[512];
-  const int cbeg = blockIdx.y * CGb * CH;
-  const int cw = C - cbeg < CGb * CH ? C - cbeg : CGb * CH;
-  dn_slab_fold(rows, gridDim.x, ncols, 1, ncols, cbeg, cw, fin);
-  for (int i = threadIdx.x; i < cw; i += blockDim.x) dbias[cbeg + i] = (float)(fin[i] * (double)gscale);
+  act_bwd_tail<CH>(acc, dout.C, ws, CGb, dbias, gscale, cvalid, c0);
 }
 
 DN_EXPORT int dn_act_bwd(const dn_view* dout, const dn_view* out, int act, float* dbias, float gscale, float* ws, void* stream) {
@@ -1161,7 +1210,10 @@ DN_EXPORT int dn_act_bwd(const dn_view* dout, const dn_view* out, int act, float
   if (vec) {
     g = cg_geom(dout->C, 8, npix, 8, 4);
     if (g.grid.y > kWsCounters) return DN_E_UNSUPPORTED;
-    act_bwd_kernel<8><<<g.grid, 256, 0, dn_stream(stream)>>>(*dout, o, act, dbias ? ws : nullptr, g.CGb, dbias, gscale);
+    if (g_bn_fast && dn_lin(dout) && (!out || dn_lin(out)) && npix < (1ll << 31))
+      actf_bwd_kernel<<<g.grid, 256, 0, dn_stream(stream)>>>(*dout, o, act, dbias ? ws : nullptr, g.CGb, dbias, gscale);
+    else
+      act_bwd_kernel<8><<<g.grid, 256, 0, dn_stream(stream)>>>(*dout, o, act, dbias ? ws : nullptr, g.CGb, dbias, gscale);
   } else {
     g = cg_geom(dout->C, 1, npix, 256, 4);
     if (g.grid.y > kWsCounters) return DN_E_UNSUPPORTED;
