@@ -86,7 +86,9 @@ __device__ __forceinline__ void load_sc_sh(const float* __restrict__ mean_invstd
   const int C = (view_for_dims).C;                                                          \
   const bool cvalid = c0 < C;                                                               \
   const unsigned npix = (unsigned)(view_for_dims).N * (view_for_dims).H * (view_for_dims).W; \
-  const unsigned stride = gridDim.x * PLn;
+  const unsigned stride = gridDim.x * PLn;                                                  \
+  dn_pdl_trigger();                                                                         \
+  dn_pdl_wait();
 
 // ---- statistics ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256, 4) bnf_stats_kernel(dn_view y, float* __restrict__ ws, int CGb, double* __restrict__ sums,
@@ -99,12 +101,12 @@ __global__ void __launch_bounds__(256, 4) bnf_stats_kernel(dn_view y, float* __r
     const char* base = (const char*)y.ptr + (long long)c0 * 2;
     const long long pitch = y.sW * 2;
     unsigned px = blockIdx.x * PLn + pl;
-    for (; px + 3 * stride < npix && px + 3 * stride >= px; px += 4 * stride) {
-      uint4 r[4];
+    for (; px + 7 * stride < npix && px + 7 * stride >= px; px += 8 * stride) {      // 8 x 16 bytes in flight per thread
+      uint4 r[8];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) r[u] = ld16(base + (long long)(px + u * stride) * pitch);
+      for (int u = 0; u < 8; ++u) r[u] = ld16(base + (long long)(px + u * stride) * pitch);
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < 8; ++u) {
         float2 f[4];
         cvt8(r[u], y.dtype, f);
 #pragma unroll

@@ -4,6 +4,8 @@
 #include <cuda_fp16.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
 #include "../../include/dispnet_b200.h"
 
 #define DN_CHECK_LAUNCH()                        \
@@ -15,6 +17,40 @@
 #define DN_EXPORT extern "C" __attribute__((visibility("default")))
 
 static inline cudaStream_t dn_stream(void* s) { return (cudaStream_t)s; }
+
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------
+// Every kernel launched through dn_launch() begins with dn_pdl_trigger() (lets the NEXT kernel of the stream / graph start
+// being scheduled as soon as all blocks of this one have started) and runs dn_pdl_wait() after its private set-up (barrier
+// init, TMEM allocation, constants) and before its first access to global memory that an earlier kernel may still be
+// reading or writing: the wait returns when the preceding grid has completed and flushed.  The launch latency, block
+// scheduling ramp and prologue of kernel i+1 thus overlap the tail of kernel i (~300 launches per training step).
+// DN_PDL=0 launches the same kernels with plain stream serialisation.
+__device__ __forceinline__ void dn_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void dn_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+static inline bool dn_pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DN_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
+template <typename... KArgs, typename... Args>
+static inline void dn_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr;
+  memset(&attr, 0, sizeof(attr));
+  attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr.val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = &attr;
+  cfg.numAttrs = dn_pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 
 // ---- dtype-erased scalar access (generic kernels; the hot kernels use vector paths) -------------
 __device__ __forceinline__ float dn_ld(const void* p, int dt, long long i) {

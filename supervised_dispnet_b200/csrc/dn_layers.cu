@@ -100,6 +100,8 @@ DN_EXPORT int dn_unpack_wgrad(const float* src, float* dst, int T, int R, int Cc
 // k*k-float runs ([..][kh][kw] is innermost in both nn.Conv2d and nn.ConvTranspose2d weights) and every packed plane is
 // written (read) with unit stride across the warp
 __global__ void __launch_bounds__(256) pack_jobs_kernel(const dn_pack_job* __restrict__ jobs) {
+  dn_pdl_trigger();
+  dn_pdl_wait();
   const dn_pack_job j = jobs[blockIdx.y];
   const unsigned k = (unsigned)j.k;
   if (!j.unpack) {
@@ -132,7 +134,7 @@ __global__ void __launch_bounds__(256) pack_jobs_kernel(const dn_pack_job* __res
 
 DN_EXPORT int dn_pack_jobs(const dn_pack_job* jobs, int njobs, void* stream) {
   if (!jobs || njobs < 1) return DN_E_ARG;
-  pack_jobs_kernel<<<dim3(512, njobs), 256, 0, dn_stream(stream)>>>(jobs);
+  dn_launch(pack_jobs_kernel, dim3(512, njobs), dim3(256), 0, dn_stream(stream), jobs);
   DN_CHECK_LAUNCH();
   return 0;
 }
@@ -713,7 +715,7 @@ static int bn_stats_launch(const dn_view* y, double* sums, const BnFinalize& fz,
   if (dn_vec8_ok(y)) {
     CgGeom g = cg_geom(y->C, 8, npix, 8, 4);
     if (g.grid.y > kWsCounters) return DN_E_UNSUPPORTED;
-    if (dn_lin(y) && npix < (1ll << 31) && g_bn_fast) bnf_stats_kernel<<<g.grid, 256, 0, dn_stream(stream)>>>(*y, ws, g.CGb, sums, fz);
+    if (dn_lin(y) && npix < (1ll << 31) && g_bn_fast) dn_launch(bnf_stats_kernel, g.grid, dim3(256), 0, dn_stream(stream), *y, ws, g.CGb, sums, fz);
     else bn_stats_kernel<8><<<g.grid, 256, 0, dn_stream(stream)>>>(*y, ws, g.CGb, sums, fz);
   } else {
     CgGeom g = cg_geom(y->C, 1, npix, 256, 3);
@@ -849,8 +851,8 @@ DN_EXPORT int dn_bn_apply(const dn_view* y, const float* scale_shift, const dn_v
                     (!pool || (y->H == 2 * out->H && y->W >= 2 * out->W));
   if (fast) {
     CgGeom g = cg_geom(out->C, 8, npix, 256, 4);
-    if (pool) bnf_apply_kernel<true><<<g.grid, 256, 0, dn_stream(stream)>>>(*y, scale_shift, act, *out, o2, out2 != nullptr, g.CGb);
-    else bnf_apply_kernel<false><<<g.grid, 256, 0, dn_stream(stream)>>>(*y, scale_shift, act, *out, o2, out2 != nullptr, g.CGb);
+    if (pool) dn_launch(bnf_apply_kernel<true>, g.grid, dim3(256), 0, dn_stream(stream), *y, scale_shift, act, *out, o2, out2 != nullptr, g.CGb);
+    else dn_launch(bnf_apply_kernel<false>, g.grid, dim3(256), 0, dn_stream(stream), *y, scale_shift, act, *out, o2, out2 != nullptr, g.CGb);
   } else if (vec) {
     CgGeom g = cg_geom(out->C, 8, npix);
     bn_apply_kernel<8><<<g.grid, 256, 0, dn_stream(stream)>>>(*y, scale_shift, r, residual != nullptr, act, pool, *out, o2, out2 != nullptr, g.CGb);
@@ -1024,8 +1026,8 @@ DN_EXPORT int dn_bn_bwd_reduce(const dn_view* dout, const dn_view* y, const dn_v
   const int hr = residual != nullptr;
   const bool fast = vec && g_bn_fast && !residual && dn_lin(dout) && dn_lin(y) && npix < (1ll << 31) &&
                     (!pool || (y->H == 2 * dout->H && y->W >= 2 * dout->W));
-  if (fast && pool) bnf_bwd_reduce_kernel<true><<<g.grid, 256, 0, st>>>(*dout, *y, mean_invstd, gamma, beta, act, ws, g.CGb, red);
-  else if (fast) bnf_bwd_reduce_kernel<false><<<g.grid, 256, 0, st>>>(*dout, *y, mean_invstd, gamma, beta, act, ws, g.CGb, red);
+  if (fast && pool) dn_launch(bnf_bwd_reduce_kernel<true>, g.grid, dim3(256), 0, st, *dout, *y, mean_invstd, gamma, beta, act, ws, g.CGb, red);
+  else if (fast) dn_launch(bnf_bwd_reduce_kernel<false>, g.grid, dim3(256), 0, st, *dout, *y, mean_invstd, gamma, beta, act, ws, g.CGb, red);
   else if (vec && pool) bn_bwd_reduce_kernel<8, true><<<g.grid, 256, 0, st>>>(*dout, *y, r, hr, mean_invstd, gamma, beta, act, ws, g.CGb, red);
   else if (vec) bn_bwd_reduce_kernel<8, false><<<g.grid, 256, 0, st>>>(*dout, *y, r, hr, mean_invstd, gamma, beta, act, ws, g.CGb, red);
   else if (pool) bn_bwd_reduce_kernel<1, true><<<g.grid, 256, 0, st>>>(*dout, *y, r, hr, mean_invstd, gamma, beta, act, ws, g.CGb, red);
@@ -1139,8 +1141,8 @@ DN_EXPORT int dn_bn_bwd_apply(const dn_view* dout, const dn_view* y, const dn_vi
                     (!pool || (y->H == 2 * dout->H && y->W >= 2 * dout->W));
   if (fast) {
     CgGeom gf = cg_geom(dout->C, 8, npix, 256, 3);
-    if (pool) bnf_bwd_apply_kernel<true><<<gf.grid, 256, 0, st>>>(*dout, *y, mean_invstd, gamma, beta, act, red, count, gscale, dgamma, dbeta, *dy, gf.CGb);
-    else bnf_bwd_apply_kernel<false><<<gf.grid, 256, 0, st>>>(*dout, *y, mean_invstd, gamma, beta, act, red, count, gscale, dgamma, dbeta, *dy, gf.CGb);
+    if (pool) dn_launch(bnf_bwd_apply_kernel<true>, gf.grid, dim3(256), 0, st, *dout, *y, mean_invstd, gamma, beta, act, red, count, gscale, dgamma, dbeta, *dy, gf.CGb);
+    else dn_launch(bnf_bwd_apply_kernel<false>, gf.grid, dim3(256), 0, st, *dout, *y, mean_invstd, gamma, beta, act, red, count, gscale, dgamma, dbeta, *dy, gf.CGb);
   } else if (vec && pool) BN_BWD_APPLY(8, true);
   else if (vec) BN_BWD_APPLY(8, false);
   else if (pool) BN_BWD_APPLY(1, true);
@@ -1211,7 +1213,7 @@ DN_EXPORT int dn_act_bwd(const dn_view* dout, const dn_view* out, int act, float
     g = cg_geom(dout->C, 8, npix, 8, 4);
     if (g.grid.y > kWsCounters) return DN_E_UNSUPPORTED;
     if (g_bn_fast && dn_lin(dout) && (!out || dn_lin(out)) && npix < (1ll << 31))
-      actf_bwd_kernel<<<g.grid, 256, 0, dn_stream(stream)>>>(*dout, o, act, dbias ? ws : nullptr, g.CGb, dbias, gscale);
+      dn_launch(actf_bwd_kernel, g.grid, dim3(256), 0, dn_stream(stream), *dout, o, act, dbias ? ws : nullptr, g.CGb, dbias, gscale);
     else
       act_bwd_kernel<8><<<g.grid, 256, 0, dn_stream(stream)>>>(*dout, o, act, dbias ? ws : nullptr, g.CGb, dbias, gscale);
   } else {

@@ -189,6 +189,7 @@ struct IgemmTcParams {
 
 template <int BN>
 __global__ void __launch_bounds__(192, 1) igemm_tc_kernel(const __grid_constant__ IgemmTcParams p) {
+  dn_pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr uint32_t A_BYTES = kRows * 128;
   constexpr uint32_t B_BYTES = BN * 128;
@@ -223,6 +224,7 @@ __global__ void __launch_bounds__(192, 1) igemm_tc_kernel(const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  dn_pdl_wait();      // set-up above overlaps the previous kernel's tail; global memory only from here on
 
   const int k_iters = p.ntaps * p.kchunks;
 
@@ -432,6 +434,7 @@ struct HaloParams {
 
 template <int BN>
 __global__ void __launch_bounds__(192, 1) igemm_halo_kernel(const __grid_constant__ HaloParams p) {
+  dn_pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr uint32_t B_BYTES = BN * 128;
   constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
@@ -469,6 +472,7 @@ __global__ void __launch_bounds__(192, 1) igemm_halo_kernel(const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  dn_pdl_wait();      // set-up above overlaps the previous kernel's tail; global memory only from here on
 
   if (warp == 0 && p.ring) {
     // ---- producer, streamed weights: the halo box of item i+1 is requested before the nine weight tiles of item i
@@ -733,6 +737,7 @@ __device__ __forceinline__ WgItem wg_decode(const WgradTcParams& p, int item) {
 
 template <int BNQ>
 __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant__ WgradTcParams p) {
+  dn_pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr uint32_t BLK_BYTES = KPX * 128;              // one [KPX px][64 ch] swizzled block
   constexpr uint32_t A_BYTES = 2 * BLK_BYTES;            // M = 128 channels of P
@@ -766,6 +771,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  dn_pdl_wait();      // set-up above overlaps the previous kernel's tail; global memory only from here on
   const uint32_t acc_cols = (uint32_t)(p.tpc * p.n_mma);
 
   if (warp == 0) {
@@ -975,7 +981,7 @@ int launch_igemm(const IgemmTcParams& P, cudaStream_t st) {
     attr_set = true;
   }
   int grid = P.num_tiles < dn_num_sms() ? P.num_tiles : dn_num_sms();
-  igemm_tc_kernel<BN><<<grid, 192, smem, st>>>(P);
+  dn_launch(igemm_tc_kernel<BN>, dim3(grid), dim3(192), smem, st, P);
   DN_CHECK_LAUNCH();
   return 0;
 }
@@ -992,7 +998,7 @@ int launch_wgrad(const WgradTcParams& P, int items, cudaStream_t st) {
   }
   int grid = items < dn_num_sms() ? items : dn_num_sms();
   if (const char* e = getenv("DN_WGRAD_NONPERSISTENT")) { if (atoi(e) == 1) grid = items; }
-  wgrad_tc_kernel<BNQ><<<grid, 192, smem, st>>>(P);
+  dn_launch(wgrad_tc_kernel<BNQ>, dim3(grid), dim3(192), smem, st, P);
   DN_CHECK_LAUNCH();
   return 0;
 }
@@ -1045,7 +1051,7 @@ int launch_halo(const HaloParams& P, cudaStream_t st) {
     attr_set = true;
   }
   int grid = P.num_tiles < dn_num_sms() ? P.num_tiles : dn_num_sms();
-  igemm_halo_kernel<BN><<<grid, 192, smem, st>>>(P);
+  dn_launch(igemm_halo_kernel<BN>, dim3(grid), dim3(192), smem, st, P);
   DN_CHECK_LAUNCH();
   return 0;
 }
