@@ -12,6 +12,8 @@
 // packing
 // =================================================================================================
 __global__ void pack_input_kernel(const float* __restrict__ src, int N, int C, int H, int W, dn_view dst, int c0) {
+  dn_pdl_trigger();
+  dn_pdl_wait();
   long long total = (long long)N * H * W;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     int w = (int)(i % W);
@@ -29,7 +31,7 @@ DN_EXPORT int dn_pack_input(const float* src, int N, int C, int H, int W, const 
   int blocks = (int)((total + 255) / 256);
   int cap = dn_num_sms() * 8;
   if (blocks > cap) blocks = cap;
-  pack_input_kernel<<<blocks, 256, 0, dn_stream(stream)>>>(src, N, C, H, W, *dst, c0);
+  dn_launch(pack_input_kernel, dim3(blocks), dim3(256), 0, dn_stream(stream), src, N, C, H, W, *dst, c0);
   DN_CHECK_LAUNCH();
   return 0;
 }
@@ -477,6 +479,8 @@ constexpr int kMaxReduceBlocks = 2048;
 template <typename TO>
 __global__ void __launch_bounds__(1024) reduce_partials_kernel(const float* __restrict__ ws, int nblk, int n, TO* __restrict__ out, double scale,
                                                                int nout = -1) {
+  dn_pdl_trigger();
+  dn_pdl_wait();
   __shared__ double part[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int j = blockIdx.x * 32 + tx;
@@ -1314,6 +1318,8 @@ DN_EXPORT int dn_maxpool_bwd(const dn_view* dout, const dn_view* x, const dn_vie
 // mode 0: out = act(a + b?)   mode 1: copy/accumulate   mode 2: add_act backward
 template <int CH>
 __global__ void __launch_bounds__(256) ew_fwd_kernel(dn_view a, dn_view b, int has_b, int act, dn_view out, int accumulate) {
+  dn_pdl_trigger();
+  dn_pdl_wait();
   const unsigned CG = (out.C + CH - 1) / CH;
   const unsigned total = (unsigned)out.N * out.H * out.W * CG;
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -1343,10 +1349,10 @@ static int ew_launch(const dn_view* a, const dn_view* b, int act, const dn_view*
   dn_view bb = b ? *b : *a;
   if (vec) {
     long long total = (long long)out->N * out->H * out->W * (out->C / 8);
-    ew_fwd_kernel<8><<<ew_blocks(total), 256, 0, dn_stream(stream)>>>(*a, bb, b != nullptr, act, *out, accumulate);
+    dn_launch(ew_fwd_kernel<8>, dim3(ew_blocks(total)), dim3(256), 0, dn_stream(stream), *a, bb, b != nullptr, act, *out, accumulate);
   } else {
     long long total = (long long)out->N * out->H * out->W * out->C;
-    ew_fwd_kernel<1><<<ew_blocks(total), 256, 0, dn_stream(stream)>>>(*a, bb, b != nullptr, act, *out, accumulate);
+    dn_launch(ew_fwd_kernel<1>, dim3(ew_blocks(total)), dim3(256), 0, dn_stream(stream), *a, bb, b != nullptr, act, *out, accumulate);
   }
   DN_CHECK_LAUNCH();
   return 0;
@@ -1423,6 +1429,8 @@ DN_EXPORT int dn_add_act_bwd(const dn_view* dout, const dn_view* out, int act, c
 __device__ __forceinline__ float dn_sigmoid(float x) { return 1.f / (1.f + expf(-x)); }
 
 __global__ void head_fwd_kernel(dn_view z, float alpha, float beta, float* __restrict__ disp) {
+  dn_pdl_trigger();
+  dn_pdl_wait();
   long long total = (long long)z.N * z.H * z.W;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     int w = (int)(i % z.W);
@@ -1444,6 +1452,8 @@ __device__ __forceinline__ void bil_src(int o, int insz, int& i0, int& i1, float
 }
 
 __global__ void head_up_kernel(const float* __restrict__ disp, int N, int H, int W, dn_view up, int mode) {
+  dn_pdl_trigger();
+  dn_pdl_wait();
   long long total = (long long)up.N * up.H * up.W;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     int x = (int)(i % up.W);
@@ -1466,12 +1476,12 @@ __global__ void head_up_kernel(const float* __restrict__ disp, int N, int H, int
 DN_EXPORT int dn_head_fwd(const dn_view* z, float alpha, float beta, float* disp, const dn_view* up, int up_mode, void* stream) {
   if (!z || !disp) return DN_E_ARG;
   long long total = (long long)z->N * z->H * z->W;
-  head_fwd_kernel<<<ew_blocks(total), 256, 0, dn_stream(stream)>>>(*z, alpha, beta, disp);
+  dn_launch(head_fwd_kernel, dim3(ew_blocks(total)), dim3(256), 0, dn_stream(stream), *z, alpha, beta, disp);
   DN_CHECK_LAUNCH();
   if (up) {
     if (up->H > 2 * z->H || up->W > 2 * z->W || up->N != z->N) return DN_E_ARG;
     long long t2 = (long long)up->N * up->H * up->W;
-    head_up_kernel<<<ew_blocks(t2), 256, 0, dn_stream(stream)>>>(disp, z->N, z->H, z->W, *up, up_mode);
+    dn_launch(head_up_kernel, dim3(ew_blocks(t2)), dim3(256), 0, dn_stream(stream), disp, z->N, z->H, z->W, *up, up_mode);
     DN_CHECK_LAUNCH();
   }
   return 0;
@@ -1479,6 +1489,8 @@ DN_EXPORT int dn_head_fwd(const dn_view* z, float alpha, float beta, float* disp
 
 __global__ void head_bwd_kernel(const float* __restrict__ gdisp, dn_view dup, int has_up, int mode, dn_view z, float alpha,
                                 float gscale, dn_view dz) {
+  dn_pdl_trigger();
+  dn_pdl_wait();
   long long total = (long long)z.N * z.H * z.W;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     int w = (int)(i % z.W);
@@ -1520,7 +1532,7 @@ DN_EXPORT int dn_head_bwd(const float* gdisp, const dn_view* dup, int up_mode, c
   if (!z || !dz) return DN_E_ARG;
   long long total = (long long)z->N * z->H * z->W;
   dn_view d = dup ? *dup : *z;
-  head_bwd_kernel<<<ew_blocks(total), 256, 0, dn_stream(stream)>>>(gdisp, d, dup != nullptr, up_mode, *z, alpha, gscale, *dz);
+  dn_launch(head_bwd_kernel, dim3(ew_blocks(total)), dim3(256), 0, dn_stream(stream), gdisp, d, dup != nullptr, up_mode, *z, alpha, gscale, *dz);
   DN_CHECK_LAUNCH();
   return 0;
 }
@@ -1642,6 +1654,8 @@ DN_EXPORT const char* dn_error_string(int code) {
 template <int CH>
 __global__ void __launch_bounds__(256) head_conv_fwd_kernel(dn_view x, const float* __restrict__ w, const float* __restrict__ bias,
                                                             dn_view z) {
+  dn_pdl_trigger();
+  dn_pdl_wait();
   extern __shared__ float ws[];          // [9][C]
   const int C = x.C;
   for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) {
@@ -1679,6 +1693,8 @@ __global__ void __launch_bounds__(256) head_conv_fwd_kernel(dn_view x, const flo
 template <int CH>
 __global__ void __launch_bounds__(256, 2) head_conv_bwd_kernel(dn_view x, const float* __restrict__ w, dn_view dz, dn_view gx,
                                                             int gx_acc, float* __restrict__ wsp, int CGb) {
+  dn_pdl_trigger();
+  dn_pdl_wait();
   extern __shared__ float ws[];          // [9][C] weights, then per-block accumulators [9*C + 1]
   const int C = x.C;
   float* accs = ws + 9 * C;
@@ -1758,8 +1774,8 @@ DN_EXPORT int dn_head_conv_fwd(const dn_view* x, const float* w, const float* bi
   const long long npix = (long long)x->N * ((x->H + 15) / 16) * ((x->W + 15) / 16) * 256;
   const size_t sm = sizeof(float) * 9 * x->C;
   int blocks = ew_blocks(npix);
-  if (dn_vec8_ok(x)) head_conv_fwd_kernel<8><<<blocks, 256, sm, dn_stream(stream)>>>(*x, w, bias, *z);
-  else head_conv_fwd_kernel<1><<<blocks, 256, sm, dn_stream(stream)>>>(*x, w, bias, *z);
+  if (dn_vec8_ok(x)) dn_launch(head_conv_fwd_kernel<8>, dim3(blocks), dim3(256), sm, dn_stream(stream), *x, w, bias, *z);
+  else dn_launch(head_conv_fwd_kernel<1>, dim3(blocks), dim3(256), sm, dn_stream(stream), *x, w, bias, *z);
   DN_CHECK_LAUNCH();
   return 0;
 }
@@ -1778,14 +1794,14 @@ DN_EXPORT int dn_head_conv_bwd(const dn_view* x, const float* w, const dn_view* 
   if ((long long)g.grid.x * n > cap) g.grid.x = (unsigned)(cap / n);
   const size_t sm = sizeof(float) * (18 * x->C + 1);
   cudaStream_t st = dn_stream(stream);
-  if (vec) head_conv_bwd_kernel<8><<<g.grid, 256, sm, st>>>(*x, w, *dz, *gx, gx_accumulate, rows, g.CGb);
-  else head_conv_bwd_kernel<1><<<g.grid, 256, sm, st>>>(*x, w, *dz, *gx, gx_accumulate, rows, g.CGb);
+  if (vec) dn_launch(head_conv_bwd_kernel<8>, dim3(g.grid), dim3(256), sm, st, *x, w, *dz, *gx, gx_accumulate, rows, g.CGb);
+  else dn_launch(head_conv_bwd_kernel<1>, dim3(g.grid), dim3(256), sm, st, *x, w, *dz, *gx, gx_accumulate, rows, g.CGb);
   DN_CHECK_LAUNCH();
   // second stage: [blocks][9C+1] -> gw (torch layout [1][C][3][3]) and gb; both scaled by gscale
-  reduce_partials_kernel<float><<<reduce_blocks(n - 1), 1024, 0, st>>>(rows, g.grid.x, n, gw, (double)gscale, n - 1);
+  dn_launch(reduce_partials_kernel<float>, dim3(reduce_blocks(n - 1)), dim3(1024), 0, st, rows, g.grid.x, n, gw, (double)gscale, n - 1);
   DN_CHECK_LAUNCH();
   if (gb) {
-    reduce_partials_kernel<float><<<1, 1024, 0, st>>>(rows + (n - 1), g.grid.x, n, gb, (double)gscale, 1);
+    dn_launch(reduce_partials_kernel<float>, dim3(1), dim3(1024), 0, st, rows + (n - 1), g.grid.x, n, gb, (double)gscale, 1);
     DN_CHECK_LAUNCH();
   }
   return 0;

@@ -9,7 +9,12 @@ and keep its own train.py.  Differences, all forced by breakages documented in S
     `(tgt_img, ref_imgs, intrinsics, intrinsics_inv, gt_depth)` the reference's commented-out line :418 used
     (the checked-in unsupervised branch reads unbound names);
   * only `--loss L1` is wired for the supervised branch (the other nine losses are out of scope);
-  * tensorboard / csv side effects happen only when `train_writer` / `args.save_path` are given.
+  * tensorboard / csv side effects happen only when `train_writer` / `args.save_path` are given;
+  * the `.to(device)` copies of batch i+1 (train.py:424-432) are issued on a copy stream while step i computes
+    (`_DevicePrefetcher`): same tensors, same order, the 27 MB H2D copy just no longer sits between two steps;
+  * the per-step `loss.item()` (:517) is an asynchronous 4-byte copy into pinned memory that is consumed one iteration
+    later (`_LossReader`): every step's loss is still read back and averaged, but the host no longer drains the GPU in
+    the middle of every step (between forward and backward).
 """
 import csv
 import os
@@ -49,6 +54,90 @@ class AverageMeter(object):
         return '{} ({})'.format(val, avg)
 
 
+class _DevicePrefetcher(object):
+    """Iterates `loader`, handing out batches whose tensors already live on `device`.  The host->device copies of the
+    NEXT batch are enqueued on a private copy stream the moment the current batch is handed out, so they overlap the
+    current step's kernels; the compute stream waits on the copy's event before it touches the batch.  At most `limit`
+    batches are pulled from the loader (the reference's loop breaks after `epoch_size` batches, train.py:536)."""
+
+    def __init__(self, loader, device, limit):
+        self.it, self.device, self.limit, self.pulled = iter(loader), torch.device(device), limit, 0
+        self.stream = torch.cuda.Stream(self.device) if self.device.type == 'cuda' else None
+        self._next = None
+        self._preload()
+
+    def _move(self, obj, out):
+        if torch.is_tensor(obj):
+            t = obj.to(self.device, non_blocking=True)
+            out.append(t)
+            return t
+        if isinstance(obj, (list, tuple)):
+            return type(obj)(self._move(o, out) for o in obj)
+        return obj
+
+    def _preload(self):
+        self._next = None
+        if self.pulled >= self.limit:
+            return
+        try:
+            batch = next(self.it)
+        except StopIteration:
+            return
+        self.pulled += 1
+        moved = []
+        if self.stream is None:
+            self._next = (self._move(batch, moved), moved, None)
+            return
+        with torch.cuda.stream(self.stream):
+            b = self._move(batch, moved)
+        ev = torch.cuda.Event()
+        ev.record(self.stream)
+        self._next = (b, moved, ev)
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        if self._next is None:
+            raise StopIteration
+        batch, moved, ev = self._next
+        if ev is not None:
+            cur = torch.cuda.current_stream(self.device)
+            cur.wait_event(ev)
+            for t in moved:
+                t.record_stream(cur)       # allocated on the copy stream, consumed on the compute stream
+        self._preload()
+        return batch
+
+
+class _LossReader(object):
+    """`losses.update(loss.item(), n)` with the device->host read deferred by one step."""
+
+    def __init__(self, meter, device):
+        self.meter, self.cuda = meter, torch.device(device).type == 'cuda'
+        self.bufs = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)] if self.cuda else None
+        self.pending, self.k = None, 0
+
+    def push(self, loss, n):
+        if not self.cuda:
+            self.meter.update(loss.item(), n)
+            return
+        buf = self.bufs[self.k]
+        self.k ^= 1
+        buf.copy_(loss.detach(), non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self.flush()
+        self.pending = (buf, ev, n)
+
+    def flush(self):
+        if self.pending is not None:
+            buf, ev, n = self.pending
+            ev.synchronize()
+            self.meter.update(buf.item(), n)
+            self.pending = None
+
+
 def default_args(**kw):
     """argparse defaults of the reference that the loop reads (train.py:28-91)."""
     a = dict(photo_loss_weight=1.0, mask_loss_weight=0.0, smooth_loss_weight=0.0, unsupervised=False, dataset='kitti',
@@ -75,7 +164,8 @@ def train(args, train_loader, disp_net, pose_exp_net, optimizer, epoch_size, log
     if logger is not None:
         logger.train_bar.update(0)
 
-    for i, batch in enumerate(train_loader):
+    reader = _LossReader(losses, device)
+    for i, batch in enumerate(_DevicePrefetcher(train_loader, device, epoch_size)):
         data_time.update(time.time() - end)
         if len(batch) == 2:
             tgt_img, gt_depth = batch
@@ -118,7 +208,7 @@ def train(args, train_loader, disp_net, pose_exp_net, optimizer, epoch_size, log
             train_writer.add_scalar('disparity_smoothness_loss', loss_3.item(), n_iter)
             train_writer.add_scalar('total_loss', loss.item(), n_iter)
 
-        losses.update(loss.item(), args.batch_size)      # the per-step D2H read of the reference (:517)
+        reader.push(loss, args.batch_size)      # the per-step D2H read of the reference (:517), consumed one step later
 
         optimizer.zero_grad()
         loss.backward()
@@ -137,4 +227,5 @@ def train(args, train_loader, disp_net, pose_exp_net, optimizer, epoch_size, log
         if i >= epoch_size - 1:
             break
         n_iter += 1
+    reader.flush()
     return losses.avg[0]
