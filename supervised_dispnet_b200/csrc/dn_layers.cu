@@ -1769,8 +1769,39 @@ __global__ void __launch_bounds__(256, 2) head_conv_bwd_kernel(dn_view x, const 
   for (int i = threadIdx.x; i < 9 * C + 1; i += blockDim.x) wsp[(long long)blockIdx.x * (9 * C + 1) + i] = accs[i];
 }
 
+#include "dn_head_mma.cuh"
+
+// DN_HEAD_MMA=0 keeps the CUDA-core kernels (A/B comparisons)
+static const bool g_head_mma = []() { const char* e = getenv("DN_HEAD_MMA"); return !(e && e[0] == '0'); }();
+
+template <typename K>
+static int hc_set_smem(K kernel, size_t bytes) {
+  if (bytes <= 48 * 1024) return 0;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  return e == cudaSuccess ? 0 : (int)e;
+}
+
 DN_EXPORT int dn_head_conv_fwd(const dn_view* x, const float* w, const float* bias, const dn_view* z, void* stream) {
   if (!x || !w || !z || z->C != 1 || z->N != x->N || z->H != x->H || z->W != x->W) return DN_E_ARG;
+  if (g_head_mma && hc::eligible(x)) {
+    const size_t sm = hc::fwd_smem(x->C);
+    const int ntiles = ((x->W + hc::TW - 1) / hc::TW) * ((x->H + hc::TH - 1) / hc::TH) * x->N;
+    int per_sm = (int)((200 * 1024) / (sm + 1024));
+    if (per_sm > 6) per_sm = 6;
+    if (per_sm < 1) per_sm = 1;
+    int grid = dn_num_sms() * per_sm;
+    if (grid > ntiles) grid = ntiles;
+    int e;
+    if (x->dtype == DN_BF16) {
+      if ((e = hc_set_smem(hc::fwd_kernel<true>, sm))) return e;
+      dn_launch(hc::fwd_kernel<true>, dim3(grid), dim3(256), sm, dn_stream(stream), *x, w, bias, *z);
+    } else {
+      if ((e = hc_set_smem(hc::fwd_kernel<false>, sm))) return e;
+      dn_launch(hc::fwd_kernel<false>, dim3(grid), dim3(256), sm, dn_stream(stream), *x, w, bias, *z);
+    }
+    DN_CHECK_LAUNCH();
+    return 0;
+  }
   const long long npix = (long long)x->N * ((x->H + 15) / 16) * ((x->W + 15) / 16) * 256;
   const size_t sm = sizeof(float) * 9 * x->C;
   int blocks = ew_blocks(npix);
@@ -1794,7 +1825,22 @@ DN_EXPORT int dn_head_conv_bwd(const dn_view* x, const float* w, const dn_view* 
   if ((long long)g.grid.x * n > cap) g.grid.x = (unsigned)(cap / n);
   const size_t sm = sizeof(float) * (18 * x->C + 1);
   cudaStream_t st = dn_stream(stream);
-  if (vec) dn_launch(head_conv_bwd_kernel<8>, dim3(g.grid), dim3(256), sm, st, *x, w, *dz, *gx, gx_accumulate, rows, g.CGb);
+  if (g_head_mma && vec && hc::eligible(x) && (gx->dtype == DN_BF16 || gx->dtype == DN_F16)) {
+    const size_t smm = hc::bwd_smem(x->C);
+    const int ntiles = ((x->W + hc::TW - 1) / hc::TW) * ((x->H + hc::TH - 1) / hc::TH) * x->N;
+    int per_sm = x->C >= 128 ? 1 : 2;
+    long long grid = (long long)dn_num_sms() * per_sm;
+    if (grid > ntiles) grid = ntiles;
+    if (grid * n > cap) grid = cap / n;
+    g.grid = dim3((unsigned)grid);
+    int e = 0;
+    switch (x->C) {
+      case 16: if ((e = hc_set_smem(hc::bwd_kernel<2>, smm))) return e; dn_launch(hc::bwd_kernel<2>, g.grid, dim3(256), smm, st, *x, w, *dz, *gx, gx_accumulate, rows); break;
+      case 32: if ((e = hc_set_smem(hc::bwd_kernel<4>, smm))) return e; dn_launch(hc::bwd_kernel<4>, g.grid, dim3(256), smm, st, *x, w, *dz, *gx, gx_accumulate, rows); break;
+      case 64: if ((e = hc_set_smem(hc::bwd_kernel<8>, smm))) return e; dn_launch(hc::bwd_kernel<8>, g.grid, dim3(256), smm, st, *x, w, *dz, *gx, gx_accumulate, rows); break;
+      default: if ((e = hc_set_smem(hc::bwd_kernel<16>, smm))) return e; dn_launch(hc::bwd_kernel<16>, g.grid, dim3(256), smm, st, *x, w, *dz, *gx, gx_accumulate, rows); break;
+    }
+  } else if (vec) dn_launch(head_conv_bwd_kernel<8>, dim3(g.grid), dim3(256), sm, st, *x, w, *dz, *gx, gx_accumulate, rows, g.CGb);
   else dn_launch(head_conv_bwd_kernel<1>, dim3(g.grid), dim3(256), sm, st, *x, w, *dz, *gx, gx_accumulate, rows, g.CGb);
   DN_CHECK_LAUNCH();
   // second stage: [blocks][9C+1] -> gw (torch layout [1][C][3][3]) and gb; both scaled by gscale

@@ -392,3 +392,59 @@ def test_cuda_graph_replay_matches_eager(monkeypatch):
     # weight-gradient partial sums are reduced with fp32 atomics (order varies run to run), so agreement is to round-off
     assert max(abs(a - b) / abs(a) for a, b in zip(le, lg)) < 1e-4
     assert rel(dg, de) < 1e-3 and rel(bg, be) < 1e-4
+
+
+# ---- disparity-head convolution (warp-MMA kernels) against F.conv2d -----------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize('C,H,W,xdt', [(16, 13, 37, 'f16'), (16, 16, 64, 'bf16'), (32, 9, 33, 'f16'), (64, 8, 32, 'f16'),
+                                       (128, 5, 20, 'f16'), (16, 24, 70, 'f16')])
+def test_head_conv_mma_vs_torch(C, H, W, xdt):
+    """nn.Conv2d(C, 1, 3, padding=1) forward / data / weight / bias gradients (reference predict_disp,
+    models/Disp_vgg_BN.py:66-70) through dn_head_conv_fwd / dn_head_conv_bwd on ragged tile shapes.  Tolerances: forward
+    1e-3 (fp16/bf16 operands, fp32 accumulate); gradients 1e-2 (bf16 operands), relative L2."""
+    import ctypes as C_
+    import torch
+    import torch.nn.functional as F
+    from supervised_dispnet_b200 import _lib as L
+    torch.manual_seed(C + H)
+    dev = torch.device('cuda')
+    N = 3
+    tdt = torch.float16 if xdt == 'f16' else torch.bfloat16
+    ddt = L.DN_F16 if xdt == 'f16' else L.DN_BF16
+    x = torch.randn(N, H, W, C, device=dev).to(tdt)
+    w = (torch.randn(1, C, 3, 3, device=dev) * 0.2).contiguous()
+    b = torch.randn(1, device=dev)
+    z = torch.zeros(N, H, W, 1, device=dev)
+
+    def view(t, dt):
+        n, h, w_, c = t.shape
+        return L.DnView(t.data_ptr(), dt, n, h, w_, c, h * w_ * c, w_ * c, c)
+    st = L.stream_ptr()
+    vx, vz = view(x, ddt), view(z, L.DN_F32)
+    L.call('dn_head_conv_fwd', C_.byref(vx), L.ptr(w), L.ptr(b), C_.byref(vz), st)
+    xr = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+    wr = w.clone().requires_grad_(True)
+    br = b.clone().requires_grad_(True)
+    ref = F.conv2d(xr, wr, br, padding=1)
+    got = z.permute(0, 3, 1, 2)
+    assert float((got - ref).norm() / ref.norm()) < (1e-3 if xdt == 'f16' else 8e-3)
+
+    dz = torch.randn(N, H, W, 1, device=dev)
+    ref.backward(dz.permute(0, 3, 1, 2))
+    g0 = torch.randn(N, H, W, C, device=dev).bfloat16()
+    gx = g0.clone()
+    gw, gb = torch.zeros_like(w), torch.zeros(1, device=dev)
+    ws = torch.zeros(int(L.lib().dn_reduce_ws_floats(C * 5)), device=dev)
+    vdz, vgx = view(dz, L.DN_F32), view(gx, L.DN_BF16)
+    L.call('dn_head_conv_bwd', C_.byref(vx), L.ptr(w), C_.byref(vdz), C_.byref(vgx), 1, L.ptr(gw), L.ptr(gb), 1.0, L.ptr(ws), st)
+    torch.cuda.synchronize()
+    dx = (gx.float() - g0.float()).permute(0, 3, 1, 2)
+    assert float((dx - xr.grad).norm() / xr.grad.norm()) < 1.5e-2
+    assert float((gw - wr.grad).norm() / wr.grad.norm()) < 1e-2
+    assert abs(float(gb) - float(br.grad)) < 1e-3 * (1 + abs(float(br.grad)))
+    # overwrite mode (first writer of the gradient slot)
+    gx2 = torch.full_like(g0, 7.0)
+    vgx2 = view(gx2, L.DN_BF16)
+    L.call('dn_head_conv_bwd', C_.byref(vx), L.ptr(w), C_.byref(vdz), C_.byref(vgx2), 0, L.ptr(gw), L.ptr(gb), 1.0, L.ptr(ws), st)
+    torch.cuda.synchronize()
+    assert float((gx2.float().permute(0, 3, 1, 2) - xr.grad).norm() / xr.grad.norm()) < 1e-2
