@@ -1773,6 +1773,7 @@ __global__ void __launch_bounds__(256, 2) head_conv_bwd_kernel(dn_view x, const 
 
 // DN_HEAD_MMA=0 keeps the CUDA-core kernels (A/B comparisons)
 static const bool g_head_mma = []() { const char* e = getenv("DN_HEAD_MMA"); return !(e && e[0] == '0'); }();
+static const bool g_head_bulk = []() { const char* e = getenv("DN_HEAD_BULK"); return !(e && e[0] == '0'); }();
 
 template <typename K>
 static int hc_set_smem(K kernel, size_t bytes) {
@@ -1783,6 +1784,27 @@ static int hc_set_smem(K kernel, size_t bytes) {
 
 DN_EXPORT int dn_head_conv_fwd(const dn_view* x, const float* w, const float* bias, const dn_view* z, void* stream) {
   if (!x || !w || !z || z->C != 1 || z->N != x->N || z->H != x->H || z->W != x->W) return DN_E_ARG;
+  if (g_head_mma && hc::eligible(x) && x->C <= 32 && x->sW == x->C && g_head_bulk) {
+    // rows of whole pixel vectors are contiguous: bulk-copy, double-buffered variant
+    constexpr int S = 4;                  // C = 16: 4 x 10.6 KB, C = 32: 4 x 21.3 KB per block
+    const size_t sm = hc::fwd_bulk_smem(x->C, S);
+    const int ntiles = ((x->W + hc::TW - 1) / hc::TW) * ((x->H + hc::TH - 1) / hc::TH) * x->N;
+    int per_sm = (int)((220 * 1024) / (sm + 1024));
+    if (per_sm > 4) per_sm = 4;
+    int grid = dn_num_sms() * per_sm;
+    if (grid > ntiles) grid = ntiles;
+    int e = 0;
+#define HC_FWD_BULK(BF, CC)                                                     \
+  do {                                                                          \
+    if ((e = hc_set_smem(hc::fwd_bulk_kernel<BF, CC, S>, sm))) return e;        \
+    dn_launch(hc::fwd_bulk_kernel<BF, CC, S>, dim3(grid), dim3(256), sm, dn_stream(stream), *x, w, bias, *z); \
+  } while (0)
+    if (x->dtype == DN_BF16) { if (x->C == 16) HC_FWD_BULK(true, 16); else HC_FWD_BULK(true, 32); }
+    else { if (x->C == 16) HC_FWD_BULK(false, 16); else HC_FWD_BULK(false, 32); }
+#undef HC_FWD_BULK
+    DN_CHECK_LAUNCH();
+    return 0;
+  }
   if (g_head_mma && hc::eligible(x)) {
     const size_t sm = hc::fwd_smem(x->C);
     const int ntiles = ((x->W + hc::TW - 1) / hc::TW) * ((x->H + hc::TH - 1) / hc::TH) * x->N;
@@ -1834,7 +1856,12 @@ DN_EXPORT int dn_head_conv_bwd(const dn_view* x, const float* w, const dn_view* 
     if (grid * n > cap) grid = cap / n;
     g.grid = dim3((unsigned)grid);
     int e = 0;
-    switch (x->C) {
+    const bool bulk = g_head_bulk && x->C <= 32 && x->sW == x->C;
+    constexpr int SB = 4;
+    const size_t smb = bulk ? hc::bwd_bulk_smem(x->C, SB) : 0;
+    switch (bulk ? -x->C : x->C) {
+      case -16: if ((e = hc_set_smem(hc::bwd_bulk_kernel<2, SB>, smb))) return e; dn_launch(hc::bwd_bulk_kernel<2, SB>, g.grid, dim3(256), smb, st, *x, w, *dz, *gx, gx_accumulate, rows); break;
+      case -32: if ((e = hc_set_smem(hc::bwd_bulk_kernel<4, SB>, smb))) return e; dn_launch(hc::bwd_bulk_kernel<4, SB>, g.grid, dim3(256), smb, st, *x, w, *dz, *gx, gx_accumulate, rows); break;
       case 16: if ((e = hc_set_smem(hc::bwd_kernel<2>, smm))) return e; dn_launch(hc::bwd_kernel<2>, g.grid, dim3(256), smm, st, *x, w, *dz, *gx, gx_accumulate, rows); break;
       case 32: if ((e = hc_set_smem(hc::bwd_kernel<4>, smm))) return e; dn_launch(hc::bwd_kernel<4>, g.grid, dim3(256), smm, st, *x, w, *dz, *gx, gx_accumulate, rows); break;
       case 64: if ((e = hc_set_smem(hc::bwd_kernel<8>, smm))) return e; dn_launch(hc::bwd_kernel<8>, g.grid, dim3(256), smm, st, *x, w, *dz, *gx, gx_accumulate, rows); break;

@@ -110,12 +110,17 @@ class _DevicePrefetcher(object):
         return batch
 
 
+_PINNED_SCALARS = []      # two pinned 4-byte landing buffers, allocated once per process (cudaHostAlloc costs milliseconds)
+
+
 class _LossReader(object):
     """`losses.update(loss.item(), n)` with the device->host read deferred by one step."""
 
     def __init__(self, meter, device):
         self.meter, self.cuda = meter, torch.device(device).type == 'cuda'
-        self.bufs = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)] if self.cuda else None
+        if self.cuda and not _PINNED_SCALARS:
+            _PINNED_SCALARS.extend(torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2))
+        self.bufs = _PINNED_SCALARS if self.cuda else None
         self.pending, self.k = None, 0
 
     def push(self, loss, n):

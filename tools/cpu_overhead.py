@@ -21,3 +21,22 @@ t1 = time.perf_counter()
 torch.cuda.synchronize()
 t2 = time.perf_counter()
 print('enqueue %.2f ms/step, total %.2f ms/step' % ((t1 - t0) * 100, (t2 - t0) * 100))
+
+# the same through train.train() with pinned host batches (prefetcher + deferred loss read)
+from supervised_dispnet_b200 import train as T
+xh, gh = bench.synth_batch(32, 10, pinned=True) if 'pinned' in bench.synth_batch.__code__.co_varnames else (x.cpu().pin_memory(), gt.cpu().pin_memory())
+targs = T.default_args(batch_size=32, smooth_loss_weight=0.0)
+T.train(targs, [(xh, gh)] * 3, net, None, opt, 3)
+torch.cuda.synchronize()
+K = 20
+t0 = time.perf_counter()
+T.train(targs, [(xh, gh)] * K, net, None, opt, K)
+t1 = time.perf_counter()
+torch.cuda.synchronize()
+t2 = time.perf_counter()
+print('train.train: host returns after %.2f ms/step, total %.2f ms/step' % ((t1 - t0) * 1e3 / K, (t2 - t0) * 1e3 / K))
+import cProfile, pstats
+pr = cProfile.Profile(); pr.enable()
+T.train(targs, [(xh, gh)] * K, net, None, opt, K)
+pr.disable(); torch.cuda.synchronize()
+pstats.Stats(pr).sort_stats('cumulative').print_stats(18)
