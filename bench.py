@@ -55,7 +55,7 @@ def synth_batch(b, seed, pinned=False):
 
 
 class ClockSampler(threading.Thread):
-    """SM clock + throttle reasons sampled during the timed region: NVML every 5 ms (in-process, ~50 us per sample), falling
+    """SM clock + throttle reasons sampled during the timed region: NVML every 10 ms (in-process, ~50 us per sample), falling
     back to `nvidia-smi --query-gpu` (the profiling recipe's clocks line, ~60 ms per sample) when NVML cannot be loaded."""
     Q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
@@ -100,7 +100,7 @@ class ClockSampler(threading.Thread):
     def run(self):
         while not self.stop_flag:
             self.sample()
-            time.sleep(0.005 if self.nv is not None else 0.05)
+            time.sleep(0.01 if self.nv is not None else 0.05)
 
     def summary(self):
         if not self.samples:
@@ -261,7 +261,7 @@ def run_ours(args):
         def __iter__(self):
             for _ in range(args.steps):
                 yield x_h, gt_h
-    T.train(targs, [(x_h, gt_h)] * 2, model, None, opt, 2)
+    T.train(targs, [(x_h, gt_h)] * 4, model, None, opt, 4)
     barrier()
     e0.record()
     T.train(targs, Loader(), model, None, opt, args.steps)

@@ -12,7 +12,7 @@ and keep its own train.py.  Differences, all forced by breakages documented in S
   * tensorboard / csv side effects happen only when `train_writer` / `args.save_path` are given;
   * the `.to(device)` copies of batch i+1 (train.py:424-432) are issued on a copy stream while step i computes
     (`_DevicePrefetcher`): same tensors, same order, the 27 MB H2D copy just no longer sits between two steps;
-  * the per-step `loss.item()` (:517) is an asynchronous 4-byte copy into pinned memory that is consumed one iteration
+  * the per-step `loss.item()` (:517) is an asynchronous 4-byte copy into pinned memory that is consumed two iterations
     later (`_LossReader`): every step's loss is still read back and averaged, but the host no longer drains the GPU in
     the middle of every step (between forward and backward).
 """
@@ -57,22 +57,45 @@ class AverageMeter(object):
 class _DevicePrefetcher(object):
     """Iterates `loader`, handing out batches whose tensors already live on `device`.  The host->device copies of the
     NEXT batch are enqueued on a private copy stream the moment the current batch is handed out, so they overlap the
-    current step's kernels; the compute stream waits on the copy's event before it touches the batch.  At most `limit`
-    batches are pulled from the loader (the reference's loop breaks after `epoch_size` batches, train.py:536)."""
+    current step's kernels; the compute stream waits on the copy's event before it touches the batch.  The device side
+    is a ring of four preallocated buffer sets (no allocator traffic in the loop): the copy into a slot waits for the
+    event that marks the end of the enqueued work of the batch that used the slot four hand-outs earlier, so a handed
+    out batch stays valid until three more batches have been requested.  At most `limit` batches are pulled from the
+    loader (the reference's loop breaks after `epoch_size` batches, train.py:536)."""
+    SLOTS = 4          # _LossReader.DEPTH + 2: the host runs at most DEPTH steps ahead of the device
+
+    _STATE = {}        # device -> (copy stream, ring buffers, slot events): kept across calls - a new stream per epoch would
+                       # strand the previous ring in another stream's allocator pool and pay cudaMalloc / cudaFree again
 
     def __init__(self, loader, device, limit):
         self.it, self.device, self.limit, self.pulled = iter(loader), torch.device(device), limit, 0
-        self.stream = torch.cuda.Stream(self.device) if self.device.type == 'cuda' else None
+        self.cuda = self.device.type == 'cuda'
+        if self.cuda:
+            key = self.device.index if self.device.index is not None else torch.cuda.current_device()
+            st = self._STATE.get(key)
+            if st is None:
+                st = (torch.cuda.Stream(self.device), [dict() for _ in range(self.SLOTS)], [None] * self.SLOTS)
+                self._STATE[key] = st
+            # slot -> {position in the batch: device tensor};  slot -> event: the work enqueued on its batch has finished
+            self.stream, self.bufs, self.done = st
+        else:
+            self.stream, self.bufs, self.done = None, [dict() for _ in range(self.SLOTS)], [None] * self.SLOTS
+        self.handed = None                                       # slot of the batch the caller is working on
         self._next = None
         self._preload()
 
-    def _move(self, obj, out):
+    def _move(self, obj, slot, path):
         if torch.is_tensor(obj):
-            t = obj.to(self.device, non_blocking=True)
-            out.append(t)
-            return t
+            if not self.cuda or obj.device == self.device:
+                return obj.to(self.device)
+            buf = self.bufs[slot].get(path)
+            if buf is None or buf.shape != obj.shape or buf.dtype != obj.dtype:
+                buf = torch.empty(obj.shape, dtype=obj.dtype, device=self.device)
+                self.bufs[slot][path] = buf
+            buf.copy_(obj, non_blocking=True)
+            return buf
         if isinstance(obj, (list, tuple)):
-            return type(obj)(self._move(o, out) for o in obj)
+            return type(obj)(self._move(o, slot, path + (k,)) for k, o in enumerate(obj))
         return obj
 
     def _preload(self):
@@ -83,29 +106,33 @@ class _DevicePrefetcher(object):
             batch = next(self.it)
         except StopIteration:
             return
+        slot = self.pulled % self.SLOTS
         self.pulled += 1
-        moved = []
-        if self.stream is None:
-            self._next = (self._move(batch, moved), moved, None)
+        if not self.cuda:
+            self._next = (self._move(batch, slot, ()), None, slot)
             return
         with torch.cuda.stream(self.stream):
-            b = self._move(batch, moved)
+            if self.done[slot] is not None:
+                self.stream.wait_event(self.done[slot])          # the slot's previous batch is no longer read by any kernel
+            b = self._move(batch, slot, ())
         ev = torch.cuda.Event()
         ev.record(self.stream)
-        self._next = (b, moved, ev)
+        self._next = (b, ev, slot)
 
     def __iter__(self):
         return self
 
     def __next__(self):
+        if self.cuda and self.handed is not None:                # everything the caller enqueued on the previous batch
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))
+            self.done[self.handed] = ev
         if self._next is None:
             raise StopIteration
-        batch, moved, ev = self._next
+        batch, ev, slot = self._next
         if ev is not None:
-            cur = torch.cuda.current_stream(self.device)
-            cur.wait_event(ev)
-            for t in moved:
-                t.record_stream(cur)       # allocated on the copy stream, consumed on the compute stream
+            torch.cuda.current_stream(self.device).wait_event(ev)
+        self.handed = slot
         self._preload()
         return batch
 
@@ -114,33 +141,38 @@ _PINNED_SCALARS = []      # two pinned 4-byte landing buffers, allocated once pe
 
 
 class _LossReader(object):
-    """`losses.update(loss.item(), n)` with the device->host read deferred by one step."""
+    """`losses.update(loss.item(), n)` with the device->host read deferred by DEPTH steps: the 4-byte copy is enqueued
+    right where the reference calls `.item()`, its value is consumed DEPTH iterations later, so the host stays up to
+    DEPTH steps ahead of the device and a few milliseconds of host jitter never drain the GPU queue."""
+    DEPTH = 2
 
     def __init__(self, meter, device):
         self.meter, self.cuda = meter, torch.device(device).type == 'cuda'
-        if self.cuda and not _PINNED_SCALARS:
-            _PINNED_SCALARS.extend(torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2))
-        self.bufs = _PINNED_SCALARS if self.cuda else None
-        self.pending, self.k = None, 0
+        if self.cuda and len(_PINNED_SCALARS) < self.DEPTH + 1:
+            _PINNED_SCALARS.extend(torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(self.DEPTH + 1 - len(_PINNED_SCALARS)))
+        self.pending, self.k = [], 0
 
     def push(self, loss, n):
         if not self.cuda:
             self.meter.update(loss.item(), n)
             return
-        buf = self.bufs[self.k]
-        self.k ^= 1
+        buf = _PINNED_SCALARS[self.k]
+        self.k = (self.k + 1) % (self.DEPTH + 1)
         buf.copy_(loss.detach(), non_blocking=True)
         ev = torch.cuda.Event()
         ev.record()
-        self.flush()
-        self.pending = (buf, ev, n)
+        self.pending.append((buf, ev, n))
+        while len(self.pending) > self.DEPTH:
+            self._pop()
+
+    def _pop(self):
+        buf, ev, n = self.pending.pop(0)
+        ev.synchronize()
+        self.meter.update(buf.item(), n)
 
     def flush(self):
-        if self.pending is not None:
-            buf, ev, n = self.pending
-            ev.synchronize()
-            self.meter.update(buf.item(), n)
-            self.pending = None
+        while self.pending:
+            self._pop()
 
 
 def default_args(**kw):
@@ -213,7 +245,7 @@ def train(args, train_loader, disp_net, pose_exp_net, optimizer, epoch_size, log
             train_writer.add_scalar('disparity_smoothness_loss', loss_3.item(), n_iter)
             train_writer.add_scalar('total_loss', loss.item(), n_iter)
 
-        reader.push(loss, args.batch_size)      # the per-step D2H read of the reference (:517), consumed one step later
+        reader.push(loss, args.batch_size)      # the per-step D2H read of the reference (:517), consumed two steps later
 
         optimizer.zero_grad()
         loss.backward()
