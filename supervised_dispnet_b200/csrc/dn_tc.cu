@@ -551,10 +551,13 @@ __global__ void __launch_bounds__(192, 1) igemm_halo_kernel(const __grid_constan
   } else if (warp == 0) {
     // ---- producer: weights once, then one halo box per (tile, chunk)
     if (elect_one()) {
-      mbar_expect_tx(bfull_bar, (uint32_t)nb_tiles * B_BYTES);
+      int present = 0;
+      for (int t = 0; t < 9; ++t) present += p.wt[t] >= 0 ? 1 : 0;
+      mbar_expect_tx(bfull_bar, (uint32_t)(present * p.kchunks) * B_BYTES);
       for (int t = 0; t < 9; ++t)
-        for (int kc = 0; kc < p.kchunks; ++kc)
-          tma_load_3d(smem_b + (size_t)(t * p.kchunks + kc) * B_BYTES, &p.tmB, bfull_bar, kc * kChunk, 0, p.wt[t]);
+        if (p.wt[t] >= 0)
+          for (int kc = 0; kc < p.kchunks; ++kc)
+            tma_load_3d(smem_b + (size_t)(t * p.kchunks + kc) * B_BYTES, &p.tmB, bfull_bar, kc * kChunk, 0, p.wt[t]);
     }
     __syncwarp();
     int stage = 0; uint32_t phase = 0;
@@ -590,8 +593,10 @@ __global__ void __launch_bounds__(192, 1) igemm_halo_kernel(const __grid_constan
         const uint32_t sa = smem_u32(smem_a + (size_t)stage * kHaloBytes);
         const int ks = (kc == p.kchunks - 1) ? p.last_ksteps : 4;
         if (elect_one()) {
+          uint32_t accumulate = kc == 0 ? 0u : 1u;
 #pragma unroll
           for (int t = 0; t < 9; ++t) {
+            if (p.wt[t] < 0) continue;      // tap subset (2x2 neighbourhood of a transposed-convolution phase)
             const int kh = t / 3, kw = t % 3;
             // base_offset stays 0: the 128B swizzle is a function of the absolute shared-memory address bits (measured on B200:
             // only base_offset = 0 reproduces the unshifted kernel), so a start that is not 1024-byte aligned needs no correction
@@ -599,7 +604,7 @@ __global__ void __launch_bounds__(192, 1) igemm_halo_kernel(const __grid_constan
             const uint64_t bd0 = make_desc(sb0 + (uint32_t)(t * p.kchunks + kc) * B_BYTES, 16, 1024);
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              if (k < ks) umma_f16(d_tmem, ad0 + (uint64_t)(2 * k), bd0 + (uint64_t)(2 * k), p.idesc, (kc == 0 && t == 0 && k == 0) ? 0u : 1u);
+              if (k < ks) { umma_f16(d_tmem, ad0 + (uint64_t)(2 * k), bd0 + (uint64_t)(2 * k), p.idesc, accumulate); accumulate = 1u; }
           }
           umma_commit(&empty_bar[stage]);
           if (kc == p.kchunks - 1) umma_commit(&tfull_bar[acc]);
@@ -1009,10 +1014,13 @@ bool g_halo_enabled = true;
 const bool g_halo_ring = []() { const char* e = getenv("DN_HALO_RING"); return !(e && e[0] == '0'); }();   // A/B knob
 
 // fills wt[kh*3+kw]; true when the taps are exactly the 3x3 neighbourhood of one source
+// taps form a subset of the 3x3 neighbourhood (all nine for a 3x3 convolution, a 2x2 corner for one output phase of a
+// 4x4 / stride-2 transposed convolution): wt[kh * 3 + kw] = packed-weight index, -1 where the tap is absent
 bool halo_taps(const dn_igemm* p, int* wt) {
-  if (p->ntaps != 9 || p->nsrc != 1 || p->stride != 1) return false;
+  if (p->ntaps > 9 || p->ntaps < 3 || p->nsrc != 1 || p->stride != 1) return false;
   bool seen[9] = {false};
-  for (int t = 0; t < 9; ++t) {
+  for (int i = 0; i < 9; ++i) wt[i] = -1;
+  for (int t = 0; t < p->ntaps; ++t) {
     int dh = p->taps[t].dh, dw = p->taps[t].dw;
     if (dh < -1 || dh > 1 || dw < -1 || dw > 1 || p->taps[t].src != 0) return false;
     int i = (dh + 1) * 3 + (dw + 1);
@@ -1032,7 +1040,7 @@ bool halo_eligible(const dn_igemm* p, int* wt) {
   // weights stay resident next to >= 2 halo stages when they fit; else they stream through a ring, which measured a gain only
   // for one-chunk problems (features.7 forward 0.099 -> 0.093 ms): N <= 128 tiles with more K are bound by the 128 B/clk
   // shared-memory operand reads of cta_group::1 either way (A 4 KB + B 4 KB per 64-cycle 128x128x16 MMA)
-  if (b_bytes + 2 * kHaloBytes > 200 * 1024 && (BN > 128 || kchunks > 1 || !g_halo_ring)) return false;
+  if (b_bytes + 2 * kHaloBytes > 200 * 1024 && (BN > 128 || kchunks > 1 || !g_halo_ring || p->ntaps != 9)) return false;
   const int H = p->out.H, W = p->out.W;
   if (H != p->in[0].H || W != p->in[0].W) return false;
   // tile = 16 rows x 8 columns: only worth it when little of the tile grid is padding
