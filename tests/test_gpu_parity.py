@@ -448,3 +448,81 @@ def test_head_conv_mma_vs_torch(C, H, W, xdt):
     L.call('dn_head_conv_bwd', C_.byref(vx), L.ptr(w), C_.byref(vdz), C_.byref(vgx2), 0, L.ptr(gw), L.ptr(gb), 1.0, L.ptr(ws), st)
     torch.cuda.synchronize()
     assert float((gx2.float().permute(0, 3, 1, 2) - xr.grad).norm() / xr.grad.norm()) < 1e-2
+
+
+# ---- BatchNorm(train) + ReLU (+ MaxPool 2x2) kernels against torch, fast paths and generic walkers -----------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize('C,H,W,pool,crop', [(64, 8, 12, 0, 0), (64, 8, 12, 1, 0), (96, 6, 10, 1, 0), (200, 5, 7, 0, 0),
+                                             (512, 4, 6, 1, 0), (20, 9, 11, 0, 0), (64, 8, 12, 0, 1), (64, 8, 12, 1, 1)])
+def test_bn_kernels_vs_torch(C, H, W, pool, crop):
+    """dn_bn_train_stats / dn_bn_apply / dn_bn_bwd_reduce / dn_bn_bwd_apply (reference: nn.BatchNorm2d + ReLU + MaxPool2d
+    of the vgg16_bn feature stack, models/Disp_vgg_BN.py:137-141) vs torch fp32 on the same fp16-rounded input.  crop=1
+    walks a W-cropped view (not pixel-linear), which forces the generic kernels; crop=0 takes the fast paths where the
+    channel count allows 16-byte vectors.  Channel counts cover one slab (64), partial slabs (96, 200), many slabs (512)
+    and the scalar path (20 channels: no 16-byte vectors).  Tolerances: statistics 1e-5 rel, forward 2e-3 (fp16 output
+    rounding), gradients 2e-2 relative L2 (bf16 gradient rounding)."""
+    import ctypes as C_
+    import torch
+    import torch.nn.functional as F
+    from supervised_dispnet_b200 import _lib as L
+    torch.manual_seed(C * 7 + H)
+    dev = torch.device('cuda')
+    N, Wb = 3, W + (3 if crop else 0)
+    yb = (torch.randn(N, H, Wb, C, device=dev) * 1.5 + 0.3).half()
+
+    def view(t, dt, w=None):
+        n, h, wb, c = t.shape
+        return L.DnView(t.data_ptr(), dt, n, h, w or wb, c, h * wb * c, wb * c, c)
+    y = yb[:, :, :W]
+    gamma, beta = torch.rand(C, device=dev) + 0.5, torch.randn(C, device=dev) * 0.2
+    rm, rv = torch.zeros(C, device=dev), torch.ones(C, device=dev)
+    nbt = torch.zeros(1, dtype=torch.int64, device=dev)
+    mi, ss = torch.zeros(2 * C, device=dev), torch.zeros(2 * C, device=dev)
+    sums = torch.zeros(2 * C, dtype=torch.float64, device=dev)
+    ws = torch.zeros(int(L.lib().dn_reduce_ws_floats(C)), device=dev)
+    st = L.stream_ptr()
+    vy = view(yb, L.DN_F16, W)
+    for _ in range(2):      # twice: the workspace counters must come back to zero
+        L.call('dn_bn_train_stats', C_.byref(vy), L.ptr(gamma), L.ptr(beta), L.ptr(rm), L.ptr(rv), L.ptr(nbt), 0.1, 1e-5, 1,
+               L.ptr(sums), L.ptr(mi), L.ptr(ss), L.ptr(ws), st)
+    torch.cuda.synchronize()
+    assert int(nbt) == 2
+    yf = y.float().permute(0, 3, 1, 2).contiguous().requires_grad_(True)
+    bn = torch.nn.BatchNorm2d(C).to(dev).train()
+    with torch.no_grad():
+        bn.weight.copy_(gamma); bn.bias.copy_(beta)
+    bn(yf); out_ref = bn(yf)
+    mean, var = yf.detach().mean((0, 2, 3)), yf.detach().var((0, 2, 3), unbiased=False)
+    assert torch.allclose(mi[:C], mean, rtol=1e-5, atol=1e-5)
+    assert torch.allclose(mi[C:], (var + 1e-5).rsqrt(), rtol=1e-4, atol=1e-5)
+    assert torch.allclose(rm, bn.running_mean, rtol=1e-4, atol=1e-5) and torch.allclose(rv, bn.running_var, rtol=1e-4, atol=1e-5)
+    assert torch.allclose(sums[:C].float(), yf.detach().sum((0, 2, 3)), rtol=1e-4, atol=1e-2)
+
+    Ho, Wo = (H // 2, W // 2) if pool else (H, W)
+    out = torch.zeros(N, Ho, Wo, C, device=dev, dtype=torch.float16)
+    out2 = torch.zeros(N, Ho, Wo, C, device=dev, dtype=torch.bfloat16)
+    vo, vo2 = view(out, L.DN_F16), view(out2, L.DN_BF16)
+    L.call('dn_bn_apply', C_.byref(vy), L.ptr(ss), None, L.ACT_RELU, pool, C_.byref(vo), C_.byref(vo2), st)
+    ref = F.relu(out_ref)
+    if pool:
+        ref = F.max_pool2d(ref, 2, 2)
+    got = out.float().permute(0, 3, 1, 2)
+    assert float((got - ref).norm() / ref.norm()) < 2e-3
+    assert float((out2.float().permute(0, 3, 1, 2) - ref).norm() / ref.norm()) < 8e-3
+
+    g = torch.randn(N, Ho, Wo, C, device=dev).bfloat16()
+    ref.backward(g.float().permute(0, 3, 1, 2))
+    red = torch.zeros(2 * C, dtype=torch.float64, device=dev)
+    dgam, dbet = torch.zeros(C, device=dev), torch.zeros(C, device=dev)
+    dyb = torch.zeros(N, H, Wb, C, device=dev, dtype=torch.bfloat16)
+    vg, vdy = view(g, L.DN_BF16), view(dyb, L.DN_BF16, W)
+    L.call('dn_bn_bwd_reduce', C_.byref(vg), C_.byref(vy), None, L.ptr(mi), L.ptr(gamma), L.ptr(beta), L.ACT_RELU, pool, L.ptr(red),
+           L.ptr(ws), st)
+    L.call('dn_bn_bwd_apply', C_.byref(vg), C_.byref(vy), None, L.ptr(mi), L.ptr(gamma), L.ptr(beta), L.ACT_RELU, pool, L.ptr(red),
+           float(N * H * W), 1.0, L.ptr(dgam), L.ptr(dbet), C_.byref(vdy), None, 0, st)
+    torch.cuda.synchronize()
+    dy = dyb[:, :, :W].float().permute(0, 3, 1, 2)
+    assert float((dy - yf.grad).norm() / yf.grad.norm()) < 2e-2
+    assert float((dgam - bn.weight.grad).norm() / bn.weight.grad.norm()) < 5e-3
+    assert float((dbet - bn.bias.grad).norm() / bn.bias.grad.norm()) < 5e-3
+    assert int(ws[:256].view(torch.int32).abs().sum()) == 0      # arrival counters left at zero
