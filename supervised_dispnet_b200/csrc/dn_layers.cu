@@ -104,9 +104,37 @@ DN_EXPORT int dn_unpack_wgrad(const float* src, float* dst, int T, int R, int Cc
 __global__ void __launch_bounds__(256) pack_jobs_kernel(const dn_pack_job* __restrict__ jobs) {
   dn_pdl_trigger();
   dn_pdl_wait();
+  __shared__ float tsm[32][33];
+  __shared__ long long toffs[DN_MAX_TAPS];          // torch-side offset of tap t (the divisions by k happen once per block)
   const dn_pack_job j = jobs[blockIdx.y];
   const unsigned k = (unsigned)j.k;
-  if (!j.unpack) {
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  if (threadIdx.x < (unsigned)j.T) toffs[threadIdx.x] = (long long)(threadIdx.x / k) * j.s_kh + (long long)(threadIdx.x % k) * j.s_kw;
+  __syncthreads();
+  if (!j.unpack && j.s_r < j.s_c) {
+    // Transposing pack (data-gradient layout [tap][Cin][Cout] of a [Cout][Cin][kh][kw] parameter): the fp32 side is
+    // contiguous along the packed ROW index, so a 32 x 32 (row, column) tile is read with the lanes along rows, turned in
+    // shared memory and written with the lanes along columns - both sides unit-stride across the warp.
+    const unsigned plane = (unsigned)j.R_pad * j.C_pad;
+    const unsigned tr = ((unsigned)j.R_pad + 31) / 32, tc = ((unsigned)j.C_pad + 31) / 32;
+    const float* src = (const float*)j.src;
+    for (unsigned tile = blockIdx.x; tile < tr * tc; tile += gridDim.x) {
+      const unsigned r0 = (tile / tc) * 32, c0 = (tile - (tile / tc) * tc) * 32;
+      for (unsigned t = 0; t < (unsigned)j.T; ++t) {
+        const long long toff = toffs[t];
+        for (int cc = wrp; cc < 32; cc += 8) {
+          const unsigned r = r0 + lane, c = c0 + cc;
+          tsm[cc][lane] = ((int)r < j.R && (int)c < j.Cc) ? src[r * j.s_r + c * j.s_c + toff] : 0.f;
+        }
+        __syncthreads();
+        for (int rr = wrp; rr < 32; rr += 8) {
+          const unsigned r = r0 + rr, c = c0 + lane;
+          if (r < (unsigned)j.R_pad && c < (unsigned)j.C_pad) dn_st(j.dst, j.dst_dtype, (long long)t * plane + (long long)r * j.C_pad + c, tsm[lane][rr]);
+        }
+        __syncthreads();
+      }
+    }
+  } else if (!j.unpack) {
     const float* src = (const float*)j.src;
     const unsigned plane = (unsigned)j.R_pad * j.C_pad;
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < plane; i += gridDim.x * blockDim.x) {
@@ -114,10 +142,37 @@ __global__ void __launch_bounds__(256) pack_jobs_kernel(const dn_pack_job* __res
       const unsigned c = i - r * (unsigned)j.C_pad;
       const bool in = (int)r < j.R && (int)c < j.Cc;
       const float* sp = src + r * j.s_r + c * j.s_c;
-      for (unsigned t = 0; t < (unsigned)j.T; ++t) {
-        const float v = in ? sp[(long long)(t / k) * j.s_kh + (long long)(t % k) * j.s_kw] : 0.f;
-        dn_st(j.dst, j.dst_dtype, (long long)t * plane + i, v);
+      if (j.dst_dtype == DN_F16) {
+        __half* d = (__half*)j.dst + i;
+        for (unsigned t = 0; t < (unsigned)j.T; ++t) d[(long long)t * plane] = __float2half_rn(in ? sp[toffs[t]] : 0.f);
+      } else if (j.dst_dtype == DN_BF16) {
+        __nv_bfloat16* d = (__nv_bfloat16*)j.dst + i;
+        for (unsigned t = 0; t < (unsigned)j.T; ++t) d[(long long)t * plane] = __float2bfloat16_rn(in ? sp[toffs[t]] : 0.f);
+      } else {
+        float* d = (float*)j.dst + i;
+        for (unsigned t = 0; t < (unsigned)j.T; ++t) d[(long long)t * plane] = in ? sp[toffs[t]] : 0.f;
       }
+    }
+  } else if (j.T <= 16 && j.s_c == j.T && j.s_kh == j.k && j.s_kw == 1) {
+    // Unpack into an [R][Cc][kh][kw] gradient (nn.Conv2d): for one row r, 32 columns x T taps are 32*T contiguous floats on
+    // the torch side.  A warp gathers them tap by tap (unit stride along the columns of the packed planes), stages them in
+    // shared memory and writes the run with unit stride.
+    __shared__ float usm[8][32 * 17];
+    const float* src = (const float*)j.src;
+    float* dst = (float*)j.dst;
+    const unsigned T = (unsigned)j.T;
+    const unsigned ctiles = ((unsigned)j.Cc + 31) / 32;
+    const unsigned units = (unsigned)j.R * ctiles;
+    const long long planeP = (long long)j.R_pad * j.C_pad;
+    for (unsigned u = blockIdx.x * 8 + wrp; u < units; u += gridDim.x * 8) {
+      const unsigned r = u / ctiles, c0 = (u - r * ctiles) * 32;
+      const unsigned nc = (unsigned)j.Cc - c0 < 32 ? (unsigned)j.Cc - c0 : 32;
+      const float* sp = src + (long long)r * j.C_pad + c0 + lane;
+      for (unsigned t = 0; t < T; ++t) usm[wrp][lane * T + t] = lane < (int)nc ? j.scale * sp[(long long)t * planeP] : 0.f;
+      __syncwarp();
+      float* dp = dst + r * j.s_r + (long long)c0 * T;
+      for (unsigned q = lane; q < nc * T; q += 32) dp[q] = usm[wrp][q];
+      __syncwarp();
     }
   } else {
     const float* src = (const float*)j.src;
@@ -128,8 +183,7 @@ __global__ void __launch_bounds__(256) pack_jobs_kernel(const dn_pack_job* __res
       const unsigned c = i - r * (unsigned)j.Cc;
       float* dp = dst + r * j.s_r + c * j.s_c;
       const float* sp = src + (long long)r * j.C_pad + c;
-      for (unsigned t = 0; t < (unsigned)j.T; ++t)
-        dp[(long long)(t / k) * j.s_kh + (long long)(t % k) * j.s_kw] = j.scale * sp[(long long)t * j.R_pad * j.C_pad];
+      for (unsigned t = 0; t < (unsigned)j.T; ++t) dp[toffs[t]] = j.scale * sp[(long long)t * j.R_pad * j.C_pad];
     }
   }
 }
