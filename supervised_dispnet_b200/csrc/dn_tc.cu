@@ -710,6 +710,7 @@ struct WgradTcParams {
   int num_items;           // ngroups * cp_tiles * cq_tiles * splits
   int stages;
   int n_mma;               // MMA N per tap (multiple of 16, <= BNQ)
+  int m64;                 // P has at most 64 channels: issue M = 64 MMAs (half the A-operand reads); 1 / 2 = TMEM row mapping variant
   int nacc;                // TMEM accumulator stages (2: the atomics of item i overlap the main loop of item i+1)
   int tmem_cols;
   int halo;                // 1: x is fetched once per pixel tile as a (8+2) x 16-pixel halo box, taps are shifted views
@@ -868,7 +869,12 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
     int acc = 0; uint32_t acc_phase = 0;
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
       const WgItem w = wg_decode(p, item);
-      const int cp = w.cpt * 128 + row;
+      // M = 64 accumulators: variant 1 = 16 rows per 32-lane TMEM quarter (row r in lane 32 * (r / 16) + r % 16),
+      // variant 2 = rows in lanes 0..63
+      int cp = w.cpt * 128 + row;
+      bool row_ok = true;
+      if (p.m64 == 1) { cp = w.cpt * 128 + q * 16 + lane; row_ok = lane < 16; }
+      else if (p.m64 == 2) { row_ok = row < 64; }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       for (int t = 0; t < w.nt; ++t) {
@@ -879,7 +885,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
           uint32_t r[16];
           tmem_ld16(taddr + c0, r);
           tmem_ld_wait();
-          if (cp < p.cp && w.cqt * BNQ + c0 < p.cq_pad) {
+          if (row_ok && cp < p.cp && w.cqt * BNQ + c0 < p.cq_pad) {
 #pragma unroll
             for (int j = 0; j < 16; j += 4)
               red_add_v4(drow + c0 + j, __uint_as_float(r[j]) * p.scale, __uint_as_float(r[j + 1]) * p.scale,
@@ -1339,7 +1345,12 @@ int dn_wgrad_tc(const dn_wgrad* p, cudaStream_t st) {
   const uint32_t stage_bytes = a_bytes + (halo ? (uint32_t)(BNQ / 64) * 16 * 10 * 128 : (uint32_t)P.tpc * b_bytes);
   P.stages = (int)((200 * 1024) / stage_bytes);
   if (P.stages > 8) P.stages = 8;
-  P.idesc = make_idesc(P0.dtype, p->q.dtype, 1, 1, 128, P.n_mma);
+  P.m64 = 0;
+  if (P.cp_blocks == 1) {
+    P.m64 = 1;
+    if (const char* e = getenv("DN_WGRAD_M64")) P.m64 = atoi(e);
+  }
+  P.idesc = make_idesc(P0.dtype, p->q.dtype, 1, 1, P.m64 ? 64 : 128, P.n_mma);
   P.dw = p->dw;
   P.cp = P0.C; P.cq = p->q.C; P.cp_pad = p->cp_pad; P.cq_pad = p->cq_pad;
   P.scale = p->scale;
