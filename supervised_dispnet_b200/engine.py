@@ -260,7 +260,8 @@ class ConvOp(Op):
             self.s_co, self.s_ci = self.Cin * T, T
         # ---- forward problems
         self.fwd_probs = []
-        if not transposed and stride == 2 and x.H % 2 == 0 and x.W % 2 == 0:
+        if not transposed and stride == 2 and x.H >= 2 and x.W >= 2:      # (odd sizes: the odd phases are one row / column shorter,
+            # what a tap reads beyond them is outside the image and zero-filled like any padding)
             # input pixel (2*ho + dh, 2*wo + dw) lives in phase (dh & 1, dw & 1) of x at (ho + (dh >> 1), wo + (dw >> 1)):
             # a strided convolution is a stride-1 gather over the four 2x2 phase views (which the tcgen05 kernel serves)
             ins = [x.phase(a, b) for a in range(2) for b in range(2)]
@@ -337,7 +338,7 @@ class ConvOp(Op):
         # ---- weight-gradient problems
         def wg_probs(q):
             probs = []
-            if not self.transposed and self.stride == 2 and q.H % 2 == 0 and q.W % 2 == 0:
+            if not self.transposed and self.stride == 2 and q.H >= 2 and q.W >= 2:
                 for a in range(2):          # one problem per input phase (see the forward tables)
                     for b in range(2):
                         taps = [(0, (kh - pad) >> 1, (kw - pad) >> 1, kh * k + kw) for kh in range(k) for kw in range(k)

@@ -73,6 +73,9 @@ CASES = [
     dict(cin=3, cout=4, k=7, stride=2, pad=3, transposed=False, hw=(9, 10)),
     dict(cin=3, cout=4, k=7, stride=2, pad=3, transposed=False, hw=(10, 12)),
     dict(cin=4, cout=3, k=5, stride=2, pad=2, transposed=False, hw=(8, 8)),
+    dict(cin=4, cout=3, k=3, stride=2, pad=1, transposed=False, hw=(4, 13)),      # DispNetS conv6 / conv7 shapes: odd widths
+    dict(cin=4, cout=3, k=3, stride=2, pad=1, transposed=False, hw=(2, 7)),
+    dict(cin=3, cout=4, k=3, stride=2, pad=1, transposed=False, hw=(5, 3)),
     dict(cin=4, cout=6, k=1, stride=2, pad=0, transposed=False, hw=(6, 6)),
     dict(cin=4, cout=3, k=4, stride=2, pad=1, transposed=True, out_pad=0, hw=(3, 5)),
     dict(cin=3, cout=5, k=3, stride=2, pad=1, transposed=True, out_pad=1, hw=(2, 4)),
