@@ -137,6 +137,17 @@ typedef struct dn_pack_job {
 } dn_pack_job;
 int dn_pack_jobs(const dn_pack_job* jobs, int njobs, void* stream);
 
+/* ---- first-layer convolutions (input = the image: 3 or 3*(1+R) channels; no data gradient) -------------------------
+ * The k x k convolution (models/DispNetS.py:17-19 conv1 7x7/2, models/Disp_res_50.py:46 stem, vgg16_bn features.0 3x3) is
+ * run as k taps over k*C channels of a row-expanded image
+ *   out[n][h][wo][kw*C + c] = x[n][h][stride*wo + kw - pad][c]   (zero outside), out: [N, H, Wo, k*C], out2: optional second
+ * copy in another dtype (the weight-gradient operand).  Weights: dst[kh][Cout_pad][Cx_pad], column kw*Cin + c. */
+int dn_rowx_expand(const dn_view* x, int k, int stride, int pad, const dn_view* out, const dn_view* out2, void* stream);
+int dn_rowx_pack_weight(const float* w /* [Cout][Cin][k][k] */, int Cout, int Cin, int k, void* dst, int dst_dtype, int cout_pad,
+                        int cx_pad, void* stream);
+int dn_rowx_unpack_wgrad(const float* dwp /* [k][cout_pad][cx_pad] */, float* grad /* [Cout][Cin][k][k] */, int Cout, int Cin, int k,
+                         int cout_pad, int cx_pad, float scale, void* stream);
+
 /* ---- convolutions (nn.Conv2d / nn.ConvTranspose2d fwd, dgrad, wgrad) ------------------------- */
 /* backend: 0 = CUDA-core tiled kernel (any shape/dtype), 1 = tcgen05/TMA kernel (fp16/bf16, stride 1). */
 int dn_igemm_run(const dn_igemm* p, int backend, void* stream);

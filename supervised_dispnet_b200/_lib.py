@@ -66,6 +66,9 @@ _SIGS = {
     'dn_igemm_tc_supported': ([C.POINTER(DnIgemm)], _I),
     'dn_wgrad_tc_supported': ([C.POINTER(DnWgrad)], _I),
     'dn_reduce_ws_floats': ([_I], _I64),
+    'dn_rowx_expand': ([_V, _I, _I, _I, _V, _V, _P], _I),
+    'dn_rowx_pack_weight': ([_P, _I, _I, _I, _P, _I, _I, _I, _P], _I),
+    'dn_rowx_unpack_wgrad': ([_P, _P, _I, _I, _I, _I, _I, _F, _P], _I),
     'dn_bn_stats': ([_V, _P, _P, _P], _I),
     'dn_bn_finalize': ([_P, _D, _P, _P, _P, _P, _F, _F, _I, _I, _P, _P, _I, _P], _I),
     'dn_bn_train_stats': ([_V, _P, _P, _P, _P, _P, _F, _F, _I, _P, _P, _P, _P, _P], _I),

@@ -98,6 +98,130 @@ DN_EXPORT int dn_unpack_wgrad(const float* src, float* dst, int T, int R, int Cc
   return 0;
 }
 
+// ---- first-layer convolutions: kernel columns folded into the channel dimension -------------------------------------------------
+// The input image has 3 (PoseExpNet: 3 * (1 + R)) channels; a k x k convolution over it as a gather-convolution spends one
+// 64-channel K chunk per tap on 3 real channels (49 taps for the 7x7 stems of DispNetS / PoseExpNet / Disp_res_50,
+// models/DispNetS.py:17-19, models/Disp_res_50.py:46).  Instead the image is expanded once per step to
+//   xr[n][h][wo][kw * C + c] = x[n][h][stride * wo + kw - pad][c]          (zero outside the image)
+// and the convolution becomes k taps (kernel rows only) over k * C channels, stride 1 in wo.  The weights are packed
+// to [kh][Cout_pad][Cx_pad] with column kw * C + c, the weight gradient comes back in that layout.
+__global__ void rowx_expand_kernel(dn_view x, int k, int stride, int pad, dn_view out, dn_view out2, int has_out2) {
+  dn_pdl_trigger();
+  dn_pdl_wait();
+  const int C = x.C, Cx = k * C;
+  const long long total = (long long)out.N * out.H * out.W * Cx;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(i % Cx);
+    long long q = i / Cx;
+    const int wo = (int)(q % out.W); q /= out.W;
+    const int h = (int)(q % out.H);
+    const int n = (int)(q / out.H);
+    const int kw = j / C, c = j - kw * C;
+    const int w = stride * wo + kw - pad;
+    const float v = (w >= 0 && w < x.W) ? dn_ld(x.ptr, x.dtype, dn_off(x, n, h, w) + c) : 0.f;
+    const long long o = dn_off(out, n, h, wo) + j;
+    dn_st(out.ptr, out.dtype, o, v);
+    if (has_out2) dn_st(out2.ptr, out2.dtype, dn_off(out2, n, h, wo) + j, v);
+  }
+}
+
+// 16-bit outputs whose pixel pitch is a multiple of 8: one thread per (pixel, 8-channel group), 16-byte stores; the channels
+// between k * C and the pitch are written as zeros (they are operand padding of the convolution)
+__global__ void __launch_bounds__(256) rowx_expand_vec_kernel(dn_view x, int k, int stride, int pad, dn_view out, dn_view out2, int has_out2) {
+  dn_pdl_trigger();
+  dn_pdl_wait();
+  const int C = x.C, Cx = k * C;
+  const unsigned groups = (unsigned)out.sW / 8;                 // out.sW == pixel pitch (dense buffer)
+  const unsigned total = (unsigned)out.N * out.H * out.W * groups;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned pix = i / groups, gidx = i - pix * groups;
+    const unsigned q = pix / (unsigned)out.W;
+    const int wo = (int)(pix - q * (unsigned)out.W);
+    const int n = (int)(q / (unsigned)out.H);
+    const int h = (int)(q - (unsigned)n * (unsigned)out.H);
+    float v[8];
+    const long long xrow = dn_off(x, n, h, 0);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int j = (int)gidx * 8 + e;
+      v[e] = 0.f;
+      if (j < Cx) {
+        const int kw = j / C, c = j - kw * C;
+        const int w = stride * wo + kw - pad;
+        if (w >= 0 && w < x.W) v[e] = dn_ld(x.ptr, x.dtype, xrow + (long long)w * x.sW + c);
+      }
+    }
+    const long long o = (long long)pix * out.sW + gidx * 8;
+    if (out.dtype == DN_F16) Vec8<__half>::store((__half*)out.ptr + o, v);
+    else Vec8<__nv_bfloat16>::store((__nv_bfloat16*)out.ptr + o, v);
+    if (has_out2) {
+      if (out2.dtype == DN_F16) Vec8<__half>::store((__half*)out2.ptr + o, v);
+      else Vec8<__nv_bfloat16>::store((__nv_bfloat16*)out2.ptr + o, v);
+    }
+  }
+}
+
+DN_EXPORT int dn_rowx_expand(const dn_view* x, int k, int stride, int pad, const dn_view* out, const dn_view* out2, void* stream) {
+  if (!x || !out || k < 1 || stride < 1 || out->C != k * x->C || out->N != x->N || out->H != x->H) return DN_E_ARG;
+  if (out2 && (out2->C != out->C || out2->N != out->N || out2->H != out->H || out2->W != out->W)) return DN_E_ARG;
+  auto dense16 = [](const dn_view* v) {
+    return v->dtype != DN_F32 && (v->sW % 8) == 0 && v->sH == (long long)v->W * v->sW && v->sN == (long long)v->H * v->sH &&
+           ((uintptr_t)v->ptr % 16) == 0 && v->sW >= v->C;
+  };
+  const bool vec = dense16(out) && (!out2 || (dense16(out2) && out2->sW == out->sW)) &&
+                   (long long)out->N * out->H * out->W * (out->sW / 8) < (1ll << 31);
+  const int cap = dn_num_sms() * 16;
+  if (vec) {
+    const long long total = (long long)out->N * out->H * out->W * (out->sW / 8);
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > cap) blocks = cap;
+    dn_launch(rowx_expand_vec_kernel, dim3(blocks), dim3(256), 0, dn_stream(stream), *x, k, stride, pad, *out, out2 ? *out2 : *out, out2 != nullptr);
+  } else {
+    const long long total = (long long)out->N * out->H * out->W * out->C;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > cap) blocks = cap;
+    dn_launch(rowx_expand_kernel, dim3(blocks), dim3(256), 0, dn_stream(stream), *x, k, stride, pad, *out, out2 ? *out2 : *out, out2 != nullptr);
+  }
+  DN_CHECK_LAUNCH();
+  return 0;
+}
+
+// unpack = 0: dst[kh][co][kw * Cin + c] = w[co][c][kh][kw] (16-bit or fp32 dst, padding untouched);  unpack = 1: the reverse, fp32, scaled
+__global__ void rowx_weight_kernel(const float* __restrict__ src, void* __restrict__ dst, int dst_dtype, int Cout, int Cin, int k,
+                                   int cout_pad, int cx_pad, int unpack, float scale) {
+  dn_pdl_trigger();
+  dn_pdl_wait();
+  const int total = Cout * Cin * k * k;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int kw = i % k;
+    int q = i / k;
+    const int kh = q % k; q /= k;
+    const int c = q % Cin;
+    const int co = q / Cin;
+    const long long pk = ((long long)kh * cout_pad + co) * cx_pad + kw * Cin + c;
+    if (!unpack) dn_st(dst, dst_dtype, pk, src[i]);
+    else ((float*)dst)[i] = scale * src[pk];
+  }
+}
+
+DN_EXPORT int dn_rowx_pack_weight(const float* w, int Cout, int Cin, int k, void* dst, int dst_dtype, int cout_pad, int cx_pad,
+                                  void* stream) {
+  if (!w || !dst || Cout < 1 || Cin < 1 || k < 1 || cout_pad < Cout || cx_pad < k * Cin) return DN_E_ARG;
+  const int total = Cout * Cin * k * k;
+  dn_launch(rowx_weight_kernel, dim3((total + 255) / 256), dim3(256), 0, dn_stream(stream), w, dst, dst_dtype, Cout, Cin, k, cout_pad, cx_pad, 0, 1.f);
+  DN_CHECK_LAUNCH();
+  return 0;
+}
+
+DN_EXPORT int dn_rowx_unpack_wgrad(const float* dwp, float* grad, int Cout, int Cin, int k, int cout_pad, int cx_pad, float scale,
+                                   void* stream) {
+  if (!dwp || !grad || Cout < 1 || Cin < 1 || k < 1 || cout_pad < Cout || cx_pad < k * Cin) return DN_E_ARG;
+  const int total = Cout * Cin * k * k;
+  dn_launch(rowx_weight_kernel, dim3((total + 255) / 256), dim3(256), 0, dn_stream(stream), dwp, (void*)grad, (int)DN_F32, Cout, Cin, k, cout_pad, cx_pad, 1, scale);
+  DN_CHECK_LAUNCH();
+  return 0;
+}
+
 // one thread per (row, column) of the packed matrices; it walks all taps, so the fp32 side is touched in contiguous
 // k*k-float runs ([..][kh][kw] is innermost in both nn.Conv2d and nn.ConvTranspose2d weights) and every packed plane is
 // written (read) with unit stride across the warp

@@ -104,6 +104,10 @@ class View:
         W = (self.W - b + 1) // 2
         return View(self.buf, self.c0, self.C, H, W, self.off + a * self.sH + b * self.sW, 2 * self.sH, 2 * self.sW)
 
+    def phase_h(self, a):
+        """every second row starting at row a (all columns)"""
+        return View(self.buf, self.c0, self.C, (self.H - a + 1) // 2, self.W, self.off + a * self.sH, 2 * self.sH, self.sW)
+
     def dn(self):
         if self._dn is None:
             es = self.buf.t.element_size()
@@ -220,6 +224,7 @@ class InputOp(Op):
         N, _, H, W = shapes[0]
         self.chans = [s[1] for s in shapes]
         self.buf = Buf(N, H, W, sum(self.chans), plan.prec.act, plan.device)
+        self.buf.is_input = True
         self.out = self.buf.view()
         self.shadow = plan.shadow_of(self.out) if plan.training else None
 
@@ -227,7 +232,7 @@ class InputOp(Op):
         c0 = 0
         for x, c in zip(plan.inputs, self.chans):
             L.call('dn_pack_input', L.ptr(x), x.shape[0], c, x.shape[2], x.shape[3], self.out.ref(), c0, plan.stream)
-            if self.shadow is not None:
+            if self.shadow is not None and getattr(self.buf, 'shadow_needed', False):    # (a row-expanded first conv has its own copy)
                 L.call('dn_pack_input', L.ptr(x), x.shape[0], c, x.shape[2], x.shape[3], self.shadow.ref(), c0, plan.stream)
             c0 += c
 
@@ -250,7 +255,23 @@ class ConvOp(Op):
         self.cinT_pad, self.coutT_pad = _ru(self.Cin, 16), _ru(self.Cout, 64)   # dgrad roles swapped
         T = k * k
         dev = plan.device
-        self.wp = torch.zeros((T, self.cout_pad, self.cin_pad), dtype=plan.prec.act, device=dev)
+        # first layer (input = the image, no data gradient): kernel columns folded into the channel dimension, k taps
+        # over k * Cin channels of a row-expanded copy of the image instead of k * k taps over 3 real channels each
+        self.rowx = (not transposed and not needs_dx and stride in (1, 2) and k > 1 and k * x.C <= 128 and tc_enabled()
+                     and plan.prec.act != torch.float32 and getattr(x.buf, 'is_input', False) and x.c0 == 0
+                     and x.C == x.buf.C and os.environ.get('DISPNET_B200_ROWX', '1') != '0')
+        if getattr(x.buf, 'is_input', False) and not self.rowx:
+            x.buf.shadow_needed = True          # this layer's weight gradient reads the gradient-dtype image of the input
+        if self.rowx:
+            cx = k * self.Cin
+            self.xr = Buf(x.N, x.H, out.W, cx, plan.prec.act, dev).view()
+            self.xr_g = None
+            if plan.training and plan.prec.grad != plan.prec.act:
+                self.xr_g = Buf(x.N, x.H, out.W, cx, plan.prec.grad, dev).view()
+            self.cin_pad = _ru(cx, 64)
+            self.wp = torch.zeros((k, self.cout_pad, self.cin_pad), dtype=plan.prec.act, device=dev)
+        else:
+            self.wp = torch.zeros((T, self.cout_pad, self.cin_pad), dtype=plan.prec.act, device=dev)
         self.kh = _i32arr([t // k for t in range(T)])
         self.kw = _i32arr([t % k for t in range(T)])
         # source strides of the torch parameter seen as [co][ci][kh][kw]
@@ -260,7 +281,14 @@ class ConvOp(Op):
             self.s_co, self.s_ci = self.Cin * T, T
         # ---- forward problems
         self.fwd_probs = []
-        if not transposed and stride == 2 and x.H >= 2 and x.W >= 2:      # (odd sizes: the odd phases are one row / column shorter,
+        if self.rowx:
+            if stride == 1:
+                ins, taps = [self.xr], [(0, kh - self.pad, 0, kh) for kh in range(k)]
+            else:       # input row 2*ho + kh - pad lives in row phase (kh - pad) & 1 at row ho + ((kh - pad) >> 1)
+                ins = [self.xr.phase_h(0), self.xr.phase_h(1)]
+                taps = [((kh - self.pad) & 1, (kh - self.pad) >> 1, 0, kh) for kh in range(k)]
+            self.fwd_probs.append(dict(ins=ins, out=out, taps=taps, stride=1))
+        elif not transposed and stride == 2 and x.H >= 2 and x.W >= 2:      # (odd sizes: the odd phases are one row / column shorter,
             # what a tap reads beyond them is outside the image and zero-filled like any padding)
             # input pixel (2*ho + dh, 2*wo + dw) lives in phase (dh & 1, dw & 1) of x at (ho + (dh >> 1), wo + (dw >> 1)):
             # a strided convolution is a stride-1 gather over the four 2x2 phase views (which the tcgen05 kernel serves)
@@ -302,6 +330,8 @@ class ConvOp(Op):
 
     # ---- weight (un)packing is batched over all layers of the plan: one dn_pack_jobs launch each (Plan._run_jobs)
     def job(self, plan, which):
+        if self.rowx:
+            return None          # packs / unpacks its weights itself (different column layout)
         T = self.k * self.k
         j = L.DnPackJob()
         j.T, j.k, j.s_kh, j.s_kw = T, self.k, self.k, 1
@@ -323,6 +353,11 @@ class ConvOp(Op):
     def fwd(self, plan):
         if self._fwd_built is None:
             self._fwd_built = self._build_fwd(plan)
+        if self.rowx:
+            L.call('dn_rowx_expand', self.x.ref(), self.k, self.stride, self.pad, self.xr.ref(),
+                   self.xr_g.ref() if self.xr_g is not None else None, plan.stream)
+            L.call('dn_rowx_pack_weight', L.ptr(plan.param(self.name + '.weight')), self.Cout, self.Cin, self.k, L.ptr(self.wp),
+                   _DT[plan.prec.act], self.cout_pad, self.cin_pad, plan.stream)
         b = plan.param(self.name + '.bias') if self.has_bias else None
         for p, be, fl in self._fwd_built:
             p.bias = b.data_ptr() if b is not None else None
@@ -333,12 +368,23 @@ class ConvOp(Op):
         T = self.k * self.k
         dev = plan.device
         self.gout = self.out.grad_view(g)
+        if self.rowx:
+            T = self.k
         self.dwp = plan.dwp_alloc(T * self.cout_pad * self.cin_pad).view(T, self.cout_pad, self.cin_pad)
         k, pad = self.k, self.pad
         # ---- weight-gradient problems
         def wg_probs(q):
             probs = []
-            if not self.transposed and self.stride == 2 and q.H >= 2 and q.W >= 2:
+            if self.rowx:
+                if self.stride == 1:
+                    probs.append(_mk_wgrad([self.gout], q, self.dwp, self.cout_pad, self.cin_pad, 1,
+                                           [(0, kh - pad, 0, kh) for kh in range(k)], 1.0))
+                else:
+                    for a in range(2):
+                        taps = [(0, (kh - pad) >> 1, 0, kh) for kh in range(k) if ((kh - pad) & 1) == a]
+                        if taps:
+                            probs.append(_mk_wgrad([self.gout], q.phase_h(a), self.dwp, self.cout_pad, self.cin_pad, 1, taps, 1.0))
+            elif not self.transposed and self.stride == 2 and q.H >= 2 and q.W >= 2:
                 for a in range(2):          # one problem per input phase (see the forward tables)
                     for b in range(2):
                         taps = [(0, (kh - pad) >> 1, (kw - pad) >> 1, kh * k + kw) for kh in range(k) for kw in range(k)
@@ -357,8 +403,8 @@ class ConvOp(Op):
             return [(p, _backend('wgrad', p), _wgrad_flops(p)) for p in probs]
 
         self.xq = None
-        self.wg = wg_probs(self.x)
-        if plan.prec.act != g and plan.prec.act != torch.float32 and tc_enabled():
+        self.wg = wg_probs(self.xr_g if (self.rowx and self.xr_g is not None) else (self.xr if self.rowx else self.x))
+        if not self.rowx and plan.prec.act != g and plan.prec.act != torch.float32 and tc_enabled():
             # kind::f16 MMAs need both operands in one format: use a just-in-time copy of x in the gradient dtype
             sh = plan.shadow_lookup(self.x)
             xq = sh if sh is not None else plan.scratch_buf(self.x.N, self.x.H, self.x.W, self.x.C, g).view()
@@ -427,16 +473,24 @@ class ConvOp(Op):
                     L.call('dn_copy_view', self.x_cp.ref(), self.xq_cp.ref(), 0, st)
                 for p, be, fl in self.wg:
                     L.call('dn_wgrad_run', C.byref(p), be, st, tag=('wgrad', be, fl, self.name))
+                self._rowx_unpack(plan, st)
         else:
             if self.xq is not None:
                 L.call('dn_copy_view', self.x_cp.ref(), self.xq_cp.ref(), 0, plan.stream)
             for p, be, fl in self.wg:
                 L.call('dn_wgrad_run', C.byref(p), be, plan.stream, tag=('wgrad', be, fl, self.name))
+            self._rowx_unpack(plan, plan.stream)
         if self.needs_dx:
             if self.dx_zero_first is not None:
                 self.dx_zero_first.buf.t.zero_()
             for p, be, fl in self.dg:
                 L.call('dn_igemm_run', C.byref(p), be, plan.stream, tag=('dgrad', be, fl, self.name))
+
+
+    def _rowx_unpack(self, plan, st):
+        if self.rowx:
+            L.call('dn_rowx_unpack_wgrad', L.ptr(self.dwp), L.ptr(plan.grad_of(self.name + '.weight')), self.Cout, self.Cin, self.k,
+                   self.cout_pad, self.cin_pad, 1.0 / plan.prec.gscale, st)
 
 
 class HeadConvOp(Op):
