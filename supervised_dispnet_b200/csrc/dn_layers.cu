@@ -1475,9 +1475,105 @@ static int ew_blocks(long long total) {
   return (int)b;
 }
 
+// 16-bit views, 8 channels per thread (ResNet stem pool 3/2/1 on [N, 128, 160, 64]: the scalar kernels above took 0.2 / 2.2 ms)
+__global__ void __launch_bounds__(256) maxpool_fwd_vec_kernel(dn_view x, dn_view out, int k, int s, int p) {
+  dn_pdl_trigger();
+  dn_pdl_wait();
+  const unsigned CG = (unsigned)out.C / 8;
+  const unsigned total = (unsigned)out.N * out.H * out.W * CG;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned cg = i % CG;
+    unsigned q = i / CG;
+    const int w = (int)(q % (unsigned)out.W); q /= (unsigned)out.W;
+    const int h = (int)(q % (unsigned)out.H);
+    const int n = (int)(q / (unsigned)out.H);
+    float best[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) best[e] = -INFINITY;
+    for (int a = 0; a < k; ++a) {
+      const int hi = h * s - p + a;
+      if (hi < 0 || hi >= x.H) continue;
+      for (int b = 0; b < k; ++b) {
+        const int wi = w * s - p + b;
+        if (wi < 0 || wi >= x.W) continue;
+        float v[8];
+        ldc<8>(x, dn_off(x, n, hi, wi) + cg * 8, v);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) best[e] = v[e] > best[e] ? v[e] : best[e];
+      }
+    }
+    stc<8>(out, dn_off(out, n, h, w) + cg * 8, best);
+  }
+}
+
+// gather form (deterministic): an input pixel collects dout of every window that covers it and whose FIRST maximum
+// (scan order kh, kw; strict >) it is - the same rule as the forward kernel
+__global__ void __launch_bounds__(256) maxpool_bwd_vec_kernel(dn_view dout, dn_view x, dn_view dx, int k, int s, int p, int accumulate) {
+  dn_pdl_trigger();
+  dn_pdl_wait();
+  const unsigned CG = (unsigned)x.C / 8;
+  const unsigned total = (unsigned)x.N * x.H * x.W * CG;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned cg = i % CG;
+    unsigned q = i / CG;
+    const int w = (int)(q % (unsigned)x.W); q /= (unsigned)x.W;
+    const int h = (int)(q % (unsigned)x.H);
+    const int n = (int)(q / (unsigned)x.H);
+    float mine[8], g[8];
+    ldc<8>(x, dn_off(x, n, h, w) + cg * 8, mine);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) g[e] = 0.f;
+    int oh_lo = (h + p - k + 1 + s - 1) / s; if (h + p - k + 1 < 0) oh_lo = 0;
+    int oh_hi = (h + p) / s; if (oh_hi > dout.H - 1) oh_hi = dout.H - 1;
+    int ow_lo = (w + p - k + 1 + s - 1) / s; if (w + p - k + 1 < 0) ow_lo = 0;
+    int ow_hi = (w + p) / s; if (ow_hi > dout.W - 1) ow_hi = dout.W - 1;
+    for (int oh = oh_lo; oh <= oh_hi; ++oh)
+      for (int ow = ow_lo; ow <= ow_hi; ++ow) {
+        // this pixel wins channel e of the window iff no earlier element is >= it and no later element is > it
+        unsigned win = 0xffu;
+        const int a0 = h - (oh * s - p), b0 = w - (ow * s - p);       // my position inside the window
+        for (int a = 0; a < k; ++a) {
+          const int hi = oh * s - p + a;
+          if (hi < 0 || hi >= x.H) continue;
+          for (int b = 0; b < k; ++b) {
+            const int wi = ow * s - p + b;
+            if (wi < 0 || wi >= x.W || (a == a0 && b == b0)) continue;
+            float v[8];
+            ldc<8>(x, dn_off(x, n, hi, wi) + cg * 8, v);
+            const bool earlier = a < a0 || (a == a0 && b < b0);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const bool beats = earlier ? (v[e] >= mine[e]) : (v[e] > mine[e]);
+              if (beats) win &= ~(1u << e);
+            }
+          }
+        }
+        if (win) {
+          float d[8];
+          ldc<8>(dout, dn_off(dout, n, oh, ow) + cg * 8, d);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) g[e] += ((win >> e) & 1u) ? d[e] : 0.f;
+        }
+      }
+    const long long o = dn_off(dx, n, h, w) + cg * 8;
+    if (accumulate) {
+      float old[8];
+      ldc<8>(dx, o, old);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) g[e] += old[e];
+    }
+    stc<8>(dx, o, g);
+  }
+}
+
 DN_EXPORT int dn_maxpool_fwd(const dn_view* x, const dn_view* out, int k, int stride, int pad, void* stream) {
   if (!x || !out || x->C != out->C) return DN_E_ARG;
   long long total = (long long)out->N * out->H * out->W * out->C;
+  if (dn_vec8_ok(x) && dn_vec8_ok(out) && total / 8 < (1ll << 31)) {
+    dn_launch(maxpool_fwd_vec_kernel, dim3(ew_blocks(total / 8)), dim3(256), 0, dn_stream(stream), *x, *out, k, stride, pad);
+    DN_CHECK_LAUNCH();
+    return 0;
+  }
   maxpool_fwd_kernel<<<ew_blocks(total), 256, 0, dn_stream(stream)>>>(*x, *out, k, stride, pad);
   DN_CHECK_LAUNCH();
   return 0;
@@ -1487,6 +1583,11 @@ DN_EXPORT int dn_maxpool_bwd(const dn_view* dout, const dn_view* x, const dn_vie
                              int accumulate, void* stream) {
   if (!x || !dout || !dx) return DN_E_ARG;
   long long total = (long long)x->N * x->H * x->W * x->C;
+  if (dn_vec8_ok(x) && dn_vec8_ok(dout) && dn_vec8_ok(dx) && total / 8 < (1ll << 31)) {
+    dn_launch(maxpool_bwd_vec_kernel, dim3(ew_blocks(total / 8)), dim3(256), 0, dn_stream(stream), *dout, *x, *dx, k, stride, pad, accumulate);
+    DN_CHECK_LAUNCH();
+    return 0;
+  }
   maxpool_bwd_kernel<<<ew_blocks(total), 256, 0, dn_stream(stream)>>>(*dout, *x, *dx, k, stride, pad, accumulate);
   DN_CHECK_LAUNCH();
   return 0;
