@@ -127,9 +127,9 @@ __global__ void __launch_bounds__(256, 4) bnf_stats_kernel(dn_view y, float* __r
 }
 
 // ---- apply: out = pool?(act(y * sc + sh)), optional second copy in another 16-bit type ------------------------------
-template <bool POOL>
+template <bool POOL, bool RES>      // RES: out = act(y * sc + sh + residual) (ResNet bottleneck tails; never together with POOL)
 __global__ void __launch_bounds__(256, 4) bnf_apply_kernel(dn_view y, const float* __restrict__ scale_shift, int act, dn_view out,
-                                                           dn_view out2, int has_out2, int CGb) {
+                                                           dn_view out2, int has_out2, int CGb, dn_view res) {
   BNF_PROLOGUE(out)
   if (!cvalid) return;
   float2 sc[4], sh[4];
@@ -142,16 +142,26 @@ __global__ void __launch_bounds__(256, 4) bnf_apply_kernel(dn_view y, const floa
   char* ob = (char*)out.ptr + (long long)c0 * 2;
   char* o2b = (char*)out2.ptr + (long long)c0 * 2;
   const long long yp = y.sW * 2, op = out.sW * 2, o2p = out2.sW * 2;
+  const char* rb = (const char*)res.ptr + (long long)c0 * 2;
+  const long long rp = res.sW * 2;
   if (!POOL) {
     unsigned px = blockIdx.x * PLn + pl;
     for (; px < npix; px += 2 * stride) {
       const bool ok1 = px + stride < npix && px + stride > px;
       const unsigned px1 = ok1 ? px + stride : px;
       const uint4 r0 = ld16(yb + (long long)px * yp), r1 = ld16(yb + (long long)px1 * yp);
+      uint4 q0 = r0, q1 = r1;
+      if (RES) { q0 = ld16(rb + (long long)px * rp); q1 = ld16(rb + (long long)px1 * rp); }
       float2 f[4];
       cvt8(r0, y.dtype, f);
 #pragma unroll
       for (int i = 0; i < 4; ++i) f[i] = __ffma2_rn(f[i], sc[i], sh[i]);
+      if (RES) {
+        float2 r[4];
+        cvt8(q0, res.dtype, r);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) f[i] = __fadd2_rn(f[i], r[i]);
+      }
       act8(f, act);
       st16(ob + (long long)px * op, pack8(f, out.dtype));
       if (has_out2) st16(o2b + (long long)px * o2p, pack8(f, out2.dtype));
@@ -159,6 +169,12 @@ __global__ void __launch_bounds__(256, 4) bnf_apply_kernel(dn_view y, const floa
         cvt8(r1, y.dtype, f);
 #pragma unroll
         for (int i = 0; i < 4; ++i) f[i] = __ffma2_rn(f[i], sc[i], sh[i]);
+        if (RES) {
+          float2 r[4];
+          cvt8(q1, res.dtype, r);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) f[i] = __fadd2_rn(f[i], r[i]);
+        }
         act8(f, act);
         st16(ob + (long long)px1 * op, pack8(f, out.dtype));
         if (has_out2) st16(o2b + (long long)px1 * o2p, pack8(f, out2.dtype));
@@ -198,15 +214,21 @@ __global__ void __launch_bounds__(256, 4) bnf_apply_kernel(dn_view y, const floa
 // ---- backward, pass 1: S1 = sum g, S2 = sum g * y  (g = dout * act'(.), routed to the arg-max position when pooled) ----------
 // pooled: picks the FIRST maximum of the pre-activation in window order (00, 01, 10, 11) - the same position the generic kernel
 // finds on the activated values, except among non-positive ReLU inputs where g is zero anyway
-template <bool POOL>
+template <bool POOL, bool RES = false>
 __device__ __forceinline__ void bnf_bwd_pix(const uint4* ry, const uint4& rg, int ydt, int gdt, const float2* sc, const float2* sh, int act,
-                                            float2* g, float2* ysel, unsigned& sel) {
+                                            float2* g, float2* ysel, unsigned& sel, const uint4* rres = nullptr, int rdt = 0) {
   cvt8(rg, gdt, g);
   if (!POOL) {
     cvt8(ry[0], ydt, ysel);
     float2 v[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) v[i] = __ffma2_rn(ysel[i], sc[i], sh[i]);
+    if (RES) {
+      float2 r[4];
+      cvt8(*rres, rdt, r);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[i] = __fadd2_rn(v[i], r[i]);
+    }
     act_grad8(g, v, act);
     sel = 0;
   } else {
@@ -233,10 +255,10 @@ __device__ __forceinline__ void bnf_bwd_pix(const uint4* ry, const uint4& rg, in
   }
 }
 
-template <bool POOL>
+template <bool POOL, bool RES>
 __global__ void __launch_bounds__(256, 3) bnf_bwd_reduce_kernel(dn_view dout, dn_view y, const float* __restrict__ mean_invstd,
                                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                                         int act, float* __restrict__ ws, int CGb, double* __restrict__ red) {
+                                                                         int act, float* __restrict__ ws, int CGb, double* __restrict__ red, dn_view res) {
   BNF_PROLOGUE(dout)
   float2 s1[4], s2[4];
 #pragma unroll
@@ -247,9 +269,11 @@ __global__ void __launch_bounds__(256, 3) bnf_bwd_reduce_kernel(dn_view dout, dn
     const char* yb = (const char*)y.ptr + (long long)c0 * 2;
     const char* gb = (const char*)dout.ptr + (long long)c0 * 2;
     const long long yp = y.sW * 2, gp = dout.sW * 2;
+    const char* rb = (const char*)res.ptr + (long long)c0 * 2;
+    const long long rp = res.sW * 2;
     if (!POOL) {
       unsigned px = blockIdx.x * PLn + pl;
-      for (; px + 3 * stride < npix && px + 3 * stride >= px; px += 4 * stride) {
+      for (; !RES && px + 3 * stride < npix && px + 3 * stride >= px; px += 4 * stride) {
         uint4 ry[4], rg[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -265,11 +289,30 @@ __global__ void __launch_bounds__(256, 3) bnf_bwd_reduce_kernel(dn_view dout, dn
           for (int i = 0; i < 4; ++i) { s1[i] = __fadd2_rn(s1[i], g[i]); s2[i] = __ffma2_rn(g[i], ys[i], s2[i]); }
         }
       }
+      for (; RES && px + stride < npix && px + stride >= px; px += 2 * stride) {      // residual operand: 2 pixels x 3 loads in flight
+        uint4 ry[2], rg[2], rr[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          ry[u] = ld16(yb + (long long)(px + u * stride) * yp);
+          rg[u] = ld16(gb + (long long)(px + u * stride) * gp);
+          rr[u] = ld16(rb + (long long)(px + u * stride) * rp);
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          float2 g[4], ys[4];
+          unsigned sel;
+          bnf_bwd_pix<false, true>(&ry[u], rg[u], y.dtype, dout.dtype, sc, sh, act, g, ys, sel, &rr[u], res.dtype);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { s1[i] = __fadd2_rn(s1[i], g[i]); s2[i] = __ffma2_rn(g[i], ys[i], s2[i]); }
+        }
+      }
       for (; px < npix; px += stride) {
         const uint4 ry = ld16(yb + (long long)px * yp), rg = ld16(gb + (long long)px * gp);
+        uint4 rr = ry;
+        if (RES) rr = ld16(rb + (long long)px * rp);
         float2 g[4], ys[4];
         unsigned sel;
-        bnf_bwd_pix<false>(&ry, rg, y.dtype, dout.dtype, sc, sh, act, g, ys, sel);
+        bnf_bwd_pix<false, RES>(&ry, rg, y.dtype, dout.dtype, sc, sh, act, g, ys, sel, &rr, res.dtype);
 #pragma unroll
         for (int i = 0; i < 4; ++i) { s1[i] = __fadd2_rn(s1[i], g[i]); s2[i] = __ffma2_rn(g[i], ys[i], s2[i]); }
       }
@@ -300,11 +343,12 @@ __global__ void __launch_bounds__(256, 3) bnf_bwd_reduce_kernel(dn_view dout, dn
 }
 
 // ---- backward, pass 2: dy = A * g - B - Cc * y ------------------------------------------------------------------------
-template <bool POOL>
+template <bool POOL, bool RES>      // RES: the residual operand enters the activation; its gradient (= g) goes to dres (= or +=)
 __global__ void __launch_bounds__(256, 3) bnf_bwd_apply_kernel(dn_view dout, dn_view y, const float* __restrict__ mean_invstd,
                                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                         int act, const double* __restrict__ red, double count, float gscale,
-                                                                        float* dgamma, float* dbeta, dn_view dy, int CGb) {
+                                                                        float* dgamma, float* dbeta, dn_view dy, int CGb, dn_view res, dn_view dres,
+                                                                        int has_dres, int dres_acc) {
   BNF_PROLOGUE(dout)
   if (!cvalid) return;
   float2 sc[4], sh[4], nB[4], nC[4];      // A == sc;  nB = -B, nC = -Cc:  dy = fma(A, g, fma(nC, y, nB))
@@ -334,6 +378,9 @@ __global__ void __launch_bounds__(256, 3) bnf_bwd_apply_kernel(dn_view dout, dn_
   const char* gb = (const char*)dout.ptr + (long long)c0 * 2;
   char* ob = (char*)dy.ptr + (long long)c0 * 2;
   const long long yp = y.sW * 2, gp = dout.sW * 2, op = dy.sW * 2;
+  const char* rb = (const char*)res.ptr + (long long)c0 * 2;
+  char* db = (char*)dres.ptr + (long long)c0 * 2;
+  const long long rp = res.sW * 2, dp = dres.sW * 2;
   if (!POOL) {
     unsigned px = blockIdx.x * PLn + pl;
     for (; px < npix; px += 2 * stride) {
@@ -341,21 +388,28 @@ __global__ void __launch_bounds__(256, 3) bnf_bwd_apply_kernel(dn_view dout, dn_
       const unsigned px1 = ok1 ? px + stride : px;
       const uint4 ry0 = ld16(yb + (long long)px * yp), rg0 = ld16(gb + (long long)px * gp);
       const uint4 ry1 = ld16(yb + (long long)px1 * yp), rg1 = ld16(gb + (long long)px1 * gp);
-      {
+      uint4 rr0 = ry0, rr1 = ry1;
+      if (RES) { rr0 = ld16(rb + (long long)px * rp); rr1 = ld16(rb + (long long)px1 * rp); }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        if (u == 1 && !ok1) break;
+        const unsigned pxu = u ? px1 : px;
         float2 g[4], ys[4], o[4];
         unsigned sel;
-        bnf_bwd_pix<false>(&ry0, rg0, y.dtype, dout.dtype, sc, sh, act, g, ys, sel);
+        bnf_bwd_pix<false, RES>(u ? &ry1 : &ry0, u ? rg1 : rg0, y.dtype, dout.dtype, sc, sh, act, g, ys, sel, u ? &rr1 : &rr0, res.dtype);
 #pragma unroll
         for (int i = 0; i < 4; ++i) o[i] = __ffma2_rn(sc[i], g[i], __ffma2_rn(nC[i], ys[i], nB[i]));
-        st16(ob + (long long)px * op, pack8(o, dy.dtype));
-      }
-      if (ok1) {
-        float2 g[4], ys[4], o[4];
-        unsigned sel;
-        bnf_bwd_pix<false>(&ry1, rg1, y.dtype, dout.dtype, sc, sh, act, g, ys, sel);
+        st16(ob + (long long)pxu * op, pack8(o, dy.dtype));
+        if (RES && has_dres) {
+          char* d = db + (long long)pxu * dp;
+          if (dres_acc) {
+            float2 old[4];
+            cvt8(*reinterpret_cast<const uint4*>(d), dres.dtype, old);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) o[i] = __ffma2_rn(sc[i], g[i], __ffma2_rn(nC[i], ys[i], nB[i]));
-        st16(ob + (long long)px1 * op, pack8(o, dy.dtype));
+            for (int i = 0; i < 4; ++i) g[i] = __fadd2_rn(old[i], g[i]);
+          }
+          st16(d, pack8(g, dres.dtype));
+        }
       }
     }
   } else {

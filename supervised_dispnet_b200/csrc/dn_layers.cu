@@ -1029,12 +1029,13 @@ DN_EXPORT int dn_bn_apply(const dn_view* y, const float* scale_shift, const dn_v
   dn_view o2 = out2 ? *out2 : *out;
   if (out2 && (out2->C != out->C || out2->H != out->H || out2->W != out->W || out2->N != out->N)) return DN_E_ARG;
   bool vec = dn_vec8_ok(y) && dn_vec8_ok(out) && (!residual || dn_vec8_ok(residual)) && (!out2 || dn_vec8_ok(out2));
-  const bool fast = vec && g_bn_fast && !residual && dn_lin(y) && dn_lin(out) && (!out2 || dn_lin(out2)) && npix < (1ll << 31) &&
-                    (!pool || (y->H == 2 * out->H && y->W >= 2 * out->W));
+  const bool fast = vec && g_bn_fast && (!residual || (!pool && dn_lin(residual))) && dn_lin(y) && dn_lin(out) && (!out2 || dn_lin(out2)) &&
+                    npix < (1ll << 31) && (!pool || (y->H == 2 * out->H && y->W >= 2 * out->W));
   if (fast) {
     CgGeom g = cg_geom(out->C, 8, npix, 256, 4);
-    if (pool) dn_launch(bnf_apply_kernel<true>, g.grid, dim3(256), 0, dn_stream(stream), *y, scale_shift, act, *out, o2, out2 != nullptr, g.CGb);
-    else dn_launch(bnf_apply_kernel<false>, g.grid, dim3(256), 0, dn_stream(stream), *y, scale_shift, act, *out, o2, out2 != nullptr, g.CGb);
+    if (pool) dn_launch(bnf_apply_kernel<true, false>, g.grid, dim3(256), 0, dn_stream(stream), *y, scale_shift, act, *out, o2, out2 != nullptr, g.CGb, r);
+    else if (residual) dn_launch(bnf_apply_kernel<false, true>, g.grid, dim3(256), 0, dn_stream(stream), *y, scale_shift, act, *out, o2, out2 != nullptr, g.CGb, r);
+    else dn_launch(bnf_apply_kernel<false, false>, g.grid, dim3(256), 0, dn_stream(stream), *y, scale_shift, act, *out, o2, out2 != nullptr, g.CGb, r);
   } else if (vec) {
     CgGeom g = cg_geom(out->C, 8, npix);
     bn_apply_kernel<8><<<g.grid, 256, 0, dn_stream(stream)>>>(*y, scale_shift, r, residual != nullptr, act, pool, *out, o2, out2 != nullptr, g.CGb);
@@ -1206,10 +1207,11 @@ DN_EXPORT int dn_bn_bwd_reduce(const dn_view* dout, const dn_view* y, const dn_v
   CgGeom g = cg_geom(dout->C, ch, npix, vec ? 8 : 256, 3);
   if (g.grid.y > kWsCounters) return DN_E_UNSUPPORTED;
   const int hr = residual != nullptr;
-  const bool fast = vec && g_bn_fast && !residual && dn_lin(dout) && dn_lin(y) && npix < (1ll << 31) &&
+  const bool fast = vec && g_bn_fast && (!residual || (!pool && dn_lin(residual))) && dn_lin(dout) && dn_lin(y) && npix < (1ll << 31) &&
                     (!pool || (y->H == 2 * dout->H && y->W >= 2 * dout->W));
-  if (fast && pool) dn_launch(bnf_bwd_reduce_kernel<true>, g.grid, dim3(256), 0, st, *dout, *y, mean_invstd, gamma, beta, act, ws, g.CGb, red);
-  else if (fast) dn_launch(bnf_bwd_reduce_kernel<false>, g.grid, dim3(256), 0, st, *dout, *y, mean_invstd, gamma, beta, act, ws, g.CGb, red);
+  if (fast && pool) dn_launch(bnf_bwd_reduce_kernel<true, false>, g.grid, dim3(256), 0, st, *dout, *y, mean_invstd, gamma, beta, act, ws, g.CGb, red, r);
+  else if (fast && residual) dn_launch(bnf_bwd_reduce_kernel<false, true>, g.grid, dim3(256), 0, st, *dout, *y, mean_invstd, gamma, beta, act, ws, g.CGb, red, r);
+  else if (fast) dn_launch(bnf_bwd_reduce_kernel<false, false>, g.grid, dim3(256), 0, st, *dout, *y, mean_invstd, gamma, beta, act, ws, g.CGb, red, r);
   else if (vec && pool) bn_bwd_reduce_kernel<8, true><<<g.grid, 256, 0, st>>>(*dout, *y, r, hr, mean_invstd, gamma, beta, act, ws, g.CGb, red);
   else if (vec) bn_bwd_reduce_kernel<8, false><<<g.grid, 256, 0, st>>>(*dout, *y, r, hr, mean_invstd, gamma, beta, act, ws, g.CGb, red);
   else if (pool) bn_bwd_reduce_kernel<1, true><<<g.grid, 256, 0, st>>>(*dout, *y, r, hr, mean_invstd, gamma, beta, act, ws, g.CGb, red);
@@ -1319,12 +1321,14 @@ DN_EXPORT int dn_bn_bwd_apply(const dn_view* dout, const dn_view* y, const dn_vi
 #define BN_BWD_APPLY(CHV, PV)                                                                                              \
   bn_bwd_apply_kernel<CHV, PV><<<g.grid, 256, 0, st>>>(*dout, *y, r, hr, mean_invstd, gamma, beta, act, red, count, gscale, \
                                                        dgamma, dbeta, *dy, dr, hd, dres_accumulate, g.CGb)
-  const bool fast = vec && g_bn_fast && !residual && !dres && dn_lin(dout) && dn_lin(y) && dn_lin(dy) && npix < (1ll << 31) &&
+  const bool res_ok = (!residual && !dres) || (residual && !pool && dn_lin(residual) && (!dres || dn_lin(dres)));
+  const bool fast = vec && g_bn_fast && res_ok && dn_lin(dout) && dn_lin(y) && dn_lin(dy) && npix < (1ll << 31) &&
                     (!pool || (y->H == 2 * dout->H && y->W >= 2 * dout->W));
   if (fast) {
     CgGeom gf = cg_geom(dout->C, 8, npix, 256, 3);
-    if (pool) dn_launch(bnf_bwd_apply_kernel<true>, gf.grid, dim3(256), 0, st, *dout, *y, mean_invstd, gamma, beta, act, red, count, gscale, dgamma, dbeta, *dy, gf.CGb);
-    else dn_launch(bnf_bwd_apply_kernel<false>, gf.grid, dim3(256), 0, st, *dout, *y, mean_invstd, gamma, beta, act, red, count, gscale, dgamma, dbeta, *dy, gf.CGb);
+    if (pool) dn_launch(bnf_bwd_apply_kernel<true, false>, gf.grid, dim3(256), 0, st, *dout, *y, mean_invstd, gamma, beta, act, red, count, gscale, dgamma, dbeta, *dy, gf.CGb, r, dr, hd, dres_accumulate);
+    else if (residual) dn_launch(bnf_bwd_apply_kernel<false, true>, gf.grid, dim3(256), 0, st, *dout, *y, mean_invstd, gamma, beta, act, red, count, gscale, dgamma, dbeta, *dy, gf.CGb, r, dr, hd, dres_accumulate);
+    else dn_launch(bnf_bwd_apply_kernel<false, false>, gf.grid, dim3(256), 0, st, *dout, *y, mean_invstd, gamma, beta, act, red, count, gscale, dgamma, dbeta, *dy, gf.CGb, r, dr, hd, dres_accumulate);
   } else if (vec && pool) BN_BWD_APPLY(8, true);
   else if (vec) BN_BWD_APPLY(8, false);
   else if (pool) BN_BWD_APPLY(1, true);

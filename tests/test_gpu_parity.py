@@ -526,3 +526,60 @@ def test_bn_kernels_vs_torch(C, H, W, pool, crop):
     assert float((dgam - bn.weight.grad).norm() / bn.weight.grad.norm()) < 5e-3
     assert float((dbet - bn.bias.grad).norm() / bn.bias.grad.norm()) < 5e-3
     assert int(ws[:256].view(torch.int32).abs().sum()) == 0      # arrival counters left at zero
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('C,H,W,acc', [(64, 8, 12, 0), (256, 5, 7, 1), (20, 6, 9, 1)])
+def test_bn_residual_kernels_vs_torch(C, H, W, acc):
+    """out = relu(BN(y) + residual) and its backward (Bottleneck tail, reference models/Disp_res_50.py via torchvision
+    resnet50): dy, the residual gradient (overwrite / accumulate) and dgamma / dbeta vs torch.  C = 20 takes the generic
+    walkers, the others the fast paths.  Tolerances as in test_bn_kernels_vs_torch."""
+    import ctypes as C_
+    import torch
+    import torch.nn.functional as F
+    from supervised_dispnet_b200 import _lib as L
+    torch.manual_seed(C + W)
+    dev = torch.device('cuda')
+    N = 3
+    y = (torch.randn(N, H, W, C, device=dev) * 1.5 + 0.3).half()
+    r = torch.randn(N, H, W, C, device=dev).half()
+
+    def view(t, dt):
+        n, h, w, c = t.shape
+        return L.DnView(t.data_ptr(), dt, n, h, w, c, h * w * c, w * c, c)
+    gamma, beta = torch.rand(C, device=dev) + 0.5, torch.randn(C, device=dev) * 0.2
+    rm, rv = torch.zeros(C, device=dev), torch.ones(C, device=dev)
+    mi, ss = torch.zeros(2 * C, device=dev), torch.zeros(2 * C, device=dev)
+    ws = torch.zeros(int(L.lib().dn_reduce_ws_floats(C)), device=dev)
+    st = L.stream_ptr()
+    vy, vr = view(y, L.DN_F16), view(r, L.DN_F16)
+    L.call('dn_bn_train_stats', C_.byref(vy), L.ptr(gamma), L.ptr(beta), L.ptr(rm), L.ptr(rv), None, 0.1, 1e-5, 1, None, L.ptr(mi),
+           L.ptr(ss), L.ptr(ws), st)
+    out = torch.zeros(N, H, W, C, device=dev, dtype=torch.float16)
+    vo = view(out, L.DN_F16)
+    L.call('dn_bn_apply', C_.byref(vy), L.ptr(ss), C_.byref(vr), L.ACT_RELU, 0, C_.byref(vo), None, st)
+    yf = y.float().permute(0, 3, 1, 2).contiguous().requires_grad_(True)
+    rf = r.float().permute(0, 3, 1, 2).contiguous().requires_grad_(True)
+    bn = torch.nn.BatchNorm2d(C).to(dev).train()
+    with torch.no_grad():
+        bn.weight.copy_(gamma); bn.bias.copy_(beta)
+    ref = F.relu(bn(yf) + rf)
+    assert float((out.float().permute(0, 3, 1, 2) - ref.detach()).norm() / ref.detach().norm()) < 2e-3
+    g = torch.randn(N, H, W, C, device=dev).bfloat16()
+    ref.backward(g.float().permute(0, 3, 1, 2))
+    red = torch.zeros(2 * C, dtype=torch.float64, device=dev)
+    dgam, dbet = torch.zeros(C, device=dev), torch.zeros(C, device=dev)
+    dy = torch.zeros(N, H, W, C, device=dev, dtype=torch.bfloat16)
+    d0 = torch.randn(N, H, W, C, device=dev).bfloat16()
+    dres = d0.clone()
+    vg, vdy, vdr = view(g, L.DN_BF16), view(dy, L.DN_BF16), view(dres, L.DN_BF16)
+    L.call('dn_bn_bwd_reduce', C_.byref(vg), C_.byref(vy), C_.byref(vr), L.ptr(mi), L.ptr(gamma), L.ptr(beta), L.ACT_RELU, 0, L.ptr(red),
+           L.ptr(ws), st)
+    L.call('dn_bn_bwd_apply', C_.byref(vg), C_.byref(vy), C_.byref(vr), L.ptr(mi), L.ptr(gamma), L.ptr(beta), L.ACT_RELU, 0, L.ptr(red),
+           float(N * H * W), 1.0, L.ptr(dgam), L.ptr(dbet), C_.byref(vdy), C_.byref(vdr), acc, st)
+    torch.cuda.synchronize()
+    assert float((dy.float().permute(0, 3, 1, 2) - yf.grad).norm() / yf.grad.norm()) < 2e-2
+    dr = (dres.float() - (d0.float() if acc else 0)).permute(0, 3, 1, 2)
+    assert float((dr - rf.grad).norm() / rf.grad.norm()) < 2e-2
+    assert float((dgam - bn.weight.grad).norm() / bn.weight.grad.norm()) < 5e-3
+    assert float((dbet - bn.bias.grad).norm() / bn.bias.grad.norm()) < 5e-3
