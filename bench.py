@@ -229,7 +229,12 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
+    # set-up: the engine builds its plan on the 1st step and captures the forward / backward CUDA graphs on the 3rd / 4th; two
+    # priming steps here keep those one-time costs out of both the warm-up count and the timed region for any W >= 3
+    for _ in range(2):
+        step(x_d, gt_d)
+    n_warm = max(args.warmup, 3)
+    for _ in range(n_warm):
         step(x_d, gt_d)
     barrier()
     sampler = ClockSampler(local)
@@ -318,7 +323,7 @@ def run_ours(args):
     total_imgs = BATCH * world * args.steps
     value = total_imgs / (ms * 1e-3)
     e2e = total_imgs / (ms2 * 1e-3)
-    line = dict(metric=METRIC, value=value, unit='images/sec', n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
+    line = dict(metric=METRIC, value=value, unit='images/sec', n_gpus=world, steps=args.steps, warmup=n_warm,
                 ms_per_step=ms / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
                 dtype='fp16 operands, fp32 accumulate, bf16 gradient activations (DISPNET_B200_PRECISION=%s)' % os.environ.get('DISPNET_B200_PRECISION', 'mixed'), data='synthetic',
                 config=dict(workload='configs[1]: Disp_vgg_BN + L1 depth loss (+0*smooth as train.py does), synthetic KITTI '
