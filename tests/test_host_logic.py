@@ -188,3 +188,35 @@ def test_plans_build_on_cpu_and_backward_plan_is_consistent(cls, shape):
     trained = {n for n, p in named.items() if p.requires_grad and not n.startswith('bn1.')}
     assert set(plan.param_names) == trained
     assert len(plan.out_shapes) == 4
+
+
+# ---- train-loop helpers (host side of supervised_dispnet_b200.train) ---------------------------------------------------------
+def test_device_prefetcher_order_and_limit_cpu():
+    """_DevicePrefetcher hands out the loader's batches in order, keeps nested list / tuple structure, and never pulls more
+    than `limit` batches (the reference's loop breaks after epoch_size batches, train.py:536)."""
+    import torch
+    from supervised_dispnet_b200.train import _DevicePrefetcher
+    pulled = []
+
+    def gen():
+        for i in range(10):
+            pulled.append(i)
+            yield (torch.full((2,), float(i)), [torch.full((1,), i + 0.5), torch.full((1,), i + 0.25)], None)
+    got = list(_DevicePrefetcher(gen(), 'cpu', 4))
+    assert len(got) == 4 and pulled == [0, 1, 2, 3]
+    for i, (a, refs, none) in enumerate(got):
+        assert none is None and isinstance(refs, list)
+        assert a.tolist() == [float(i)] * 2 and refs[0].item() == i + 0.5 and refs[1].item() == i + 0.25
+    assert list(_DevicePrefetcher(iter([]), 'cpu', 3)) == []
+
+
+def test_loss_reader_average_cpu():
+    """_LossReader feeds every pushed loss into the meter exactly once (CPU path reads immediately)."""
+    import torch
+    from supervised_dispnet_b200.train import AverageMeter, _LossReader
+    m = AverageMeter(precision=4)
+    r = _LossReader(m, 'cpu')
+    for v in (1.0, 2.0, 6.0):
+        r.push(torch.tensor(v), 4)
+    r.flush()
+    assert m.count == 12 and abs(m.avg[0] - 3.0) < 1e-6
