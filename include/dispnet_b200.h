@@ -215,6 +215,10 @@ int dn_head_conv_bwd(const dn_view* x, const float* w, const dn_view* dz, const 
  * receives the x2-upsampled disparity (mode 0 nearest, 1 bilinear align_corners=False), cropped to the view. */
 int dn_head_fwd(const dn_view* z, float alpha, float beta, float* disp, const dn_view* up, int up_mode,
                 void* stream);
+/* the same with a second up-sampled copy `up2` (same geometry, another 16-bit dtype: the weight-gradient operand of the next
+ * iconv) written in the same pass when up_mode == 0 */
+int dn_head_fwd2(const dn_view* z, float alpha, float beta, float* disp, const dn_view* up, const dn_view* up2, int up_mode,
+                 void* stream);
 /* dz = (gscale*gdisp + upsample^T(dup)) * alpha*s*(1-s), s = sigmoid(z) recomputed from the saved conv output.
  * gdisp (fp32, from autograd, may be NULL) is unscaled; dup already carries the gradient scale. */
 int dn_head_bwd(const float* gdisp, const dn_view* dup, int up_mode, const dn_view* z, float alpha, float gscale,

@@ -85,6 +85,7 @@ _SIGS = {
     'dn_head_conv_fwd': ([_V, _P, _P, _V, _P], _I),
     'dn_head_conv_bwd': ([_V, _P, _V, _V, _I, _P, _P, _F, _P, _P], _I),
     'dn_head_fwd': ([_V, _F, _F, _P, _V, _I, _P], _I),
+    'dn_head_fwd2': ([_V, _F, _F, _P, _V, _V, _I, _P], _I),
     'dn_head_bwd': ([_P, _V, _I, _V, _F, _F, _V, _P], _I),
     'dn_sigmoid_nchw_fwd': ([_V, _P, _P], _I),
     'dn_sigmoid_nchw_bwd': ([_P, _P, _F, _V, _P], _I),

@@ -1770,6 +1770,48 @@ DN_EXPORT int dn_head_fwd(const dn_view* z, float alpha, float beta, float* disp
   return 0;
 }
 
+// disparity + nearest x2 up-sampled copies (activation dtype and, optionally, its gradient-dtype twin) in one pass
+__global__ void head_fwd_nearest_kernel(dn_view z, float alpha, float beta, float* __restrict__ disp, dn_view up, dn_view up2, int has_up2) {
+  dn_pdl_trigger();
+  dn_pdl_wait();
+  long long total = (long long)z.N * z.H * z.W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int w = (int)(i % z.W);
+    long long q = i / z.W;
+    int h = (int)(q % z.H), n = (int)(q / z.H);
+    const float v = alpha * dn_sigmoid(dn_ld(z.ptr, z.dtype, dn_off(z, n, h, w))) + beta;
+    disp[i] = v;
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        const int y = 2 * h + a, x = 2 * w + b;
+        if (y < up.H && x < up.W) {
+          dn_st(up.ptr, up.dtype, dn_off(up, n, y, x), v);
+          if (has_up2) dn_st(up2.ptr, up2.dtype, dn_off(up2, n, y, x), v);
+        }
+      }
+  }
+}
+
+/* dn_head_fwd with a second up-sampled copy (`up2`, same geometry as `up`, another dtype): saves the separate copy pass */
+DN_EXPORT int dn_head_fwd2(const dn_view* z, float alpha, float beta, float* disp, const dn_view* up, const dn_view* up2, int up_mode,
+                           void* stream) {
+  if (!z || !disp) return DN_E_ARG;
+  if (up && up_mode == 0 && up->H <= 2 * z->H && up->W <= 2 * z->W && up->N == z->N &&
+      (!up2 || (up2->H == up->H && up2->W == up->W && up2->N == up->N))) {
+    long long total = (long long)z->N * z->H * z->W;
+    dn_launch(head_fwd_nearest_kernel, dim3(ew_blocks(total)), dim3(256), 0, dn_stream(stream), *z, alpha, beta, disp, *up, up2 ? *up2 : *up,
+              up2 != nullptr);
+    DN_CHECK_LAUNCH();
+    return 0;
+  }
+  int e = dn_head_fwd(z, alpha, beta, disp, up, up_mode, stream);
+  if (e) return e;
+  if (up && up2) return dn_copy_view(up, up2, 0, stream);
+  return 0;
+}
+
 __global__ void head_bwd_kernel(const float* __restrict__ gdisp, dn_view dup, int has_up, int mode, dn_view z, float alpha,
                                 float gscale, dn_view dz) {
   dn_pdl_trigger();

@@ -624,10 +624,8 @@ class HeadOp(Op):
 
     def fwd(self, plan):
         out = plan.outputs[self.idx]
-        L.call('dn_head_fwd', self.z.ref(), self.alpha, self.beta, L.ptr(out), self.up.ref() if self.up else None,
-               self.up_mode, plan.stream)
-        if self.up_shadow is not None:
-            L.call('dn_copy_view', self.up.ref(), self.up_shadow.ref(), 0, plan.stream)
+        L.call('dn_head_fwd2', self.z.ref(), self.alpha, self.beta, L.ptr(out), self.up.ref() if self.up else None,
+               self.up_shadow.ref() if self.up_shadow is not None else None, self.up_mode, plan.stream)
 
     def plan_bwd(self, plan):
         g = plan.prec.grad
