@@ -142,9 +142,14 @@ def cpu_baseline(budget_s=20.0):
     t0 = time.time()
     step(x, gt)
     dt = time.time() - t0
-    return dict(value=b / dt, unit='images/sec', cores=torch.get_num_threads(), kind='port',
-                sample='1 step of the oracle port (torch CPU fp32: Disp_vgg_BN fwd + L1 + smooth + bwd + Adam) at b=%d, %dx%d, '
-                       'after a b=1 warm-up step' % (b, H, W))
+    n = 1
+    while dt < 0.5 * budget_s and n < 8:        # ~10-20 s of CPU work in total
+        step(x, gt)
+        n += 1
+        dt = time.time() - t0
+    return dict(value=n * b / dt, unit='images/sec', cores=torch.get_num_threads(), kind='port',
+                sample='%d step(s) of the oracle port (torch CPU fp32: Disp_vgg_BN fwd + L1 + smooth + bwd + Adam) at b=%d, %dx%d, '
+                       'after a b=1 warm-up step' % (n, b, H, W))
 
 
 def run_reference(args):
