@@ -28,6 +28,8 @@ extern "C" {
 #define DN_F32 0
 #define DN_F16 1
 #define DN_BF16 2
+/* pack-only code: the bf16 residual  bf16(v - float(bf16(v)))  of a split-precision operand (precision 'tc32') */
+#define DN_BF16_LO 3
 
 #define DN_ACT_NONE 0
 #define DN_ACT_RELU 1
@@ -36,8 +38,9 @@ extern "C" {
 #define DN_E_ARG (-1)
 #define DN_E_UNSUPPORTED (-2)
 
-#define DN_MAX_TAPS 49
-#define DN_MAX_SRC 4
+/* 7x7 taps x 3 split-precision terms; 4 stride-2 phases x (hi, lo) planes */
+#define DN_MAX_TAPS 160
+#define DN_MAX_SRC 8
 
 /* NHWC view of an activation tensor (strides in ELEMENTS of `dtype`; channel stride is 1). */
 typedef struct dn_view {
@@ -203,6 +206,11 @@ int dn_add_act_bwd(const dn_view* dout, const dn_view* out, int act, const dn_vi
 /* out (same shape) = act(x)  and its backward (not in place) */
 int dn_act_fwd(const dn_view* x, int act, const dn_view* out, void* stream);
 int dn_copy_view(const dn_view* src, const dn_view* dst, int accumulate, void* stream);
+/* Split-precision operands (precision 'tc32': fp32 storage, tcgen05 arithmetic): hi = bf16(x), lo = bf16(x - hi), so that
+ * x = hi + lo to 2^-18 relative.  A convolution then runs as the three tensor-core terms hi*w_hi + lo*w_hi + hi*w_lo of
+ * nn.Conv2d's fp32 product (models/Disp_vgg_BN.py:136-191 runs fp32 end to end).  x: fp32 view; hi, lo: bf16 views of the
+ * same geometry. */
+int dn_split_bf16(const dn_view* x, const dn_view* hi, const dn_view* lo, void* stream);
 
 /* ---- disparity heads (alpha*sigmoid(conv)+beta, models/Disp_vgg_BN.py:168) -------------------- */
 /* predict_disp's nn.Conv2d(C, 1, 3, padding=1) (models/Disp_vgg_BN.py:66-70): w is the fp32 torch parameter [1,C,3,3],

@@ -9,9 +9,9 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libdispnet_b200.so')
 
-DN_F32, DN_F16, DN_BF16 = 0, 1, 2
+DN_F32, DN_F16, DN_BF16, DN_BF16_LO = 0, 1, 2, 3
 ACT_NONE, ACT_RELU, ACT_LRELU = 0, 1, 2
-MAX_TAPS, MAX_SRC = 49, 4
+MAX_TAPS, MAX_SRC = 160, 8
 
 
 class DnView(C.Structure):
@@ -82,6 +82,7 @@ _SIGS = {
     'dn_add_act_bwd': ([_V, _V, _I, _V, _I, _V, _I, _P], _I),
     'dn_act_fwd': ([_V, _I, _V, _P], _I),
     'dn_copy_view': ([_V, _V, _I, _P], _I),
+    'dn_split_bf16': ([_V, _V, _V, _P], _I),
     'dn_head_conv_fwd': ([_V, _P, _P, _V, _P], _I),
     'dn_head_conv_bwd': ([_V, _P, _V, _V, _I, _P, _P, _F, _P, _P], _I),
     'dn_head_fwd': ([_V, _F, _F, _P, _V, _I, _P], _I),

@@ -61,6 +61,7 @@ __device__ __forceinline__ float dn_ld(const void* p, int dt, long long i) {
 __device__ __forceinline__ void dn_st(void* p, int dt, long long i, float v) {
   if (dt == DN_F32) ((float*)p)[i] = v;
   else if (dt == DN_F16) ((__half*)p)[i] = __float2half_rn(v);
+  else if (dt == DN_BF16_LO) ((__nv_bfloat16*)p)[i] = __float2bfloat16_rn(v - __bfloat162float(__float2bfloat16_rn(v)));
   else ((__nv_bfloat16*)p)[i] = __float2bfloat16_rn(v);
 }
 __host__ __device__ __forceinline__ int dn_esize(int dt) { return dt == DN_F32 ? 4 : 2; }

@@ -272,6 +272,8 @@ __global__ void __launch_bounds__(256) pack_jobs_kernel(const dn_pack_job* __res
       } else if (j.dst_dtype == DN_BF16) {
         __nv_bfloat16* d = (__nv_bfloat16*)j.dst + i;
         for (unsigned t = 0; t < (unsigned)j.T; ++t) d[(long long)t * plane] = __float2bfloat16_rn(in ? sp[toffs[t]] : 0.f);
+      } else if (j.dst_dtype == DN_BF16_LO) {
+        for (unsigned t = 0; t < (unsigned)j.T; ++t) dn_st(j.dst, DN_BF16_LO, (long long)t * plane + i, in ? sp[toffs[t]] : 0.f);
       } else {
         float* d = (float*)j.dst + i;
         for (unsigned t = 0; t < (unsigned)j.T; ++t) d[(long long)t * plane] = in ? sp[toffs[t]] : 0.f;
@@ -1649,6 +1651,64 @@ DN_EXPORT int dn_act_fwd(const dn_view* x, int act, const dn_view* out, void* st
 }
 DN_EXPORT int dn_copy_view(const dn_view* src, const dn_view* dst, int accumulate, void* stream) {
   return ew_launch(src, nullptr, DN_ACT_NONE, dst, accumulate, stream);
+}
+
+// fp32 view -> bf16 (hi, lo) planes of the same geometry: hi = bf16(x), lo = bf16(x - hi)   (precision 'tc32')
+template <int CH>
+__global__ void __launch_bounds__(256) split_bf16_kernel(dn_view x, dn_view hi, dn_view lo) {
+  dn_pdl_trigger();
+  dn_pdl_wait();
+  const unsigned CG = (x.C + CH - 1) / CH;
+  const unsigned total = (unsigned)x.N * x.H * x.W * CG;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    unsigned q = i / CG;
+    const int c0 = (int)(i - q * CG) * CH;
+    unsigned q2 = q / (unsigned)x.W;
+    const int w = (int)(q - q2 * (unsigned)x.W);
+    const int n = (int)(q2 / (unsigned)x.H);
+    const int h = (int)(q2 - (unsigned)n * (unsigned)x.H);
+    const float* xp = (const float*)x.ptr + dn_off(x, n, h, w) + c0;
+    __nv_bfloat16* hp = (__nv_bfloat16*)hi.ptr + dn_off(hi, n, h, w) + c0;
+    __nv_bfloat16* lp = (__nv_bfloat16*)lo.ptr + dn_off(lo, n, h, w) + c0;
+    if (CH == 8) {
+      const float4 a = *reinterpret_cast<const float4*>(xp), b = *reinterpret_cast<const float4*>(xp + 4);
+      const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+      float r[8];
+      uint4 uh;
+      __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&uh);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        h2[k] = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]);
+        const float2 f = __bfloat1622float2(h2[k]);
+        r[2 * k] = v[2 * k] - f.x;
+        r[2 * k + 1] = v[2 * k + 1] - f.y;
+      }
+      *reinterpret_cast<uint4*>(hp) = uh;
+      Vec8<__nv_bfloat16>::store(lp, r);
+    } else {
+      const float v = xp[0];
+      const __nv_bfloat16 hb = __float2bfloat16_rn(v);
+      hp[0] = hb;
+      lp[0] = __float2bfloat16_rn(v - __bfloat162float(hb));
+    }
+  }
+}
+
+DN_EXPORT int dn_split_bf16(const dn_view* x, const dn_view* hi, const dn_view* lo, void* stream) {
+  if (!x || !hi || !lo || x->dtype != DN_F32 || hi->dtype != DN_BF16 || lo->dtype != DN_BF16) return DN_E_ARG;
+  if (x->C != hi->C || x->N != hi->N || x->H != hi->H || x->W != hi->W) return DN_E_ARG;
+  if (x->C != lo->C || x->N != lo->N || x->H != lo->H || x->W != lo->W) return DN_E_ARG;
+  const bool vec = (x->C % 8) == 0 && ((uintptr_t)x->ptr % 16) == 0 && (x->sN % 4) == 0 && (x->sH % 4) == 0 && (x->sW % 4) == 0 &&
+                   dn_vec8_ok(hi) && dn_vec8_ok(lo);
+  if (vec) {
+    const long long total = (long long)x->N * x->H * x->W * (x->C / 8);
+    dn_launch(split_bf16_kernel<8>, dim3(ew_blocks(total)), dim3(256), 0, dn_stream(stream), *x, *hi, *lo);
+  } else {
+    const long long total = (long long)x->N * x->H * x->W * x->C;
+    dn_launch(split_bf16_kernel<1>, dim3(ew_blocks(total)), dim3(256), 0, dn_stream(stream), *x, *hi, *lo);
+  }
+  DN_CHECK_LAUNCH();
+  return 0;
 }
 
 template <int CH>

@@ -25,12 +25,20 @@ def _ru(x, m):
 
 class Precision:
     """Storage / compute types of a plan.  'fp32': CUDA-core kernels, fp32 everywhere (exact-parity mode).
+    'tc32': fp32 storage, split-bf16 (3-term) tcgen05 GEMMs -- the parity mode on the tensor cores.
     'fp16': fp16 activations and weights, gradient activations in `grad` dtype (scaled by `gscale` when
     fp16), fp32 accumulation everywhere, tcgen05 kernels where the problem shape allows."""
 
     def __init__(self, name):
         self.name = name
-        if name == 'fp32':
+        self.split = None
+        if name == 'tc32':
+            # fp32 storage and fp32-class arithmetic ON the tensor cores: every GEMM operand is split into two bf16 terms
+            # (hi = bf16(x), lo = bf16(x - hi); x = hi + lo to 2^-18) and a convolution runs as the three tcgen05 terms
+            # hi*w_hi + lo*w_hi + hi*w_lo with fp32 accumulation in TMEM (the dropped lo*w_lo term is 2^-18 relative).
+            # This is the mode that meets the reference's fp32 results to 1e-3 / 1e-5 (models/Disp_vgg_BN.py:136-191).
+            self.act, self.grad, self.gscale, self.split = torch.float32, torch.float32, 1.0, torch.bfloat16
+        elif name == 'fp32':
             self.act, self.grad, self.gscale = torch.float32, torch.float32, 1.0
         elif name == 'fp16':
             self.act, self.grad, self.gscale = torch.float16, torch.float16, 4096.0
@@ -75,6 +83,13 @@ class Buf:
     def view(self):
         return View(self, 0, self.C, self.H, self.W, 0, self.W * self.Cp, self.Cp)
 
+    def split_planes(self, dtype):
+        """(hi, lo) 16-bit planes of an fp32 buffer (precision 'tc32'); same N/H/W/C, hence the same element strides."""
+        if getattr(self, 'planes', None) is None:
+            self.planes = (Buf(self.N, self.H, self.W, self.C, dtype, self.t.device), Buf(self.N, self.H, self.W, self.C, dtype, self.t.device))
+            self.split_done = []       # channel intervals already split earlier in the forward op order (plan time)
+        return self.planes
+
     def grad_buf(self, gdtype):
         if self.grad is None:
             self.grad = Buf(self.N, self.H, self.W, self.C, gdtype, self.t.device)
@@ -107,6 +122,24 @@ class View:
     def phase_h(self, a):
         """every second row starting at row a (all columns)"""
         return View(self.buf, self.c0, self.C, (self.H - a + 1) // 2, self.W, self.off + a * self.sH, 2 * self.sH, self.sW)
+
+    def on(self, buf):
+        """The same region of another buffer with identical geometry (a gradient, shadow or split plane)."""
+        return View(buf, self.c0, self.C, self.H, self.W, self.off, self.sH, self.sW)
+
+    def planes(self, dtype):
+        hi, lo = self.buf.split_planes(dtype)
+        return self.on(hi), self.on(lo)
+
+    def claim_split(self, dtype):
+        """Plan time: True when this region's (hi, lo) planes are not yet produced by an earlier op of the forward order
+        (the caller then launches dn_split_bf16 for the whole view before its GEMM)."""
+        self.buf.split_planes(dtype)
+        lo, hi = self.c0, self.c0 + self.C
+        if any(a <= lo and hi <= b for a, b in self.buf.split_done):
+            return False
+        self.buf.split_done.append((lo, hi))
+        return True
 
     def dn(self):
         if self._dn is None:
@@ -206,6 +239,25 @@ def _wgrad_flops(p):
     return 2.0 * p.p[0].N * p.p[0].H * p.p[0].W * p.p[0].C * p.q.C * p.ntaps
 
 
+def _split3_igemm(ins, taps, T, dtype):
+    """Split-precision form of a gather-convolution (precision 'tc32'): every source view becomes its (hi, lo) planes
+    and every tap the three terms  hi * w_hi + lo * w_hi + hi * w_lo ; the packed weights hold the T hi matrices followed by
+    the T lo matrices."""
+    ins3 = []
+    for v in ins:
+        ins3 += list(v.planes(dtype))
+    taps3 = []
+    for (s_, dh, dw, wt) in taps:
+        taps3 += [(2 * s_, dh, dw, wt), (2 * s_ + 1, dh, dw, wt), (2 * s_, dh, dw, T + wt)]
+    return ins3, taps3
+
+
+def _full_extent(v):
+    """All pixels of v's buffer for v's channel slice (what dn_split_bf16 converts: phases and crops of it are views)."""
+    b = v.buf
+    return View(b, v.c0, v.C, b.H, b.W, 0, b.W * b.Cp, b.Cp)
+
+
 class Op:
     def fwd(self, plan):
         raise NotImplementedError
@@ -270,8 +322,15 @@ class ConvOp(Op):
                 self.xr_g = Buf(x.N, x.H, out.W, cx, plan.prec.grad, dev).view()
             self.cin_pad = _ru(cx, 64)
             self.wp = torch.zeros((k, self.cout_pad, self.cin_pad), dtype=plan.prec.act, device=dev)
+        elif plan.prec.split is not None:
+            self.wp = torch.zeros((2 * T, self.cout_pad, self.cin_pad), dtype=plan.prec.split, device=dev)     # [hi | lo]
         else:
             self.wp = torch.zeros((T, self.cout_pad, self.cin_pad), dtype=plan.prec.act, device=dev)
+        # split-precision operands: this op converts its input to (hi, lo) planes unless an earlier consumer already did
+        self.split_x = None
+        if plan.prec.split is not None:
+            xs = _full_extent(x)
+            self.split_x = xs if xs.claim_split(plan.prec.split) else False
         self.kh = _i32arr([t // k for t in range(T)])
         self.kw = _i32arr([t % k for t in range(T)])
         # source strides of the torch parameter seen as [co][ci][kh][kw]
@@ -323,12 +382,29 @@ class ConvOp(Op):
             o2 = None
             if self.out_shadow is not None:
                 o2 = self.out_shadow.phase(*pr['phase']) if 'phase' in pr else self.out_shadow
-            p = _mk_igemm(pr['ins'], pr['out'], self.wp, plan.prec.act, self.cin_pad, self.cout_pad, None, self.act, False,
-                          pr['stride'], pr['taps'], out2=o2)
-            built.append((p, _backend('igemm', p), _igemm_flops(p)))
+            ins, taps, wdt, div = pr['ins'], pr['taps'], plan.prec.act, 1.0
+            if plan.prec.split is not None:
+                ins, taps = _split3_igemm(ins, taps, self.k * self.k, plan.prec.split)
+                wdt, div = plan.prec.split, 3.0
+            p = _mk_igemm(ins, pr['out'], self.wp, wdt, self.cin_pad, self.cout_pad, None, self.act, False,
+                          pr['stride'], taps, out2=o2)
+            built.append((p, _backend('igemm', p), _igemm_flops(p) / div))
         return built
 
     # ---- weight (un)packing is batched over all layers of the plan: one dn_pack_jobs launch each (Plan._run_jobs)
+    def jobs(self, plan, which):
+        j = self.job(plan, which)
+        if j is None:
+            return []
+        if plan.prec.split is None or which == 'unpack':
+            return [j]
+        # split precision: the same pack once more for the residual matrices (planes T .. 2T-1 of the packed tensor)
+        j2 = self.job(plan, which)
+        j.dst_dtype, j2.dst_dtype = L.DN_BF16, L.DN_BF16_LO
+        T = self.k * self.k
+        j2.dst = j.dst + T * j.R_pad * j.C_pad * 2
+        return [j, j2]
+
     def job(self, plan, which):
         if self.rowx:
             return None          # packs / unpacks its weights itself (different column layout)
@@ -337,12 +413,12 @@ class ConvOp(Op):
         j.T, j.k, j.s_kh, j.s_kw = T, self.k, self.k, 1
         W = plan.param(self.name + '.weight')
         if which == 'fwd':
-            j.src, j.dst, j.dst_dtype, j.unpack = W.data_ptr(), self.wp.data_ptr(), _DT[plan.prec.act], 0
+            j.src, j.dst, j.dst_dtype, j.unpack = W.data_ptr(), self.wp.data_ptr(), _DT[plan.prec.split or plan.prec.act], 0
             j.R, j.Cc, j.R_pad, j.C_pad, j.s_r, j.s_c = self.Cout, self.Cin, self.cout_pad, self.cin_pad, self.s_co, self.s_ci
         elif which == 'dgrad':
             if not self.needs_dx:
                 return None
-            j.src, j.dst, j.dst_dtype, j.unpack = W.data_ptr(), self.wpT.data_ptr(), _DT[plan.prec.grad], 0
+            j.src, j.dst, j.dst_dtype, j.unpack = W.data_ptr(), self.wpT.data_ptr(), _DT[plan.prec.split or plan.prec.grad], 0
             j.R, j.Cc, j.R_pad, j.C_pad, j.s_r, j.s_c = self.Cin, self.Cout, self.cinT_pad, self.coutT_pad, self.s_ci, self.s_co
         else:
             j.src, j.dst, j.unpack = self.dwp.data_ptr(), plan.grad_of(self.name + '.weight').data_ptr(), 1
@@ -358,6 +434,9 @@ class ConvOp(Op):
                    self.xr_g.ref() if self.xr_g is not None else None, plan.stream)
             L.call('dn_rowx_pack_weight', L.ptr(plan.param(self.name + '.weight')), self.Cout, self.Cin, self.k, L.ptr(self.wp),
                    _DT[plan.prec.act], self.cout_pad, self.cin_pad, plan.stream)
+        if self.split_x:
+            hi, lo = self.split_x.planes(plan.prec.split)
+            L.call('dn_split_bf16', self.split_x.ref(), hi.ref(), lo.ref(), plan.stream)
         b = plan.param(self.name + '.bias') if self.has_bias else None
         for p, be, fl in self._fwd_built:
             p.bias = b.data_ptr() if b is not None else None
@@ -365,6 +444,7 @@ class ConvOp(Op):
 
     def plan_bwd(self, plan):
         g = plan.prec.grad
+        sp = plan.prec.split
         T = self.k * self.k
         dev = plan.device
         self.gout = self.out.grad_view(g)
@@ -373,38 +453,48 @@ class ConvOp(Op):
         self.dwp = plan.dwp_alloc(T * self.cout_pad * self.cin_pad).view(T, self.cout_pad, self.cin_pad)
         k, pad = self.k, self.pad
         # ---- weight-gradient problems
-        def wg_probs(q):
+        def wg_probs(q, gout=None, div=1.0):
+            gout = self.gout if gout is None else gout
             probs = []
             if self.rowx:
                 if self.stride == 1:
-                    probs.append(_mk_wgrad([self.gout], q, self.dwp, self.cout_pad, self.cin_pad, 1,
+                    probs.append(_mk_wgrad([gout], q, self.dwp, self.cout_pad, self.cin_pad, 1,
                                            [(0, kh - pad, 0, kh) for kh in range(k)], 1.0))
                 else:
                     for a in range(2):
                         taps = [(0, (kh - pad) >> 1, 0, kh) for kh in range(k) if ((kh - pad) & 1) == a]
                         if taps:
-                            probs.append(_mk_wgrad([self.gout], q.phase_h(a), self.dwp, self.cout_pad, self.cin_pad, 1, taps, 1.0))
+                            probs.append(_mk_wgrad([gout], q.phase_h(a), self.dwp, self.cout_pad, self.cin_pad, 1, taps, 1.0))
             elif not self.transposed and self.stride == 2 and q.H >= 2 and q.W >= 2:
                 for a in range(2):          # one problem per input phase (see the forward tables)
                     for b in range(2):
                         taps = [(0, (kh - pad) >> 1, (kw - pad) >> 1, kh * k + kw) for kh in range(k) for kw in range(k)
                                 if ((kh - pad) & 1) == a and ((kw - pad) & 1) == b]
                         if taps:
-                            probs.append(_mk_wgrad([self.gout], q.phase(a, b), self.dwp, self.cout_pad, self.cin_pad, 1, taps,
+                            probs.append(_mk_wgrad([gout], q.phase(a, b), self.dwp, self.cout_pad, self.cin_pad, 1, taps,
                                                    1.0))
             elif not self.transposed:
                 taps = [(0, kh - pad, kw - pad, kh * k + kw) for kh in range(k) for kw in range(k)]
-                probs.append(_mk_wgrad([self.gout], q, self.dwp, self.cout_pad, self.cin_pad, self.stride, taps, 1.0))
+                probs.append(_mk_wgrad([gout], q, self.dwp, self.cout_pad, self.cin_pad, self.stride, taps, 1.0))
             else:
                 for pr in self.fwd_probs:
                     a, b = pr['phase']
-                    probs.append(_mk_wgrad([self.gout.phase(a, b)], q, self.dwp, self.cout_pad, self.cin_pad, 1, pr['taps'],
+                    probs.append(_mk_wgrad([gout.phase(a, b)], q, self.dwp, self.cout_pad, self.cin_pad, 1, pr['taps'],
                                            1.0))
-            return [(p, _backend('wgrad', p), _wgrad_flops(p)) for p in probs]
+            return [(p, _backend('wgrad', p), _wgrad_flops(p) / div) for p in probs]
 
         self.xq = None
-        self.wg = wg_probs(self.xr_g if (self.rowx and self.xr_g is not None) else (self.xr if self.rowx else self.x))
-        if not self.rowx and plan.prec.act != g and plan.prec.act != torch.float32 and tc_enabled():
+        self.gsplit = None
+        if sp is not None:
+            # split precision: dw = g_hi^T x_hi + g_lo^T x_hi + g_hi^T x_lo, three launches that add into the same fp32 dw
+            # (the weight-gradient kernel accumulates with red.global.add); x's planes are the ones the forward made
+            self.gsplit = _full_extent(self.gout)
+            gh, gl = self.gout.planes(sp)
+            xh, xl = self.x.planes(sp)
+            self.wg = wg_probs(xh, gh, 3.0) + wg_probs(xh, gl, 3.0) + wg_probs(xl, gh, 3.0)
+        else:
+            self.wg = wg_probs(self.xr_g if (self.rowx and self.xr_g is not None) else (self.xr if self.rowx else self.x))
+        if sp is None and not self.rowx and plan.prec.act != g and plan.prec.act != torch.float32 and tc_enabled():
             # kind::f16 MMAs need both operands in one format: use a just-in-time copy of x in the gradient dtype
             sh = plan.shadow_lookup(self.x)
             xq = sh if sh is not None else plan.scratch_buf(self.x.N, self.x.H, self.x.W, self.x.C, g).view()
@@ -420,7 +510,7 @@ class ConvOp(Op):
         # ---- data-gradient problems
         self.dg = []
         if self.needs_dx:
-            self.wpT = torch.zeros((T, self.cinT_pad, self.coutT_pad), dtype=g, device=dev)
+            self.wpT = torch.zeros(((2 if sp is not None else 1) * T, self.cinT_pad, self.coutT_pad), dtype=sp or g, device=dev)
             gx = self.x.grad_view(g)
             acc = gx.claim_grad_write()
             self.dx_zero_first = None
@@ -450,9 +540,12 @@ class ConvOp(Op):
                     taps += [(len(ins) - 1, -dh, -dw, wt) for (_, dh, dw, wt) in pr['taps']]
                 probs = [dict(ins=ins, out=gx, taps=taps)]
             for pr in probs:
-                p = _mk_igemm(pr['ins'], pr['out'], self.wpT, g, self.coutT_pad, self.cinT_pad, None, L.ACT_NONE, acc, 1,
-                              pr['taps'])
-                self.dg.append((p, _backend('igemm', p), _igemm_flops(p)))
+                ins, taps, wdt, div = pr['ins'], pr['taps'], g, 1.0
+                if sp is not None:
+                    ins, taps = _split3_igemm(ins, taps, T, sp)
+                    wdt, div = sp, 3.0
+                p = _mk_igemm(ins, pr['out'], self.wpT, wdt, self.coutT_pad, self.cinT_pad, None, L.ACT_NONE, acc, 1, taps)
+                self.dg.append((p, _backend('igemm', p), _igemm_flops(p) / div))
 
     def bwd(self, plan):
         inv = 1.0 / plan.prec.gscale
@@ -460,6 +553,9 @@ class ConvOp(Op):
         if self.act != L.ACT_NONE or gb is not None:
             L.call('dn_act_bwd', self.gout.ref(), self.out.ref(), self.act, L.ptr(gb), inv, L.ptr(plan.reduce_ws(self.Cout)),
                    plan.stream)
+        if self.gsplit is not None:       # (hi, lo) planes of the output gradient: operands of both gradient GEMMs
+            gh, gl = self.gsplit.planes(plan.prec.split)
+            L.call('dn_split_bf16', self.gsplit.ref(), gh.ref(), gl.ref(), plan.stream)
         # the weight gradient only feeds the final unpack: it runs on the plan's side stream, concurrently with the data
         # gradient and the (HBM-bound) BatchNorm / activation backward passes of the layers below on the main stream
         side = plan.side_stream()
@@ -797,7 +893,7 @@ class Plan:
         key = (which, self._ptr_key())
         ent = self._job_tables.get(which)
         if ent is None or ent[0] != key:
-            jobs = [j for j in (op.job(self, which) for op in self.ops if isinstance(op, ConvOp)) if j is not None]
+            jobs = [j for op in self.ops if isinstance(op, ConvOp) for j in op.jobs(self, which)]
             arr = (L.DnPackJob * len(jobs))(*jobs)
             dev = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(self.device)
             ent = (key, dev, len(jobs))

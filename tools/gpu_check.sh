@@ -7,7 +7,7 @@ run() {  # name, env, args...
   local name=$1; shift
   local envs=$1; shift
   echo "######## $name"
-  env $envs timeout 150 python tools/gpu_check.py "$@" --out gpurun_out/check_$name.json > gpurun_out/check_$name.log 2>&1
+  env $envs timeout 400 python tools/gpu_check.py "$@" --out gpurun_out/check_$name.json > gpurun_out/check_$name.log 2>&1
   echo "exit=$?" >> gpurun_out/check_$name.log
   grep -E "^(conv|loss|model|full)/|^exit=|tc_available" gpurun_out/check_$name.log | cut -c1-220
 }
@@ -28,5 +28,8 @@ for s in $SECTIONS; do
     full_fp32) run full_fp32 "DISPNET_B200_BACKEND=generic" full --precision fp32 ;;
     full_bf16) run full_bf16 "A=1" full --precision bf16 ;;
     full_mixed) run full_mixed "A=1" full --precision mixed ;;
+    conv_tc32) run conv_tc32 "A=1" conv --precision tc32 ;;
+    models_tc32) run models_tc32 "A=1" models --precision tc32 ;;
+    full_tc32) run full_tc32 "A=1" full --precision tc32 ;;
   esac
 done
