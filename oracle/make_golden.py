@@ -240,5 +240,50 @@ def main():
         print('%-24s %8.1f KB' % (k, os.path.getsize(os.path.join(OUT, k + '.pt')) / 1024))
 
 
+G8_KEYS = ('features.features.0.weight', 'features.features.1.weight', 'features.features.40.weight', 'upconv4.0.weight',
+           'iconv2.0.weight', 'iconv0.0.weight', 'disp0.0.weight', 'disp3.0.bias')
+
+
+def g8_batches(n=3, b=4, h=128, w=416):
+    import _inputs as I
+    return [(I.images(b, h, w, seed=300 + i), I.sparse_gt(b, h, w, seed=310 + i, dataset='kitti')) for i in range(n)]
+
+
+def make_g8():
+    """G8: three steps of the UNMODIFIED reference `train.train` (train.py:394-539) with Adam on Disp_vgg_BN,
+    b=4, 128x416, `--loss L1`: the per-step [loss, loss_1, loss_2, loss_3] rows the loop itself logs (train.py:530-532), the
+    returned average, and a few parameters / BatchNorm buffers after the third optimizer step."""
+    import csv
+    import tempfile
+    from oracle import refshim as R
+    ref = R.import_reference(REF)
+    T = ref.train
+    net = ref.models.Disp_vgg_BN()
+    torch.manual_seed(0)               # same order as fixture G0: construct, seed, init_weights()
+    net.init_weights()
+    init = {k: v.clone() for k, v in net.state_dict().items()}
+    opt = torch.optim.Adam([p for p in net.parameters() if p.requires_grad], lr=2e-4, betas=(0.9, 0.999), weight_decay=0)
+    with tempfile.TemporaryDirectory() as d:
+        args = R.reference_args(d, batch_size=4)
+        T.device, T.n_iter = torch.device('cpu'), 0
+        avg = T.train(args, g8_batches(), net, torch.nn.Identity(), opt, 3, R.NullLogger(), None)
+        rows = [[float(v) for v in r] for r in csv.reader(open(os.path.join(d, args.log_full)), delimiter='\t')]
+    sd = net.state_dict()
+    out = dict(rows=rows, avg=float(avg),
+               params={k: I_sub(sd[k]) for k in G8_KEYS}, init={k: I_sub(init[k]) for k in G8_KEYS},
+               running={k: sd[k].clone() for k in sd if k.startswith('features.features.1.') and ('running' in k or 'num_batches' in k)})
+    torch.save(out, os.path.join(OUT, 'g8_train_trajectory.pt'))
+    print('g8 rows', rows, 'avg', avg)
+
+
+def I_sub(t):
+    import _inputs as I
+    return I.subsample(t)
+
+
 if __name__ == '__main__':
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == 'g8':
+        make_g8()
+    else:
+        main()
+        make_g8()

@@ -290,3 +290,58 @@ MODEL_CASES = [
     ('PoseExpNet_r4_exp', lambda p: pose_case(p, 4, True)),
     ('Disp_res_50_train', res50_case),
 ]
+
+
+# ------------------------------------------------------------------------------------------------------------
+# BASELINE configs[1] step at full image size: disparities, loss scalar, per-parameter gradients
+# ------------------------------------------------------------------------------------------------------------
+def _grad_errors(got, want, floor_frac=1e-3):
+    """Per-parameter and global L2-relative gradient errors of `got` against `want` (dicts name -> tensor).  A parameter's
+    error is taken relative to max(its own gradient norm, floor_frac x the global norm): analytically-zero gradients (conv
+    biases in front of BatchNorm) are judged on an absolute scale."""
+    gnorm = math.sqrt(sum(float(v.double().norm() ** 2) for v in want.values()))
+    num2, per = 0.0, {}
+    for k, w in want.items():
+        d = float((got[k].detach().double().cpu() - w.double()).norm())
+        num2 += d * d
+        per[k] = d / max(float(w.double().norm()), floor_frac * gnorm)
+    worst = max(per, key=per.get)
+    return dict(glob=math.sqrt(num2) / gnorm, worst=per[worst], worst_name=worst, per=per)
+
+
+def config2_step_case(precision, B=4, H=128, W=416, fp64=False, seed=200):
+    """Disp_vgg_BN (train mode) + l1_loss + 0*smooth_loss on B x 3 x H x W (train.py:420-522), product vs oracle (fp32 CPU),
+    optionally also vs the oracle evaluated in fp64 -- the yardstick for gradients: the fp32 reference itself is only
+    ~1e-3 away from the exact gradient of this 23-layer BatchNorm/ReLU stack."""
+    sd = ON.init_state_dict('Disp_vgg_BN', 0, skip_dead=True)
+    m = S.models.Disp_vgg_BN()
+    m.load_state_dict({k: v.clone() for k, v in sd.items()}, strict=False)
+    m.precision = precision
+    m.to(DEV).train()
+    x = I.images(B, H, W, seed=seed)
+    gt = I.sparse_gt(B, H, W, seed=seed + 1, dataset='kitti')
+
+    def oracle(dtype):
+        s = {k: (v.clone().to(dtype).requires_grad_(True) if v.dtype.is_floating_point and 'running' not in k
+                 else (v.clone().to(dtype) if v.dtype.is_floating_point else v.clone())) for k, v in sd.items()}
+        d = ON.disp_vgg_bn(s, x.to(dtype), True)
+        l = OL.l1_loss(gt.to(dtype), [1 / t for t in d], 'kitti')
+        l.backward()
+        return [t.detach() for t in d], float(l), {k: v.grad for k, v in s.items() if torch.is_tensor(v) and v.requires_grad and v.grad is not None}
+
+    d32, l32, g32 = oracle(torch.float32)
+    dp = m(x.to(DEV))
+    lp = PL.l1_loss(gt.to(DEV), [1 / d for d in dp], 'kitti') + 0.0 * PL.smooth_loss([1 / d for d in dp])
+    lp.backward()
+    gp = {k: p.grad for k, p in m.named_parameters() if p.grad is not None}
+    e32 = _grad_errors(gp, g32)
+    res = dict(disp=[rel(a, b) for a, b in zip(dp, d32)], loss=abs(float(lp) - l32) / abs(l32), grad_global=e32['glob'],
+               grad_worst=e32['worst'], grad_worst_name=e32['worst_name'], loss_value=float(lp))
+    if fp64:
+        d64, l64, g64 = oracle(torch.float64)
+        ep, er = _grad_errors(gp, g64), _grad_errors(g32, g64)
+        res.update(disp_vs64=[rel(a, b) for a, b in zip(dp, d64)], ref32_disp_vs64=[rel(a, b) for a, b in zip(d32, d64)],
+                   grad_global_vs64=ep['glob'], grad_worst_vs64=ep['worst'], grad_worst_name_vs64=ep['worst_name'],
+                   ref32_grad_global_vs64=er['glob'], ref32_grad_worst_vs64=er['worst'],
+                   worst_ratio=max(ep['per'][k] / max(er['per'][k], 1e-4) for k in g64))
+    return res

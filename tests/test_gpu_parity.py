@@ -184,7 +184,7 @@ def test_golden_g1_dispnets_eval_config1(golden):
     m = S.models.DispNetS()
     m.load_state_dict(ON.init_state_dict('DispNetS', 0))
     x = I.images(1, 128, 416, seed=1).to(DEV)
-    for prec, tol in (('fp32', 1e-5), ('mixed', 1e-3)):
+    for prec, tol in (('fp32', 1e-5), ('tc32', 5e-5), ('mixed', 1e-3)):
         m.precision = prec
         m.to(DEV).eval()
         with torch.no_grad():
@@ -199,7 +199,7 @@ def test_golden_g2_vgg_eval(golden):
     m = S.models.Disp_vgg_BN()
     m.load_state_dict(ON.init_state_dict('Disp_vgg_BN', 0, skip_dead=True), strict=False)
     x = I.images(1, 128, 416, seed=4).to(DEV)
-    for prec, tol in (('fp32', 1e-5), ('mixed', 1e-3)):
+    for prec, tol in (('fp32', 1e-5), ('tc32', 5e-5), ('mixed', 1e-3)):
         m.precision = prec
         m.to(DEV).eval()
         with torch.no_grad():
@@ -207,23 +207,24 @@ def test_golden_g2_vgg_eval(golden):
         assert rel(d, golden('g2_vgg_eval')) < tol, prec
 
 
-def test_golden_g2_vgg_train_fp32(golden):
+@pytest.mark.parametrize('prec,tol', [('fp32', 1e-5), ('tc32', 1e-4)])
+def test_golden_g2_vgg_train_fp32(golden, prec, tol):
     """Training-mode forward (4 disparities), BatchNorm running statistics after one step, and parameter gradients
-    against the reference-generated fixture (precision 'fp32')."""
+    against the reference-generated fixture (precisions 'fp32' = CUDA cores and 'tc32' = tcgen05 split-bf16)."""
     import supervised_dispnet_b200 as S
     from oracle import nets as ON
     g = golden('g2_vgg_train')
     m = S.models.Disp_vgg_BN()
     m.load_state_dict(ON.init_state_dict('Disp_vgg_BN', 0, skip_dead=True), strict=False)
-    m.precision = 'fp32'
+    m.precision = prec
     m.to(DEV).train()
     outs = m(I.images(2, 64, 96, seed=3).to(DEV))
     for o, r in zip(outs, g['outs']):
-        assert o.shape == r.shape and rel(o, r) < 1e-5
+        assert o.shape == r.shape and rel(o, r) < tol
     bufs = dict(m.named_buffers())
     for k, r in g['running'].items():
         if r.dtype.is_floating_point:
-            assert rel(bufs[k], r) < 1e-5, k
+            assert rel(bufs[k], r) < tol, k
         else:
             assert int(bufs[k]) == int(r), k
     sum((o * I.probe_like(o, 20 + i).to(DEV)).sum() for i, o in enumerate(outs)).backward()
@@ -235,7 +236,7 @@ def test_golden_g2_vgg_train_fp32(golden):
         a = I.subsample(named[k].grad.cpu())
         num += float((a.double() - r.double()).norm() ** 2)
         den += float(r.double().norm() ** 2)
-    assert math.sqrt(num / den) < 3e-3
+    assert math.sqrt(num / den) < (3e-3 if prec == 'fp32' else 1e-2)
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -296,6 +297,37 @@ def test_conv_layers_tcgen05(idx):
         assert all(b == 1 for b in r['backends']['fwd']), (name, r['backends'])     # really ran on the tensor cores
 
 
+@pytest.mark.parametrize('idx', range(16))
+def test_conv_layers_tc32(idx):
+    """precision 'tc32' (fp32 storage, three split-bf16 tcgen05 terms per product, fp32 TMEM accumulation) vs torch fp32
+    (TF32 off): fp32-class results ON the tensor cores.  Gradients of layers with a fused ReLU / LeakyReLU differ where a
+    pre-activation within ~1e-5 of zero changes sign (~sqrt(1e-5) of the L2 norm), hence 1e-2 there."""
+    import _harness as Hn
+    name, cfg, shape = _conv_cases()[idx]
+    r = Hn.conv_case(cfg, shape, 'tc32')
+    assert r['fwd'] < 3e-5, (name, r)
+    gtol = 1e-2 if cfg.get('act', 0) else 3e-5
+    for k in ('dx', 'dw', 'db'):
+        if k in r:
+            assert r[k] < gtol, (name, k, r)
+    for kind in ('fwd', 'dgrad', 'wgrad'):
+        assert all(b == 1 for b in r['backends'][kind]), (name, r['backends'])      # every GEMM really ran on tcgen05
+
+
+@pytest.mark.parametrize('name', ['Disp_vgg_BN_train', 'Disp_vgg_BN_eval', 'DispNetS_train', 'PoseExpNet_r2', 'PoseExpNet_r4_exp',
+                                  'Disp_res_50_train'])
+def test_models_tc32_vs_oracle(name):
+    """All four networks in the tensor-core parity mode: outputs within 1e-4 of the fp32 oracle (north star: 1e-3; Disp_res_50
+    at 64x96 normalises over 12 samples per channel in layer4 and is allowed 5e-4), BatchNorm running statistics 1e-4,
+    gradients within the fp32-vs-fp64 conditioning of the nets themselves."""
+    r = dict(P().MODEL_CASES)[name]('tc32')
+    assert r['out'] < (5e-4 if 'res_50' in name else 1e-4), r
+    if 'running' in r:
+        assert r['running'] < (3e-3 if 'res_50' in name else 1e-4), r
+    if 'gglobal' in r:
+        assert r['gglobal'] < (1e-1 if 'res_50' in name else 1e-2), r
+
+
 @pytest.mark.parametrize('name', ['Disp_vgg_BN_train', 'Disp_vgg_BN_eval', 'DispNetS_train', 'PoseExpNet_r2', 'PoseExpNet_r4_exp',
                                   'Disp_res_50_train'])
 def test_models_fp32_vs_oracle(name, monkeypatch):
@@ -316,36 +348,23 @@ def test_models_tcgen05_vs_oracle(name):
     assert r['out'] < (2e-2 if 'res_50' in name else 3e-3), r
 
 
-def test_config2_step_loss_and_disparity_full_size():
-    """BASELINE configs[1] at reduced batch: Disp_vgg_BN (train mode) + l1_loss on 4x3x128x416, tcgen05 path vs oracle:
-    disparities within 3e-3 (L2-relative), loss scalar within 1e-3, gradient direction cosine > 0.99."""
-    import supervised_dispnet_b200 as S
-    from supervised_dispnet_b200 import loss_functions as LF
-    from oracle import nets as ON, losses as OL
-    sd = ON.init_state_dict('Disp_vgg_BN', 0, skip_dead=True)
-    m = S.models.Disp_vgg_BN()
-    m.load_state_dict({k: v.clone() for k, v in sd.items()}, strict=False)
-    m.precision = 'mixed'
-    m.to(DEV).train()
-    x = I.images(4, 128, 416, seed=200)
-    gt = I.sparse_gt(4, 128, 416, seed=201, dataset='kitti')
-    sd_o = {k: (v.clone().requires_grad_(True) if v.dtype.is_floating_point and 'running' not in k else v.clone()) for k, v in sd.items()}
-    do = ON.disp_vgg_bn(sd_o, x, True)
-    lo = OL.l1_loss(gt, [1 / d for d in do], 'kitti')
-    lo.backward()
-    dp = m(x.to(DEV))
-    lp = LF.l1_loss(gt.to(DEV), [1 / d for d in dp], 'kitti') + 0.0 * LF.smooth_loss([1 / d for d in dp])
-    lp.backward()
-    for a, b in zip(dp, do):
-        assert rel(a, b) < 3e-3
-    assert abs(float(lp) - float(lo)) < 1e-3 * abs(float(lo))
-    named = dict(m.named_parameters())
-    dot = na = nb_ = 0.0
-    for k, v in sd_o.items():
-        if v.requires_grad and v.grad is not None and named[k].grad is not None:
-            a, b = named[k].grad.double().cpu().flatten(), v.grad.double().flatten()
-            dot += float(a @ b); na += float(a @ a); nb_ += float(b @ b)
-    assert dot / math.sqrt(na * nb_) > 0.99
+@pytest.mark.parametrize('precision', ['tc32', 'mixed'])
+def test_config2_step_loss_and_disparity_full_size(precision):
+    """BASELINE configs[1] at reduced batch: Disp_vgg_BN (train mode) + l1_loss (+0*smooth_loss, train.py:420-522) on
+    4x3x128x416 against the oracle.
+      tc32  (tensor-core parity mode): all four disparity maps within 1e-4 -- ten times inside the north star's 1e-3 --, loss
+             scalar 1e-5, gradients 1e-3 globally and 3e-2 for the worst single parameter (the fp32 reference itself is
+             2e-3 away from the fp64 gradient on that parameter, features.features.14.weight).
+      mixed (fp16 operands / bf16 gradient activations, the throughput mode): measured 1.4e-4 / 4.6e-4 / 1.2e-3 / 1.5e-3 on the
+             four scales -- it does NOT meet 1e-3 on the two coarse maps and is asserted at 3e-3; loss 1e-3; gradients 1e-2
+             globally, 0.25 worst parameter."""
+    r = P().config2_step_case(precision, B=4, H=128, W=416)
+    if precision == 'tc32':
+        assert max(r['disp']) < 1e-4, r
+        assert r['loss'] < 1e-5 and r['grad_global'] < 1e-3 and r['grad_worst'] < 3e-2, r
+    else:
+        assert max(r['disp']) < 3e-3 and r['disp'][0] < 1e-3, r
+        assert r['loss'] < 1e-3 and r['grad_global'] < 1e-2 and r['grad_worst'] < 0.25, r
 
 
 def test_no_cpu_fallback():

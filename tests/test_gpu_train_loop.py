@@ -87,3 +87,48 @@ def test_train_loop_configs(kind):
     moved = sum(int((a - b.detach()).abs().max() > 0) for a, b in zip(before, params))
     dead = 2 if kind == 'res50_nyu' else 0                                # Disp_res_50.bn1 never receives a gradient
     assert moved >= len(params) - dead - 13, (moved, len(params))         # (biases in front of BatchNorm get exact zeros)
+
+
+@pytest.mark.parametrize('precision,tol', [('tc32', 2e-4), ('mixed', 2e-3)])
+def test_unchanged_reference_train_loop_g8(golden, tmp_path, precision, tol):
+    """Drop-in claim (north star): the reference's OWN `train.train` (unmodified train.py:394-539, imported
+    from the staged checkout baseline/_ref) runs three Adam steps with `loss_functions` and the model swapped for this
+    package, and reproduces fixture G8 -- the per-step [loss, loss_1, loss_2, loss_3] rows the loop itself logs and the
+    returned average -- that the unmodified reference produced on CPU."""
+    import csv
+    import supervised_dispnet_b200 as S
+    from oracle import nets as ON, refshim as R
+    from oracle.make_golden import G8_KEYS, g8_batches
+    root = R.find_root()
+    assert root is not None, 'stage the reference first: python -m oracle.refshim (baseline/_ref is git-ignored, travels with gpurun)'
+    ref = R.import_reference(root)
+    T = ref.train
+    g = golden('g8_train_trajectory')
+    net = S.models.Disp_vgg_BN('kitti')
+    net.load_state_dict({k: v.clone() for k, v in ON.init_state_dict('Disp_vgg_BN', 0, skip_dead=True).items()}, strict=False)
+    net.precision = precision
+    net.to(DEV)
+    init = {k: v.detach().clone() for k, v in net.state_dict().items() if k in G8_KEYS}
+    opt = torch.optim.Adam([p for p in net.parameters() if p.requires_grad], lr=2e-4, betas=(0.9, 0.999), weight_decay=0)
+    args = R.reference_args(tmp_path, batch_size=4)
+    T.device, T.n_iter = torch.device(DEV), 0
+    T.loss_functions = S.loss_functions          # the reference's `import loss_functions` (train.py:17) swapped
+    avg = T.train(args, g8_batches(), net, torch.nn.Identity(), opt, 3, R.NullLogger(), None)
+    rows = [[float(v) for v in r] for r in csv.reader(open(tmp_path / args.log_full), delimiter='\t')]
+    assert len(rows) == 3
+    for r, q in zip(rows, g['rows']):
+        for a, b in zip(r, q):
+            assert abs(a - b) <= tol * max(abs(b), 1e-6), (rows, g['rows'])
+    assert abs(avg - g['avg']) <= tol * abs(g['avg'])
+    sd = net.state_dict()
+    for k in G8_KEYS:
+        du = (I.subsample(sd[k].detach().cpu()) - I.subsample(init[k].cpu()))
+        dr = g['params'][k] - g['init'][k]
+        assert float((du - dr).norm() / dr.norm().clamp_min(1e-30)) < 0.3, k
+    for k, v in g['running'].items():
+        if k.endswith('running_mean'):          # shifted by the +-lr Adam steps of the (zero-gradient) conv bias on the reference side
+            assert float((sd[k].cpu() - v).abs().max()) < 3 * 2e-4, k
+        elif v.dtype.is_floating_point:
+            assert float((sd[k].cpu() - v).norm() / v.norm()) < (1e-4 if precision == 'tc32' else 3e-3), k
+        else:
+            assert int(sd[k]) == int(v), k

@@ -228,3 +228,39 @@ def test_g9_layers_terms(golden):
     b = I.depth_map(1, 8, 200, seed=134).flatten()
     for u, v in zip(OL.compute_depth_errors(a, b), g9['depth_errors']):
         assert float(u) == pytest.approx(v, rel=1e-5)
+
+
+def test_g8_train_trajectory_oracle_port(golden):
+    """G8: three Adam steps of the unmodified reference `train.train` (train.py:394-539; fixture made by
+    oracle/make_golden.py:make_g8) against the same three steps on the oracle port -- pins the optimizer-coupled behaviour
+    (BatchNorm running statistics after more than one step, Adam on rounding-noise gradients) of the restatement."""
+    from oracle.make_golden import G8_KEYS, g8_batches
+    g = golden('g8_train_trajectory')
+    sd = ON.init_state_dict('Disp_vgg_BN', 0, skip_dead=True)
+    params = [v.requires_grad_(True) for k, v in sd.items() if v.dtype.is_floating_point and 'running' not in k]
+    opt = torch.optim.Adam(params, lr=2e-4, betas=(0.9, 0.999))
+    rows = []
+    for x, gt in g8_batches():
+        disp = ON.disp_vgg_bn(sd, x, True)
+        depth = [1 / d for d in disp]
+        l1, l3 = OL.l1_loss(gt, depth, 'kitti'), OL.smooth_loss(depth)
+        loss = 1.0 * l1 + 0.0 * l3
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        rows.append([float(loss), float(l1), 0.0, float(l3)])
+    for r, q in zip(rows, g['rows']):
+        for a, b in zip(r, q):
+            assert abs(a - b) <= 2e-4 * max(abs(b), 1e-6), (rows, g['rows'])
+    for k in G8_KEYS:
+        # parameter UPDATES (Adam moves every element by ~lr per step whatever the gradient's size, so elements whose
+        # gradient is round-off noise differ in sign between two fp32 implementations: compare on a loose L2 scale)
+        du, dr = I.subsample(sd[k].detach()) - g['init'][k], g['params'][k] - g['init'][k]
+        assert float((du - dr).norm() / dr.norm().clamp_min(1e-30)) < 0.2, k
+    for k, v in g['running'].items():
+        # the conv bias in front of this BatchNorm has an analytically zero gradient; Adam turns its round-off noise into
+        # +-lr steps per iteration, which shift the batch mean (not the variance) by the same amount on either side
+        if k.endswith('running_mean'):
+            assert float((sd[k] - v).abs().max()) < 3 * 2e-4, k
+        else:
+            assert rel(sd[k].float(), v.float()) < 1e-4, k
