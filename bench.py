@@ -12,6 +12,12 @@ backward -> Adam (what train.train() does per batch, reference train.py:420-522)
   roofline : the tcgen05 gather-convolution kernel (forward + data-gradient launches), algorithmic FLOPs / device time
           measured with CUDA events around every launch in a separate pass of the same step
   cpu_baseline : the oracle port (oracle/nets.py + oracle/losses.py, torch CPU fp32) on this box's host cores
+  parity   : the benchmarked step at b=32, 128x416 against the fp32 CPU oracle (disparities, loss, gradients) and the Abs Rel
+          figure (compute_errors(...)[1], loss_functions.py:444) of an eval-mode validation batch, reference vs this path
+  parity_mode : the same step in precision 'tc32' (fp32 storage, split-bf16 tcgen05 GEMMs: the tensor-core mode that meets the
+          north star's 1e-3) benched beside the headline mode, with its own parity figures
+  gpu_baseline : the reference's own modules (staged baseline/_ref, else the oracle port) on the same B200 through
+          PyTorch/cuDNN in fp32, TF32 and bf16-autocast -- the kernel to beat
 --impl reference times that CPU implementation alone (bounded sample per step).
 """
 import argparse
@@ -187,6 +193,159 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------------------
+def make_step(model, opt, LF):
+    def step(x, gt, m=None):
+        disp = (m or model)(x)
+        depth = [1 / d for d in disp]
+        loss = 1.0 * LF.l1_loss(gt, depth, 'kitti') + 0.0 * LF.smooth_loss(depth)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        return loss
+    return step
+
+
+def gpu_parity(precision, dev):
+    """The benchmarked step against the fp32 CPU oracle at the benchmark's own size (b=32, 128x416): L2-relative error of the
+    four disparity maps, relative error of the loss scalar, global / worst-parameter gradient error; plus Abs Rel
+    (compute_errors(...)[1]) of an eval-mode validation batch computed by the reference arithmetic and by this path."""
+    import _parity as P
+    import _inputs as I
+    import supervised_dispnet_b200 as S
+    from supervised_dispnet_b200 import loss_functions as LF
+    from oracle import nets as ON, losses as OL
+    t0 = time.time()
+    r = P.config2_step_case(precision, B=BATCH, H=H, W=W)
+    out = dict(precision=precision, batch=BATCH, disp_rel=max(r['disp']), disp_rel_per_scale=r['disp'], loss_rel=r['loss'],
+               grad_global_rel=r['grad_global'], grad_worst_param_rel=r['grad_worst'], grad_worst_param=r['grad_worst_name'])
+    # Abs Rel on a validation batch (validate_with_gt, train.py:642-723: eval-mode forward, depth = 1/disp, compute_errors)
+    sd = ON.init_state_dict('Disp_vgg_BN', 0, skip_dead=True)
+    xv, gv = I.images(8, H, W, seed=400), I.sparse_gt(8, H, W, seed=401, dataset='kitti', density=0.05)
+    with torch.no_grad():
+        d_ref = ON.disp_vgg_bn({k: v.clone() for k, v in sd.items()}, xv, False)
+        e_ref = OL.compute_errors(gv, 1 / d_ref[:, 0], 'kitti', True)
+        c_ref = OL.error_counters(gv, 1 / d_ref[:, 0], 'kitti', True)
+        m = S.models.Disp_vgg_BN()
+        m.load_state_dict({k: v.clone() for k, v in sd.items()}, strict=False)
+        m.precision = precision
+        m.to(dev).eval()
+        d_our = m(xv.to(dev))
+        e_our = LF.compute_errors(gv.to(dev), 1 / d_our[:, 0], 'kitti', True)
+        c_our, _ = LF.error_counters(gv.to(dev), (1 / d_ref[:, 0]).to(dev), 'kitti', True)     # identical (gt, pred): bit-exact ints
+    out.update(abs_rel_ref=e_ref[1], abs_rel_ours=e_our[1], abs_rel_rel_diff=abs(e_our[1] - e_ref[1]) / abs(e_ref[1]),
+               error_counters_bit_exact_on_identical_inputs=bool((torch.as_tensor(c_ref).cpu() == torch.as_tensor(c_our).cpu()).all()),
+               eval_disp_rel=float((d_our.cpu().double() - d_ref.double()).norm() / d_ref.double().norm()),
+               seconds=round(time.time() - t0, 1))
+    del m
+    torch.cuda.empty_cache()
+    return out
+
+
+def gpu_baseline(dev, steps=20, warmup=5):
+    """The reference's own Disp_vgg_BN + l1_loss + smooth_loss step (unmodified modules from baseline/_ref when staged, else the
+    oracle port) on this B200 through PyTorch/cuDNN, cudnn.benchmark as train.py sets it: fp32 (TF32 off), TF32 (PyTorch's
+    default for cuDNN convolutions) and bf16 autocast.  Also each mode's disparity error against the fp32 CPU oracle."""
+    import _inputs as I
+    from oracle import nets as ON, losses as OL, refshim as R
+    res = dict(source=None, modes={})
+    sd = ON.init_state_dict('Disp_vgg_BN', 0, skip_dead=True)
+    x_h, gt_h = synth_batch(BATCH, 10)
+    x, gt = x_h.to(dev), gt_h.to(dev)
+    xs = I.images(4, H, W, seed=200)
+    with torch.no_grad():
+        d_cpu = ON.disp_vgg_bn({k: v.clone() for k, v in sd.items()}, xs, True)
+    root = R.find_root()
+    ref = None
+    if root is not None:
+        try:
+            ref = R.import_reference(root, with_train=False)
+            res['source'] = 'unmodified reference modules (%s)' % os.path.relpath(root, ROOT) if root.startswith(ROOT) else root
+        except Exception as e:  # noqa: BLE001
+            res['import_error'] = repr(e)[:200]
+    if ref is None:
+        res['source'] = 'oracle port (functional restatement on torch ops)'
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark)
+    torch.backends.cudnn.benchmark = True
+    try:
+        for mode in ('fp32', 'tf32', 'bf16_autocast'):
+            torch.backends.cudnn.allow_tf32 = mode != 'fp32'
+            torch.backends.cuda.matmul.allow_tf32 = mode != 'fp32'
+            cast = torch.autocast('cuda', dtype=torch.bfloat16, enabled=(mode == 'bf16_autocast'))
+            if ref is not None:
+                net = ref.models.Disp_vgg_BN()
+                net.load_state_dict({k: v.clone() for k, v in sd.items()}, strict=False)
+                net = net.to(dev).train()
+                params = [p for p in net.parameters() if p.requires_grad]
+                fwd = lambda t: net(t)                                        # noqa: E731
+                l1, sm = ref.loss_functions.l1_loss, ref.loss_functions.smooth_loss
+            else:
+                sdd = {k: v.clone().to(dev) for k, v in sd.items()}
+                params = [v.requires_grad_(True) for k, v in sdd.items() if v.dtype.is_floating_point and 'running' not in k]
+                fwd = lambda t: ON.disp_vgg_bn(sdd, t, True)                  # noqa: E731
+                l1, sm = OL.l1_loss, OL.smooth_loss
+            opt = torch.optim.Adam(params, lr=2e-4, betas=(0.9, 0.999))
+            with torch.no_grad(), cast:
+                d = fwd(xs.to(dev))
+            err = max(float((a.float().cpu().double() - b.double()).norm() / b.double().norm()) for a, b in zip(d, d_cpu))
+
+            def step(full=True):
+                with cast:
+                    disp = fwd(x)
+                    depth = [1 / t.float() for t in disp]
+                    loss = (1.0 * l1(gt, depth, 'kitti') + 0.0 * sm(depth)) if full else sum(t.mean() for t in depth)
+                opt.zero_grad()
+                loss.backward()
+                opt.step()
+            out = {}
+            for tag, full in (('step', True), ('net_only', False)):
+                for _ in range(warmup):
+                    step(full)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(steps):
+                    step(full)
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / steps
+                out[tag + '_ms'] = ms
+                out[tag + '_images_per_sec'] = BATCH / (ms * 1e-3)
+            out['disp_rel_vs_cpu_fp32'] = err
+            res['modes'][mode] = out
+            del opt, params
+            torch.cuda.empty_cache()
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark = old
+    res['note'] = ('step = forward + l1_loss + 0*smooth_loss + backward + Adam at b=%d (the reference loss code syncs the host per '
+                   'sample, loss_functions.py:104-129); net_only = the same with a trivial loss; %d timed steps, CUDA events' % (BATCH, steps))
+    return res
+
+
+def unchanged_loop_e2e(net, opt, x_h, gt_h, steps, dev):
+    """images/sec through the reference's OWN train.train (unmodified train.py:394-539 from baseline/_ref) with this package's
+    model and loss_functions swapped in: blocking .to(device) copies, 3+ .item() syncs and a CSV append per step included."""
+    import tempfile
+    import supervised_dispnet_b200 as S
+    from oracle import refshim as R
+    root = R.find_root()
+    if root is None:
+        return dict(unavailable='reference checkout not staged (python -m oracle.refshim)')
+    ref = R.import_reference(root)
+    T = ref.train
+    T.device, T.n_iter = dev, 0
+    T.loss_functions = S.loss_functions
+    with tempfile.TemporaryDirectory() as d:
+        a = R.reference_args(d, batch_size=BATCH)
+        T.train(a, [(x_h, gt_h)] * 4, net, torch.nn.Identity(), opt, 4, R.NullLogger(), R.NullWriter())
+        torch.cuda.synchronize()
+        t0 = time.time()
+        T.train(a, [(x_h, gt_h)] * steps, net, torch.nn.Identity(), opt, steps, R.NullLogger(), R.NullWriter())
+        torch.cuda.synchronize()
+        dt = time.time() - t0
+    return dict(value=BATCH * steps / dt, unit='images/sec', ms_per_step=1000 * dt / steps, steps=steps,
+                loop='unmodified reference train.train (%s/train.py:394-539), models + loss_functions swapped' % os.path.basename(root))
+
+
 def run_ours(args):
     import torch.distributed as dist
     import supervised_dispnet_b200 as S
@@ -201,38 +360,43 @@ def run_ours(args):
         dist.init_process_group('nccl', device_id=dev)
     if L.lib().dn_tc_available() != 1:
         raise RuntimeError('tcgen05 path unavailable on this device; bench.py measures the sm_100a kernels only')
+    precision = args.precision
 
-    torch.manual_seed(0)
-    net = S.models.Disp_vgg_BN('kitti')
-    net.init_weights()
-    net = net.to(dev).train()
+    def build(prec):
+        torch.manual_seed(0)
+        net = S.models.Disp_vgg_BN('kitti')
+        net.init_weights()
+        net.precision = prec
+        return net.to(dev).train()
+
+    net = build(precision)
     model = net
     dp_mode = os.environ.get('DISPNET_B200_DP', 'flat')
     if world > 1:
         from supervised_dispnet_b200 import dist as D
         if dp_mode == 'ddp':       # torch DistributedDataParallel wrapper (bucketed all-reduce)
             model = D.wrap_ddp(net, dev)
-        else:                      # one NCCL all-reduce of the module's flat gradient arena per step
+        else:                      # NCCL all-reduce of the module's flat gradient arena, overlapped with the backward
             D.attach(net)
     params = [p for p in net.parameters() if p.requires_grad]
     opt = torch.optim.Adam(params, lr=2e-4, betas=(0.9, 0.999), fused=True)
 
     x_h, gt_h = synth_batch(BATCH, 10 + rank, pinned=True)
     x_d, gt_d = x_h.to(dev), gt_h.to(dev)
-
-    def step(x, gt, m=None):
-        disp = (m or model)(x)
-        depth = [1 / d for d in disp]
-        loss = 1.0 * LF.l1_loss(gt, depth, 'kitti') + 0.0 * LF.smooth_loss(depth)
-        opt.zero_grad()
-        loss.backward()
-        opt.step()
-        return loss
+    step = make_step(model, opt, LF)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def timed_steps(stp, n):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            loss = stp(x_d, gt_d)
+        e1.record()
+        return e0, e1, loss
 
     # set-up: the engine builds its plan on the 1st step and captures the forward / backward CUDA graphs on the 3rd / 4th; two
     # priming steps here keep those one-time costs out of both the warm-up count and the timed region for any W >= 3
@@ -245,11 +409,7 @@ def run_ours(args):
     sampler = ClockSampler(local)
     sampler.start()
     calls0 = L.CALLS
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        loss = step(x_d, gt_d)
-    e1.record()
+    e0, e1, loss = timed_steps(step, args.steps)
     sampler.sample()          # the device is still working through the enqueued steps here: at least one sample under load
     barrier()
     calls = L.CALLS - calls0
@@ -261,7 +421,7 @@ def run_ours(args):
     if args.minimal:
         if rank == 0:
             print(json.dumps(dict(metric=METRIC, value=BATCH * world * args.steps / (ms * 1e-3), ms_per_step=ms / args.steps,
-                                  minimal=True)), flush=True)
+                                  minimal=True, precision=precision)), flush=True)
         return
 
     # ---- e2e: public API with host batches
@@ -271,17 +431,21 @@ def run_ours(args):
         def __iter__(self):
             for _ in range(args.steps):
                 yield x_h, gt_h
-    T.train(targs, [(x_h, gt_h)] * 4, model, None, opt, 4)
-    barrier()
-    e0.record()
-    T.train(targs, Loader(), model, None, opt, args.steps)
-    e1.record()
-    barrier()
+
+    def e2e_ms(mdl, optim):
+        T.train(targs, [(x_h, gt_h)] * 4, mdl, None, optim, 4)
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        T.train(targs, Loader(), mdl, None, optim, args.steps)
+        b.record()
+        barrier()
+        t = torch.tensor([a.elapsed_time(b)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+    ms2 = e2e_ms(model, opt)
     sampler.stop_flag = True
-    ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
-    ms2 = float(ms2)
 
     if rank != 0:
         if world > 1:
@@ -313,32 +477,43 @@ def run_ours(args):
             for k, (t, f) in sorted(per.items(), key=lambda kv: -kv[1][0]):
                 fh.write('%-44s %8.3f ms %9.2f GFLOP %8.1f TFLOP/s\n' % (k, t, f / 1e9, f / (t * 1e-3) / 1e12 if t > 0 else 0))
     L.PROFILE = None
-    tc_t = sum(t for k, (t, n, f) in agg.items() if k.startswith('dn_igemm_run') and 'tc' in k) / nprof
-    tc_f = sum(f for k, (t, n, f) in agg.items() if k.startswith('dn_igemm_run') and 'tc' in k) / nprof
-    tc_n = sum(n for k, (t, n, f) in agg.items() if k.startswith('dn_igemm_run') and 'tc' in k) / nprof
+
+    def cls(prefix):
+        t = sum(t for k, (t, n, f) in agg.items() if k.startswith(prefix) and 'tc' in k) / nprof
+        f = sum(f for k, (t, n, f) in agg.items() if k.startswith(prefix) and 'tc' in k) / nprof
+        n = sum(n for k, (t, n, f) in agg.items() if k.startswith(prefix) and 'tc' in k) / nprof
+        return t, f, n
+    tc_t, tc_f, tc_n = cls('dn_igemm_run')
+    wg_t, wg_f, wg_n = cls('dn_wgrad_run')
     kern_ms = sum(t for (t, n, f) in agg.values()) / nprof
     achieved = tc_f / (tc_t * 1e-3) / 1e12 if tc_t > 0 else 0.0
+    wg_achieved = wg_f / (wg_t * 1e-3) / 1e12 if wg_t > 0 else 0.0
     breakdown = {k: round(t / nprof, 3) for k, (t, n, f) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:14]}
 
     traffic, traffic_src = None, None
-    tp = os.path.join(ROOT, 'profiles', 'r1_traffic.json')
-    if os.path.exists(tp):
-        tj = json.load(open(tp))
-        traffic, traffic_src = tj['dram_bytes_per_launch'], tj['source']
+    for tp in ('r2_traffic.json', 'r1_traffic.json'):
+        tp = os.path.join(ROOT, 'profiles', tp)
+        if os.path.exists(tp):
+            tj = json.load(open(tp))
+            traffic, traffic_src = tj['dram_bytes_per_launch'], tj['source']
+            break
     total_imgs = BATCH * world * args.steps
     value = total_imgs / (ms * 1e-3)
     e2e = total_imgs / (ms2 * 1e-3)
+    dtype_txt = {'mixed': 'fp16 operands, fp32 accumulate, bf16 gradient activations',
+                 'tc32': 'fp32 storage; split-bf16 (3-term) tcgen05 operands, fp32 accumulate'}.get(precision, precision)
     line = dict(metric=METRIC, value=value, unit='images/sec', n_gpus=world, steps=args.steps, warmup=n_warm,
                 ms_per_step=ms / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
-                dtype='fp16 operands, fp32 accumulate, bf16 gradient activations (DISPNET_B200_PRECISION=%s)' % os.environ.get('DISPNET_B200_PRECISION', 'mixed'), data='synthetic',
+                dtype='%s (precision=%s)' % (dtype_txt, precision), data='synthetic',
                 config=dict(workload='configs[1]: Disp_vgg_BN + L1 depth loss (+0*smooth as train.py does), synthetic KITTI '
-                                     '128x416, b=32/GPU, fwd+loss+bwd+Adam', global_batch=BATCH * world,
+                                     '128x416, b=32/GPU, fwd+loss+bwd+Adam', global_batch=BATCH * world, precision=precision,
                             parallelism='dp%d' % world, dp_mode=(dp_mode if world > 1 else None),
                             l2='per-step working set (activations+gradients ~4 GB) >> 126 MB L2; no explicit flush needed',
                             last_loss=last_loss),
                 clocks=sampler.summary(),
                 e2e=dict(value=e2e, unit='images/sec', h2d_bytes_per_step=x_h.numel() * 4 + gt_h.numel() * 4,
-                         d2h_bytes_per_step=4, ms_per_step=ms2 / args.steps),
+                         d2h_bytes_per_step=4, ms_per_step=ms2 / args.steps,
+                         api='supervised_dispnet_b200.train.train() (pipelined mirror of train.py:394-539)'),
                 gpu_launches=calls,
                 roofline=dict(bound='tensor', kernel='igemm_tc_kernel (forward + data-gradient gather-convolutions)',
                               achieved=achieved, peak=peaks['tf_sust'], unit='TFLOP/s', frac=achieved / peaks['tf_sust'],
@@ -346,8 +521,49 @@ def run_ours(args):
                               traffic_source=traffic_src, algorithmic_bytes_per_launch=ALGO_CONV_BYTES_PER_STEP / max(tc_n, 1),
                               peak_source=peaks['src'] + ' sustained bf16 (kernel timed inside a long step)',
                               launches_per_step=tc_n, kernel_ms_per_step=tc_t, flops_per_step=tc_f,
+                              wgrad=dict(kernel='wgrad_tc_kernel (weight-gradient GEMMs)', achieved=wg_achieved,
+                                         frac=wg_achieved / peaks['tf_sust'], launches_per_step=wg_n, kernel_ms_per_step=wg_t,
+                                         flops_per_step=wg_f),
                               step_fraction_of_tensor_roofline=(value / world * TRAIN_GFLOP_PER_IMG) / (peaks['tf_sust'] * 1e3)),
                 kernel_breakdown_ms_per_step=breakdown, all_kernels_ms_per_step=kern_ms)
+    if world == 1 and not args.no_extras:
+        def guarded(fn, *a):
+            try:
+                return fn(*a)
+            except Exception as e:  # noqa: BLE001
+                import traceback
+                traceback.print_exc()
+                return dict(error=repr(e)[:300])
+        line['e2e_unchanged_loop'] = guarded(unchanged_loop_e2e, net, opt, x_h, gt_h, args.steps, dev)
+        line['parity'] = guarded(gpu_parity, precision, dev)
+        other = 'tc32' if precision != 'tc32' else 'mixed'
+        del step, model, opt, params
+        net._plans = {}
+        del net
+        torch.cuda.empty_cache()
+
+        def second_mode():
+            net2 = build(other)
+            opt2 = torch.optim.Adam([p for p in net2.parameters() if p.requires_grad], lr=2e-4, betas=(0.9, 0.999), fused=True)
+            step2 = make_step(net2, opt2, LF)
+            for _ in range(2 + n_warm):
+                step2(x_d, gt_d)
+            torch.cuda.synchronize()
+            a, b, _ = timed_steps(step2, args.steps)
+            torch.cuda.synchronize()
+            m1 = a.elapsed_time(b)
+            m2 = e2e_ms(net2, opt2)
+            r = dict(precision=other, value=total_imgs / (m1 * 1e-3), unit='images/sec', ms_per_step=m1 / args.steps,
+                     e2e=dict(value=total_imgs / (m2 * 1e-3), unit='images/sec', ms_per_step=m2 / args.steps),
+                     step_fraction_of_tensor_roofline=(total_imgs / (m1 * 1e-3) * TRAIN_GFLOP_PER_IMG) / (peaks['tf_sust'] * 1e3))
+            net2._plans = {}
+            return r
+        pm = guarded(second_mode)
+        torch.cuda.empty_cache()
+        if 'error' not in pm:
+            pm['parity'] = guarded(gpu_parity, other, dev)
+        line['parity_mode' if other == 'tc32' else 'fast_mode'] = pm
+        line['gpu_baseline'] = guarded(gpu_baseline, dev)
     if world == 1 and not args.no_cpu:
         line['cpu_baseline'] = cpu_baseline()
     print(json.dumps(line), flush=True)
@@ -362,6 +578,9 @@ def main():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours')
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--no-extras', action='store_true', help='skip parity / second precision mode / cuDNN baseline (N=1 only)')
+    ap.add_argument('--precision', default=os.environ.get('DISPNET_B200_PRECISION', 'mixed'),
+                    help="headline precision: 'mixed' (fp16 operands) or 'tc32' (fp32-class split-bf16 tensor-core mode)")
     ap.add_argument('--dump', default=None, help='write per-layer conv kernel timings of the roofline pass here')
     ap.add_argument('--minimal', action='store_true', help='warm-up + timed steps only (for runs under ncu)')
     args = ap.parse_args()

@@ -266,7 +266,7 @@ def make_g8():
     with tempfile.TemporaryDirectory() as d:
         args = R.reference_args(d, batch_size=4)
         T.device, T.n_iter = torch.device('cpu'), 0
-        avg = T.train(args, g8_batches(), net, torch.nn.Identity(), opt, 3, R.NullLogger(), None)
+        avg = T.train(args, g8_batches(), net, torch.nn.Identity(), opt, 3, R.NullLogger(), R.NullWriter())
         rows = [[float(v) for v in r] for r in csv.reader(open(os.path.join(d, args.log_full)), delimiter='\t')]
     sd = net.state_dict()
     out = dict(rows=rows, avg=float(avg),

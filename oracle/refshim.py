@@ -136,6 +136,19 @@ class NullLogger(object):
         self.train_bar, self.train_writer = self._Bar(), self._Writer()
 
 
+class NullWriter(object):
+    """tensorboardX.SummaryWriter surface that train.train touches (train.py:490-515)."""
+
+    def __init__(self):
+        self.scalars = []
+
+    def add_scalar(self, tag, value, step):
+        self.scalars.append((tag, value, step))
+
+    def add_image(self, *a, **k):
+        pass
+
+
 def reference_args(save_path, **kw):
     """argparse defaults that train.train reads (train.py:28-91)."""
     import pathlib

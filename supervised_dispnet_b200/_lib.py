@@ -174,7 +174,20 @@ def ptr(t):
 
 
 def require_cuda(*tensors):
+    """Every tensor handed to a kernel must live on the CURRENT CUDA device: launches go to that device's current stream
+    (stream_ptr) and the library never switches devices, so a tensor of another GPU would be an illegal access / a
+    wrong-stream race.  One process per GPU with torch.cuda.set_device(LOCAL_RANK) (bench.py, DDP) satisfies this; use
+    `with torch.cuda.device(t.device):` otherwise."""
+    import torch
+    cur = None
     for t in tensors:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise RuntimeError('dispnet_b200: tensors must live on a CUDA device (got %s); the CUDA extension is the '
                                'only implementation of this path' % t.device)
+        if cur is None:
+            cur = torch.cuda.current_device()
+        if t.device.index != cur:
+            raise RuntimeError('dispnet_b200: tensor on cuda:%d but the current device is cuda:%d -- wrap the call in '
+                               '`with torch.cuda.device(tensor.device):`' % (t.device.index, cur))

@@ -578,7 +578,11 @@ class ConvOp(Op):
             self._rowx_unpack(plan, plan.stream)
         if self.needs_dx:
             if self.dx_zero_first is not None:
-                self.dx_zero_first.buf.t.zero_()
+                v = self.dx_zero_first
+                if v.c0 == 0 and v.C == v.buf.C:
+                    v.buf.t.zero_()
+                else:       # a channel slice of a shared (concat) gradient buffer: clear the slice only
+                    v.buf.t[..., v.c0:v.c0 + v.C].zero_()
             for p, be, fl in self.dg:
                 L.call('dn_igemm_run', C.byref(p), be, plan.stream, tag=('dgrad', be, fl, self.name))
 
@@ -636,7 +640,7 @@ class BNOp(Op):
         st = plan.stream
         g, b = plan.param(self.name + '.weight'), plan.param(self.name + '.bias')
         rm, rv = plan.buffer(self.name + '.running_mean'), plan.buffer(self.name + '.running_var')
-        if plan.training:      # statistics, finalize and num_batches_tracked += 1 in one launch
+        if plan.training and not plan.bn_frozen:      # statistics, finalize and num_batches_tracked += 1 in one launch
             L.call('dn_bn_train_stats', self.y.ref(), L.ptr(g), L.ptr(b), L.ptr(rm), L.ptr(rv),
                    L.ptr(plan.buffer(self.name + '.num_batches_tracked')), 0.1, 1e-5, 1, None, L.ptr(self.mean_invstd),
                    L.ptr(self.scale_shift), L.ptr(plan.reduce_ws(self.y.C)), st)
@@ -663,12 +667,14 @@ class BNOp(Op):
         if self.out is None:
             return
         st = plan.stream
+        # frozen statistics (plan.bn_frozen): mean / invstd are constants, dy = gamma * invstd * g -- the batch-mean terms of the
+        # training formula are sum / count, so an infinite count removes them while dgamma / dbeta keep their sums
         gm, bt = plan.param(self.name + '.weight'), plan.param(self.name + '.bias')
         res = self.res.ref() if self.res else None
         L.call('dn_bn_bwd_reduce', self.gout.ref(), self.y.ref(), res, L.ptr(self.mean_invstd), L.ptr(gm), L.ptr(bt),
                self.act, self.pool, L.ptr(self.red), L.ptr(plan.reduce_ws(self.y.C)), st)
         L.call('dn_bn_bwd_apply', self.gout.ref(), self.y.ref(), res, L.ptr(self.mean_invstd), L.ptr(gm), L.ptr(bt),
-               self.act, self.pool, L.ptr(self.red), self.count, 1.0 / plan.prec.gscale,
+               self.act, self.pool, L.ptr(self.red), (1e300 if plan.bn_frozen else self.count), 1.0 / plan.prec.gscale,
                L.ptr(plan.grad_of(self.name + '.weight')), L.ptr(plan.grad_of(self.name + '.bias')), self.gy.ref(),
                self.gres.ref() if self.gres else None, self.gres_acc, st)
 
@@ -778,11 +784,18 @@ class MeanOutOp(Op):
 
 
 class Plan:
-    def __init__(self, module, device, precision, training):
+    def __init__(self, module, device, precision, training, bn_frozen=False, only_train_dec=False):
         self.module = module
         self.device = device
         self.prec = Precision(precision)
         self.training = training
+        # train.py:405-411 `--diff_lr`: BatchNorm modules put in eval() inside a training network normalise with their running
+        # statistics (which are then constants of the graph) and leave the buffers alone; gamma / beta still train
+        self.bn_frozen = bool(bn_frozen)
+        # models/Disp_vgg_BN.py:148-153, models/Disp_res_50.py:154-160 `only_train_dec`: the encoder outputs are detached, so no
+        # op before `encoder_end` (set by the model's _build_plan) runs a backward and its parameters receive no gradient
+        self.only_train_dec = bool(only_train_dec)
+        self.encoder_end = 0
         self.ops = []
         self.param_names = []
         self.out_shapes = []
@@ -893,7 +906,8 @@ class Plan:
         key = (which, self._ptr_key())
         ent = self._job_tables.get(which)
         if ent is None or ent[0] != key:
-            jobs = [j for op in self.ops if isinstance(op, ConvOp) for j in op.jobs(self, which)]
+            ops = self.ops if which == 'fwd' else self.ops[self._bwd_cut():]
+            jobs = [j for op in ops if isinstance(op, ConvOp) for j in op.jobs(self, which)]
             arr = (L.DnPackJob * len(jobs))(*jobs)
             dev = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(self.device)
             ent = (key, dev, len(jobs))
@@ -927,7 +941,7 @@ class Plan:
         self._run_jobs('dgrad')
         if self.side_stream() is not None:          # the side stream must see the zeroed arenas / packed weights
             self._side.wait_stream(torch.cuda.current_stream())
-        for op in reversed(self.ops):
+        for op in reversed(self.ops[self._bwd_cut():]):
             op.bwd(self)
         if self._side is not None:
             torch.cuda.current_stream().wait_stream(self._side)
@@ -979,9 +993,23 @@ class Plan:
         self._dwp_arena = torch.zeros(sum(_ru(op.k * op.k * op.cout_pad * op.cin_pad, 64) for op in convs) + 64,
                                       dtype=torch.float32, device=self.device)
         self._dwp_used = 0
-        for op in reversed(self.ops):
+        for op in reversed(self.ops[self._bwd_cut():]):
             op.plan_bwd(self)
         self._bwd_planned = True
+
+    def _bwd_cut(self):
+        return self.encoder_end if self.only_train_dec else 0
+
+    def frozen_param_names(self):
+        """Parameters that receive no gradient in this plan (the encoder under `only_train_dec`)."""
+        if not self.only_train_dec:
+            return set()
+        live = set()
+        for op in self.ops[self._bwd_cut():]:
+            n = getattr(op, 'name', None)
+            if n is not None:
+                live.update((n + '.weight', n + '.bias'))
+        return set(self.param_names) - live
 
     def run_backward(self, gouts):
         self.plan_backward()
@@ -1043,8 +1071,9 @@ class _NetFn(torch.autograd.Function):
                                'arena has been overwritten (run forward -> backward in lockstep, as train.py does)')
         grads = plan.run_backward(gouts)
         res = [None, None] + [None] * ctx.n_inputs
+        dead = plan.frozen_param_names()
         for name in ctx.param_order:
-            res.append(grads.get(name))
+            res.append(None if name in dead else grads.get(name))
         return tuple(res)
 
 
@@ -1060,10 +1089,13 @@ class PlannedModule(torch.nn.Module):
     def _plan_for(self, inputs):
         dev = inputs[0].device
         prec = self.precision or default_precision()
-        key = (tuple(tuple(x.shape) for x in inputs), self.training, prec, str(dev))
+        bn_frozen = self.training and any(isinstance(m, torch.nn.modules.batchnorm._BatchNorm) and not m.training
+                                          for m in self.modules())
+        only_dec = self.training and bool(getattr(self, 'only_train_dec', False))
+        key = (tuple(tuple(x.shape) for x in inputs), self.training, prec, str(dev), bn_frozen, only_dec)
         plans = self.__dict__.setdefault('_plans', {})
         if key not in plans:
-            plan = Plan(self, dev, prec, self.training)
+            plan = Plan(self, dev, prec, self.training, bn_frozen, only_dec)
             with torch.no_grad():
                 self._build_plan(plan, [tuple(x.shape) for x in inputs])
             plans[key] = plan
@@ -1080,4 +1112,5 @@ class PlannedModule(torch.nn.Module):
         plan.bind(tensors)
         order = [n for n in plan.param_names]
         plan._fn_param_order = order
-        return _NetFn.apply(plan, len(inputs), *inputs, *[named[n] for n in order])
+        with torch.cuda.device(inputs[0].device):       # kernels go to the current stream of the tensors' device
+            return _NetFn.apply(plan, len(inputs), *inputs, *[named[n] for n in order])

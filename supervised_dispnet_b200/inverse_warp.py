@@ -65,5 +65,8 @@ def inverse_warp(img, depth, pose, intrinsics, intrinsics_inv, rotation_mode='eu
     check_sizes(intrinsics, 'intrinsics', 'B33')
     check_sizes(intrinsics_inv, 'intrinsics', 'B33')
     assert(intrinsics_inv.size() == intrinsics.size())
+    # the reference builds its pixel grid from depth's size (inverse_warp.py:178, set_id_grid): it must equal the image's
+    assert tuple(depth.shape[-2:]) == tuple(img.shape[-2:]) and depth.size(0) == img.size(0), 'depth %s vs img %s' % (
+        tuple(depth.shape), tuple(img.shape))
     return _InverseWarpFn.apply(img, depth, pose, intrinsics, intrinsics_inv, _ROT[rotation_mode], _PAD[padding_mode],
                                 int(bool(align_corners)))

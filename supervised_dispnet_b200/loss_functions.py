@@ -61,6 +61,9 @@ def l1_loss(gt_depth, depth, datasets):
     """sum_b mean_{valid_b} |gt - clamp(pred, 1e-3, max)| / B, using depth[0][:, 0] only (reference :104-129)."""
     maxd = _max_depth(datasets)
     pred = depth[0][:, 0]
+    # the reference indexes pred[valid] with a mask built from gt (:112-121): mismatching shapes raise there, and must not
+    # become an out-of-bounds device read here
+    assert tuple(gt_depth.shape) == tuple(pred.shape), 'gt_depth %s vs depth[0][:, 0] %s' % (tuple(gt_depth.shape), tuple(pred.shape))
     return _L1Fn.apply(gt_depth, pred, maxd)
 
 
@@ -160,8 +163,14 @@ class _PhotoFn(torch.autograd.Function):
         refs = [r.contiguous().float() for r in refs]
         pose = pose.contiguous().float()
         K, Kinv = K.contiguous().float(), Kinv.contiguous().float()
-        B, _, H, W = tgt.shape
+        B, C3, H, W = tgt.shape
         R = len(refs)
+        assert C3 == 3 and all(tuple(r.shape) == tuple(tgt.shape) for r in refs), 'tgt / ref images must be [B,3,H,W]'
+        assert pose.dim() == 3 and pose.size(0) == B and pose.size(1) == R and pose.size(2) == 6      # reference :319-320
+        assert tuple(K.shape) == (B, 3, 3) and tuple(Kinv.shape) == (B, 3, 3)
+        for d, m in zip(depths, masks):
+            assert d.dim() == 4 and d.size(0) == B and d.size(1) == 1, 'depth maps must be [B,1,h,w]'
+            assert m is None or tuple(m.shape) == (B, R, d.size(2), d.size(3)), 'explainability mask must be [B,R,h,w]'
         dev = tgt.device
         st = L.stream_ptr()
         loss = torch.zeros((), dtype=torch.float32, device=dev)
@@ -238,6 +247,7 @@ def error_counters(gt, pred, dataset='kitti', crop=True, unsupervised=False):
     """Raw per-sample results of the metric kernel: (counters int64 [B,4], sums float64 [B,5]) on the host.
     counters = n_valid, n(thresh<1.25), n(<1.25^2), n(<1.25^3); these are the bit-exact integers of SURVEY 8(a9)."""
     L.require_cuda(gt, pred)
+    assert gt.dim() == 3 and tuple(gt.shape) == tuple(pred.shape), 'gt %s vs pred %s' % (tuple(gt.shape), tuple(pred.shape))
     gt, pred = gt.contiguous().float(), pred.contiguous().float()
     B, H, W = gt.shape
     if dataset == 'kitti':

@@ -48,6 +48,10 @@ class Disp_res_50(E.PlannedModule):
         self.inplanes = 64
         self.conv1 = nn.Conv2d(3, 64, kernel_size=7, stride=2, padding=3, bias=False)
         self.bn1 = nn.BatchNorm2d(64)
+        # bn1's output is discarded by the reference's forward (:143-145): its affine parameters never receive a gradient.  Frozen
+        # like the dead VGG classifier so that DistributedDataParallel's reducer does not wait for them (buffers still update).
+        for p in self.bn1.parameters():
+            p.requires_grad_(False)
         self.relu = nn.ReLU(inplace=True)
         self.pool1 = nn.MaxPool2d(kernel_size=3, stride=2, padding=1)
         self.layer1 = self.resblock(64, 3)
@@ -140,6 +144,7 @@ class Disp_res_50(E.PlannedModule):
                 x = out
                 h, w = ho, wo
         c5 = x
+        plan.encoder_end = len(plan.ops)          # `only_train_dec` (reference :154-160) detaches relu1 .. conv5 here
 
         def upc(name, src, dst):
             plan.add(E.ConvOp(plan, name + '.0', src, dst, 3, stride=2, pad=1, transposed=True, act=ACT_LRELU))

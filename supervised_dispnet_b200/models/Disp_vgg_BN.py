@@ -110,6 +110,7 @@ class Disp_vgg_BN(E.PlannedModule):
                 x = out
                 k += 1
         c5 = x
+        plan.encoder_end = len(plan.ops)          # `only_train_dec` (reference :148-153) detaches conv1..conv5 here
 
         def up(name, src, dst):
             plan.add(E.ConvOp(plan, name + '.0', src, dst, 4, stride=2, pad=1, transposed=True, act=ACT_LRELU))

@@ -602,3 +602,69 @@ def test_bn_residual_kernels_vs_torch(C, H, W, acc):
     assert float((dr - rf.grad).norm() / rf.grad.norm()) < 2e-2
     assert float((dgam - bn.weight.grad).norm() / bn.weight.grad.norm()) < 5e-3
     assert float((dbet - bn.bias.grad).norm() / bn.bias.grad.norm()) < 5e-3
+
+
+@pytest.mark.parametrize('precision,tol', [('tc32', 1e-4), ('mixed', 5e-3)])
+def test_frozen_batchnorm_diff_lr_mode(precision, tol):
+    """train.py:405-411 (`--diff_lr`): `disp_net.apply(set_bn_eval)` puts the BatchNorm modules in eval() inside a training
+    network -- running statistics normalise (as constants of the graph), the buffers do not move, gamma / beta still train."""
+    import supervised_dispnet_b200 as S
+    from oracle import nets as ON
+    sd = ON.init_state_dict('Disp_vgg_BN', 0, skip_dead=True)
+    g = torch.Generator().manual_seed(5)
+    for k in sd:
+        if k.endswith('running_mean'):
+            sd[k] = torch.randn(sd[k].shape, generator=g) * 0.05
+        elif k.endswith('running_var'):
+            sd[k] = torch.rand(sd[k].shape, generator=g) * 0.5 + 0.75
+    m = S.models.Disp_vgg_BN()
+    m.load_state_dict({k: v.clone() for k, v in sd.items()}, strict=False)
+    m.precision = precision
+    m.to(DEV).train()
+
+    def set_bn_eval(mod):
+        if mod.__class__.__name__.find('BatchNorm') != -1:
+            mod.eval()
+    m.apply(set_bn_eval)
+    x = I.images(2, 64, 96, seed=11)
+    sd_o = {k: (v.clone().requires_grad_(True) if v.dtype.is_floating_point and 'running' not in k else v.clone()) for k, v in sd.items()}
+    d_o = ON.disp_vgg_bn(sd_o, x, False)
+    (d_o * I.probe_like(d_o, 3)).sum().backward()
+    outs = m(x.to(DEV))
+    assert len(outs) == 4
+    assert rel(outs[0], d_o) < tol
+    (outs[0] * I.probe_like(d_o, 3).to(DEV)).sum().backward()
+    named = dict(m.named_parameters())
+    for k in ('features.features.1.weight', 'features.features.41.bias', 'features.features.0.weight', 'iconv0.0.weight'):
+        assert rel(named[k].grad, sd_o[k].grad) < (3e-2 if precision == 'tc32' else 0.3), k     # (ReLU sign flips, as in the train-mode cases)
+    bufs = dict(m.named_buffers())
+    for k in sd:
+        if 'running' in k:
+            assert torch.equal(bufs[k].cpu(), sd[k]), k
+        if 'num_batches' in k:
+            assert int(bufs[k]) == int(sd[k]), k
+
+
+def test_only_train_dec_detaches_the_encoder():
+    """models/Disp_vgg_BN.py:148-153: with `only_train_dec` the encoder outputs are detached -- encoder parameters get no
+    gradient, decoder gradients are unchanged."""
+    import supervised_dispnet_b200 as S
+    from oracle import nets as ON
+    sd = ON.init_state_dict('Disp_vgg_BN', 0, skip_dead=True)
+    x = I.images(2, 64, 96, seed=12).to(DEV)
+    grads = []
+    for flag in (False, True):
+        m = S.models.Disp_vgg_BN()
+        m.load_state_dict({k: v.clone() for k, v in sd.items()}, strict=False)
+        m.precision = 'tc32'
+        m.only_train_dec = flag
+        m.to(DEV).train()
+        outs = m(x)
+        sum((o * I.probe_like(o, 20 + i).to(DEV)).sum() for i, o in enumerate(outs)).backward()
+        grads.append({k: (None if p.grad is None else p.grad.clone()) for k, p in m.named_parameters()})
+    full, dec = grads
+    for k, g in dec.items():
+        if k.startswith('features.'):
+            assert g is None, k
+        else:
+            assert g is not None and rel(g, full[k]) < 1e-6, k

@@ -113,7 +113,7 @@ def test_unchanged_reference_train_loop_g8(golden, tmp_path, precision, tol):
     args = R.reference_args(tmp_path, batch_size=4)
     T.device, T.n_iter = torch.device(DEV), 0
     T.loss_functions = S.loss_functions          # the reference's `import loss_functions` (train.py:17) swapped
-    avg = T.train(args, g8_batches(), net, torch.nn.Identity(), opt, 3, R.NullLogger(), None)
+    avg = T.train(args, g8_batches(), net, torch.nn.Identity(), opt, 3, R.NullLogger(), R.NullWriter())
     rows = [[float(v) for v in r] for r in csv.reader(open(tmp_path / args.log_full), delimiter='\t')]
     assert len(rows) == 3
     for r, q in zip(rows, g['rows']):
