@@ -38,7 +38,7 @@ def allreduce_error_counters(counters, sums, group=None):
 
 def attach(net, group=None):
     """Data parallelism without the DDP wrapper: broadcast rank 0's parameters and buffers once, then let the module's own
-    backward all-reduce (average) its flat fp32 gradient arena with ONE NCCL call per step (engine.Plan._clone_grads).
+    backward all-reduce (average) its flat fp32 gradient arena with ONE NCCL call per step (engine.Plan.run_backward: three parameter ranges, each all-reduced while the ranges below it are still in their backward).
     The gradients already live in one contiguous buffer, so DDP's bucket copies, hooks and per-step buffer broadcasts buy
     nothing here; BatchNorm running statistics stay per rank and rank 0's are the ones checkpointed, which is what the
     reference's nn.DataParallel keeps (replica 0; train.py:316-317, 378)."""

@@ -902,17 +902,22 @@ class Plan:
         assert out.numel() == numel, 'packed weight-gradient arena exhausted'
         return out
 
-    def _run_jobs(self, which):
-        key = (which, self._ptr_key())
-        ent = self._job_tables.get(which)
+    def _run_jobs(self, which, rng=None, launch=True):
+        """One batched dn_pack_jobs launch for the convolutions of ops[rng] (all ops of the direction when rng is None).
+        launch=False only builds the device-side job table (a host-to-device copy, which a stream capture must not contain)."""
+        tkey = (which, rng)
+        key = (which, rng, self._ptr_key())
+        ent = self._job_tables.get(tkey)
         if ent is None or ent[0] != key:
-            ops = self.ops if which == 'fwd' else self.ops[self._bwd_cut():]
-            jobs = [j for op in ops if isinstance(op, ConvOp) for j in op.jobs(self, which)]
-            arr = (L.DnPackJob * len(jobs))(*jobs)
-            dev = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(self.device)
+            lo, hi = rng if rng is not None else ((0 if which == 'fwd' else self._bwd_cut()), len(self.ops))
+            jobs = [j for op in self.ops[lo:hi] if isinstance(op, ConvOp) for j in op.jobs(self, which)]
+            dev = None
+            if jobs:
+                arr = (L.DnPackJob * len(jobs))(*jobs)
+                dev = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(self.device)
             ent = (key, dev, len(jobs))
-            self._job_tables[which] = ent
-        if ent[2]:
+            self._job_tables[tkey] = ent
+        if ent[2] and launch:
             L.call('dn_pack_jobs', L.ptr(ent[1]), ent[2], self.stream)
 
     def _forward_impl(self, inputs):
@@ -925,28 +930,75 @@ class Plan:
         self.saved_outputs = self.outputs
         return tuple(self.outputs)
 
-    def _backward_impl(self, gouts):
-        self.stream = L.stream_ptr()
-        self.gouts = gouts
+    def _ensure_gflat(self):
         if self._gflat is None:      # persistent fp32 gradient arena, one slice per parameter
             total = sum(self._params[n].numel() for n in self.param_names)
             self._gflat = torch.zeros(total, dtype=torch.float32, device=self.device)
-            self._grads, o = {}, 0
+            self._grads, self._goffs, o = {}, {}, 0
             for n in self.param_names:
                 p = self._params[n]
                 self._grads[n] = self._gflat[o:o + p.numel()].view(p.shape)
+                self._goffs[n] = (o, o + p.numel())
                 o += p.numel()
-        self._gflat.zero_()
-        self._dwp_arena.zero_()
-        self._run_jobs('dgrad')
+
+    def _backward_segment(self, gouts, lo, hi, first):
+        """Backward of ops[lo:hi] (reverse order); `first`: this is the first segment of the step (clears the arenas and
+        packs the data-gradient weights).  Leaves the gradients of the segment's parameters final in the flat arena."""
+        self.stream = L.stream_ptr()
+        self.gouts = gouts
+        self._ensure_gflat()
+        if first:
+            self._gflat.zero_()
+            self._dwp_arena.zero_()
+            self._run_jobs('dgrad')
         if self.side_stream() is not None:          # the side stream must see the zeroed arenas / packed weights
             self._side.wait_stream(torch.cuda.current_stream())
-        for op in reversed(self.ops[self._bwd_cut():]):
+        for op in reversed(self.ops[lo:hi]):
             op.bwd(self)
         if self._side is not None:
             torch.cuda.current_stream().wait_stream(self._side)
-        self._run_jobs('unpack')
+        self._run_jobs('unpack', (lo, hi))
         return self._gflat
+
+    def _backward_impl(self, gouts):
+        return self._backward_segment(gouts, self._bwd_cut(), len(self.ops), True)
+
+    def _segments(self, distributed):
+        """Op ranges (forward order) whose backward runs as one unit.  Data parallel: three ranges, cut where the cumulative
+        parameter count (forward order) passes 10 % and 60 % -- the all-reduce of a range is issued as soon as its backward is
+        enqueued and overlaps the backward of the ranges below it, so only the smallest one (the first layers, ~10 % of the
+        bytes) is exposed at the end of the step."""
+        cut, n = self._bwd_cut(), len(self.ops)
+        if not distributed or os.environ.get('DISPNET_B200_DP_SEGMENTS', '3') == '1':
+            return [(cut, n)]
+        sizes = []
+        for op in self.ops[cut:]:
+            nm = getattr(op, 'name', None)
+            sizes.append(sum(self._params[k].numel() for k in ((nm + '.weight', nm + '.bias') if nm else ()) if k in self.param_names))
+        total = float(sum(sizes)) or 1.0
+        marks, acc, want = [], 0.0, [0.10, 0.60]
+        for i, sz in enumerate(sizes):
+            acc += sz
+            while want and acc / total >= want[0]:
+                if 0 < i + 1 < len(sizes) and (not marks or marks[-1] != cut + i + 1):
+                    marks.append(cut + i + 1)
+                want.pop(0)
+        edges = [cut] + marks + [n]
+        return [(a, b) for a, b in zip(edges[:-1], edges[1:]) if b > a]
+
+    def _segment_span(self, lo, hi):
+        """[begin, end) of the flat gradient arena that belongs to the parameters of ops[lo:hi] (contiguous: parameters are
+        registered in op order)."""
+        names = []
+        for op in self.ops[lo:hi]:
+            nm = getattr(op, 'name', None)
+            if nm:
+                names += [k for k in (nm + '.weight', nm + '.bias') if k in self._goffs]
+        if not names:
+            return None
+        b, e = min(self._goffs[k][0] for k in names), max(self._goffs[k][1] for k in names)
+        assert sum(self._goffs[k][1] - self._goffs[k][0] for k in set(names)) == e - b, 'segment parameters are not contiguous'
+        return b, e
 
     # ---- CUDA-graph execution: the whole forward (and backward) op list is captured once per plan and replayed, so a
     # step costs two graph launches instead of ~300 host-side launches (the reference's loop is launch-bound; SURVEY 2.4)
@@ -1014,41 +1066,63 @@ class Plan:
     def run_backward(self, gouts):
         self.plan_backward()
         gouts = [None if g is None else g.contiguous().float() for g in gouts]
-        if not graphs_enabled() or self._fwd_graph is None:
-            return self._clone_grads(self._backward_impl(gouts))
-        pattern = tuple(g is not None for g in gouts)
-        ent = self._bwd_graphs.get(pattern)
-        if ent is None:
+        group = getattr(self.module, '_dp_group', None)
+        segs = list(reversed(self._segments(group is not None)))          # execution order: last layers first
+        use_graph = graphs_enabled() and self._fwd_graph is not None
+        pattern = (tuple(g is not None for g in gouts), len(segs))
+        ent = self._bwd_graphs.get(pattern) if use_graph else None
+        if use_graph and ent is None:
             if self._bwd_warm < 1:
                 self._bwd_warm += 1
-                return self._clone_grads(self._backward_impl(gouts))
-            static_g = [None if g is None else g.clone() for g in gouts]
-            torch.cuda.synchronize()
-            g = torch.cuda.CUDAGraph()
-            calls0 = L.CALLS
-            with torch.cuda.graph(g, capture_error_mode='thread_local'):
-                flat = self._backward_impl(static_g)
-            ent = (g, static_g, flat, dict(self._grads), L.CALLS - calls0)
-            self._bwd_graphs[pattern] = ent
-        g, static_g, flat, views, ncalls = ent
-        for s_, x in zip(static_g, gouts):
-            if s_ is not None:
-                s_.copy_(x)
-        g.replay()
-        L.CALLS += ncalls
-        return self._clone_grads(flat)
-
-    def _clone_grads(self, flat):
-        out = flat.clone()          # autograd may keep / accumulate into what we return: hand out a private copy
-        group = getattr(self.module, '_dp_group', None)
-        if group is not None:       # data parallel: one NCCL all-reduce (mean) of the whole gradient arena
-            import torch.distributed as dist
-            dist.all_reduce(out, op=dist.ReduceOp.AVG, group=group)
-        res, o = {}, 0
+                use_graph = False
+            else:
+                static_g = [None if g is None else g.clone() for g in gouts]
+                self._ensure_gflat()
+                self._run_jobs('dgrad', launch=False)
+                for rng in segs:
+                    self._run_jobs('unpack', rng, launch=False)
+                torch.cuda.synchronize()
+                graphs, calls0 = [], L.CALLS
+                for si, (lo, hi) in enumerate(segs):
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, capture_error_mode='thread_local'):
+                        self._backward_segment(static_g, lo, hi, si == 0)
+                    graphs.append(g)
+                ent = (graphs, static_g, L.CALLS - calls0)
+                self._bwd_graphs[pattern] = ent
+                # the captures only recorded the work: run it now through the common replay path below
+        if use_graph:
+            graphs, static_g, ncalls = ent
+            for s_, x in zip(static_g, gouts):
+                if s_ is not None:
+                    s_.copy_(x)
+            L.CALLS += ncalls
+        self._ensure_gflat()
+        out = torch.empty_like(self._gflat)     # autograd may keep / accumulate into what we return: hand out a private copy
+        works = []
+        for si, (lo, hi) in enumerate(segs):
+            if use_graph:
+                graphs[si].replay()
+            else:
+                self._backward_segment(gouts, lo, hi, si == 0)
+            span = self._segment_span(lo, hi)
+            if span is None:
+                continue
+            seg = out[span[0]:span[1]]
+            seg.copy_(self._gflat[span[0]:span[1]])
+            if group is not None:
+                # data parallel: the NCCL all-reduce (mean) of this range's gradients starts as soon as the range's backward
+                # is enqueued and runs on NCCL's stream, concurrently with the backward of the remaining ranges
+                import torch.distributed as dist
+                works.append(dist.all_reduce(seg, op=dist.ReduceOp.AVG, group=group, async_op=True))
+        for w in works:
+            w.wait()                            # stream-level wait: the compute stream resumes after the last all-reduce
+        covered = self._segment_span(self._bwd_cut(), len(self.ops))
+        res = {}
         for n in self.param_names:
-            p = self._params[n]
-            res[n] = out[o:o + p.numel()].view(p.shape)
-            o += p.numel()
+            b, e = self._goffs[n]
+            if covered is not None and covered[0] <= b and e <= covered[1]:
+                res[n] = out[b:e].view(self._params[n].shape)
         return res
 
 

@@ -220,3 +220,28 @@ def test_loss_reader_average_cpu():
         r.push(torch.tensor(v), 4)
     r.flush()
     assert m.count == 12 and abs(m.avg[0] - 3.0) < 1e-6
+
+
+def test_dp_segments_partition_the_gradient_arena():
+    """Host logic of the overlapped data-parallel all-reduce (engine.Plan._segments / _segment_span): three op ranges that
+    cover the op list, whose parameter spans tile the flat gradient arena, the range that finishes last (the first layers)
+    holding about a tenth of the bytes."""
+    import torch
+    import supervised_dispnet_b200 as S
+    m = S.models.Disp_vgg_BN()
+    x = torch.zeros(1, 3, 64, 96)
+    plan = m._plan_for([x])
+    tensors = dict(m.named_parameters())
+    tensors.update(dict(m.named_buffers()))
+    plan.bind(tensors)
+    plan.plan_backward()
+    plan._ensure_gflat()
+    segs = plan._segments(True)
+    assert len(segs) == 3 and segs[0][0] == 0 and segs[-1][1] == len(plan.ops)
+    assert all(a[1] == b[0] for a, b in zip(segs[:-1], segs[1:]))
+    spans = [plan._segment_span(lo, hi) for lo, hi in segs]
+    assert spans[0][0] == 0 and spans[-1][1] == plan._gflat.numel()
+    assert all(a[1] == b[0] for a, b in zip(spans[:-1], spans[1:]))
+    frac = (spans[0][1] - spans[0][0]) / plan._gflat.numel()
+    assert 0.05 < frac < 0.2, frac
+    assert plan._segments(False) == [(0, len(plan.ops))]
