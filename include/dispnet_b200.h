@@ -245,6 +245,22 @@ int dn_l1_fwd(const float* gt, const float* pred, int B, int HW, float max_depth
               void* stream);
 int dn_l1_bwd(const float* gt, const float* pred, int B, int HW, float max_depth, const float* ws,
               const float* gout, float* gpred, void* stream);
+/* The supervised depth losses behind train.py's `--loss` switch (train.py:449-470), one masked-reduce kernel family:
+ *   kind 0 l1_loss (:104-129)  1 l2_loss (:77-102)  2 berhu_loss (:131-160)  3 Scale_invariant_loss (:162-187)
+ * per sample: valid = (gt > 0) & (gt < max_depth), pred clamped to [1e-3, max_depth], value_b from the sample's masked sums,
+ * loss[0] (+)= weight * sum_b value_b / B.  joint = 1: one mask over the whole batch and no division by B -- the
+ * Multiscale_{L1,L2,berhu,scale_inv}_loss forms (:217-315; weight = 1/2^scale, max_depth = 80).  up_factor > 1: pred is
+ * [B, H/f, W/f] and is up-sampled on the fly (mode 0 nearest, 1 bilinear align_corners=False) as Multiscale_FULL_L1_loss does
+ * (:224-241).  Reductions are two-stage and deterministic (no float atomics); berhu runs a second pass with c = 0.2 max|d|.
+ * ws: dn_depth_loss_ws_floats(B) floats, written by fwd and read by bwd.  bwd: gpred [B, H/f, W/f] overwritten. */
+int64_t dn_depth_loss_ws_floats(int B);
+int dn_depth_loss_fwd(const float* gt, const float* pred, int B, int H, int W, int up_factor, int up_mode, float max_depth,
+                      int kind, int joint, float weight, int accumulate, float* ws, float* loss, void* stream);
+int dn_depth_loss_bwd(const float* gt, const float* pred, int B, int H, int W, int up_factor, int up_mode, float max_depth,
+                      int kind, int joint, float weight, const float* ws, const float* gout, float* gpred, void* stream);
+/* 2x2 / stride-2 pooling of the ground-truth pyramid (loss_functions.py:185-215): mode 0 = average (= F.interpolate(
+ * scale_factor=0.5, 'bilinear', align_corners=False) and F.avg_pool2d), 1 = F.max_pool2d; src [NC,H,W] -> dst [NC,H/2,W/2] */
+int dn_pool2(const float* src, int64_t NC, int H, int W, int mode, float* dst, void* stream);
 /* smooth_loss (loss_functions.py:367-386) for one scale: loss[0] += weight * (4 abs-means).  p fp32 [B,H,W]. */
 int dn_smooth_fwd(const float* p, int B, int H, int W, float weight, float* loss, void* stream);
 int dn_smooth_bwd(const float* p, int B, int H, int W, float weight, const float* gout, float* gp, void* stream);

@@ -12,6 +12,7 @@ Reference lines restated:
   explainability_loss               loss_functions.py:357-364
   smooth_loss                       loss_functions.py:367-386
   l1_loss                           loss_functions.py:104-129
+  l2 / berhu / Scale_invariant / Multiscale_*       loss_functions.py:77-315
   compute_errors                    loss_functions.py:401-448
   SSIM / get_smooth_loss / compute_depth_errors    layers.py:215-245 / :199-212 / :248-266
 """
@@ -184,6 +185,110 @@ def l1_loss(gt_depth, depth, datasets):
     err = (gt_depth - pred.clamp(1e-3, M)).abs() * valid
     per = err.flatten(1).sum(1) / valid.flatten(1).sum(1)
     return per.sum() / pred.size(0)
+
+
+# --------------------------------------------------------------------------------------------------
+# the other supervised depth losses behind train.py's --loss switch (loss_functions.py:77-315), restated with masked sums
+# --------------------------------------------------------------------------------------------------
+def _masked(gt, pred, M):
+    """valid mask (as float), residual gt - clamp(pred) zeroed outside the mask, count per leading index."""
+    valid = ((gt > 0) & (gt < M)).to(pred.dtype)
+    d = (gt - pred.clamp(1e-3, M)) * valid
+    return valid, d
+
+
+def _berhu_rows(valid, d):
+    """rows = samples (or one row for the whole batch): reverse Huber with c = 0.2 max|d| over the row's valid pixels."""
+    r = d.abs().flatten(1)
+    v = valid.flatten(1)
+    c = 0.2 * r.max(1, keepdim=True)[0]
+    per = torch.where(r > c, (r * r + c * c) / (2 * c), r) * v
+    return per.sum(1) / v.sum(1)
+
+
+def l2_loss(gt_depth, depth, datasets):
+    """loss_functions.py:77-102 (the 'nyu' branch averages |d|, not d^2: line 97)."""
+    M = max_depth_of(datasets)
+    pred = depth[0][:, 0]
+    valid, d = _masked(gt_depth, pred, M)
+    e = d * d if datasets == 'kitti' else d.abs()
+    return (e.flatten(1).sum(1) / valid.flatten(1).sum(1)).sum() / pred.size(0)
+
+
+def berhu_loss(gt_depth, depth, datasets):
+    """loss_functions.py:131-160, 'kitti' branch (the 'nyu' branch of the reference raises UnboundLocalError)."""
+    pred = depth[0][:, 0]
+    valid, d = _masked(gt_depth, pred, max_depth_of(datasets))
+    return _berhu_rows(valid, d).sum() / pred.size(0)
+
+
+def _scale_inv_rows(valid, d):
+    n = valid.flatten(1).sum(1)
+    return (d * d).flatten(1).sum(1) / n - 0.5 * d.flatten(1).sum(1) ** 2 / (n * n)
+
+
+def scale_invariant_loss(gt_depth, depth, datasets):
+    """loss_functions.py:162-187 (gt > 0 and pred >= 1e-3 inside the mask, so |gt| - |pred| = gt - pred)."""
+    pred = depth[0][:, 0]
+    valid, d = _masked(gt_depth, pred, max_depth_of(datasets))
+    return _scale_inv_rows(valid, d).sum() / pred.size(0)
+
+
+def gt_pyramid(gt, pool_type='bilinear'):
+    """loss_functions.py:189-215: three 2x2/stride-2 poolings; 'bilinear' (scale 0.5, align_corners=False) = 'avg' = block mean."""
+    pyr = [gt]
+    for _ in range(3):
+        g = pyr[-1]
+        b, h, w = g.shape
+        blk = g[:, :h // 2 * 2, :w // 2 * 2].reshape(b, h // 2, 2, w // 2, 2)
+        pyr.append(blk.amax((2, 4)) if pool_type == 'max' else blk.mean((2, 4)))
+    return pyr
+
+
+def multiscale_loss(kind, gt_depth, depth, pool_type='bilinear'):
+    """Multiscale_{L1,L2,berhu,scale_inv}_loss (loss_functions.py:217-222, :243-315): one mask over the whole batch per scale,
+    max depth 80, weight 1/2^i."""
+    gts = gt_pyramid(gt_depth, pool_type)
+    loss = 0
+    for i, dmap in enumerate(depth):
+        pred = dmap[:, 0]
+        valid, d = _masked(gts[i], pred, 80.0)
+        valid, d = valid.reshape(1, -1), d.reshape(1, -1)
+        if kind == 'l1':
+            v = d.abs().sum() / valid.sum()
+        elif kind == 'l2':
+            v = (d * d).sum() / valid.sum()
+        elif kind == 'berhu':
+            v = _berhu_rows(valid, d)[0]
+        else:
+            v = _scale_inv_rows(valid, d)[0]
+        loss = loss + v / (2 ** i)
+    return loss
+
+
+def upsample_bilinear(x, f):
+    """F.upsample(x, scale_factor=f, mode='bilinear') (align_corners=False) of [B,h,w] with explicit gathers."""
+    b, h, w = x.shape
+    ys = ((torch.arange(h * f, dtype=x.dtype) + 0.5) / f - 0.5).clamp(min=0)
+    xs = ((torch.arange(w * f, dtype=x.dtype) + 0.5) / f - 0.5).clamp(min=0)
+    y0, x0 = ys.floor().long(), xs.floor().long()
+    y1, x1 = (y0 + 1).clamp(max=h - 1), (x0 + 1).clamp(max=w - 1)
+    ly, lx = (ys - y0.to(x.dtype)).view(1, -1, 1), (xs - x0.to(x.dtype)).view(1, 1, -1)
+    g = lambda yy, xx: x[:, yy][:, :, xx]          # noqa: E731
+    return (1 - ly) * ((1 - lx) * g(y0, x0) + lx * g(y0, x1)) + ly * ((1 - lx) * g(y1, x0) + lx * g(y1, x1))
+
+
+def multiscale_full_l1_loss(gt_depth, depth, pool_type='bilinear'):
+    """Multiscale_FULL_L1_loss (loss_functions.py:224-241): predictions up-sampled to full size."""
+    loss = 0
+    for i, dmap in enumerate(depth):
+        f = 2 ** i
+        pred = dmap[:, 0]
+        if f > 1:
+            pred = upsample_bilinear(pred, f) if pool_type == 'bilinear' else pred.repeat_interleave(f, 1).repeat_interleave(f, 2)
+        valid, d = _masked(gt_depth, pred, 80.0)
+        loss = loss + (d.abs().sum() / valid.sum()) / f
+    return loss
 
 
 def garg_crop(h, w):

@@ -276,6 +276,42 @@ def make_g8():
     print('g8 rows', rows, 'avg', avg)
 
 
+def make_g10():
+    """G10: the supervised losses behind train.py's --loss switch other than L1 (loss_functions.py:77-315), values and
+    gradients w.r.t. every scale's prediction, from the unmodified reference."""
+    import _inputs as I
+    rm, rl, rw, rlay = import_reference()
+    B, H, W = 3, 32, 64
+    gt = I.sparse_gt(B, H, W, seed=140, dataset='kitti', density=0.3)
+    gtn = I.sparse_gt(B, H, W, seed=141, dataset='nyu', density=0.9)
+    out = {}
+
+    def preds(hi):
+        return [I.depth_map(B, H >> s, W >> s, seed=150 + s, lo=0.0005, hi=hi).unsqueeze(1).requires_grad_(True) for s in range(4)]
+    cases = [('l2_kitti', lambda d: rl.l2_loss(gt, d, 'kitti'), 95.0), ('l2_nyu', lambda d: rl.l2_loss(gtn, d, 'nyu'), 12.0),
+             ('berhu_kitti', lambda d: rl.berhu_loss(gt, d, 'kitti'), 95.0),
+             ('scale_inv_kitti', lambda d: rl.Scale_invariant_loss(gt, d, 'kitti'), 95.0),
+             ('scale_inv_nyu', lambda d: rl.Scale_invariant_loss(gtn, d, 'nyu'), 12.0),
+             ('multi_l1', lambda d: rl.Multiscale_L1_loss(gt, d), 95.0),
+             ('multi_l1_max', lambda d: rl.Multiscale_L1_loss(gt, d, 'max'), 95.0),
+             ('multi_full_l1', lambda d: rl.Multiscale_FULL_L1_loss(gt, d), 95.0),
+             ('multi_l2', lambda d: rl.Multiscale_L2_loss(gt, d), 95.0),
+             ('multi_berhu', lambda d: rl.Multiscale_berhu_loss(gt, d), 95.0),
+             ('multi_scale_inv', lambda d: rl.Multiscale_scale_inv_loss(gt, d), 95.0)]
+    for name, fn, hi in cases:
+        d = preds(hi)
+        l = fn(d)
+        l.backward()
+        out[name] = dict(loss=l.detach().clone(), grads=[None if t.grad is None else t.grad.clone() for t in d])
+        print('%-18s %.6f' % (name, float(l)))
+    try:
+        rl.berhu_loss(gtn, preds(12.0), 'nyu')
+        out['berhu_nyu_raises'] = None
+    except Exception as e:  # noqa: BLE001
+        out['berhu_nyu_raises'] = type(e).__name__
+    torch.save(out, os.path.join(OUT, 'g10_supervised_losses.pt'))
+
+
 def I_sub(t):
     import _inputs as I
     return I.subsample(t)
@@ -284,6 +320,9 @@ def I_sub(t):
 if __name__ == '__main__':
     if len(sys.argv) > 1 and sys.argv[1] == 'g8':
         make_g8()
+    elif len(sys.argv) > 1 and sys.argv[1] == 'g10':
+        make_g10()
     else:
         main()
         make_g8()
+        make_g10()

@@ -94,6 +94,10 @@ _SIGS = {
     'dn_spatial_mean_bwd': ([_P, _F, _V, _P], _I),
     'dn_l1_fwd': ([_P, _P, _I, _I, _F, _P, _P, _P], _I),
     'dn_l1_bwd': ([_P, _P, _I, _I, _F, _P, _P, _P, _P], _I),
+    'dn_depth_loss_ws_floats': ([_I], _I64),
+    'dn_depth_loss_fwd': ([_P, _P, _I, _I, _I, _I, _I, _F, _I, _I, _F, _I, _P, _P, _P], _I),
+    'dn_depth_loss_bwd': ([_P, _P, _I, _I, _I, _I, _I, _F, _I, _I, _F, _P, _P, _P, _P], _I),
+    'dn_pool2': ([_P, _I64, _I, _I, _I, _P, _P], _I),
     'dn_smooth_fwd': ([_P, _I, _I, _I, _F, _P, _P], _I),
     'dn_smooth_bwd': ([_P, _I, _I, _I, _F, _P, _P, _P], _I),
     'dn_depth_errors': ([_P, _P, _I, _I, _I, _F, _I, _I, _I, _I, _I, _P, _P, _P, _P], _I),

@@ -592,11 +592,207 @@ __global__ void __launch_bounds__(256) inverse_warp_bwd_kernel(const float* __re
   block_reduce12(acc12, ws + 12 * b);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Supervised depth losses on the masked-reduce pattern (loss_functions.py:77-315): l1 / l2 / berhu / Scale_invariant per
+// sample, and their Multiscale_* forms (one mask over the whole batch, B = 1 here).  Deterministic: every block writes its
+// partial row, one block per sample folds the rows in a fixed order in double (no float atomics).
+//   ws layout (floats): [B][DL_NSTAT] folded statistics, then [B][nblk][DL_NPART] partial rows.
+//   statistics per sample: 0 count, 1 sum|d|, 2 sum d^2, 3 sum d (d = gt - pred_clamped), 4 max|d|, 5 sum berhu, 6 sum dberhu/dc
+// ---------------------------------------------------------------------------------------------------
+constexpr int DL_NSTAT = 8, DL_NPART = 6, DL_NBLK = 64;
+enum { DL_L1 = 0, DL_L2 = 1, DL_BERHU = 2, DL_SCALE_INV = 3 };
+
+__device__ __forceinline__ float block_max(float v) {
+  __shared__ float redm[32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) redm[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+  if (threadIdx.x < 32) {
+    t = threadIdx.x < (blockDim.x >> 5) ? redm[threadIdx.x] : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t = fmaxf(t, __shfl_xor_sync(0xffffffffu, t, o));
+  }
+  return t;
+}
+
+// optional x f up-sampling of pred (Multiscale_FULL_L1_loss :224-241): value of F.upsample(pred, scale_factor=f) at (y, x)
+struct UpSrc { int f, mode, h, w; };     // mode 0 nearest, 1 bilinear (align_corners=False); f == 1: pred is full size
+__device__ __forceinline__ float up_sample(const float* __restrict__ p, const UpSrc u, int y, int x, int* i00, float* wts) {
+  if (u.f == 1) { i00[0] = y * u.w + x; i00[1] = i00[2] = i00[3] = -1; wts[0] = 1.f; return p[i00[0]]; }
+  if (u.mode == 0) { i00[0] = (y / u.f) * u.w + x / u.f; i00[1] = i00[2] = i00[3] = -1; wts[0] = 1.f; return p[i00[0]]; }
+  const float inv = 1.f / (float)u.f;
+  float sy = ((float)y + 0.5f) * inv - 0.5f, sx = ((float)x + 0.5f) * inv - 0.5f;
+  sy = sy < 0.f ? 0.f : sy; sx = sx < 0.f ? 0.f : sx;
+  const int y0 = (int)sy, x0 = (int)sx;
+  const int y1 = y0 + (y0 < u.h - 1 ? 1 : 0), x1 = x0 + (x0 < u.w - 1 ? 1 : 0);
+  const float ly = sy - (float)y0, lx = sx - (float)x0;
+  i00[0] = y0 * u.w + x0; i00[1] = y0 * u.w + x1; i00[2] = y1 * u.w + x0; i00[3] = y1 * u.w + x1;
+  wts[0] = (1.f - ly) * (1.f - lx); wts[1] = (1.f - ly) * lx; wts[2] = ly * (1.f - lx); wts[3] = ly * lx;
+  return wts[0] * p[i00[0]] + wts[1] * p[i00[1]] + wts[2] * p[i00[2]] + wts[3] * p[i00[3]];
+}
+
+// pass 0: count, sum|d|, sum d^2, sum d, max|d|;  pass 1 (berhu): sum berhu(|d|, c), sum d berhu / dc  with c = 0.2 max|d|
+__global__ void __launch_bounds__(256) dl_partial_kernel(const float* __restrict__ gt, const float* __restrict__ pred, long long HW,
+                                                         long long pHW, int W, UpSrc up, float maxd, int pass, float* __restrict__ ws, int B,
+                                                         int joint) {
+  const int b = blockIdx.y;
+  const float* g = gt + (long long)b * HW;
+  const float* p = pred + (long long)b * pHW;
+  const float* stat = ws + (long long)(joint ? 0 : b) * DL_NSTAT;
+  float* part = ws + (long long)B * DL_NSTAT + ((long long)b * gridDim.x + blockIdx.x) * DL_NPART;
+  const float c = pass ? 0.2f * stat[4] : 0.f;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, mx = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += (long long)gridDim.x * blockDim.x) {
+    const float gv = g[i];
+    if (gv > 0.f && gv < maxd) {
+      int idx[4]; float wt[4];
+      const float raw = up.f == 1 ? p[i] : up_sample(p, up, (int)(i / W), (int)(i % W), idx, wt);
+      const float pv = fminf(fmaxf(raw, 1e-3f), maxd);
+      const float d = gv - pv, r = fabsf(d);
+      if (!pass) { a0 += 1.f; a1 += r; a2 += d * d; a3 += d; mx = fmaxf(mx, r); }
+      else if (r > c) { a0 += (r * r + c * c) / (2.f * c); a1 += 0.5f * (1.f - (r * r) / (c * c)); }
+      else a0 += r;
+    }
+  }
+  a0 = block_sum(a0); a1 = block_sum(a1); a2 = block_sum(a2); a3 = block_sum(a3); mx = block_max(mx);
+  if (threadIdx.x == 0) { part[0] = a0; part[1] = a1; part[2] = a2; part[3] = a3; part[4] = mx; }
+}
+// one block per sample folds the partial rows in block order (double) into the sample's statistics
+// (joint: one mask over the whole batch, Multiscale_* losses -- a single block folds the rows of all samples into sample 0)
+__global__ void dl_fold_kernel(float* ws, int B, int nblk, int pass, int joint) {
+  const int b = blockIdx.x;
+  if (threadIdx.x != 0) return;
+  const float* part = ws + (long long)B * DL_NSTAT + (long long)b * nblk * DL_NPART;
+  float* stat = ws + (long long)b * DL_NSTAT;
+  if (joint) nblk *= B;
+  double s[4] = {0, 0, 0, 0};
+  float mx = 0.f;
+  for (int k = 0; k < nblk; ++k) {
+    for (int j = 0; j < 4; ++j) s[j] += (double)part[k * DL_NPART + j];
+    mx = fmaxf(mx, part[k * DL_NPART + 4]);
+  }
+  if (!pass) { stat[0] = (float)s[0]; stat[1] = (float)s[1]; stat[2] = (float)s[2]; stat[3] = (float)s[3]; stat[4] = mx; }
+  else { stat[5] = (float)s[0]; stat[6] = (float)s[1]; }
+}
+__device__ __forceinline__ float dl_value(const float* st, int kind) {
+  const float n = st[0];
+  if (kind == DL_L1) return st[1] / n;                       // 0/0 -> NaN like mean() of an empty selection
+  if (kind == DL_L2) return st[2] / n;
+  if (kind == DL_BERHU) return st[5] / n;
+  return st[2] / n - 0.5f * (st[3] * st[3]) / (n * n);       // Scale_invariant_loss :166
+}
+__global__ void dl_finalize_kernel(const float* ws, int B, int kind, float weight, int accumulate, float* loss) {
+  float t = 0.f;
+  for (int b = 0; b < B; ++b) t += dl_value(ws + (long long)b * DL_NSTAT, kind);
+  t = weight * t / (float)B;
+  loss[0] = accumulate ? loss[0] + t : t;
+}
+__global__ void __launch_bounds__(256) dl_bwd_kernel(const float* __restrict__ gt, const float* __restrict__ pred, long long HW,
+                                                     long long pHW, int W, UpSrc up, float maxd, int kind, float weight,
+                                                     const float* __restrict__ ws, int B, int joint, const float* __restrict__ gout,
+                                                     float* __restrict__ gpred) {
+  const int b = blockIdx.y;
+  const float* g = gt + (long long)b * HW;
+  const float* p = pred + (long long)b * pHW;
+  float* o = gpred + (long long)b * pHW;
+  const float* st = ws + (long long)(joint ? 0 : b) * DL_NSTAT;
+  const float n = st[0], k = gout[0] * weight / (float)(joint ? 1 : B);
+  const float mxr = st[4], c = 0.2f * mxr;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += (long long)gridDim.x * blockDim.x) {
+    const float gv = g[i];
+    float r = 0.f;
+    int idx[4] = {(int)i, -1, -1, -1};
+    float wt[4] = {1.f, 0.f, 0.f, 0.f};
+    if (gv > 0.f && gv < maxd) {
+      const float raw = up.f == 1 ? p[i] : up_sample(p, up, (int)(i / W), (int)(i % W), idx, wt);
+      if (raw >= 1e-3f && raw <= maxd) {                       // clamp passes the gradient on [min, max]
+        const float d = raw - gv, ad = fabsf(d), sg = sgn(d);  // d(pred - gt)
+        if (kind == DL_L1) r = k * sg / n;
+        else if (kind == DL_L2) r = k * 2.f * d / n;
+        else if (kind == DL_SCALE_INV) r = k * (2.f * d / n + st[3] / (n * n));
+        else {
+          r = k * sg * (ad > c ? ad / c : 1.f) / n;
+          if (ad == mxr) r += k * st[6] * 0.2f * sg / n;       // through c = 0.2 * max|d| (torch.max routes it to the arg-max)
+        }
+      }
+    }
+    if (up.f == 1) o[i] = r;
+    else if (r != 0.f) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (idx[j] >= 0 && wt[j] != 0.f) atomicAdd(o + idx[j], r * wt[j]);
+    }
+  }
+}
+// F.max_pool2d(x, 2, 2) / F.avg_pool2d(x, 2, 2) (= F.interpolate(scale_factor=0.5, 'bilinear', align_corners=False)) of the
+// ground-truth pyramid (loss_functions.py:185-215)
+__global__ void __launch_bounds__(256) pool2_kernel(const float* __restrict__ src, long long NC, int H, int W, int mode, float* __restrict__ dst) {
+  const int h = H / 2, w = W / 2;
+  const long long total = NC * h * w;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % w);
+    const long long q = i / w;
+    const int y = (int)(q % h);
+    const float* r = src + (q / h) * (long long)H * W + (long long)(2 * y) * W + 2 * x;
+    const float a = r[0], b2 = r[1], c2 = r[W], d = r[W + 1];
+    dst[i] = mode ? fmaxf(fmaxf(a, b2), fmaxf(c2, d)) : 0.5f * (0.5f * a + 0.5f * b2) + 0.5f * (0.5f * c2 + 0.5f * d);
+  }
+}
+
+
 }  // namespace
 
 // =================================================================================================
 // C ABI
 // =================================================================================================
+
+DN_EXPORT int64_t dn_depth_loss_ws_floats(int B) { return (int64_t)B * DL_NSTAT + (int64_t)B * DL_NBLK * DL_NPART; }
+
+static int dl_check(const float* gt, const float* pred, int B, int H, int W, int upf, int kind) {
+  if (!gt || !pred || B < 1 || H < 1 || W < 1 || upf < 1 || (H % upf) || (W % upf) || kind < 0 || kind > 3) return DN_E_ARG;
+  return 0;
+}
+
+DN_EXPORT int dn_depth_loss_fwd(const float* gt, const float* pred, int B, int H, int W, int up_factor, int up_mode, float max_depth,
+                                int kind, int joint, float weight, int accumulate, float* ws, float* loss, void* stream) {
+  int e = dl_check(gt, pred, B, H, W, up_factor, kind);
+  if (e || !ws || !loss) return e ? e : DN_E_ARG;
+  cudaStream_t st = dn_stream(stream);
+  const long long HW = (long long)H * W, pHW = HW / ((long long)up_factor * up_factor);
+  UpSrc up{up_factor, up_mode, H / up_factor, W / up_factor};
+  const int nfold = joint ? 1 : B;
+  for (int pass = 0; pass < (kind == DL_BERHU ? 2 : 1); ++pass) {
+    dl_partial_kernel<<<dim3(DL_NBLK, B), 256, 0, st>>>(gt, pred, HW, pHW, W, up, max_depth, pass, ws, B, joint);
+    dl_fold_kernel<<<nfold, 32, 0, st>>>(ws, B, DL_NBLK, pass, joint);
+  }
+  dl_finalize_kernel<<<1, 1, 0, st>>>(ws, nfold, kind, weight, accumulate, loss);
+  DN_CHECK_LAUNCH();
+  return 0;
+}
+
+DN_EXPORT int dn_depth_loss_bwd(const float* gt, const float* pred, int B, int H, int W, int up_factor, int up_mode, float max_depth,
+                                int kind, int joint, float weight, const float* ws, const float* gout, float* gpred, void* stream) {
+  int e = dl_check(gt, pred, B, H, W, up_factor, kind);
+  if (e || !ws || !gout || !gpred) return e ? e : DN_E_ARG;
+  cudaStream_t st = dn_stream(stream);
+  const long long HW = (long long)H * W, pHW = HW / ((long long)up_factor * up_factor);
+  UpSrc up{up_factor, up_mode, H / up_factor, W / up_factor};
+  if (up_factor > 1) cudaMemsetAsync(gpred, 0, sizeof(float) * (size_t)B * pHW, st);
+  dl_bwd_kernel<<<dim3(DL_NBLK * 2, B), 256, 0, st>>>(gt, pred, HW, pHW, W, up, max_depth, kind, weight, ws, B, joint, gout, gpred);
+  DN_CHECK_LAUNCH();
+  return 0;
+}
+
+DN_EXPORT int dn_pool2(const float* src, int64_t NC, int H, int W, int mode, float* dst, void* stream) {
+  if (!src || !dst || NC < 1 || H < 2 || W < 2 || mode < 0 || mode > 1) return DN_E_ARG;
+  pool2_kernel<<<blocks_for(NC * (H / 2) * (W / 2), 256), 256, 0, dn_stream(stream)>>>(src, NC, H, W, mode, dst);
+  DN_CHECK_LAUNCH();
+  return 0;
+}
+
 DN_EXPORT int dn_l1_fwd(const float* gt, const float* pred, int B, int HW, float max_depth, float* ws, float* loss, void* stream) {
   if (!gt || !pred || !ws || !loss || B < 1 || HW < 1) return DN_E_ARG;
   cudaStream_t st = dn_stream(stream);

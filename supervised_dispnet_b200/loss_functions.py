@@ -1,7 +1,8 @@
 """Drop-in `loss_functions` module (reference: loss_functions.py): same names, argument meaning and return
 types for the functions on the training hot path, each executed by fused CUDA kernels of libdispnet_b200.so.
 
-  l1_loss                           reference :104-129   one masked-reduce kernel (+ finalize), no host sync
+  l1_loss / l2_loss / berhu_loss / Scale_invariant_loss / Multiscale_{L1,FULL_L1,L2,berhu,scale_inv}_loss
+                                    reference :77-315    one masked-reduce kernel family, deterministic, no host sync
   photometric_reconstruction_loss   reference :317-354   area pyramid + one fused warp/photometric kernel per
                                                           (scale, ref) pair, fused analytic backward
   explainability_loss               reference :357-364
@@ -32,39 +33,156 @@ def _max_depth(datasets):
 
 
 # ---------------------------------------------------------------------------------------------------------
-class _L1Fn(torch.autograd.Function):
+_KIND = {'l1': 0, 'l2': 1, 'berhu': 2, 'scale_inv': 3}
+
+
+class _DepthLossFn(torch.autograd.Function):
+    """One masked-reduce kernel family for every supervised depth loss (dn_depth_loss_fwd / _bwd): deterministic
+    two-stage reductions, no host sync, NaN on an empty mask like `mean()` of an empty selection."""
+
     @staticmethod
-    def forward(ctx, gt, pred, maxd):
+    def forward(ctx, gt, pred, cfg):
+        kind, joint, weight, maxd, upf, upmode = cfg
         L.require_cuda(gt, pred)
         gt, pred = gt.contiguous().float(), pred.contiguous().float()
-        B = pred.shape[0]
-        HW = pred[0].numel()
-        ws = torch.empty(2 * B, dtype=torch.float32, device=pred.device)
+        B, H, W = gt.shape
+        assert tuple(pred.shape) == (B, H // upf, W // upf) and H % upf == 0 and W % upf == 0, (tuple(gt.shape), tuple(pred.shape), upf)
+        ws = torch.empty(int(L.lib().dn_depth_loss_ws_floats(B)), dtype=torch.float32, device=pred.device)
         loss = torch.empty((), dtype=torch.float32, device=pred.device)
-        L.call('dn_l1_fwd', L.ptr(gt), L.ptr(pred), B, HW, maxd, L.ptr(ws), L.ptr(loss), L.stream_ptr())
+        L.call('dn_depth_loss_fwd', L.ptr(gt), L.ptr(pred), B, H, W, upf, upmode, maxd, kind, int(joint), weight, 0, L.ptr(ws),
+               L.ptr(loss), L.stream_ptr())
         ctx.save_for_backward(gt, pred, ws)
-        ctx.maxd = maxd
+        ctx.cfg = cfg
         return loss
 
     @staticmethod
     def backward(ctx, gout):
         gt, pred, ws = ctx.saved_tensors
-        B = pred.shape[0]
+        kind, joint, weight, maxd, upf, upmode = ctx.cfg
+        B, H, W = gt.shape
         g = torch.empty_like(pred)
         gout = gout.contiguous().float()
-        L.call('dn_l1_bwd', L.ptr(gt), L.ptr(pred), B, pred[0].numel(), ctx.maxd, L.ptr(ws), L.ptr(gout), L.ptr(g),
-               L.stream_ptr())
+        L.call('dn_depth_loss_bwd', L.ptr(gt), L.ptr(pred), B, H, W, upf, upmode, maxd, kind, int(joint), weight, L.ptr(ws),
+               L.ptr(gout), L.ptr(g), L.stream_ptr())
         return None, g, None
 
 
-def l1_loss(gt_depth, depth, datasets):
-    """sum_b mean_{valid_b} |gt - clamp(pred, 1e-3, max)| / B, using depth[0][:, 0] only (reference :104-129)."""
+def _per_sample(kind, gt_depth, depth, datasets):
     maxd = _max_depth(datasets)
     pred = depth[0][:, 0]
     # the reference indexes pred[valid] with a mask built from gt (:112-121): mismatching shapes raise there, and must not
     # become an out-of-bounds device read here
     assert tuple(gt_depth.shape) == tuple(pred.shape), 'gt_depth %s vs depth[0][:, 0] %s' % (tuple(gt_depth.shape), tuple(pred.shape))
-    return _L1Fn.apply(gt_depth, pred, maxd)
+    return _DepthLossFn.apply(gt_depth, pred, (_KIND[kind], False, 1.0, maxd, 1, 0))
+
+
+def l1_loss(gt_depth, depth, datasets):
+    """sum_b mean_{valid_b} |gt - clamp(pred, 1e-3, max)| / B, using depth[0][:, 0] only (reference :104-129)."""
+    return _per_sample('l1', gt_depth, depth, datasets)
+
+
+def l2_loss(gt_depth, depth, datasets):
+    """reference :77-102.  NOTE the reference's 'nyu' branch computes the mean ABSOLUTE error (:97), not the squared one;
+    that behaviour is kept."""
+    return _per_sample('l2' if datasets == 'kitti' else 'l1', gt_depth, depth, datasets)
+
+
+def berhu_loss(gt_depth, depth, datasets):
+    """reverse Huber with c = 0.2 max|residual| per sample (reference :131-160).  The reference's 'nyu' branch has lost its
+    loop header (:147-159 read `current_gt` before assignment); the same UnboundLocalError is raised here."""
+    if datasets == 'nyu':
+        raise UnboundLocalError("cannot access local variable 'current_gt' where it is not associated with a value "
+                                "(reference loss_functions.py:148)")
+    if datasets != 'kitti':          # the reference falls through both branches and returns 0 / B
+        return torch.zeros((), dtype=torch.float32, device=depth[0].device)
+    return _per_sample('berhu', gt_depth, depth, datasets)
+
+
+def Scale_invariant_loss(gt_depth, depth, datasets):
+    """mean((|gt| - |pred|)^2) - 0.5 (sum(gt - pred))^2 / n^2 per sample (reference :162-187)."""
+    if datasets not in ('kitti', 'nyu'):
+        return torch.zeros((), dtype=torch.float32, device=depth[0].device)
+    return _per_sample('scale_inv', gt_depth, depth, datasets)
+
+
+def _pool2(x, mode):
+    x = x.contiguous().float()
+    B, H, W = x.shape
+    out = torch.empty((B, H // 2, W // 2), dtype=torch.float32, device=x.device)
+    L.call('dn_pool2', L.ptr(x), B, H, W, mode, L.ptr(out), L.stream_ptr())
+    return out
+
+
+def generate_max_pyramid(image):
+    """reference :189-194"""
+    L.require_cuda(image)
+    pyr = [image]
+    for i in range(3):
+        pyr.append(_pool2(pyr[i], 1))
+    return pyr
+
+
+def generate_avg_pyramid(image):
+    """reference :196-201"""
+    L.require_cuda(image)
+    pyr = [image]
+    for i in range(3):
+        pyr.append(_pool2(pyr[i], 0))
+    return pyr
+
+
+def generate_bilinear_pyramid(image):
+    """reference :203-215: F.interpolate(scale_factor=0.5, mode='bilinear', align_corners=False) of an even-sized map samples
+    exactly between the four pixels of every 2x2 block, i.e. it is their mean."""
+    return generate_avg_pyramid(image)
+
+
+def _multiscale(kind, gt_depth, depth, pool_type='bilinear'):
+    if pool_type == 'max':
+        gts = generate_max_pyramid(gt_depth)
+    elif pool_type == 'avg':
+        gts = generate_avg_pyramid(gt_depth)
+    elif pool_type == 'bilinear':
+        gts = generate_bilinear_pyramid(gt_depth)
+    else:
+        raise TypeError('undefined pool type')
+    loss = 0
+    for i in range(len(depth)):
+        pred = depth[i][:, 0] if depth[i].dim() == 4 else depth[i]
+        loss = loss + _DepthLossFn.apply(gts[i], pred, (_KIND[kind], True, 1.0 / (2 ** i), 80.0, 1, 0))
+    return loss
+
+
+def Multiscale_L1_loss(gt_depth, depth, pool_type='bilinear'):
+    """sum_i mean_{valid_i} |gt_i - clamp(pred_i)| / 2^i with ONE mask over the whole batch per scale (reference :217-222...)."""
+    return _multiscale('l1', gt_depth, depth, pool_type)
+
+
+def Multiscale_L2_loss(gt_depth, depth):
+    """reference :243-258"""
+    return _multiscale('l2', gt_depth, depth)
+
+
+def Multiscale_berhu_loss(gt_depth, depth):
+    """reference :260-283"""
+    return _multiscale('berhu', gt_depth, depth)
+
+
+def Multiscale_scale_inv_loss(gt_depth, depth):
+    """reference :285-315"""
+    return _multiscale('scale_inv', gt_depth, depth)
+
+
+def Multiscale_FULL_L1_loss(gt_depth, depth, pool_type='bilinear'):
+    """every scale's prediction up-sampled x2^i (F.upsample, mode = pool_type) against the full-resolution ground truth
+    (reference :224-241); the up-sampling is fused into the masked-reduce kernel and its backward."""
+    if pool_type not in ('bilinear', 'nearest'):
+        raise NotImplementedError("Multiscale_FULL_L1_loss: up-sampling mode %r" % pool_type)
+    loss = 0
+    for i in range(len(depth)):
+        pred = depth[i][:, 0] if depth[i].dim() == 4 else depth[i]
+        loss = loss + _DepthLossFn.apply(gt_depth, pred, (_KIND['l1'], True, 1.0 / (2 ** i), 80.0, 2 ** i, int(pool_type == 'bilinear')))
+    return loss
 
 
 # ---------------------------------------------------------------------------------------------------------

@@ -8,7 +8,7 @@ and keep its own train.py.  Differences, all forced by breakages documented in S
   * a batch may be the reference's 2-tuple `(tgt_img, gt_depth)` (supervised) or the 5-tuple
     `(tgt_img, ref_imgs, intrinsics, intrinsics_inv, gt_depth)` the reference's commented-out line :418 used
     (the checked-in unsupervised branch reads unbound names);
-  * only `--loss L1` is wired for the supervised branch (the other nine losses are out of scope);
+  * every `--loss` choice of train.py:449-470 except DORN (which needs the DORN network) is wired;
   * tensorboard / csv side effects happen only when `train_writer` / `args.save_path` are given;
   * the `.to(device)` copies of batch i+1 (train.py:424-432) are issued on a copy stream while step i computes
     (`_DevicePrefetcher`): same tensors, same order, the 27 MB H2D copy just no longer sits between two steps;
@@ -226,10 +226,27 @@ def train(args, train_loader, disp_net, pose_exp_net, optimizer, epoch_size, log
         scale = 5.4 if getattr(args, 'monodepth2', False) else 1
         depth = [scale / disp for disp in disparities]
 
-        if not args.unsupervised:
-            if args.loss != 'L1':
+        if not args.unsupervised:           # the `--loss` switch of train.py:449-470 (DORN needs its own network: out of scope)
+            if args.loss == 'Multi_L1':
+                loss_1 = loss_functions.Multiscale_L1_loss(gt_depth, depth)
+            elif args.loss == 'Multi_full_L1':
+                loss_1 = loss_functions.Multiscale_FULL_L1_loss(gt_depth, depth)
+            elif args.loss == 'Multi_berhu':
+                loss_1 = loss_functions.Multiscale_berhu_loss(gt_depth, depth)
+            elif args.loss == 'Multi_L2':
+                loss_1 = loss_functions.Multiscale_L2_loss(gt_depth, depth)
+            elif args.loss == 'L1':
+                loss_1 = loss_functions.l1_loss(gt_depth, depth, args.dataset)
+            elif args.loss == 'berhu':
+                loss_1 = loss_functions.berhu_loss(gt_depth, depth, args.dataset)
+            elif args.loss == 'L2':
+                loss_1 = loss_functions.l2_loss(gt_depth, depth, args.dataset)
+            elif args.loss == 'scale_inv':
+                loss_1 = loss_functions.Scale_invariant_loss(gt_depth, depth, args.dataset)
+            elif args.loss == 'Multi_scale_inv':
+                loss_1 = loss_functions.Multiscale_scale_inv_loss(gt_depth, depth)
+            else:
                 raise TypeError('undefined loss')      # the reference does `raise "undefined loss"` (a TypeError in py3)
-            loss_1 = loss_functions.l1_loss(gt_depth, depth, args.dataset)
         else:
             loss_1 = loss_functions.photometric_reconstruction_loss(tgt_img, ref_imgs, intrinsics, intrinsics_inv, depth,
                                                                     explainability_mask, pose, args.rotation_mode,

@@ -668,3 +668,36 @@ def test_only_train_dec_detaches_the_encoder():
             assert g is None, k
         else:
             assert g is not None and rel(g, full[k]) < 1e-6, k
+
+
+def _g10():
+    import test_oracle_golden as TG
+    return TG
+
+
+@pytest.mark.parametrize('name,ds,hi', __import__('test_oracle_golden').G10_CASES)
+def test_golden_g10_supervised_losses(golden, name, ds, hi):
+    """l2 / berhu / Scale_invariant and the Multiscale_* losses of train.py's `--loss` switch
+    (loss_functions.py:77-315) on the masked-reduce kernel family, values and gradients vs the reference's own outputs."""
+    from supervised_dispnet_b200 import loss_functions as LF
+    g = golden('g10_supervised_losses')[name]
+    gt, preds = _g10().g10_inputs(ds, hi, DEV)
+    l = _g10().g10_call(LF, name, gt, preds, ds, False)
+    l.backward()
+    assert abs(float(l) - float(g['loss'])) <= 1e-5 * abs(float(g['loss'])), (float(l), float(g['loss']))
+    for p, r in zip(preds, g['grads']):
+        if r is None:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0
+        else:
+            assert rel(p.grad, r) < 1e-4, name
+    # deterministic reductions: a second evaluation gives the same bits
+    l2 = _g10().g10_call(LF, name, gt, [p.detach() for p in preds], ds, False)
+    assert float(l2) == float(l)
+
+
+def test_berhu_nyu_raises_like_the_reference(golden):
+    from supervised_dispnet_b200 import loss_functions as LF
+    assert golden('g10_supervised_losses')['berhu_nyu_raises'] == 'UnboundLocalError'
+    gt, preds = _g10().g10_inputs('nyu', 12.0, DEV)
+    with pytest.raises(UnboundLocalError):
+        LF.berhu_loss(gt, preds, 'nyu')

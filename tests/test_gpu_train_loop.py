@@ -132,3 +132,37 @@ def test_unchanged_reference_train_loop_g8(golden, tmp_path, precision, tol):
             assert float((sd[k].cpu() - v).norm() / v.norm()) < (1e-4 if precision == 'tc32' else 3e-3), k
         else:
             assert int(sd[k]) == int(v), k
+
+
+@pytest.mark.parametrize('loss_name', ['Multi_L1', 'Multi_full_L1', 'Multi_berhu', 'Multi_L2', 'berhu', 'L2', 'scale_inv', 'Multi_scale_inv'])
+def test_loss_switch_through_the_reference_loop(tmp_path, loss_name):
+    """train.py:449-470: every `--loss` choice (bar DORN) dispatched by the reference's own unmodified loop onto this
+    package's loss_functions; the first logged loss equals the oracle's value on the same weights and batch."""
+    import csv
+    import supervised_dispnet_b200 as S
+    from oracle import nets as ON, losses as OL, refshim as R
+    root = R.find_root()
+    assert root is not None
+    T = R.import_reference(root).train
+    sd = ON.init_state_dict('DispNetS', 0)
+    net = S.models.DispNetS('kitti')
+    net.load_state_dict({k: v.clone() for k, v in sd.items()})
+    net.precision = 'tc32'
+    net.to(DEV)
+    x, gt = I.images(2, 128, 416, seed=500), I.sparse_gt(2, 128, 416, seed=501, dataset='kitti', density=0.3)
+    d = ON.dispnets({k: v.clone() for k, v in sd.items()}, x, True)
+    depth = [1 / t for t in d]
+    want = {'Multi_L1': lambda: OL.multiscale_loss('l1', gt, depth), 'Multi_full_L1': lambda: OL.multiscale_full_l1_loss(gt, depth),
+            'Multi_berhu': lambda: OL.multiscale_loss('berhu', gt, depth), 'Multi_L2': lambda: OL.multiscale_loss('l2', gt, depth),
+            'berhu': lambda: OL.berhu_loss(gt, depth, 'kitti'), 'L2': lambda: OL.l2_loss(gt, depth, 'kitti'),
+            'scale_inv': lambda: OL.scale_invariant_loss(gt, depth, 'kitti'),
+            'Multi_scale_inv': lambda: OL.multiscale_loss('scale_inv', gt, depth)}[loss_name]()
+    opt = torch.optim.Adam(net.parameters(), lr=2e-4)
+    args = R.reference_args(tmp_path, batch_size=2, loss=loss_name, network='dispnet')
+    T.device, T.n_iter = torch.device(DEV), 0
+    T.loss_functions = S.loss_functions
+    T.train(args, [(x, gt)] * 2, net, torch.nn.Identity(), opt, 2, R.NullLogger(), R.NullWriter())
+    rows = [[float(v) for v in r] for r in csv.reader(open(tmp_path / args.log_full), delimiter='\t')]
+    assert len(rows) == 2 and all(math.isfinite(v) for r in rows for v in r)
+    assert abs(rows[0][1] - float(want)) <= 1e-4 * abs(float(want)), (rows[0], float(want))
+    assert rows[1][1] != rows[0][1]          # the optimizer step changed the prediction

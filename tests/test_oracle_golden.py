@@ -264,3 +264,47 @@ def test_g8_train_trajectory_oracle_port(golden):
             assert float((sd[k] - v).abs().max()) < 3 * 2e-4, k
         else:
             assert rel(sd[k].float(), v.float()) < 1e-4, k
+
+
+G10_CASES = [('l2_kitti', 'kitti', 95.0), ('l2_nyu', 'nyu', 12.0), ('berhu_kitti', 'kitti', 95.0), ('scale_inv_kitti', 'kitti', 95.0),
+             ('scale_inv_nyu', 'nyu', 12.0), ('multi_l1', 'kitti', 95.0), ('multi_l1_max', 'kitti', 95.0), ('multi_full_l1', 'kitti', 95.0),
+             ('multi_l2', 'kitti', 95.0), ('multi_berhu', 'kitti', 95.0), ('multi_scale_inv', 'kitti', 95.0)]
+
+
+def g10_inputs(ds, hi, device='cpu'):
+    B, H, W = 3, 32, 64
+    gt = I.sparse_gt(B, H, W, seed=140 if ds == 'kitti' else 141, dataset=ds, density=0.3 if ds == 'kitti' else 0.9)
+    preds = [I.depth_map(B, H >> s, W >> s, seed=150 + s, lo=0.0005, hi=hi).unsqueeze(1).to(device).requires_grad_(True) for s in range(4)]
+    return gt.to(device), preds
+
+
+def g10_call(mod, name, gt, preds, ds, oracle):
+    """Dispatch one G10 case on the oracle (oracle=True) or on a module with the reference's function names."""
+    if oracle:
+        return {'l2': lambda: mod.l2_loss(gt, preds, ds), 'berhu': lambda: mod.berhu_loss(gt, preds, ds),
+                'scale_inv': lambda: mod.scale_invariant_loss(gt, preds, ds), 'multi_l1': lambda: mod.multiscale_loss('l1', gt, preds),
+                'multi_l1_max': lambda: mod.multiscale_loss('l1', gt, preds, 'max'),
+                'multi_full_l1': lambda: mod.multiscale_full_l1_loss(gt, preds), 'multi_l2': lambda: mod.multiscale_loss('l2', gt, preds),
+                'multi_berhu': lambda: mod.multiscale_loss('berhu', gt, preds),
+                'multi_scale_inv': lambda: mod.multiscale_loss('scale_inv', gt, preds)}[name.replace('_kitti', '').replace('_nyu', '')]()
+    return {'l2': lambda: mod.l2_loss(gt, preds, ds), 'berhu': lambda: mod.berhu_loss(gt, preds, ds),
+            'scale_inv': lambda: mod.Scale_invariant_loss(gt, preds, ds), 'multi_l1': lambda: mod.Multiscale_L1_loss(gt, preds),
+            'multi_l1_max': lambda: mod.Multiscale_L1_loss(gt, preds, 'max'),
+            'multi_full_l1': lambda: mod.Multiscale_FULL_L1_loss(gt, preds), 'multi_l2': lambda: mod.Multiscale_L2_loss(gt, preds),
+            'multi_berhu': lambda: mod.Multiscale_berhu_loss(gt, preds),
+            'multi_scale_inv': lambda: mod.Multiscale_scale_inv_loss(gt, preds)}[name.replace('_kitti', '').replace('_nyu', '')]()
+
+
+@pytest.mark.parametrize('name,ds,hi', G10_CASES)
+def test_g10_supervised_losses(golden, name, ds, hi):
+    """The remaining `--loss` choices of train.py:449-470 (loss_functions.py:77-315): oracle restatement vs the reference."""
+    g = golden('g10_supervised_losses')[name]
+    gt, preds = g10_inputs(ds, hi)
+    l = g10_call(OL, name, gt, preds, ds, True)
+    l.backward()
+    assert abs(float(l) - float(g['loss'])) <= 2e-5 * abs(float(g['loss'])), (float(l), float(g['loss']))
+    for p, r in zip(preds, g['grads']):
+        if r is None:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0
+        else:
+            assert rel(p.grad, r) < 2e-5
