@@ -137,6 +137,9 @@ typedef struct dn_pack_job {
   int64_t s_r, s_c, s_kh, s_kw;
   float scale;          /* unpack only */
   int32_t pad_;
+  const float* row_scale; /* pack only, may be NULL: row r is multiplied by row_scale[r] -- the per-output-channel
+                             gamma/sqrt(var+eps) of an eval-mode BatchNorm folded into the convolution (validate_with_gt,
+                             train.py:642-723: BN uses running statistics there, so conv+BN is one affine map) */
 } dn_pack_job;
 int dn_pack_jobs(const dn_pack_job* jobs, int njobs, void* stream);
 
@@ -147,7 +150,7 @@ int dn_pack_jobs(const dn_pack_job* jobs, int njobs, void* stream);
  * copy in another dtype (the weight-gradient operand).  Weights: dst[kh][Cout_pad][Cx_pad], column kw*Cin + c. */
 int dn_rowx_expand(const dn_view* x, int k, int stride, int pad, const dn_view* out, const dn_view* out2, void* stream);
 int dn_rowx_pack_weight(const float* w /* [Cout][Cin][k][k] */, int Cout, int Cin, int k, void* dst, int dst_dtype, int cout_pad,
-                        int cx_pad, void* stream);
+                        int cx_pad, const float* row_scale /* [Cout] or NULL, see dn_pack_job */, void* stream);
 int dn_rowx_unpack_wgrad(const float* dwp /* [k][cout_pad][cx_pad] */, float* grad /* [Cout][Cin][k][k] */, int Cout, int Cin, int k,
                          int cout_pad, int cx_pad, float scale, void* stream);
 
@@ -172,6 +175,9 @@ int dn_bn_stats(const dn_view* y, double* sums, float* ws, void* stream);
 int dn_bn_finalize(const double* sums, double count, const float* gamma, const float* beta, float* running_mean,
                    float* running_var, float momentum, float eps, int training, int update_running,
                    float* mean_invstd, float* scale_shift, int C, void* stream);
+/* Eval-mode conv+BN folding: bias_out[c] = (conv_bias ? conv_bias[c] : 0) * scale_shift[c] + scale_shift[C + c], with
+ * scale_shift from dn_bn_finalize(training = 0); the scale half goes into the packed weights through dn_pack_job.row_scale. */
+int dn_bn_fold_bias(const float* conv_bias, const float* scale_shift, int C, float* bias_out, void* stream);
 /* Training-mode statistics in ONE launch: dn_bn_stats + dn_bn_finalize(training = 1) + `num_batches_tracked += 1`
  * (nn.BatchNorm2d.forward, torch/nn/modules/batchnorm.py; reference call sites models/Disp_vgg_BN.py:137-141).
  * sums (double[2C]) and num_batches_tracked (int64[1]) may be NULL. */
@@ -269,6 +275,9 @@ int dn_smooth_bwd(const float* p, int B, int H, int W, float weight, const float
  * crop window [y1,y2)x[x1,x2) (whole image when crop==0).  scale[b] (optional) multiplies pred (median scaling). */
 int dn_depth_errors(const float* gt, const float* pred, int B, int H, int W, float max_depth, int crop, int y1,
                     int y2, int x1, int x2, const float* scale, int32_t* counters, double* sums, void* stream);
+/* nn.UpsamplingBilinear2d(size=(H, W)) (align_corners=True) of fp32 [N,h,w] -> [N,H,W]: the NYU branch of validate_with_gt
+ * (train.py:696-700) brings the prediction to the ground truth's resolution before compute_errors. */
+int dn_resize_bilinear_ac(const float* src, int N, int h, int w, int H, int W, float* dst, void* stream);
 /* F.interpolate(mode='area') by integer factor f (loss_functions.py:326-327): NCHW fp32 */
 int dn_area_down(const float* src, int NC, int H, int W, int f, float* dst, void* stream);
 /*

@@ -291,6 +291,36 @@ def multiscale_full_l1_loss(gt_depth, depth, pool_type='bilinear'):
     return loss
 
 
+def resize_bilinear_ac(x, size):
+    """nn.UpsamplingBilinear2d(size) = bilinear with align_corners=True on [B,h,w] (train.py:698-700), explicit gathers."""
+    b, h, w = x.shape
+    H, W = size
+    ys = torch.arange(H, dtype=x.dtype) * ((h - 1) / (H - 1) if H > 1 else 0.0)
+    xs = torch.arange(W, dtype=x.dtype) * ((w - 1) / (W - 1) if W > 1 else 0.0)
+    y0, x0 = ys.floor().long().clamp(max=h - 1), xs.floor().long().clamp(max=w - 1)
+    y1, x1 = (y0 + 1).clamp(max=h - 1), (x0 + 1).clamp(max=w - 1)
+    ly, lx = (ys - y0.to(x.dtype)).view(1, -1, 1), (xs - x0.to(x.dtype)).view(1, 1, -1)
+    g = lambda yy, xx: x[:, yy][:, :, xx]          # noqa: E731
+    return (1 - ly) * ((1 - lx) * g(y0, x0) + lx * g(y0, x1)) + ly * ((1 - lx) * g(y1, x0) + lx * g(y1, x1))
+
+
+def validate_with_gt(forward_eval, loader, dataset):
+    """validate_with_gt (train.py:642-723): per batch depth = 1/disp[:, 0] of the eval-mode forward (NYU: resized to the ground
+    truth), compute_errors, then the batch average (AverageMeter with n = 1 per batch, logger.py:62-89)."""
+    tot, n = None, 0
+    with torch.no_grad():
+        for x, depth in loader:
+            if dataset == 'nyu':
+                depth = torch.squeeze(depth[:, 0])
+            out = 1 / forward_eval(x)[:, 0]
+            if dataset == 'nyu':
+                out = resize_bilinear_ac(out, depth.shape[1:])
+            e = compute_errors(depth, out, dataset)
+            tot = e if tot is None else [a + b for a, b in zip(tot, e)]
+            n += 1
+    return [t / n for t in tot]
+
+
 def garg_crop(h, w):
     return int(0.40810811 * h), int(0.99189189 * h), int(0.03594771 * w), int(0.96405229 * w)
 

@@ -312,6 +312,41 @@ def make_g10():
     torch.save(out, os.path.join(OUT, 'g10_supervised_losses.pt'))
 
 
+def g11_loaders():
+    import _inputs as I
+    kitti = [(I.images(2, 128, 416, seed=600 + i), I.sparse_gt(2, 128, 416, seed=610 + i, dataset='kitti', density=0.05)) for i in range(2)]
+    # NYU: the loader yields [B, 2, H, W] (depth, mask); the ground truth is larger than the network output (train.py:696-700)
+    nyu = [(I.images(2, 128, 160, seed=620 + i),
+            torch.stack([I.sparse_gt(2, 150, 200, seed=630 + i, dataset='nyu', density=0.9), torch.ones(2, 150, 200)], 1)) for i in range(2)]
+    return kitti, nyu
+
+
+def make_g11():
+    """G11: the reference's validate_with_gt (train.py:642-723) on two synthetic validation batches: Disp_vgg_BN / kitti
+    (Garg crop) and Disp_res_50 / nyu (prediction up-sampled to the ground truth's resolution), BatchNorm running
+    statistics taken after one training step so that eval mode is not the identity normalisation."""
+    from oracle import refshim as R
+    ref = R.import_reference(REF)
+    T = ref.train
+    T.device = torch.device('cpu')
+    kitti, nyu = g11_loaders()
+    out = {}
+    for tag, ctor, loader, ds in (('vgg_kitti', lambda: ref.models.Disp_vgg_BN('kitti'), kitti, 'kitti'),
+                                  ('res50_nyu', lambda: ref.models.Disp_res_50('nyu'), nyu, 'nyu')):
+        net = ctor()
+        torch.manual_seed(0)
+        net.init_weights()
+        net.train()
+        with torch.no_grad():
+            net(loader[0][0])                       # one training-mode forward: running statistics move off (0, 1)
+        sd = {k: v.clone() for k, v in net.state_dict().items() if 'running' in k or 'num_batches' in k}
+        args = R.reference_args('/tmp', dataset=ds)
+        errs, names = T.validate_with_gt(args, loader, net, 0, R.NullLogger(), [])
+        out[tag] = dict(errors=[float(e) for e in errs], names=names, running=sd)
+        print(tag, [round(float(e), 5) for e in errs])
+    torch.save(out, os.path.join(OUT, 'g11_validate.pt'))
+
+
 def I_sub(t):
     import _inputs as I
     return I.subsample(t)
@@ -322,7 +357,11 @@ if __name__ == '__main__':
         make_g8()
     elif len(sys.argv) > 1 and sys.argv[1] == 'g10':
         make_g10()
+        make_g11()
+    elif len(sys.argv) > 1 and sys.argv[1] == 'g11':
+        make_g11()
     else:
         main()
         make_g8()
         make_g10()
+        make_g11()

@@ -134,6 +134,7 @@ class NullLogger(object):
 
     def __init__(self):
         self.train_bar, self.train_writer = self._Bar(), self._Writer()
+        self.valid_bar, self.valid_writer = self._Bar(), self._Writer()
 
 
 class NullWriter(object):

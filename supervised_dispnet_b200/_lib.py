@@ -41,7 +41,7 @@ class DnPackJob(C.Structure):
     _fields_ = [('src', C.c_void_p), ('dst', C.c_void_p), ('dst_dtype', C.c_int32), ('unpack', C.c_int32), ('T', C.c_int32),
                 ('R', C.c_int32), ('Cc', C.c_int32), ('R_pad', C.c_int32), ('C_pad', C.c_int32), ('k', C.c_int32),
                 ('s_r', C.c_int64), ('s_c', C.c_int64), ('s_kh', C.c_int64), ('s_kw', C.c_int64), ('scale', C.c_float),
-                ('pad_', C.c_int32)]
+                ('pad_', C.c_int32), ('row_scale', C.c_void_p)]
 
 
 _P = C.c_void_p
@@ -67,9 +67,11 @@ _SIGS = {
     'dn_wgrad_tc_supported': ([C.POINTER(DnWgrad)], _I),
     'dn_reduce_ws_floats': ([_I], _I64),
     'dn_rowx_expand': ([_V, _I, _I, _I, _V, _V, _P], _I),
-    'dn_rowx_pack_weight': ([_P, _I, _I, _I, _P, _I, _I, _I, _P], _I),
+    'dn_rowx_pack_weight': ([_P, _I, _I, _I, _P, _I, _I, _I, _P, _P], _I),
     'dn_rowx_unpack_wgrad': ([_P, _P, _I, _I, _I, _I, _I, _F, _P], _I),
     'dn_bn_stats': ([_V, _P, _P, _P], _I),
+    'dn_bn_fold_bias': ([_P, _P, _I, _P, _P], _I),
+    'dn_resize_bilinear_ac': ([_P, _I, _I, _I, _I, _I, _P, _P], _I),
     'dn_bn_finalize': ([_P, _D, _P, _P, _P, _P, _F, _F, _I, _I, _P, _P, _I, _P], _I),
     'dn_bn_train_stats': ([_V, _P, _P, _P, _P, _P, _F, _F, _I, _P, _P, _P, _P, _P], _I),
     'dn_bn_apply': ([_V, _P, _V, _I, _I, _V, _V, _P], _I),

@@ -188,7 +188,7 @@ DN_EXPORT int dn_rowx_expand(const dn_view* x, int k, int stride, int pad, const
 
 // unpack = 0: dst[kh][co][kw * Cin + c] = w[co][c][kh][kw] (16-bit or fp32 dst, padding untouched);  unpack = 1: the reverse, fp32, scaled
 __global__ void rowx_weight_kernel(const float* __restrict__ src, void* __restrict__ dst, int dst_dtype, int Cout, int Cin, int k,
-                                   int cout_pad, int cx_pad, int unpack, float scale) {
+                                   int cout_pad, int cx_pad, int unpack, float scale, const float* __restrict__ row_scale) {
   dn_pdl_trigger();
   dn_pdl_wait();
   const int total = Cout * Cin * k * k;
@@ -199,16 +199,16 @@ __global__ void rowx_weight_kernel(const float* __restrict__ src, void* __restri
     const int c = q % Cin;
     const int co = q / Cin;
     const long long pk = ((long long)kh * cout_pad + co) * cx_pad + kw * Cin + c;
-    if (!unpack) dn_st(dst, dst_dtype, pk, src[i]);
+    if (!unpack) dn_st(dst, dst_dtype, pk, row_scale ? src[i] * row_scale[co] : src[i]);
     else ((float*)dst)[i] = scale * src[pk];
   }
 }
 
 DN_EXPORT int dn_rowx_pack_weight(const float* w, int Cout, int Cin, int k, void* dst, int dst_dtype, int cout_pad, int cx_pad,
-                                  void* stream) {
+                                  const float* row_scale, void* stream) {
   if (!w || !dst || Cout < 1 || Cin < 1 || k < 1 || cout_pad < Cout || cx_pad < k * Cin) return DN_E_ARG;
   const int total = Cout * Cin * k * k;
-  dn_launch(rowx_weight_kernel, dim3((total + 255) / 256), dim3(256), 0, dn_stream(stream), w, dst, dst_dtype, Cout, Cin, k, cout_pad, cx_pad, 0, 1.f);
+  dn_launch(rowx_weight_kernel, dim3((total + 255) / 256), dim3(256), 0, dn_stream(stream), w, dst, dst_dtype, Cout, Cin, k, cout_pad, cx_pad, 0, 1.f, row_scale);
   DN_CHECK_LAUNCH();
   return 0;
 }
@@ -217,7 +217,7 @@ DN_EXPORT int dn_rowx_unpack_wgrad(const float* dwp, float* grad, int Cout, int 
                                    void* stream) {
   if (!dwp || !grad || Cout < 1 || Cin < 1 || k < 1 || cout_pad < Cout || cx_pad < k * Cin) return DN_E_ARG;
   const int total = Cout * Cin * k * k;
-  dn_launch(rowx_weight_kernel, dim3((total + 255) / 256), dim3(256), 0, dn_stream(stream), dwp, (void*)grad, (int)DN_F32, Cout, Cin, k, cout_pad, cx_pad, 1, scale);
+  dn_launch(rowx_weight_kernel, dim3((total + 255) / 256), dim3(256), 0, dn_stream(stream), dwp, (void*)grad, (int)DN_F32, Cout, Cin, k, cout_pad, cx_pad, 1, scale, (const float*)nullptr);
   DN_CHECK_LAUNCH();
   return 0;
 }
@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(256) pack_jobs_kernel(const dn_pack_job* __res
         const long long toff = toffs[t];
         for (int cc = wrp; cc < 32; cc += 8) {
           const unsigned r = r0 + lane, c = c0 + cc;
-          tsm[cc][lane] = ((int)r < j.R && (int)c < j.Cc) ? src[r * j.s_r + c * j.s_c + toff] : 0.f;
+          tsm[cc][lane] = ((int)r < j.R && (int)c < j.Cc) ? src[r * j.s_r + c * j.s_c + toff] * (j.row_scale ? j.row_scale[r] : 1.f) : 0.f;
         }
         __syncthreads();
         for (int rr = wrp; rr < 32; rr += 8) {
@@ -266,17 +266,18 @@ __global__ void __launch_bounds__(256) pack_jobs_kernel(const dn_pack_job* __res
       const unsigned c = i - r * (unsigned)j.C_pad;
       const bool in = (int)r < j.R && (int)c < j.Cc;
       const float* sp = src + r * j.s_r + c * j.s_c;
+      const float rs = (in && j.row_scale) ? j.row_scale[r] : 1.f;
       if (j.dst_dtype == DN_F16) {
         __half* d = (__half*)j.dst + i;
-        for (unsigned t = 0; t < (unsigned)j.T; ++t) d[(long long)t * plane] = __float2half_rn(in ? sp[toffs[t]] : 0.f);
+        for (unsigned t = 0; t < (unsigned)j.T; ++t) d[(long long)t * plane] = __float2half_rn(in ? sp[toffs[t]] * rs : 0.f);
       } else if (j.dst_dtype == DN_BF16) {
         __nv_bfloat16* d = (__nv_bfloat16*)j.dst + i;
-        for (unsigned t = 0; t < (unsigned)j.T; ++t) d[(long long)t * plane] = __float2bfloat16_rn(in ? sp[toffs[t]] : 0.f);
+        for (unsigned t = 0; t < (unsigned)j.T; ++t) d[(long long)t * plane] = __float2bfloat16_rn(in ? sp[toffs[t]] * rs : 0.f);
       } else if (j.dst_dtype == DN_BF16_LO) {
-        for (unsigned t = 0; t < (unsigned)j.T; ++t) dn_st(j.dst, DN_BF16_LO, (long long)t * plane + i, in ? sp[toffs[t]] : 0.f);
+        for (unsigned t = 0; t < (unsigned)j.T; ++t) dn_st(j.dst, DN_BF16_LO, (long long)t * plane + i, in ? sp[toffs[t]] * rs : 0.f);
       } else {
         float* d = (float*)j.dst + i;
-        for (unsigned t = 0; t < (unsigned)j.T; ++t) d[(long long)t * plane] = in ? sp[toffs[t]] : 0.f;
+        for (unsigned t = 0; t < (unsigned)j.T; ++t) d[(long long)t * plane] = in ? sp[toffs[t]] * rs : 0.f;
       }
     }
   } else if (j.T <= 16 && j.s_c == j.T && j.s_kh == j.k && j.s_kw == 1) {
@@ -957,6 +958,17 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, double count
   bn_scale_shift(gamma ? gamma[c] : 1.f, beta ? beta[c] : 0.f, mean, invstd, sc, sh);
   scale_shift[c] = sc;
   scale_shift[C + c] = sh;
+}
+
+__global__ void bn_fold_bias_kernel(const float* __restrict__ cb, const float* __restrict__ ss, int C, float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) out[c] = (cb ? cb[c] : 0.f) * ss[c] + ss[C + c];
+}
+DN_EXPORT int dn_bn_fold_bias(const float* conv_bias, const float* scale_shift, int C, float* bias_out, void* stream) {
+  if (!scale_shift || !bias_out || C < 1) return DN_E_ARG;
+  bn_fold_bias_kernel<<<(C + 127) / 128, 128, 0, dn_stream(stream)>>>(conv_bias, scale_shift, C, bias_out);
+  DN_CHECK_LAUNCH();
+  return 0;
 }
 
 DN_EXPORT int dn_bn_finalize(const double* sums, double count, const float* gamma, const float* beta, float* running_mean,

@@ -848,6 +848,29 @@ DN_EXPORT int dn_depth_errors(const float* gt, const float* pred, int B, int H, 
   return 0;
 }
 
+__global__ void __launch_bounds__(256) resize_bilinear_ac_kernel(const float* __restrict__ src, int N, int h, int w, int H, int W,
+                                                                 float* __restrict__ dst) {
+  const float ry = H > 1 ? (float)(h - 1) / (float)(H - 1) : 0.f, rx = W > 1 ? (float)(w - 1) / (float)(W - 1) : 0.f;
+  const long long total = (long long)N * H * W;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % W);
+    const long long q = i / W;
+    const int y = (int)(q % H);
+    const float* p = src + (q / H) * (long long)h * w;
+    const float sy = ry * (float)y, sx = rx * (float)x;
+    const int y0 = (int)sy, x0 = (int)sx;
+    const int y1 = y0 + (y0 < h - 1 ? 1 : 0), x1 = x0 + (x0 < w - 1 ? 1 : 0);
+    const float ly = sy - (float)y0, lx = sx - (float)x0;
+    dst[i] = (1.f - ly) * ((1.f - lx) * p[y0 * w + x0] + lx * p[y0 * w + x1]) + ly * ((1.f - lx) * p[y1 * w + x0] + lx * p[y1 * w + x1]);
+  }
+}
+DN_EXPORT int dn_resize_bilinear_ac(const float* src, int N, int h, int w, int H, int W, float* dst, void* stream) {
+  if (!src || !dst || N < 1 || h < 1 || w < 1 || H < 1 || W < 1) return DN_E_ARG;
+  resize_bilinear_ac_kernel<<<blocks_for((long long)N * H * W, 256), 256, 0, dn_stream(stream)>>>(src, N, h, w, H, W, dst);
+  DN_CHECK_LAUNCH();
+  return 0;
+}
+
 DN_EXPORT int dn_area_down(const float* src, int NC, int H, int W, int f, float* dst, void* stream) {
   if (!src || !dst || f < 1 || H % f || W % f) return DN_E_ARG;
   long long total = (long long)NC * (H / f) * (W / f);

@@ -293,8 +293,19 @@ class ConvOp(Op):
     """nn.Conv2d (any k / stride / pad) or nn.ConvTranspose2d (stride 2), with fused bias + activation."""
 
     def __init__(self, plan, name, x, out, k, stride=1, pad=None, transposed=False, bias=True, act=L.ACT_NONE,
-                 needs_dx=True, bn_follows=False):
+                 needs_dx=True, bn_follows=False, fold_bn=None):
         self.name, self.x, self.out = name, x, out
+        # eval mode (validate_with_gt, train.py:642-723): the BatchNorm behind this convolution normalises with its running
+        # statistics, so conv + BN is one affine map -- gamma / sqrt(var + eps) goes into the packed weights (row_scale), the
+        # rest into the epilogue's bias vector, and the separate normalise pass over the activation disappears
+        self.fold_bn = fold_bn
+        if fold_bn is not None:
+            assert not plan.training and not transposed
+            self.fold_ss = torch.zeros(2 * out.C, dtype=torch.float32, device=plan.device)
+            self.fold_mi = torch.zeros(2 * out.C, dtype=torch.float32, device=plan.device)
+            self.fold_bias = torch.zeros(out.C, dtype=torch.float32, device=plan.device)
+            for suffix in ('.weight', '.bias'):
+                plan.register_param(fold_bn + suffix)
         # a bias in front of BatchNorm has an analytically zero gradient (BN subtracts the batch mean); the reference
         # computes rounding noise around 0 there.  We write exact zeros and skip the extra pass over dy.
         self.bias_grad_zero = bn_follows
@@ -415,6 +426,8 @@ class ConvOp(Op):
         if which == 'fwd':
             j.src, j.dst, j.dst_dtype, j.unpack = W.data_ptr(), self.wp.data_ptr(), _DT[plan.prec.split or plan.prec.act], 0
             j.R, j.Cc, j.R_pad, j.C_pad, j.s_r, j.s_c = self.Cout, self.Cin, self.cout_pad, self.cin_pad, self.s_co, self.s_ci
+            if self.fold_bn is not None:
+                j.row_scale = self.fold_ss.data_ptr()
         elif which == 'dgrad':
             if not self.needs_dx:
                 return None
@@ -426,6 +439,17 @@ class ConvOp(Op):
             j.scale = 1.0 / plan.prec.gscale
         return j
 
+    def pre_fwd(self, plan):
+        """Runs before the batched weight pack of the step: the folded BatchNorm's scale / bias vectors (eval mode)."""
+        if self.fold_bn is None:
+            return
+        n = self.fold_bn
+        L.call('dn_bn_finalize', None, 1.0, L.ptr(plan.param(n + '.weight')), L.ptr(plan.param(n + '.bias')),
+               L.ptr(plan.buffer(n + '.running_mean')), L.ptr(plan.buffer(n + '.running_var')), 0.1, 1e-5, 0, 0,
+               L.ptr(self.fold_mi), L.ptr(self.fold_ss), self.Cout, plan.stream)
+        cb = plan.param(self.name + '.bias') if self.has_bias else None
+        L.call('dn_bn_fold_bias', L.ptr(cb), L.ptr(self.fold_ss), self.Cout, L.ptr(self.fold_bias), plan.stream)
+
     def fwd(self, plan):
         if self._fwd_built is None:
             self._fwd_built = self._build_fwd(plan)
@@ -433,11 +457,14 @@ class ConvOp(Op):
             L.call('dn_rowx_expand', self.x.ref(), self.k, self.stride, self.pad, self.xr.ref(),
                    self.xr_g.ref() if self.xr_g is not None else None, plan.stream)
             L.call('dn_rowx_pack_weight', L.ptr(plan.param(self.name + '.weight')), self.Cout, self.Cin, self.k, L.ptr(self.wp),
-                   _DT[plan.prec.act], self.cout_pad, self.cin_pad, plan.stream)
+                   _DT[plan.prec.act], self.cout_pad, self.cin_pad, L.ptr(self.fold_ss) if self.fold_bn is not None else None,
+                   plan.stream)
         if self.split_x:
             hi, lo = self.split_x.planes(plan.prec.split)
             L.call('dn_split_bf16', self.split_x.ref(), hi.ref(), lo.ref(), plan.stream)
         b = plan.param(self.name + '.bias') if self.has_bias else None
+        if self.fold_bn is not None:
+            b = self.fold_bias
         for p, be, fl in self._fwd_built:
             p.bias = b.data_ptr() if b is not None else None
             L.call('dn_igemm_run', C.byref(p), be, plan.stream, tag=('fwd', be, fl, self.name))
@@ -591,6 +618,26 @@ class ConvOp(Op):
         if self.rowx:
             L.call('dn_rowx_unpack_wgrad', L.ptr(self.dwp), L.ptr(plan.grad_of(self.name + '.weight')), self.Cout, self.Cin, self.k,
                    self.cout_pad, self.cin_pad, 1.0 / plan.prec.gscale, st)
+
+
+def conv_bn(plan, conv_name, bn_name, x, y_shape, out, k, act=L.ACT_RELU, pool=False, stride=1, pad=None, bias=True,
+            needs_dx=True):
+    """nn.Conv2d -> nn.BatchNorm2d -> activation (-> MaxPool2d(2, 2)).  Training: the convolution writes y, BNOp normalises with
+    batch statistics (fused activation / pool).  Eval: BatchNorm is folded into the convolution (ConvOp fold_bn) and only
+    the optional pool remains as a pass of its own.  y_shape = (N, H, W, C) of the convolution output."""
+    N, H, W, Cc = y_shape
+    fold = (not plan.training) and os.environ.get('DISPNET_B200_FOLD_BN', '1') != '0'
+    if not fold:
+        y = plan.new_buf(N, H, W, Cc).view()
+        plan.add(ConvOp(plan, conv_name, x, y, k, stride=stride, pad=pad, bias=bias, needs_dx=needs_dx, bn_follows=True))
+        plan.add(BNOp(plan, bn_name, y, out, act, pool=pool))
+        return
+    if pool:
+        y = plan.new_buf(N, H, W, Cc).view()
+        plan.add(ConvOp(plan, conv_name, x, y, k, stride=stride, pad=pad, bias=bias, act=act, needs_dx=needs_dx, fold_bn=bn_name))
+        plan.add(MaxPoolOp(plan, y, out, 2, 2, 0))
+    else:
+        plan.add(ConvOp(plan, conv_name, x, out, k, stride=stride, pad=pad, bias=bias, act=act, needs_dx=needs_dx, fold_bn=bn_name))
 
 
 class HeadConvOp(Op):
@@ -924,6 +971,9 @@ class Plan:
         self.inputs = inputs
         self.stream = L.stream_ptr()
         self.outputs = [torch.empty(s, dtype=torch.float32, device=self.device) for s in self.out_shapes]
+        for op in self.ops:
+            if isinstance(op, ConvOp):
+                op.pre_fwd(self)
         self._run_jobs('fwd')
         for op in self.ops:
             op.fwd(self)

@@ -121,21 +121,16 @@ class Disp_res_50(E.PlannedModule):
                 p = 'layer%d.%d.' % (li + 1, b)
                 s = stride if b == 0 else 1
                 ho, wo = h // s, w // s
-                ya = nb(N, h, w, pl).view()
-                plan.add(E.ConvOp(plan, p + 'conv1', x, ya, 1, pad=0, bias=False))
                 a1 = nb(N, h, w, pl).view()
-                plan.add(E.BNOp(plan, p + 'bn1', ya, a1, ACT_RELU))
-                yb = nb(N, ho, wo, pl).view()
-                plan.add(E.ConvOp(plan, p + 'conv2', a1, yb, 3, stride=s, pad=1, bias=False))
+                E.conv_bn(plan, p + 'conv1', p + 'bn1', x, (N, h, w, pl), a1, 1, ACT_RELU, pad=0, bias=False)
                 a2 = nb(N, ho, wo, pl).view()
-                plan.add(E.BNOp(plan, p + 'bn2', yb, a2, ACT_RELU))
+                E.conv_bn(plan, p + 'conv2', p + 'bn2', a1, (N, ho, wo, pl), a2, 3, ACT_RELU, stride=s, pad=1, bias=False)
                 yc = nb(N, ho, wo, pl * 4).view()
                 plan.add(E.ConvOp(plan, p + 'conv3', a2, yc, 1, pad=0, bias=False))
                 if b == 0:
-                    yd = nb(N, ho, wo, pl * 4).view()
-                    plan.add(E.ConvOp(plan, p + 'downsample.0', x, yd, 1, stride=s, pad=0, bias=False))
                     idn = nb(N, ho, wo, pl * 4).view()
-                    plan.add(E.BNOp(plan, p + 'downsample.1', yd, idn, ACT_NONE))
+                    E.conv_bn(plan, p + 'downsample.0', p + 'downsample.1', x, (N, ho, wo, pl * 4), idn, 1, ACT_NONE, stride=s,
+                              pad=0, bias=False)
                 else:
                     idn = x
                 last = b == nblk - 1

@@ -98,15 +98,15 @@ class Disp_vgg_BN(E.PlannedModule):
         for b, nconv in enumerate(_BLOCKS):
             for j in range(nconv):
                 ci = conv_idx[k]
-                y = nb(N, h, w, planes[b]).view()
-                plan.add(E.ConvOp(plan, 'features.features.%d' % ci, x, y, 3, needs_dx=(k > 0), bn_follows=True))
+                yshape = (N, h, w, planes[b])
                 last = j == nconv - 1
                 if last:
                     h, w = h // 2, w // 2
                     out = skip_dst[b] if skip_dst[b] is not None else nb(N, h, w, planes[b]).view()
                 else:
                     out = nb(N, h, w, planes[b]).view()
-                plan.add(E.BNOp(plan, 'features.features.%d' % (ci + 1), y, out, ACT_RELU, pool=last))
+                E.conv_bn(plan, 'features.features.%d' % ci, 'features.features.%d' % (ci + 1), x, yshape, out, 3, ACT_RELU,
+                          pool=last, needs_dx=(k > 0))
                 x = out
                 k += 1
         c5 = x

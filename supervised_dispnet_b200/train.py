@@ -283,3 +283,60 @@ def train(args, train_loader, disp_net, pose_exp_net, optimizer, epoch_size, log
         n_iter += 1
     reader.flush()
     return losses.avg[0]
+
+
+def upsample_bilinear_ac(x, size):
+    """nn.UpsamplingBilinear2d(size=size) (align_corners=True) of [B,h,w] on the device kernel (train.py:696-700)."""
+    from . import _lib as L
+    L.require_cuda(x)
+    x = x.contiguous().float()
+    B, h, w = x.shape
+    H, W = int(size[0]), int(size[1])
+    out = torch.empty((B, H, W), dtype=torch.float32, device=x.device)
+    L.call('dn_resize_bilinear_ac', L.ptr(x), B, h, w, H, W, L.ptr(out), L.stream_ptr())
+    return out
+
+
+@torch.no_grad()
+def validate_with_gt(args, val_loader, disp_net, epoch, logger=None, output_writers=[], device=None):
+    """Mirror of the reference's validate_with_gt (train.py:642-723): eval-mode forward (BatchNorm folded into the
+    convolutions by the engine), depth = 1/disp (x5.4 under --monodepth2), the NYU branch's UpsamplingBilinear2d to the
+    ground truth's size, loss_functions.compute_errors per batch, AverageMeter over batches.  Returns (errors.avg, names)."""
+    device = device or next(disp_net.parameters()).device
+    batch_time = AverageMeter()
+    error_names = ['abs_diff', 'abs_rel', 'sq_rel', 'rmse', 'rmse_log', 'a1', 'a2', 'a3']
+    errors = AverageMeter(i=len(error_names))
+    disp_net.eval()
+    end = time.time()
+    if logger is not None:
+        logger.valid_bar.update(0)
+    n = 0
+    for i, (tgt_img, depth) in enumerate(val_loader):
+        tgt_img = tgt_img.to(device)
+        depth = depth.to(device)
+        if args.dataset == 'nyu':
+            depth = torch.squeeze(depth[:, 0, :, :])
+        if getattr(args, 'loss', 'L1') == 'DORN':
+            raise TypeError('DORN is outside the accelerated path')
+        output_disp = disp_net(tgt_img)
+        output_depth = 1 / output_disp[:, 0]
+        if getattr(args, 'monodepth2', False):
+            output_depth = output_depth * 5.4
+        if args.dataset == 'nyu':
+            d3 = depth if depth.dim() == 3 else depth.unsqueeze(0)
+            output_depth = torch.squeeze(upsample_bilinear_ac(output_depth, d3.shape[1:]))
+            depth = d3 if output_depth.dim() == 3 else depth
+            if output_depth.dim() == 2:
+                output_depth, depth = output_depth.unsqueeze(0), d3
+        errors.update(loss_functions.compute_errors(depth, output_depth, dataset=args.dataset,
+                                                    unsupervised=getattr(args, 'unsupervised', False)))
+        batch_time.update(time.time() - end)
+        end = time.time()
+        n = i + 1
+        if logger is not None:
+            logger.valid_bar.update(i + 1)
+            if i % args.print_freq == 0:
+                logger.valid_writer.write('valid: Time {} Abs Error {:.4f} ({:.4f})'.format(batch_time, errors.val[0], errors.avg[0]))
+    if logger is not None:
+        logger.valid_bar.update(n)
+    return errors.avg, error_names

@@ -166,3 +166,44 @@ def test_loss_switch_through_the_reference_loop(tmp_path, loss_name):
     assert len(rows) == 2 and all(math.isfinite(v) for r in rows for v in r)
     assert abs(rows[0][1] - float(want)) <= 1e-4 * abs(float(want)), (rows[0], float(want))
     assert rows[1][1] != rows[0][1]          # the optimizer step changed the prediction
+
+
+@pytest.mark.parametrize('tag', ['vgg_kitti', 'res50_nyu'])
+@pytest.mark.parametrize('precision,tol', [('tc32', 1e-4), ('mixed', 3e-3)])
+def test_validate_with_gt_g11(golden, tag, precision, tol):
+    """validate_with_gt (train.py:642-723) -- (a) the reference's OWN unmodified function with this package's
+    model and loss_functions swapped in, (b) the mirror supervised_dispnet_b200.train.validate_with_gt -- both against the
+    errors the unmodified reference computed on CPU (fixture G11).  Eval mode folds BatchNorm into the convolutions; the NYU
+    branch up-samples the prediction to the ground truth's size."""
+    import supervised_dispnet_b200 as S
+    from supervised_dispnet_b200 import train as MT
+    from oracle import nets as ON, refshim as R
+    from oracle.make_golden import g11_loaders
+    g = golden('g11_validate')[tag]
+    kitti, nyu = g11_loaders()
+    if tag == 'vgg_kitti':
+        net, sd, loader, ds = S.models.Disp_vgg_BN('kitti'), ON.init_state_dict('Disp_vgg_BN', 0, skip_dead=True), kitti, 'kitti'
+    else:
+        net, sd, loader, ds = S.models.Disp_res_50('nyu'), ON.init_state_dict('Disp_res_50', 0), nyu, 'nyu'
+    sd.update({k: v.clone() for k, v in g['running'].items()})
+    net.load_state_dict({k: v.clone() for k, v in sd.items()}, strict=False)
+    net.precision = precision
+    net.to(DEV)
+    root = R.find_root()
+    assert root is not None
+    T = R.import_reference(root).train
+    T.device = torch.device(DEV)
+    T.loss_functions = S.loss_functions
+    args = R.reference_args('/tmp', dataset=ds)
+    e_ref_loop, names = T.validate_with_gt(args, loader, net, 0, R.NullLogger(), [])
+    e_mirror, names2 = MT.validate_with_gt(args, loader, net, 0)
+    assert names == names2 == g['names']
+    for got in (e_ref_loop, e_mirror):
+        for a, b in zip(got, g['errors']):
+            assert abs(float(a) - b) <= tol * max(abs(b), 1e-2), (tag, got, g['errors'])
+    # the folded plan really dropped the BatchNorm passes
+    from supervised_dispnet_b200 import engine as E
+    plan = [p for k, p in net._plans.items() if k[1] is False][0]
+    assert any(isinstance(op, E.ConvOp) and op.fold_bn for op in plan.ops)
+    if tag == 'vgg_kitti':
+        assert not any(isinstance(op, E.BNOp) for op in plan.ops)

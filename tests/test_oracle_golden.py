@@ -308,3 +308,21 @@ def test_g10_supervised_losses(golden, name, ds, hi):
             assert p.grad is None or float(p.grad.abs().max()) == 0.0
         else:
             assert rel(p.grad, r) < 2e-5
+
+
+@pytest.mark.parametrize('tag', ['vgg_kitti', 'res50_nyu'])
+def test_g11_validate_with_gt_oracle(golden, tag):
+    """validate_with_gt (train.py:642-723) restated on the oracle vs the reference's own run (fixture G11)."""
+    from oracle.make_golden import g11_loaders
+    g = golden('g11_validate')[tag]
+    kitti, nyu = g11_loaders()
+    if tag == 'vgg_kitti':
+        sd = ON.init_state_dict('Disp_vgg_BN', 0, skip_dead=True)
+        sd.update({k: v.clone() for k, v in g['running'].items()})
+        errs = OL.validate_with_gt(lambda x: ON.disp_vgg_bn(sd, x, False, 'kitti'), kitti, 'kitti')
+    else:
+        sd = ON.init_state_dict('Disp_res_50', 0)
+        sd.update({k: v.clone() for k, v in g['running'].items()})
+        errs = OL.validate_with_gt(lambda x: ON.disp_res_50(sd, x, False, 'nyu'), nyu, 'nyu')
+    for a, b in zip(errs, g['errors']):
+        assert abs(a - b) <= 1e-4 * max(abs(b), 1e-3), (errs, g['errors'])
