@@ -116,6 +116,14 @@ int dn_tc_set_halo(int enabled);
 /* ---- layout / packing (replaces ATen copies: torch.cat, .contiguous(), weight re-layout) ---- */
 /* NCHW fp32 [N,C,H,W] -> channels [c0, c0+C) of NHWC view `dst` (channels >= c0+C left untouched). */
 int dn_pack_input(const float* src, int N, int C, int H, int W, const dn_view* dst, int c0, void* stream);
+/* Device input pipeline (custom_transforms.py:25-70; train.py:137-142 composes RandomHorizontalFlip, ArrayToTensor, Normalize):
+ * src uint8 [B,H,W,C] frames as the loader reads them -> dst fp32 [B,C,H,W] = ((src/255) - mean[c]) / std[c], sample b mirrored
+ * left-right when flip[b] != 0 (flip may be NULL; mean / std are HOST arrays of C <= 4 floats).  Bit-identical to the reference's
+ * per-sample numpy/torch chain; the host sends 1 byte per value instead of 4. */
+int dn_input_transform(const uint8_t* src, int B, int H, int W, int C, const int32_t* flip, const float* mean,
+                       const float* std, float* dst, void* stream);
+/* the same mirror for the ground-truth depth (custom_transforms.py:64): src, dst fp32 [B, rows, W] */
+int dn_flip_rows(const float* src, int B, int64_t rows, int W, const int32_t* flip, float* dst, void* stream);
 /* dst[t][r][c] = src[r*s_r + c*s_c + kh[t]*s_kh + kw[t]*s_kw] for r<R, c<Cc, else 0.
  * dst is [T][R_pad][C_pad] of dtype `dst_dtype`; src is the fp32 torch parameter. */
 int dn_pack_weight(const float* src, void* dst, int dst_dtype, int T, int R, int Cc, int R_pad, int C_pad,

@@ -13,5 +13,7 @@ from . import models  # noqa: F401
 from . import loss_functions  # noqa: F401
 from . import inverse_warp  # noqa: F401
 from . import layers  # noqa: F401
+from . import custom_transforms  # noqa: F401
+from . import utils  # noqa: F401
 
 __version__ = '0.1.0'

@@ -58,6 +58,8 @@ _SIGS = {
     'dn_tc_set_debug': ([_P], _I),
     'dn_tc_set_halo': ([_I], _I),
     'dn_pack_input': ([_P, _I, _I, _I, _I, _V, _I, _P], _I),
+    'dn_input_transform': ([_P, _I, _I, _I, _I, _P, C.POINTER(C.c_float), C.POINTER(C.c_float), _P, _P], _I),
+    'dn_flip_rows': ([_P, _I, _I64, _I, _P, _P, _P], _I),
     'dn_pack_weight': ([_P, _P, _I, _I, _I, _I, _I, _I, _IP, _IP, _I64, _I64, _I64, _I64, _P], _I),
     'dn_unpack_wgrad': ([_P, _P, _I, _I, _I, _I, _I, _IP, _IP, _I64, _I64, _I64, _I64, _F, _P], _I),
     'dn_pack_jobs': ([_P, _I, _P], _I),

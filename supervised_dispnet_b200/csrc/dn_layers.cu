@@ -36,6 +36,58 @@ DN_EXPORT int dn_pack_input(const float* src, int N, int C, int H, int W, const 
   return 0;
 }
 
+// ---- device input pipeline (custom_transforms.py:25-70): uint8 HWC frames -> normalised fp32 NCHW, optional horizontal flip --
+// RandomHorizontalFlip (:56-72) + ArrayToTensor (:41-53: HWC -> CHW, float, /255) + Normalize (:25-38: (x - mean) / std) for a whole
+// batch in one pass; the flip decision per sample comes from the host (the reference draws random.random() per sample).
+struct Norm4 { float mean[4], std[4]; };
+__global__ void __launch_bounds__(256) input_transform_kernel(const uint8_t* __restrict__ src, int B, int H, int W, int C,
+                                                              const int32_t* __restrict__ flip, Norm4 nm, float* __restrict__ dst) {
+  const long long total = (long long)B * H * W;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int w = (int)(i % W);
+    const long long q = i / W;
+    const int h = (int)(q % H);
+    const int b = (int)(q / H);
+    const int ws = (flip && flip[b]) ? W - 1 - w : w;
+    const uint8_t* p = src + (((long long)b * H + h) * W + ws) * C;
+    for (int c = 0; c < C; ++c) {
+      const float v = __fdiv_rn((float)p[c], 255.f);
+      dst[(((long long)b * C + c) * H + h) * W + w] = __fdiv_rn(__fsub_rn(v, nm.mean[c]), nm.std[c]);
+    }
+  }
+}
+__global__ void __launch_bounds__(256) flip_rows_kernel(const float* __restrict__ src, int B, long long rows, int W,
+                                                        const int32_t* __restrict__ flip, float* __restrict__ dst) {
+  const long long total = (long long)B * rows * W;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int w = (int)(i % W);
+    const long long q = i / W;
+    const int b = (int)(q / rows);
+    dst[i] = src[q * W + ((flip && flip[b]) ? W - 1 - w : w)];
+  }
+}
+DN_EXPORT int dn_input_transform(const uint8_t* src, int B, int H, int W, int C, const int32_t* flip, const float* mean,
+                                 const float* std, float* dst, void* stream) {
+  if (!src || !dst || !mean || !std || B < 1 || H < 1 || W < 1 || C < 1 || C > 4) return DN_E_ARG;
+  Norm4 nm;
+  for (int c = 0; c < 4; ++c) { nm.mean[c] = c < C ? mean[c] : 0.f; nm.std[c] = c < C ? std[c] : 1.f; }
+  long long total = (long long)B * H * W;
+  int blocks = (int)((total + 255) / 256), cap = dn_num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  input_transform_kernel<<<blocks, 256, 0, dn_stream(stream)>>>(src, B, H, W, C, flip, nm, dst);
+  DN_CHECK_LAUNCH();
+  return 0;
+}
+DN_EXPORT int dn_flip_rows(const float* src, int B, int64_t rows, int W, const int32_t* flip, float* dst, void* stream) {
+  if (!src || !dst || B < 1 || rows < 1 || W < 1) return DN_E_ARG;
+  long long total = (long long)B * rows * W;
+  int blocks = (int)((total + 255) / 256), cap = dn_num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  flip_rows_kernel<<<blocks, 256, 0, dn_stream(stream)>>>(src, B, rows, W, flip, dst);
+  DN_CHECK_LAUNCH();
+  return 0;
+}
+
 struct TapList {
   int32_t kh[DN_MAX_TAPS];
   int32_t kw[DN_MAX_TAPS];

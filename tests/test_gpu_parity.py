@@ -701,3 +701,49 @@ def test_berhu_nyu_raises_like_the_reference(golden):
     gt, preds = _g10().g10_inputs('nyu', 12.0, DEV)
     with pytest.raises(UnboundLocalError):
         LF.berhu_loss(gt, preds, 'nyu')
+
+
+def test_device_input_pipeline_bit_exact_vs_reference_transforms(monkeypatch):
+    """uint8 HWC frames -> normalised fp32 NCHW with the per-sample horizontal flip, ground-truth mirror and
+    intrinsics fix-up on the device, against the reference's own per-sample chain
+    Compose([RandomHorizontalFlip(), ArrayToTensor(), Normalize(.5, .5)]) (custom_transforms.py:14-72, train.py:137-142)."""
+    import random
+    import numpy as np
+    import supervised_dispnet_b200 as S
+    from oracle import refshim as R
+    root = R.find_root()
+    assert root is not None
+    ct = R.import_reference(root, with_train=False).custom_transforms
+    B, Hh, Ww = 6, 32, 52
+    rs = np.random.RandomState(0)
+    tgt = rs.randint(0, 256, (B, Hh, Ww, 3)).astype(np.uint8)
+    refs = [rs.randint(0, 256, (B, Hh, Ww, 3)).astype(np.uint8) for _ in range(2)]
+    gt = rs.rand(B, Hh, Ww).astype(np.float32) * 80
+    K = np.tile(np.array([[241.67, 0, 20.4], [0, 246.28, 15.9], [0, 0, 1]], np.float32), (B, 1, 1))
+    ref_t = ct.Compose([ct.RandomHorizontalFlip(), ct.ArrayToTensor(), ct.Normalize([0.5] * 3, [0.5] * 3)])
+    draws = [0.1, 0.9, 0.3, 0.7, 0.49, 0.51]
+    want_img, want_gt, want_K = [], [], []
+    for b in range(B):
+        monkeypatch.setattr(random, 'random', lambda b=b: draws[b])
+        imgs, g, k = ref_t([tgt[b].astype(np.float32)] + [r[b].astype(np.float32) for r in refs], gt[b], K[b])
+        want_img.append(imgs)
+        want_gt.append(g)
+        want_K.append(torch.as_tensor(np.array(k)))
+    monkeypatch.undo()
+    dt = S.custom_transforms.DeviceTransform(S.custom_transforms.Compose([S.custom_transforms.RandomHorizontalFlip(),
+                                                                         S.custom_transforms.ArrayToTensor(),
+                                                                         S.custom_transforms.Normalize([0.5] * 3, [0.5] * 3)]), device=DEV)
+    outs, g_dev, K_dev = dt([tgt] + refs, gt, K, flips=[int(d < 0.5) for d in draws])
+    for j, o in enumerate(outs):
+        w = torch.stack([want_img[b][j] for b in range(B)])
+        assert o.shape == w.shape and torch.equal(o.cpu(), w), j            # bit-exact
+    assert torch.equal(g_dev.cpu(), torch.stack(want_gt))
+    assert torch.equal(K_dev.cpu(), torch.stack(want_K))
+    # the random draw follows the reference's rule (one random.random() < 0.5 per sample)
+    dt2 = S.custom_transforms.DeviceTransform([0.5] * 3, [0.5] * 3, flip=True, device=DEV, rng=random.Random(1))
+    r = random.Random(1)
+    assert dt2.draw_flips(8) == [int(r.random() < 0.5) for _ in range(8)]
+    # the network consumes the transformed batch directly
+    m = S.models.Disp_vgg_BN().to(DEV).eval()
+    with torch.no_grad():
+        assert m(torch.nn.functional.pad(outs[0], (0, 12, 0, 32))).shape == (B, 1, 64, 64)

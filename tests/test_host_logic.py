@@ -245,3 +245,48 @@ def test_dp_segments_partition_the_gradient_arena():
     frac = (spans[0][1] - spans[0][0]) / plan._gflat.numel()
     assert 0.05 < frac < 0.2, frac
     assert plan._segments(False) == [(0, len(plan.ops))]
+
+
+@pytest.mark.parametrize('name', ['Disp_vgg_BN', 'DispNetS', 'Disp_res_50'])
+def test_checkpoint_roundtrip_with_reference_format(tmp_path, name):
+    """SURVEY 8(f4) / utils.py:79-93: a checkpoint written by this package's save_checkpoint loads into the REFERENCE model
+    class the way train.py:280-281 does (strict), and a checkpoint written by the reference's own save_checkpoint loads into
+    this package's model; the two files, their keys and the model_best copy follow the reference layout."""
+    import pathlib
+    import torch
+    import supervised_dispnet_b200 as S
+    from oracle import refshim as R
+    root = R.find_root()
+    if root is None:
+        pytest.skip('reference checkout not available')
+    ref = R.import_reference(root, with_train=False)
+    ours = getattr(S.models, name)()
+    torch.manual_seed(3)
+    ours.init_weights()
+    pose = S.models.PoseExpNet(2, False)
+    pose.init_weights()
+    opt = torch.optim.Adam([p for p in ours.parameters() if p.requires_grad], lr=1e-4)
+    d1 = tmp_path / 'ours'
+    d1.mkdir()
+    S.utils.save_checkpoint(d1, {'epoch': 4, 'state_dict': ours.state_dict(), 'optimizer': opt.state_dict()},
+                            {'epoch': 4, 'state_dict': pose.state_dict()}, is_best=True, epoch=3, record=True)
+    assert sorted(p.name for p in d1.iterdir()) == ['dispnet_checkpoint.pth.tar', 'dispnet_model_best.pth.tar',
+                                                    'exp_pose_checkpoint.pth.tar', 'exp_pose_model_best.pth.tar', 'weights_3']
+    rnet = getattr(ref.models, name)()
+    weights = torch.load(d1 / 'dispnet_checkpoint.pth.tar', weights_only=False)
+    rnet.load_state_dict(weights['state_dict'])                              # strict, as train.py:281
+    assert weights['epoch'] == 4 and 'optimizer' in weights
+    for k, v in rnet.state_dict().items():
+        assert torch.equal(v, ours.state_dict()[k]), k
+    rpose = ref.models.PoseExpNet(2, False)
+    rpose.load_state_dict(torch.load(d1 / 'exp_pose_model_best.pth.tar', weights_only=False)['state_dict'], strict=False)
+    # the other direction, written by the reference's own utils.save_checkpoint (it needs path.py's Path: pathlib + makedirs_p)
+    d2 = tmp_path / 'ref'
+    d2.mkdir()
+    torch.manual_seed(4)
+    rnet.init_weights()
+    ref.utils.save_checkpoint(pathlib.Path(d2), {'epoch': 7, 'state_dict': rnet.state_dict()}, {'epoch': 7, 'state_dict': rpose.state_dict()},
+                              is_best=False, epoch=6)
+    assert S.utils.load_checkpoint(d2 / 'dispnet_checkpoint.pth.tar', ours) == 7
+    for k, v in ours.state_dict().items():
+        assert torch.equal(v, rnet.state_dict()[k]), k
