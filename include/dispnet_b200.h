@@ -305,6 +305,45 @@ int dn_warp_photo_bwd(const float* tgt, const float* ref, const float* depth, co
                       const float* K, const float* Kinv, const float* mask, int64_t mask_bstride, int B, int h,
                       int w, int rot_mode, int pad_mode, int align_corners, const float* gout, float* gdepth,
                       float* gpose, float* gmask, int64_t gmask_bstride, float* ws /* [12*B] scratch */, void* stream);
+/*
+ * The whole photometric_reconstruction_loss (loss_functions.py:317-354) in three launches instead of one launch per
+ * (scale, reference frame) pair plus ~20 ATen launches for the pyramids and the scaled intrinsics:
+ *   dn_area_pyramid     the /2, /4, /8 area pyramids (F.interpolate(mode='area'), :326-327) of the target and all reference
+ *                       frames in ONE pass over the full-size images (each thread owns an 8x8 block: float4 loads / stores);
+ *   dn_photo_batch_fwd  every scale and every reference frame in one grid: a thread handles four neighbouring pixels
+ *                       (float4 loads of target / depth / mask), loops over the reference frames, scales K / K^-1 for its
+ *                       pyramid level itself (:329-330); block partials + a fixed-order fold: the scalar is deterministic;
+ *   dn_photo_batch_bwd  the analytic backward likewise; the depth gradient of a pixel is summed over the reference frames in
+ *                       registers and written once (no read-modify-write), the pose accumulators go through partial rows.
+ */
+#define DN_PHOTO_MAX_SCALES 4
+#define DN_PHOTO_MAX_REFS 4
+typedef struct dn_photo_scale {
+  const float* tgt;                      /* [B,3,h,w] target at this pyramid level */
+  const float* ref[DN_PHOTO_MAX_REFS];   /* [B,3,h,w] reference frames at this level */
+  const float* depth;                    /* [B,h,w] */
+  const float* mask;                     /* [B,R,h,w] explainability mask or NULL */
+  float* gdepth;                         /* bwd: [B,h,w], overwritten */
+  float* gmask;                          /* bwd: [B,R,h,w], overwritten (NULL without mask) */
+  int32_t h, w;
+  float downscale;                       /* H_full / h (:328) */
+  int32_t pad_;
+} dn_photo_scale;
+typedef struct dn_photo_batch {
+  dn_photo_scale sc[DN_PHOTO_MAX_SCALES];
+  int32_t nscales, nrefs, B;
+  int32_t rot_mode, pad_mode, align_corners;
+  const float* K;                        /* [B,3,3] full-resolution intrinsics and inverse */
+  const float* Kinv;
+  const float* pose;                     /* [B,R,6] */
+} dn_photo_batch;
+typedef struct dn_pyr_job { const float* src; float* l1; float* l2; float* l3; } dn_pyr_job;  /* [NC,H,W] -> /2, /4, /8 */
+int dn_area_pyramid(const dn_pyr_job* jobs /* host array */, int njobs /* <= 8 */, int64_t NC, int H, int W, void* stream);
+int64_t dn_photo_ws_floats(const dn_photo_batch* p);
+/* loss[0] += sum over scales and reference frames of mean|diff|; nanflag[0] |= 1 on a NaN difference */
+int dn_photo_batch_fwd(const dn_photo_batch* p, float* ws, float* loss, int32_t* nanflag, void* stream);
+/* gpose [B,R,6] overwritten; gdepth / gmask of every scale overwritten */
+int dn_photo_batch_bwd(const dn_photo_batch* p, const float* gout, float* ws, float* gpose, void* stream);
 /* plain inverse_warp forward/backward on its own (inverse_warp.py:160-193): out [B,C,h,w]. */
 int dn_inverse_warp_fwd(const float* img, const float* depth, const float* pose, const float* K, const float* Kinv,
                         int B, int C, int h, int w, int rot_mode, int pad_mode, int align_corners, float* out,

@@ -44,6 +44,25 @@ class DnPackJob(C.Structure):
                 ('pad_', C.c_int32), ('row_scale', C.c_void_p)]
 
 
+PHOTO_MAX_SCALES, PHOTO_MAX_REFS = 4, 4
+
+
+class DnPhotoScale(C.Structure):
+    _fields_ = [('tgt', C.c_void_p), ('ref', C.c_void_p * PHOTO_MAX_REFS), ('depth', C.c_void_p), ('mask', C.c_void_p),
+                ('gdepth', C.c_void_p), ('gmask', C.c_void_p), ('h', C.c_int32), ('w', C.c_int32), ('downscale', C.c_float),
+                ('pad_', C.c_int32)]
+
+
+class DnPhotoBatch(C.Structure):
+    _fields_ = [('sc', DnPhotoScale * PHOTO_MAX_SCALES), ('nscales', C.c_int32), ('nrefs', C.c_int32), ('B', C.c_int32),
+                ('rot_mode', C.c_int32), ('pad_mode', C.c_int32), ('align_corners', C.c_int32), ('K', C.c_void_p),
+                ('Kinv', C.c_void_p), ('pose', C.c_void_p)]
+
+
+class DnPyrJob(C.Structure):
+    _fields_ = [('src', C.c_void_p), ('l1', C.c_void_p), ('l2', C.c_void_p), ('l3', C.c_void_p)]
+
+
 _P = C.c_void_p
 _I = C.c_int
 _I64 = C.c_int64
@@ -106,6 +125,10 @@ _SIGS = {
     'dn_smooth_bwd': ([_P, _I, _I, _I, _F, _P, _P, _P], _I),
     'dn_depth_errors': ([_P, _P, _I, _I, _I, _F, _I, _I, _I, _I, _I, _P, _P, _P, _P], _I),
     'dn_area_down': ([_P, _I, _I, _I, _I, _P, _P], _I),
+    'dn_area_pyramid': ([C.POINTER(DnPyrJob), _I, _I64, _I, _I, _P], _I),
+    'dn_photo_ws_floats': ([C.POINTER(DnPhotoBatch)], _I64),
+    'dn_photo_batch_fwd': ([C.POINTER(DnPhotoBatch), _P, _P, _P, _P], _I),
+    'dn_photo_batch_bwd': ([C.POINTER(DnPhotoBatch), _P, _P, _P, _P], _I),
     'dn_warp_photo_fwd': ([_P, _P, _P, _P, _I, _P, _P, _P, _I64, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P], _I),
     'dn_warp_photo_bwd': ([_P, _P, _P, _P, _I, _P, _P, _P, _I64, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _I64, _P,
                            _P], _I),

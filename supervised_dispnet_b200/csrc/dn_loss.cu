@@ -406,13 +406,7 @@ __device__ void block_reduce12(float* acc12, float* dst) {
 }
 
 // (q, G) -> pose gradient for one batch element
-__global__ void pose_grad_finalize_kernel(const float* __restrict__ ws, const float* __restrict__ pose, int pose_stride, int B,
-                                          int rot_mode, float* gpose) {
-  int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= B) return;
-  const float* a = ws + 12 * b;
-  const float* ps = pose + (long long)b * pose_stride;
-  float* g = gpose + (long long)b * pose_stride;
+__device__ void pose_grad_chain(const float* a, const float* ps, int rot_mode, float* g) {
   g[0] += a[0]; g[1] += a[1]; g[2] += a[2];
   const float* G = a + 3;
   if (rot_mode == 0) {
@@ -447,6 +441,13 @@ __global__ void pose_grad_finalize_kernel(const float* __restrict__ ws, const fl
     g[4] += (gy - y * dot) / nrm;
     g[5] += (gz - z * dot) / nrm;
   }
+}
+
+__global__ void pose_grad_finalize_kernel(const float* __restrict__ ws, const float* __restrict__ pose, int pose_stride, int B,
+                                          int rot_mode, float* gpose) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  pose_grad_chain(ws + 12 * b, pose + (long long)b * pose_stride, rot_mode, gpose + (long long)b * pose_stride);
 }
 
 __global__ void __launch_bounds__(256) warp_photo_fwd_kernel(const float* __restrict__ tgt, const float* __restrict__ ref,
@@ -529,6 +530,292 @@ __global__ void __launch_bounds__(256) warp_photo_bwd_kernel(const float* __rest
     if (gmask) gmask[gmask_bs * b + i] = gm;
   }
   block_reduce12(acc12, ws + 12 * b);
+}
+
+
+// ---------------------------------------------------------------------------------------------------
+// batched photometric loss: area pyramid, all (scale, reference) pairs forward, all backward -- three launches
+// ---------------------------------------------------------------------------------------------------
+struct PyrJobs { dn_pyr_job j[8]; };
+// one thread per 8x8 block of a full-size plane: 16 float4 loads, /2 level as 4 float4 stores, /4 as 2 float2, /8 as one float
+__global__ void __launch_bounds__(256) area_pyramid_kernel(PyrJobs jobs, long long NC, int H, int W) {
+  const dn_pyr_job jb = jobs.j[blockIdx.y];
+  const int bw = W >> 3, bh = H >> 3;
+  const long long total = NC * bh * bw;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int bx = (int)(i % bw);
+    const long long q = i / bw;
+    const int by = (int)(q % bh);
+    const long long nc = q / bh;
+    const float* s = jb.src + (nc * H + (long long)by * 8) * W + bx * 8;
+    float l1v[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const float4 a0 = *reinterpret_cast<const float4*>(s + (2 * r) * W), a1 = *reinterpret_cast<const float4*>(s + (2 * r) * W + 4);
+      const float4 b0 = *reinterpret_cast<const float4*>(s + (2 * r + 1) * W), b1 = *reinterpret_cast<const float4*>(s + (2 * r + 1) * W + 4);
+      l1v[r][0] = ((a0.x + a0.y) + (b0.x + b0.y)) * 0.25f;
+      l1v[r][1] = ((a0.z + a0.w) + (b0.z + b0.w)) * 0.25f;
+      l1v[r][2] = ((a1.x + a1.y) + (b1.x + b1.y)) * 0.25f;
+      l1v[r][3] = ((a1.z + a1.w) + (b1.z + b1.w)) * 0.25f;
+    }
+    const int W1 = W >> 1, W2 = W >> 2, W3 = W >> 3;
+    if (jb.l1) {
+      float* d = jb.l1 + (nc * (H >> 1) + (long long)by * 4) * W1 + bx * 4;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) *reinterpret_cast<float4*>(d + r * W1) = make_float4(l1v[r][0], l1v[r][1], l1v[r][2], l1v[r][3]);
+    }
+    float l2v[2][2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+      for (int c = 0; c < 2; ++c)
+        l2v[r][c] = ((l1v[2 * r][2 * c] + l1v[2 * r][2 * c + 1]) + (l1v[2 * r + 1][2 * c] + l1v[2 * r + 1][2 * c + 1])) * 0.25f;
+    if (jb.l2) {
+      float* d = jb.l2 + (nc * (H >> 2) + (long long)by * 2) * W2 + bx * 2;
+      *reinterpret_cast<float2*>(d) = make_float2(l2v[0][0], l2v[0][1]);
+      *reinterpret_cast<float2*>(d + W2) = make_float2(l2v[1][0], l2v[1][1]);
+    }
+    if (jb.l3) jb.l3[(nc * (H >> 3) + by) * W3 + bx] = ((l2v[0][0] + l2v[0][1]) + (l2v[1][0] + l2v[1][1])) * 0.25f;
+  }
+}
+
+constexpr int PB_NBX = 52;      // blocks per (scale, sample): 52 x 256 threads x 4 pixels = one 128x416 plane
+
+__device__ __forceinline__ void pb_build_poses(const dn_photo_batch& P, const dn_photo_scale& sc, int b, PoseMats* m) {
+  if ((int)threadIdx.x < P.nrefs) {
+    float Ks[9], Kis[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+      const float k = P.K[9 * b + i], ki = P.Kinv[9 * b + i];
+      Ks[i] = i < 6 ? k / sc.downscale : k;                      // intrinsics[:, 0:2] / downscale (:329)
+      Kis[i] = (i % 3) < 2 ? ki * sc.downscale : ki;             // intrinsics_inv[:, :, 0:2] * downscale (:330)
+    }
+    build_pose(P.pose + ((long long)b * P.nrefs + threadIdx.x) * 6, Ks, Kis, P.rot_mode, m[threadIdx.x]);
+  }
+}
+
+__global__ void __launch_bounds__(256, 3) photo_batch_fwd_kernel(const __grid_constant__ dn_photo_batch P, float* __restrict__ part,
+                                                              int32_t* nanflag) {
+  __shared__ PoseMats m[DN_PHOTO_MAX_REFS];
+  const int s_ = blockIdx.z, b = blockIdx.y;
+  const dn_photo_scale& sc = P.sc[s_];
+  const int h = sc.h, w = sc.w;
+  const long long hw = (long long)h * w;
+  const int nq = (int)((hw + 3) >> 2);
+  float acc = 0.f;
+  bool bad = false;
+  if ((int)(blockIdx.x * blockDim.x) < nq) {          // (uniform per block: coarse levels need only the first few blocks)
+    pb_build_poses(P, sc, b, m);
+    __syncthreads();
+    const float* tb = sc.tgt + 3 * hw * b;
+    const float* db = sc.depth + hw * b;
+    const bool vec = (w & 3) == 0;
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += gridDim.x * blockDim.x) {
+      const int i0 = q << 2;
+      const int v0 = i0 / w, u0 = i0 - v0 * w;       // w % 4 == 0: the four pixels share the image row
+      float t[3][4], d[4];
+      if (vec) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float4 v4 = *reinterpret_cast<const float4*>(tb + c * hw + i0);
+          t[c][0] = v4.x; t[c][1] = v4.y; t[c][2] = v4.z; t[c][3] = v4.w;
+        }
+        const float4 d4 = *reinterpret_cast<const float4*>(db + i0);
+        d[0] = d4.x; d[1] = d4.y; d[2] = d4.z; d[3] = d4.w;
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const bool in = i0 + k < hw;
+          d[k] = in ? db[i0 + k] : 1.f;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) t[c][k] = in ? tb[c * hw + i0 + k] : 0.f;
+        }
+      }
+      for (int r = 0; r < P.nrefs; ++r) {
+        const float* rb = sc.ref[r] + 3 * hw * b;
+        float mk[4] = {1.f, 1.f, 1.f, 1.f};
+        if (sc.mask) {
+          const float* mp = sc.mask + ((long long)b * P.nrefs + r) * hw + i0;
+          if (vec) { const float4 m4 = *reinterpret_cast<const float4*>(mp); mk[0] = m4.x; mk[1] = m4.y; mk[2] = m4.z; mk[3] = m4.w; }
+          else
+#pragma unroll
+            for (int k = 0; k < 4; ++k) mk[k] = i0 + k < hw ? mp[k] : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int i = i0 + k;
+          if (i >= hw) break;
+          WarpPix p;
+          warp_pixel(m[r], vec ? u0 + k : i % w, vec ? v0 : i / w, d[k], h, w, P.pad_mode, P.align_corners, p);
+          float val[3];
+          bil_fetch<3, false>(rb, hw, h, w, p, val, nullptr, nullptr);
+          const float oob = (val[0] == 0.f && val[1] == 0.f && val[2] == 0.f) ? 0.f : 1.f;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            float e = (t[c][k] - val[c]) * oob;
+            if (sc.mask) e *= mk[k];
+            acc += fabsf(e);
+            bad |= (e != e);
+          }
+        }
+      }
+    }
+  }
+  acc = block_sum(acc);
+  if (threadIdx.x == 0) part[((long long)s_ * P.B + b) * gridDim.x + blockIdx.x] = acc;
+  if (bad && nanflag) atomicOr(nanflag, 1);
+}
+// one warp per scale folds that scale's partials in a fixed order; thread 0 adds the weighted total to the loss
+__global__ void photo_fold_kernel(const __grid_constant__ dn_photo_batch P, const float* __restrict__ part, int nbx, float* loss) {
+  __shared__ double tot[DN_PHOTO_MAX_SCALES];
+  const int s_ = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (s_ < P.nscales) {
+    const int n = P.B * nbx;
+    double a = 0.0;
+    for (int k = lane; k < n; k += 32) a += (double)part[(long long)s_ * n + k];
+    a = dn_warp_sum_d(a);
+    if (lane == 0) tot[s_] = a / ((double)P.B * 3.0 * P.sc[s_].h * P.sc[s_].w);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int k = 0; k < P.nscales; ++k) t += tot[k];
+    loss[0] += (float)t;
+  }
+}
+
+__device__ void block_reduce12_row(float* acc12, float* dst) {     // like block_reduce12, written (not added) to a partial row
+  __shared__ float red12r[12][33];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 12; ++i) {
+    float v = dn_warp_sum(acc12[i]);
+    if (lane == 0) red12r[i][wid] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 12) {
+    float t = 0.f;
+    for (int k = 0; k < (int)(blockDim.x >> 5); ++k) t += red12r[threadIdx.x][k];
+    dst[threadIdx.x] = t;
+  }
+}
+
+__global__ void __launch_bounds__(256) photo_batch_bwd_kernel(const __grid_constant__ dn_photo_batch P, const float* __restrict__ gout,
+                                                              float* __restrict__ part12) {
+  __shared__ PoseMats m[DN_PHOTO_MAX_REFS];
+  const int s_ = blockIdx.z, b = blockIdx.y;
+  const dn_photo_scale& sc = P.sc[s_];
+  const int h = sc.h, w = sc.w;
+  const long long hw = (long long)h * w;
+  const int nq = (int)((hw + 3) >> 2);
+  const bool active = (int)(blockIdx.x * blockDim.x) < nq;
+  if (active) pb_build_poses(P, sc, b, m);
+  __syncthreads();
+  const float go = gout[0] / ((float)P.B * 3.f * (float)h * (float)w);
+  const float* tb = sc.tgt + 3 * hw * b;
+  const float* db = sc.depth + hw * b;
+  const bool vec = (w & 3) == 0;
+  for (int r = 0; r < P.nrefs; ++r) {
+    // one reference frame at a time keeps 12 pose accumulators live; the depth gradient of the quad is carried across the
+    // frames through gdepth itself only when R > 1 (first frame writes, later frames add: same thread, same address)
+    float acc12[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) acc12[i] = 0.f;
+    if (active) {
+      const float* rb = sc.ref[r] + 3 * hw * b;
+      for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += gridDim.x * blockDim.x) {
+        const int i0 = q << 2;
+        const int v0 = i0 / w, u0 = i0 - v0 * w;
+        float t[3][4], d[4], mk[4] = {1.f, 1.f, 1.f, 1.f}, gd[4] = {0.f, 0.f, 0.f, 0.f}, gm[4] = {0.f, 0.f, 0.f, 0.f};
+        if (vec) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const float4 v4 = *reinterpret_cast<const float4*>(tb + c * hw + i0);
+            t[c][0] = v4.x; t[c][1] = v4.y; t[c][2] = v4.z; t[c][3] = v4.w;
+          }
+          const float4 d4 = *reinterpret_cast<const float4*>(db + i0);
+          d[0] = d4.x; d[1] = d4.y; d[2] = d4.z; d[3] = d4.w;
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const bool in = i0 + k < hw;
+            d[k] = in ? db[i0 + k] : 1.f;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) t[c][k] = in ? tb[c * hw + i0 + k] : 0.f;
+          }
+        }
+        const float* mp = sc.mask ? sc.mask + ((long long)b * P.nrefs + r) * hw + i0 : nullptr;
+        if (mp) {
+          if (vec) { const float4 m4 = *reinterpret_cast<const float4*>(mp); mk[0] = m4.x; mk[1] = m4.y; mk[2] = m4.z; mk[3] = m4.w; }
+          else
+#pragma unroll
+            for (int k = 0; k < 4; ++k) mk[k] = i0 + k < hw ? mp[k] : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int i = i0 + k;
+          if (i >= hw) break;
+          WarpPix p;
+          warp_pixel(m[r], vec ? u0 + k : i % w, vec ? v0 : i / w, d[k], h, w, P.pad_mode, P.align_corners, p);
+          float val[3], dvx[3], dvy[3];
+          bil_fetch<3, true>(rb, hw, h, w, p, val, dvx, dvy);
+          const float oob = (val[0] == 0.f && val[1] == 0.f && val[2] == 0.f) ? 0.f : 1.f;
+          float gix = 0.f, giy = 0.f;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const float e0 = (t[c][k] - val[c]) * oob;
+            const float e = mp ? e0 * mk[k] : e0;
+            const float sg = sgn(e) * go;
+            gm[k] += sg * e0;
+            const float gW = -sg * oob * (mp ? mk[k] : 1.f);
+            gix += gW * dvx[c];
+            giy += gW * dvy[c];
+          }
+          warp_chain(m[r], p, h, w, gix, giy, gd[k], acc12);
+        }
+        float* gp = sc.gdepth + hw * b + i0;
+        if (vec) {
+          float4 o = make_float4(gd[0], gd[1], gd[2], gd[3]);
+          if (r > 0) { const float4 pr = *reinterpret_cast<const float4*>(gp); o.x += pr.x; o.y += pr.y; o.z += pr.z; o.w += pr.w; }
+          *reinterpret_cast<float4*>(gp) = o;
+          if (sc.gmask) *reinterpret_cast<float4*>(sc.gmask + ((long long)b * P.nrefs + r) * hw + i0) = make_float4(gm[0], gm[1], gm[2], gm[3]);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (i0 + k < hw) {
+              gp[k] = r > 0 ? gp[k] + gd[k] : gd[k];
+              if (sc.gmask) sc.gmask[((long long)b * P.nrefs + r) * hw + i0 + k] = gm[k];
+            }
+        }
+      }
+    }
+    block_reduce12_row(acc12, part12 + ((((long long)s_ * P.nrefs + r) * P.B + b) * gridDim.x + blockIdx.x) * 12);
+  }
+}
+// one warp per (sample, reference frame): lanes stride over the partial rows of all scales and blocks, a shuffle tree adds them
+// (fixed order: deterministic), lane 0 chains the 12 sums to the 6-DoF pose gradient
+__global__ void __launch_bounds__(128) photo_pose_finalize_kernel(const __grid_constant__ dn_photo_batch P, const float* __restrict__ part12,
+                                                                  int nbx, float* __restrict__ gpose) {
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (i >= P.B * P.nrefs) return;
+  const int b = i / P.nrefs, r = i % P.nrefs;
+  float a[12];
+#pragma unroll
+  for (int k = 0; k < 12; ++k) a[k] = 0.f;
+  for (int s_ = 0; s_ < P.nscales; ++s_) {
+    const float* row = part12 + ((((long long)s_ * P.nrefs + r) * P.B + b) * nbx) * 12;
+    for (int x = lane; x < nbx; x += 32)
+#pragma unroll
+      for (int k = 0; k < 12; ++k) a[k] += row[x * 12 + k];
+  }
+#pragma unroll
+  for (int k = 0; k < 12; ++k) a[k] = dn_warp_sum(a[k]);
+  if (lane == 0) {
+    float g[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    pose_grad_chain(a, P.pose + (long long)i * 6, P.rot_mode, g);
+    for (int k = 0; k < 6; ++k) gpose[(long long)i * 6 + k] = g[k];
+  }
 }
 
 template <int CMAX>
@@ -660,23 +947,9 @@ __global__ void __launch_bounds__(256) dl_partial_kernel(const float* __restrict
   a0 = block_sum(a0); a1 = block_sum(a1); a2 = block_sum(a2); a3 = block_sum(a3); mx = block_max(mx);
   if (threadIdx.x == 0) { part[0] = a0; part[1] = a1; part[2] = a2; part[3] = a3; part[4] = mx; }
 }
-// one block per sample folds the partial rows in block order (double) into the sample's statistics
-// (joint: one mask over the whole batch, Multiscale_* losses -- a single block folds the rows of all samples into sample 0)
-__global__ void dl_fold_kernel(float* ws, int B, int nblk, int pass, int joint) {
-  const int b = blockIdx.x;
-  if (threadIdx.x != 0) return;
-  const float* part = ws + (long long)B * DL_NSTAT + (long long)b * nblk * DL_NPART;
-  float* stat = ws + (long long)b * DL_NSTAT;
-  if (joint) nblk *= B;
-  double s[4] = {0, 0, 0, 0};
-  float mx = 0.f;
-  for (int k = 0; k < nblk; ++k) {
-    for (int j = 0; j < 4; ++j) s[j] += (double)part[k * DL_NPART + j];
-    mx = fmaxf(mx, part[k * DL_NPART + 4]);
-  }
-  if (!pass) { stat[0] = (float)s[0]; stat[1] = (float)s[1]; stat[2] = (float)s[2]; stat[3] = (float)s[3]; stat[4] = mx; }
-  else { stat[5] = (float)s[0]; stat[6] = (float)s[1]; }
-}
+// fold + finalize in one launch: warp w folds the partial rows of samples w, w + nwarps, ... (lanes stride over the rows, shuffle
+// tree: a fixed order, double) into the sample's statistics; after the last pass warp 0 adds the per-sample values in sample
+// order.  (joint: one mask over the whole batch, Multiscale_* losses -- all rows fold into sample 0.)
 __device__ __forceinline__ float dl_value(const float* st, int kind) {
   const float n = st[0];
   if (kind == DL_L1) return st[1] / n;                       // 0/0 -> NaN like mean() of an empty selection
@@ -684,11 +957,37 @@ __device__ __forceinline__ float dl_value(const float* st, int kind) {
   if (kind == DL_BERHU) return st[5] / n;
   return st[2] / n - 0.5f * (st[3] * st[3]) / (n * n);       // Scale_invariant_loss :166
 }
-__global__ void dl_finalize_kernel(const float* ws, int B, int kind, float weight, int accumulate, float* loss) {
-  float t = 0.f;
-  for (int b = 0; b < B; ++b) t += dl_value(ws + (long long)b * DL_NSTAT, kind);
-  t = weight * t / (float)B;
-  loss[0] = accumulate ? loss[0] + t : t;
+__global__ void __launch_bounds__(1024) dl_fold_kernel(float* ws, int B, int nblk, int pass, int joint, int final, int kind, float weight,
+                                                       int accumulate, float* loss) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int nfold = joint ? 1 : B, rows = joint ? nblk * B : nblk;
+  for (int b = warp; b < nfold; b += nwarps) {
+    const float* part = ws + (long long)B * DL_NSTAT + (long long)b * nblk * DL_NPART;
+    float* stat = ws + (long long)b * DL_NSTAT;
+    double s[4] = {0, 0, 0, 0};
+    float mx = 0.f;
+    for (int k = lane; k < rows; k += 32) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) s[j] += (double)part[k * DL_NPART + j];
+      mx = fmaxf(mx, part[k * DL_NPART + 4]);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) s[j] = dn_warp_sum_d(s[j]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) {
+      if (!pass) { stat[0] = (float)s[0]; stat[1] = (float)s[1]; stat[2] = (float)s[2]; stat[3] = (float)s[3]; stat[4] = mx; }
+      else { stat[5] = (float)s[0]; stat[6] = (float)s[1]; }
+    }
+  }
+  if (!final) return;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int b = 0; b < nfold; ++b) t += dl_value(ws + (long long)b * DL_NSTAT, kind);
+    t = weight * t / (float)nfold;
+    loss[0] = accumulate ? loss[0] + t : t;
+  }
 }
 __global__ void __launch_bounds__(256) dl_bwd_kernel(const float* __restrict__ gt, const float* __restrict__ pred, long long HW,
                                                      long long pHW, int W, UpSrc up, float maxd, int kind, float weight,
@@ -763,12 +1062,11 @@ DN_EXPORT int dn_depth_loss_fwd(const float* gt, const float* pred, int B, int H
   cudaStream_t st = dn_stream(stream);
   const long long HW = (long long)H * W, pHW = HW / ((long long)up_factor * up_factor);
   UpSrc up{up_factor, up_mode, H / up_factor, W / up_factor};
-  const int nfold = joint ? 1 : B;
-  for (int pass = 0; pass < (kind == DL_BERHU ? 2 : 1); ++pass) {
+  const int npass = kind == DL_BERHU ? 2 : 1;
+  for (int pass = 0; pass < npass; ++pass) {
     dl_partial_kernel<<<dim3(DL_NBLK, B), 256, 0, st>>>(gt, pred, HW, pHW, W, up, max_depth, pass, ws, B, joint);
-    dl_fold_kernel<<<nfold, 32, 0, st>>>(ws, B, DL_NBLK, pass, joint);
+    dl_fold_kernel<<<1, 1024, 0, st>>>(ws, B, DL_NBLK, pass, joint, pass == npass - 1, kind, weight, accumulate, loss);
   }
-  dl_finalize_kernel<<<1, 1, 0, st>>>(ws, nfold, kind, weight, accumulate, loss);
   DN_CHECK_LAUNCH();
   return 0;
 }
@@ -888,6 +1186,58 @@ DN_EXPORT int dn_explain_fwd(const float* mask, int64_t n, float* loss, void* st
 DN_EXPORT int dn_explain_bwd(const float* mask, int64_t n, const float* gout, float* gmask, void* stream) {
   if (!mask || !gout || !gmask || n < 1) return DN_E_ARG;
   explain_bwd_kernel<<<blocks_for(n, 1024), 256, 0, dn_stream(stream)>>>(mask, n, 1.f / (float)n, gout, gmask);
+  DN_CHECK_LAUNCH();
+  return 0;
+}
+
+
+DN_EXPORT int dn_area_pyramid(const dn_pyr_job* jobs, int njobs, int64_t NC, int H, int W, void* stream) {
+  if (!jobs || njobs < 1 || njobs > 8 || NC < 1 || (H & 7) || (W & 7)) return DN_E_ARG;
+  PyrJobs pj;
+  memset(&pj, 0, sizeof(pj));
+  for (int i = 0; i < njobs; ++i) {
+    pj.j[i] = jobs[i];
+    if (!jobs[i].src || ((uintptr_t)jobs[i].src & 15)) return DN_E_ARG;
+  }
+  const long long total = NC * (H >> 3) * (W >> 3);
+  area_pyramid_kernel<<<dim3(blocks_for(total, 256), njobs), 256, 0, dn_stream(stream)>>>(pj, NC, H, W);
+  DN_CHECK_LAUNCH();
+  return 0;
+}
+
+static int photo_check(const dn_photo_batch* p) {
+  if (!p || p->nscales < 1 || p->nscales > DN_PHOTO_MAX_SCALES || p->nrefs < 1 || p->nrefs > DN_PHOTO_MAX_REFS || p->B < 1) return DN_E_ARG;
+  if (!p->K || !p->Kinv || !p->pose) return DN_E_ARG;
+  for (int s = 0; s < p->nscales; ++s) {
+    const dn_photo_scale& sc = p->sc[s];
+    if (!sc.tgt || !sc.depth || sc.h < 1 || sc.w < 1) return DN_E_ARG;
+    for (int r = 0; r < p->nrefs; ++r)
+      if (!sc.ref[r]) return DN_E_ARG;
+  }
+  return 0;
+}
+DN_EXPORT int64_t dn_photo_ws_floats(const dn_photo_batch* p) {
+  if (photo_check(p)) return 0;
+  return (int64_t)p->nscales * p->nrefs * p->B * PB_NBX * 12;      // the backward's partial rows (the forward needs 1/12 of it)
+}
+DN_EXPORT int dn_photo_batch_fwd(const dn_photo_batch* p, float* ws, float* loss, int32_t* nanflag, void* stream) {
+  int e = photo_check(p);
+  if (e || !ws || !loss) return e ? e : DN_E_ARG;
+  cudaStream_t st = dn_stream(stream);
+  photo_batch_fwd_kernel<<<dim3(PB_NBX, p->B, p->nscales), 256, 0, st>>>(*p, ws, nanflag);
+  photo_fold_kernel<<<1, 32 * DN_PHOTO_MAX_SCALES, 0, st>>>(*p, ws, PB_NBX, loss);
+  DN_CHECK_LAUNCH();
+  return 0;
+}
+DN_EXPORT int dn_photo_batch_bwd(const dn_photo_batch* p, const float* gout, float* ws, float* gpose, void* stream) {
+  int e = photo_check(p);
+  if (e || !ws || !gout || !gpose) return e ? e : DN_E_ARG;
+  for (int s = 0; s < p->nscales; ++s)
+    if (!p->sc[s].gdepth || (p->sc[s].mask && !p->sc[s].gmask)) return DN_E_ARG;
+  cudaStream_t st = dn_stream(stream);
+  photo_batch_bwd_kernel<<<dim3(PB_NBX, p->B, p->nscales), 256, 0, st>>>(*p, gout, ws);
+  const int n = p->B * p->nrefs;
+  photo_pose_finalize_kernel<<<(n + 3) / 4, 128, 0, st>>>(*p, ws, PB_NBX, gpose);
   DN_CHECK_LAUNCH();
   return 0;
 }

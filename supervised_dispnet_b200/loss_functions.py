@@ -268,6 +268,97 @@ def _area_down(x, h, w):
     return out
 
 
+BATCHED_PHOTO = True      # False: one launch per (scale, reference frame) pair (the round-1 path, kept for odd pyramid shapes)
+
+
+def _photo_batch_ok(H, W, depths, R):
+    """The three-launch path serves the reference's own pyramid: every depth map is the full size divided by 1, 2, 4 or 8."""
+    if not BATCHED_PHOTO or R > L.PHOTO_MAX_REFS or len(depths) > L.PHOTO_MAX_SCALES or (H % 8) or (W % 8):
+        return False
+    for d in depths:
+        f = H // max(int(d.shape[2]), 1)
+        if f not in (1, 2, 4, 8) or d.shape[2] * f != H or d.shape[3] * f != W:
+            return False
+    return True
+
+
+class _PhotoBatchFn(torch.autograd.Function):
+    """photometric_reconstruction_loss in three launches (dn_area_pyramid, dn_photo_batch_fwd; dn_photo_batch_bwd)."""
+
+    @staticmethod
+    def forward(ctx, cfg, tgt, refs, K, Kinv, pose, *maps):
+        rot, pad, align, S, has_mask = cfg
+        depths = [d.contiguous().float() for d in maps[:S]]
+        masks = [m.contiguous().float() for m in maps[S:]] if has_mask else [None] * S
+        tgt = tgt.contiguous().float()
+        refs = [r.contiguous().float() for r in refs]
+        pose = pose.contiguous().float()
+        K, Kinv = K.contiguous().float(), Kinv.contiguous().float()
+        B, _, H, W = tgt.shape
+        R = len(refs)
+        dev = tgt.device
+        st = L.stream_ptr()
+        # /2, /4, /8 area pyramids of the target and every reference frame: one pass over the full-size images
+        need = sorted({H // d.shape[2] for d in depths} - {1})
+        imgs = [tgt] + refs
+        pyr = [{1: im} for im in imgs]
+        if need:
+            jobs = (L.DnPyrJob * len(imgs))()
+            for j, im in enumerate(imgs):
+                jobs[j].src = im.data_ptr()
+                for f, fld in ((2, 'l1'), (4, 'l2'), (8, 'l3')):
+                    if f in need:
+                        pyr[j][f] = torch.empty((B, 3, H // f, W // f), dtype=torch.float32, device=dev)
+                        setattr(jobs[j], fld, pyr[j][f].data_ptr())
+            L.call('dn_area_pyramid', jobs, len(imgs), B * 3, H, W, st)
+        P = L.DnPhotoBatch()
+        P.nscales, P.nrefs, P.B = S, R, B
+        P.rot_mode, P.pad_mode, P.align_corners = rot, pad, align
+        P.K, P.Kinv, P.pose = K.data_ptr(), Kinv.data_ptr(), pose.data_ptr()
+        for s_, (d, m) in enumerate(zip(depths, masks)):
+            f = H // d.shape[2]
+            sc = P.sc[s_]
+            sc.tgt = pyr[0][f].data_ptr()
+            for r in range(R):
+                sc.ref[r] = pyr[1 + r][f].data_ptr()
+            sc.depth = d.data_ptr()
+            sc.mask = m.data_ptr() if m is not None else None
+            sc.h, sc.w, sc.downscale = d.shape[2], d.shape[3], float(H) / d.shape[2]
+        ws = torch.empty(int(L.lib().dn_photo_ws_floats(C_byref(P))), dtype=torch.float32, device=dev)
+        loss = torch.zeros((), dtype=torch.float32, device=dev)
+        nanflag = torch.zeros(1, dtype=torch.int32, device=dev)
+        L.call('dn_photo_batch_fwd', C_byref(P), L.ptr(ws), L.ptr(loss), L.ptr(nanflag), st)
+        if STRICT_NAN_CHECK:
+            assert int(nanflag.item()) == 0, 'photometric loss is NaN'
+        ctx.cfg = cfg
+        ctx.P = P
+        ctx.keep = (pyr, depths, masks, pose, K, Kinv, ws)
+        ctx.nanflag = nanflag
+        return loss
+
+    @staticmethod
+    def backward(ctx, gout):
+        rot, pad, align, S, has_mask = ctx.cfg
+        pyr, depths, masks, pose, K, Kinv, ws = ctx.keep
+        P = ctx.P
+        gout = gout.contiguous().float()
+        gpose = torch.empty_like(pose)
+        gdepths = [torch.empty_like(d) for d in depths]
+        gmasks = [torch.empty_like(m) if m is not None else None for m in masks]
+        for s_ in range(S):
+            P.sc[s_].gdepth = gdepths[s_].data_ptr()
+            P.sc[s_].gmask = gmasks[s_].data_ptr() if gmasks[s_] is not None else None
+        L.call('dn_photo_batch_bwd', C_byref(P), L.ptr(gout), L.ptr(ws), L.ptr(gpose), L.stream_ptr())
+        res = [None, None, None, None, None, gpose] + gdepths
+        if has_mask:
+            res += gmasks
+        return tuple(res)
+
+
+def C_byref(x):
+    return L.C.byref(x)
+
+
 class _PhotoFn(torch.autograd.Function):
     """inputs: pose [B,R,6], then S depth maps [B,1,h,w], then S masks [B,R,h,w] (or absent)."""
 
@@ -357,7 +448,17 @@ def photometric_reconstruction_loss(tgt_img, ref_imgs, intrinsics, intrinsics_in
         S = min(S, len(explainability_mask))       # zip() semantics of the reference loop (:352)
     cfg = (_ROT[rotation_mode], _PAD[padding_mode], int(ALIGN_CORNERS), S, has_mask)
     maps = list(depth[:S]) + (list(explainability_mask[:S]) if has_mask else [])
-    return _PhotoFn.apply(cfg, tgt_img, list(ref_imgs), intrinsics, intrinsics_inv, pose, *maps)
+    L.require_cuda(tgt_img, pose, intrinsics, intrinsics_inv, *depth[:S])
+    B, C3, H, W = tgt_img.shape
+    R = len(ref_imgs)
+    assert C3 == 3 and all(tuple(r.shape) == tuple(tgt_img.shape) for r in ref_imgs), 'tgt / ref images must be [B,3,H,W]'
+    assert pose.dim() == 3 and pose.size(0) == B and pose.size(1) == R and pose.size(2) == 6      # reference :319-320
+    assert tuple(intrinsics.shape) == (B, 3, 3) and tuple(intrinsics_inv.shape) == (B, 3, 3)
+    for d, m in zip(depth[:S], explainability_mask[:S] if has_mask else [None] * S):
+        assert d.dim() == 4 and d.size(0) == B and d.size(1) == 1, 'depth maps must be [B,1,h,w]'
+        assert m is None or tuple(m.shape) == (B, R, d.size(2), d.size(3)), 'explainability mask must be [B,R,h,w]'
+    fn = _PhotoBatchFn if _photo_batch_ok(H, W, depth[:S], R) else _PhotoFn
+    return fn.apply(cfg, tgt_img, list(ref_imgs), intrinsics, intrinsics_inv, pose, *maps)
 
 
 # ---------------------------------------------------------------------------------------------------------

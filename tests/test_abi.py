@@ -39,16 +39,18 @@ def test_header_symbols_exported(lib):
 
 def test_struct_layout_matches_c(lib, tmp_path):
     src = tmp_path / 'sz.c'
-    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "dispnet_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",'
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "dispnet_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",'
                    'sizeof(dn_view),sizeof(dn_tap),sizeof(dn_igemm),sizeof(dn_wgrad),offsetof(dn_igemm,taps),'
-                   'offsetof(dn_igemm,out_pad_ok),offsetof(dn_wgrad,scale),sizeof(dn_pack_job),offsetof(dn_pack_job,row_scale));'
+                   'offsetof(dn_igemm,out_pad_ok),offsetof(dn_wgrad,scale),sizeof(dn_pack_job),offsetof(dn_pack_job,row_scale),sizeof(dn_photo_scale),sizeof(dn_photo_batch),'
+                   'offsetof(dn_photo_batch,K),sizeof(dn_pyr_job));'
                    'return 0;}\n')
     exe = tmp_path / 'sz'
     subprocess.check_call(['gcc', '-I', os.path.join(ROOT, 'include'), str(src), '-o', str(exe)])
     c = [int(v) for v in subprocess.check_output([str(exe)]).split()]
     py = [ctypes.sizeof(lib.DnView), ctypes.sizeof(lib.DnTap), ctypes.sizeof(lib.DnIgemm), ctypes.sizeof(lib.DnWgrad),
           lib.DnIgemm.taps.offset, lib.DnIgemm.out_pad_ok.offset, lib.DnWgrad.scale.offset, ctypes.sizeof(lib.DnPackJob),
-          lib.DnPackJob.row_scale.offset]
+          lib.DnPackJob.row_scale.offset, ctypes.sizeof(lib.DnPhotoScale), ctypes.sizeof(lib.DnPhotoBatch), lib.DnPhotoBatch.K.offset,
+          ctypes.sizeof(lib.DnPyrJob)]
     assert c == py
 
 

@@ -747,3 +747,19 @@ def test_device_input_pipeline_bit_exact_vs_reference_transforms(monkeypatch):
     m = S.models.Disp_vgg_BN().to(DEV).eval()
     with torch.no_grad():
         assert m(torch.nn.functional.pad(outs[0], (0, 12, 0, 32))).shape == (B, 1, 64, 64)
+
+
+@pytest.mark.parametrize('name', ['photo_euler_zeros', 'photo_quat_zeros_mask', 'photo_euler_border_mask_r4'])
+def test_photometric_pairwise_path_still_matches_oracle(name, monkeypatch):
+    """The one-launch-per-(scale, reference) form of the photometric loss (used for pyramid shapes the three-launch path does
+    not serve) against the oracle, and bit-level run-to-run determinism of the batched path's scalar."""
+    from supervised_dispnet_b200 import loss_functions as LF
+    monkeypatch.setattr(LF, 'BATCHED_PHOTO', False)
+    r = dict(P().LOSS_CASES)[name]()
+    for k, v in r.items():
+        assert v <= LOSS_TOL[k], (name, k, v)
+    monkeypatch.setattr(LF, 'BATCHED_PHOTO', True)
+    tgt, refs, K, Kinv, depth, masks, pose = P()._photo_inputs(2, 2, 64, 96, 0, False)
+    args = (tgt.to(DEV), [t.to(DEV) for t in refs], K.to(DEV), Kinv.to(DEV), [d.to(DEV) for d in depth], masks, pose.to(DEV))
+    a, b = float(LF.photometric_reconstruction_loss(*args)), float(LF.photometric_reconstruction_loss(*args))
+    assert a == b
