@@ -119,6 +119,13 @@ static inline bool dn_vec8_ok(const dn_view* v) {
          (v->sH % 8) == 0 && (v->sW % 8) == 0;
 }
 
+// ... or with two float4 per 8 fp32 channels (precisions 'fp32' / 'tc32'): the generic channel-group walkers (ldc<8> / stc<8>)
+// serve both; the 16-bit-only fast paths keep testing dn_vec8_ok
+static inline bool dn_vec8_any(const dn_view* v) {
+  if (v->dtype != DN_F32) return dn_vec8_ok(v);
+  return (v->C % 8) == 0 && ((uintptr_t)v->ptr % 16) == 0 && (v->sN % 4) == 0 && (v->sH % 4) == 0 && (v->sW % 4) == 0;
+}
+
 __device__ __forceinline__ float dn_warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

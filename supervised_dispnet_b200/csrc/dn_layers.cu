@@ -627,7 +627,11 @@ template <int CH>
 __device__ __forceinline__ void ldc(const dn_view& v, long long off, float* f) {
   if (CH == 8) {
     if (v.dtype == DN_F16) Vec8<__half>::load((const __half*)v.ptr + off, f);
-    else Vec8<__nv_bfloat16>::load((const __nv_bfloat16*)v.ptr + off, f);
+    else if (v.dtype == DN_BF16) Vec8<__nv_bfloat16>::load((const __nv_bfloat16*)v.ptr + off, f);
+    else {
+      const float4 a = *reinterpret_cast<const float4*>((const float*)v.ptr + off), b = *reinterpret_cast<const float4*>((const float*)v.ptr + off + 4);
+      f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+    }
   } else {
     f[0] = dn_ld(v.ptr, v.dtype, off);
   }
@@ -636,7 +640,11 @@ template <int CH>
 __device__ __forceinline__ void stc(const dn_view& v, long long off, const float* f) {
   if (CH == 8) {
     if (v.dtype == DN_F16) Vec8<__half>::store((__half*)v.ptr + off, f);
-    else Vec8<__nv_bfloat16>::store((__nv_bfloat16*)v.ptr + off, f);
+    else if (v.dtype == DN_BF16) Vec8<__nv_bfloat16>::store((__nv_bfloat16*)v.ptr + off, f);
+    else {
+      *reinterpret_cast<float4*>((float*)v.ptr + off) = make_float4(f[0], f[1], f[2], f[3]);
+      *reinterpret_cast<float4*>((float*)v.ptr + off + 4) = make_float4(f[4], f[5], f[6], f[7]);
+    }
   } else {
     dn_st(v.ptr, v.dtype, off, f[0]);
   }
@@ -949,10 +957,10 @@ __device__ __forceinline__ void act_bwd_tail(float* acc, int C, float* __restric
 
 static int bn_stats_launch(const dn_view* y, double* sums, const BnFinalize& fz, float* ws, void* stream) {
   long long npix = (long long)y->N * y->H * y->W;
-  if (dn_vec8_ok(y)) {
+  if (dn_vec8_any(y)) {
     CgGeom g = cg_geom(y->C, 8, npix, 8, 4);
     if (g.grid.y > kWsCounters) return DN_E_UNSUPPORTED;
-    if (dn_lin(y) && npix < (1ll << 31) && g_bn_fast) dn_launch(bnf_stats_kernel, g.grid, dim3(256), 0, dn_stream(stream), *y, ws, g.CGb, sums, fz);
+    if (dn_vec8_ok(y) && dn_lin(y) && npix < (1ll << 31) && g_bn_fast) dn_launch(bnf_stats_kernel, g.grid, dim3(256), 0, dn_stream(stream), *y, ws, g.CGb, sums, fz);
     else bn_stats_kernel<8><<<g.grid, 256, 0, dn_stream(stream)>>>(*y, ws, g.CGb, sums, fz);
   } else {
     CgGeom g = cg_geom(y->C, 1, npix, 256, 3);
@@ -1094,8 +1102,9 @@ DN_EXPORT int dn_bn_apply(const dn_view* y, const float* scale_shift, const dn_v
   dn_view r = residual ? *residual : *y;
   dn_view o2 = out2 ? *out2 : *out;
   if (out2 && (out2->C != out->C || out2->H != out->H || out2->W != out->W || out2->N != out->N)) return DN_E_ARG;
-  bool vec = dn_vec8_ok(y) && dn_vec8_ok(out) && (!residual || dn_vec8_ok(residual)) && (!out2 || dn_vec8_ok(out2));
-  const bool fast = vec && g_bn_fast && (!residual || (!pool && dn_lin(residual))) && dn_lin(y) && dn_lin(out) && (!out2 || dn_lin(out2)) &&
+  bool vec = dn_vec8_any(y) && dn_vec8_any(out) && (!residual || dn_vec8_any(residual)) && (!out2 || dn_vec8_any(out2));
+  const bool all16 = dn_vec8_ok(y) && dn_vec8_ok(out) && (!residual || dn_vec8_ok(residual)) && (!out2 || dn_vec8_ok(out2));
+  const bool fast = vec && all16 && g_bn_fast && (!residual || (!pool && dn_lin(residual))) && dn_lin(y) && dn_lin(out) && (!out2 || dn_lin(out2)) &&
                     npix < (1ll << 31) && (!pool || (y->H == 2 * out->H && y->W >= 2 * out->W));
   if (fast) {
     CgGeom g = cg_geom(out->C, 8, npix, 256, 4);
@@ -1267,13 +1276,14 @@ DN_EXPORT int dn_bn_bwd_reduce(const dn_view* dout, const dn_view* y, const dn_v
   if (!dout || !y || !mean_invstd || !red || !ws) return DN_E_ARG;
   long long npix = (long long)dout->N * dout->H * dout->W;
   dn_view r = residual ? *residual : *y;
-  bool vec = dn_vec8_ok(y) && dn_vec8_ok(dout) && (!residual || dn_vec8_ok(residual));
+  bool vec = dn_vec8_any(y) && dn_vec8_any(dout) && (!residual || dn_vec8_any(residual));
+  const bool all16 = dn_vec8_ok(y) && dn_vec8_ok(dout) && (!residual || dn_vec8_ok(residual));
   cudaStream_t st = dn_stream(stream);
   const int ch = vec ? 8 : 1;
   CgGeom g = cg_geom(dout->C, ch, npix, vec ? 8 : 256, 3);
   if (g.grid.y > kWsCounters) return DN_E_UNSUPPORTED;
   const int hr = residual != nullptr;
-  const bool fast = vec && g_bn_fast && (!residual || (!pool && dn_lin(residual))) && dn_lin(dout) && dn_lin(y) && npix < (1ll << 31) &&
+  const bool fast = vec && all16 && g_bn_fast && (!residual || (!pool && dn_lin(residual))) && dn_lin(dout) && dn_lin(y) && npix < (1ll << 31) &&
                     (!pool || (y->H == 2 * dout->H && y->W >= 2 * dout->W));
   if (fast && pool) dn_launch(bnf_bwd_reduce_kernel<true, false>, g.grid, dim3(256), 0, st, *dout, *y, mean_invstd, gamma, beta, act, ws, g.CGb, red, r);
   else if (fast && residual) dn_launch(bnf_bwd_reduce_kernel<false, true>, g.grid, dim3(256), 0, st, *dout, *y, mean_invstd, gamma, beta, act, ws, g.CGb, red, r);
@@ -1379,7 +1389,8 @@ DN_EXPORT int dn_bn_bwd_apply(const dn_view* dout, const dn_view* y, const dn_vi
   long long npix = (long long)dout->N * dout->H * dout->W;
   dn_view r = residual ? *residual : *y;
   dn_view dr = dres ? *dres : *dy;
-  bool vec = dn_vec8_ok(y) && dn_vec8_ok(dout) && dn_vec8_ok(dy) && (!residual || dn_vec8_ok(residual)) && (!dres || dn_vec8_ok(dres));
+  bool vec = dn_vec8_any(y) && dn_vec8_any(dout) && dn_vec8_any(dy) && (!residual || dn_vec8_any(residual)) && (!dres || dn_vec8_any(dres));
+  const bool all16 = dn_vec8_ok(y) && dn_vec8_ok(dout) && dn_vec8_ok(dy) && (!residual || dn_vec8_ok(residual)) && (!dres || dn_vec8_ok(dres));
   cudaStream_t st = dn_stream(stream);
   const int ch = vec ? 8 : 1;
   CgGeom g = cg_geom(dout->C, ch, npix);
@@ -1388,7 +1399,7 @@ DN_EXPORT int dn_bn_bwd_apply(const dn_view* dout, const dn_view* y, const dn_vi
   bn_bwd_apply_kernel<CHV, PV><<<g.grid, 256, 0, st>>>(*dout, *y, r, hr, mean_invstd, gamma, beta, act, red, count, gscale, \
                                                        dgamma, dbeta, *dy, dr, hd, dres_accumulate, g.CGb)
   const bool res_ok = (!residual && !dres) || (residual && !pool && dn_lin(residual) && (!dres || dn_lin(dres)));
-  const bool fast = vec && g_bn_fast && res_ok && dn_lin(dout) && dn_lin(y) && dn_lin(dy) && npix < (1ll << 31) &&
+  const bool fast = vec && all16 && g_bn_fast && res_ok && dn_lin(dout) && dn_lin(y) && dn_lin(dy) && npix < (1ll << 31) &&
                     (!pool || (y->H == 2 * dout->H && y->W >= 2 * dout->W));
   if (fast) {
     CgGeom gf = cg_geom(dout->C, 8, npix, 256, 3);
@@ -1459,12 +1470,13 @@ DN_EXPORT int dn_act_bwd(const dn_view* dout, const dn_view* out, int act, float
   if (act == DN_ACT_NONE && !dbias) return 0;
   long long npix = (long long)dout->N * dout->H * dout->W;
   dn_view o = out ? *out : *dout;
-  bool vec = dn_vec8_ok(dout) && (!out || dn_vec8_ok(out));
+  bool vec = dn_vec8_any(dout) && (!out || dn_vec8_any(out));
+  const bool all16 = dn_vec8_ok(dout) && (!out || dn_vec8_ok(out));
   CgGeom g;
   if (vec) {
     g = cg_geom(dout->C, 8, npix, 8, 4);
     if (g.grid.y > kWsCounters) return DN_E_UNSUPPORTED;
-    if (g_bn_fast && dn_lin(dout) && (!out || dn_lin(out)) && npix < (1ll << 31))
+    if (all16 && g_bn_fast && dn_lin(dout) && (!out || dn_lin(out)) && npix < (1ll << 31))
       dn_launch(actf_bwd_kernel, g.grid, dim3(256), 0, dn_stream(stream), *dout, o, act, dbias ? ws : nullptr, g.CGb, dbias, gscale);
     else
       act_bwd_kernel<8><<<g.grid, 256, 0, dn_stream(stream)>>>(*dout, o, act, dbias ? ws : nullptr, g.CGb, dbias, gscale);
@@ -1694,7 +1706,7 @@ __global__ void __launch_bounds__(256) ew_fwd_kernel(dn_view a, dn_view b, int h
 
 static int ew_launch(const dn_view* a, const dn_view* b, int act, const dn_view* out, int accumulate, void* stream) {
   if (!a || !out || a->C != out->C || a->N != out->N || a->H != out->H || a->W != out->W) return DN_E_ARG;
-  bool vec = dn_vec8_ok(a) && dn_vec8_ok(out) && (!b || dn_vec8_ok(b));
+  bool vec = dn_vec8_any(a) && dn_vec8_any(out) && (!b || dn_vec8_any(b));
   dn_view bb = b ? *b : *a;
   if (vec) {
     long long total = (long long)out->N * out->H * out->W * (out->C / 8);
@@ -1820,7 +1832,7 @@ DN_EXPORT int dn_add_act_bwd(const dn_view* dout, const dn_view* out, int act, c
   if (!dout || (!out && act != DN_ACT_NONE)) return DN_E_ARG;
   dn_view o = out ? *out : *dout;
   dn_view a = da ? *da : *dout, b = db ? *db : *dout;
-  bool vec = dn_vec8_ok(dout) && (!out || dn_vec8_ok(out)) && (!da || dn_vec8_ok(da)) && (!db || dn_vec8_ok(db));
+  bool vec = dn_vec8_any(dout) && (!out || dn_vec8_any(out)) && (!da || dn_vec8_any(da)) && (!db || dn_vec8_any(db));
   if (vec) {
     long long total = (long long)dout->N * dout->H * dout->W * (dout->C / 8);
     add_act_bwd_kernel<8><<<ew_blocks(total), 256, 0, dn_stream(stream)>>>(*dout, o, act, a, da_acc, da != nullptr, b, db_acc, db != nullptr);
@@ -2276,7 +2288,7 @@ DN_EXPORT int dn_head_conv_fwd(const dn_view* x, const float* w, const float* bi
   const long long npix = (long long)x->N * ((x->H + 15) / 16) * ((x->W + 15) / 16) * 256;
   const size_t sm = sizeof(float) * 9 * x->C;
   int blocks = ew_blocks(npix);
-  if (dn_vec8_ok(x)) dn_launch(head_conv_fwd_kernel<8>, dim3(blocks), dim3(256), sm, dn_stream(stream), *x, w, bias, *z);
+  if (dn_vec8_any(x)) dn_launch(head_conv_fwd_kernel<8>, dim3(blocks), dim3(256), sm, dn_stream(stream), *x, w, bias, *z);
   else dn_launch(head_conv_fwd_kernel<1>, dim3(blocks), dim3(256), sm, dn_stream(stream), *x, w, bias, *z);
   DN_CHECK_LAUNCH();
   return 0;
@@ -2286,7 +2298,7 @@ DN_EXPORT int dn_head_conv_bwd(const dn_view* x, const float* w, const dn_view* 
                                float* gw, float* gb, float gscale, float* ws, void* stream) {
   if (!x || !w || !dz || !gx || !gw || !ws || gx->C != x->C) return DN_E_ARG;
   const long long npix = (long long)x->N * x->H * x->W;
-  const bool vec = dn_vec8_ok(x) && dn_vec8_ok(gx);
+  const bool vec = dn_vec8_any(x) && dn_vec8_any(gx);
   const int ch = vec ? 8 : 1;
   CgGeom g = cg_geom(x->C, ch, npix);
   if (g.grid.y != 1) return DN_E_UNSUPPORTED;

@@ -321,7 +321,7 @@ class ConvOp(Op):
         # first layer (input = the image, no data gradient): kernel columns folded into the channel dimension, k taps
         # over k * Cin channels of a row-expanded copy of the image instead of k * k taps over 3 real channels each
         self.rowx = (not transposed and not needs_dx and stride in (1, 2) and k > 1 and k * x.C <= 128 and tc_enabled()
-                     and plan.prec.act != torch.float32 and getattr(x.buf, 'is_input', False) and x.c0 == 0
+                     and (plan.prec.act != torch.float32 or plan.prec.split is not None) and getattr(x.buf, 'is_input', False) and x.c0 == 0
                      and x.C == x.buf.C and os.environ.get('DISPNET_B200_ROWX', '1') != '0')
         if getattr(x.buf, 'is_input', False) and not self.rowx:
             x.buf.shadow_needed = True          # this layer's weight gradient reads the gradient-dtype image of the input
@@ -332,7 +332,10 @@ class ConvOp(Op):
             if plan.training and plan.prec.grad != plan.prec.act:
                 self.xr_g = Buf(x.N, x.H, out.W, cx, plan.prec.grad, dev).view()
             self.cin_pad = _ru(cx, 64)
-            self.wp = torch.zeros((k, self.cout_pad, self.cin_pad), dtype=plan.prec.act, device=dev)
+            if plan.prec.split is not None:
+                self.wp = torch.zeros((2 * k, self.cout_pad, self.cin_pad), dtype=plan.prec.split, device=dev)     # [hi | lo]
+            else:
+                self.wp = torch.zeros((k, self.cout_pad, self.cin_pad), dtype=plan.prec.act, device=dev)
         elif plan.prec.split is not None:
             self.wp = torch.zeros((2 * T, self.cout_pad, self.cin_pad), dtype=plan.prec.split, device=dev)     # [hi | lo]
         else:
@@ -340,7 +343,7 @@ class ConvOp(Op):
         # split-precision operands: this op converts its input to (hi, lo) planes unless an earlier consumer already did
         self.split_x = None
         if plan.prec.split is not None:
-            xs = _full_extent(x)
+            xs = _full_extent(self.xr if self.rowx else x)
             self.split_x = xs if xs.claim_split(plan.prec.split) else False
         self.kh = _i32arr([t // k for t in range(T)])
         self.kw = _i32arr([t % k for t in range(T)])
@@ -395,7 +398,7 @@ class ConvOp(Op):
                 o2 = self.out_shadow.phase(*pr['phase']) if 'phase' in pr else self.out_shadow
             ins, taps, wdt, div = pr['ins'], pr['taps'], plan.prec.act, 1.0
             if plan.prec.split is not None:
-                ins, taps = _split3_igemm(ins, taps, self.k * self.k, plan.prec.split)
+                ins, taps = _split3_igemm(ins, taps, self.k if self.rowx else self.k * self.k, plan.prec.split)
                 wdt, div = plan.prec.split, 3.0
             p = _mk_igemm(ins, pr['out'], self.wp, wdt, self.cin_pad, self.cout_pad, None, self.act, False,
                           pr['stride'], taps, out2=o2)
@@ -456,9 +459,14 @@ class ConvOp(Op):
         if self.rowx:
             L.call('dn_rowx_expand', self.x.ref(), self.k, self.stride, self.pad, self.xr.ref(),
                    self.xr_g.ref() if self.xr_g is not None else None, plan.stream)
-            L.call('dn_rowx_pack_weight', L.ptr(plan.param(self.name + '.weight')), self.Cout, self.Cin, self.k, L.ptr(self.wp),
-                   _DT[plan.prec.act], self.cout_pad, self.cin_pad, L.ptr(self.fold_ss) if self.fold_bn is not None else None,
-                   plan.stream)
+            rs = L.ptr(self.fold_ss) if self.fold_bn is not None else None
+            if plan.prec.split is not None:         # hi matrices, then the residual matrices
+                for half, code in ((0, L.DN_BF16), (1, L.DN_BF16_LO)):
+                    L.call('dn_rowx_pack_weight', L.ptr(plan.param(self.name + '.weight')), self.Cout, self.Cin, self.k,
+                           L.ptr(self.wp[half * self.k:]), code, self.cout_pad, self.cin_pad, rs, plan.stream)
+            else:
+                L.call('dn_rowx_pack_weight', L.ptr(plan.param(self.name + '.weight')), self.Cout, self.Cin, self.k, L.ptr(self.wp),
+                       _DT[plan.prec.act], self.cout_pad, self.cin_pad, rs, plan.stream)
         if self.split_x:
             hi, lo = self.split_x.planes(plan.prec.split)
             L.call('dn_split_bf16', self.split_x.ref(), hi.ref(), lo.ref(), plan.stream)
@@ -467,7 +475,7 @@ class ConvOp(Op):
             b = self.fold_bias
         for p, be, fl in self._fwd_built:
             p.bias = b.data_ptr() if b is not None else None
-            L.call('dn_igemm_run', C.byref(p), be, plan.stream, tag=('fwd', be, fl, self.name))
+        plan.run_group([(p, be, ('fwd', be, fl, self.name)) for p, be, fl in self._fwd_built])
 
     def plan_bwd(self, plan):
         g = plan.prec.grad
@@ -517,7 +525,7 @@ class ConvOp(Op):
             # (the weight-gradient kernel accumulates with red.global.add); x's planes are the ones the forward made
             self.gsplit = _full_extent(self.gout)
             gh, gl = self.gout.planes(sp)
-            xh, xl = self.x.planes(sp)
+            xh, xl = (self.xr if self.rowx else self.x).planes(sp)
             self.wg = wg_probs(xh, gh, 3.0) + wg_probs(xh, gl, 3.0) + wg_probs(xl, gh, 3.0)
         else:
             self.wg = wg_probs(self.xr_g if (self.rowx and self.xr_g is not None) else (self.xr if self.rowx else self.x))
@@ -610,8 +618,7 @@ class ConvOp(Op):
                     v.buf.t.zero_()
                 else:       # a channel slice of a shared (concat) gradient buffer: clear the slice only
                     v.buf.t[..., v.c0:v.c0 + v.C].zero_()
-            for p, be, fl in self.dg:
-                L.call('dn_igemm_run', C.byref(p), be, plan.stream, tag=('dgrad', be, fl, self.name))
+            plan.run_group([(p, be, ('dgrad', be, fl, self.name)) for p, be, fl in self.dg])
 
 
     def _rowx_unpack(self, plan, st):
@@ -629,8 +636,8 @@ def conv_bn(plan, conv_name, bn_name, x, y_shape, out, k, act=L.ACT_RELU, pool=F
     fold = (not plan.training) and os.environ.get('DISPNET_B200_FOLD_BN', '1') != '0'
     if not fold:
         y = plan.new_buf(N, H, W, Cc).view()
-        plan.add(ConvOp(plan, conv_name, x, y, k, stride=stride, pad=pad, bias=bias, needs_dx=needs_dx, bn_follows=True))
-        plan.add(BNOp(plan, bn_name, y, out, act, pool=pool))
+        conv = plan.add(ConvOp(plan, conv_name, x, y, k, stride=stride, pad=pad, bias=bias, needs_dx=needs_dx, bn_follows=True))
+        plan.add(BNOp(plan, bn_name, y, out, act, pool=pool, conv=conv))
         return
     if pool:
         y = plan.new_buf(N, H, W, Cc).view()
@@ -669,8 +676,9 @@ class BNOp(Op):
     """nn.BatchNorm2d (+ residual add) + activation (+ MaxPool2d(2,2)).  `out=None`: statistics only (the dead bn1
     of Disp_res_50, models/Disp_res_50.py:143-145, whose running buffers still update)."""
 
-    def __init__(self, plan, name, y, out, act=L.ACT_RELU, pool=False, residual=None):
+    def __init__(self, plan, name, y, out, act=L.ACT_RELU, pool=False, residual=None, conv=None):
         self.name, self.y, self.out, self.act, self.pool, self.res = name, y, out, act, int(pool), residual
+        self.conv = conv          # the ConvOp that produced y
         self.out2 = plan.shadow_of(out) if (out is not None and plan.training) else None
         Cc = y.C
         dev = plan.device
@@ -941,6 +949,35 @@ class Plan:
         if self._side is None:
             self._side = torch.cuda.Stream(device=self.device)
         return self._side
+
+    def run_group(self, items):
+        """Gather-convolutions that are independent of each other (the four output phases of a transposed convolution, the four
+        input phases of a stride-2 data gradient).  Small ones (fewer tiles than SMs each) are launched on separate streams so
+        that they share the GPU instead of running one under-filled persistent grid after the other; inside a CUDA-graph
+        capture the fork / join becomes parallel branches of the graph."""
+        small = len(items) > 1 and all(it[0].out.N * it[0].out.H * it[0].out.W <= 128 * 160 for it in items)
+        if not small or L.PROFILE is not None or os.environ.get('DISPNET_B200_PHASE_STREAMS', '1') == '0':
+            for p, be, tag in items:
+                L.call('dn_igemm_run', C.byref(p), be, self.stream, tag=tag)
+            return
+        if getattr(self, '_phase_streams', None) is None:
+            self._phase_streams = [torch.cuda.Stream(device=self.device) for _ in range(3)]
+        main = torch.cuda.current_stream()
+        fork = torch.cuda.Event()
+        fork.record(main)
+        joins = []
+        for i, (p, be, tag) in enumerate(items):
+            if i == 0:
+                L.call('dn_igemm_run', C.byref(p), be, self.stream, tag=tag)
+                continue
+            st = self._phase_streams[(i - 1) % 3]
+            st.wait_event(fork)
+            L.call('dn_igemm_run', C.byref(p), be, C.c_void_p(st.cuda_stream), tag=tag)
+            ev = torch.cuda.Event()
+            ev.record(st)
+            joins.append(ev)
+        for ev in joins:
+            main.wait_event(ev)
 
     def dwp_alloc(self, numel):
         numel = _ru(numel, 64)

@@ -126,7 +126,7 @@ class Disp_res_50(E.PlannedModule):
                 a2 = nb(N, ho, wo, pl).view()
                 E.conv_bn(plan, p + 'conv2', p + 'bn2', a1, (N, ho, wo, pl), a2, 3, ACT_RELU, stride=s, pad=1, bias=False)
                 yc = nb(N, ho, wo, pl * 4).view()
-                plan.add(E.ConvOp(plan, p + 'conv3', a2, yc, 1, pad=0, bias=False))
+                conv3 = plan.add(E.ConvOp(plan, p + 'conv3', a2, yc, 1, pad=0, bias=False, bn_follows=True))
                 if b == 0:
                     idn = nb(N, ho, wo, pl * 4).view()
                     E.conv_bn(plan, p + 'downsample.0', p + 'downsample.1', x, (N, ho, wo, pl * 4), idn, 1, ACT_NONE, stride=s,
@@ -135,7 +135,7 @@ class Disp_res_50(E.PlannedModule):
                     idn = x
                 last = b == nblk - 1
                 out = layer_dst[li] if (last and layer_dst[li] is not None) else nb(N, ho, wo, pl * 4).view()
-                plan.add(E.BNOp(plan, p + 'bn3', yc, out, ACT_RELU, residual=idn))
+                plan.add(E.BNOp(plan, p + 'bn3', yc, out, ACT_RELU, residual=idn, conv=conv3))
                 x = out
                 h, w = ho, wo
         c5 = x
