@@ -1310,14 +1310,22 @@ int dn_wgrad_tc(const dn_wgrad* p, cudaStream_t st) {
   if (by_smem < 1) by_smem = 1;
   if (!halo && tpc > by_smem) tpc = by_smem;
   if (tpc > P.ntaps) tpc = P.ntaps;
-  // all taps of a group must read the same dy view
-  for (int t = 1; t < P.ntaps; ++t)
-    if (p->taps[t].src != p->taps[0].src) { tpc = 1; break; }
   // wide tiles: prefer two accumulator stages (<= 256 columns per stage) over sharing the dy tile between more taps
   if (P.n_mma >= 128 && tpc * P.n_mma > 256) tpc = 256 / P.n_mma;
-  P.ngroups = (P.ntaps + tpc - 1) / tpc;
-  P.tpc = (P.ntaps + P.ngroups - 1) / P.ngroups;
-  P.ngroups = (P.ntaps + P.tpc - 1) / P.tpc;
+  // all taps of a group (consecutive taps [g * tpc, (g + 1) * tpc)) must read the same dy view: the four output phases of a
+  // transposed convolution arrive as one problem with the taps ordered phase by phase
+  auto uniform = [&](int n) {
+    for (int t = 0; t < P.ntaps; ++t)
+      if (p->taps[t].src != p->taps[(t / n) * n].src) return false;
+    return true;
+  };
+  for (;;) {
+    P.ngroups = (P.ntaps + tpc - 1) / tpc;
+    P.tpc = (P.ntaps + P.ngroups - 1) / P.ngroups;
+    P.ngroups = (P.ntaps + P.tpc - 1) / P.tpc;
+    if (P.tpc == 1 || uniform(P.tpc)) break;
+    tpc = P.tpc - 1;
+  }
   int cols = P.tpc * P.n_mma;
   P.nacc = cols <= 256 ? 2 : 1;
   if (const char* e = getenv("DN_WGRAD_NACC")) { if (atoi(e) == 1) P.nacc = 1; }

@@ -511,11 +511,17 @@ class ConvOp(Op):
             elif not self.transposed:
                 taps = [(0, kh - pad, kw - pad, kh * k + kw) for kh in range(k) for kw in range(k)]
                 probs.append(_mk_wgrad([gout], q, self.dwp, self.cout_pad, self.cin_pad, self.stride, taps, 1.0))
-            else:
+            else:       # transposed: the output phases are the dy sources of ONE problem, taps ordered phase by phase
+                srcs, taps = [], []
                 for pr in self.fwd_probs:
                     a, b = pr['phase']
-                    probs.append(_mk_wgrad([gout.phase(a, b)], q, self.dwp, self.cout_pad, self.cin_pad, 1, pr['taps'],
-                                           1.0))
+                    srcs.append(gout.phase(a, b))
+                    taps += [(len(srcs) - 1, dh, dw, wt) for (_, dh, dw, wt) in pr['taps']]
+                if len({(v.H, v.W) for v in srcs}) == 1 and len(taps) <= L.MAX_TAPS:
+                    probs.append(_mk_wgrad(srcs, q, self.dwp, self.cout_pad, self.cin_pad, 1, taps, 1.0))
+                else:   # (odd output sizes: the phases differ in extent)
+                    for v, pr in zip(srcs, self.fwd_probs):
+                        probs.append(_mk_wgrad([v], q, self.dwp, self.cout_pad, self.cin_pad, 1, pr['taps'], 1.0))
             return [(p, _backend('wgrad', p), _wgrad_flops(p) / div) for p in probs]
 
         self.xq = None
