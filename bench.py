@@ -404,7 +404,7 @@ def run_ours(args):
         step(x_d, gt_d)
     # (N > 1: the first all-reduces of a fresh NCCL communicator still set up channels / NVLS buffers; with a short timed region
     # -- the driver's scaling run times ~20 steps = 0.17 s -- that start-up would be measured instead of the steady state)
-    n_warm = max(args.warmup, 3) if world == 1 else max(args.warmup, 20)
+    n_warm = max(args.warmup, 3) if world == 1 else max(args.warmup, 20 if world < 4 else 60)
     for _ in range(n_warm):
         step(x_d, gt_d)
     barrier()
