@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libdispnet_b200.so')
+LIB_PATH = os.environ.get('DISPNET_B200_LIB') or os.path.join(_HERE, 'libdispnet_b200.so')      # (override: A/B runs of two builds)
 
 DN_F32, DN_F16, DN_BF16, DN_BF16_LO = 0, 1, 2, 3
 ACT_NONE, ACT_RELU, ACT_LRELU = 0, 1, 2

@@ -47,6 +47,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
+// polling wait with a back-off: for roles that are not on the critical path (their polling must not take issue slots from the
+// MMA-issuing warp that shares their scheduler)
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  for (;;) {
+    asm volatile(
+        "{\n.reg .pred P1;\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\nselp.u32 %0, 1, 0, P1;\n}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (ok) break;
+    __nanosleep(200);
+  }
+}
 // one lane of a fully converged warp; keeps the surrounding control flow warp-uniform so that descriptors and barrier
 // addresses stay in uniform registers (issuing tcgen05 / TMA from inside `if (lane == 0)` makes the compiler wrap every
 // instruction in an elect/broadcast loop)
@@ -76,12 +90,74 @@ __device__ __forceinline__ void tma_load_4d(void* smem, const CUtensorMap* m, ui
       "l"((uint64_t)m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_5d(void* smem, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(
+          smem_u32(smem)),
+      "l"((uint64_t)m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
 __device__ __forceinline__ void tma_load_3d(void* smem, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
           smem_u32(smem)),
       "l"((uint64_t)m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
+}
+
+// ---- "one lane issues" forms ------------------------------------------------------------------------------------------
+// tcgen05.mma / tcgen05.commit / TMA loads are issued by ONE lane.  Wrapping them in `if (elect_one()) { ... }` makes the
+// branch divergent for the compiler: every stage then pays BRA.DIV / BSYNC scaffolding and moves its operands between the
+// vector and the uniform register files (~100 SASS instructions per pipeline stage, more than the ~300 tensor-pipe cycles of
+// a 4-MMA N=128 stage can hide).  With the election INSIDE the asm block the surrounding code stays warp-uniform: ptxas keeps
+// descriptors and barrier addresses in uniform registers and emits a bare UTCHMMA / UTCBAR / UTMALDG.
+__device__ __forceinline__ void mbar_expect_tx_e(uint64_t* bar, uint32_t bytes) {
+  asm volatile("{\n.reg .pred E;\nelect.sync _|E, 0xffffffff;\n@E mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n}\n" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_e(void* smem, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "{\n.reg .pred E;\nelect.sync _|E, 0xffffffff;\n"
+      "@E cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n}\n" ::"r"(
+          smem_u32(smem)),
+      "l"((uint64_t)m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_e(void* smem, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "{\n.reg .pred E;\nelect.sync _|E, 0xffffffff;\n"
+      "@E cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n}\n" ::"r"(
+          smem_u32(smem)),
+      "l"((uint64_t)m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void umma_e(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, E;\n"
+      "elect.sync _|E, 0xffffffff;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "@E tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_acc_e(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, E;\n"
+      "elect.sync _|E, 0xffffffff;\n"
+      "setp.eq.u32 p, 1, 1;\n"
+      "@E tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_e(uint64_t* bar) {
+  asm volatile("{\n.reg .pred E;\nelect.sync _|E, 0xffffffff;\n@E tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n}\n" ::"r"(
+                   smem_u32(bar))
+               : "memory");
 }
 
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
@@ -102,6 +178,17 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
       "}\n" ::"r"(d_tmem),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// accumulate form (enable-input-d is the constant true predicate: no runtime set-predicate instruction)
+__device__ __forceinline__ void umma_f16_acc(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.eq.u32 p, 1, 1;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc)
       : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -128,6 +215,18 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+template <int NV>
+__device__ __forceinline__ void tmem_ldn(uint32_t taddr, uint32_t* r) {
+  if (NV == 8) tmem_ld8(taddr, r);
+  else if (NV == 16) tmem_ld16(taddr, r);
+  else tmem_ld32(taddr, r);
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
@@ -136,13 +235,14 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 
 // shared-memory matrix descriptor, 128B swizzle (cute::UMMA::SmemDescriptor): start>>4 | LBO>>4 <<16 | SBO>>4 <<32 | version 1
 // <<46 | layout SWIZZLE_128B (2) << 61
-__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// layout: 2 = SWIZZLE_128B (64 16-bit channels per row), 4 = SWIZZLE_64B (32 channels), 6 = SWIZZLE_32B (16 channels)
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout = 2) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)layout << 61;
   return d;
 }
 
@@ -159,9 +259,139 @@ __device__ __forceinline__ void store_out2(void* base, int dtype, size_t elem_of
   }
 }
 
+// The MMAs of one (tile, chunk): 9 shifted views x KS K-steps plus the commit(s), as ONE asm block.  The issuing warp's
+// instruction stream paces thin layers (an M=128, N<=32 MMA takes ~50 cycles on the tensor pipe -- tools/ubench_tc.cu), so
+// the block is branch-free: the election happens once, every operand offset is a PTX constant expression of the template
+// constants, absent taps (tap subsets of transposed-convolution phases / row-expanded first layers) are predicated off.
+// operands: %0 d_tmem, %1 A descriptor of the stage, %2 B descriptor of the chunk, %3 idesc, %4 accumulate flag of the first
+// MMA, %5 empty barrier, %6 tap mask, %7 A row bytes, %8 B tile bytes, %9 tmem-full barrier, %10 "last chunk" flag
+#define DN_HTAP_HEAD(KH, KW, T)                                   \
+  "and.b32 m, %6, (1 << " #T ");\n"                               \
+  "setp.ne.u32 Tp, m, 0;\n"                                       \
+  "and.pred Q, Tp, E;\n"                                          \
+  "add.u64 a, %1, ((" #KH " * 16 + " #KW ") * %7) / 16;\n"        \
+  "add.u64 b, %2, (" #T " * %8) / 16;\n"                          \
+  "@Q tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %3, A;\n"    \
+  "or.pred A, A, Tp;\n"
+#define DN_HTAP_STEP                                              \
+  "add.u64 a, a, 2;\n"                                            \
+  "add.u64 b, b, 2;\n"                                            \
+  "@Q tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %3, TR;\n"
+#define DN_HTAP1(KH, KW, T) DN_HTAP_HEAD(KH, KW, T)
+#define DN_HTAP2(KH, KW, T) DN_HTAP_HEAD(KH, KW, T) DN_HTAP_STEP
+#define DN_HTAP3(KH, KW, T) DN_HTAP_HEAD(KH, KW, T) DN_HTAP_STEP DN_HTAP_STEP
+#define DN_HTAP4(KH, KW, T) DN_HTAP_HEAD(KH, KW, T) DN_HTAP_STEP DN_HTAP_STEP DN_HTAP_STEP
+#define DN_HALO_BLOCK(TAP)                                                                                                   \
+  asm volatile(                                                                                                              \
+      "{\n.reg .pred E, A, TR, Tp, Q, L;\n.reg .b64 a, b;\n.reg .b32 m;\n"                                                   \
+      "elect.sync _|E, 0xffffffff;\n"                                                                                        \
+      "setp.ne.u32 A, %4, 0;\nsetp.eq.u32 TR, 1, 1;\n"                                                                       \
+      TAP(0, 0, 0) TAP(0, 1, 1) TAP(0, 2, 2) TAP(1, 0, 3) TAP(1, 1, 4) TAP(1, 2, 5) TAP(2, 0, 6) TAP(2, 1, 7) TAP(2, 2, 8)   \
+      "@E tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%5];\n"                                     \
+      "setp.ne.u32 L, %10, 0;\nand.pred L, L, E;\n"                                                                          \
+      "@L tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%9];\n"                                     \
+      "}\n" ::"r"(d_tmem), "l"(ad), "l"(bd), "r"(idesc), "r"(acc0), "r"(empty_bar), "r"(mask), "n"(A_RB), "n"(B_BYTES),      \
+      "r"(tfull_bar), "r"(last)                                                                                              \
+      : "memory")
+template <int KS, int A_RB, int B_BYTES>
+__device__ __forceinline__ void halo_issue(uint32_t d_tmem, uint64_t ad, uint64_t bd, uint32_t idesc, uint32_t mask, uint32_t acc0,
+                                           uint32_t empty_bar, uint32_t tfull_bar, uint32_t last) {
+  if (KS == 1) DN_HALO_BLOCK(DN_HTAP1);
+  else if (KS == 2) DN_HALO_BLOCK(DN_HTAP2);
+  else if (KS == 3) DN_HALO_BLOCK(DN_HTAP3);
+  else DN_HALO_BLOCK(DN_HTAP4);
+}
+
+// One pipeline stage of the plain kernel: KS MMAs on the stage's A / B tiles, release of the stage, optional "accumulator
+// complete" commit.  %0 d_tmem, %1 / %2 descriptors, %3 idesc, %4 accumulate flag of the first MMA, %5 empty barrier,
+// %6 tmem-full barrier, %7 "last stage of the tile" flag
+#define DN_STEP2 "add.u64 a, a, 2;\nadd.u64 b, b, 2;\n@E tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %3, TR;\n"
+#define DN_STAGE_BLOCK(STEPS)                                                                                       \
+  asm volatile(                                                                                                     \
+      "{\n.reg .pred E, A, TR, L;\n.reg .b64 a, b;\n"                                                               \
+      "elect.sync _|E, 0xffffffff;\n"                                                                               \
+      "setp.ne.u32 A, %4, 0;\nsetp.eq.u32 TR, 1, 1;\n"                                                              \
+      "mov.b64 a, %1;\nmov.b64 b, %2;\n"                                                                            \
+      "@E tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %3, A;\n" STEPS                                            \
+      "@E tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%5];\n"                            \
+      "setp.ne.u32 L, %7, 0;\nand.pred L, L, E;\n"                                                                  \
+      "@L tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%6];\n"                            \
+      "}\n" ::"r"(d_tmem), "l"(ad), "l"(bd), "r"(idesc), "r"(acc0), "r"(empty_bar), "r"(tfull_bar), "r"(last)       \
+      : "memory")
+__device__ __forceinline__ void stage_issue(int ks, uint32_t d_tmem, uint64_t ad, uint64_t bd, uint32_t idesc, uint32_t acc0, uint32_t empty_bar,
+                                            uint32_t tfull_bar, uint32_t last) {
+  if (ks == 4) DN_STAGE_BLOCK(DN_STEP2 DN_STEP2 DN_STEP2);
+  else if (ks == 1) DN_STAGE_BLOCK("");
+  else if (ks == 2) DN_STAGE_BLOCK(DN_STEP2);
+  else DN_STAGE_BLOCK(DN_STEP2 DN_STEP2);
+}
+
+// Four K steps (64 pixels) of one tap of the weight gradient: A advances by `ka`, B by `kb` 16-byte units per step
+__device__ __forceinline__ void wg_issue4(uint32_t d_tmem, uint64_t ad, uint64_t bd, uint32_t idesc, uint32_t acc0, uint32_t kb) {
+  asm volatile(
+      "{\n.reg .pred E, A, TR;\n.reg .b64 a, b, kb;\n"
+      "elect.sync _|E, 0xffffffff;\n"
+      "setp.ne.u32 A, %4, 0;\nsetp.eq.u32 TR, 1, 1;\n"
+      "mov.b64 a, %1;\nmov.b64 b, %2;\ncvt.u64.u32 kb, %5;\n"
+      "@E tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %3, A;\n"
+      "add.u64 a, a, 128;\nadd.u64 b, b, kb;\n@E tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %3, TR;\n"
+      "add.u64 a, a, 128;\nadd.u64 b, b, kb;\n@E tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %3, TR;\n"
+      "add.u64 a, a, 128;\nadd.u64 b, b, kb;\n@E tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %3, TR;\n"
+      "}\n" ::"r"(d_tmem), "l"(ad), "l"(bd), "r"(idesc), "r"(acc0), "r"(kb)
+      : "memory");
+}
+
+// one epilogue chunk: NV (8 / 16 / 32) accumulator columns of one pixel -> bias / activation -> one 16-byte store per 8 channels
+template <int NV>
+__device__ __forceinline__ void epi_store(const uint32_t* r, const float* bs, float out_scale, int act, bool valid, int c_base, int c_eff, int out_C,
+                                          int out_dtype, uint8_t* optr_c, int accumulate, void* out2, int out2_dtype, size_t elem_off) {
+  if (!valid) return;
+#pragma unroll
+  for (int g = 0; g < NV / 8; ++g) {
+    const int c0 = c_base + 8 * g;
+    if (c0 >= c_eff) break;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = dn_act(__uint_as_float(r[8 * g + j]) * out_scale + bs[8 * g + j], act);
+    if (out2) {
+      if (out2_dtype == DN_F16) Vec8<__half>::store((__half*)out2 + elem_off + 8 * g, v);
+      else Vec8<__nv_bfloat16>::store((__nv_bfloat16*)out2 + elem_off + 8 * g, v);
+    }
+    if (out_dtype == DN_F32) {
+      float* o = (float*)optr_c + 8 * g;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (c0 + j < out_C) o[j] = accumulate ? o[j] + v[j] : v[j];
+    } else if (out_dtype == DN_F16) {
+      __half* o = (__half*)optr_c + 8 * g;
+      if (accumulate) {
+        float a[8];
+        Vec8<__half>::load(o, a);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] += a[j];
+      }
+      Vec8<__half>::store(o, v);
+    } else {
+      __nv_bfloat16* o = (__nv_bfloat16*)optr_c + 8 * g;
+      if (accumulate) {
+        float a[8];
+        Vec8<__nv_bfloat16>::load(o, a);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] += a[j];
+      }
+      Vec8<__nv_bfloat16>::store(o, v);
+    }
+  }
+}
+
 constexpr int kMaxTcTaps = DN_MAX_TAPS;
 constexpr int kRows = 128;          // pixels per tile = UMMA M
 constexpr int kChunk = 64;          // channels per K chunk = one 128-byte swizzled row
+// Thin tensors (C <= 32) are fetched as 32- or 16-channel rows instead (SWIZZLE_64B / SWIZZLE_32B boxes): a 64-channel box
+// over a 17-channel tensor makes every box row partially out of bounds, and TMA fills such rows at ~7 cycles each
+// (tools/ubench_tc.cu: 1 940 cycles per 18x16-pixel halo box against 750-850 for the same box with 32-channel rows).
+__host__ __device__ __forceinline__ int thin_layout(int cb) { return cb == 64 ? 2 : cb == 32 ? 4 : 6; }
+static inline int thin_cb(int C) { return C <= 16 ? 16 : C <= 32 ? 32 : 64; }
 
 struct TcTap { int16_t src, dh, dw, wt; };
 
@@ -170,8 +400,9 @@ struct IgemmTcParams {
   CUtensorMap tmB;
   TcTap taps[kMaxTcTaps];
   int ntaps, nsrc;
-  int kchunks;        // ceil(Cin / 64)
+  int kchunks;        // ceil(Cin / cb)
   int last_ksteps;    // UMMA_K steps in the last chunk (1..4)
+  int cb;             // channels per A row in shared memory: 64 (128-byte rows), 32 or 16 (thin tensors, one chunk)
   int wb, hb, nb;     // pixel box (wb*hb*nb == 128)
   int tilesW, tilesH, tilesN, ntile_n, num_tiles;
   int stages;
@@ -188,13 +419,17 @@ struct IgemmTcParams {
 };
 
 template <int BN>
-__global__ void __launch_bounds__(192, 1) igemm_tc_kernel(const __grid_constant__ IgemmTcParams p) {
+__global__ void __launch_bounds__(320, 1) igemm_tc_kernel(const __grid_constant__ IgemmTcParams p) {
   dn_pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  constexpr uint32_t A_BYTES = kRows * 128;
+  const uint32_t A_BYTES = (uint32_t)(kRows * 2 * p.cb);
   constexpr uint32_t B_BYTES = BN * 128;
-  constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  const uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  const uint32_t a_layout = (uint32_t)thin_layout(p.cb), a_sbo = (uint32_t)(16 * p.cb);     // 8 rows of 2 * cb bytes
   constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+  constexpr int EW = 8;                               // epilogue warps: two per TMEM lane quarter, half of the columns each
+  constexpr int CPT = BN / 2 < 8 ? 8 : BN / 2;        // accumulator columns per epilogue thread
+  constexpr int CH = CPT < 32 ? CPT : 32;
   // carve: [stages x (A|B)] | barriers | tmem ptr | bias tile
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int stages = p.stages;
@@ -205,14 +440,14 @@ __global__ void __launch_bounds__(192, 1) igemm_tc_kernel(const __grid_constant_
   uint32_t* tmem_ptr = (uint32_t*)(tempty_bar + 2);
   float* bias_s = (float*)(tmem_ptr + 2);   // [2][BN]
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);      // (tells the compiler the role branches are warp-uniform)
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.nsrc; ++s) tma_prefetch_desc(&p.tmA[s]);
     tma_prefetch_desc(&p.tmB);
     for (int s = 0; s < stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 128); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], EW); }     // one arrival per epilogue warp
     fence_barrier_init();
     fence_proxy_async();
   }
@@ -225,8 +460,6 @@ __global__ void __launch_bounds__(192, 1) igemm_tc_kernel(const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   dn_pdl_wait();      // set-up above overlaps the previous kernel's tail; global memory only from here on
-
-  const int k_iters = p.ntaps * p.kchunks;
 
   if (warp == 0) {
     // ================= TMA producer (whole warp runs the loop, one elected lane issues) =================
@@ -250,8 +483,8 @@ __global__ void __launch_bounds__(192, 1) igemm_tc_kernel(const __grid_constant_
             uint8_t* sa = smem + (size_t)stage * STAGE_BYTES;
             uint8_t* sb = sa + A_BYTES;
             mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
-            tma_load_4d(sa, &p.tmA[tap.src], &full_bar[stage], kc * kChunk, w0 + tap.dw, h0 + tap.dh, n0);
-            tma_load_3d(sb, &p.tmB, &full_bar[stage], kc * kChunk, nt * BN, tap.wt);
+            tma_load_4d(sa, &p.tmA[tap.src], &full_bar[stage], kc * p.cb, w0 + tap.dw, h0 + tap.dh, n0);
+            tma_load_3d(sb, &p.tmB, &full_bar[stage], kc * p.cb, nt * BN, tap.wt);
           }
           __syncwarp();
           if (++stage == stages) { stage = 0; phase ^= 1; }
@@ -264,8 +497,16 @@ __global__ void __launch_bounds__(192, 1) igemm_tc_kernel(const __grid_constant_
     }
   } else if (warp == 1) {
     // ================= MMA issuer (whole warp waits on the barriers, one elected lane issues) =================
+    // The issuing thread's instruction stream paces N <= 128 tiles (a 128 x 128 x 16 MMA occupies the tensor pipe for ~70
+    // cycles): the descriptors are running values advanced by one add per stage, the K steps are unrolled per count.
     int stage = 0; uint32_t phase = 0;
     int acc = 0; uint32_t acc_phase = 0;
+    const uint64_t ad_base = make_desc(smem_u32(smem), 16, a_sbo, a_layout);
+    const uint64_t bd_base = make_desc(smem_u32(smem) + A_BYTES, 16, 1024);
+    const uint64_t stage_inc = (uint64_t)(STAGE_BYTES >> 4);
+    uint64_t ad = ad_base, bd = bd_base;
+    const uint32_t idesc = p.idesc;
+    const int kchunks = p.kchunks, last_ks = p.last_ksteps, full_ks = p.cb / 16, k_iters_m1 = p.ntaps * p.kchunks - 1;
     long long dbg_full = 0, dbg_te = 0;
     const long long tstart = p.dbg ? clock64() : 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -274,32 +515,18 @@ __global__ void __launch_bounds__(192, 1) igemm_tc_kernel(const __grid_constant_
       if (p.dbg) dbg_te += clock64() - t0;
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-      uint32_t first = 1;
-      for (int t = 0; t < p.ntaps; ++t) {
-        for (int kc = 0; kc < p.kchunks; ++kc) {
-          t0 = p.dbg ? clock64() : 0;
-          mbar_wait(&full_bar[stage], phase);
-          if (p.dbg) dbg_full += clock64() - t0;
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + (size_t)stage * STAGE_BYTES);
-          const uint64_t ad0 = make_desc(sa, 16, 1024);
-          const uint64_t bd0 = make_desc(sa + A_BYTES, 16, 1024);
-          const int ks = (kc == p.kchunks - 1) ? p.last_ksteps : 4;
-          if (elect_one()) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              if (k < ks) {
-                // advance 16 K-elements = 32 bytes inside the 128-byte swizzled row: +2 in the (addr >> 4) field
-                umma_f16(d_tmem, ad0 + (uint64_t)(2 * k), bd0 + (uint64_t)(2 * k), p.idesc, (first && k == 0) ? 0u : 1u);
-              }
-            }
-            umma_commit(&empty_bar[stage]);
-            if (t == p.ntaps - 1 && kc == p.kchunks - 1) umma_commit(&tfull_bar[acc]);
-          }
-          __syncwarp();
-          first = 0;
-          if (++stage == stages) { stage = 0; phase ^= 1; }
-        }
+      int kc = 0;
+      for (int it = 0; it <= k_iters_m1; ++it) {
+        t0 = p.dbg ? clock64() : 0;
+        mbar_wait(&full_bar[stage], phase);
+        if (p.dbg) dbg_full += clock64() - t0;
+        tc_fence_after();
+        const int ks = (kc == kchunks - 1) ? last_ks : full_ks;
+        stage_issue(ks, d_tmem, ad, bd, idesc, it == 0 ? 0u : 1u, smem_u32(&empty_bar[stage]), smem_u32(&tfull_bar[acc]),
+                    it == k_iters_m1 ? 1u : 0u);
+        if (++kc == kchunks) kc = 0;
+        ad += stage_inc; bd += stage_inc;
+        if (++stage == stages) { stage = 0; phase ^= 1; ad = ad_base; bd = bd_base; }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
@@ -308,15 +535,20 @@ __global__ void __launch_bounds__(192, 1) igemm_tc_kernel(const __grid_constant_
       atomicAdd(p.dbg + 4, (unsigned long long)(clock64() - tstart));
     }
   } else {
-    // ================= epilogue warps (2..5): TMEM -> registers -> bias/act -> HBM =================
+    // ================= epilogue warps (2..9): TMEM -> registers -> bias/act -> HBM =================
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;          // tile row = TMEM lane = pixel within the box
-    const int et = threadIdx.x - 64;        // 0..127
+    const int et = threadIdx.x - 64;        // 0..255
+    const int cbeg = (warp >= 6 ? 1 : 0) * CPT;
     int acc = 0; uint32_t acc_phase = 0;
     const int wi = row % p.wb;
     const int hi = (row / p.wb) % p.hb;
     const int ni = row / (p.wb * p.hb);
     const int esz = p.out.dtype == DN_F32 ? 4 : 2;
+    const int out_dtype = p.out.dtype, out_C = p.out.C, c_eff = p.c_eff, act = p.act, accumulate = p.accumulate, n_mma = p.n_mma;
+    const float out_scale = p.out_scale;
+    float breg[CH];
+    int nt_loaded = -1;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const int nt = tile % p.ntile_n;
       int m = tile / p.ntile_n;
@@ -327,62 +559,48 @@ __global__ void __launch_bounds__(192, 1) igemm_tc_kernel(const __grid_constant_
       const bool valid = (w < p.out.W) && (h < p.out.H) && (n < p.out.N);
       const int co0 = nt * BN;
       float* bs = bias_s + acc * BN;
-      for (int c = et; c < BN; c += 128) bs[c] = (p.bias && co0 + c < p.out.C) ? p.bias[co0 + c] : 0.f;
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (CPT <= 32) {       // bias in registers, reloaded only when the N tile changes (it never does for Cout <= 256)
+        if (nt != nt_loaded) {
+#pragma unroll
+          for (int j = 0; j < CH; ++j) breg[j] = (p.bias && co0 + cbeg + j < p.out.C) ? p.bias[co0 + cbeg + j] : 0.f;
+          nt_loaded = nt;
+        }
+      } else {
+        for (int c = et; c < BN; c += EW * 32) bs[c] = (p.bias && co0 + c < p.out.C) ? p.bias[co0 + c] : 0.f;
+        asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");
+      }
+      const size_t eoff = (size_t)(dn_off(p.out, n, h, w) + co0);
+      uint8_t* optr = (uint8_t*)p.out.ptr + eoff * esz;
       const long long te0 = p.dbg ? clock64() : 0;
       mbar_wait(&tfull_bar[acc], acc_phase);
       const long long te1 = p.dbg ? clock64() : 0;
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
-      uint8_t* optr = (uint8_t*)p.out.ptr + (size_t)(dn_off(p.out, n, h, w) + co0) * esz;
+      const int ce = c_eff - co0, oc = out_C - co0;      // channel limits relative to this N tile
+      if (CPT <= 32) {
+        uint32_t ra[CH];
+        if (cbeg < n_mma) {
+          tmem_ldn<CH>(taddr + cbeg, ra);
+          tmem_ld_wait();
+          epi_store<CH>(ra, breg, out_scale, act, valid, cbeg, ce, oc, out_dtype, optr + (size_t)cbeg * esz, accumulate, p.out2, p.out2_dtype, eoff + cbeg);
+        }
+      } else {
+        uint32_t ra[32], rb[32];
+        if (cbeg < n_mma) tmem_ld32(taddr + cbeg, ra);
 #pragma unroll 1
-      for (int c0 = 0; c0 < p.n_mma; c0 += 16) {
-        uint32_t r[16];
-        tmem_ld16(taddr + c0, r);
-        tmem_ld_wait();
-        if (valid && co0 + c0 < p.c_eff) {
-          float v[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = dn_act(__uint_as_float(r[j]) * p.out_scale + bs[c0 + j], p.act);
-          if (p.out2) store_out2(p.out2, p.out2_dtype, (size_t)(dn_off(p.out, n, h, w) + co0 + c0), v, co0 + c0, p.c_eff);
-          if (p.out.dtype == DN_F32) {
-            float* o = (float*)optr + c0;
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (co0 + c0 + j < p.out.C) o[j] = p.accumulate ? o[j] + v[j] : v[j];
-          } else if (p.out.dtype == DN_F16) {
-            __half* o = (__half*)optr + c0;
-#pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-              if (co0 + c0 + 8 * hh < p.c_eff) {
-                if (p.accumulate) {
-                  float a[8];
-                  Vec8<__half>::load(o + 8 * hh, a);
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) v[8 * hh + j] += a[j];
-                }
-                Vec8<__half>::store(o + 8 * hh, v + 8 * hh);
-              }
-            }
-          } else {
-            __nv_bfloat16* o = (__nv_bfloat16*)optr + c0;
-#pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-              if (co0 + c0 + 8 * hh < p.c_eff) {
-                if (p.accumulate) {
-                  float a[8];
-                  Vec8<__nv_bfloat16>::load(o + 8 * hh, a);
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) v[8 * hh + j] += a[j];
-                }
-                Vec8<__nv_bfloat16>::store(o + 8 * hh, v + 8 * hh);
-              }
-            }
-          }
+        for (int c0 = cbeg; c0 < cbeg + CPT && c0 < n_mma; c0 += 64) {
+          tmem_ld_wait();
+          if (c0 + 32 < cbeg + CPT && c0 + 32 < n_mma) tmem_ld32(taddr + c0 + 32, rb);
+          epi_store<32>(ra, bs + c0, out_scale, act, valid, c0, ce, oc, out_dtype, optr + (size_t)c0 * esz, accumulate, p.out2, p.out2_dtype, eoff + c0);
+          if (!(c0 + 32 < cbeg + CPT && c0 + 32 < n_mma)) break;
+          tmem_ld_wait();
+          if (c0 + 64 < cbeg + CPT && c0 + 64 < n_mma) tmem_ld32(taddr + c0 + 64, ra);
+          epi_store<32>(rb, bs + c0 + 32, out_scale, act, valid, c0 + 32, ce, oc, out_dtype, optr + (size_t)(c0 + 32) * esz, accumulate, p.out2, p.out2_dtype, eoff + c0 + 32);
         }
       }
       tc_fence_before();
-      mbar_arrive(&tempty_bar[acc]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       if (p.dbg && et == 0) {
         atomicAdd(p.dbg + 5, (unsigned long long)(te1 - te0));
         atomicAdd(p.dbg + 6, (unsigned long long)(clock64() - te1));
@@ -411,13 +629,13 @@ __global__ void __launch_bounds__(192, 1) igemm_tc_kernel(const __grid_constant_
 // lifetime of the persistent CTA.
 // ------------------------------------------------------------------------------------------------
 constexpr int kHaloW = 16, kHaloH = 18;
-constexpr uint32_t kHaloBytes = kHaloW * kHaloH * 128;     // 36864
 
 
 struct HaloParams {
   CUtensorMap tmA;
   CUtensorMap tmB;
   int kchunks, last_ksteps;
+  int cb;               // channels per halo-box row: 64, or 32 / 16 for thin inputs (one chunk)
   int wt[9];            // packed-weight matrix index of tap (kh, kw), kh = dh + 1, kw = dw + 1
   int tilesW, tilesH, num_tiles;
   int stages;
@@ -430,20 +648,31 @@ struct HaloParams {
   const float* bias;
   int act, accumulate;
   float out_scale;
+  unsigned long long* dbg;   // optional per-role cycle counters (dn_tc_set_debug), same slots as igemm_tc_kernel
+  int dbg_flags;             // experiments (DN_TC_FLAGS): 1 = epilogue neither reads TMEM nor stores, 2 = epilogue waits with nanosleep back-off
 };
 
-template <int BN>
-__global__ void __launch_bounds__(192, 1) igemm_halo_kernel(const __grid_constant__ HaloParams p) {
+// BN = MMA N tile, CB = channels per halo-box row (64 / 32 / 16).  Eight epilogue warps: two per TMEM lane quarter, each draining
+// half of the accumulator columns (a single warp per scheduler is latency-bound: ~1 700 cycles per 128 x 16 tile measured).
+// Thin tiles (BN <= 32) run two CTAs per SM for the same reason -- every role of this kernel is a single latency-bound warp.
+template <int BN, int CB>
+__global__ void __launch_bounds__(320, BN <= 32 ? 2 : 1) igemm_halo_kernel(const __grid_constant__ HaloParams p) {
   dn_pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr uint32_t B_BYTES = BN * 128;
+  constexpr int EW = 8;
+  constexpr int CPT = BN / 2 < 8 ? 8 : BN / 2;      // accumulator columns per epilogue thread
+  constexpr int CH = CPT < 32 ? CPT : 32;           // ... drained in chunks of CH
+  constexpr uint32_t halo_bytes = kHaloW * kHaloH * 2 * CB;      // 36 864 for 64-channel rows
+  constexpr uint32_t a_rb = 2 * CB, a_sbo = kHaloW * 2 * CB;
+  constexpr uint32_t a_layout = CB == 64 ? 2 : CB == 32 ? 4 : 6;
   constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int stages = p.stages;
   const int nb_tiles = p.ring ? p.bstages : 9 * p.kchunks;   // weight tiles in shared memory (ring slots or all of them)
   uint8_t* smem_b = smem;
   uint8_t* smem_a = smem + (size_t)nb_tiles * B_BYTES;
-  uint64_t* full_bar = (uint64_t*)(smem_a + (size_t)stages * kHaloBytes);
+  uint64_t* full_bar = (uint64_t*)(smem_a + (size_t)stages * halo_bytes);
   uint64_t* empty_bar = full_bar + stages;
   uint64_t* tfull_bar = empty_bar + stages;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -452,14 +681,14 @@ __global__ void __launch_bounds__(192, 1) igemm_halo_kernel(const __grid_constan
   uint32_t* tmem_ptr = (uint32_t*)(bfull_bar + 16);
   float* bias_s = (float*)(tmem_ptr + 2);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);      // (tells the compiler the role branches are warp-uniform)
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmA);
     tma_prefetch_desc(&p.tmB);
     for (int s = 0; s < stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 128); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], EW); }      // one arrival per epilogue warp
     for (int s = 0; s < 8; ++s) { mbar_init(&bfull_bar[s], 1); mbar_init(&bempty_bar[s], 1); }
     fence_barrier_init();
     fence_proxy_async();
@@ -486,11 +715,8 @@ __global__ void __launch_bounds__(192, 1) igemm_halo_kernel(const __grid_constan
       const int th = m % p.tilesH;
       const int n0 = m / p.tilesH;
       mbar_wait(&empty_bar[stage], phase ^ 1);
-      if (elect_one()) {
-        mbar_expect_tx(&full_bar[stage], kHaloBytes);
-        tma_load_4d(smem_a + (size_t)stage * kHaloBytes, &p.tmA, &full_bar[stage], a_kc * kChunk, tw * 8 - 1, th * 16 - 1, n0);
-      }
-      __syncwarp();
+      mbar_expect_tx_e(&full_bar[stage], halo_bytes);
+      tma_load_4d_e(smem_a + (size_t)stage * halo_bytes, &p.tmA, &full_bar[stage], a_kc * CB, tw * 8 - 1, th * 16 - 1, n0);
       if (++stage == stages) { stage = 0; phase ^= 1; }
       if (++a_kc == p.kchunks) { a_kc = 0; a_tile += gridDim.x; }
     };
@@ -500,11 +726,8 @@ __global__ void __launch_bounds__(192, 1) igemm_halo_kernel(const __grid_constan
         load_a();
         for (int t = 0; t < 9; ++t) {
           mbar_wait(&bempty_bar[bs], bphase ^ 1);
-          if (elect_one()) {
-            mbar_expect_tx(&bfull_bar[bs], B_BYTES);
-            tma_load_3d(smem_b + (size_t)bs * B_BYTES, &p.tmB, &bfull_bar[bs], kc * kChunk, 0, p.wt[t]);
-          }
-          __syncwarp();
+          mbar_expect_tx_e(&bfull_bar[bs], B_BYTES);
+          tma_load_3d_e(smem_b + (size_t)bs * B_BYTES, &p.tmB, &bfull_bar[bs], kc * kChunk, 0, p.wt[t]);
           if (++bs == p.bstages) { bs = 0; bphase ^= 1; }
         }
       }
@@ -514,7 +737,8 @@ __global__ void __launch_bounds__(192, 1) igemm_halo_kernel(const __grid_constan
     int stage = 0; uint32_t phase = 0;
     int bs = 0; uint32_t bphase = 0;
     int acc = 0; uint32_t acc_phase = 0;
-    const uint32_t sb0 = smem_u32(smem_b);
+    const uint64_t ad_base = make_desc(smem_u32(smem_a), 16, a_sbo, a_layout);
+    const uint64_t bd_base = make_desc(smem_u32(smem_b), 16, 1024);
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
       tc_fence_after();
@@ -522,26 +746,25 @@ __global__ void __launch_bounds__(192, 1) igemm_halo_kernel(const __grid_constan
       for (int kc = 0; kc < p.kchunks; ++kc) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem_a + (size_t)stage * kHaloBytes);
+        const uint64_t ad = ad_base + (uint64_t)((uint32_t)stage * (halo_bytes >> 4));
         const int ks = (kc == p.kchunks - 1) ? p.last_ksteps : 4;
-#pragma unroll 1
+#pragma unroll
         for (int t = 0; t < 9; ++t) {
           mbar_wait(&bfull_bar[bs], bphase);
           tc_fence_after();
-          if (elect_one()) {
-            const int kh = t / 3, kw = t - 3 * kh;
-            const uint64_t ad0 = make_desc(sa + (uint32_t)(kh * kHaloW + kw) * 128, 16, 2048);
-            const uint64_t bd0 = make_desc(sb0 + (uint32_t)bs * B_BYTES, 16, 1024);
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              if (k < ks) umma_f16(d_tmem, ad0 + (uint64_t)(2 * k), bd0 + (uint64_t)(2 * k), p.idesc, (kc == 0 && t == 0 && k == 0) ? 0u : 1u);
-            umma_commit(&bempty_bar[bs]);
+          {
+            const uint64_t ad0 = ad + (uint64_t)((((t / 3) * kHaloW + t % 3) * a_rb) >> 4);
+            const uint64_t bd0 = bd_base + (uint64_t)((uint32_t)bs * (B_BYTES >> 4));
+            umma_e(d_tmem, ad0, bd0, p.idesc, (kc == 0 && t == 0) ? 0u : 1u);
+            if (ks > 1) umma_acc_e(d_tmem, ad0 + 2, bd0 + 2, p.idesc);
+            if (ks > 2) umma_acc_e(d_tmem, ad0 + 4, bd0 + 4, p.idesc);
+            if (ks > 3) umma_acc_e(d_tmem, ad0 + 6, bd0 + 6, p.idesc);
+            umma_commit_e(&bempty_bar[bs]);
             if (t == 8) {
-              umma_commit(&empty_bar[stage]);
-              if (kc == p.kchunks - 1) umma_commit(&tfull_bar[acc]);
+              umma_commit_e(&empty_bar[stage]);
+              if (kc == p.kchunks - 1) umma_commit_e(&tfull_bar[acc]);
             }
           }
-          __syncwarp();
           if (++bs == p.bstages) { bs = 0; bphase ^= 1; }
         }
         if (++stage == stages) { stage = 0; phase ^= 1; }
@@ -549,32 +772,37 @@ __global__ void __launch_bounds__(192, 1) igemm_halo_kernel(const __grid_constan
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else if (warp == 0) {
-    // ---- producer: weights once, then one halo box per (tile, chunk)
+    // ---- producer: weights once (tile (kc, t) at slot kc * 9 + t), then one halo box per (tile, chunk)
     if (elect_one()) {
       int present = 0;
       for (int t = 0; t < 9; ++t) present += p.wt[t] >= 0 ? 1 : 0;
       mbar_expect_tx(bfull_bar, (uint32_t)(present * p.kchunks) * B_BYTES);
-      for (int t = 0; t < 9; ++t)
-        if (p.wt[t] >= 0)
-          for (int kc = 0; kc < p.kchunks; ++kc)
-            tma_load_3d(smem_b + (size_t)(t * p.kchunks + kc) * B_BYTES, &p.tmB, bfull_bar, kc * kChunk, 0, p.wt[t]);
+      for (int kc = 0; kc < p.kchunks; ++kc)
+        for (int t = 0; t < 9; ++t)
+          if (p.wt[t] >= 0)
+            tma_load_3d(smem_b + (size_t)(kc * 9 + t) * B_BYTES, &p.tmB, bfull_bar, kc * kChunk, 0, p.wt[t]);
     }
     __syncwarp();
     int stage = 0; uint32_t phase = 0;
+    long long dbg_acc0 = 0;
+    const long long tstart = p.dbg ? clock64() : 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       int m = tile;
       const int tw = m % p.tilesW; m /= p.tilesW;
       const int th = m % p.tilesH;
       const int n0 = m / p.tilesH;
       for (int kc = 0; kc < p.kchunks; ++kc) {
+        const long long t0 = p.dbg ? clock64() : 0;
         mbar_wait(&empty_bar[stage], phase ^ 1);
-        if (elect_one()) {
-          mbar_expect_tx(&full_bar[stage], kHaloBytes);
-          tma_load_4d(smem_a + (size_t)stage * kHaloBytes, &p.tmA, &full_bar[stage], kc * kChunk, tw * 8 - 1, th * 16 - 1, n0);
-        }
-        __syncwarp();
+        if (p.dbg) dbg_acc0 += clock64() - t0;
+        mbar_expect_tx_e(&full_bar[stage], halo_bytes);
+        tma_load_4d_e(smem_a + (size_t)stage * halo_bytes, &p.tmA, &full_bar[stage], kc * CB, tw * 8 - 1, th * 16 - 1, n0);
         if (++stage == stages) { stage = 0; phase ^= 1; }
       }
+    }
+    if (p.dbg && lane == 0) {
+      atomicAdd(p.dbg + 0, (unsigned long long)dbg_acc0);
+      atomicAdd(p.dbg + 1, (unsigned long long)(clock64() - tstart));
     }
   } else if (warp == 1) {
     // ---- MMA issuer
@@ -582,46 +810,65 @@ __global__ void __launch_bounds__(192, 1) igemm_halo_kernel(const __grid_constan
     tc_fence_after();
     int stage = 0; uint32_t phase = 0;
     int acc = 0; uint32_t acc_phase = 0;
-    const uint32_t sb0 = smem_u32(smem_b);
+    uint32_t mask = 0;
+    for (int t = 0; t < 9; ++t) mask |= (p.wt[t] >= 0 ? 1u : 0u) << t;
+    const uint64_t ad_base = make_desc(smem_u32(smem_a), 16, a_sbo, a_layout);
+    const uint64_t bd_base = make_desc(smem_u32(smem_b), 16, 1024);
+    const uint32_t idesc = p.idesc;
+    const int kchunks = p.kchunks, last_ks = p.last_ksteps;
+    long long dbg_full = 0, dbg_te = 0;
+    const long long tstart = p.dbg ? clock64() : 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      long long t0 = p.dbg ? clock64() : 0;
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      if (p.dbg) dbg_te += clock64() - t0;
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-      for (int kc = 0; kc < p.kchunks; ++kc) {
+      for (int kc = 0; kc < kchunks; ++kc) {
+        t0 = p.dbg ? clock64() : 0;
         mbar_wait(&full_bar[stage], phase);
+        if (p.dbg) dbg_full += clock64() - t0;
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem_a + (size_t)stage * kHaloBytes);
-        const int ks = (kc == p.kchunks - 1) ? p.last_ksteps : 4;
-        if (elect_one()) {
-          uint32_t accumulate = kc == 0 ? 0u : 1u;
-#pragma unroll
-          for (int t = 0; t < 9; ++t) {
-            if (p.wt[t] < 0) continue;      // tap subset (2x2 neighbourhood of a transposed-convolution phase)
-            const int kh = t / 3, kw = t % 3;
-            // base_offset stays 0: the 128B swizzle is a function of the absolute shared-memory address bits (measured on B200:
-            // only base_offset = 0 reproduces the unshifted kernel), so a start that is not 1024-byte aligned needs no correction
-            const uint64_t ad0 = make_desc(sa + (uint32_t)(kh * kHaloW + kw) * 128, 16, 2048);
-            const uint64_t bd0 = make_desc(sb0 + (uint32_t)(t * p.kchunks + kc) * B_BYTES, 16, 1024);
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              if (k < ks) { umma_f16(d_tmem, ad0 + (uint64_t)(2 * k), bd0 + (uint64_t)(2 * k), p.idesc, accumulate); accumulate = 1u; }
-          }
-          umma_commit(&empty_bar[stage]);
-          if (kc == p.kchunks - 1) umma_commit(&tfull_bar[acc]);
+        const uint64_t ad = ad_base + (uint64_t)((uint32_t)stage * (halo_bytes >> 4));
+        const uint64_t bd = bd_base + (uint64_t)((uint32_t)kc * (9 * B_BYTES >> 4));
+        const uint32_t last = kc == kchunks - 1 ? 1u : 0u;
+        {
+          const uint32_t acc0 = kc == 0 ? 0u : 1u;
+          const int ks = last ? last_ks : CB / 16;
+          const uint32_t eb = smem_u32(&empty_bar[stage]), tb = smem_u32(&tfull_bar[acc]);
+          if (CB == 16 || ks == 1) halo_issue<1, (int)a_rb, (int)B_BYTES>(d_tmem, ad, bd, idesc, mask, acc0, eb, tb, last);
+          else if (CB == 32 || ks == 2) halo_issue<2, (int)a_rb, (int)B_BYTES>(d_tmem, ad, bd, idesc, mask, acc0, eb, tb, last);
+          else if (ks == 3) halo_issue<3, (int)a_rb, (int)B_BYTES>(d_tmem, ad, bd, idesc, mask, acc0, eb, tb, last);
+          else halo_issue<4, (int)a_rb, (int)B_BYTES>(d_tmem, ad, bd, idesc, mask, acc0, eb, tb, last);
         }
-        __syncwarp();
         if (++stage == stages) { stage = 0; phase ^= 1; }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (p.dbg && lane == 0) {
+      atomicAdd(p.dbg + 2, (unsigned long long)dbg_full); atomicAdd(p.dbg + 3, (unsigned long long)dbg_te);
+      atomicAdd(p.dbg + 4, (unsigned long long)(clock64() - tstart));
+    }
   } else {
-    // ---- epilogue: tile row r = 8 * h_local + w_local
+    // ---- epilogue: tile row r = 8 * h_local + w_local; warps 2..5 drain columns [0, CPT), warps 6..9 columns [CPT, 2 CPT)
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const int et = threadIdx.x - 64;
+    const int cbeg = (warp >= 6 ? 1 : 0) * CPT;
     int acc = 0; uint32_t acc_phase = 0;
     const int wi = row & 7, hi = row >> 3;
     const int esz = p.out.dtype == DN_F32 ? 4 : 2;
+    const int out_dtype = p.out.dtype, out_C = p.out.C, c_eff = p.c_eff, act = p.act, accumulate = p.accumulate, n_mma = p.n_mma;
+    const float out_scale = p.out_scale;
+    // bias: registers when a thread owns at most 32 columns, shared memory otherwise (one N tile: the same for every tile)
+    float breg[CH];
+    if (CPT <= 32) {
+#pragma unroll
+      for (int j = 0; j < CH; ++j) breg[j] = (p.bias && cbeg + j < p.out.C) ? p.bias[cbeg + j] : 0.f;
+    } else {
+      for (int c = et; c < BN; c += EW * 32) bias_s[c] = (p.bias && c < p.out.C) ? p.bias[c] : 0.f;
+      asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");
+    }
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       int m = tile;
       const int tw = m % p.tilesW; m /= p.tilesW;
@@ -629,59 +876,46 @@ __global__ void __launch_bounds__(192, 1) igemm_halo_kernel(const __grid_constan
       const int n = m / p.tilesH;
       const int w = tw * 8 + wi, h = th * 16 + hi;
       const bool valid = (w < p.out.W) && (h < p.out.H);
-      float* bs = bias_s + acc * BN;
-      for (int c = et; c < BN; c += 128) bs[c] = (p.bias && c < p.out.C) ? p.bias[c] : 0.f;
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      mbar_wait(&tfull_bar[acc], acc_phase);
+      const size_t eoff = (size_t)dn_off(p.out, n, h, w);
+      uint8_t* optr = (uint8_t*)p.out.ptr + eoff * esz;
+      const long long te0 = p.dbg ? clock64() : 0;
+      if (p.dbg_flags & 2) mbar_wait_sleep(&tfull_bar[acc], acc_phase); else mbar_wait(&tfull_bar[acc], acc_phase);
+      const long long te1 = p.dbg ? clock64() : 0;
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
-      uint8_t* optr = (uint8_t*)p.out.ptr + (size_t)dn_off(p.out, n, h, w) * esz;
+      if (p.dbg_flags & 1) {
+      } else if (CPT <= 32) {
+        uint32_t ra[CH];
+        if (cbeg < n_mma) {
+          tmem_ldn<CH>(taddr + cbeg, ra);
+          tmem_ld_wait();
+          if (p.dbg && et == 0) atomicAdd(p.dbg + 7, (unsigned long long)(clock64() - te1));
+          epi_store<CH>(ra, breg, out_scale, act, valid, cbeg, c_eff, out_C, out_dtype, optr + (size_t)cbeg * esz, accumulate, p.out2, p.out2_dtype, eoff + cbeg);
+        }
+      } else {
+        // chunks of 32 columns; the TMEM load of chunk i + 1 is in flight while chunk i is converted and stored
+        uint32_t ra[32], rb[32];
+        if (cbeg < n_mma) tmem_ld32(taddr + cbeg, ra);
 #pragma unroll 1
-      for (int c0 = 0; c0 < p.n_mma; c0 += 16) {
-        uint32_t r[16];
-        tmem_ld16(taddr + c0, r);
-        tmem_ld_wait();
-        if (valid && c0 < p.c_eff) {
-          float v[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = dn_act(__uint_as_float(r[j]) * p.out_scale + bs[c0 + j], p.act);
-          if (p.out2) store_out2(p.out2, p.out2_dtype, (size_t)(dn_off(p.out, n, h, w) + c0), v, c0, p.c_eff);
-          if (p.out.dtype == DN_F32) {
-            float* o = (float*)optr + c0;
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (c0 + j < p.out.C) o[j] = p.accumulate ? o[j] + v[j] : v[j];
-          } else if (p.out.dtype == DN_F16) {
-            __half* o = (__half*)optr + c0;
-#pragma unroll
-            for (int hh = 0; hh < 2; ++hh)
-              if (c0 + 8 * hh < p.c_eff) {
-                if (p.accumulate) {
-                  float a[8];
-                  Vec8<__half>::load(o + 8 * hh, a);
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) v[8 * hh + j] += a[j];
-                }
-                Vec8<__half>::store(o + 8 * hh, v + 8 * hh);
-              }
-          } else {
-            __nv_bfloat16* o = (__nv_bfloat16*)optr + c0;
-#pragma unroll
-            for (int hh = 0; hh < 2; ++hh)
-              if (c0 + 8 * hh < p.c_eff) {
-                if (p.accumulate) {
-                  float a[8];
-                  Vec8<__nv_bfloat16>::load(o + 8 * hh, a);
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) v[8 * hh + j] += a[j];
-                }
-                Vec8<__nv_bfloat16>::store(o + 8 * hh, v + 8 * hh);
-              }
-          }
+        for (int c0 = cbeg; c0 < cbeg + CPT && c0 < n_mma; c0 += 64) {
+          tmem_ld_wait();
+          if (c0 + 32 < cbeg + CPT && c0 + 32 < n_mma) tmem_ld32(taddr + c0 + 32, rb);
+          epi_store<32>(ra, bias_s + c0, out_scale, act, valid, c0, c_eff, out_C, out_dtype, optr + (size_t)c0 * esz, accumulate, p.out2, p.out2_dtype, eoff + c0);
+          if (!(c0 + 32 < cbeg + CPT && c0 + 32 < n_mma)) break;
+          tmem_ld_wait();
+          if (c0 + 64 < cbeg + CPT && c0 + 64 < n_mma) tmem_ld32(taddr + c0 + 64, ra);
+          epi_store<32>(rb, bias_s + c0 + 32, out_scale, act, valid, c0 + 32, c_eff, out_C, out_dtype, optr + (size_t)(c0 + 32) * esz, accumulate, p.out2, p.out2_dtype, eoff + c0 + 32);
         }
       }
+      const long long te2 = p.dbg ? clock64() : 0;
       tc_fence_before();
-      mbar_arrive(&tempty_bar[acc]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (p.dbg && et == 0) {
+        atomicAdd(p.dbg + 5, (unsigned long long)(te1 - te0));
+        atomicAdd(p.dbg + 6, (unsigned long long)(clock64() - te1));
+        atomicAdd(p.dbg + 15, (unsigned long long)(clock64() - te2));
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
@@ -714,13 +948,17 @@ struct WgradTcParams {
   int nacc;                // TMEM accumulator stages (2: the atomics of item i overlap the main loop of item i+1)
   int tmem_cols;
   int halo;                // 1: x is fetched once per pixel tile as a (8+2) x 16-pixel halo box, taps are shifted views
+  int p5, q5;              // dy / x maps are 5-D (64 ch, W, H, N, channel block): all 64-channel blocks of a stage in ONE TMA
+  int cbq;                 // channels per x row in shared memory: 64, or 32 / 16 for thin x (one 64-wide cq tile, n_mma <= cbq)
   uint32_t idesc;
   float* dw;
   int cp, cq, cp_pad, cq_pad;
   float scale;
+  unsigned long long* dbg;   // optional per-role cycle counters (dn_tc_set_debug), slots 8..14 (same roles as slots 0..6)
 };
 
 constexpr int KPX = 64;   // pixels (= GEMM K) per pipeline stage
+constexpr int kWgMaxTpc = 32;   // taps per work item: 512 TMEM columns / 16
 
 struct WgItem { int grp, cqt, cpt, split, t0, nt, src, pt_beg, n_iters; };
 
@@ -747,8 +985,10 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr uint32_t BLK_BYTES = KPX * 128;              // one [KPX px][64 ch] swizzled block
   constexpr uint32_t A_BYTES = 2 * BLK_BYTES;            // M = 128 channels of P
-  constexpr uint32_t B_BYTES = (BNQ / 64) * BLK_BYTES;   // per tap (plain mode)
-  constexpr uint32_t HALO_BLK = 16 * 10 * 128;           // one [10 rows][16 px][64 ch] halo block (halo mode)
+  const uint32_t q_rb = (uint32_t)(2 * p.cbq), q_layout = (uint32_t)thin_layout(p.cbq);   // bytes per pixel row of x
+  const uint32_t Q_BLK = KPX * q_rb;                     // one [KPX px][cbq ch] block of x
+  const uint32_t B_BYTES = (BNQ / 64) * Q_BLK;           // per tap (plain mode)
+  const uint32_t HALO_BLK = 16 * 10 * q_rb;              // one [10 rows][16 px][cbq ch] halo block (halo mode)
   const uint32_t STAGE_BYTES = A_BYTES + (p.halo ? (uint32_t)(BNQ / 64) * HALO_BLK : (uint32_t)p.tpc * B_BYTES);
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int stages = p.stages;
@@ -758,7 +998,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_ptr = (uint32_t*)(tempty_bar + 2);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);      // (tells the compiler the role branches are warp-uniform)
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
@@ -783,22 +1023,33 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
   if (warp == 0) {
     // ================= TMA producer =================
     int stage = 0; uint32_t phase = 0;
+    long long dbg_acc0 = 0;
+    const long long tstart = p.dbg ? clock64() : 0;
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
       const WgItem w = wg_decode(p, item);
       // bytes that really arrive per stage: only the P blocks that exist and the taps of this group are loaded
       const uint32_t tx_bytes = (uint32_t)p.cp_blocks * BLK_BYTES + (p.halo ? (uint32_t)(BNQ / 64) * HALO_BLK : (uint32_t)w.nt * B_BYTES);
+      // pixel-tile coordinates: one division per item, then incremental (the divisions cost more than the TMA issue itself)
+      int tw, th, tn;
+      {
+        int m = w.pt_beg;
+        tw = m % p.tilesW; m /= p.tilesW;
+        th = m % p.tilesH;
+        tn = m / p.tilesH;
+      }
       for (int it = 0; it < w.n_iters; ++it) {
-        int m = w.pt_beg + it;
-        const int tw = m % p.tilesW; m /= p.tilesW;
-        const int th = m % p.tilesH;
-        const int tn = m / p.tilesH;
         const int w0 = tw * p.wb, h0 = th * p.hb, n0 = tn * p.nb;
+        if (++tw == p.tilesW) { tw = 0; if (++th == p.tilesH) { th = 0; ++tn; } }
+        const long long t0 = p.dbg ? clock64() : 0;
         mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (p.dbg) dbg_acc0 += clock64() - t0;
         if (elect_one()) {
           uint8_t* sa = smem + (size_t)stage * STAGE_BYTES;
           mbar_expect_tx(&full_bar[stage], tx_bytes);
-          for (int j = 0; j < p.cp_blocks; ++j)
-            tma_load_4d(sa + j * BLK_BYTES, &p.tmP[w.src], &full_bar[stage], w.cpt * 128 + j * 64, w0, h0, n0);
+          if (p.p5) tma_load_5d(sa, &p.tmP[w.src], &full_bar[stage], 0, w0, h0, n0, w.cpt * 2);
+          else
+            for (int j = 0; j < p.cp_blocks; ++j)
+              tma_load_4d(sa + j * BLK_BYTES, &p.tmP[w.src], &full_bar[stage], w.cpt * 128 + j * 64, w0, h0, n0);
           if (p.halo) {
 #pragma unroll
             for (int j = 0; j < BNQ / 64; ++j)
@@ -807,9 +1058,12 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
             for (int t = 0; t < w.nt; ++t) {
               const TcTap tap = p.taps[w.t0 + t];
               uint8_t* sb = sa + A_BYTES + (size_t)t * B_BYTES;
+              if (p.q5) tma_load_5d(sb, &p.tmQ, &full_bar[stage], 0, w0 + tap.dw, h0 + tap.dh, n0, w.cqt * (BNQ / 64));
+              else {
 #pragma unroll
-              for (int j = 0; j < BNQ / 64; ++j)
-                tma_load_4d(sb + j * BLK_BYTES, &p.tmQ, &full_bar[stage], w.cqt * BNQ + j * 64, w0 + tap.dw, h0 + tap.dh, n0);
+                for (int j = 0; j < BNQ / 64; ++j)
+                  tma_load_4d(sb + j * Q_BLK, &p.tmQ, &full_bar[stage], w.cqt * BNQ + j * 64, w0 + tap.dw, h0 + tap.dh, n0);
+              }
             }
           }
         }
@@ -817,50 +1071,74 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
         if (++stage == stages) { stage = 0; phase ^= 1; }
       }
     }
+    if (p.dbg && lane == 0) {
+      atomicAdd(p.dbg + 8, (unsigned long long)dbg_acc0);
+      atomicAdd(p.dbg + 9, (unsigned long long)(clock64() - tstart));
+    }
   } else if (warp == 1) {
     // ================= MMA issuer =================
     int stage = 0; uint32_t phase = 0;
     int acc = 0; uint32_t acc_phase = 0;
+    long long dbg_full = 0, dbg_te = 0;
+    const long long tstart = p.dbg ? clock64() : 0;
+    static_assert(KPX == 64, "four K steps per stage are unrolled below");
+    const uint64_t ad_base = make_desc(smem_u32(smem), BLK_BYTES, 1024);
+    const uint64_t bd_base = make_desc(smem_u32(smem), p.halo ? HALO_BLK : Q_BLK, p.halo ? 16 * q_rb : 8 * q_rb, q_layout);
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
       const WgItem w = wg_decode(p, item);
+      long long t0 = p.dbg ? clock64() : 0;
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      if (p.dbg) dbg_te += clock64() - t0;
       tc_fence_after();
       const uint32_t d_base = tmem_base + (uint32_t)acc * acc_cols;
+      // per-tap operand offsets of this item, computed once (the inner loop then spends two adds per MMA: the issuing thread's
+      // instruction stream is what paces thin problems, tools/ubench_tc.cu)
+      uint32_t boff[kWgMaxTpc];
+#pragma unroll
+      for (int t = 0; t < kWgMaxTpc; ++t) {
+        if (t >= w.nt) break;
+        {
+          if (p.halo) {
+            // pixel tile = 8 rows x 8 columns; tap (dh, dw) reads halo pixel (row + dh + 1, col + dw + 1): a view that starts
+            // ((dh+1)*16 + (dw+1)) pixels into the 16-pixel-pitch halo block.  One UMMA_K step = 16 pixels = 2 image rows.
+            const TcTap tap = p.taps[w.t0 + t];
+            boff[t] = (A_BYTES + (uint32_t)((tap.dh + 1) * 16 + (tap.dw + 1)) * q_rb) >> 4;
+          } else {
+            boff[t] = (A_BYTES + (uint32_t)t * B_BYTES) >> 4;
+          }
+        }
+      }
+      const uint32_t kadv = p.halo ? 2 * q_rb : q_rb;      // 16 pixels further down the x block, in 16-byte units
+      const uint32_t n_mma = (uint32_t)p.n_mma, idesc = p.idesc;
       for (int it = 0; it < w.n_iters; ++it) {
+        t0 = p.dbg ? clock64() : 0;
         mbar_wait(&full_bar[stage], phase);
+        if (p.dbg) dbg_full += clock64() - t0;
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + (size_t)stage * STAGE_BYTES);
         // MN-major, 128B swizzle: LBO = distance between 64-channel blocks, SBO = 8 pixel rows = 1024 B;
         // 16 pixels (one UMMA_K step) further down = +2048 bytes = +128 in the (addr >> 4) field
-        const uint64_t ad0 = make_desc(sa, BLK_BYTES, 1024);
-        if (elect_one()) {
-          for (int t = 0; t < w.nt; ++t) {
-            if (p.halo) {
-              // pixel tile = 8 rows x 8 columns; tap (dh, dw) reads halo pixel (row + dh + 1, col + dw + 1): a view that starts
-              // ((dh+1)*16 + (dw+1)) pixels into the 16-pixel-pitch halo block.  One UMMA_K step = 16 pixels = 2 image rows.
-              const TcTap tap = p.taps[w.t0 + t];
-              const uint32_t sb = sa + A_BYTES + (uint32_t)((tap.dh + 1) * 16 + (tap.dw + 1)) * 128;
-              const uint64_t bd0 = make_desc(sb, HALO_BLK, 2048);
+        const uint64_t ad0 = ad_base + (uint64_t)((uint32_t)stage * (STAGE_BYTES >> 4));
+        const uint64_t bd0 = bd_base + (uint64_t)((uint32_t)stage * (STAGE_BYTES >> 4));
+        {
+          const uint32_t first = it > 0 ? 1u : 0u;
+          uint32_t d = d_base;
 #pragma unroll
-              for (int k = 0; k < KPX / 16; ++k)
-                umma_f16(d_base + (uint32_t)(t * p.n_mma), ad0 + (uint64_t)(128 * k), bd0 + (uint64_t)(256 * k), p.idesc,
-                         (it > 0 || k > 0) ? 1u : 0u);
-            } else {
-              const uint64_t bd0 = make_desc(sa + A_BYTES + (uint32_t)t * B_BYTES, BLK_BYTES, 1024);
-#pragma unroll
-              for (int k = 0; k < KPX / 16; ++k)
-                umma_f16(d_base + (uint32_t)(t * p.n_mma), ad0 + (uint64_t)(128 * k), bd0 + (uint64_t)(128 * k), p.idesc,
-                         (it > 0 || k > 0) ? 1u : 0u);
-            }
+          for (int t = 0; t < kWgMaxTpc; ++t) {
+            if (t >= w.nt) break;
+            wg_issue4(d, ad0, bd0 + (uint64_t)boff[t], idesc, first, kadv);
+            d += n_mma;
           }
-          umma_commit(&empty_bar[stage]);
-          if (it == w.n_iters - 1) umma_commit(&tfull_bar[acc]);
+          umma_commit_e(&empty_bar[stage]);
+          if (it == w.n_iters - 1) umma_commit_e(&tfull_bar[acc]);
         }
-        __syncwarp();
         if (++stage == stages) { stage = 0; phase ^= 1; }
       }
       if (p.nacc == 2) { if (++acc == 2) { acc = 0; acc_phase ^= 1; } }
       else acc_phase ^= 1;
+    }
+    if (p.dbg && lane == 0) {
+      atomicAdd(p.dbg + 10, (unsigned long long)dbg_full); atomicAdd(p.dbg + 11, (unsigned long long)dbg_te);
+      atomicAdd(p.dbg + 12, (unsigned long long)(clock64() - tstart));
     }
   } else {
     // ================= epilogue: TMEM -> scaled fp32 partial sums -> red.global.add =================
@@ -875,7 +1153,9 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
       bool row_ok = true;
       if (p.m64 == 1) { cp = w.cpt * 128 + q * 16 + lane; row_ok = lane < 16; }
       else if (p.m64 == 2) { row_ok = row < 64; }
+      const long long te0 = p.dbg ? clock64() : 0;
       mbar_wait(&tfull_bar[acc], acc_phase);
+      const long long te1 = p.dbg ? clock64() : 0;
       tc_fence_after();
       for (int t = 0; t < w.nt; ++t) {
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * acc_cols + (uint32_t)(t * p.n_mma);
@@ -895,6 +1175,10 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
       }
       tc_fence_before();
       mbar_arrive(&tempty_bar[acc]);
+      if (p.dbg && threadIdx.x == 64) {
+        atomicAdd(p.dbg + 13, (unsigned long long)(te1 - te0));
+        atomicAdd(p.dbg + 14, (unsigned long long)(clock64() - te1));
+      }
       if (p.nacc == 2) { if (++acc == 2) { acc = 0; acc_phase ^= 1; } }
       else acc_phase ^= 1;
     }
@@ -930,19 +1214,41 @@ bool view_tma_ok(const dn_view& v) {
   return true;
 }
 
-// 4-D map (C, W, H, N) of an NHWC view, box {64, wb, hb, nb}, 128B swizzle, zero OOB fill
-int make_view_map(CUtensorMap* tm, const dn_view& v, int wb, int hb, int nb) {
+CUtensorMapSwizzle swizzle_of(int cb) {
+  return cb == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : cb == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+}
+
+// 4-D map (C, W, H, N) of an NHWC view, box {cb, wb, hb, nb} (cb = 64 / 32 / 16 channels -> 128B / 64B / 32B swizzle), zero OOB fill
+int make_view_map(CUtensorMap* tm, const dn_view& v, int wb, int hb, int nb, int cb = kChunk) {
   auto enc = get_encode();
   if (!enc) return DN_E_UNSUPPORTED;
   cuuint64_t dims[4] = {(cuuint64_t)v.C, (cuuint64_t)v.W, (cuuint64_t)v.H, (cuuint64_t)v.N};
   cuuint64_t strides[3] = {(cuuint64_t)v.sW * 2, (cuuint64_t)v.sH * 2, (cuuint64_t)v.sN * 2};
-  cuuint32_t box[4] = {(cuuint32_t)kChunk, (cuuint32_t)wb, (cuuint32_t)hb, (cuuint32_t)nb};
+  cuuint32_t box[4] = {(cuuint32_t)cb, (cuuint32_t)wb, (cuuint32_t)hb, (cuuint32_t)nb};
   cuuint32_t es[4] = {1, 1, 1, 1};
   CUtensorMapDataType dt = v.dtype == DN_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
-  CUresult r = enc(tm, dt, 4, v.ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+  CUresult r = enc(tm, dt, 4, v.ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_of(cb),
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : DN_E_ARG;
 }
+
+// 5-D map (64 ch, W, H, N, channel block) of a view whose channel count is a multiple of 64: box {64, wb, hb, nb, nblk} lands as
+// nblk consecutive [pixels][64 ch] blocks -- the layout the weight-gradient kernel wants -- with one TMA instruction
+int make_view_map5(CUtensorMap* tm, const dn_view& v, int wb, int hb, int nb, int nblk) {
+  auto enc = get_encode();
+  if (!enc) return DN_E_UNSUPPORTED;
+  cuuint64_t dims[5] = {64, (cuuint64_t)v.W, (cuuint64_t)v.H, (cuuint64_t)v.N, (cuuint64_t)(v.C / 64)};
+  cuuint64_t strides[4] = {(cuuint64_t)v.sW * 2, (cuuint64_t)v.sH * 2, (cuuint64_t)v.sN * 2, 128};
+  cuuint32_t box[5] = {64, (cuuint32_t)wb, (cuuint32_t)hb, (cuuint32_t)nb, (cuuint32_t)nblk};
+  cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  CUtensorMapDataType dt = v.dtype == DN_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  CUresult r = enc(tm, dt, 5, v.ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : DN_E_ARG;
+}
+
+const bool g_thin_rows = []() { const char* e = getenv("DN_THIN_ROWS"); return !(e && e[0] == '0'); }();   // A/B knob
+int pick_cb(int C) { return g_thin_rows ? thin_cb(C) : kChunk; }
 
 // choose a pixel box with wb*hb*nb == rows that minimises the number of tiles
 void choose_box(int N, int H, int W, int rows, int& wb, int& hb, int& nb) {
@@ -982,7 +1288,7 @@ int pick_bn(int cout_pad) {
 
 template <int BN>
 int launch_igemm(const IgemmTcParams& P, cudaStream_t st) {
-  constexpr uint32_t STAGE_BYTES = kRows * 128 + BN * 128;
+  const uint32_t STAGE_BYTES = kRows * 2 * P.cb + BN * 128;
   int stages = P.stages;
   size_t smem = (size_t)stages * STAGE_BYTES + 1024 + (2 * stages + 4) * 8 + 16 + 2 * BN * 4;
   static bool attr_set = false;
@@ -992,14 +1298,15 @@ int launch_igemm(const IgemmTcParams& P, cudaStream_t st) {
     attr_set = true;
   }
   int grid = P.num_tiles < dn_num_sms() ? P.num_tiles : dn_num_sms();
-  dn_launch(igemm_tc_kernel<BN>, dim3(grid), dim3(192), smem, st, P);
+  dn_launch(igemm_tc_kernel<BN>, dim3(grid), dim3(320), smem, st, P);
   DN_CHECK_LAUNCH();
   return 0;
 }
 
 template <int BNQ>
 int launch_wgrad(const WgradTcParams& P, int items, cudaStream_t st) {
-  const uint32_t stage_bytes = 2 * KPX * 128 + (P.halo ? (uint32_t)(BNQ / 64) * 16 * 10 * 128 : (uint32_t)P.tpc * (BNQ / 64) * KPX * 128);
+  const uint32_t q_rb = 2 * P.cbq;
+  const uint32_t stage_bytes = 2 * KPX * 128 + (P.halo ? (uint32_t)(BNQ / 64) * 16 * 10 * q_rb : (uint32_t)P.tpc * (BNQ / 64) * KPX * q_rb);
   size_t smem = (size_t)P.stages * stage_bytes + 1024 + (2 * P.stages + 4) * 8 + 16;
   static bool attr_set = false;
   if (!attr_set) {
@@ -1014,6 +1321,8 @@ int launch_wgrad(const WgradTcParams& P, int items, cudaStream_t st) {
   return 0;
 }
 
+
+unsigned long long* g_tc_dbg = nullptr;
 
 // ---- halo variant: eligibility + launch -------------------------------------------------------------------------
 bool g_halo_enabled = true;
@@ -1041,8 +1350,10 @@ bool halo_eligible(const dn_igemm* p, int* wt) {
   if (!g_halo_enabled || !halo_taps(p, wt)) return false;
   if (p->cout_pad > 256) return false;
   const int BN = pick_bn(p->cout_pad);
-  const int kchunks = (p->in[0].C + kChunk - 1) / kChunk;
+  const int cb = pick_cb(p->in[0].C);
+  const int kchunks = (p->in[0].C + cb - 1) / cb;
   const size_t b_bytes = (size_t)9 * kchunks * BN * 128;
+  const size_t kHaloBytes = (size_t)kHaloW * kHaloH * 2 * cb;
   // weights stay resident next to >= 2 halo stages when they fit; else they stream through a ring, which measured a gain only
   // for one-chunk problems (features.7 forward 0.099 -> 0.093 ms): N <= 128 tiles with more K are bound by the 128 B/clk
   // shared-memory operand reads of cta_group::1 either way (A 4 KB + B 4 KB per 64-cycle 128x128x16 MMA)
@@ -1054,20 +1365,29 @@ bool halo_eligible(const dn_igemm* p, int* wt) {
   return eff >= 0.85;
 }
 
-template <int BN>
-int launch_halo(const HaloParams& P, cudaStream_t st) {
+template <int BN, int CB>
+int launch_halo_cb(const HaloParams& P, cudaStream_t st) {
   const size_t b_bytes = (size_t)(P.ring ? P.bstages : 9 * P.kchunks) * BN * 128;
+  const size_t kHaloBytes = (size_t)kHaloW * kHaloH * 2 * P.cb;
   size_t smem = b_bytes + (size_t)P.stages * kHaloBytes + 1024 + (2 * P.stages + 20) * 8 + 16 + 2 * BN * 4;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(igemm_halo_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(igemm_halo_kernel<BN, CB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  int grid = P.num_tiles < dn_num_sms() ? P.num_tiles : dn_num_sms();
-  dn_launch(igemm_halo_kernel<BN>, dim3(grid), dim3(192), smem, st, P);
+  const int ctas = ((BN <= 32 && smem <= 110 * 1024) ? 2 : 1) * dn_num_sms();
+  int grid = P.num_tiles < ctas ? P.num_tiles : ctas;
+  dn_launch(igemm_halo_kernel<BN, CB>, dim3(grid), dim3(320), smem, st, P);
   DN_CHECK_LAUNCH();
   return 0;
+}
+
+template <int BN>
+int launch_halo(const HaloParams& P, cudaStream_t st) {
+  if (P.cb == 16) return launch_halo_cb<BN, 16>(P, st);
+  if (P.cb == 32) return launch_halo_cb<BN, 32>(P, st);
+  return launch_halo_cb<BN, 64>(P, st);
 }
 
 int dn_igemm_halo(const dn_igemm* p, const int* wt, cudaStream_t st) {
@@ -1076,16 +1396,11 @@ int dn_igemm_halo(const dn_igemm* p, const int* wt, cudaStream_t st) {
   const int BN = pick_bn(p->cout_pad);
   auto enc = get_encode();
   if (!enc) return DN_E_UNSUPPORTED;
+  P.cb = pick_cb(p->in[0].C);
+  const size_t kHaloBytes = (size_t)kHaloW * kHaloH * 2 * P.cb;
   {
-    const dn_view& v = p->in[0];
-    cuuint64_t dims[4] = {(cuuint64_t)v.C, (cuuint64_t)v.W, (cuuint64_t)v.H, (cuuint64_t)v.N};
-    cuuint64_t strides[3] = {(cuuint64_t)v.sW * 2, (cuuint64_t)v.sH * 2, (cuuint64_t)v.sN * 2};
-    cuuint32_t box[4] = {(cuuint32_t)kChunk, (cuuint32_t)kHaloW, (cuuint32_t)kHaloH, 1};
-    cuuint32_t es[4] = {1, 1, 1, 1};
-    CUtensorMapDataType dt = v.dtype == DN_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
-    if (enc(&P.tmA, dt, 4, v.ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-      return DN_E_ARG;
+    int e = make_view_map(&P.tmA, p->in[0], kHaloW, kHaloH, 1, P.cb);
+    if (e) return e;
   }
   {
     int nw = 0;
@@ -1101,8 +1416,8 @@ int dn_igemm_halo(const dn_igemm* p, const int* wt, cudaStream_t st) {
   }
   for (int t = 0; t < 9; ++t) P.wt[t] = wt[t];
   const int Cin = p->in[0].C;
-  P.kchunks = (Cin + kChunk - 1) / kChunk;
-  P.last_ksteps = (Cin - (P.kchunks - 1) * kChunk + 15) / 16;
+  P.kchunks = (Cin + P.cb - 1) / P.cb;
+  P.last_ksteps = (Cin - (P.kchunks - 1) * P.cb + 15) / 16;
   P.tilesW = (p->out.W + 7) / 8;
   P.tilesH = (p->out.H + 15) / 16;
   P.num_tiles = P.tilesW * P.tilesH * p->out.N;
@@ -1113,8 +1428,11 @@ int dn_igemm_halo(const dn_igemm* p, const int* wt, cudaStream_t st) {
     P.bstages = (int)((200 * 1024 - 2 * kHaloBytes) / ((size_t)BN * 128));
     if (P.bstages > 8) P.bstages = 8;
   } else {
-    P.stages = (int)((200 * 1024 - b_bytes) / kHaloBytes);
-    if (P.stages > 4) P.stages = 4;
+    // thin output tiles (BN <= 32): two CTAs per SM when the weights leave room for >= 3 stages in half of the shared memory
+    size_t budget = 200 * 1024;
+    if (BN <= 32 && b_bytes + 3 * kHaloBytes <= 100 * 1024) budget = 100 * 1024;
+    P.stages = (int)((budget - b_bytes) / kHaloBytes);
+    if (P.stages > (P.cb == kChunk ? 4 : 6)) P.stages = P.cb == kChunk ? 4 : 6;     // thin boxes are latency-bound: more in flight
   }
   P.n_mma = p->cout_pad < BN ? p->cout_pad : BN;
   P.c_eff = (p->out.dtype != DN_F32 && p->out_pad_ok) ? (p->out.C + 7) / 8 * 8 : p->out.C;
@@ -1126,6 +1444,8 @@ int dn_igemm_halo(const dn_igemm* p, const int* wt, cudaStream_t st) {
   P.act = p->act;
   P.accumulate = p->accumulate;
   P.out_scale = p->out_scale;
+  P.dbg = g_tc_dbg;
+  { const char* e = getenv("DN_TC_FLAGS"); P.dbg_flags = e ? atoi(e) : 0; }
   switch (BN) {
     case 256: return launch_halo<256>(P, st);
     case 128: return launch_halo<128>(P, st);
@@ -1135,11 +1455,9 @@ int dn_igemm_halo(const dn_igemm* p, const int* wt, cudaStream_t st) {
   }
 }
 
-unsigned long long* g_tc_dbg = nullptr;
-
 }  // namespace
 
-// debug: device buffer of 8 counters (cycles summed over CTAs): [0] producer wait-empty, [1] producer total,
+// debug: device buffer of 16 counters (slots 8..14: the same roles of the weight-gradient kernel) (cycles summed over CTAs): [0] producer wait-empty, [1] producer total,
 // [2] MMA wait-full, [3] MMA wait-tmem-empty, [4] MMA total, [5] epilogue wait-tmem-full, [6] epilogue drain+store
 DN_EXPORT int dn_tc_set_debug(void* device_counters) {
   g_tc_dbg = (unsigned long long*)device_counters;
@@ -1188,8 +1506,9 @@ int dn_igemm_tc(const dn_igemm* p, cudaStream_t st) {
   memset(&P, 0, sizeof(P));
   const int BN = pick_bn(p->cout_pad);
   choose_box(p->out.N, p->out.H, p->out.W, kRows, P.wb, P.hb, P.nb);
+  P.cb = pick_cb(p->in[0].C);
   for (int s = 0; s < p->nsrc; ++s) {
-    int e = make_view_map(&P.tmA[s], p->in[s], P.wb, P.hb, P.nb);
+    int e = make_view_map(&P.tmA[s], p->in[s], P.wb, P.hb, P.nb, P.cb);
     if (e) return e;
   }
   {
@@ -1213,15 +1532,15 @@ int dn_igemm_tc(const dn_igemm* p, cudaStream_t st) {
   P.ntaps = p->ntaps;
   P.nsrc = p->nsrc;
   const int Cin = p->in[0].C;
-  P.kchunks = (Cin + kChunk - 1) / kChunk;
-  int rem = Cin - (P.kchunks - 1) * kChunk;
+  P.kchunks = (Cin + P.cb - 1) / P.cb;
+  int rem = Cin - (P.kchunks - 1) * P.cb;
   P.last_ksteps = (rem + 15) / 16;
   P.tilesW = (p->out.W + P.wb - 1) / P.wb;
   P.tilesH = (p->out.H + P.hb - 1) / P.hb;
   P.tilesN = (p->out.N + P.nb - 1) / P.nb;
   P.ntile_n = (p->cout_pad + BN - 1) / BN;
   P.num_tiles = P.tilesW * P.tilesH * P.tilesN * P.ntile_n;
-  const uint32_t stage_bytes = kRows * 128 + BN * 128;
+  const uint32_t stage_bytes = kRows * 2 * P.cb + BN * 128;
   P.stages = (int)((200 * 1024) / stage_bytes);
   if (P.stages > 8) P.stages = 8;
   P.n_mma = p->cout_pad < BN ? p->cout_pad : BN;
@@ -1277,12 +1596,19 @@ int dn_wgrad_tc(const dn_wgrad* p, cudaStream_t st) {
   P.halo = halo ? 1 : 0;
   if (halo) { P.wb = 8; P.hb = 8; P.nb = 1; }
   else choose_box(P0.N, P0.H, P0.W, KPX, P.wb, P.hb, P.nb);
+  const bool wg5 = []() { const char* e = getenv("DN_WGRAD_5D"); return !(e && e[0] == '0'); }();
+  P.p5 = (wg5 && P0.C > 64 && P0.C % 128 == 0) ? 1 : 0;
   for (int s = 0; s < p->nsrc; ++s) {
-    int e = make_view_map(&P.tmP[s], p->p[s], P.wb, P.hb, P.nb);
+    int e = P.p5 ? make_view_map5(&P.tmP[s], p->p[s], P.wb, P.hb, P.nb, 2) : make_view_map(&P.tmP[s], p->p[s], P.wb, P.hb, P.nb);
     if (e) return e;
   }
+  // thin x (<= 32 channels in a single 64-wide cq tile): 32- / 16-channel rows, see thin_cb()
+  P.cbq = (p->cq_pad <= 64) ? pick_cb(p->q.C) : kChunk;
   {
-    int e = halo ? make_view_map(&P.tmQ, p->q, 16, 10, 1) : make_view_map(&P.tmQ, p->q, P.wb, P.hb, P.nb);
+    const int bnq = p->cq_pad >= 256 ? 256 : (p->cq_pad >= 128 ? 128 : 64);
+    P.q5 = (wg5 && !halo && bnq > 64 && p->q.C % bnq == 0) ? 1 : 0;
+    int e = P.q5 ? make_view_map5(&P.tmQ, p->q, P.wb, P.hb, P.nb, bnq / 64)
+                 : (halo ? make_view_map(&P.tmQ, p->q, 16, 10, 1, P.cbq) : make_view_map(&P.tmQ, p->q, P.wb, P.hb, P.nb, P.cbq));
     if (e) return e;
   }
   for (int t = 0; t < p->ntaps; ++t) {
@@ -1304,7 +1630,7 @@ int dn_wgrad_tc(const dn_wgrad* p, cudaStream_t st) {
     if (n16 < BNQ) P.n_mma = n16;
   }
   // taps that share one dy tile in a CTA: bounded by TMEM columns (512) and by keeping >= 3 pipeline stages
-  const uint32_t a_bytes = 2 * KPX * 128, b_bytes = (BNQ / 64) * KPX * 128;
+  const uint32_t a_bytes = 2 * KPX * 128, b_bytes = (BNQ / 64) * KPX * 2 * P.cbq;
   int tpc = 512 / P.n_mma;
   int by_smem = (int)((64 * 1024 - a_bytes) / b_bytes);
   if (by_smem < 1) by_smem = 1;
@@ -1350,7 +1676,7 @@ int dn_wgrad_tc(const dn_wgrad* p, cudaStream_t st) {
   }
   P.ptiles_per_split = (P.num_ptiles + splits - 1) / splits;
   P.splits = (P.num_ptiles + P.ptiles_per_split - 1) / P.ptiles_per_split;
-  const uint32_t stage_bytes = a_bytes + (halo ? (uint32_t)(BNQ / 64) * 16 * 10 * 128 : (uint32_t)P.tpc * b_bytes);
+  const uint32_t stage_bytes = a_bytes + (halo ? (uint32_t)(BNQ / 64) * 16 * 10 * 2 * P.cbq : (uint32_t)P.tpc * b_bytes);
   P.stages = (int)((200 * 1024) / stage_bytes);
   if (P.stages > 8) P.stages = 8;
   P.m64 = 0;
@@ -1362,6 +1688,7 @@ int dn_wgrad_tc(const dn_wgrad* p, cudaStream_t st) {
   P.dw = p->dw;
   P.cp = P0.C; P.cq = p->q.C; P.cp_pad = p->cp_pad; P.cq_pad = p->cq_pad;
   P.scale = p->scale;
+  P.dbg = g_tc_dbg;
   const int items = out_tiles * P.splits;
   P.num_items = items;
   switch (BNQ) {
