@@ -42,11 +42,16 @@ extern "C" {
 #define DN_MAX_TAPS 160
 #define DN_MAX_SRC 8
 
-/* NHWC view of an activation tensor (strides in ELEMENTS of `dtype`; channel stride is 1). */
+/* NHWC view of an activation tensor (strides in ELEMENTS of `dtype`; channel stride is 1).
+ * c_ext (0 = C): channels readable from `ptr` inside one pixel record, c_ext >= C.  Channels [C, c_ext) hold FINITE values
+ * (zero padding of the buffer or the neighbouring slices of a concatenation buffer) that a gather-convolution may fetch as
+ * padding -- they meet zero rows of the packed weights.  Lets the TMA maps of 17- / 97- / 193-channel tensors declare whole
+ * 32- / 64-channel rows instead of partially out-of-bounds ones (which the TMA unit fills at a fraction of its row rate). */
 typedef struct dn_view {
   void* ptr;
   int32_t dtype;
   int32_t N, H, W, C;
+  int32_t c_ext;
   int64_t sN, sH, sW;
 } dn_view;
 
@@ -82,7 +87,11 @@ typedef struct dn_igemm {
                                 kernel may overwrite (lets the 16-byte vector epilogue serve odd channel counts) */
   void* out2;                /* optional second copy of the result (same N/H/W/C and strides as `out`) ... */
   int32_t out2_dtype;        /* ... in this 16-bit dtype: the bf16 image a later weight-gradient GEMM consumes */
-  int32_t pad_;
+  int32_t nphase;            /* 0 / 1: one output view.  n > 1 (the output phases of a stride-2 nn.ConvTranspose2d,
+                                models/Disp_vgg_BN.py:92-104, as ONE launch): n sub-problems that share `in`, the weights and the
+                                geometry of `out`; sub-problem i uses taps [i * ntaps / n, (i + 1) * ntaps / n) and writes at
+                                out.ptr (and out2) + phase_off[i] elements */
+  int64_t phase_off[4];
 } dn_igemm;
 
 /*

@@ -16,7 +16,7 @@ MAX_TAPS, MAX_SRC = 160, 8
 
 class DnView(C.Structure):
     _fields_ = [('ptr', C.c_void_p), ('dtype', C.c_int32), ('N', C.c_int32), ('H', C.c_int32), ('W', C.c_int32),
-                ('C', C.c_int32), ('sN', C.c_int64), ('sH', C.c_int64), ('sW', C.c_int64)]
+                ('C', C.c_int32), ('c_ext', C.c_int32), ('sN', C.c_int64), ('sH', C.c_int64), ('sW', C.c_int64)]
 
 
 class DnTap(C.Structure):
@@ -28,7 +28,7 @@ class DnIgemm(C.Structure):
                 ('w_dtype', C.c_int32), ('cin_pad', C.c_int32), ('cout_pad', C.c_int32), ('bias', C.c_void_p),
                 ('act', C.c_int32), ('accumulate', C.c_int32), ('stride', C.c_int32), ('ntaps', C.c_int32),
                 ('taps', DnTap * MAX_TAPS), ('out_scale', C.c_float), ('out_pad_ok', C.c_int32), ('out2', C.c_void_p),
-                ('out2_dtype', C.c_int32), ('pad_', C.c_int32)]
+                ('out2_dtype', C.c_int32), ('nphase', C.c_int32), ('phase_off', C.c_int64 * 4)]
 
 
 class DnWgrad(C.Structure):

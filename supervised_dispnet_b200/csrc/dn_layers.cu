@@ -474,12 +474,28 @@ static int igemm_check(const dn_igemm* p) {
   for (int s = 0; s < p->nsrc; ++s)
     if (!p->in[s].ptr || p->in[s].C > p->cin_pad || p->in[s].N != p->out.N) return DN_E_ARG;
   if (p->out.C > p->cout_pad) return DN_E_ARG;
+  if (p->nphase < 0 || p->nphase > 4 || (p->nphase > 1 && p->ntaps % p->nphase != 0)) return DN_E_ARG;
   return 0;
 }
 
 int dn_igemm_generic(const dn_igemm* p, cudaStream_t st) {
   long long M = (long long)p->out.N * p->out.H * p->out.W;
   if (M == 0) return 0;
+  if (p->nphase > 1) {      // merged output phases: one single-view problem per phase
+    const int tph = p->ntaps / p->nphase;
+    const int esz = dn_esize(p->out.dtype);
+    for (int i = 0; i < p->nphase; ++i) {
+      dn_igemm q = *p;
+      q.nphase = 0;
+      q.ntaps = tph;
+      for (int t = 0; t < tph; ++t) q.taps[t] = p->taps[i * tph + t];
+      q.out.ptr = (char*)p->out.ptr + p->phase_off[i] * esz;
+      if (p->out2) q.out2 = (char*)p->out2 + p->phase_off[i] * 2;
+      int e = dn_igemm_generic(&q, st);
+      if (e) return e;
+    }
+    return 0;
+  }
   if (p->out.C <= 16) {
     dim3 grid((unsigned)((M + 255) / 256), (unsigned)((p->out.C + 15) / 16));
     igemm_generic_kernel<256, 16><<<grid, 256, 0, st>>>(*p);

@@ -405,6 +405,10 @@ struct IgemmTcParams {
   int cb;             // channels per A row in shared memory: 64 (128-byte rows), 32 or 16 (thin tensors, one chunk)
   int wb, hb, nb;     // pixel box (wb*hb*nb == 128)
   int tilesW, tilesH, tilesN, ntile_n, num_tiles;
+  int nph, tph;       // merged output phases: tile index = ((((ph * tilesN + tn) * tilesH + th) * tilesW + tw) * ntile_n + nt; phase ph uses
+                      // taps [ph * tph, (ph + 1) * tph) and writes at out + phase_off[ph]
+  long long phase_off[4];
+  int step[5];        // gridDim.x as mixed-radix digits (nt, tw, th, tn, ph): tiles advance by carries, not by divisions
   int stages;
   int n_mma;          // MMA N actually issued (multiple of 16, <= BN)
   int c_eff;          // output channels the epilogue may write (out.C, or rounded up to 8 when padding may be overwritten)
@@ -417,6 +421,27 @@ struct IgemmTcParams {
   float out_scale;
   unsigned long long* dbg;   // optional per-role cycle counters (dn_tc_set_debug)
 };
+
+// position of a persistent CTA's current tile in the (nt, tw, th, tn, ph) index space
+struct TilePos { int nt, tw, th, tn, ph; };
+__device__ __forceinline__ void tile_init(TilePos& t, const IgemmTcParams& p, int tile) {
+  t.nt = tile % p.ntile_n; tile /= p.ntile_n;
+  t.tw = tile % p.tilesW; tile /= p.tilesW;
+  t.th = tile % p.tilesH; tile /= p.tilesH;
+  t.tn = tile % p.tilesN;
+  t.ph = tile / p.tilesN;
+}
+__device__ __forceinline__ void tile_next(TilePos& t, const IgemmTcParams& p) {
+  t.nt += p.step[0];
+  int c = t.nt >= p.ntile_n ? 1 : 0; t.nt -= c * p.ntile_n;
+  t.tw += p.step[1] + c;
+  c = t.tw >= p.tilesW ? 1 : 0; t.tw -= c * p.tilesW;
+  t.th += p.step[2] + c;
+  c = t.th >= p.tilesH ? 1 : 0; t.th -= c * p.tilesH;
+  t.tn += p.step[3] + c;
+  c = t.tn >= p.tilesN ? 1 : 0; t.tn -= c * p.tilesN;
+  t.ph += p.step[4] + c;
+}
 
 template <int BN>
 __global__ void __launch_bounds__(320, 1) igemm_tc_kernel(const __grid_constant__ IgemmTcParams p) {
@@ -466,14 +491,13 @@ __global__ void __launch_bounds__(320, 1) igemm_tc_kernel(const __grid_constant_
     int stage = 0; uint32_t phase = 0;
     long long dbg_acc0 = 0;
     const long long tstart = p.dbg ? clock64() : 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const int nt = tile % p.ntile_n;
-      int m = tile / p.ntile_n;
-      const int tw = m % p.tilesW; m /= p.tilesW;
-      const int th = m % p.tilesH;
-      const int tn = m / p.tilesH;
-      const int w0 = tw * p.wb, h0 = th * p.hb, n0 = tn * p.nb;
-      for (int t = 0; t < p.ntaps; ++t) {
+    TilePos tp;
+    tile_init(tp, p, blockIdx.x);
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, tile_next(tp, p)) {
+      const int nt = tp.nt;
+      const int w0 = tp.tw * p.wb, h0 = tp.th * p.hb, n0 = tp.tn * p.nb;
+      const int tbeg = tp.ph * p.tph;
+      for (int t = tbeg; t < tbeg + p.tph; ++t) {
         const TcTap tap = p.taps[t];
         for (int kc = 0; kc < p.kchunks; ++kc) {
           const long long t0 = p.dbg ? clock64() : 0;
@@ -506,7 +530,7 @@ __global__ void __launch_bounds__(320, 1) igemm_tc_kernel(const __grid_constant_
     const uint64_t stage_inc = (uint64_t)(STAGE_BYTES >> 4);
     uint64_t ad = ad_base, bd = bd_base;
     const uint32_t idesc = p.idesc;
-    const int kchunks = p.kchunks, last_ks = p.last_ksteps, full_ks = p.cb / 16, k_iters_m1 = p.ntaps * p.kchunks - 1;
+    const int kchunks = p.kchunks, last_ks = p.last_ksteps, full_ks = p.cb / 16, k_iters_m1 = p.tph * p.kchunks - 1;
     long long dbg_full = 0, dbg_te = 0;
     const long long tstart = p.dbg ? clock64() : 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -549,13 +573,11 @@ __global__ void __launch_bounds__(320, 1) igemm_tc_kernel(const __grid_constant_
     const float out_scale = p.out_scale;
     float breg[CH];
     int nt_loaded = -1;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const int nt = tile % p.ntile_n;
-      int m = tile / p.ntile_n;
-      const int tw = m % p.tilesW; m /= p.tilesW;
-      const int th = m % p.tilesH;
-      const int tn = m / p.tilesH;
-      const int w = tw * p.wb + wi, h = th * p.hb + hi, n = tn * p.nb + ni;
+    TilePos tp;
+    tile_init(tp, p, blockIdx.x);
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, tile_next(tp, p)) {
+      const int nt = tp.nt;
+      const int w = tp.tw * p.wb + wi, h = tp.th * p.hb + hi, n = tp.tn * p.nb + ni;
       const bool valid = (w < p.out.W) && (h < p.out.H) && (n < p.out.N);
       const int co0 = nt * BN;
       float* bs = bias_s + acc * BN;
@@ -569,7 +591,7 @@ __global__ void __launch_bounds__(320, 1) igemm_tc_kernel(const __grid_constant_
         for (int c = et; c < BN; c += EW * 32) bs[c] = (p.bias && co0 + c < p.out.C) ? p.bias[co0 + c] : 0.f;
         asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");
       }
-      const size_t eoff = (size_t)(dn_off(p.out, n, h, w) + co0);
+      const size_t eoff = (size_t)(dn_off(p.out, n, h, w) + co0 + p.phase_off[tp.ph]);
       uint8_t* optr = (uint8_t*)p.out.ptr + eoff * esz;
       const long long te0 = p.dbg ? clock64() : 0;
       mbar_wait(&tfull_bar[acc], acc_phase);
@@ -649,6 +671,7 @@ struct HaloParams {
   int act, accumulate;
   float out_scale;
   unsigned long long* dbg;   // optional per-role cycle counters (dn_tc_set_debug), same slots as igemm_tc_kernel
+  int step[3];               // gridDim.x as mixed-radix digits (tw, th, n): tiles advance by carries, not by divisions
   int dbg_flags;             // experiments (DN_TC_FLAGS): 1 = epilogue neither reads TMEM nor stores, 2 = epilogue waits with nanosleep back-off
 };
 
@@ -786,17 +809,23 @@ __global__ void __launch_bounds__(320, BN <= 32 ? 2 : 1) igemm_halo_kernel(const
     int stage = 0; uint32_t phase = 0;
     long long dbg_acc0 = 0;
     const long long tstart = p.dbg ? clock64() : 0;
+    int tw, th, n0;
+    { int m = blockIdx.x; tw = m % p.tilesW; m /= p.tilesW; th = m % p.tilesH; n0 = m / p.tilesH; }
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      int m = tile;
-      const int tw = m % p.tilesW; m /= p.tilesW;
-      const int th = m % p.tilesH;
-      const int n0 = m / p.tilesH;
+      const int tw_c = tw, th_c = th, n0_c = n0;
+      {     // next tile of this CTA
+        tw += p.step[0];
+        int c = tw >= p.tilesW ? 1 : 0; tw -= c * p.tilesW;
+        th += p.step[1] + c;
+        c = th >= p.tilesH ? 1 : 0; th -= c * p.tilesH;
+        n0 += p.step[2] + c;
+      }
       for (int kc = 0; kc < p.kchunks; ++kc) {
         const long long t0 = p.dbg ? clock64() : 0;
         mbar_wait(&empty_bar[stage], phase ^ 1);
         if (p.dbg) dbg_acc0 += clock64() - t0;
         mbar_expect_tx_e(&full_bar[stage], halo_bytes);
-        tma_load_4d_e(smem_a + (size_t)stage * halo_bytes, &p.tmA, &full_bar[stage], kc * CB, tw * 8 - 1, th * 16 - 1, n0);
+        tma_load_4d_e(smem_a + (size_t)stage * halo_bytes, &p.tmA, &full_bar[stage], kc * CB, tw_c * 8 - 1, th_c * 16 - 1, n0_c);
         if (++stage == stages) { stage = 0; phase ^= 1; }
       }
     }
@@ -869,14 +898,20 @@ __global__ void __launch_bounds__(320, BN <= 32 ? 2 : 1) igemm_halo_kernel(const
       for (int c = et; c < BN; c += EW * 32) bias_s[c] = (p.bias && c < p.out.C) ? p.bias[c] : 0.f;
       asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");
     }
+    int tw, th, n;
+    { int m = blockIdx.x; tw = m % p.tilesW; m /= p.tilesW; th = m % p.tilesH; n = m / p.tilesH; }
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      int m = tile;
-      const int tw = m % p.tilesW; m /= p.tilesW;
-      const int th = m % p.tilesH;
-      const int n = m / p.tilesH;
       const int w = tw * 8 + wi, h = th * 16 + hi;
+      const int n_c = n;
+      {     // next tile of this CTA
+        tw += p.step[0];
+        int c = tw >= p.tilesW ? 1 : 0; tw -= c * p.tilesW;
+        th += p.step[1] + c;
+        c = th >= p.tilesH ? 1 : 0; th -= c * p.tilesH;
+        n += p.step[2] + c;
+      }
       const bool valid = (w < p.out.W) && (h < p.out.H);
-      const size_t eoff = (size_t)dn_off(p.out, n, h, w);
+      const size_t eoff = (size_t)dn_off(p.out, n_c, h, w);
       uint8_t* optr = (uint8_t*)p.out.ptr + eoff * esz;
       const long long te0 = p.dbg ? clock64() : 0;
       if (p.dbg_flags & 2) mbar_wait_sleep(&tfull_bar[acc], acc_phase); else mbar_wait(&tfull_bar[acc], acc_phase);
@@ -1222,7 +1257,12 @@ CUtensorMapSwizzle swizzle_of(int cb) {
 int make_view_map(CUtensorMap* tm, const dn_view& v, int wb, int hb, int nb, int cb = kChunk) {
   auto enc = get_encode();
   if (!enc) return DN_E_UNSUPPORTED;
-  cuuint64_t dims[4] = {(cuuint64_t)v.C, (cuuint64_t)v.W, (cuuint64_t)v.H, (cuuint64_t)v.N};
+  // channel extent: whole box rows where the view says the bytes behind its channels are readable padding (dn_view.c_ext) -- a box
+  // row that is partially out of bounds takes the TMA unit ~7 cycles instead of ~2.6 (tools/ubench_tc.cu)
+  int ext = (v.C + cb - 1) / cb * cb;
+  const int readable = v.c_ext > v.C ? v.c_ext : v.C;
+  if (ext > readable) ext = readable;
+  cuuint64_t dims[4] = {(cuuint64_t)ext, (cuuint64_t)v.W, (cuuint64_t)v.H, (cuuint64_t)v.N};
   cuuint64_t strides[3] = {(cuuint64_t)v.sW * 2, (cuuint64_t)v.sH * 2, (cuuint64_t)v.sN * 2};
   cuuint32_t box[4] = {(cuuint32_t)cb, (cuuint32_t)wb, (cuuint32_t)hb, (cuuint32_t)nb};
   cuuint32_t es[4] = {1, 1, 1, 1};
@@ -1332,7 +1372,7 @@ const bool g_halo_ring = []() { const char* e = getenv("DN_HALO_RING"); return !
 // taps form a subset of the 3x3 neighbourhood (all nine for a 3x3 convolution, a 2x2 corner for one output phase of a
 // 4x4 / stride-2 transposed convolution): wt[kh * 3 + kw] = packed-weight index, -1 where the tap is absent
 bool halo_taps(const dn_igemm* p, int* wt) {
-  if (p->ntaps > 9 || p->ntaps < 3 || p->nsrc != 1 || p->stride != 1) return false;
+  if (p->ntaps > 9 || p->ntaps < 3 || p->nsrc != 1 || p->stride != 1 || p->nphase > 1) return false;
   bool seen[9] = {false};
   for (int i = 0; i < 9; ++i) wt[i] = -1;
   for (int t = 0; t < p->ntaps; ++t) {
@@ -1378,7 +1418,11 @@ int launch_halo_cb(const HaloParams& P, cudaStream_t st) {
   }
   const int ctas = ((BN <= 32 && smem <= 110 * 1024) ? 2 : 1) * dn_num_sms();
   int grid = P.num_tiles < ctas ? P.num_tiles : ctas;
-  dn_launch(igemm_halo_kernel<BN, CB>, dim3(grid), dim3(320), smem, st, P);
+  HaloParams Q = P;
+  Q.step[0] = grid % P.tilesW;
+  Q.step[1] = (grid / P.tilesW) % P.tilesH;
+  Q.step[2] = grid / P.tilesW / P.tilesH;
+  dn_launch(igemm_halo_kernel<BN, CB>, dim3(grid), dim3(320), smem, st, Q);
   DN_CHECK_LAUNCH();
   return 0;
 }
@@ -1483,6 +1527,7 @@ DN_EXPORT int dn_tc_available(void) {
 
 DN_EXPORT int dn_igemm_tc_supported(const dn_igemm* p) {
   if (!p || p->stride != 1 || p->ntaps > kMaxTcTaps || p->ntaps < 1) return 0;
+  if (p->nphase < 0 || p->nphase > 4 || (p->nphase > 1 && (p->ntaps % p->nphase) != 0)) return 0;
   if (p->w_dtype != DN_F16 && p->w_dtype != DN_BF16) return 0;
   if (p->out.dtype != DN_F32) {   // 16-byte vector epilogue
     if (!view_tma_ok(p->out)) return 0;
@@ -1504,8 +1549,21 @@ int dn_igemm_tc(const dn_igemm* p, cudaStream_t st) {
   }
   IgemmTcParams P;
   memset(&P, 0, sizeof(P));
-  const int BN = pick_bn(p->cout_pad);
+  int BN = pick_bn(p->cout_pad);
   choose_box(p->out.N, p->out.H, p->out.W, kRows, P.wb, P.hb, P.nb);
+  {
+    // few pixel tiles (the 4x13 ... 8x26 layers): a narrower N tile can put more SMs to work.  cost = waves x tensor-pipe cycles of
+    // one 128 x BN x 16 MMA (tools/ubench_tc.cu: 55 / 70 / 128 cycles for N = 64 / 128 / 256)
+    const long long m_tiles = (long long)((p->out.W + P.wb - 1) / P.wb) * ((p->out.H + P.hb - 1) / P.hb) * ((p->out.N + P.nb - 1) / P.nb) *
+                              (p->nphase > 1 ? p->nphase : 1);
+    const int sms = dn_num_sms();
+    auto cost = [&](int bn) {
+      const long long tiles = m_tiles * ((p->cout_pad + bn - 1) / bn);
+      return (double)((tiles + sms - 1) / sms) * (bn >= 256 ? 128.0 : bn >= 128 ? 70.0 : 55.0) * ((p->cout_pad + bn - 1) / bn) /
+             (double)((p->cout_pad + bn - 1) / bn);
+    };
+    while (BN > 64 && (p->cout_pad % (BN / 2)) == 0 && cost(BN / 2) < cost(BN)) BN /= 2;
+  }
   P.cb = pick_cb(p->in[0].C);
   for (int s = 0; s < p->nsrc; ++s) {
     int e = make_view_map(&P.tmA[s], p->in[s], P.wb, P.hb, P.nb, P.cb);
@@ -1539,7 +1597,16 @@ int dn_igemm_tc(const dn_igemm* p, cudaStream_t st) {
   P.tilesH = (p->out.H + P.hb - 1) / P.hb;
   P.tilesN = (p->out.N + P.nb - 1) / P.nb;
   P.ntile_n = (p->cout_pad + BN - 1) / BN;
-  P.num_tiles = P.tilesW * P.tilesH * P.tilesN * P.ntile_n;
+  P.nph = p->nphase > 1 ? p->nphase : 1;
+  P.tph = p->ntaps / P.nph;
+  for (int i = 0; i < 4; ++i) P.phase_off[i] = (p->nphase > 1 && i < p->nphase) ? p->phase_off[i] : 0;
+  P.num_tiles = P.tilesW * P.tilesH * P.tilesN * P.ntile_n * P.nph;
+  {
+    int g = P.num_tiles < dn_num_sms() ? P.num_tiles : dn_num_sms();      // = the grid size of launch_igemm
+    const int radix[4] = {P.ntile_n, P.tilesW, P.tilesH, P.tilesN};
+    for (int i = 0; i < 4; ++i) { P.step[i] = g % radix[i]; g /= radix[i]; }
+    P.step[4] = g;
+  }
   const uint32_t stage_bytes = kRows * 2 * P.cb + BN * 128;
   P.stages = (int)((200 * 1024) / stage_bytes);
   if (P.stages > 8) P.stages = 8;

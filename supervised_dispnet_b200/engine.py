@@ -70,7 +70,11 @@ class Buf:
 
     def __init__(self, N, H, W, Cc, dtype, device, zero=True, storage=None):
         self.N, self.H, self.W, self.C = N, H, W, Cc
-        self.Cp = _ru(Cc, 8)
+        # channel pitch: whole TMA rows for the odd channel counts (the 3-channel image, the 17- / 97- / 193- / 385-channel
+        # concatenation buffers): 16 / 32 / 64-channel rows below 64 channels, multiples of 64 above; everything else is
+        # already a multiple of 8.  The padding is zero-filled once and never written.
+        self.Cp = _pitch(Cc)
+        self.readable_pad = storage is None and zero
         self.dtype = dtype
         if storage is not None:     # carve from a shared scratch tensor
             self.t = storage[:N * H * W * self.Cp * torch.empty((), dtype=dtype).element_size()].view(dtype).view(N, H, W, self.Cp)
@@ -144,8 +148,12 @@ class View:
     def dn(self):
         if self._dn is None:
             es = self.buf.t.element_size()
+            # c_ext: what follows the view's channels inside the pixel record is zero padding of the buffer or other slices of a
+            # concatenation buffer -- finite values a gather-convolution may read against zero weight rows (dn_view.c_ext);
+            # scratch-backed buffers are not zero-initialised, so they declare nothing beyond C
+            c_ext = (self.buf.Cp - self.c0) if (self.buf.readable_pad and self.sW % self.buf.Cp == 0) else self.C
             self._dn = L.DnView(self.buf.t.data_ptr() + (self.off + self.c0) * es, _DT[self.buf.dtype], self.N, self.H,
-                                self.W, self.C, self.sN, self.sH, self.sW)
+                                self.W, self.C, c_ext, self.sN, self.sH, self.sW)
         return self._dn
 
     def ref(self):
@@ -175,6 +183,13 @@ class View:
         idx_w = torch.arange(self.W, device=t.device).view(1, 1, -1, 1) * self.sW
         idx_c = torch.arange(self.C, device=t.device).view(1, 1, 1, -1)
         return t[idx_n + idx_h + idx_w + idx_c + self.off + self.c0].permute(0, 3, 1, 2).float().contiguous()
+
+
+def _pitch(Cc):
+    """Channel pitch of a buffer with Cc channels (see Buf)."""
+    if Cc % 8 != 0 and os.environ.get('DISPNET_B200_PAD_PITCH', '1') != '0':
+        return 16 if Cc <= 16 else 32 if Cc <= 32 else _ru(Cc, 64)
+    return _ru(Cc, 8)
 
 
 def _i32arr(vals):
@@ -392,6 +407,9 @@ class ConvOp(Op):
 
     def _build_fwd(self, plan):
         built = []
+        merged = self._build_fwd_merged(plan)
+        if merged is not None:
+            return merged
         for pr in self.fwd_probs:
             o2 = None
             if self.out_shadow is not None:
@@ -404,6 +422,33 @@ class ConvOp(Op):
                           pr['stride'], taps, out2=o2)
             built.append((p, _backend('igemm', p), _igemm_flops(p) / div))
         return built
+
+    def _build_fwd_merged(self, plan):
+        """The output phases of a transposed convolution as ONE gather-convolution launch (dn_igemm.nphase): same input view and
+        weights, the taps ordered phase by phase, every phase writing its 2x2 sub-lattice of `out` through an element offset.  Four
+        13-tile launches of upconv4 become one 104-tile launch; None when the phases differ in extent or the tensor-core kernel
+        does not take the problem."""
+        prs = self.fwd_probs
+        if not (self.transposed and len(prs) > 1 and tc_enabled() and os.environ.get('DISPNET_B200_MERGE_PHASES', '1') != '0'):
+            return None
+        if len({(pr['out'].H, pr['out'].W, len(pr['taps'])) for pr in prs}) != 1:
+            return None
+        base = prs[0]['out']
+        ins, taps, wdt, div = prs[0]['ins'], [t for pr in prs for t in pr['taps']], plan.prec.act, 1.0
+        if plan.prec.split is not None:
+            ins, taps = _split3_igemm(ins, taps, self.k * self.k, plan.prec.split)
+            wdt, div = plan.prec.split, 3.0
+        if len(taps) > L.MAX_TAPS:
+            return None
+        o2 = self.out_shadow.phase(*prs[0]['phase']) if self.out_shadow is not None else None
+        p = _mk_igemm(ins, base, self.wp, wdt, self.cin_pad, self.cout_pad, None, self.act, False, 1, taps, out2=o2)
+        p.nphase = len(prs)
+        for i, pr in enumerate(prs):
+            p.phase_off[i] = pr['out'].off - base.off
+        if _backend('igemm', p) != 1:
+            return None
+        flops = _igemm_flops(p)       # (ntaps counts every phase's taps, out = one phase's pixels)
+        return [(p, 1, flops / div)]
 
     # ---- weight (un)packing is batched over all layers of the plan: one dn_pack_jobs launch each (Plan._run_jobs)
     def jobs(self, plan, which):
@@ -924,7 +969,7 @@ class Plan:
 
     def scratch_buf(self, N, H, W, Cc, dtype):
         """Buf carved from the plan's shared scratch storage (valid only between consecutive launches)."""
-        need = N * H * W * _ru(Cc, 8) * 4
+        need = N * H * W * _pitch(Cc) * 4
         if self._scratch is None or self._scratch.numel() < need:
             raise RuntimeError('scratch storage too small')
         return Buf(N, H, W, Cc, dtype, self.device, storage=self._scratch)

@@ -437,7 +437,7 @@ def test_head_conv_mma_vs_torch(C, H, W, xdt):
 
     def view(t, dt):
         n, h, w_, c = t.shape
-        return L.DnView(t.data_ptr(), dt, n, h, w_, c, h * w_ * c, w_ * c, c)
+        return L.DnView(t.data_ptr(), dt, n, h, w_, c, 0, h * w_ * c, w_ * c, c)
     st = L.stream_ptr()
     vx, vz = view(x, ddt), view(z, L.DN_F32)
     L.call('dn_head_conv_fwd', C_.byref(vx), L.ptr(w), L.ptr(b), C_.byref(vz), st)
@@ -491,7 +491,7 @@ def test_bn_kernels_vs_torch(C, H, W, pool, crop):
 
     def view(t, dt, w=None):
         n, h, wb, c = t.shape
-        return L.DnView(t.data_ptr(), dt, n, h, w or wb, c, h * wb * c, wb * c, c)
+        return L.DnView(t.data_ptr(), dt, n, h, w or wb, c, 0, h * wb * c, wb * c, c)
     y = yb[:, :, :W]
     gamma, beta = torch.rand(C, device=dev) + 0.5, torch.randn(C, device=dev) * 0.2
     rm, rv = torch.zeros(C, device=dev), torch.ones(C, device=dev)
@@ -565,7 +565,7 @@ def test_bn_residual_kernels_vs_torch(C, H, W, acc):
 
     def view(t, dt):
         n, h, w, c = t.shape
-        return L.DnView(t.data_ptr(), dt, n, h, w, c, h * w * c, w * c, c)
+        return L.DnView(t.data_ptr(), dt, n, h, w, c, 0, h * w * c, w * c, c)
     gamma, beta = torch.rand(C, device=dev) + 0.5, torch.randn(C, device=dev) * 0.2
     rm, rv = torch.zeros(C, device=dev), torch.ones(C, device=dev)
     mi, ss = torch.zeros(2 * C, device=dev), torch.zeros(2 * C, device=dev)

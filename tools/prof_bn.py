@@ -19,7 +19,7 @@ flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 def view(t):
     n, h, w, c = t.shape
     dt = {torch.float32: L.DN_F32, torch.float16: L.DN_F16, torch.bfloat16: L.DN_BF16}[t.dtype]
-    return L.DnView(t.data_ptr(), dt, n, h, w, c, h * w * c, w * c, c)
+    return L.DnView(t.data_ptr(), dt, n, h, w, c, 0, h * w * c, w * c, c)
 
 
 def timeit(fn, reps=5):

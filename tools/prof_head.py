@@ -12,7 +12,7 @@ flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
 def view(t, dt):
     n, h, w, c = t.shape
-    return L.DnView(t.data_ptr(), dt, n, h, w, c, h * w * c, w * c, c)
+    return L.DnView(t.data_ptr(), dt, n, h, w, c, 0, h * w * c, w * c, c)
 
 
 def timeit(fn, reps=5):
