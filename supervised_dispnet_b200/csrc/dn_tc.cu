@@ -327,17 +327,17 @@ __device__ __forceinline__ void stage_issue(int ks, uint32_t d_tmem, uint64_t ad
 }
 
 // Four K steps (64 pixels) of one tap of the weight gradient: A advances by `ka`, B by `kb` 16-byte units per step
-__device__ __forceinline__ void wg_issue4(uint32_t d_tmem, uint64_t ad, uint64_t bd, uint32_t idesc, uint32_t acc0, uint32_t kb) {
+__device__ __forceinline__ void wg_issue4(uint32_t d_tmem, uint64_t ad, uint64_t bd, uint32_t idesc, uint32_t acc0, uint32_t kb, uint32_t ka = 128) {
   asm volatile(
-      "{\n.reg .pred E, A, TR;\n.reg .b64 a, b, kb;\n"
+      "{\n.reg .pred E, A, TR;\n.reg .b64 a, b, ka, kb;\n"
       "elect.sync _|E, 0xffffffff;\n"
       "setp.ne.u32 A, %4, 0;\nsetp.eq.u32 TR, 1, 1;\n"
-      "mov.b64 a, %1;\nmov.b64 b, %2;\ncvt.u64.u32 kb, %5;\n"
+      "mov.b64 a, %1;\nmov.b64 b, %2;\ncvt.u64.u32 kb, %5;\ncvt.u64.u32 ka, %6;\n"
       "@E tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %3, A;\n"
-      "add.u64 a, a, 128;\nadd.u64 b, b, kb;\n@E tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %3, TR;\n"
-      "add.u64 a, a, 128;\nadd.u64 b, b, kb;\n@E tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %3, TR;\n"
-      "add.u64 a, a, 128;\nadd.u64 b, b, kb;\n@E tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %3, TR;\n"
-      "}\n" ::"r"(d_tmem), "l"(ad), "l"(bd), "r"(idesc), "r"(acc0), "r"(kb)
+      "add.u64 a, a, ka;\nadd.u64 b, b, kb;\n@E tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %3, TR;\n"
+      "add.u64 a, a, ka;\nadd.u64 b, b, kb;\n@E tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %3, TR;\n"
+      "add.u64 a, a, ka;\nadd.u64 b, b, kb;\n@E tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %3, TR;\n"
+      "}\n" ::"r"(d_tmem), "l"(ad), "l"(bd), "r"(idesc), "r"(acc0), "r"(kb), "r"(ka)
       : "memory");
 }
 
@@ -679,7 +679,7 @@ struct HaloParams {
 // half of the accumulator columns (a single warp per scheduler is latency-bound: ~1 700 cycles per 128 x 16 tile measured).
 // Thin tiles (BN <= 32) run two CTAs per SM for the same reason -- every role of this kernel is a single latency-bound warp.
 template <int BN, int CB>
-__global__ void __launch_bounds__(320, BN <= 32 ? 2 : 1) igemm_halo_kernel(const __grid_constant__ HaloParams p) {
+__global__ void __launch_bounds__(320, (BN <= 32 || (BN == 64 && CB <= 32)) ? 2 : 1) igemm_halo_kernel(const __grid_constant__ HaloParams p) {
   dn_pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr uint32_t B_BYTES = BN * 128;
@@ -985,6 +985,10 @@ struct WgradTcParams {
   int halo;                // 1: x is fetched once per pixel tile as a (8+2) x 16-pixel halo box, taps are shifted views
   int p5, q5;              // dy / x maps are 5-D (64 ch, W, H, N, channel block): all 64-channel blocks of a stage in ONE TMA
   int cbq;                 // channels per x row in shared memory: 64, or 32 / 16 for thin x (one 64-wide cq tile, n_mma <= cbq)
+  int mstack, cbp;         // thin dy (<= 32 channels), full 3x3: the M dimension holds THREE column-shifted copies of the dy tile
+                           // (cbp = 16 / 32 channels per copy, slot s = dy shifted by s - 1 pixels), x is fetched as an (8+2)-row
+                           // strip and the three MMAs per K step (one per kernel row) produce all nine taps: 12 MMAs per 64 pixels
+                           // instead of 36 (thin weight gradients are bound by the MMA count, ~40 cycles each)
   uint32_t idesc;
   float* dw;
   int cp, cq, cp_pad, cq_pad;
@@ -1023,8 +1027,9 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
   const uint32_t q_rb = (uint32_t)(2 * p.cbq), q_layout = (uint32_t)thin_layout(p.cbq);   // bytes per pixel row of x
   const uint32_t Q_BLK = KPX * q_rb;                     // one [KPX px][cbq ch] block of x
   const uint32_t B_BYTES = (BNQ / 64) * Q_BLK;           // per tap (plain mode)
-  const uint32_t HALO_BLK = 16 * 10 * q_rb;              // one [10 rows][16 px][cbq ch] halo block (halo mode)
-  const uint32_t STAGE_BYTES = A_BYTES + (p.halo ? (uint32_t)(BNQ / 64) * HALO_BLK : (uint32_t)p.tpc * B_BYTES);
+  const uint32_t HALO_BLK = (p.mstack ? 8 : 16) * 10 * q_rb;   // one [10 rows][16 px][cbq ch] halo block (halo mode; 8 px wide when mstack)
+  const uint32_t STAGE_BYTES = A_BYTES + ((p.halo || p.mstack) ? (uint32_t)(BNQ / 64) * HALO_BLK : (uint32_t)p.tpc * B_BYTES);
+  const uint32_t p_rb = (uint32_t)(2 * p.cbp), P_SLOT = KPX * p_rb;       // mstack: bytes per dy pixel row, per shifted copy
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int stages = p.stages;
   uint64_t* full_bar = (uint64_t*)(smem + (size_t)stages * STAGE_BYTES);
@@ -1063,7 +1068,8 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
       const WgItem w = wg_decode(p, item);
       // bytes that really arrive per stage: only the P blocks that exist and the taps of this group are loaded
-      const uint32_t tx_bytes = (uint32_t)p.cp_blocks * BLK_BYTES + (p.halo ? (uint32_t)(BNQ / 64) * HALO_BLK : (uint32_t)w.nt * B_BYTES);
+      const uint32_t tx_bytes = p.mstack ? 3 * P_SLOT + (uint32_t)(BNQ / 64) * HALO_BLK
+                                         : (uint32_t)p.cp_blocks * BLK_BYTES + (p.halo ? (uint32_t)(BNQ / 64) * HALO_BLK : (uint32_t)w.nt * B_BYTES);
       // pixel-tile coordinates: one division per item, then incremental (the divisions cost more than the TMA issue itself)
       int tw, th, tn;
       {
@@ -1081,6 +1087,13 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
         if (elect_one()) {
           uint8_t* sa = smem + (size_t)stage * STAGE_BYTES;
           mbar_expect_tx(&full_bar[stage], tx_bytes);
+          if (p.mstack) {
+            for (int sft = 0; sft < 3; ++sft)
+              tma_load_4d(sa + sft * P_SLOT, &p.tmP[0], &full_bar[stage], 0, w0 + sft - 1, h0, n0);
+#pragma unroll
+            for (int j = 0; j < BNQ / 64; ++j)
+              tma_load_4d(sa + A_BYTES + j * HALO_BLK, &p.tmQ, &full_bar[stage], w.cqt * BNQ + j * 64, w0, h0 - 1, n0);
+          } else {
           if (p.p5) tma_load_5d(sa, &p.tmP[w.src], &full_bar[stage], 0, w0, h0, n0, w.cpt * 2);
           else
             for (int j = 0; j < p.cp_blocks; ++j)
@@ -1101,6 +1114,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
               }
             }
           }
+          }
         }
         __syncwarp();
         if (++stage == stages) { stage = 0; phase ^= 1; }
@@ -1117,8 +1131,9 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
     long long dbg_full = 0, dbg_te = 0;
     const long long tstart = p.dbg ? clock64() : 0;
     static_assert(KPX == 64, "four K steps per stage are unrolled below");
-    const uint64_t ad_base = make_desc(smem_u32(smem), BLK_BYTES, 1024);
-    const uint64_t bd_base = make_desc(smem_u32(smem), p.halo ? HALO_BLK : Q_BLK, p.halo ? 16 * q_rb : 8 * q_rb, q_layout);
+    const uint64_t ad_base = p.mstack ? make_desc(smem_u32(smem), P_SLOT, 8 * p_rb, (uint32_t)thin_layout(p.cbp)) : make_desc(smem_u32(smem), BLK_BYTES, 1024);
+    const uint64_t bd_base = make_desc(smem_u32(smem), (p.halo || p.mstack) ? HALO_BLK : Q_BLK, p.halo ? 16 * q_rb : 8 * q_rb, q_layout);
+    const uint32_t ka = p.mstack ? p_rb : 128u;          // 16 pixels further down the dy tile, in 16-byte units
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
       const WgItem w = wg_decode(p, item);
       long long t0 = p.dbg ? clock64() : 0;
@@ -1133,7 +1148,9 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
       for (int t = 0; t < kWgMaxTpc; ++t) {
         if (t >= w.nt) break;
         {
-          if (p.halo) {
+          if (p.mstack) {
+            boff[t] = (A_BYTES + (uint32_t)t * 8 * q_rb) >> 4;       // kernel row t: the x strip starts t image rows (8 pixels each) further
+          } else if (p.halo) {
             // pixel tile = 8 rows x 8 columns; tap (dh, dw) reads halo pixel (row + dh + 1, col + dw + 1): a view that starts
             // ((dh+1)*16 + (dw+1)) pixels into the 16-pixel-pitch halo block.  One UMMA_K step = 16 pixels = 2 image rows.
             const TcTap tap = p.taps[w.t0 + t];
@@ -1160,7 +1177,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
 #pragma unroll
           for (int t = 0; t < kWgMaxTpc; ++t) {
             if (t >= w.nt) break;
-            wg_issue4(d, ad0, bd0 + (uint64_t)boff[t], idesc, first, kadv);
+            wg_issue4(d, ad0, bd0 + (uint64_t)boff[t], idesc, first, kadv, ka);
             d += n_mma;
           }
           umma_commit_e(&empty_bar[stage]);
@@ -1186,7 +1203,8 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
       // variant 2 = rows in lanes 0..63
       int cp = w.cpt * 128 + row;
       bool row_ok = true;
-      if (p.m64 == 1) { cp = w.cpt * 128 + q * 16 + lane; row_ok = lane < 16; }
+      if (p.mstack) { cp = lane; row_ok = q < 3 && lane < p.cbp; }      // TMEM quarter q = column shift slot, lane = dy channel
+      else if (p.m64 == 1) { cp = w.cpt * 128 + q * 16 + lane; row_ok = lane < 16; }
       else if (p.m64 == 2) { row_ok = row < 64; }
       const long long te0 = p.dbg ? clock64() : 0;
       mbar_wait(&tfull_bar[acc], acc_phase);
@@ -1194,7 +1212,9 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
       tc_fence_after();
       for (int t = 0; t < w.nt; ++t) {
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * acc_cols + (uint32_t)(t * p.n_mma);
-        float* drow = p.dw + ((size_t)p.taps[w.t0 + t].wt * p.cp_pad + cp) * p.cq_pad + w.cqt * BNQ;
+        // mstack: accumulator t = kernel row t, slot q = dy shifted by q - 1 columns = kernel column 2 - q; taps[] is ordered (kh, kw)
+        const int tap_i = p.mstack ? t * 3 + (q < 3 ? 2 - q : 0) : w.t0 + t;
+        float* drow = p.dw + ((size_t)p.taps[tap_i].wt * p.cp_pad + cp) * p.cq_pad + w.cqt * BNQ;
 #pragma unroll 1
         for (int c0 = 0; c0 < p.n_mma; c0 += 16) {
           uint32_t r[16];
@@ -1346,7 +1366,8 @@ int launch_igemm(const IgemmTcParams& P, cudaStream_t st) {
 template <int BNQ>
 int launch_wgrad(const WgradTcParams& P, int items, cudaStream_t st) {
   const uint32_t q_rb = 2 * P.cbq;
-  const uint32_t stage_bytes = 2 * KPX * 128 + (P.halo ? (uint32_t)(BNQ / 64) * 16 * 10 * q_rb : (uint32_t)P.tpc * (BNQ / 64) * KPX * q_rb);
+  const uint32_t stage_bytes = 2 * KPX * 128 + (P.mstack ? (uint32_t)(BNQ / 64) * 8 * 10 * q_rb
+                                                          : P.halo ? (uint32_t)(BNQ / 64) * 16 * 10 * q_rb : (uint32_t)P.tpc * (BNQ / 64) * KPX * q_rb);
   size_t smem = (size_t)P.stages * stage_bytes + 1024 + (2 * P.stages + 4) * 8 + 16;
   static bool attr_set = false;
   if (!attr_set) {
@@ -1416,7 +1437,7 @@ int launch_halo_cb(const HaloParams& P, cudaStream_t st) {
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  const int ctas = ((BN <= 32 && smem <= 110 * 1024) ? 2 : 1) * dn_num_sms();
+  const int ctas = (((BN <= 32 || (BN == 64 && CB <= 32)) && smem <= 110 * 1024) ? 2 : 1) * dn_num_sms();
   int grid = P.num_tiles < ctas ? P.num_tiles : ctas;
   HaloParams Q = P;
   Q.step[0] = grid % P.tilesW;
@@ -1474,7 +1495,7 @@ int dn_igemm_halo(const dn_igemm* p, const int* wt, cudaStream_t st) {
   } else {
     // thin output tiles (BN <= 32): two CTAs per SM when the weights leave room for >= 3 stages in half of the shared memory
     size_t budget = 200 * 1024;
-    if (BN <= 32 && b_bytes + 3 * kHaloBytes <= 100 * 1024) budget = 100 * 1024;
+    if ((BN <= 32 || (BN == 64 && P.cb <= 32)) && b_bytes + 3 * kHaloBytes <= 108 * 1024) budget = 108 * 1024;
     P.stages = (int)((budget - b_bytes) / kHaloBytes);
     if (P.stages > (P.cb == kChunk ? 4 : 6)) P.stages = P.cb == kChunk ? 4 : 6;     // thin boxes are latency-bound: more in flight
   }
@@ -1660,22 +1681,44 @@ int dn_wgrad_tc(const dn_wgrad* p, cudaStream_t st) {
     const int n_mma_est = p->cq_pad >= 256 ? 256 : (n16 < 64 ? n16 : (p->cq_pad >= 128 ? 128 : 64));
     if (512 / n_mma_est < 3 || (n_mma_est >= 128)) halo = false;
   }
+  // M-stacked mode (see WgradTcParams::mstack): thin dy, full 3x3, one source
+  static const bool g_mstack = []() { const char* e = getenv("DN_WGRAD_MSTACK"); return !(e && e[0] == '0'); }();
+  bool mstack = false;
+  int wt9[9];
+  if (g_mstack && g_thin_rows && p->ntaps == 9 && p->nsrc == 1 && P0.H == p->q.H && P0.W == p->q.W && P0.C <= 32) {
+    bool seen[9] = {false};
+    mstack = true;
+    for (int t = 0; t < 9 && mstack; ++t) {
+      int dh = p->taps[t].dh, dw = p->taps[t].dw;
+      if (dh < -1 || dh > 1 || dw < -1 || dw > 1 || seen[(dh + 1) * 3 + dw + 1]) mstack = false;
+      else { seen[(dh + 1) * 3 + dw + 1] = true; wt9[(dh + 1) * 3 + dw + 1] = p->taps[t].wt; }
+    }
+    const int bnq = p->cq_pad >= 256 ? 256 : (p->cq_pad >= 128 ? 128 : 64);
+    const int cq_tiles = (p->cq_pad + bnq - 1) / bnq;
+    const int n16 = (p->q.C + 15) / 16 * 16;
+    const int n_mma = (cq_tiles == 1 && n16 < bnq) ? n16 : bnq;
+    if (3 * n_mma > 512) mstack = false;
+  }
+  if (mstack) halo = false;
+  P.mstack = mstack ? 1 : 0;
+  P.cbp = mstack ? thin_cb(P0.C) : kChunk;
   P.halo = halo ? 1 : 0;
-  if (halo) { P.wb = 8; P.hb = 8; P.nb = 1; }
+  if (halo || mstack) { P.wb = 8; P.hb = 8; P.nb = 1; }
   else choose_box(P0.N, P0.H, P0.W, KPX, P.wb, P.hb, P.nb);
   const bool wg5 = []() { const char* e = getenv("DN_WGRAD_5D"); return !(e && e[0] == '0'); }();
   P.p5 = (wg5 && P0.C > 64 && P0.C % 128 == 0) ? 1 : 0;
   for (int s = 0; s < p->nsrc; ++s) {
-    int e = P.p5 ? make_view_map5(&P.tmP[s], p->p[s], P.wb, P.hb, P.nb, 2) : make_view_map(&P.tmP[s], p->p[s], P.wb, P.hb, P.nb);
+    int e = P.p5 ? make_view_map5(&P.tmP[s], p->p[s], P.wb, P.hb, P.nb, 2) : make_view_map(&P.tmP[s], p->p[s], P.wb, P.hb, P.nb, P.cbp);
     if (e) return e;
   }
   // thin x (<= 32 channels in a single 64-wide cq tile): 32- / 16-channel rows, see thin_cb()
   P.cbq = (p->cq_pad <= 64) ? pick_cb(p->q.C) : kChunk;
   {
     const int bnq = p->cq_pad >= 256 ? 256 : (p->cq_pad >= 128 ? 128 : 64);
-    P.q5 = (wg5 && !halo && bnq > 64 && p->q.C % bnq == 0) ? 1 : 0;
+    P.q5 = (wg5 && !halo && !mstack && bnq > 64 && p->q.C % bnq == 0) ? 1 : 0;
     int e = P.q5 ? make_view_map5(&P.tmQ, p->q, P.wb, P.hb, P.nb, bnq / 64)
-                 : (halo ? make_view_map(&P.tmQ, p->q, 16, 10, 1, P.cbq) : make_view_map(&P.tmQ, p->q, P.wb, P.hb, P.nb, P.cbq));
+                 : (mstack ? make_view_map(&P.tmQ, p->q, 8, 10, 1, P.cbq)
+                           : (halo ? make_view_map(&P.tmQ, p->q, 16, 10, 1, P.cbq) : make_view_map(&P.tmQ, p->q, P.wb, P.hb, P.nb, P.cbq)));
     if (e) return e;
   }
   for (int t = 0; t < p->ntaps; ++t) {
@@ -1683,6 +1726,10 @@ int dn_wgrad_tc(const dn_wgrad* p, cudaStream_t st) {
     P.taps[t].dw = (int16_t)p->taps[t].dw; P.taps[t].wt = (int16_t)p->taps[t].wt;
   }
   P.ntaps = p->ntaps;
+  if (mstack) {       // the kernel sees three "taps" (kernel rows); taps[kh * 3 + kw] keeps the packed-weight index of every real tap
+    for (int i = 0; i < 9; ++i) { P.taps[i].src = 0; P.taps[i].dh = (int16_t)(i / 3 - 1); P.taps[i].dw = (int16_t)(i % 3 - 1); P.taps[i].wt = (int16_t)wt9[i]; }
+    P.ntaps = 3;
+  }
   P.tilesW = (P0.W + P.wb - 1) / P.wb;
   P.tilesH = (P0.H + P.hb - 1) / P.hb;
   P.tilesN = (P0.N + P.nb - 1) / P.nb;
@@ -1701,10 +1748,10 @@ int dn_wgrad_tc(const dn_wgrad* p, cudaStream_t st) {
   int tpc = 512 / P.n_mma;
   int by_smem = (int)((64 * 1024 - a_bytes) / b_bytes);
   if (by_smem < 1) by_smem = 1;
-  if (!halo && tpc > by_smem) tpc = by_smem;
+  if (!halo && !mstack && tpc > by_smem) tpc = by_smem;
   if (tpc > P.ntaps) tpc = P.ntaps;
   // wide tiles: prefer two accumulator stages (<= 256 columns per stage) over sharing the dy tile between more taps
-  if (P.n_mma >= 128 && tpc * P.n_mma > 256) tpc = 256 / P.n_mma;
+  if (!mstack && P.n_mma >= 128 && tpc * P.n_mma > 256) tpc = 256 / P.n_mma;
   // all taps of a group (consecutive taps [g * tpc, (g + 1) * tpc)) must read the same dy view: the four output phases of a
   // transposed convolution arrive as one problem with the taps ordered phase by phase
   auto uniform = [&](int n) {
@@ -1743,7 +1790,8 @@ int dn_wgrad_tc(const dn_wgrad* p, cudaStream_t st) {
   }
   P.ptiles_per_split = (P.num_ptiles + splits - 1) / splits;
   P.splits = (P.num_ptiles + P.ptiles_per_split - 1) / P.ptiles_per_split;
-  const uint32_t stage_bytes = a_bytes + (halo ? (uint32_t)(BNQ / 64) * 16 * 10 * 2 * P.cbq : (uint32_t)P.tpc * b_bytes);
+  const uint32_t stage_bytes = a_bytes + (mstack ? (uint32_t)(BNQ / 64) * 8 * 10 * 2 * P.cbq
+                                                 : halo ? (uint32_t)(BNQ / 64) * 16 * 10 * 2 * P.cbq : (uint32_t)P.tpc * b_bytes);
   P.stages = (int)((200 * 1024) / stage_bytes);
   if (P.stages > 8) P.stages = 8;
   P.m64 = 0;
@@ -1751,7 +1799,8 @@ int dn_wgrad_tc(const dn_wgrad* p, cudaStream_t st) {
     P.m64 = 1;
     if (const char* e = getenv("DN_WGRAD_M64")) P.m64 = atoi(e);
   }
-  P.idesc = make_idesc(P0.dtype, p->q.dtype, 1, 1, P.m64 ? 64 : 128, P.n_mma);
+  if (mstack) P.m64 = 0;
+  P.idesc = make_idesc(P0.dtype, p->q.dtype, 1, 1, mstack ? 4 * P.cbp : (P.m64 ? 64 : 128), P.n_mma);
   P.dw = p->dw;
   P.cp = P0.C; P.cq = p->q.C; P.cp_pad = p->cp_pad; P.cq_pad = p->cq_pad;
   P.scale = p->scale;

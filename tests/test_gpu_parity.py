@@ -270,7 +270,7 @@ def _conv_cases():
     return mod.CONV_CASES
 
 
-@pytest.mark.parametrize('idx', range(16))
+@pytest.mark.parametrize('idx', range(18))
 def test_conv_layers_fp32_cuda_core(idx, monkeypatch):
     import _harness as Hn
     monkeypatch.setenv('DISPNET_B200_BACKEND', 'generic')
@@ -281,7 +281,7 @@ def test_conv_layers_fp32_cuda_core(idx, monkeypatch):
             assert r[k] < 2e-5, (name, r)
 
 
-@pytest.mark.parametrize('idx', range(16))
+@pytest.mark.parametrize('idx', range(18))
 def test_conv_layers_tcgen05(idx):
     """fp16 operands / fp32 TMEM accumulation vs torch fp32 (TF32 off).  Gradients of layers with a fused ReLU /
     LeakyReLU differ where an fp16-rounded pre-activation changes sign (~sqrt(3e-4) of the L2 norm), hence 5e-2 there."""
@@ -297,7 +297,7 @@ def test_conv_layers_tcgen05(idx):
         assert all(b == 1 for b in r['backends']['fwd']), (name, r['backends'])     # really ran on the tensor cores
 
 
-@pytest.mark.parametrize('idx', range(16))
+@pytest.mark.parametrize('idx', range(18))
 def test_conv_layers_tc32(idx):
     """precision 'tc32' (fp32 storage, three split-bf16 tcgen05 terms per product, fp32 TMEM accumulation) vs torch fp32
     (TF32 off): fp32-class results ON the tensor cores.  Gradients of layers with a fused ReLU / LeakyReLU differ where a

@@ -59,6 +59,9 @@ CONV_CASES = [
     ('ct3_s2_op1_512_512_crop', dict(cin=512, cout=512, k=3, stride=2, pad=1, transposed=True, out_pad=1, act=1,
                                      crop=(2, 7)), (2, 512, 1, 4)),
     ('ct3_s2_op1_64_32', dict(cin=64, cout=32, k=3, stride=2, pad=1, transposed=True, out_pad=1, act=1), (2, 64, 8, 12)),
+    # thin output gradients: the weight gradient stacks three column-shifted dy copies in the MMA M dimension (dn_tc.cu, mstack)
+    ('c3x3_s1_128_4_mstack', dict(cin=128, cout=4, k=3), (4, 128, 8, 12)),
+    ('c3x3_s1_97_32_mstack', dict(cin=97, cout=32, k=3, act=2), (2, 97, 16, 24)),
 ]
 
 

@@ -8,6 +8,11 @@ DISPNET_B200_GRAPHS=0 DISPNET_B200_SIDE_STREAM=0 DISPNET_B200_PHASE_STREAMS=0 DN
 # 2. full captures of one launch each
 cap() { timeout 300 ncu --set full --import-source on --clock-control none -k regex:$1 -s $2 -c 1 -f -o gpurun_out/r2_full_$3 ${@:4} > gpurun_out/r2_full_$3.log 2>&1; }
 cap igemm_tc 2 igemm_tc_feat27 python tools/prof_conv.py feat27
+cap igemm_tc 2 igemm_tc_feat10 python tools/prof_conv.py feat10
+cap igemm_halo 2 igemm_halo_iconv0 python tools/prof_conv.py iconv0
+cap igemm_halo 2 igemm_halo_feat0 python tools/prof_conv.py feat0
+cap wgrad_tc 2 wgrad_tc_iconv0 python tools/prof_conv.py iconv0
+cap igemm_tc 2 igemm_tc_upconv0 python tools/prof_conv.py upconv0
 cap igemm_halo 2 igemm_halo_feat3 python tools/prof_conv.py feat3
 cap wgrad_tc 2 wgrad_tc_feat27 python tools/prof_conv.py feat27
 cap wgrad_tc 2 wgrad_tc_feat3 python tools/prof_conv.py feat3
