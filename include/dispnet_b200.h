@@ -92,6 +92,12 @@ typedef struct dn_igemm {
                                 geometry of `out`; sub-problem i uses taps [i * ntaps / n, (i + 1) * ntaps / n) and writes at
                                 out.ptr (and out2) + phase_off[i] elements */
   int64_t phase_off[4];
+  int32_t phase_cout;        /* > 0 (with nphase > 1): the phases are stacked along the OUTPUT CHANNELS instead: `taps` is the union of the
+                                phases' taps over one input neighbourhood, the packed weight matrices have nphase * phase_cout rows
+                                (rows [i * phase_cout, (i + 1) * phase_cout) = phase i, zero where a phase does not use the tap),
+                                cout_pad = nphase * phase_cout, and column block i of every output pixel goes to out + phase_off[i].
+                                One fetch of the input tile serves all phases (thin transposed convolutions). */
+  int32_t pad2_;
 } dn_igemm;
 
 /*

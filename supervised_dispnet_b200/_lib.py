@@ -28,7 +28,8 @@ class DnIgemm(C.Structure):
                 ('w_dtype', C.c_int32), ('cin_pad', C.c_int32), ('cout_pad', C.c_int32), ('bias', C.c_void_p),
                 ('act', C.c_int32), ('accumulate', C.c_int32), ('stride', C.c_int32), ('ntaps', C.c_int32),
                 ('taps', DnTap * MAX_TAPS), ('out_scale', C.c_float), ('out_pad_ok', C.c_int32), ('out2', C.c_void_p),
-                ('out2_dtype', C.c_int32), ('nphase', C.c_int32), ('phase_off', C.c_int64 * 4)]
+                ('out2_dtype', C.c_int32), ('nphase', C.c_int32), ('phase_off', C.c_int64 * 4), ('phase_cout', C.c_int32),
+                ('pad2_', C.c_int32)]
 
 
 class DnWgrad(C.Structure):

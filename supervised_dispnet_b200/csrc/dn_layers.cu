@@ -474,13 +474,15 @@ static int igemm_check(const dn_igemm* p) {
   for (int s = 0; s < p->nsrc; ++s)
     if (!p->in[s].ptr || p->in[s].C > p->cin_pad || p->in[s].N != p->out.N) return DN_E_ARG;
   if (p->out.C > p->cout_pad) return DN_E_ARG;
-  if (p->nphase < 0 || p->nphase > 4 || (p->nphase > 1 && p->ntaps % p->nphase != 0)) return DN_E_ARG;
+  if (p->phase_cout > 0 && (p->nphase < 2 || p->cout_pad != p->nphase * p->phase_cout || p->out.C > p->phase_cout)) return DN_E_ARG;
+  if (p->nphase < 0 || p->nphase > 4 || (p->nphase > 1 && p->phase_cout <= 0 && p->ntaps % p->nphase != 0)) return DN_E_ARG;
   return 0;
 }
 
 int dn_igemm_generic(const dn_igemm* p, cudaStream_t st) {
   long long M = (long long)p->out.N * p->out.H * p->out.W;
   if (M == 0) return 0;
+  if (p->nphase > 1 && p->phase_cout > 0) return DN_E_UNSUPPORTED;      // (channel-stacked phases exist on the tensor-core path only)
   if (p->nphase > 1) {      // merged output phases: one single-view problem per phase
     const int tph = p->ntaps / p->nphase;
     const int esz = dn_esize(p->out.dtype);

@@ -341,10 +341,34 @@ __device__ __forceinline__ void wg_issue4(uint32_t d_tmem, uint64_t ad, uint64_t
       : "memory");
 }
 
-// one epilogue chunk: NV (8 / 16 / 32) accumulator columns of one pixel -> bias / activation -> one 16-byte store per 8 channels
+// previous contents of an accumulate target (16-bit output): all 16-byte loads of the chunk are issued together -- and, where
+// the caller can, before it waits for the accumulator -- instead of one dependent load per eight channels
+template <int NV>
+__device__ __forceinline__ void epi_prefetch(uint4* old, bool valid, int c_base, int c_eff, const uint8_t* optr_c) {
+#pragma unroll
+  for (int g = 0; g < NV / 8; ++g) {
+    old[g] = make_uint4(0, 0, 0, 0);
+    if (valid && c_base + 8 * g < c_eff) old[g] = *reinterpret_cast<const uint4*>(optr_c + 16 * g);
+  }
+}
+__device__ __forceinline__ void epi_add_old(float* v, const uint4& u, int out_dtype) {
+  if (out_dtype == DN_F16) {
+    const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { float2 t = __half22float2(h[i]); v[2 * i] += t.x; v[2 * i + 1] += t.y; }
+  } else {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { float2 t = __bfloat1622float2(h[i]); v[2 * i] += t.x; v[2 * i + 1] += t.y; }
+  }
+}
+
+// one epilogue chunk: NV (8 / 16 / 32) accumulator columns of one pixel -> bias / activation -> one 16-byte store per 8 channels.
+// `old` = epi_prefetch() of the same chunk when accumulate is set and the output is 16-bit, else unused
 template <int NV>
 __device__ __forceinline__ void epi_store(const uint32_t* r, const float* bs, float out_scale, int act, bool valid, int c_base, int c_eff, int out_C,
-                                          int out_dtype, uint8_t* optr_c, int accumulate, void* out2, int out2_dtype, size_t elem_off) {
+                                          int out_dtype, uint8_t* optr_c, int accumulate, void* out2, int out2_dtype, size_t elem_off,
+                                          const uint4* old) {
   if (!valid) return;
 #pragma unroll
   for (int g = 0; g < NV / 8; ++g) {
@@ -363,24 +387,37 @@ __device__ __forceinline__ void epi_store(const uint32_t* r, const float* bs, fl
       for (int j = 0; j < 8; ++j)
         if (c0 + j < out_C) o[j] = accumulate ? o[j] + v[j] : v[j];
     } else if (out_dtype == DN_F16) {
-      __half* o = (__half*)optr_c + 8 * g;
-      if (accumulate) {
-        float a[8];
-        Vec8<__half>::load(o, a);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] += a[j];
-      }
-      Vec8<__half>::store(o, v);
+      if (accumulate) epi_add_old(v, old[g], out_dtype);
+      Vec8<__half>::store((__half*)optr_c + 8 * g, v);
     } else {
-      __nv_bfloat16* o = (__nv_bfloat16*)optr_c + 8 * g;
-      if (accumulate) {
-        float a[8];
-        Vec8<__nv_bfloat16>::load(o, a);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] += a[j];
-      }
-      Vec8<__nv_bfloat16>::store(o, v);
+      if (accumulate) epi_add_old(v, old[g], out_dtype);
+      Vec8<__nv_bfloat16>::store((__nv_bfloat16*)optr_c + 8 * g, v);
     }
+  }
+}
+
+// epilogue chunk of a channel-stacked phase problem: every 8-channel group belongs to one phase (cpp is a multiple of 8) and goes
+// to that phase's pixel; no accumulate form (forward of transposed convolutions only)
+template <int NV>
+__device__ __forceinline__ void epi_store_phases(const uint32_t* r, const float* bs, float out_scale, int act, bool valid, int c_base, int cpp_shift,
+                                                 int c_eff, int out_dtype, uint8_t* out_px, const long long* phase_off, void* out2,
+                                                 int out2_dtype, size_t px_off) {
+  if (!valid) return;
+#pragma unroll
+  for (int g = 0; g < NV / 8; ++g) {
+    const int c0 = c_base + 8 * g;
+    const int ph = c0 >> cpp_shift, cc = c0 - (ph << cpp_shift);      // (cpp is a power of two: no division in the epilogue)
+    if (ph >= 4 || cc >= c_eff) continue;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = dn_act(__uint_as_float(r[8 * g + j]) * out_scale + bs[8 * g + j], act);
+    const size_t e = (size_t)(phase_off[ph] + cc);
+    if (out2) {
+      if (out2_dtype == DN_F16) Vec8<__half>::store((__half*)out2 + px_off + e, v);
+      else Vec8<__nv_bfloat16>::store((__nv_bfloat16*)out2 + px_off + e, v);
+    }
+    if (out_dtype == DN_F16) Vec8<__half>::store((__half*)out_px + e, v);
+    else Vec8<__nv_bfloat16>::store((__nv_bfloat16*)out_px + e, v);
   }
 }
 
@@ -593,6 +630,8 @@ __global__ void __launch_bounds__(320, 1) igemm_tc_kernel(const __grid_constant_
       }
       const size_t eoff = (size_t)(dn_off(p.out, n, h, w) + co0 + p.phase_off[tp.ph]);
       uint8_t* optr = (uint8_t*)p.out.ptr + eoff * esz;
+      uint4 old[CH / 8];
+      if (CPT <= 32 && accumulate && esz == 2) epi_prefetch<CH>(old, valid && cbeg < n_mma, cbeg, c_eff - co0, optr + (size_t)cbeg * esz);
       const long long te0 = p.dbg ? clock64() : 0;
       mbar_wait(&tfull_bar[acc], acc_phase);
       const long long te1 = p.dbg ? clock64() : 0;
@@ -604,20 +643,23 @@ __global__ void __launch_bounds__(320, 1) igemm_tc_kernel(const __grid_constant_
         if (cbeg < n_mma) {
           tmem_ldn<CH>(taddr + cbeg, ra);
           tmem_ld_wait();
-          epi_store<CH>(ra, breg, out_scale, act, valid, cbeg, ce, oc, out_dtype, optr + (size_t)cbeg * esz, accumulate, p.out2, p.out2_dtype, eoff + cbeg);
+          epi_store<CH>(ra, breg, out_scale, act, valid, cbeg, ce, oc, out_dtype, optr + (size_t)cbeg * esz, accumulate, p.out2, p.out2_dtype, eoff + cbeg, old);
         }
       } else {
         uint32_t ra[32], rb[32];
+        uint4 old4[4];
         if (cbeg < n_mma) tmem_ld32(taddr + cbeg, ra);
 #pragma unroll 1
         for (int c0 = cbeg; c0 < cbeg + CPT && c0 < n_mma; c0 += 64) {
+          if (accumulate && esz == 2) epi_prefetch<32>(old4, valid, c0, ce, optr + (size_t)c0 * esz);
           tmem_ld_wait();
           if (c0 + 32 < cbeg + CPT && c0 + 32 < n_mma) tmem_ld32(taddr + c0 + 32, rb);
-          epi_store<32>(ra, bs + c0, out_scale, act, valid, c0, ce, oc, out_dtype, optr + (size_t)c0 * esz, accumulate, p.out2, p.out2_dtype, eoff + c0);
+          epi_store<32>(ra, bs + c0, out_scale, act, valid, c0, ce, oc, out_dtype, optr + (size_t)c0 * esz, accumulate, p.out2, p.out2_dtype, eoff + c0, old4);
           if (!(c0 + 32 < cbeg + CPT && c0 + 32 < n_mma)) break;
+          if (accumulate && esz == 2) epi_prefetch<32>(old4, valid, c0 + 32, ce, optr + (size_t)(c0 + 32) * esz);
           tmem_ld_wait();
           if (c0 + 64 < cbeg + CPT && c0 + 64 < n_mma) tmem_ld32(taddr + c0 + 64, ra);
-          epi_store<32>(rb, bs + c0 + 32, out_scale, act, valid, c0 + 32, ce, oc, out_dtype, optr + (size_t)(c0 + 32) * esz, accumulate, p.out2, p.out2_dtype, eoff + c0 + 32);
+          epi_store<32>(rb, bs + c0 + 32, out_scale, act, valid, c0 + 32, ce, oc, out_dtype, optr + (size_t)(c0 + 32) * esz, accumulate, p.out2, p.out2_dtype, eoff + c0 + 32, old4);
         }
       }
       tc_fence_before();
@@ -671,6 +713,8 @@ struct HaloParams {
   int act, accumulate;
   float out_scale;
   unsigned long long* dbg;   // optional per-role cycle counters (dn_tc_set_debug), same slots as igemm_tc_kernel
+  int nph, cpp;              // channel-stacked output phases (dn_igemm.phase_cout): column block i of a pixel goes to out + phase_off[i]
+  long long phase_off[4];
   int step[3];               // gridDim.x as mixed-radix digits (tw, th, n): tiles advance by carries, not by divisions
   int dbg_flags;             // experiments (DN_TC_FLAGS): 1 = epilogue neither reads TMEM nor stores, 2 = epilogue waits with nanosleep back-off
 };
@@ -891,11 +935,13 @@ __global__ void __launch_bounds__(320, (BN <= 32 || (BN == 64 && CB <= 32)) ? 2 
     const float out_scale = p.out_scale;
     // bias: registers when a thread owns at most 32 columns, shared memory otherwise (one N tile: the same for every tile)
     float breg[CH];
+    const int cpp = p.nph > 1 ? p.cpp : BN;        // (channel-stacked phases: bias / channel limits repeat every cpp columns)
+    const int cpp_shift = 31 - __clz(cpp);
     if (CPT <= 32) {
 #pragma unroll
-      for (int j = 0; j < CH; ++j) breg[j] = (p.bias && cbeg + j < p.out.C) ? p.bias[cbeg + j] : 0.f;
+      for (int j = 0; j < CH; ++j) breg[j] = (p.bias && (cbeg + j) % cpp < p.out.C) ? p.bias[(cbeg + j) % cpp] : 0.f;
     } else {
-      for (int c = et; c < BN; c += EW * 32) bias_s[c] = (p.bias && c < p.out.C) ? p.bias[c] : 0.f;
+      for (int c = et; c < BN; c += EW * 32) bias_s[c] = (p.bias && c % cpp < p.out.C) ? p.bias[c % cpp] : 0.f;
       asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");
     }
     int tw, th, n;
@@ -913,33 +959,48 @@ __global__ void __launch_bounds__(320, (BN <= 32 || (BN == 64 && CB <= 32)) ? 2 
       const bool valid = (w < p.out.W) && (h < p.out.H);
       const size_t eoff = (size_t)dn_off(p.out, n_c, h, w);
       uint8_t* optr = (uint8_t*)p.out.ptr + eoff * esz;
+      uint4 old[CH / 8];
+      if (CPT <= 32 && accumulate && esz == 2) epi_prefetch<CH>(old, valid && cbeg < n_mma, cbeg, c_eff, optr + (size_t)cbeg * esz);
       const long long te0 = p.dbg ? clock64() : 0;
       if (p.dbg_flags & 2) mbar_wait_sleep(&tfull_bar[acc], acc_phase); else mbar_wait(&tfull_bar[acc], acc_phase);
       const long long te1 = p.dbg ? clock64() : 0;
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
       if (p.dbg_flags & 1) {
+      } else if (p.nph > 1) {
+        // channel-stacked phases: chunks of CH columns, each 8-channel group scattered to its phase's pixel
+        uint32_t ra[CH];
+#pragma unroll 1
+        for (int c0 = cbeg; c0 < cbeg + CPT && c0 < n_mma; c0 += CH) {
+          tmem_ldn<CH>(taddr + c0, ra);
+          tmem_ld_wait();
+          epi_store_phases<CH>(ra, CPT <= 32 ? breg : bias_s + c0, out_scale, act, valid, c0, cpp_shift, c_eff, out_dtype, optr, p.phase_off, p.out2,
+                               p.out2_dtype, eoff);
+        }
       } else if (CPT <= 32) {
         uint32_t ra[CH];
         if (cbeg < n_mma) {
           tmem_ldn<CH>(taddr + cbeg, ra);
           tmem_ld_wait();
           if (p.dbg && et == 0) atomicAdd(p.dbg + 7, (unsigned long long)(clock64() - te1));
-          epi_store<CH>(ra, breg, out_scale, act, valid, cbeg, c_eff, out_C, out_dtype, optr + (size_t)cbeg * esz, accumulate, p.out2, p.out2_dtype, eoff + cbeg);
+          epi_store<CH>(ra, breg, out_scale, act, valid, cbeg, c_eff, out_C, out_dtype, optr + (size_t)cbeg * esz, accumulate, p.out2, p.out2_dtype, eoff + cbeg, old);
         }
       } else {
         // chunks of 32 columns; the TMEM load of chunk i + 1 is in flight while chunk i is converted and stored
         uint32_t ra[32], rb[32];
+        uint4 old4[4];
         if (cbeg < n_mma) tmem_ld32(taddr + cbeg, ra);
 #pragma unroll 1
         for (int c0 = cbeg; c0 < cbeg + CPT && c0 < n_mma; c0 += 64) {
+          if (accumulate && esz == 2) epi_prefetch<32>(old4, valid, c0, c_eff, optr + (size_t)c0 * esz);
           tmem_ld_wait();
           if (c0 + 32 < cbeg + CPT && c0 + 32 < n_mma) tmem_ld32(taddr + c0 + 32, rb);
-          epi_store<32>(ra, bias_s + c0, out_scale, act, valid, c0, c_eff, out_C, out_dtype, optr + (size_t)c0 * esz, accumulate, p.out2, p.out2_dtype, eoff + c0);
+          epi_store<32>(ra, bias_s + c0, out_scale, act, valid, c0, c_eff, out_C, out_dtype, optr + (size_t)c0 * esz, accumulate, p.out2, p.out2_dtype, eoff + c0, old4);
           if (!(c0 + 32 < cbeg + CPT && c0 + 32 < n_mma)) break;
+          if (accumulate && esz == 2) epi_prefetch<32>(old4, valid, c0 + 32, c_eff, optr + (size_t)(c0 + 32) * esz);
           tmem_ld_wait();
           if (c0 + 64 < cbeg + CPT && c0 + 64 < n_mma) tmem_ld32(taddr + c0 + 64, ra);
-          epi_store<32>(rb, bias_s + c0 + 32, out_scale, act, valid, c0 + 32, c_eff, out_C, out_dtype, optr + (size_t)(c0 + 32) * esz, accumulate, p.out2, p.out2_dtype, eoff + c0 + 32);
+          epi_store<32>(rb, bias_s + c0 + 32, out_scale, act, valid, c0 + 32, c_eff, out_C, out_dtype, optr + (size_t)(c0 + 32) * esz, accumulate, p.out2, p.out2_dtype, eoff + c0 + 32, old4);
         }
       }
       const long long te2 = p.dbg ? clock64() : 0;
@@ -1393,7 +1454,7 @@ const bool g_halo_ring = []() { const char* e = getenv("DN_HALO_RING"); return !
 // taps form a subset of the 3x3 neighbourhood (all nine for a 3x3 convolution, a 2x2 corner for one output phase of a
 // 4x4 / stride-2 transposed convolution): wt[kh * 3 + kw] = packed-weight index, -1 where the tap is absent
 bool halo_taps(const dn_igemm* p, int* wt) {
-  if (p->ntaps > 9 || p->ntaps < 3 || p->nsrc != 1 || p->stride != 1 || p->nphase > 1) return false;
+  if (p->ntaps > 9 || p->ntaps < 3 || p->nsrc != 1 || p->stride != 1 || (p->nphase > 1 && p->phase_cout <= 0)) return false;
   bool seen[9] = {false};
   for (int i = 0; i < 9; ++i) wt[i] = -1;
   for (int t = 0; t < p->ntaps; ++t) {
@@ -1437,7 +1498,8 @@ int launch_halo_cb(const HaloParams& P, cudaStream_t st) {
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  const int ctas = (((BN <= 32 || (BN == 64 && CB <= 32)) && smem <= 110 * 1024) ? 2 : 1) * dn_num_sms();
+  static const bool one_cta = []() { const char* e = getenv("DN_HALO_ONE_CTA"); return e && e[0] == '1'; }();      // A/B knob
+  const int ctas = (((BN <= 32 || (BN == 64 && CB <= 32)) && smem <= 110 * 1024 && !one_cta) ? 2 : 1) * dn_num_sms();
   int grid = P.num_tiles < ctas ? P.num_tiles : ctas;
   HaloParams Q = P;
   Q.step[0] = grid % P.tilesW;
@@ -1509,6 +1571,13 @@ int dn_igemm_halo(const dn_igemm* p, const int* wt, cudaStream_t st) {
   P.act = p->act;
   P.accumulate = p->accumulate;
   P.out_scale = p->out_scale;
+  P.nph = (p->nphase > 1 && p->phase_cout > 0) ? p->nphase : 1;
+  P.cpp = p->phase_cout;
+  for (int i = 0; i < 4; ++i) P.phase_off[i] = (P.nph > 1 && i < p->nphase) ? p->phase_off[i] : 0;
+  if (P.nph > 1) {       // channel limits are per phase
+    if (p->out.dtype == DN_F32 || p->accumulate || (p->phase_cout % 8) != 0 || (p->phase_cout & (p->phase_cout - 1)) != 0) return DN_E_UNSUPPORTED;
+    P.n_mma = p->cout_pad;
+  }
   P.dbg = g_tc_dbg;
   { const char* e = getenv("DN_TC_FLAGS"); P.dbg_flags = e ? atoi(e) : 0; }
   switch (BN) {
@@ -1548,7 +1617,13 @@ DN_EXPORT int dn_tc_available(void) {
 
 DN_EXPORT int dn_igemm_tc_supported(const dn_igemm* p) {
   if (!p || p->stride != 1 || p->ntaps > kMaxTcTaps || p->ntaps < 1) return 0;
-  if (p->nphase < 0 || p->nphase > 4 || (p->nphase > 1 && (p->ntaps % p->nphase) != 0)) return 0;
+  if (p->nphase < 0 || p->nphase > 4 || (p->nphase > 1 && p->phase_cout <= 0 && (p->ntaps % p->nphase) != 0)) return 0;
+  if (p->phase_cout > 0) {
+    int wt[9];
+    if (p->nphase < 2 || p->out.dtype == DN_F32 || p->accumulate || (p->phase_cout % 8) != 0 || (p->phase_cout & (p->phase_cout - 1)) != 0 ||
+        !halo_eligible(p, wt))
+      return 0;
+  }
   if (p->w_dtype != DN_F16 && p->w_dtype != DN_BF16) return 0;
   if (p->out.dtype != DN_F32) {   // 16-byte vector epilogue
     if (!view_tma_ok(p->out)) return 0;
@@ -1567,6 +1642,7 @@ int dn_igemm_tc(const dn_igemm* p, cudaStream_t st) {
   {
     int wt[9];
     if (halo_eligible(p, wt)) return dn_igemm_halo(p, wt, st);
+    if (p->phase_cout > 0) return DN_E_UNSUPPORTED;       // channel-stacked phases exist in the halo kernel only
   }
   IgemmTcParams P;
   memset(&P, 0, sizeof(P));

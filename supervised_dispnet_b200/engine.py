@@ -407,7 +407,7 @@ class ConvOp(Op):
 
     def _build_fwd(self, plan):
         built = []
-        merged = self._build_fwd_merged(plan)
+        merged = self._build_fwd_stacked(plan) or self._build_fwd_merged(plan)
         if merged is not None:
             return merged
         for pr in self.fwd_probs:
@@ -422,6 +422,43 @@ class ConvOp(Op):
                           pr['stride'], taps, out2=o2)
             built.append((p, _backend('igemm', p), _igemm_flops(p) / div))
         return built
+
+    def _build_fwd_stacked(self, plan):
+        """Thin transposed convolution (4x4 / stride 2, at most 64 input channels, 4 * Cout_pad <= 128): the four output phases stacked
+        along the output channels of ONE 3x3 gather-convolution over the input (dn_igemm.phase_cout).  Every input tile is fetched
+        once and nine taps x N = 4 * Cout MMAs replace sixteen taps x N = Cout ones; the weights are packed as nine
+        [4 * Cout_pad][Cin_pad] matrices that are zero where a phase does not use the tap.  None when not applicable."""
+        prs = self.fwd_probs
+        cpp = self.cout_pad
+        if not (self.transposed and len(prs) == 4 and tc_enabled() and plan.prec.split is None and self.x.C <= 64 and 4 * cpp <= 128
+                and plan.prec.act != torch.float32 and os.environ.get('DISPNET_B200_STACK_PHASES', '1') != '0'):
+            return None
+        if len({(pr['out'].H, pr['out'].W) for pr in prs}) != 1 or (prs[0]['out'].H, prs[0]['out'].W) != (self.x.H, self.x.W):
+            return None
+        union = sorted({(dh, dw) for pr in prs for (_, dh, dw, _) in pr['taps']})
+        if any(abs(dh) > 1 or abs(dw) > 1 for dh, dw in union) or len(union) != 9:
+            return None
+        if getattr(self, 'wp9', None) is None:
+            self.wp9 = torch.zeros((9, 4 * cpp, self.cin_pad), dtype=plan.prec.act, device=plan.device)
+        base = prs[0]['out']
+        taps = [(0, dh, dw, (dh + 1) * 3 + (dw + 1)) for dh, dw in union]
+        o2 = self.out_shadow.phase(*prs[0]['phase']) if self.out_shadow is not None else None
+        p = _mk_igemm([self.x], base, self.wp9, plan.prec.act, self.cin_pad, 4 * cpp, None, self.act, False, 1, taps, out2=o2)
+        p.nphase, p.phase_cout = 4, cpp
+        for i, pr in enumerate(prs):
+            p.phase_off[i] = pr['out'].off - base.off
+        if _backend('igemm', p) != 1:
+            return None
+        # one pack job per (phase, tap): the k x k parameter plane (kh, kw) goes to rows [phase * cpp, ...) of matrix (dh, dw)
+        self.stack_jobs = []
+        W = plan.param(self.name + '.weight')
+        for i, pr in enumerate(prs):
+            for (_, dh, dw, wt) in pr['taps']:
+                # (source offset: (kh * k + kw) floats into the parameter; destination offset in bytes)
+                self.stack_jobs.append((wt * 4, (((dh + 1) * 3 + (dw + 1)) * 4 * cpp + i * cpp) * self.cin_pad * self.wp9.element_size()))
+        flops = sum(_igemm_flops(_mk_igemm([self.x], pr['out'], self.wp, plan.prec.act, self.cin_pad, self.cout_pad, None, self.act, False, 1,
+                                           pr['taps'])) for pr in prs)
+        return [(p, 1, flops)]
 
     def _build_fwd_merged(self, plan):
         """The output phases of a transposed convolution as ONE gather-convolution launch (dn_igemm.nphase): same input view and
@@ -452,6 +489,20 @@ class ConvOp(Op):
 
     # ---- weight (un)packing is batched over all layers of the plan: one dn_pack_jobs launch each (Plan._run_jobs)
     def jobs(self, plan, which):
+        if which == 'fwd' and self.transposed:
+            if self._fwd_built is None:      # (decides whether the forward runs channel-stacked: different packed weights)
+                self._fwd_built = self._build_fwd(plan)
+            if getattr(self, 'stack_jobs', None):
+                W = plan.param(self.name + '.weight')
+                out = []
+                for src_off, dst_off in self.stack_jobs:
+                    j = L.DnPackJob()
+                    j.T, j.k, j.s_kh, j.s_kw = 1, self.k, self.k, 1
+                    j.src, j.dst = W.data_ptr() + src_off, self.wp9.data_ptr() + dst_off
+                    j.dst_dtype, j.unpack = _DT[plan.prec.act], 0
+                    j.R, j.Cc, j.R_pad, j.C_pad, j.s_r, j.s_c = self.Cout, self.Cin, self.cout_pad, self.cin_pad, self.s_co, self.s_ci
+                    out.append(j)
+                return out
         j = self.job(plan, which)
         if j is None:
             return []
