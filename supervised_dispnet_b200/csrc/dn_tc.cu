@@ -97,6 +97,14 @@ __device__ __forceinline__ void tma_load_5d(void* smem, const CUtensorMap* m, ui
       "l"((uint64_t)m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
 }
+// TMA store of a shared-memory box (bulk-group completion)
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* smem, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"((uint64_t)m), "r"(smem_u32(smem)),
+               "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_load_3d(void* smem, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
@@ -392,6 +400,35 @@ __device__ __forceinline__ void epi_store(const uint32_t* r, const float* bs, fl
     } else {
       if (accumulate) epi_add_old(v, old[g], out_dtype);
       Vec8<__nv_bfloat16>::store((__nv_bfloat16*)optr_c + 8 * g, v);
+    }
+  }
+}
+
+// Epilogue chunk for the TMA-store path: NV accumulator columns of tile row `row` -> bias / activation -> 16-byte chunks of the
+// staging tile(s) in shared memory, laid out as the TMA store boxes expect them: blocks of `ob` channels, [128 rows][2 * ob bytes]
+// each, 16-byte chunks XOR-swizzled like the matching TMA swizzle mode (ob = 64 / 32 / 16 -> 128B / 64B / 32B).
+// Why: a row-per-thread epilogue that stores to global memory touches 32 different 128-byte lines per st.v4 instruction
+// (32 LSU wavefronts each); through shared memory the same bytes cost 4 wavefronts and one bulk store per tile.
+template <int NV>
+__device__ __forceinline__ void epi_stage(const uint32_t* r, const float* bs, float out_scale, int act, int c_base, int ob_shift, int row,
+                                          uint8_t* stg, int out_dtype, uint8_t* stg2, int out2_dtype) {
+  const int ob = 1 << ob_shift;
+  const uint32_t swz = ob == 64 ? (uint32_t)(row & 7) : ob == 32 ? (uint32_t)((row >> 1) & 3) : (uint32_t)((row >> 2) & 1);
+  const uint32_t row_off = (uint32_t)row * (uint32_t)(2 * ob);
+  const uint32_t blk_bytes = 128u * (uint32_t)(2 * ob);
+#pragma unroll
+  for (int g = 0; g < NV / 8; ++g) {
+    const int c0 = c_base + 8 * g;
+    const uint32_t j = (uint32_t)(c0 >> ob_shift), ci = (uint32_t)((c0 & (ob - 1)) >> 3);
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = dn_act(__uint_as_float(r[8 * g + i]) * out_scale + bs[8 * g + i], act);
+    const uint32_t off = j * blk_bytes + row_off + ((ci ^ swz) << 4);
+    if (out_dtype == DN_F16) Vec8<__half>::store((__half*)(stg + off), v);
+    else Vec8<__nv_bfloat16>::store((__nv_bfloat16*)(stg + off), v);
+    if (stg2) {
+      if (out2_dtype == DN_F16) Vec8<__half>::store((__half*)(stg2 + off), v);
+      else Vec8<__nv_bfloat16>::store((__nv_bfloat16*)(stg2 + off), v);
     }
   }
 }
@@ -713,6 +750,8 @@ struct HaloParams {
   int act, accumulate;
   float out_scale;
   unsigned long long* dbg;   // optional per-role cycle counters (dn_tc_set_debug), same slots as igemm_tc_kernel
+  CUtensorMap tmO[4], tmO2[4];   // TMA-store epilogue: output maps (one per phase; [0] alone otherwise), box {ob, 8, 16, 1}
+  int tstore, ob_shift, nblk;    // tstore = 1: staged epilogue + bulk stores; the tile is nblk blocks of (1 << ob_shift) channels
   int nph, cpp;              // channel-stacked output phases (dn_igemm.phase_cout): column block i of a pixel goes to out + phase_off[i]
   long long phase_off[4];
   int step[3];               // gridDim.x as mixed-radix digits (tw, th, n): tiles advance by carries, not by divisions
@@ -739,7 +778,10 @@ __global__ void __launch_bounds__(320, (BN <= 32 || (BN == 64 && CB <= 32)) ? 2 
   const int nb_tiles = p.ring ? p.bstages : 9 * p.kchunks;   // weight tiles in shared memory (ring slots or all of them)
   uint8_t* smem_b = smem;
   uint8_t* smem_a = smem + (size_t)nb_tiles * B_BYTES;
-  uint64_t* full_bar = (uint64_t*)(smem_a + (size_t)stages * halo_bytes);
+  uint8_t* stg = smem_a + (size_t)stages * halo_bytes;                          // TMA-store staging tile(s), 1024-byte aligned
+  const uint32_t stg_bytes = p.tstore ? (uint32_t)p.nblk * (256u << p.ob_shift) : 0u;      // nblk x [128 rows][2 * ob bytes]
+  uint8_t* stg2 = (p.tstore && p.out2) ? stg + stg_bytes : nullptr;
+  uint64_t* full_bar = (uint64_t*)(stg + (size_t)stg_bytes * (stg2 ? 2 : 1));
   uint64_t* empty_bar = full_bar + stages;
   uint64_t* tfull_bar = empty_bar + stages;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -967,6 +1009,31 @@ __global__ void __launch_bounds__(320, (BN <= 32 || (BN == 64 && CB <= 32)) ? 2 
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
       if (p.dbg_flags & 1) {
+      } else if (p.tstore) {
+        // staged epilogue: the previous tile's bulk stores must have read the staging tile before it is overwritten
+        if (et == 0) tma_store_wait_read();
+        asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");
+        uint32_t ra[CH];
+#pragma unroll 1
+        for (int c0 = cbeg; c0 < cbeg + CPT && c0 < n_mma; c0 += CH) {
+          tmem_ldn<CH>(taddr + c0, ra);
+          tmem_ld_wait();
+          epi_stage<CH>(ra, CPT <= 32 ? breg : bias_s + c0, out_scale, act, c0, p.ob_shift, row, stg, out_dtype, stg2, p.out2_dtype);
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");
+        if (et == 0) {
+          const int w0 = (w - wi), h0 = (h - hi);
+          const uint32_t blk = 256u << p.ob_shift;
+          for (int j = 0; j < p.nblk; ++j) {
+            const CUtensorMap* mo = p.nph > 1 ? &p.tmO[j] : &p.tmO[0];
+            const int cj = p.nph > 1 ? 0 : (j << p.ob_shift);
+            tma_store_4d(mo, stg + (size_t)j * blk, cj, w0, h0, n_c);
+            if (stg2) tma_store_4d(p.nph > 1 ? &p.tmO2[j] : &p.tmO2[0], stg2 + (size_t)j * blk, cj, w0, h0, n_c);
+          }
+          tma_store_commit();
+        }
       } else if (p.nph > 1) {
         // channel-stacked phases: chunks of CH columns, each 8-channel group scattered to its phase's pixel
         uint32_t ra[CH];
@@ -1014,6 +1081,7 @@ __global__ void __launch_bounds__(320, (BN <= 32 || (BN == 64 && CB <= 32)) ? 2 
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (p.tstore && et == 0) tma_store_wait_read();      // the staging tile must outlive the last bulk store's reads
   }
   tc_fence_before();
   __syncthreads();
@@ -1335,7 +1403,7 @@ CUtensorMapSwizzle swizzle_of(int cb) {
 }
 
 // 4-D map (C, W, H, N) of an NHWC view, box {cb, wb, hb, nb} (cb = 64 / 32 / 16 channels -> 128B / 64B / 32B swizzle), zero OOB fill
-int make_view_map(CUtensorMap* tm, const dn_view& v, int wb, int hb, int nb, int cb = kChunk) {
+int make_view_map(CUtensorMap* tm, const dn_view& v, int wb, int hb, int nb, int cb = kChunk, bool exact = false) {
   auto enc = get_encode();
   if (!enc) return DN_E_UNSUPPORTED;
   // channel extent: whole box rows where the view says the bytes behind its channels are readable padding (dn_view.c_ext) -- a box
@@ -1343,6 +1411,7 @@ int make_view_map(CUtensorMap* tm, const dn_view& v, int wb, int hb, int nb, int
   int ext = (v.C + cb - 1) / cb * cb;
   const int readable = v.c_ext > v.C ? v.c_ext : v.C;
   if (ext > readable) ext = readable;
+  if (exact) ext = v.C;      // store maps: nothing beyond the view's channels may be written
   cuuint64_t dims[4] = {(cuuint64_t)ext, (cuuint64_t)v.W, (cuuint64_t)v.H, (cuuint64_t)v.N};
   cuuint64_t strides[3] = {(cuuint64_t)v.sW * 2, (cuuint64_t)v.sH * 2, (cuuint64_t)v.sN * 2};
   cuuint32_t box[4] = {(cuuint32_t)cb, (cuuint32_t)wb, (cuuint32_t)hb, (cuuint32_t)nb};
@@ -1491,7 +1560,8 @@ template <int BN, int CB>
 int launch_halo_cb(const HaloParams& P, cudaStream_t st) {
   const size_t b_bytes = (size_t)(P.ring ? P.bstages : 9 * P.kchunks) * BN * 128;
   const size_t kHaloBytes = (size_t)kHaloW * kHaloH * 2 * P.cb;
-  size_t smem = b_bytes + (size_t)P.stages * kHaloBytes + 1024 + (2 * P.stages + 20) * 8 + 16 + 2 * BN * 4;
+  const size_t stg = P.tstore ? (size_t)P.nblk * (256u << P.ob_shift) * (P.out2 ? 2 : 1) : 0;
+  size_t smem = b_bytes + stg + (size_t)P.stages * kHaloBytes + 1024 + (2 * P.stages + 20) * 8 + 16 + 2 * BN * 4;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(igemm_halo_kernel<BN, CB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -1548,7 +1618,37 @@ int dn_igemm_halo(const dn_igemm* p, const int* wt, cudaStream_t st) {
   P.tilesW = (p->out.W + 7) / 8;
   P.tilesH = (p->out.H + 15) / 16;
   P.num_tiles = P.tilesW * P.tilesH * p->out.N;
-  const size_t b_bytes = (size_t)9 * P.kchunks * BN * 128;
+  size_t b_bytes = (size_t)9 * P.kchunks * BN * 128;
+  // TMA-store epilogue (16-bit output, no accumulate, N tile <= 128): staging tile(s) in shared memory
+  // Measured (B200): it pays for the channel-stacked phases of thin transposed convolutions, whose direct stores scatter 16-byte
+  // pieces over four output pixels (upconv0 forward 62 -> 49 us); ordinary tiles (a thread stores its own pixel's channels) are
+  // as fast or faster with direct stores (features.3 148 vs 158 us), so those keep them.  DN_TMA_STORE=0 / 2: never / always.
+  static const int g_tstore = []() { const char* e = getenv("DN_TMA_STORE"); return e ? atoi(e) : 1; }();
+  const bool stacked = p->nphase > 1 && p->phase_cout > 0;
+  size_t stg_total = 0;
+  if ((g_tstore == 2 || (g_tstore == 1 && stacked)) && p->out.dtype != DN_F32 && !p->accumulate && BN <= 128 && view_tma_ok(p->out) && (!p->out2 || ((uintptr_t)p->out2 % 16) == 0)) {
+    const int ob = stacked ? p->phase_cout : (BN >= 64 ? 64 : BN);
+    if (ob == 16 || ob == 32 || ob == 64) {
+      P.tstore = 1;
+      P.ob_shift = ob == 64 ? 6 : ob == 32 ? 5 : 4;
+      P.nblk = ((stacked ? p->cout_pad : (p->cout_pad < BN ? p->cout_pad : BN)) + ob - 1) / ob;
+      stg_total = (size_t)P.nblk * 256 * ob * (p->out2 ? 2 : 1);
+      for (int i = 0; i < (stacked ? p->nphase : 1); ++i) {
+        dn_view v = p->out;
+        v.ptr = (char*)p->out.ptr + (stacked ? p->phase_off[i] : 0) * 2;
+        if (make_view_map(&P.tmO[i], v, 8, 16, 1, ob, true)) return DN_E_ARG;
+        if (p->out2) {
+          v.ptr = (char*)p->out2 + (stacked ? p->phase_off[i] : 0) * 2;
+          v.dtype = p->out2_dtype;
+          if (make_view_map(&P.tmO2[i], v, 8, 16, 1, ob, true)) return DN_E_ARG;
+        }
+      }
+    }
+  }
+  b_bytes += stg_total;        // (the staging area competes with the pipeline stages for shared memory)
+  if (b_bytes + 2 * kHaloBytes > 200 * 1024) {
+    if (stg_total) { P.tstore = 0; b_bytes -= stg_total; stg_total = 0; }
+  }
   if (b_bytes + 2 * kHaloBytes > 200 * 1024) {
     P.ring = 1;
     P.stages = 2;
