@@ -6,7 +6,8 @@ DISPNET_B200_GRAPHS=0 DISPNET_B200_SIDE_STREAM=0 DISPNET_B200_PHASE_STREAMS=0 DN
 tail -1 gpurun_out/r2_launches.log
 DISPNET_B200_GRAPHS=0 DISPNET_B200_SIDE_STREAM=0 DISPNET_B200_PHASE_STREAMS=0 DN_PDL=0 timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 8000 --csv --log-file gpurun_out/r2_launches_tc32_ncu.csv python bench.py --precision tc32 --steps 2 --warmup 3 --minimal > gpurun_out/r2_launches_tc32.log 2>&1
 # 2. full captures of one launch each
-cap() { timeout 300 ncu --set full --import-source on --clock-control none -k regex:$1 -s $2 -c 1 -f -o gpurun_out/r2_full_$3 ${@:4} > gpurun_out/r2_full_$3.log 2>&1; }
+# (the .ncu-rep files are excerpted on the box and deleted: gpurun copies at most 64 MiB back)
+cap() { timeout 300 ncu --set full --import-source on --clock-control none -k regex:$1 -s $2 -c 1 -f -o gpurun_out/r2_full_$3 ${@:4} > gpurun_out/r2_full_$3.log 2>&1; python tools/ncu_excerpt.py gpurun_out/r2_full_$3.ncu-rep > gpurun_out/r2_full_$3.txt 2>/dev/null; rm -f gpurun_out/r2_full_$3.ncu-rep; }
 cap igemm_tc 2 igemm_tc_feat27 python tools/prof_conv.py feat27
 cap igemm_tc 2 igemm_tc_feat10 python tools/prof_conv.py feat10
 cap igemm_halo 2 igemm_halo_iconv0 python tools/prof_conv.py iconv0
@@ -25,7 +26,7 @@ cap smooth_fwd 4 smooth_fwd python tools/prof_loss.py 1
 cap smooth_bwd 4 smooth_bwd python tools/prof_loss.py 1
 cap dl_partial 1 dl_partial python tools/prof_loss.py 1
 cap dl_bwd 1 dl_bwd python tools/prof_loss.py 1
-ls -la gpurun_out/r2_full_*.ncu-rep
+ls -la gpurun_out/r2_full_*.txt
 timeout 200 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2_loss_launches.csv python tools/prof_loss.py 1 > /dev/null 2>&1
 # 3. numbers (never under a profiler)
 timeout 200 python tools/prof_loss.py 20 > gpurun_out/r2_loss_timing.txt 2>&1; cat gpurun_out/r2_loss_timing.txt
