@@ -1515,6 +1515,11 @@ int launch_wgrad(const WgradTcParams& P, int items, cudaStream_t st) {
 
 unsigned long long* g_tc_dbg = nullptr;
 
+// shared memory the halo kernel may spend on resident weights + staging + halo stages: 217 KB leaves room for two 64-channel halo
+// stages next to 144 KB of weights (N = 64 over 128 input channels, N = 128 over 64), i.e. those layers keep their weights resident
+// instead of falling back to the plain kernel / the streamed-weight ring; the rest of the 227 KB holds barriers and the bias tile
+const size_t kHaloBudget = []() { const char* e = getenv("DN_HALO_BUDGET_KB"); return (size_t)(e ? atoi(e) : 217) * 1024; }();
+
 // ---- halo variant: eligibility + launch -------------------------------------------------------------------------
 bool g_halo_enabled = true;
 const bool g_halo_ring = []() { const char* e = getenv("DN_HALO_RING"); return !(e && e[0] == '0'); }();   // A/B knob
@@ -1548,7 +1553,7 @@ bool halo_eligible(const dn_igemm* p, int* wt) {
   // weights stay resident next to >= 2 halo stages when they fit; else they stream through a ring, which measured a gain only
   // for one-chunk problems (features.7 forward 0.099 -> 0.093 ms): N <= 128 tiles with more K are bound by the 128 B/clk
   // shared-memory operand reads of cta_group::1 either way (A 4 KB + B 4 KB per 64-cycle 128x128x16 MMA)
-  if (b_bytes + 2 * kHaloBytes > 200 * 1024 && (BN > 128 || kchunks > 1 || !g_halo_ring || p->ntaps != 9)) return false;
+  if (b_bytes + 2 * kHaloBytes > kHaloBudget && (BN > 128 || kchunks > 1 || !g_halo_ring || p->ntaps != 9)) return false;
   const int H = p->out.H, W = p->out.W;
   if (H != p->in[0].H || W != p->in[0].W) return false;
   // tile = 16 rows x 8 columns: only worth it when little of the tile grid is padding
@@ -1646,17 +1651,17 @@ int dn_igemm_halo(const dn_igemm* p, const int* wt, cudaStream_t st) {
     }
   }
   b_bytes += stg_total;        // (the staging area competes with the pipeline stages for shared memory)
-  if (b_bytes + 2 * kHaloBytes > 200 * 1024) {
+  if (b_bytes + 2 * kHaloBytes > kHaloBudget) {
     if (stg_total) { P.tstore = 0; b_bytes -= stg_total; stg_total = 0; }
   }
-  if (b_bytes + 2 * kHaloBytes > 200 * 1024) {
+  if (b_bytes + 2 * kHaloBytes > kHaloBudget) {
     P.ring = 1;
     P.stages = 2;
     P.bstages = (int)((200 * 1024 - 2 * kHaloBytes) / ((size_t)BN * 128));
     if (P.bstages > 8) P.bstages = 8;
   } else {
     // thin output tiles (BN <= 32): two CTAs per SM when the weights leave room for >= 3 stages in half of the shared memory
-    size_t budget = 200 * 1024;
+    size_t budget = kHaloBudget;
     if ((BN <= 32 || (BN == 64 && P.cb <= 32)) && b_bytes + 3 * kHaloBytes <= 108 * 1024) budget = 108 * 1024;
     P.stages = (int)((budget - b_bytes) / kHaloBytes);
     if (P.stages > (P.cb == kChunk ? 4 : 6)) P.stages = P.cb == kChunk ? 4 : 6;     // thin boxes are latency-bound: more in flight
