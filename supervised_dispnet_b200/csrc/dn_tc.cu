@@ -178,30 +178,6 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// accumulate form (enable-input-d is the constant true predicate: no runtime set-predicate instruction)
-__device__ __forceinline__ void umma_f16_acc(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.eq.u32 p, 1, 1;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(idesc)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -254,18 +230,6 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_b
   return d;
 }
 
-// second copy of an epilogue chunk (16 fp32 values) in another 16-bit dtype
-__device__ __forceinline__ void store_out2(void* base, int dtype, size_t elem_off, const float* v, int c_lo, int c_eff) {
-  if (dtype == DN_F16) {
-    __half* o = (__half*)base + elem_off;
-    if (c_lo < c_eff) Vec8<__half>::store(o, v);
-    if (c_lo + 8 < c_eff) Vec8<__half>::store(o + 8, v + 8);
-  } else {
-    __nv_bfloat16* o = (__nv_bfloat16*)base + elem_off;
-    if (c_lo < c_eff) Vec8<__nv_bfloat16>::store(o, v);
-    if (c_lo + 8 < c_eff) Vec8<__nv_bfloat16>::store(o + 8, v + 8);
-  }
-}
 
 // The MMAs of one (tile, chunk): 9 shifted views x KS K-steps plus the commit(s), as ONE asm block.  The issuing warp's
 // instruction stream paces thin layers (an M=128, N<=32 MMA takes ~50 cycles on the tensor pipe -- tools/ubench_tc.cu), so

@@ -290,3 +290,31 @@ def test_checkpoint_roundtrip_with_reference_format(tmp_path, name):
     assert S.utils.load_checkpoint(d2 / 'dispnet_checkpoint.pth.tar', ours) == 7
     for k, v in ours.state_dict().items():
         assert torch.equal(v, rnet.state_dict()[k]), k
+
+
+def test_channel_pitch_and_readable_extent():
+    """Odd channel counts get whole-TMA-row pitches (16 / 32 / multiples of 64) whose zero padding a gather-convolution may read:
+    dn_view.c_ext = channels readable behind the view inside a pixel record.  Buffers carved from scratch storage are not
+    zero-initialised and declare nothing beyond their channels."""
+    assert [E._pitch(c) for c in (3, 9, 16, 17, 24, 32, 33, 64, 97, 193, 385, 512)] == [16, 16, 16, 32, 24, 32, 64, 64, 128, 256, 448, 512]
+    dev = torch.device('cpu')
+    b = E.Buf(2, 4, 6, 97, torch.float16, dev)
+    assert b.Cp == 128 and b.t.shape == (2, 4, 6, 128) and float(b.t.abs().sum()) == 0.0
+    v = b.view()
+    assert (v.dn().C, v.dn().c_ext, v.dn().sW) == (97, 128, 128)
+    s = v.channels(32, 64)                  # a slice of the concatenation buffer: the neighbouring slice + padding are readable
+    assert (s.dn().C, s.dn().c_ext) == (64, 96)
+    ph = v.phase(1, 0)                      # stride-2 sub-lattice: same pixel records, doubled strides
+    assert (ph.dn().c_ext, ph.dn().sW, ph.dn().H) == (128, 256, 2)
+    scratch = torch.empty(2 * 4 * 6 * 128 * 2, dtype=torch.uint8)
+    sb = E.Buf(2, 4, 6, 97, torch.float16, dev, storage=scratch)
+    assert sb.view().dn().c_ext == 97
+
+
+def test_igemm_struct_has_the_phase_fields():
+    """dn_igemm carries the merged / channel-stacked phase description of a transposed convolution (include/dispnet_b200.h)."""
+    p = L.DnIgemm()
+    p.nphase, p.phase_cout = 4, 16
+    for i in range(4):
+        p.phase_off[i] = 1000 * i
+    assert [int(p.phase_off[i]) for i in range(4)] == [0, 1000, 2000, 3000] and (p.nphase, p.phase_cout) == (4, 16)
