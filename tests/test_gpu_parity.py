@@ -349,6 +349,19 @@ def test_models_tcgen05_vs_oracle(name):
 
 
 @pytest.mark.parametrize('precision', ['tc32', 'mixed'])
+def test_disp_res_50_at_configs3_image_size(precision):
+    """Disp_res_50 (train mode) at the image size of BASELINE configs[3] (NYU 256x320, batch 4) against the oracle.
+      tc32 : measured 1.2e-4 on the outputs (north star 1e-3), BatchNorm running statistics 8e-5; asserted 5e-4.
+      mixed: measured 8.5e-3 -- 53 BatchNorm layers deep, the fp16 throughput mode does NOT meet 1e-3 on this network and is
+             asserted at the documented 2e-2; the parity mode for Disp_res_50 is tc32."""
+    r = P().res50_case(precision, B=4, H=256, W=320)
+    if precision == 'tc32':
+        assert r['out'] < 5e-4 and r['running'] < 5e-4, r
+    else:
+        assert r['out'] < 2e-2, r
+
+
+@pytest.mark.parametrize('precision', ['tc32', 'mixed'])
 def test_config2_step_loss_and_disparity_full_size(precision):
     """BASELINE configs[1] at reduced batch: Disp_vgg_BN (train mode) + l1_loss (+0*smooth_loss, train.py:420-522) on
     4x3x128x416 against the oracle.
