@@ -1,17 +1,24 @@
 // tcgen05 / TMA / TMEM implicit-GEMM convolution kernels for sm_100a (backend 1 of dn_igemm_run / dn_wgrad_run).
 //
 //   igemm_tc_kernel : out[pixel][co] = sum_tap sum_ci in[pixel + tap][ci] * w[tap][co][ci]
-//       A (activations) is fetched by 4-D TMA boxes {64 ch, wb, hb, nb} straight from the NHWC view -- the tap shift is a
-//       coordinate offset and zero padding is TMA out-of-bounds fill, so there is no im2col buffer; B (packed weights) by 3-D
-//       TMA; both land in 128B-swizzled shared memory and feed tcgen05.mma (M=128, N<=256, K=16) with fp32 accumulators in
-//       TMEM.  Persistent CTAs (one per SM), 3 warp roles (TMA producer / MMA issuer / 4 epilogue warps), a multi-stage
-//       smem ring and two TMEM accumulator stages so the epilogue of tile i overlaps the main loop of tile i+1.
+//       A (activations) is fetched by 4-D TMA boxes {cb ch, wb, hb, nb} straight from the NHWC view -- the tap shift is a
+//       coordinate offset and zero padding is TMA out-of-bounds fill, so there is no im2col buffer; cb = 64 / 32 / 16 channels
+//       per row (128B / 64B / 32B swizzle) so that thin tensors are fetched as whole rows.  B (packed weights) by 3-D TMA.
+//       tcgen05.mma (M=128, N<=256, K=16) with fp32 accumulators in TMEM.  Persistent CTAs, ten warps: TMA producer, MMA
+//       issuer (one asm block per pipeline stage, warp-uniform), eight epilogue warps (two per TMEM lane quarter); a multi-stage
+//       smem ring and two TMEM accumulator stages so the epilogue of tile i overlaps the main loop of tile i+1.  The output
+//       phases of a transposed convolution run as one launch (dn_igemm.nphase).
+//   igemm_halo_kernel : the same for 3x3 stride-1 layers with many pixels: one (16+2) x 16-pixel halo box per 64-channel chunk,
+//       the nine taps are nine shifted UMMA descriptors over it, weights resident in shared memory; two CTAs per SM for thin
+//       tiles; channel-stacked output phases of thin transposed convolutions with a TMA-store epilogue.
 //   wgrad_tc_kernel : dw[tap][cp][cq] += sum_pixel dy[pixel][cp] * x[pixel + tap][cq]
 //       both operands are "MN-major" (the reduction index = pixel is the row index of the TMA box), split-K over pixel
-//       tiles across CTAs, fp32 partial sums reduced with vector red.global.add.
+//       tiles across CTAs, fp32 partial sums reduced with vector red.global.add; halo mode (one x box for nine taps) and an
+//       M-stacked mode for thin dy (three column-shifted dy copies fill the MMA M dimension).
 //
-// Forward nn.Conv2d (stride 1), the four output phases of nn.ConvTranspose2d, and the data gradients of both run on
-// igemm_tc_kernel with different tap tables / views; weight gradients of both on wgrad_tc_kernel.
+// Forward nn.Conv2d (stride 1), the output phases of nn.ConvTranspose2d, and the data gradients of both run on the igemm
+// kernels with different tap tables / views; weight gradients of both on wgrad_tc_kernel.  What bounds
+// these kernels was measured with tools/ubench_tc.cu and is written up in DESIGN.md 4.1.
 #include "dn_common.cuh"
 #include <cuda.h>
 #include <cudaTypedefs.h>

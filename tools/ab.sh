@@ -1,4 +1,7 @@
 # A/B of two builds of the library on full-size single layers (one process per case): tools/ab.sh case...
+# libdispnet_b200_base.so = the build to compare against, e.g.
+#   git archive <commit> supervised_dispnet_b200/csrc include | tar -x -C /tmp/base && make -C /tmp/base/supervised_dispnet_b200/csrc \
+#     && cp /tmp/base/supervised_dispnet_b200/libdispnet_b200.so supervised_dispnet_b200/libdispnet_b200_base.so
 for lib in libdispnet_b200_base.so libdispnet_b200.so; do
   echo "== $lib"
   for c in "$@"; do
