@@ -281,19 +281,20 @@ __device__ __forceinline__ void halo_issue(uint32_t d_tmem, uint64_t ad, uint64_
   else DN_HALO_BLOCK(DN_HTAP4);
 }
 
-// One pipeline stage of the plain kernel: KS MMAs on the stage's A / B tiles, release of the stage, optional "accumulator
-// complete" commit.  %0 d_tmem, %1 / %2 descriptors, %3 idesc, %4 accumulate flag of the first MMA, %5 empty barrier,
-// %6 tmem-full barrier, %7 "last stage of the tile" flag
+// One (tap, chunk) of the plain kernel: KS MMAs on its A / B tiles, release of the stage, optional "accumulator complete"
+// commit.  %0 d_tmem, %1 / %2 descriptors, %3 idesc, %4 accumulate flag of the first MMA, %5 empty barrier, %6 tmem-full
+// barrier, %7 flags: bit 0 = last MMAs of the tile (commit tmem-full), bit 1 = more taps of the same stage follow (no release)
 #define DN_STEP2 "add.u64 a, a, 2;\nadd.u64 b, b, 2;\n@E tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %3, TR;\n"
 #define DN_STAGE_BLOCK(STEPS)                                                                                       \
   asm volatile(                                                                                                     \
-      "{\n.reg .pred E, A, TR, L;\n.reg .b64 a, b;\n"                                                               \
+      "{\n.reg .pred E, A, TR, L;\n.reg .b64 a, b;\n.reg .b32 fl;\n"                                               \
       "elect.sync _|E, 0xffffffff;\n"                                                                               \
       "setp.ne.u32 A, %4, 0;\nsetp.eq.u32 TR, 1, 1;\n"                                                              \
       "mov.b64 a, %1;\nmov.b64 b, %2;\n"                                                                            \
       "@E tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %3, A;\n" STEPS                                            \
-      "@E tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%5];\n"                            \
-      "setp.ne.u32 L, %7, 0;\nand.pred L, L, E;\n"                                                                  \
+      "and.b32 fl, %7, 2;\nsetp.eq.u32 L, fl, 0;\nand.pred L, L, E;\n"                                             \
+      "@L tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%5];\n"                            \
+      "and.b32 fl, %7, 1;\nsetp.ne.u32 L, fl, 0;\nand.pred L, L, E;\n"                                             \
       "@L tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%6];\n"                            \
       "}\n" ::"r"(d_tmem), "l"(ad), "l"(bd), "r"(idesc), "r"(acc0), "r"(empty_bar), "r"(tfull_bar), "r"(last)       \
       : "memory")
@@ -455,6 +456,8 @@ struct IgemmTcParams {
   long long phase_off[4];
   int step[5];        // gridDim.x as mixed-radix digits (nt, tw, th, tn, ph): tiles advance by carries, not by divisions
   int stages;
+  int tps;            // taps per pipeline stage (thin one-chunk problems with many taps: a 7x7 / 5x5 kernel, the 16 taps of a
+                      // transposed-convolution data gradient): one barrier round trip per tps taps instead of one per tap
   int n_mma;          // MMA N actually issued (multiple of 16, <= BN)
   int c_eff;          // output channels the epilogue may write (out.C, or rounded up to 8 when padding may be overwritten)
   uint32_t idesc;
@@ -494,7 +497,8 @@ __global__ void __launch_bounds__(320, 1) igemm_tc_kernel(const __grid_constant_
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t A_BYTES = (uint32_t)(kRows * 2 * p.cb);
   constexpr uint32_t B_BYTES = BN * 128;
-  const uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  const uint32_t SUB_BYTES = A_BYTES + B_BYTES;                 // one (tap, chunk): A tile + B tile
+  const uint32_t STAGE_BYTES = (uint32_t)p.tps * SUB_BYTES;
   const uint32_t a_layout = (uint32_t)thin_layout(p.cb), a_sbo = (uint32_t)(16 * p.cb);     // 8 rows of 2 * cb bytes
   constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
   constexpr int EW = 8;                               // epilogue warps: two per TMEM lane quarter, half of the columns each
@@ -542,6 +546,23 @@ __global__ void __launch_bounds__(320, 1) igemm_tc_kernel(const __grid_constant_
       const int nt = tp.nt;
       const int w0 = tp.tw * p.wb, h0 = tp.th * p.hb, n0 = tp.tn * p.nb;
       const int tbeg = tp.ph * p.tph;
+      if (p.tps > 1) {      // (one chunk) several taps share a stage
+        for (int t = tbeg; t < tbeg + p.tph; t += p.tps) {
+          const int nsub = tbeg + p.tph - t < p.tps ? tbeg + p.tph - t : p.tps;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (elect_one()) {
+            uint8_t* sa = smem + (size_t)stage * STAGE_BYTES;
+            mbar_expect_tx(&full_bar[stage], (uint32_t)nsub * SUB_BYTES);
+            for (int j = 0; j < nsub; ++j) {
+              const TcTap tap = p.taps[t + j];
+              tma_load_4d(sa + (size_t)j * SUB_BYTES, &p.tmA[tap.src], &full_bar[stage], 0, w0 + tap.dw, h0 + tap.dh, n0);
+              tma_load_3d(sa + (size_t)j * SUB_BYTES + A_BYTES, &p.tmB, &full_bar[stage], 0, nt * BN, tap.wt);
+            }
+          }
+          __syncwarp();
+          if (++stage == stages) { stage = 0; phase ^= 1; }
+        }
+      } else
       for (int t = tbeg; t < tbeg + p.tph; ++t) {
         const TcTap tap = p.taps[t];
         for (int kc = 0; kc < p.kchunks; ++kc) {
@@ -585,6 +606,23 @@ __global__ void __launch_bounds__(320, 1) igemm_tc_kernel(const __grid_constant_
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
       int kc = 0;
+      if (p.tps > 1) {      // (one chunk) several taps per stage: one wait and one release per stage
+        const uint64_t sub_inc = (uint64_t)(SUB_BYTES >> 4);
+        for (int t = 0; t < p.tph; t += p.tps) {
+          const int nsub = p.tph - t < p.tps ? p.tph - t : p.tps;
+          t0 = p.dbg ? clock64() : 0;
+          mbar_wait(&full_bar[stage], phase);
+          if (p.dbg) dbg_full += clock64() - t0;
+          tc_fence_after();
+          const uint32_t eb = smem_u32(&empty_bar[stage]), tb = smem_u32(&tfull_bar[acc]);
+          for (int j = 0; j < nsub; ++j) {
+            const uint32_t flags = (j + 1 < nsub ? 2u : 0u) | ((t + j == p.tph - 1) ? 1u : 0u);
+            stage_issue(last_ks, d_tmem, ad + (uint64_t)j * sub_inc, bd + (uint64_t)j * sub_inc, idesc, (t + j) == 0 ? 0u : 1u, eb, tb, flags);
+          }
+          ad += stage_inc; bd += stage_inc;
+          if (++stage == stages) { stage = 0; phase ^= 1; ad = ad_base; bd = bd_base; }
+        }
+      } else
       for (int it = 0; it <= k_iters_m1; ++it) {
         t0 = p.dbg ? clock64() : 0;
         mbar_wait(&full_bar[stage], phase);
@@ -1449,7 +1487,7 @@ int pick_bn(int cout_pad) {
 
 template <int BN>
 int launch_igemm(const IgemmTcParams& P, cudaStream_t st) {
-  const uint32_t STAGE_BYTES = kRows * 2 * P.cb + BN * 128;
+  const uint32_t STAGE_BYTES = (uint32_t)P.tps * (kRows * 2 * P.cb + BN * 128);
   int stages = P.stages;
   size_t smem = (size_t)stages * STAGE_BYTES + 1024 + (2 * stages + 4) * 8 + 16 + 2 * BN * 4;
   static bool attr_set = false;
@@ -1780,7 +1818,12 @@ int dn_igemm_tc(const dn_igemm* p, cudaStream_t st) {
     for (int i = 0; i < 4; ++i) { P.step[i] = g % radix[i]; g /= radix[i]; }
     P.step[4] = g;
   }
-  const uint32_t stage_bytes = kRows * 2 * P.cb + BN * 128;
+  // thin one-chunk problems with many taps: up to four taps per stage
+  static const bool g_tps = []() { const char* e = getenv("DN_TAPS_PER_STAGE"); return !(e && e[0] == '0'); }();
+  P.tps = 1;
+  if (g_tps && P.kchunks == 1 && P.cb <= 32 && P.tph >= 4) P.tps = 4;
+  while (P.tps > 1 && (200 * 1024) / ((uint32_t)P.tps * (kRows * 2 * P.cb + BN * 128)) < 3) --P.tps;      // keep >= 3 stages
+  const uint32_t stage_bytes = (uint32_t)P.tps * (kRows * 2 * P.cb + BN * 128);
   P.stages = (int)((200 * 1024) / stage_bytes);
   if (P.stages > 8) P.stages = 8;
   P.n_mma = p->cout_pad < BN ? p->cout_pad : BN;
