@@ -253,7 +253,9 @@ int dn_head_conv_bwd(const dn_view* x, const float* w, const dn_view* dz, const 
 int dn_head_fwd(const dn_view* z, float alpha, float beta, float* disp, const dn_view* up, int up_mode,
                 void* stream);
 /* the same with a second up-sampled copy `up2` (same geometry, another 16-bit dtype: the weight-gradient operand of the next
- * iconv) written in the same pass when up_mode == 0 */
+ * iconv) written in the same pass when up_mode == 0.  up_mode bit 4 (value 16): `up` / `up2` are the LAST channel slice of their
+ * buffer and what follows them inside the pixel record is zero padding (dn_view.c_ext >= 16) -- the slot is then written as whole
+ * 32-byte sectors (value + zeros) */
 int dn_head_fwd2(const dn_view* z, float alpha, float beta, float* disp, const dn_view* up, const dn_view* up2, int up_mode,
                  void* stream);
 /* dz = (gscale*gdisp + upsample^T(dup)) * alpha*s*(1-s), s = sigmoid(z) recomputed from the saved conv output.

@@ -1925,7 +1925,20 @@ DN_EXPORT int dn_head_fwd(const dn_view* z, float alpha, float beta, float* disp
 }
 
 // disparity + nearest x2 up-sampled copies (activation dtype and, optionally, its gradient-dtype twin) in one pass
-__global__ void head_fwd_nearest_kernel(dn_view z, float alpha, float beta, float* __restrict__ disp, dn_view up, dn_view up2, int has_up2) {
+// 16-bit value followed by 15 zeros as one 32-byte (full DRAM sector) store
+__device__ __forceinline__ void st_sector16(void* p, int dtype, float v) {
+  uint4 a = make_uint4(0, 0, 0, 0);
+  if (dtype == DN_F16) a.x = (uint32_t)__half_as_ushort(__float2half_rn(v));
+  else a.x = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v));
+  reinterpret_cast<uint4*>(p)[0] = a;
+  reinterpret_cast<uint4*>(p)[1] = make_uint4(0, 0, 0, 0);
+}
+
+// `sector`: the up-sampled slot is the LAST channel slice of its concatenation buffer and at least 15 zero padding channels follow
+// it inside the 32-byte aligned pixel record -- the slot is then written as a whole 32-byte sector (value + zeros) instead of a
+// 2-byte piece of one, which spares DRAM the read-modify-write of 1.7 M partially written sectors
+__global__ void head_fwd_nearest_kernel(dn_view z, float alpha, float beta, float* __restrict__ disp, dn_view up, dn_view up2, int has_up2,
+                                        int sector) {
   dn_pdl_trigger();
   dn_pdl_wait();
   long long total = (long long)z.N * z.H * z.W;
@@ -1941,8 +1954,13 @@ __global__ void head_fwd_nearest_kernel(dn_view z, float alpha, float beta, floa
       for (int b = 0; b < 2; ++b) {
         const int y = 2 * h + a, x = 2 * w + b;
         if (y < up.H && x < up.W) {
-          dn_st(up.ptr, up.dtype, dn_off(up, n, y, x), v);
-          if (has_up2) dn_st(up2.ptr, up2.dtype, dn_off(up2, n, y, x), v);
+          if (sector) {
+            st_sector16((char*)up.ptr + dn_off(up, n, y, x) * 2, up.dtype, v);
+            if (has_up2) st_sector16((char*)up2.ptr + dn_off(up2, n, y, x) * 2, up2.dtype, v);
+          } else {
+            dn_st(up.ptr, up.dtype, dn_off(up, n, y, x), v);
+            if (has_up2) dn_st(up2.ptr, up2.dtype, dn_off(up2, n, y, x), v);
+          }
         }
       }
   }
@@ -1952,11 +1970,20 @@ __global__ void head_fwd_nearest_kernel(dn_view z, float alpha, float beta, floa
 DN_EXPORT int dn_head_fwd2(const dn_view* z, float alpha, float beta, float* disp, const dn_view* up, const dn_view* up2, int up_mode,
                            void* stream) {
   if (!z || !disp) return DN_E_ARG;
+  // up_mode bit 4 (16): everything behind `up` (and `up2`) inside the pixel record is zero padding that may be rewritten with zeros
+  const int tail_is_pad = up_mode & 16;
+  up_mode &= 15;
   if (up && up_mode == 0 && up->H <= 2 * z->H && up->W <= 2 * z->W && up->N == z->N &&
       (!up2 || (up2->H == up->H && up2->W == up->W && up2->N == up->N))) {
     long long total = (long long)z->N * z->H * z->W;
+    static const bool g_sector = []() { const char* e = getenv("DN_HEAD_SECTOR"); return !(e && e[0] == '0'); }();
+    auto sector_ok = [](const dn_view* v) {
+      return v->dtype != DN_F32 && v->C == 1 && v->c_ext >= 16 && ((uintptr_t)v->ptr % 32) == 0 && (v->sW % 16) == 0 && (v->sH % 16) == 0 &&
+             (v->sN % 16) == 0;
+    };
+    const int sector = (g_sector && tail_is_pad && sector_ok(up) && (!up2 || sector_ok(up2))) ? 1 : 0;
     dn_launch(head_fwd_nearest_kernel, dim3(ew_blocks(total)), dim3(256), 0, dn_stream(stream), *z, alpha, beta, disp, *up, up2 ? *up2 : *up,
-              up2 != nullptr);
+              up2 != nullptr, sector);
     DN_CHECK_LAUNCH();
     return 0;
   }

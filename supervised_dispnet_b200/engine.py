@@ -883,8 +883,11 @@ class HeadOp(Op):
 
     def fwd(self, plan):
         out = plan.outputs[self.idx]
+        # (bit 4: the slot is the last slice of its concatenation buffer -- what follows it in the pixel record is zero padding,
+        # so the kernel may write whole 32-byte sectors)
+        tail_pad = 16 if (self.up is not None and self.up.c0 + self.up.C == self.up.buf.C and self.up.buf.readable_pad) else 0
         L.call('dn_head_fwd2', self.z.ref(), self.alpha, self.beta, L.ptr(out), self.up.ref() if self.up else None,
-               self.up_shadow.ref() if self.up_shadow is not None else None, self.up_mode, plan.stream)
+               self.up_shadow.ref() if self.up_shadow is not None else None, self.up_mode | tail_pad, plan.stream)
 
     def plan_bwd(self, plan):
         g = plan.prec.grad
