@@ -66,7 +66,7 @@ def test_sass_has_tcgen05_and_tma():
     so = os.path.join(ROOT, 'supervised_dispnet_b200', 'libdispnet_b200.so')
     sass = subprocess.run(['cuobjdump', '-sass', so], capture_output=True, text=True).stdout
     assert 'sm_100a' in sass or 'SM100' in sass.upper()
-    for mnem in ('UTCHMMA', 'UTMALDG', 'LDTM', 'UTCBAR'):
+    for mnem in ('UTCHMMA', 'UTMALDG', 'LDTM', 'UTCBAR', 'UTMASTG.4D', 'UTMALDG.5D'):      # (TMA-store epilogue, 5-D operand maps)
         assert mnem in sass, mnem
 
 
